@@ -1,0 +1,77 @@
+"""ctypes binding of the C-ABI library (include/firecode_b200.h). Fails loudly; no fallback."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from .errors import FirecodeB200Error
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libfirecode_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+c_dp = C.POINTER(C.c_double)
+c_fp = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u8p = C.POINTER(C.c_uint8)
+VP = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/firecode_b200.h declares
+SIGNATURES = {
+    "fc_last_error": (C.c_char_p, []),
+    "fc_version": (C.c_int, []),
+    "fc_device_count": (C.c_int, []),
+    "fc_clash_tile_poses": (C.c_int, [C.c_int]),
+    "fc_clash_screen_dev": (C.c_int, [VP, C.c_int, C.c_int, VP, C.c_int, C.c_int, VP, C.c_int64, VP,
+                                      C.c_int64, C.c_double, C.c_int, C.c_int, VP, VP, VP, VP, VP,
+                                      C.c_int64, C.c_int64, VP]),
+    "fc_clash_batch": (C.c_int, [VP, C.c_int, C.c_int, VP, C.c_int, C.c_int, VP, C.c_int64, VP,
+                                 C.c_int64, C.c_double, C.c_int, C.c_int, VP, VP, VP, VP, VP,
+                                 C.c_int64]),
+    "fc_clash_geometry": (C.c_int, [C.c_int, c_i32p]),
+    "fc_clash_timing": (C.c_int, [C.c_int, c_dp, c_i64p]),
+    "fc_pack_mask_dev": (C.c_int, [VP, C.c_int64, VP, VP]),
+    "fc_probe_fp32_peak": (C.c_int, [c_dp, c_dp, VP]),
+}
+
+
+def load(require_device: bool = False):
+    """Return the loaded library (ctypes.CDLL). Raises FirecodeB200Error if it cannot be used."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.isfile(LIB_PATH):
+                raise FirecodeB200Error(
+                    f"CUDA library not built: {LIB_PATH} is missing. Run "
+                    "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C "
+                    "firecode_b200/csrc`). firecode_b200 has no CPU fallback."
+                )
+            try:
+                lib = C.CDLL(LIB_PATH)
+            except OSError as exc:  # pragma: no cover
+                raise FirecodeB200Error(f"cannot load {LIB_PATH}: {exc}") from exc
+            for name, (res, args) in SIGNATURES.items():
+                try:
+                    fn = getattr(lib, name)
+                except AttributeError as exc:
+                    raise FirecodeB200Error(f"{LIB_PATH} does not export {name}") from exc
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    if require_device and _lib.fc_device_count() <= 0:
+        raise FirecodeB200Error(
+            "no CUDA device visible: firecode_b200 runs only on a B200 (sm_100a) and has no CPU "
+            f"fallback ({_lib.fc_last_error().decode()})"
+        )
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().fc_last_error().decode(errors="replace")
+        raise FirecodeB200Error(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,516 @@
+// firecode_b200 -- compenetration (clash) screen for sm_100a.
+//
+// Replaces the per-pose call `compenetration_check(pose, ids=..., thresh=...)`
+// (/root/reference/firecode/utils.py:507-575, called at embeds.py:139, 559, 718) by a batched
+// screen over (conformer_a, conformer_b, rigid transform) poses.
+//
+// FP32 pass (clash_f32_kernel): the squared distance is evaluated in Gram form
+//      |a - b'|^2 = (|a|^2 - 2 a.b') + |b'|^2
+// so one atom pair costs 3 FMA lanes instead of the 6 FMA-pipe slots of the difference form.
+//   * thread (pose_local, chunk) owns TB atoms of the transformed fragment B as TB/2 packed
+//     f32x2 register pairs (x, y, z) and TB running minima;
+//   * fragment A sits in shared memory in a duplicated broadcast layout
+//     {-2ax,-2ax,-2ay,-2ay | -2az,-2az,|a|^2,|a|^2} so every LDS.128 is a warp-wide broadcast and
+//     its halves are ready-made FFMA2 operands;
+//   * per A atom and B pair: 3 FFMA2; per two A atoms and B pair: 2 FMNMX3 (ALU pipe).
+// The FP32 result is trusted only outside a rigorous rounding band around thresh^2; poses inside
+// the band (and every pose when max_clashes > 0 and a clash is possible) go to the FP64 recheck
+// kernel, which restates the reference arithmetic (f64 transform, sqrt of the summed squares,
+// `<` / `<=` compare, clash count).  Poses whose FP64 minimum distance lies within FC_NEAR_EPS of
+// the threshold are flagged and listed.
+#include "fc_common.cuh"
+
+namespace fc {
+
+struct ClashGeom {
+    int tb;       // B atoms per thread (even)
+    int chunks;   // threads per pose
+    int poses;    // poses per tile
+    int threads;  // block size (multiple of 32)
+};
+
+static ClashGeom choose_geom(int n_b) {
+    static const int kTB[] = {16, 14, 12, 10, 8, 6, 4, 2};
+    ClashGeom best{0, 0, 0, 0};
+    long best_pad = 1L << 60;
+    for (int tb : kTB) {
+        int chunks = (n_b + tb - 1) / tb;
+        if (chunks > 512) continue;
+        long pad = (long)chunks * tb;
+        if (pad < best_pad) {
+            best_pad = pad;
+            best.tb = tb;
+            best.chunks = chunks;
+        }
+    }
+    if (best.tb == 0) return best;
+    // poses per tile: keep the block <= 512 threads and waste as few lanes as possible
+    int c = best.chunks;
+    int p_hi = 512 / c;
+    if (p_hi < 1) p_hi = 1;
+    int p_lo = (p_hi + 1) / 2;
+    double best_u = -1.0;
+    for (int p = p_hi; p >= p_lo; --p) {
+        int used = p * c;
+        int threads = (used + 31) / 32 * 32;
+        double u = (double)used / threads;
+        if (u > best_u + 1e-9) {
+            best_u = u;
+            best.poses = p;
+            best.threads = threads;
+        }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// table preparation: f64 ensembles -> FP32 layouts used by the screen
+// ---------------------------------------------------------------------------------------------
+// a_tab: [conf][n_a_pad][2] float4  (n_a_pad even; padding atoms: a' = 0, |a|^2 = 1e30)
+// b_tab: [conf][n_b_pad]    float4  {x, y, z, 0}  (padding atoms carry w = 1e30)
+// rad  : [conf] max |x| over the conformer (f32, rounded up)
+__global__ void clash_prep_kernel(const double* __restrict__ coords, int n_conf, int n_atoms,
+                                  int n_pad, int as_a, float4* __restrict__ tab,
+                                  float* __restrict__ rad) {
+    int conf = blockIdx.x;
+    const double* src = coords + (size_t)conf * n_atoms * 3;
+    float r2max = 0.f;
+    for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        if (i < n_atoms) {
+            float x = (float)src[3 * i], y = (float)src[3 * i + 1], z = (float)src[3 * i + 2];
+            float n2 = fmaf(x, x, fmaf(y, y, z * z));
+            r2max = fmaxf(r2max, n2);
+            if (as_a) {
+                tab[((size_t)conf * n_pad + i) * 2] = make_float4(-2.f * x, -2.f * x, -2.f * y, -2.f * y);
+                tab[((size_t)conf * n_pad + i) * 2 + 1] = make_float4(-2.f * z, -2.f * z, n2, n2);
+            } else {
+                tab[(size_t)conf * n_pad + i] = make_float4(x, y, z, 0.f);
+            }
+        } else {
+            if (as_a) {
+                tab[((size_t)conf * n_pad + i) * 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                tab[((size_t)conf * n_pad + i) * 2 + 1] = make_float4(0.f, 0.f, 1e30f, 1e30f);
+            } else {
+                tab[(size_t)conf * n_pad + i] = make_float4(0.f, 0.f, 0.f, 1e30f);
+            }
+        }
+    }
+    __shared__ float s_r[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r2max = fmaxf(r2max, __shfl_xor_sync(0xffffffffu, r2max, o));
+    if ((threadIdx.x & 31) == 0) s_r[threadIdx.x >> 5] = r2max;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = 0.f;
+        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) m = fmaxf(m, s_r[w]);
+        rad[conf] = sqrtf(m) * 1.000001f + 1e-6f;
+    }
+}
+
+struct UncEntry {  // a pose the FP32 pass could not decide
+    long long pose;
+    int conf_a, conf_b;
+};
+
+struct ClashArgs {
+    const float4* a_tab;
+    const float* a_rad;
+    const float4* b_tab;
+    const float* b_rad;
+    const double* xf;
+    const int4* tiles;  // may be null: implicit single-group tiling
+    long long n_tiles;
+    long long n_poses;
+    int n_a_pad, n_b_pad, chunks, poses;
+    float thr2;
+    int count_mode;  // max_clashes > 0: FP32 pass may only prove "no pair can clash"
+    uint8_t* status;
+    float* min_dist;
+    int* unc_count;
+    UncEntry* unc_list;
+};
+
+template <int TB>
+__global__ void __launch_bounds__(512, 1) clash_f32_kernel(ClashArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ulonglong2* sA = reinterpret_cast<ulonglong2*>(smem_raw);                  // n_a_pad * 2
+    float4* sB = reinterpret_cast<float4*>(smem_raw + (size_t)p.n_a_pad * 32);  // n_b_pad
+    int* sMin = reinterpret_cast<int*>(smem_raw + (size_t)p.n_a_pad * 32 + (size_t)p.n_b_pad * 16);
+
+    const int tid = threadIdx.x;
+    const int pose_local = tid / p.chunks;
+    const int chunk = tid - pose_local * p.chunks;
+    const bool lane_used = pose_local < p.poses;
+
+    int cur_a = -1, cur_b = -1;
+    for (int i = tid; i < p.poses; i += blockDim.x) sMin[i] = 0x7fffffff;
+
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        int conf_a = 0, conf_b = 0, count;
+        long long first;
+        if (p.tiles) {
+            int4 t = p.tiles[tile];
+            conf_a = t.x;
+            conf_b = t.y;
+            first = t.z;
+            count = t.w;
+        } else {
+            first = tile * p.poses;
+            long long left = p.n_poses - first;
+            count = left < p.poses ? (int)left : p.poses;
+        }
+        if (conf_a != cur_a || conf_b != cur_b) {
+            __syncthreads();  // everybody is done with the previous tables
+            if (conf_a != cur_a) {
+                const ulonglong2* src =
+                    reinterpret_cast<const ulonglong2*>(p.a_tab) + (size_t)conf_a * p.n_a_pad * 2;
+                for (int i = tid; i < p.n_a_pad * 2; i += blockDim.x) sA[i] = src[i];
+            }
+            if (conf_b != cur_b) {
+                const float4* src = p.b_tab + (size_t)conf_b * p.n_b_pad;
+                for (int i = tid; i < p.n_b_pad; i += blockDim.x) sB[i] = src[i];
+            }
+            cur_a = conf_a;
+            cur_b = conf_b;
+        }
+        __syncthreads();  // tables + sMin reset visible
+
+        const bool active = lane_used && pose_local < count;
+        const long long pose = first + pose_local;
+        float lane_min = 3.0e38f;
+        float tnorm = 0.f;
+        if (active) {
+            // ---- transform this thread's TB atoms of fragment B --------------------------------
+            const double* x = p.xf + pose * 12;
+            float r[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) r[k] = (float)__ldg(x + k);
+            tnorm = sqrtf(fmaf(r[9], r[9], fmaf(r[10], r[10], r[11] * r[11])));
+
+            f32x2 bx[TB / 2], by[TB / 2], bz[TB / 2];
+            float nb[TB], m[TB];
+#pragma unroll
+            for (int q = 0; q < TB / 2; ++q) {
+                float4 b0 = sB[chunk * TB + 2 * q];
+                float4 b1 = sB[chunk * TB + 2 * q + 1];
+                float x0 = fmaf(r[0], b0.x, fmaf(r[1], b0.y, fmaf(r[2], b0.z, r[9])));
+                float y0 = fmaf(r[3], b0.x, fmaf(r[4], b0.y, fmaf(r[5], b0.z, r[10])));
+                float z0 = fmaf(r[6], b0.x, fmaf(r[7], b0.y, fmaf(r[8], b0.z, r[11])));
+                float x1 = fmaf(r[0], b1.x, fmaf(r[1], b1.y, fmaf(r[2], b1.z, r[9])));
+                float y1 = fmaf(r[3], b1.x, fmaf(r[4], b1.y, fmaf(r[5], b1.z, r[10])));
+                float z1 = fmaf(r[6], b1.x, fmaf(r[7], b1.y, fmaf(r[8], b1.z, r[11])));
+                // padding atoms: keep them at the origin and push |b|^2 to 1e30
+                nb[2 * q] = fmaf(x0, x0, fmaf(y0, y0, z0 * z0)) + b0.w;
+                nb[2 * q + 1] = fmaf(x1, x1, fmaf(y1, y1, z1 * z1)) + b1.w;
+                bx[q] = pack2(x0, x1);
+                by[q] = pack2(y0, y1);
+                bz[q] = pack2(z0, z1);
+                m[2 * q] = 3.0e38f;
+                m[2 * q + 1] = 3.0e38f;
+            }
+
+            // ---- all atom pairs: A broadcast from shared memory, two A atoms per step --------
+            const int n_a_pad = p.n_a_pad;
+#pragma unroll 2
+            for (int i = 0; i < n_a_pad; i += 2) {
+                ulonglong2 u0 = sA[2 * i], u1 = sA[2 * i + 1];
+                ulonglong2 v0 = sA[2 * i + 2], v1 = sA[2 * i + 3];
+#pragma unroll
+                for (int q = 0; q < TB / 2; ++q) {
+                    f32x2 e0 = fma2(u0.x, bx[q], fma2(u0.y, by[q], fma2(u1.x, bz[q], u1.y)));
+                    f32x2 e1 = fma2(v0.x, bx[q], fma2(v0.y, by[q], fma2(v1.x, bz[q], v1.y)));
+                    float e0l, e0h, e1l, e1h;
+                    unpack2(e0, e0l, e0h);
+                    unpack2(e1, e1l, e1h);
+                    m[2 * q] = min3(m[2 * q], e0l, e1l);
+                    m[2 * q + 1] = min3(m[2 * q + 1], e0h, e1h);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < TB; ++j) lane_min = fminf(lane_min, m[j] + nb[j]);
+            atomicMin(&sMin[pose_local], float_key(lane_min));
+        }
+        __syncthreads();
+        if (active && chunk == 0) {
+            float d2 = key_float(sMin[pose_local]);
+            sMin[pose_local] = 0x7fffffff;  // reset for the next tile (ordered by the barrier above)
+            // rounding band of the Gram-form FP32 evaluation (DESIGN.md "clash band")
+            float ext = p.a_rad[conf_a] + p.b_rad[conf_b] + tnorm;
+            float band = fmaf(1.5e-6f * ext, ext, 1e-6f);
+            uint8_t st;
+            bool uncertain;
+            if (p.count_mode) {
+                uncertain = !(d2 > p.thr2 + band);
+                st = FC_STATUS_PASS;
+            } else {
+                uncertain = fabsf(d2 - p.thr2) <= band;
+                st = d2 > p.thr2 ? FC_STATUS_PASS : 0;
+            }
+            if (uncertain) {
+                int slot = atomicAdd(p.unc_count, 1);
+                UncEntry e;
+                e.pose = pose;
+                e.conf_a = conf_a;
+                e.conf_b = conf_b;
+                p.unc_list[slot] = e;
+            }
+            p.status[pose] = st;
+            if (p.min_dist) p.min_dist[pose] = sqrtf(fmaxf(d2, 0.f));
+        }
+        // next iteration's first barrier orders the sMin reset before any atomicMin
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 recheck: one warp per undecided pose, reference arithmetic (utils.py:544-575)
+// ---------------------------------------------------------------------------------------------
+struct RecheckArgs {
+    const double* a_coords;
+    const double* b_coords;
+    const double* xf;
+    int n_a, n_b;
+    double thresh;
+    int max_clashes;
+    int strict;
+    const int* unc_count;
+    const UncEntry* unc_list;
+    uint8_t* status;
+    float* min_dist;
+    int* near_count;
+    long long* near_idx;
+    double* near_dist;
+    long long near_cap;
+    long long pose_base;
+};
+
+__global__ void __launch_bounds__(256) clash_recheck_f64_kernel(RecheckArgs p) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int n_unc = *p.unc_count;
+    for (int u = blockIdx.x * warps_per_block + (threadIdx.x >> 5); u < n_unc;
+         u += gridDim.x * warps_per_block) {
+        UncEntry e = p.unc_list[u];
+        const double* a = p.a_coords + (size_t)e.conf_a * p.n_a * 3;
+        const double* b = p.b_coords + (size_t)e.conf_b * p.n_b * 3;
+        const double* x = p.xf + e.pose * 12;
+        double r[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) r[k] = x[k];
+        int clashes = 0;
+        double dmin = 1e300, closest = 1e300;
+        for (int j = lane; j < p.n_b; j += 32) {
+            double bx = b[3 * j], by = b[3 * j + 1], bz = b[3 * j + 2];
+            // (R @ b) + t, the get_embed expression embeds.py:815-817
+            double px = (r[0] * bx + r[1] * by + r[2] * bz) + r[9];
+            double py = (r[3] * bx + r[4] * by + r[5] * bz) + r[10];
+            double pz = (r[6] * bx + r[7] * by + r[8] * bz) + r[11];
+            for (int i = 0; i < p.n_a; ++i) {
+                double dx = px - a[3 * i], dy = py - a[3 * i + 1], dz = pz - a[3 * i + 2];
+                double d = sqrt(dx * dx + dy * dy + dz * dz);
+                bool hit = p.strict ? (d < p.thresh) : (d <= p.thresh);
+                clashes += hit ? 1 : 0;
+                dmin = fmin(dmin, d);
+                closest = fmin(closest, fabs(d - p.thresh));
+            }
+        }
+        clashes = warp_sum(clashes);
+        dmin = warp_min(dmin);
+        closest = warp_min(closest);
+        if (lane == 0) {
+            uint8_t st = FC_STATUS_RECHECKED;
+            if (clashes <= p.max_clashes) st |= FC_STATUS_PASS;
+            // with max_clashes == 0 only the minimum distance decides; otherwise any pair may
+            const double margin = p.max_clashes == 0 ? fabs(dmin - p.thresh) : closest;
+            if (margin <= FC_NEAR_EPS) {
+                st |= FC_STATUS_NEAR;
+                if (p.near_count) {
+                    int slot = atomicAdd(p.near_count, 1);
+                    if (slot < p.near_cap) {
+                        if (p.near_idx) p.near_idx[slot] = e.pose + p.pose_base;
+                        if (p.near_dist) p.near_dist[slot] = dmin;
+                    }
+                }
+            }
+            p.status[e.pose] = st;
+            if (p.min_dist) p.min_dist[e.pose] = (float)dmin;
+        }
+    }
+}
+
+// optional CUDA-event timing of the dominant kernel (bench.py roofline leg)
+static thread_local bool g_time_on = false;
+static thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static thread_local double g_ms_sum = 0.0;
+static thread_local long g_ms_n = 0;
+static thread_local bool g_ev_pending = false;
+
+static void timing_flush() {
+    if (g_ev_pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(g_ev1) == cudaSuccess && cudaEventElapsedTime(&ms, g_ev0, g_ev1) == cudaSuccess) {
+            g_ms_sum += ms;
+            g_ms_n += 1;
+        }
+        g_ev_pending = false;
+    }
+}
+
+template <int TB>
+static cudaError_t launch_f32(const ClashArgs& args, int threads, size_t smem, int grid,
+                              cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(clash_f32_kernel<TB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (g_time_on) {
+        timing_flush();
+        if (!g_ev0) {
+            cudaEventCreate(&g_ev0);
+            cudaEventCreate(&g_ev1);
+        }
+        cudaEventRecord(g_ev0, s);
+    }
+    clash_f32_kernel<TB><<<grid, threads, smem, s>>>(args);
+    e = cudaGetLastError();
+    if (g_time_on) {
+        cudaEventRecord(g_ev1, s);
+        g_ev_pending = true;
+    }
+    return e;
+}
+
+}  // namespace fc
+
+using namespace fc;
+
+extern "C" int fc_clash_timing(int enable, double* ms_sum, int64_t* launches) {
+    timing_flush();
+    if (ms_sum) *ms_sum = g_ms_sum;
+    if (launches) *launches = g_ms_n;
+    g_time_on = enable != 0;
+    g_ms_sum = 0.0;
+    g_ms_n = 0;
+    return FC_OK;
+}
+
+extern "C" int fc_clash_geometry(int n_b, int32_t* out4) {
+    ClashGeom g = choose_geom(n_b);
+    if (out4) {
+        out4[0] = g.tb;
+        out4[1] = g.chunks;
+        out4[2] = g.poses;
+        out4[3] = g.threads;
+    }
+    return g.tb > 0 ? FC_OK : FC_ERR_INVALID;
+}
+
+extern "C" int fc_clash_tile_poses(int n_b) {
+    ClashGeom g = choose_geom(n_b);
+    return g.poses;
+}
+
+extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a,
+                                   const double* b_coords, int n_conf_b, int n_b, const double* xf,
+                                   int64_t n_poses, const int32_t* tiles, int64_t n_tiles,
+                                   double thresh, int max_clashes, int strict, uint8_t* status,
+                                   float* min_dist, int32_t* near_count, int64_t* near_idx,
+                                   double* near_dist, int64_t near_cap, int64_t pose_index_base,
+                                   void* stream) {
+    FC_REQUIRE(n_a > 0 && n_b > 0 && n_conf_a > 0 && n_conf_b > 0, "fc_clash_screen_dev: empty fragment");
+    FC_REQUIRE(n_poses >= 0 && max_clashes >= 0, "fc_clash_screen_dev: negative size");
+    if (n_poses == 0) return FC_OK;
+    FC_REQUIRE(a_coords && b_coords && xf && status, "fc_clash_screen_dev: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    ClashGeom g = choose_geom(n_b);
+    FC_REQUIRE(g.tb > 0, "fc_clash_screen_dev: fragment B too large (%d atoms)", n_b);
+    const int n_a_pad = (n_a + 1) / 2 * 2;
+    const int n_b_pad = g.chunks * g.tb;
+    if (!tiles) n_tiles = (n_poses + g.poses - 1) / g.poses;
+    FC_REQUIRE(n_tiles > 0, "fc_clash_screen_dev: empty tile list");
+
+    size_t smem = (size_t)n_a_pad * 32 + (size_t)n_b_pad * 16 + (size_t)g.poses * 4;
+    FC_REQUIRE(smem <= 227 * 1024, "fc_clash_screen_dev: fragments need %zu B of shared memory", smem);
+
+    // stream-ordered scratch
+    size_t a_bytes = (size_t)n_conf_a * n_a_pad * 32, b_bytes = (size_t)n_conf_b * n_b_pad * 16;
+    size_t off_a = 0, off_b = off_a + a_bytes, off_ra = off_b + b_bytes;
+    size_t off_rb = off_ra + (size_t)n_conf_a * 4, off_cnt = (off_rb + (size_t)n_conf_b * 4 + 15) / 16 * 16;
+    size_t off_list = off_cnt + 16;
+    size_t total = off_list + (size_t)n_poses * sizeof(UncEntry);
+    unsigned char* scratch = nullptr;
+    FC_CUDA(cudaMallocAsync((void**)&scratch, total, s));
+
+    clash_prep_kernel<<<n_conf_a, 128, 0, s>>>(a_coords, n_conf_a, n_a, n_a_pad, 1,
+                                               (float4*)(scratch + off_a), (float*)(scratch + off_ra));
+    clash_prep_kernel<<<n_conf_b, 128, 0, s>>>(b_coords, n_conf_b, n_b, n_b_pad, 0,
+                                               (float4*)(scratch + off_b), (float*)(scratch + off_rb));
+    FC_CUDA(cudaMemsetAsync(scratch + off_cnt, 0, 16, s));
+
+    ClashArgs a;
+    a.a_tab = (const float4*)(scratch + off_a);
+    a.a_rad = (const float*)(scratch + off_ra);
+    a.b_tab = (const float4*)(scratch + off_b);
+    a.b_rad = (const float*)(scratch + off_rb);
+    a.xf = xf;
+    a.tiles = (const int4*)tiles;
+    a.n_tiles = n_tiles;
+    a.n_poses = n_poses;
+    a.n_a_pad = n_a_pad;
+    a.n_b_pad = n_b_pad;
+    a.chunks = g.chunks;
+    a.poses = g.poses;
+    a.thr2 = (float)(thresh * thresh);
+    a.count_mode = max_clashes > 0;
+    a.status = status;
+    a.min_dist = min_dist;
+    a.unc_count = (int*)(scratch + off_cnt);
+    a.unc_list = (UncEntry*)(scratch + off_list);
+
+    int sms = sm_count();
+    // persistent grid: resident CTAs per SM follow from the register/thread budget
+    int ctas_per_sm = 2048 / g.threads;
+    if (ctas_per_sm > 4) ctas_per_sm = 4;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    long long grid_ll = (long long)sms * ctas_per_sm;
+    if (grid_ll > n_tiles) grid_ll = n_tiles;
+    int grid = (int)grid_ll;
+    cudaError_t e;
+    switch (g.tb) {
+        case 2: e = launch_f32<2>(a, g.threads, smem, grid, s); break;
+        case 4: e = launch_f32<4>(a, g.threads, smem, grid, s); break;
+        case 6: e = launch_f32<6>(a, g.threads, smem, grid, s); break;
+        case 8: e = launch_f32<8>(a, g.threads, smem, grid, s); break;
+        case 10: e = launch_f32<10>(a, g.threads, smem, grid, s); break;
+        case 12: e = launch_f32<12>(a, g.threads, smem, grid, s); break;
+        case 14: e = launch_f32<14>(a, g.threads, smem, grid, s); break;
+        default: e = launch_f32<16>(a, g.threads, smem, grid, s); break;
+    }
+    if (e != cudaSuccess) {
+        cudaFreeAsync(scratch, s);
+        return cuda_fail(e, "clash_f32_kernel launch", __FILE__, __LINE__);
+    }
+
+    RecheckArgs r;
+    r.a_coords = a_coords;
+    r.b_coords = b_coords;
+    r.xf = xf;
+    r.n_a = n_a;
+    r.n_b = n_b;
+    r.thresh = thresh;
+    r.max_clashes = max_clashes;
+    r.strict = strict;
+    r.unc_count = a.unc_count;
+    r.unc_list = a.unc_list;
+    r.status = status;
+    r.min_dist = min_dist;
+    r.near_count = near_count;
+    r.near_idx = (long long*)near_idx;
+    r.near_dist = near_dist;
+    r.near_cap = near_cap;
+    r.pose_base = pose_index_base;
+    clash_recheck_f64_kernel<<<sms * 2, 256, 0, s>>>(r);
+    e = cudaGetLastError();
+    cudaError_t e2 = cudaFreeAsync(scratch, s);
+    if (e != cudaSuccess) return cuda_fail(e, "clash_recheck_f64_kernel launch", __FILE__, __LINE__);
+    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFreeAsync", __FILE__, __LINE__);
+    return FC_OK;
+}

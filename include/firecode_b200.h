@@ -1,0 +1,101 @@
+/* firecode_b200 -- C-ABI of the B200-native FIRECODE embedding screen.
+ *
+ * Every entry point is plain C: pointers + sizes, no torch / C++ types.  Functions return 0 on
+ * success and a non-zero code on failure; fc_last_error() then holds a thread-local message.
+ * "_dev" entry points take DEVICE pointers and a cudaStream_t passed as void* (0 = default
+ * stream) and never synchronise; the un-suffixed ones take HOST pointers, do their own
+ * host<->device copies on an internal stream and return when the results are in host memory.
+ *
+ * Reference citations are file:line under /root/reference/firecode (FIRECODE v2.0.4).
+ */
+#ifndef FIRECODE_B200_H
+#define FIRECODE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FC_OK 0
+#define FC_ERR_INVALID 1
+#define FC_ERR_CUDA 2
+#define FC_ERR_NOMEM 3
+
+/* status byte written per pose by the clash screen */
+#define FC_STATUS_PASS 1u      /* bit0: pose passes the compenetration check                       */
+#define FC_STATUS_RECHECKED 2u /* bit1: decided by the FP64 recheck (FP32 value was inside the band) */
+#define FC_STATUS_NEAR 4u      /* bit2: FP64 min distance within FC_NEAR_EPS of the threshold        */
+#define FC_NEAR_EPS 1e-6
+
+const char* fc_last_error(void);
+int fc_version(void);
+/* number of visible CUDA devices; <= 0 means the library cannot run (there is no CPU fallback) */
+int fc_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Clash screen (compenetration check).
+ * Replaces utils.py:507-575 `compenetration_check(coords, ids=..., thresh, max_clashes)` as it is
+ * called once per candidate pose at embeds.py:139-141, 559-563, 718-722, and torsion_module.py:
+ * 894-918 `torsion_comp_check`.  A pose is (conformer a of ensemble A, conformer b of ensemble B,
+ * rigid transform): fragment A stays in its own frame, fragment B is placed at R @ b + t, exactly
+ * the `get_embed` expression embeds.py:815-817 with mol1 at identity (only the relative transform
+ * matters for intermolecular distances).  pass <=> #{(i,j): |a_i - (R b_j + t)| < thresh} <=
+ * max_clashes  (strict `<`, utils.py:551; `strict == 0` selects the `<=` of the trimolecular
+ * branch utils.py:563-571).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Largest number of poses one tile may hold for fragments of n_b atoms (explicit tile lists must
+ * not exceed it) and the FP32-kernel geometry chosen for it. */
+int fc_clash_tile_poses(int n_b);
+
+/* Device-pointer entry.
+ *  a_coords  (n_conf_a, n_a, 3) f64   ensemble A
+ *  b_coords  (n_conf_b, n_b, 3) f64   ensemble B
+ *  xf        (n_poses, 12)      f64   per pose: R row-major (9) then t (3)
+ *  tiles     (n_tiles, 4)       i32   {conf_a, conf_b, first_pose, n_poses_in_tile<=tile_poses} or
+ *                                      NULL: every pose uses conformer 0 of both ensembles
+ *  status    (n_poses)          u8    FC_STATUS_* bits
+ *  min_dist  (n_poses)          f32   optional (may be NULL): FP32 estimate of the min distance
+ *  near_count (1) i32 device, near_idx (near_cap) i64, near_dist (near_cap) f64: optional list of
+ *            poses whose FP64 min distance lies within FC_NEAR_EPS of thresh (NULL to skip)
+ *  pose_index_base  added to the pose numbers written to near_idx (chunked callers)
+ * Scratch memory is taken from the stream-ordered pool (cudaMallocAsync) on `stream`.
+ */
+int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a, const double* b_coords,
+                        int n_conf_b, int n_b, const double* xf, int64_t n_poses,
+                        const int32_t* tiles, int64_t n_tiles, double thresh, int max_clashes,
+                        int strict, uint8_t* status, float* min_dist, int32_t* near_count,
+                        int64_t* near_idx, double* near_dist, int64_t near_cap,
+                        int64_t pose_index_base, void* stream);
+
+/* Host-pointer entry: same arguments in host memory; copies are pipelined in chunks with the
+ * kernels.  counts[0] = passing poses, counts[1] = poses decided by the FP64 recheck,
+ * counts[2] = near-threshold poses (near_idx/near_dist hold the first near_cap of them). */
+int fc_clash_batch(const double* a_coords, int n_conf_a, int n_a, const double* b_coords,
+                   int n_conf_b, int n_b, const double* xf, int64_t n_poses, const int32_t* tiles,
+                   int64_t n_tiles, double thresh, int max_clashes, int strict, uint8_t* status,
+                   float* min_dist, int64_t* counts, int64_t* near_idx, double* near_dist,
+                   int64_t near_cap);
+
+/* FP32-kernel geometry chosen for fragments of n_b atoms: out4 = {atoms per thread, threads per
+ * pose, poses per tile, threads per block}. */
+int fc_clash_geometry(int n_b, int32_t* out4);
+
+/* CUDA-event timing of the FP32 clash kernel alone (bench.py roofline leg): returns the summed
+ * milliseconds and launch count recorded on this thread since the previous call, then switches
+ * recording on (enable != 0) or off. */
+int fc_clash_timing(int enable, double* ms_sum, int64_t* launches);
+
+/* Survivor bitmask: bit (i & 31) of bits[i >> 5] = status[i] & FC_STATUS_PASS; bits holds
+ * ceil(n / 32) words.  This is the buffer the ranks exchange with one NCCL all-gather. */
+int fc_pack_mask_dev(const uint8_t* status, int64_t n, uint32_t* bits, void* stream);
+
+/* FP32 FMA-pipe peak probe used by bench.py for the roofline denominator: runs a dependent-free
+ * FFMA2 loop on every SM and returns achieved TFLOP/s (2 flop per FMA lane). */
+int fc_probe_fp32_peak(double* tflops_out, double* ms_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIRECODE_B200_H */

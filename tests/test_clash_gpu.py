@@ -1,0 +1,110 @@
+"""GPU parity: CUDA clash screen (C-ABI fc_clash_batch) vs the CPU oracle, bit-exact masks."""
+
+import numpy as np
+import pytest
+
+from firecode_b200 import synthetic
+from firecode_b200.clash import NEAR_EPS, STATUS_NEAR, compenetration_check_batch
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _frags(rng, n_a, n_b):
+    _, a, _, _ = synthetic.molecule_cloud(rng, n_a)
+    _, b, _, _ = synthetic.molecule_cloud(rng, n_b)
+    return a, b
+
+
+@pytest.mark.parametrize("n_a,n_b,n_poses", [(150, 150, 8000), (30, 30, 5000), (5, 5, 300),
+                                             (61, 47, 3000), (1, 1, 64), (150, 33, 2000),
+                                             (7, 150, 2000)])
+def test_mask_matches_oracle(gpu, n_a, n_b, n_poses):
+    rng = np.random.default_rng(synthetic.SEED + n_a * 1000 + n_b)
+    a, b = _frags(rng, max(n_a, 2), max(n_b, 2))
+    a, b = a[:n_a], b[:n_b]
+    xf = synthetic.sweep_poses(rng, a, b, n_poses)
+    res = compenetration_check_batch(a, b, xf, thresh=1.5, want_min_dist=True)
+    mask, dmin, closest = port.clash_batch(a, b, xf, thresh=1.5)
+    assert res.mask.dtype == bool and res.mask.shape == (n_poses,)
+    near = np.abs(dmin - 1.5) <= NEAR_EPS
+    # every near-threshold pose is listed; everything else is bit-exact
+    assert np.array_equal(res.mask[~near], mask[~near])
+    assert set(np.flatnonzero(near)) <= set(res.near_idx.tolist())
+    assert np.allclose(res.min_dist, dmin, atol=5e-3)
+    # clash rate sanity: the sweep is a mixed set
+    assert 0.02 < mask.mean() < 0.98 or n_a * n_b < 100
+
+
+def test_empty_and_single(gpu):
+    rng = np.random.default_rng(1)
+    a, b = _frags(rng, 20, 20)
+    res = compenetration_check_batch(a, b, np.zeros((0, 12)), thresh=1.5)
+    assert res.mask.shape == (0,)
+    xf = np.array([[1, 0, 0, 0, 1, 0, 0, 0, 1, 100.0, 0, 0]], dtype=float)
+    assert compenetration_check_batch(a, b, xf, thresh=1.5).mask.tolist() == [True]
+    xf[0, 9] = 0.0
+    assert compenetration_check_batch(a, a, xf, thresh=1.5).mask.tolist() == [False]
+
+
+def test_conformer_tiles(gpu):
+    rng = np.random.default_rng(7)
+    _, ens_a, _, _ = synthetic.conformer_ensemble(rng, 6, 40)
+    _, ens_b, _, _ = synthetic.conformer_ensemble(rng, 5, 33)
+    n = 7000
+    ca = np.sort(rng.integers(0, 6, size=n))
+    cb = rng.integers(0, 5, size=n)
+    order = np.lexsort((cb, ca))
+    ca, cb = ca[order], cb[order]
+    xf = synthetic.sweep_poses(rng, ens_a[0], ens_b[0], n)
+    res = compenetration_check_batch(ens_a, ens_b, xf, thresh=1.5, conf_a=ca, conf_b=cb)
+    mask, dmin, _ = port.clash_batch(ens_a, ens_b, xf, thresh=1.5, conf_a=ca, conf_b=cb)
+    ok = np.abs(dmin - 1.5) > NEAR_EPS
+    assert np.array_equal(res.mask[ok], mask[ok])
+
+
+@pytest.mark.parametrize("max_clashes,strict", [(0, False), (3, True), (10, False)])
+def test_count_mode_and_nonstrict(gpu, max_clashes, strict):
+    rng = np.random.default_rng(11 + max_clashes)
+    a, b = _frags(rng, 60, 60)
+    xf = synthetic.sweep_poses(rng, a, b, 4000, shell=(-3.0, 2.0))
+    res = compenetration_check_batch(a, b, xf, thresh=1.5, max_clashes=max_clashes, strict=strict)
+    mask, _, closest = port.clash_batch(a, b, xf, thresh=1.5, max_clashes=max_clashes, strict=strict)
+    ok = closest > NEAR_EPS
+    assert np.array_equal(res.mask[ok], mask[ok])
+
+
+def test_adversarial_near_threshold(gpu):
+    """Poses constructed so the closest pair sits at thresh + delta for tiny deltas: the FP64
+    recheck must decide them like the oracle and list those within 1e-6 A."""
+    rng = np.random.default_rng(2026)
+    a, b = _frags(rng, 150, 150)
+    thr = 1.5
+    base = synthetic.sweep_poses(rng, a, b, 3000, shell=(2.0, 6.0), dtype=np.float64)
+    _, dmin, _ = port.clash_batch(a, b, base, thresh=thr)
+    out = []
+    deltas = [0.0, 1e-7, -1e-7, 1e-6, -1e-6, 1e-5, -1e-5, 3e-4, -3e-4]
+    k = 0
+    for p in np.flatnonzero(dmin > thr + 0.2)[:600]:
+        placed = port.place(b, base[p])
+        d = np.linalg.norm(placed[:, None, :] - a[None, :, :], axis=-1)
+        j, i = np.unravel_index(np.argmin(d), d.shape)
+        u = (a[i] - placed[j]) / d[j, i]
+        xf = base[p].copy()
+        xf[9:12] += u * (d[j, i] - (thr + deltas[k % len(deltas)]))
+        k += 1
+        out.append(xf)
+    xf = np.array(out)
+    res = compenetration_check_batch(a, b, xf, thresh=thr, want_min_dist=True)
+    mask, dmin2, closest = port.clash_batch(a, b, xf, thresh=thr)
+    gap = np.abs(dmin2 - thr)
+    far = gap > 1e-9  # beyond double rounding noise the decision must agree
+    assert np.array_equal(res.mask[far], mask[far])
+    near = gap <= NEAR_EPS
+    assert near.sum() > 100
+    assert set(np.flatnonzero(near)) <= set(res.near_idx.tolist())
+    assert np.all(res.status[np.flatnonzero(near)] & STATUS_NEAR)
+    # listed distances are the FP64 minimum distances
+    lut = dict(zip(res.near_idx.tolist(), res.near_dist.tolist()))
+    for p in np.flatnonzero(near)[:50]:
+        assert abs(lut[p] - dmin2[p]) < 1e-9
