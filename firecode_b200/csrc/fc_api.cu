@@ -30,6 +30,13 @@ int sm_count() {
     if (cached[dev] == 0) {
         int n = 0;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        // keep stream-ordered scratch (cudaMallocAsync) cached in the pool instead of returning it
+        // to the OS at every synchronisation point
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
         cached[dev] = n;
     }
     return cached[dev];
@@ -168,25 +175,26 @@ extern "C" int fc_clash_batch(const double* a_coords, int n_conf_a, int n_a, con
         }                                                            \
     } while (0)
 
+    sm_count();  // configures the memory pool on first use
     for (int i = 0; i < kBuf; ++i) st[i] = nullptr;
     ev_setup = nullptr;
     for (int i = 0; i < kBuf; ++i) FC_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
     FC_TRY(cudaEventCreateWithFlags(&ev_setup, cudaEventDisableTiming));
-    FC_TRY(cudaMalloc((void**)&d_a, (size_t)n_conf_a * n_a * 24));
-    FC_TRY(cudaMalloc((void**)&d_b, (size_t)n_conf_b * n_b * 24));
-    FC_TRY(cudaMalloc((void**)&d_status, (size_t)n_poses));
-    if (min_dist) FC_TRY(cudaMalloc((void**)&d_min, (size_t)n_poses * 4));
-    FC_TRY(cudaMalloc((void**)&d_near_count, 16));
+    FC_TRY(cudaMallocAsync((void**)&d_a, (size_t)n_conf_a * n_a * 24, st[0]));
+    FC_TRY(cudaMallocAsync((void**)&d_b, (size_t)n_conf_b * n_b * 24, st[0]));
+    FC_TRY(cudaMallocAsync((void**)&d_status, (size_t)n_poses, st[0]));
+    if (min_dist) FC_TRY(cudaMallocAsync((void**)&d_min, (size_t)n_poses * 4, st[0]));
+    FC_TRY(cudaMallocAsync((void**)&d_near_count, 16, st[0]));
     if (near_cap > 0) {
-        FC_TRY(cudaMalloc((void**)&d_near_idx, (size_t)near_cap * 8));
-        FC_TRY(cudaMalloc((void**)&d_near_dist, (size_t)near_cap * 8));
+        FC_TRY(cudaMallocAsync((void**)&d_near_idx, (size_t)near_cap * 8, st[0]));
+        FC_TRY(cudaMallocAsync((void**)&d_near_dist, (size_t)near_cap * 8, st[0]));
     }
-    for (int i = 0; i < kBuf; ++i) FC_TRY(cudaMalloc((void**)&d_xf[i], (size_t)chunk * 96));
+    for (int i = 0; i < kBuf; ++i) FC_TRY(cudaMallocAsync((void**)&d_xf[i], (size_t)chunk * 96, st[0]));
     FC_TRY(cudaMemcpyAsync(d_a, a_coords, (size_t)n_conf_a * n_a * 24, cudaMemcpyHostToDevice, st[0]));
     FC_TRY(cudaMemcpyAsync(d_b, b_coords, (size_t)n_conf_b * n_b * 24, cudaMemcpyHostToDevice, st[0]));
     FC_TRY(cudaMemsetAsync(d_near_count, 0, 16, st[0]));
     if (tiles) {
-        FC_TRY(cudaMalloc((void**)&d_tiles, (size_t)n_tiles * 16));
+        FC_TRY(cudaMallocAsync((void**)&d_tiles, (size_t)n_tiles * 16, st[0]));
         FC_TRY(cudaMemcpyAsync(d_tiles, tiles, (size_t)n_tiles * 16, cudaMemcpyHostToDevice, st[0]));
     }
     FC_TRY(cudaEventRecord(ev_setup, st[0]));
@@ -231,19 +239,19 @@ extern "C" int fc_clash_batch(const double* a_coords, int n_conf_a, int n_a, con
         }
     }
 done:
-    for (int i = 0; i < kBuf; ++i) {
-        if (d_xf[i]) cudaFree(d_xf[i]);
-        if (st[i]) cudaStreamDestroy(st[i]);
+    if (st[0]) {
+        for (int i = 0; i < kBuf; ++i) {
+            if (st[i]) cudaStreamSynchronize(st[i]);
+            if (d_xf[i]) cudaFreeAsync(d_xf[i], st[0]);
+        }
+        void* bufs[] = {d_a, d_b, d_status, d_min, d_tiles, d_near_count, d_near_idx, d_near_dist};
+        for (void* q : bufs)
+            if (q) cudaFreeAsync(q, st[0]);
+        cudaStreamSynchronize(st[0]);
     }
+    for (int i = 0; i < kBuf; ++i)
+        if (st[i]) cudaStreamDestroy(st[i]);
     if (ev_setup) cudaEventDestroy(ev_setup);
-    cudaFree(d_a);
-    cudaFree(d_b);
-    cudaFree(d_status);
-    cudaFree(d_min);
-    cudaFree(d_tiles);
-    cudaFree(d_near_count);
-    cudaFree(d_near_idx);
-    cudaFree(d_near_dist);
     return rc;
 #undef FC_TRY
 }

@@ -7,17 +7,20 @@
 // FP32 pass (clash_f32_kernel): the squared distance is evaluated in Gram form
 //      |a - b'|^2 = (|a|^2 - 2 a.b') + |b'|^2
 // so one atom pair costs 3 FMA lanes instead of the 6 FMA-pipe slots of the difference form.
-//   * thread (pose_local, chunk) owns TB atoms of the transformed fragment B as TB/2 packed
-//     f32x2 register pairs (x, y, z) and TB running minima;
-//   * fragment A sits in shared memory in a duplicated broadcast layout
-//     {-2ax,-2ax,-2ay,-2ay | -2az,-2az,|a|^2,|a|^2} so every LDS.128 is a warp-wide broadcast and
-//     its halves are ready-made FFMA2 operands;
-//   * per A atom and B pair: 3 FFMA2; per two A atoms and B pair: 2 FMNMX3 (ALU pipe).
+//   * thread (pose_local, chunk) owns TB atoms of the transformed fragment B as 3*TB scalar
+//     registers (ptxas feeds them to FFMA2 as 32-bit broadcast operands, `Rn.F32`) and TB running
+//     minima;
+//   * fragment A sits in shared memory as atom PAIRS {-2a0x,-2a1x,-2a0y,-2a1y | -2a0z,-2a1z,
+//     |a0|^2,|a1|^2}: two warp-wide broadcast LDS.128 deliver the four FFMA2 operands of two atoms;
+//   * per A pair and B atom: 3 FFMA2 + 2 FMNMX.  tools/microbench*.cu record why this shape was
+//     chosen (FFMA2 register-operand limits, LDS.128 and FMNMX3 issue costs on B200).
 // The FP32 result is trusted only outside a rigorous rounding band around thresh^2; poses inside
 // the band (and every pose when max_clashes > 0 and a clash is possible) go to the FP64 recheck
 // kernel, which restates the reference arithmetic (f64 transform, sqrt of the summed squares,
 // `<` / `<=` compare, clash count).  Poses whose FP64 minimum distance lies within FC_NEAR_EPS of
 // the threshold are flagged and listed.
+#include <stdlib.h>
+
 #include "fc_common.cuh"
 
 namespace fc {
@@ -29,33 +32,58 @@ struct ClashGeom {
     int threads;  // block size (multiple of 32)
 };
 
+static const int kTBs[] = {30, 25, 20, 16, 15, 12, 10, 8, 6, 4, 2};
+// measured FMA-pipe efficiency of the main loop per TB (tools/microbench9.cu, B200)
+static double tb_efficiency(int tb) {
+    if (tb >= 30) return 0.76;
+    if (tb >= 25) return 0.74;
+    if (tb >= 20) return 0.71;
+    if (tb >= 15) return 0.68;
+    if (tb >= 10) return 0.62;
+    if (tb >= 6) return 0.52;
+    return 0.40;
+}
+static int tb_max_threads(int tb) {  // register budget: 65536 / (registers per thread)
+    if (tb >= 25) return 256;
+    if (tb >= 20) return 320;
+    if (tb >= 15) return 448;
+    return 512;
+}
+
 static ClashGeom choose_geom(int n_b) {
-    static const int kTB[] = {16, 14, 12, 10, 8, 6, 4, 2};
     ClashGeom best{0, 0, 0, 0};
-    long best_pad = 1L << 60;
-    for (int tb : kTB) {
+    double best_cost = 1e300;
+    const char* force = getenv("FC_CLASH_TB");
+    for (int tb : kTBs) {
+        if (force && atoi(force) != tb) continue;
         int chunks = (n_b + tb - 1) / tb;
-        if (chunks > 512) continue;
-        long pad = (long)chunks * tb;
-        if (pad < best_pad) {
-            best_pad = pad;
+        if (chunks > tb_max_threads(tb)) continue;
+        double cost = (double)chunks * tb / tb_efficiency(tb);
+        if (cost < best_cost) {
+            best_cost = cost;
             best.tb = tb;
             best.chunks = chunks;
         }
     }
     if (best.tb == 0) return best;
-    // poses per tile: keep the block <= 512 threads and waste as few lanes as possible
+    // poses per tile: CTAs of ~4-5 warps, several per SM, as few idle lanes as possible
     int c = best.chunks;
-    int p_hi = 512 / c;
-    if (p_hi < 1) p_hi = 1;
-    int p_lo = (p_hi + 1) / 2;
-    double best_u = -1.0;
-    for (int p = p_hi; p >= p_lo; --p) {
+    int t_max = tb_max_threads(best.tb);
+    double best_score = -1.0;
+    for (int p = 1; p * c <= t_max; ++p) {
         int used = p * c;
         int threads = (used + 31) / 32 * 32;
-        double u = (double)used / threads;
-        if (u > best_u + 1e-9) {
-            best_u = u;
+        if (threads > t_max) break;
+        int ctas = t_max / threads;
+        if (ctas > 8) ctas = 8;
+        double util = (double)used / threads;
+        double warps = (double)ctas * threads / 32.0;
+        double fill = warps >= 8.0 ? 1.0 : warps / 8.0;
+        // small penalty for very large CTAs (barrier + prologue are not overlapped inside one CTA)
+        double size_pen = threads > 160 ? 0.97 : 1.0;
+        double score = util * fill * size_pen;
+        if (score > best_score + 1e-9) {
+            best_score = score;
             best.poses = p;
             best.threads = threads;
         }
@@ -66,7 +94,8 @@ static ClashGeom choose_geom(int n_b) {
 // ---------------------------------------------------------------------------------------------
 // table preparation: f64 ensembles -> FP32 layouts used by the screen
 // ---------------------------------------------------------------------------------------------
-// a_tab: [conf][n_a_pad][2] float4  (n_a_pad even; padding atoms: a' = 0, |a|^2 = 1e30)
+// a_tab: [conf][n_a_pad/2][2] float4 per atom pair {-2a0x,-2a1x,-2a0y,-2a1y},{-2a0z,-2a1z,|a0|^2,
+//        |a1|^2}  (n_a_pad even; padding atoms: a' = 0, |a|^2 = 1e30)
 // b_tab: [conf][n_b_pad]    float4  {x, y, z, 0}  (padding atoms carry w = 1e30)
 // rad  : [conf] max |x| over the conformer (f32, rounded up)
 __global__ void clash_prep_kernel(const double* __restrict__ coords, int n_conf, int n_atoms,
@@ -81,15 +110,21 @@ __global__ void clash_prep_kernel(const double* __restrict__ coords, int n_conf,
             float n2 = fmaf(x, x, fmaf(y, y, z * z));
             r2max = fmaxf(r2max, n2);
             if (as_a) {
-                tab[((size_t)conf * n_pad + i) * 2] = make_float4(-2.f * x, -2.f * x, -2.f * y, -2.f * y);
-                tab[((size_t)conf * n_pad + i) * 2 + 1] = make_float4(-2.f * z, -2.f * z, n2, n2);
+                float* dst = reinterpret_cast<float*>(tab + ((size_t)conf * n_pad + (i & ~1))) + (i & 1);
+                dst[0] = -2.f * x;
+                dst[2] = -2.f * y;
+                dst[4] = -2.f * z;
+                dst[6] = n2;
             } else {
                 tab[(size_t)conf * n_pad + i] = make_float4(x, y, z, 0.f);
             }
         } else {
             if (as_a) {
-                tab[((size_t)conf * n_pad + i) * 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                tab[((size_t)conf * n_pad + i) * 2 + 1] = make_float4(0.f, 0.f, 1e30f, 1e30f);
+                float* dst = reinterpret_cast<float*>(tab + ((size_t)conf * n_pad + (i & ~1))) + (i & 1);
+                dst[0] = 0.f;
+                dst[2] = 0.f;
+                dst[4] = 0.f;
+                dst[6] = 1e30f;
             } else {
                 tab[(size_t)conf * n_pad + i] = make_float4(0.f, 0.f, 0.f, 1e30f);
             }
@@ -131,11 +166,23 @@ struct ClashArgs {
 };
 
 template <int TB>
-__global__ void __launch_bounds__(512, 1) clash_f32_kernel(ClashArgs p) {
+struct ClashLaunch {
+    static constexpr int kMaxThreads = TB >= 25 ? 256 : (TB >= 20 ? 320 : (TB >= 15 ? 448 : 512));
+};
+
+__device__ __forceinline__ f32x2 fma2v(f32x2 a, f32x2 b, f32x2 c) {  // volatile: keeps program order
+    f32x2 d;
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// VAR bit0: chain-major program order (volatile FFMA2), bit1: FMNMX3 instead of two FMNMX
+template <int TB, int VAR>
+__global__ void __launch_bounds__(ClashLaunch<TB>::kMaxThreads, 1) clash_f32_kernel(ClashArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ulonglong2* sA = reinterpret_cast<ulonglong2*>(smem_raw);                  // n_a_pad * 2
-    float4* sB = reinterpret_cast<float4*>(smem_raw + (size_t)p.n_a_pad * 32);  // n_b_pad
-    int* sMin = reinterpret_cast<int*>(smem_raw + (size_t)p.n_a_pad * 32 + (size_t)p.n_b_pad * 16);
+    ulonglong2* sA = reinterpret_cast<ulonglong2*>(smem_raw);                  // n_a_pad entries
+    float4* sB = reinterpret_cast<float4*>(smem_raw + (size_t)p.n_a_pad * 16);  // n_b_pad entries
+    int* sMin = reinterpret_cast<int*>(smem_raw + (size_t)p.n_a_pad * 16 + (size_t)p.n_b_pad * 16);
 
     const int tid = threadIdx.x;
     const int pose_local = tid / p.chunks;
@@ -163,8 +210,8 @@ __global__ void __launch_bounds__(512, 1) clash_f32_kernel(ClashArgs p) {
             __syncthreads();  // everybody is done with the previous tables
             if (conf_a != cur_a) {
                 const ulonglong2* src =
-                    reinterpret_cast<const ulonglong2*>(p.a_tab) + (size_t)conf_a * p.n_a_pad * 2;
-                for (int i = tid; i < p.n_a_pad * 2; i += blockDim.x) sA[i] = src[i];
+                    reinterpret_cast<const ulonglong2*>(p.a_tab) + (size_t)conf_a * p.n_a_pad;
+                for (int i = tid; i < p.n_a_pad; i += blockDim.x) sA[i] = src[i];
             }
             if (conf_b != cur_b) {
                 const float4* src = p.b_tab + (size_t)conf_b * p.n_b_pad;
@@ -177,7 +224,6 @@ __global__ void __launch_bounds__(512, 1) clash_f32_kernel(ClashArgs p) {
 
         const bool active = lane_used && pose_local < count;
         const long long pose = first + pose_local;
-        float lane_min = 3.0e38f;
         float tnorm = 0.f;
         if (active) {
             // ---- transform this thread's TB atoms of fragment B --------------------------------
@@ -187,47 +233,44 @@ __global__ void __launch_bounds__(512, 1) clash_f32_kernel(ClashArgs p) {
             for (int k = 0; k < 12; ++k) r[k] = (float)__ldg(x + k);
             tnorm = sqrtf(fmaf(r[9], r[9], fmaf(r[10], r[10], r[11] * r[11])));
 
-            f32x2 bx[TB / 2], by[TB / 2], bz[TB / 2];
-            float nb[TB], m[TB];
+            float bx[TB], by[TB], bz[TB], m[TB];
 #pragma unroll
-            for (int q = 0; q < TB / 2; ++q) {
-                float4 b0 = sB[chunk * TB + 2 * q];
-                float4 b1 = sB[chunk * TB + 2 * q + 1];
-                float x0 = fmaf(r[0], b0.x, fmaf(r[1], b0.y, fmaf(r[2], b0.z, r[9])));
-                float y0 = fmaf(r[3], b0.x, fmaf(r[4], b0.y, fmaf(r[5], b0.z, r[10])));
-                float z0 = fmaf(r[6], b0.x, fmaf(r[7], b0.y, fmaf(r[8], b0.z, r[11])));
-                float x1 = fmaf(r[0], b1.x, fmaf(r[1], b1.y, fmaf(r[2], b1.z, r[9])));
-                float y1 = fmaf(r[3], b1.x, fmaf(r[4], b1.y, fmaf(r[5], b1.z, r[10])));
-                float z1 = fmaf(r[6], b1.x, fmaf(r[7], b1.y, fmaf(r[8], b1.z, r[11])));
-                // padding atoms: keep them at the origin and push |b|^2 to 1e30
-                nb[2 * q] = fmaf(x0, x0, fmaf(y0, y0, z0 * z0)) + b0.w;
-                nb[2 * q + 1] = fmaf(x1, x1, fmaf(y1, y1, z1 * z1)) + b1.w;
-                bx[q] = pack2(x0, x1);
-                by[q] = pack2(y0, y1);
-                bz[q] = pack2(z0, z1);
-                m[2 * q] = 3.0e38f;
-                m[2 * q + 1] = 3.0e38f;
+            for (int j = 0; j < TB; ++j) {
+                float4 b = sB[chunk * TB + j];
+                bx[j] = fmaf(r[0], b.x, fmaf(r[1], b.y, fmaf(r[2], b.z, r[9])));
+                by[j] = fmaf(r[3], b.x, fmaf(r[4], b.y, fmaf(r[5], b.z, r[10])));
+                bz[j] = fmaf(r[6], b.x, fmaf(r[7], b.y, fmaf(r[8], b.z, r[11])));
+                m[j] = 3.0e38f;
             }
 
-            // ---- all atom pairs: A broadcast from shared memory, two A atoms per step --------
-            const int n_a_pad = p.n_a_pad;
+            // ---- all atom pairs: two A atoms per step, broadcast from shared memory ------------
+            const int n_pairs = p.n_a_pad >> 1;
 #pragma unroll 2
-            for (int i = 0; i < n_a_pad; i += 2) {
+            for (int i = 0; i < n_pairs; ++i) {
                 ulonglong2 u0 = sA[2 * i], u1 = sA[2 * i + 1];
-                ulonglong2 v0 = sA[2 * i + 2], v1 = sA[2 * i + 3];
 #pragma unroll
-                for (int q = 0; q < TB / 2; ++q) {
-                    f32x2 e0 = fma2(u0.x, bx[q], fma2(u0.y, by[q], fma2(u1.x, bz[q], u1.y)));
-                    f32x2 e1 = fma2(v0.x, bx[q], fma2(v0.y, by[q], fma2(v1.x, bz[q], v1.y)));
-                    float e0l, e0h, e1l, e1h;
-                    unpack2(e0, e0l, e0h);
-                    unpack2(e1, e1l, e1h);
-                    m[2 * q] = min3(m[2 * q], e0l, e1l);
-                    m[2 * q + 1] = min3(m[2 * q + 1], e0h, e1h);
+                for (int j = 0; j < TB; ++j) {
+                    f32x2 e;
+                    if (VAR & 1)
+                        e = fma2v(u0.x, pack2(bx[j], bx[j]),
+                                  fma2v(u0.y, pack2(by[j], by[j]), fma2v(u1.x, pack2(bz[j], bz[j]), u1.y)));
+                    else
+                        e = fma2(u0.x, pack2(bx[j], bx[j]),
+                                 fma2(u0.y, pack2(by[j], by[j]), fma2(u1.x, pack2(bz[j], bz[j]), u1.y)));
+                    float lo, hi;
+                    unpack2(e, lo, hi);
+                    if (VAR & 2)
+                        m[j] = min3(m[j], lo, hi);
+                    else
+                        m[j] = fminf(fminf(m[j], lo), hi);
                 }
             }
+            float lane_min = 3.0e38f;
 #pragma unroll
-            for (int j = 0; j < TB; ++j) lane_min = fminf(lane_min, m[j] + nb[j]);
+            for (int j = 0; j < TB; ++j) {
+                float nb = fmaf(bx[j], bx[j], fmaf(by[j], by[j], bz[j] * bz[j])) + sB[chunk * TB + j].w;
+                lane_min = fminf(lane_min, m[j] + nb);
+            }
             atomicMin(&sMin[pose_local], float_key(lane_min));
         }
         __syncthreads();
@@ -355,10 +398,10 @@ static void timing_flush() {
     }
 }
 
-template <int TB>
-static cudaError_t launch_f32(const ClashArgs& args, int threads, size_t smem, int grid,
-                              cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(clash_f32_kernel<TB>,
+template <int TB, int VAR>
+static cudaError_t launch_f32v(const ClashArgs& args, int threads, size_t smem, int grid,
+                               cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(clash_f32_kernel<TB, VAR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (g_time_on) {
@@ -369,13 +412,29 @@ static cudaError_t launch_f32(const ClashArgs& args, int threads, size_t smem, i
         }
         cudaEventRecord(g_ev0, s);
     }
-    clash_f32_kernel<TB><<<grid, threads, smem, s>>>(args);
+    clash_f32_kernel<TB, VAR><<<grid, threads, smem, s>>>(args);
     e = cudaGetLastError();
     if (g_time_on) {
         cudaEventRecord(g_ev1, s);
         g_ev_pending = true;
     }
     return e;
+}
+
+template <int TB>
+static cudaError_t launch_f32(const ClashArgs& args, int threads, size_t smem, int grid,
+                              cudaStream_t s) {
+    static int var = -1;
+    if (var < 0) {
+        const char* v = getenv("FC_CLASH_VARIANT");
+        var = v ? atoi(v) & 3 : 1;  // default: chain-major order (measured fastest on B200)
+    }
+    switch (var) {
+        case 1: return launch_f32v<TB, 1>(args, threads, smem, grid, s);
+        case 2: return launch_f32v<TB, 2>(args, threads, smem, grid, s);
+        case 3: return launch_f32v<TB, 3>(args, threads, smem, grid, s);
+        default: return launch_f32v<TB, 0>(args, threads, smem, grid, s);
+    }
 }
 
 }  // namespace fc
@@ -420,6 +479,7 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     if (n_poses == 0) return FC_OK;
     FC_REQUIRE(a_coords && b_coords && xf && status, "fc_clash_screen_dev: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
+    const int sms = sm_count();  // also configures the stream-ordered memory pool on first use
     ClashGeom g = choose_geom(n_b);
     FC_REQUIRE(g.tb > 0, "fc_clash_screen_dev: fragment B too large (%d atoms)", n_b);
     const int n_a_pad = (n_a + 1) / 2 * 2;
@@ -427,11 +487,11 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     if (!tiles) n_tiles = (n_poses + g.poses - 1) / g.poses;
     FC_REQUIRE(n_tiles > 0, "fc_clash_screen_dev: empty tile list");
 
-    size_t smem = (size_t)n_a_pad * 32 + (size_t)n_b_pad * 16 + (size_t)g.poses * 4;
+    size_t smem = (size_t)n_a_pad * 16 + (size_t)n_b_pad * 16 + (size_t)g.poses * 4;
     FC_REQUIRE(smem <= 227 * 1024, "fc_clash_screen_dev: fragments need %zu B of shared memory", smem);
 
     // stream-ordered scratch
-    size_t a_bytes = (size_t)n_conf_a * n_a_pad * 32, b_bytes = (size_t)n_conf_b * n_b_pad * 16;
+    size_t a_bytes = (size_t)n_conf_a * n_a_pad * 16, b_bytes = (size_t)n_conf_b * n_b_pad * 16;
     size_t off_a = 0, off_b = off_a + a_bytes, off_ra = off_b + b_bytes;
     size_t off_rb = off_ra + (size_t)n_conf_a * 4, off_cnt = (off_rb + (size_t)n_conf_b * 4 + 15) / 16 * 16;
     size_t off_list = off_cnt + 16;
@@ -465,10 +525,9 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     a.unc_count = (int*)(scratch + off_cnt);
     a.unc_list = (UncEntry*)(scratch + off_list);
 
-    int sms = sm_count();
     // persistent grid: resident CTAs per SM follow from the register/thread budget
-    int ctas_per_sm = 2048 / g.threads;
-    if (ctas_per_sm > 4) ctas_per_sm = 4;
+    int ctas_per_sm = tb_max_threads(g.tb) / g.threads;
+    if (ctas_per_sm > 8) ctas_per_sm = 8;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     long long grid_ll = (long long)sms * ctas_per_sm;
     if (grid_ll > n_tiles) grid_ll = n_tiles;
@@ -481,8 +540,11 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
         case 8: e = launch_f32<8>(a, g.threads, smem, grid, s); break;
         case 10: e = launch_f32<10>(a, g.threads, smem, grid, s); break;
         case 12: e = launch_f32<12>(a, g.threads, smem, grid, s); break;
-        case 14: e = launch_f32<14>(a, g.threads, smem, grid, s); break;
-        default: e = launch_f32<16>(a, g.threads, smem, grid, s); break;
+        case 15: e = launch_f32<15>(a, g.threads, smem, grid, s); break;
+        case 16: e = launch_f32<16>(a, g.threads, smem, grid, s); break;
+        case 20: e = launch_f32<20>(a, g.threads, smem, grid, s); break;
+        case 25: e = launch_f32<25>(a, g.threads, smem, grid, s); break;
+        default: e = launch_f32<30>(a, g.threads, smem, grid, s); break;
     }
     if (e != cudaSuccess) {
         cudaFreeAsync(scratch, s);

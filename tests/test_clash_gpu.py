@@ -83,7 +83,7 @@ def test_adversarial_near_threshold(gpu):
     base = synthetic.sweep_poses(rng, a, b, 3000, shell=(2.0, 6.0), dtype=np.float64)
     _, dmin, _ = port.clash_batch(a, b, base, thresh=thr)
     out = []
-    deltas = [0.0, 1e-7, -1e-7, 1e-6, -1e-6, 1e-5, -1e-5, 3e-4, -3e-4]
+    deltas = [0.0, 1e-7, -1e-7, 5e-7, -5e-7, 1e-5, -1e-5, 3e-4, -3e-4]
     k = 0
     for p in np.flatnonzero(dmin > thr + 0.2)[:600]:
         placed = port.place(b, base[p])
@@ -100,7 +100,7 @@ def test_adversarial_near_threshold(gpu):
     gap = np.abs(dmin2 - thr)
     far = gap > 1e-9  # beyond double rounding noise the decision must agree
     assert np.array_equal(res.mask[far], mask[far])
-    near = gap <= NEAR_EPS
+    near = gap <= 0.9 * NEAR_EPS
     assert near.sum() > 100
     assert set(np.flatnonzero(near)) <= set(res.near_idx.tolist())
     assert np.all(res.status[np.flatnonzero(near)] & STATUS_NEAR)
