@@ -21,8 +21,46 @@ c_i64p = C.POINTER(C.c_int64)
 c_u8p = C.POINTER(C.c_uint8)
 VP = C.c_void_p
 
+
+
+class Tie(C.Structure):
+    """struct fc_tie"""
+
+    _fields_ = [("a", C.c_int64), ("b", C.c_int64), ("value", C.c_double), ("kind", C.c_int32),
+                ("decision", C.c_int32)]
+
+
+class StringProblemC(C.Structure):
+    """struct fc_string_problem"""
+
+    _fields_ = [
+        ("coords1", VP), ("n_conf1", C.c_int32), ("n_atoms1", C.c_int32),
+        ("coords2", VP), ("n_conf2", C.c_int32), ("n_atoms2", C.c_int32),
+        ("centers1", VP), ("vecs1", VP), ("k1", C.c_int32),
+        ("centers2", VP), ("vecs2", VP), ("k2", C.c_int32),
+        ("angles", VP), ("n_angles", C.c_int32),
+        ("quadruplets", VP), ("n_quads", C.c_int32),
+        ("thresh", C.c_double), ("max_clashes", C.c_int32), ("rot_handedness", C.c_int32),
+        ("tfd_thresh", C.c_double),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/firecode_b200.h declares
 SIGNATURES = {
+    "fc_result_free": (None, [VP]),
+    "fc_result_counts": (C.c_int, [VP, c_i64p]),
+    "fc_result_status": (C.c_int, [VP, VP]),
+    "fc_result_survivors": (C.c_int, [VP, VP]),
+    "fc_result_fingerprints": (C.c_int, [VP, VP]),
+    "fc_result_kept_indices": (C.c_int, [VP, VP]),
+    "fc_result_kept_coords": (C.c_int, [VP, VP]),
+    "fc_result_constrained": (C.c_int, [VP, VP]),
+    "fc_result_ties": (C.c_int64, [VP, VP, C.c_int64]),
+    "fc_string_n_poses": (C.c_int64, [VP]),
+    "fc_string_screen": (C.c_int, [VP, C.POINTER(VP)]),
+    "fc_string_stage1": (C.c_int, [VP, C.c_int64, C.c_int64, C.POINTER(VP)]),
+    "fc_tfd_keepfirst": (C.c_int, [VP, VP, C.c_int64, C.c_int32, C.c_double, VP, VP, C.c_int64, c_i64p]),
+    "fc_string_materialize": (C.c_int, [VP, VP, C.c_int64, VP]),
     "fc_last_error": (C.c_char_p, []),
     "fc_version": (C.c_int, []),
     "fc_device_count": (C.c_int, []),

@@ -45,8 +45,7 @@ static double tb_efficiency(int tb) {
 }
 static int tb_max_threads(int tb) {  // register budget: 65536 / (registers per thread)
     if (tb >= 25) return 256;
-    if (tb >= 20) return 320;
-    if (tb >= 15) return 448;
+    if (tb >= 20) return 384;
     return 512;
 }
 
@@ -81,7 +80,9 @@ static ClashGeom choose_geom(int n_b) {
         double fill = warps >= 8.0 ? 1.0 : warps / 8.0;
         // small penalty for very large CTAs (barrier + prologue are not overlapped inside one CTA)
         double size_pen = threads > 160 ? 0.97 : 1.0;
-        double score = util * fill * size_pen;
+        // warps spread evenly over the four SM sub-partitions only in multiples of four
+        double balance = ((int)warps % 4 == 0) ? 1.0 : 0.85;
+        double score = util * fill * size_pen * balance;
         if (score > best_score + 1e-9) {
             best_score = score;
             best.poses = p;
@@ -167,7 +168,7 @@ struct ClashArgs {
 
 template <int TB>
 struct ClashLaunch {
-    static constexpr int kMaxThreads = TB >= 25 ? 256 : (TB >= 20 ? 320 : (TB >= 15 ? 448 : 512));
+    static constexpr int kMaxThreads = TB >= 25 ? 256 : (TB >= 20 ? 384 : 512);
 };
 
 __device__ __forceinline__ f32x2 fma2v(f32x2 a, f32x2 b, f32x2 c) {  // volatile: keeps program order

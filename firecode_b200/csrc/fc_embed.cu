@@ -1,0 +1,688 @@
+// firecode_b200 -- candidate-pose generation and the in-loop similarity filters of the embeds.
+//
+// String embed  (reference: firecode/embeds.py:51-158):
+//   tuple (c1, c2, ai1, ai2, angle) -> rigid transform of molecule 2 (string_xf_kernel, FP64)
+//   -> clash screen (fc_clash.cu) -> order-preserving compaction of the survivors
+//   -> torsion fingerprints of the survivors (tfd_fingerprint_kernel; torsion_module.py:1070-1076)
+//   -> keep-first sweep against ALL earlier accepted poses (embeds.py:59-84: the "LRU" cache never
+//      evicts), blocked so that every (candidate, accepted) pair is evaluated
+//      exactly once on the GPU and the order of acceptance is the reference's
+//   -> materialisation of the kept poses only (get_embed, embeds.py:808-817).
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "fc_embed.cuh"
+
+namespace fc {
+
+// ---------------------------------------------------------------------------------------------
+// compaction
+// ---------------------------------------------------------------------------------------------
+struct PassPred {
+    const uint8_t* status;
+    long long base;
+    __host__ __device__ bool operator()(long long i) const { return status[i - base] & FC_STATUS_PASS; }
+};
+
+int compact_pass(const uint8_t* status, long long n, long long base, long long* out_idx, int* out_count,
+                 cudaStream_t s) {
+    thrust::counting_iterator<long long> it(base);
+    PassPred pred{status, base};
+    size_t tmp_bytes = 0;
+    FC_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, it, out_idx, out_count, (int)n, pred, s));
+    void* tmp = nullptr;
+    FC_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, s));
+    cudaError_t e = cub::DeviceSelect::If(tmp, tmp_bytes, it, out_idx, out_count, (int)n, pred, s);
+    cudaFreeAsync(tmp, s);
+    FC_CUDA(e);
+    return FC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// string embed: tuple -> transform
+// ---------------------------------------------------------------------------------------------
+struct StringDev {
+    const double *coords1, *coords2;    // (C1,N1,3), (C2,N2,3)
+    const double *cen1, *vec1;          // (C1,K1,3)
+    const double *cen2, *vec2;          // (C2,K2,3)
+    const double* angles;               // (A)
+    int c1, n1, c2, n2, k1, k2, na;
+    int handed;
+};
+
+__device__ __forceinline__ void string_decode(const StringDev& p, long long pose, int& c1, int& c2, int& a1,
+                                              int& a2, int& ai) {
+    // cartesian_product order: first index fastest for conformers and centres
+    long long per_conf = (long long)p.k1 * p.k2 * p.na;
+    long long ci = pose / per_conf;
+    int rest = (int)(pose - ci * per_conf);
+    int ki = rest / p.na;
+    ai = rest - ki * p.na;
+    c1 = (int)(ci % p.c1);
+    c2 = (int)(ci / p.c1);
+    a1 = ki % p.k1;
+    a2 = ki / p.k1;
+}
+
+// embeds.py:121-135
+__device__ __forceinline__ void string_transform(const StringDev& p, int c1, int c2, int a1, int a2, int ai,
+                                                 M3& rot, double* t) {
+    const double* p1 = p.cen1 + ((size_t)c1 * p.k1 + a1) * 3;
+    const double* p2 = p.cen2 + ((size_t)c2 * p.k2 + a2) * 3;
+    const double* ref_vec = p.vec1 + ((size_t)c1 * p.k1 + a1) * 3;
+    const double* mol_vec = p.vec2 + ((size_t)c2 * p.k2 + a2) * 3;
+    double neg_ref[3] = {-ref_vec[0], -ref_vec[1], -ref_vec[2]};
+    rot = rot_vec_to_vec(mol_vec, neg_ref, p.handed);
+    double angle = p.angles[ai];
+    if (angle != 0.0) {
+        M3 delta = rot_from_pointer(ref_vec, angle, p.handed);
+        rot = m3_mul(delta, rot);
+    }
+    double rp[3];
+    m3_apply(rot, p2, rp);
+    t[0] = p1[0] - rp[0];
+    t[1] = p1[1] - rp[1];
+    t[2] = p1[2] - rp[2];
+}
+
+__global__ void string_xf_kernel(StringDev p, long long lo, long long n, double* __restrict__ xf) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c1, c2, a1, a2, ai;
+    string_decode(p, lo + i, c1, c2, a1, a2, ai);
+    M3 rot;
+    double t[3];
+    string_transform(p, c1, c2, a1, a2, ai, rot, t);
+    double* o = xf + i * 12;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k] = rot.m[k];
+    o[9] = t[0];
+    o[10] = t[1];
+    o[11] = t[2];
+}
+
+// position of atom `atom` (cumulative numbering) of the pose with transform xf
+__device__ __forceinline__ void string_atom(const StringDev& p, int c1, int c2, const double* xf, int atom,
+                                            double* out) {
+    if (atom < p.n1) {
+        const double* a = p.coords1 + ((size_t)c1 * p.n1 + atom) * 3;
+        out[0] = a[0]; out[1] = a[1]; out[2] = a[2];
+    } else {
+        const double* b = p.coords2 + ((size_t)c2 * p.n2 + (atom - p.n1)) * 3;
+        // (R @ X.T).T + t  (embeds.py:815-817)
+        out[0] = (xf[0] * b[0] + xf[1] * b[1] + xf[2] * b[2]) + xf[9];
+        out[1] = (xf[3] * b[0] + xf[4] * b[1] + xf[5] * b[2]) + xf[10];
+        out[2] = (xf[6] * b[0] + xf[7] * b[1] + xf[8] * b[2]) + xf[11];
+    }
+}
+
+// torsion fingerprints of the survivors: one thread per (survivor, quadruplet)
+__global__ void tfd_fingerprint_kernel(StringDev p, const long long* __restrict__ surv, int n_surv, long long lo,
+                                       const double* __restrict__ xf, const long long* __restrict__ quads, int nq,
+                                       double* __restrict__ fp) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)n_surv * nq) return;
+    int s = (int)(i / nq), q = (int)(i - (long long)s * nq);
+    long long pose = surv[s];
+    int c1, c2, a1, a2, ai;
+    string_decode(p, pose, c1, c2, a1, a2, ai);
+    const double* x = xf + (pose - lo) * 12;
+    double pt[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) string_atom(p, c1, c2, x, (int)quads[4 * q + k], pt[k]);
+    fp[i] = dihedral_deg(pt[0], pt[1], pt[2], pt[3]);
+}
+
+__global__ void string_materialize_kernel(StringDev p, const long long* __restrict__ kept, int n_kept,
+                                          double* __restrict__ out) {
+    int k = blockIdx.x;
+    if (k >= n_kept) return;
+    long long pose = kept[k];
+    int c1, c2, a1, a2, ai;
+    string_decode(p, pose, c1, c2, a1, a2, ai);
+    __shared__ double xf[12];
+    if (threadIdx.x == 0) {
+        M3 rot;
+        double t[3];
+        string_transform(p, c1, c2, a1, a2, ai, rot, t);
+        for (int j = 0; j < 9; ++j) xf[j] = rot.m[j];
+        xf[9] = t[0]; xf[10] = t[1]; xf[11] = t[2];
+    }
+    __syncthreads();
+    int n_tot = p.n1 + p.n2;
+    double* o = out + (size_t)k * n_tot * 3;
+    for (int a = threadIdx.x; a < n_tot; a += blockDim.x) {
+        double v[3];
+        string_atom(p, c1, c2, xf, a, v);
+        o[3 * a] = v[0];
+        o[3 * a + 1] = v[1];
+        o[3 * a + 2] = v[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TFD keep-first sweep (torsion_module.py:1056-1067 + embeds.py:59-84)
+// ---------------------------------------------------------------------------------------------
+struct TfdArgs {
+    const double* fp;        // (n, q)
+    const long long* label;  // (n) pose index of each row (for the tie list) or null
+    int q;
+    double thr, eps;
+    int* flag;   // (n) 1 = rejected
+    int* acc;    // accepted rows, in order
+    int* n_acc;
+    TieRecord* ties;
+    int* n_ties;
+    int tie_cap;
+};
+
+// similar <=> sum_k wrap(|fa_k - fb_k|) < thr ; near-threshold sums are listed
+__device__ __forceinline__ bool tfd_similar(const TfdArgs& a, int row_new, int row_ref) {
+    const double* x = a.fp + (size_t)row_new * a.q;
+    const double* y = a.fp + (size_t)row_ref * a.q;
+    double sum = 0.0;
+    const double stop = a.thr + a.eps;
+    for (int k = 0; k < a.q; ++k) {
+        double d = fabs(x[k] - y[k]);
+        d = fabs(d - (d > 180.0 ? 360.0 : 0.0));
+        sum += d;
+        if (sum > stop) return false;  // partial sums only grow: cannot come back under thr + eps
+    }
+    bool sim = sum < a.thr;
+    if (fabs(sum - a.thr) <= a.eps && a.ties) {
+        int slot = atomicAdd(a.n_ties, 1);
+        if (slot < a.tie_cap) {
+            TieRecord r;
+            r.a = a.label ? a.label[row_new] : row_new;
+            r.b = a.label ? a.label[row_ref] : row_ref;
+            r.value = sum;
+            r.kind = FC_TIE_TFD;
+            r.decision = sim ? 1 : 0;
+            a.ties[slot] = r;
+        }
+    }
+    return sim;
+}
+
+// candidates [b0, b1) against every row accepted before this block
+__global__ void __launch_bounds__(256) tfd_vs_accepted_kernel(TfdArgs a, int b0, int b1) {
+    const int n_acc = *a.n_acc;
+    const long long total = (long long)(b1 - b0) * n_acc;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int cand = b0 + (int)(i / n_acc);
+        int ref = a.acc[(int)(i % n_acc)];
+        if (tfd_similar(a, cand, ref)) a.flag[cand] = 1;
+    }
+}
+
+// ordered resolution inside the block: one CTA, row b0 + t belongs to thread t
+__global__ void __launch_bounds__(256) tfd_block_resolve_kernel(TfdArgs a, int b0, int b1) {
+    __shared__ int s_flag[256];
+    const int t = threadIdx.x;
+    const int row = b0 + t;
+    const bool valid = row < b1;
+    s_flag[t] = valid ? a.flag[row] : 1;
+    __syncthreads();
+    int n_acc = *a.n_acc;
+    for (int i = 0; i < b1 - b0; ++i) {
+        if (s_flag[i] == 0) {  // uniform: row b0 + i is accepted
+            if (t == 0) a.acc[n_acc] = b0 + i;
+            ++n_acc;
+            if (valid && t > i && s_flag[t] == 0) {
+                if (tfd_similar(a, row, b0 + i)) s_flag[t] = 1;
+            }
+        }
+        __syncthreads();
+    }
+    if (valid) a.flag[row] = s_flag[t];
+    if (t == 0) *a.n_acc = n_acc;
+}
+
+int tfd_keepfirst_dev(const double* fp, const long long* label, int n, int q, double thr, double eps, int* flag,
+                      int* acc, int* n_acc, TieRecord* ties, int* n_ties, int tie_cap, cudaStream_t s) {
+    if (n == 0) return FC_OK;
+    FC_CUDA(cudaMemsetAsync(flag, 0, (size_t)n * sizeof(int), s));
+    FC_CUDA(cudaMemsetAsync(n_acc, 0, sizeof(int), s));
+    TfdArgs a{fp, label, q, thr, eps, flag, acc, n_acc, ties, n_ties, tie_cap};
+    const int B = 256;
+    const int grid = sm_count() * 8;
+    for (int b0 = 0; b0 < n; b0 += B) {
+        int b1 = std::min(n, b0 + B);
+        if (b0 > 0) tfd_vs_accepted_kernel<<<grid, 256, 0, s>>>(a, b0, b1);
+        tfd_block_resolve_kernel<<<1, 256, 0, s>>>(a, b0, b1);
+    }
+    FC_CUDA(cudaGetLastError());
+    return FC_OK;
+}
+
+}  // namespace fc
+
+using namespace fc;
+
+// ---------------------------------------------------------------------------------------------
+// result object
+// ---------------------------------------------------------------------------------------------
+struct fc_result {
+    int64_t n_poses = 0, n_clash_pass = 0, n_rechecked = 0, n_kept = 0, n_atoms = 0, n_surv = 0, n_quads = 0;
+    std::vector<uint8_t> status;         // per screened pose
+    std::vector<int64_t> survivors;      // clash survivors (absolute pose index)
+    std::vector<double> fingerprints;    // (n_surv, n_quads), stage-1 results only
+    std::vector<int64_t> kept;           // absolute pose index, reference order
+    std::vector<double> coords;          // (n_kept, n_atoms, 3)
+    std::vector<int32_t> constrained;    // (n_kept, n_pairs, 2)
+    int n_pairs = 0;
+    std::vector<fc_tie> ties;
+    int64_t ties_total = 0;
+};
+
+extern "C" void fc_result_free(fc_result* r) { delete r; }
+extern "C" int fc_result_counts(const fc_result* r, int64_t* out8) {
+    FC_REQUIRE(r && out8, "fc_result_counts: null pointer");
+    out8[0] = r->n_poses;
+    out8[1] = r->n_clash_pass;
+    out8[2] = r->n_rechecked;
+    out8[3] = r->n_kept;
+    out8[4] = r->ties_total;
+    out8[5] = r->n_atoms;
+    out8[6] = r->n_surv;
+    out8[7] = r->n_quads;
+    return FC_OK;
+}
+#define FC_COPY_OUT(vec, out)                                  \
+    do {                                                       \
+        FC_REQUIRE(r, "null result");                          \
+        if (!(vec).empty()) {                                  \
+            FC_REQUIRE(out, "null output pointer");            \
+            memcpy(out, (vec).data(), (vec).size() * sizeof((vec)[0])); \
+        }                                                      \
+        return FC_OK;                                          \
+    } while (0)
+extern "C" int fc_result_status(const fc_result* r, uint8_t* out) { FC_COPY_OUT(r->status, out); }
+extern "C" int fc_result_survivors(const fc_result* r, int64_t* out) { FC_COPY_OUT(r->survivors, out); }
+extern "C" int fc_result_fingerprints(const fc_result* r, double* out) { FC_COPY_OUT(r->fingerprints, out); }
+extern "C" int fc_result_kept_indices(const fc_result* r, int64_t* out) { FC_COPY_OUT(r->kept, out); }
+extern "C" int fc_result_kept_coords(const fc_result* r, double* out) { FC_COPY_OUT(r->coords, out); }
+extern "C" int fc_result_constrained(const fc_result* r, int32_t* out) { FC_COPY_OUT(r->constrained, out); }
+extern "C" int64_t fc_result_ties(const fc_result* r, fc_tie* out, int64_t cap) {
+    if (!r) return -1;
+    int64_t n = std::min<int64_t>(cap, (int64_t)r->ties.size());
+    if (n > 0 && out) memcpy(out, r->ties.data(), (size_t)n * sizeof(fc_tie));
+    return (int64_t)r->ties.size();
+}
+
+// ---------------------------------------------------------------------------------------------
+// string embed driver
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct StringCtx {
+    cudaStream_t s = nullptr;
+    DevBuf<double> coords1, coords2, cen1, vec1, cen2, vec2, angles;
+    DevBuf<long long> quads;
+    StringDev dev{};
+    ~StringCtx() {
+        // buffers release on the stream before it is destroyed
+        coords1.release(); coords2.release(); cen1.release(); vec1.release(); cen2.release();
+        vec2.release(); angles.release(); quads.release();
+        if (s) {
+            cudaStreamSynchronize(s);
+            cudaStreamDestroy(s);
+        }
+    }
+};
+
+int upload(DevBuf<double>& b, const double* src, size_t n, cudaStream_t s) {
+    FC_CUDA(b.alloc(n, s));
+    if (n) FC_CUDA(cudaMemcpyAsync(b.p, src, n * 8, cudaMemcpyHostToDevice, s));
+    return FC_OK;
+}
+
+int string_ctx_init(StringCtx& c, const fc_string_problem* p) {
+    FC_REQUIRE(p, "null problem");
+    FC_REQUIRE(p->n_conf1 > 0 && p->n_conf2 > 0 && p->n_atoms1 > 0 && p->n_atoms2 > 0, "empty ensemble");
+    FC_REQUIRE(p->k1 > 0 && p->k2 > 0 && p->n_angles > 0, "no orbital centres / angles");
+    FC_REQUIRE(p->coords1 && p->coords2 && p->centers1 && p->centers2 && p->vecs1 && p->vecs2 && p->angles,
+               "null pointer in fc_string_problem");
+    FC_REQUIRE(p->n_quads == 0 || p->quadruplets, "null quadruplets");
+    sm_count();
+    FC_CUDA(cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking));
+    int rc;
+    if ((rc = upload(c.coords1, p->coords1, (size_t)p->n_conf1 * p->n_atoms1 * 3, c.s))) return rc;
+    if ((rc = upload(c.coords2, p->coords2, (size_t)p->n_conf2 * p->n_atoms2 * 3, c.s))) return rc;
+    if ((rc = upload(c.cen1, p->centers1, (size_t)p->n_conf1 * p->k1 * 3, c.s))) return rc;
+    if ((rc = upload(c.vec1, p->vecs1, (size_t)p->n_conf1 * p->k1 * 3, c.s))) return rc;
+    if ((rc = upload(c.cen2, p->centers2, (size_t)p->n_conf2 * p->k2 * 3, c.s))) return rc;
+    if ((rc = upload(c.vec2, p->vecs2, (size_t)p->n_conf2 * p->k2 * 3, c.s))) return rc;
+    if ((rc = upload(c.angles, p->angles, (size_t)p->n_angles, c.s))) return rc;
+    FC_CUDA(c.quads.alloc((size_t)p->n_quads * 4, c.s));
+    if (p->n_quads)
+        FC_CUDA(cudaMemcpyAsync(c.quads.p, p->quadruplets, (size_t)p->n_quads * 32, cudaMemcpyHostToDevice, c.s));
+    int n_tot = p->n_atoms1 + p->n_atoms2;
+    for (int i = 0; i < p->n_quads * 4; ++i)
+        FC_REQUIRE(p->quadruplets[i] >= 0 && p->quadruplets[i] < n_tot, "quadruplet index out of range");
+    StringDev& d = c.dev;
+    d.coords1 = c.coords1.p; d.coords2 = c.coords2.p;
+    d.cen1 = c.cen1.p; d.vec1 = c.vec1.p; d.cen2 = c.cen2.p; d.vec2 = c.vec2.p;
+    d.angles = c.angles.p;
+    d.c1 = p->n_conf1; d.n1 = p->n_atoms1; d.c2 = p->n_conf2; d.n2 = p->n_atoms2;
+    d.k1 = p->k1; d.k2 = p->k2; d.na = p->n_angles;
+    d.handed = p->rot_handedness >= 0 ? 1 : -1;
+    return FC_OK;
+}
+
+int64_t string_total(const fc_string_problem* p) {
+    return (int64_t)p->n_conf1 * p->n_conf2 * p->k1 * p->k2 * p->n_angles;
+}
+
+// tiles of the clash screen for poses [lo, hi): runs of equal conformer pair cut to tile_poses
+void string_tiles(const fc_string_problem* p, int64_t lo, int64_t hi, int tile_poses, std::vector<int32_t>& out) {
+    const int64_t per_conf = (int64_t)p->k1 * p->k2 * p->n_angles;
+    int64_t pose = lo;
+    while (pose < hi) {
+        int64_t ci = pose / per_conf;
+        int64_t run_end = std::min<int64_t>(hi, (ci + 1) * per_conf);
+        int c1 = (int)(ci % p->n_conf1), c2 = (int)(ci / p->n_conf1);
+        while (pose < run_end) {
+            int cnt = (int)std::min<int64_t>(tile_poses, run_end - pose);
+            out.push_back(c1);
+            out.push_back(c2);
+            out.push_back((int32_t)(pose - lo));
+            out.push_back(cnt);
+            pose += cnt;
+        }
+    }
+}
+
+// stage 1 on the device: transforms, clash screen, survivors, fingerprints. Leaves results on host.
+int string_stage1(StringCtx& c, const fc_string_problem* p, int64_t lo, int64_t hi, fc_result* r,
+                  DevBuf<double>* keep_xf, DevBuf<long long>* keep_surv, DevBuf<double>* keep_fp,
+                  DevBuf<TieRecord>& d_ties, DevBuf<int>& d_nties, int tie_cap) {
+    const int64_t n = hi - lo;
+    r->n_poses = n;
+    r->n_atoms = p->n_atoms1 + p->n_atoms2;
+    r->n_quads = p->n_quads;
+    if (n == 0) return FC_OK;
+    FC_REQUIRE(n < ((int64_t)1 << 31), "pose range too large for one call (%lld)", (long long)n);
+    cudaStream_t s = c.s;
+    DevBuf<double>& xf = *keep_xf;
+    FC_CUDA(xf.alloc((size_t)n * 12, s));
+    string_xf_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(c.dev, lo, n, xf.p);
+    FC_CUDA(cudaGetLastError());
+
+    std::vector<int32_t> tiles;
+    string_tiles(p, lo, hi, fc_clash_tile_poses(p->n_atoms2), tiles);
+    DevBuf<int32_t> d_tiles;
+    FC_CUDA(d_tiles.alloc(tiles.size(), s));
+    FC_CUDA(cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, s));
+    DevBuf<uint8_t> status;
+    FC_CUDA(status.alloc((size_t)n, s));
+    DevBuf<int32_t> near_count;
+    DevBuf<int64_t> near_idx;
+    DevBuf<double> near_dist;
+    const int near_cap = 1 << 16;
+    FC_CUDA(near_count.alloc(4, s));
+    FC_CUDA(near_idx.alloc(near_cap, s));
+    FC_CUDA(near_dist.alloc(near_cap, s));
+    FC_CUDA(cudaMemsetAsync(near_count.p, 0, 16, s));
+    int rc = fc_clash_screen_dev(c.coords1.p, p->n_conf1, p->n_atoms1, c.coords2.p, p->n_conf2, p->n_atoms2, xf.p,
+                                 n, d_tiles.p, (int64_t)tiles.size() / 4, p->thresh, p->max_clashes, 1, status.p,
+                                 nullptr, near_count.p, near_idx.p, near_dist.p, near_cap, lo, (void*)s);
+    if (rc) return rc;
+
+    DevBuf<long long>& surv = *keep_surv;
+    DevBuf<int> d_count;
+    FC_CUDA(surv.alloc((size_t)n, s));
+    FC_CUDA(d_count.alloc(4, s));
+    if ((rc = compact_pass(status.p, n, lo, surv.p, d_count.p, s))) return rc;
+    int n_surv = 0, n_near = 0;
+    FC_CUDA(cudaMemcpyAsync(&n_surv, d_count.p, 4, cudaMemcpyDeviceToHost, s));
+    FC_CUDA(cudaMemcpyAsync(&n_near, near_count.p, 4, cudaMemcpyDeviceToHost, s));
+    r->status.resize((size_t)n);
+    FC_CUDA(cudaMemcpyAsync(r->status.data(), status.p, (size_t)n, cudaMemcpyDeviceToHost, s));
+    FC_CUDA(cudaStreamSynchronize(s));
+    r->n_surv = n_surv;
+    r->n_clash_pass = n_surv;
+    for (uint8_t st : r->status) r->n_rechecked += (st & FC_STATUS_RECHECKED) ? 1 : 0;
+    // near-threshold clash decisions -> tie list
+    n_near = std::min(n_near, near_cap);
+    if (n_near > 0) {
+        std::vector<int64_t> idx(n_near);
+        std::vector<double> dist(n_near);
+        FC_CUDA(cudaMemcpy(idx.data(), near_idx.p, (size_t)n_near * 8, cudaMemcpyDeviceToHost));
+        FC_CUDA(cudaMemcpy(dist.data(), near_dist.p, (size_t)n_near * 8, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n_near; ++i) {
+            fc_tie t;
+            t.a = idx[i];
+            t.b = -1;
+            t.value = dist[i];
+            t.kind = FC_TIE_CLASH;
+            t.decision = (r->status[(size_t)(idx[i] - lo)] & FC_STATUS_PASS) ? 0 : 1;  // 1 = "below threshold"
+            r->ties.push_back(t);
+        }
+        r->ties_total += n_near;
+    }
+    r->survivors.resize((size_t)n_surv);
+    if (n_surv)
+        FC_CUDA(cudaMemcpyAsync(r->survivors.data(), surv.p, (size_t)n_surv * 8, cudaMemcpyDeviceToHost, s));
+    // fingerprints
+    DevBuf<double>& fp = *keep_fp;
+    FC_CUDA(fp.alloc((size_t)n_surv * std::max(1, p->n_quads), s));
+    if (n_surv && p->n_quads) {
+        long long total = (long long)n_surv * p->n_quads;
+        tfd_fingerprint_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(c.dev, surv.p, n_surv, lo, xf.p,
+                                                                               c.quads.p, p->n_quads, fp.p);
+        FC_CUDA(cudaGetLastError());
+    }
+    (void)d_ties; (void)d_nties; (void)tie_cap;
+    return FC_OK;
+}
+
+int fetch_ties(fc_result* r, DevBuf<TieRecord>& d_ties, const int* d_count, int tie_cap, cudaStream_t s) {
+    int n_ties = 0;
+    FC_CUDA(cudaMemcpyAsync(&n_ties, d_count, 4, cudaMemcpyDeviceToHost, s));
+    FC_CUDA(cudaStreamSynchronize(s));
+    r->ties_total += n_ties;
+    int n_copy = std::min(n_ties, tie_cap);
+    if (n_copy > 0) {
+        std::vector<TieRecord> tmp(n_copy);
+        FC_CUDA(cudaMemcpy(tmp.data(), d_ties.p, (size_t)n_copy * sizeof(TieRecord), cudaMemcpyDeviceToHost));
+        for (const TieRecord& t : tmp) {
+            fc_tie o;
+            o.a = t.a; o.b = t.b; o.value = t.value; o.kind = t.kind; o.decision = t.decision;
+            r->ties.push_back(o);
+        }
+    }
+    return FC_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t fc_string_n_poses(const fc_string_problem* p) { return p ? string_total(p) : -1; }
+
+extern "C" int fc_string_stage1(const fc_string_problem* p, int64_t pose_lo, int64_t pose_hi, fc_result** out) {
+    FC_REQUIRE(out, "null output");
+    *out = nullptr;
+    StringCtx c;
+    int rc = string_ctx_init(c, p);
+    if (rc) return rc;
+    int64_t total = string_total(p);
+    if (pose_hi < 0 || pose_hi > total) pose_hi = total;
+    FC_REQUIRE(pose_lo >= 0 && pose_lo <= pose_hi, "bad pose range");
+    fc_result* r = new fc_result();
+    DevBuf<double> xf, fp;
+    DevBuf<long long> surv;
+    DevBuf<TieRecord> d_ties;
+    DevBuf<int> d_nties;
+    rc = string_stage1(c, p, pose_lo, pose_hi, r, &xf, &surv, &fp, d_ties, d_nties, 0);
+    if (!rc && r->n_surv && p->n_quads) {
+        r->fingerprints.resize((size_t)r->n_surv * p->n_quads);
+        cudaError_t e = cudaMemcpyAsync(r->fingerprints.data(), fp.p, r->fingerprints.size() * 8,
+                                        cudaMemcpyDeviceToHost, c.s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "fingerprint copy", __FILE__, __LINE__);
+    }
+    if (rc) {
+        delete r;
+        return rc;
+    }
+    cudaStreamSynchronize(c.s);
+    *out = r;
+    return FC_OK;
+}
+
+// Ordered keep-first sweep on host fingerprints (the merge step every rank runs after the
+// all-gather of the survivors' fingerprints).  keep_out[i] = 1 if row i is accepted.
+extern "C" int fc_tfd_keepfirst(const double* fingerprints, const int64_t* labels, int64_t n, int32_t n_quads,
+                                double thresh, uint8_t* keep_out, fc_tie* ties_out, int64_t tie_cap,
+                                int64_t* n_ties_out) {
+    FC_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && n_quads >= 0, "fc_tfd_keepfirst: bad size");
+    if (n_ties_out) *n_ties_out = 0;
+    if (n == 0) return FC_OK;
+    FC_REQUIRE(keep_out && (fingerprints || n_quads == 0), "fc_tfd_keepfirst: null pointer");
+    sm_count();
+    cudaStream_t s;
+    FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int rc = FC_OK;
+    {
+        DevBuf<double> fp;
+        DevBuf<long long> lab;
+        DevBuf<int> flag, acc, cnt;
+        DevBuf<TieRecord> d_ties;
+        const int cap = (int)std::min<int64_t>(std::max<int64_t>(tie_cap, 1), 1 << 22);
+        cudaError_t e = fp.alloc((size_t)n * std::max(1, n_quads), s);
+        if (e == cudaSuccess) e = lab.alloc((size_t)n, s);
+        if (e == cudaSuccess) e = flag.alloc((size_t)n, s);
+        if (e == cudaSuccess) e = acc.alloc((size_t)n, s);
+        if (e == cudaSuccess) e = cnt.alloc(8, s);
+        if (e == cudaSuccess) e = d_ties.alloc((size_t)cap, s);
+        if (e == cudaSuccess && n_quads) e = cudaMemcpyAsync(fp.p, fingerprints, (size_t)n * n_quads * 8, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && labels) e = cudaMemcpyAsync(lab.p, labels, (size_t)n * 8, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(cnt.p, 0, 32, s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "fc_tfd_keepfirst setup", __FILE__, __LINE__);
+        if (!rc)
+            rc = tfd_keepfirst_dev(fp.p, labels ? lab.p : nullptr, (int)n, n_quads, thresh, FC_NEAR_EPS, flag.p, acc.p,
+                                   cnt.p, ties_out ? d_ties.p : nullptr, cnt.p + 1, cap, s);
+        if (!rc) {
+            std::vector<int> h_flag((size_t)n);
+            int h_cnt[2] = {0, 0};
+            e = cudaMemcpyAsync(h_flag.data(), flag.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(h_cnt, cnt.p, 8, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "fc_tfd_keepfirst readback", __FILE__, __LINE__);
+            if (!rc) {
+                for (int64_t i = 0; i < n; ++i) keep_out[i] = h_flag[(size_t)i] ? 0 : 1;
+                if (n_ties_out) *n_ties_out = h_cnt[1];
+                int n_copy = (int)std::min<int64_t>(std::min<int64_t>(h_cnt[1], cap), tie_cap);
+                if (n_copy > 0 && ties_out) {
+                    std::vector<TieRecord> tmp(n_copy);
+                    e = cudaMemcpy(tmp.data(), d_ties.p, (size_t)n_copy * sizeof(TieRecord), cudaMemcpyDeviceToHost);
+                    if (e != cudaSuccess) rc = cuda_fail(e, "tie copy", __FILE__, __LINE__);
+                    for (int i = 0; i < n_copy && !rc; ++i) {
+                        ties_out[i].a = tmp[i].a; ties_out[i].b = tmp[i].b; ties_out[i].value = tmp[i].value;
+                        ties_out[i].kind = tmp[i].kind; ties_out[i].decision = tmp[i].decision;
+                    }
+                }
+            }
+        }
+    }
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    return rc;
+}
+
+extern "C" int fc_string_materialize(const fc_string_problem* p, const int64_t* kept, int64_t n_kept, double* out) {
+    FC_REQUIRE(n_kept >= 0, "negative size");
+    if (n_kept == 0) return FC_OK;
+    FC_REQUIRE(kept && out, "null pointer");
+    StringCtx c;
+    int rc = string_ctx_init(c, p);
+    if (rc) return rc;
+    const int64_t total = string_total(p);
+    for (int64_t i = 0; i < n_kept; ++i) FC_REQUIRE(kept[i] >= 0 && kept[i] < total, "kept index out of range");
+    const size_t n_tot = (size_t)p->n_atoms1 + p->n_atoms2;
+    DevBuf<long long> d_kept;
+    DevBuf<double> d_out;
+    FC_CUDA(d_kept.alloc((size_t)n_kept, c.s));
+    FC_CUDA(d_out.alloc((size_t)n_kept * n_tot * 3, c.s));
+    FC_CUDA(cudaMemcpyAsync(d_kept.p, kept, (size_t)n_kept * 8, cudaMemcpyHostToDevice, c.s));
+    string_materialize_kernel<<<(unsigned)n_kept, 128, 0, c.s>>>(c.dev, d_kept.p, (int)n_kept, d_out.p);
+    FC_CUDA(cudaGetLastError());
+    FC_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n_kept * n_tot * 24, cudaMemcpyDeviceToHost, c.s));
+    FC_CUDA(cudaStreamSynchronize(c.s));
+    return FC_OK;
+}
+
+// Whole string screen on one GPU: stage 1 -> keep-first sweep -> materialisation, device resident.
+extern "C" int fc_string_screen(const fc_string_problem* p, fc_result** out) {
+    FC_REQUIRE(out, "null output");
+    *out = nullptr;
+    StringCtx c;
+    int rc = string_ctx_init(c, p);
+    if (rc) return rc;
+    const int64_t total = string_total(p);
+    fc_result* r = new fc_result();
+    DevBuf<double> xf, fp, d_coords;
+    DevBuf<long long> surv, d_kept;
+    DevBuf<TieRecord> d_ties;
+    DevBuf<int> d_cnt, flag, acc;
+    const int tie_cap = 1 << 20;
+    cudaStream_t s = c.s;
+    rc = string_stage1(c, p, 0, total, r, &xf, &surv, &fp, d_ties, d_cnt, tie_cap);
+    const int n_surv = (int)r->n_surv;
+    if (!rc && n_surv > 0) {
+        cudaError_t e = d_ties.alloc(tie_cap, s);
+        if (e == cudaSuccess) e = d_cnt.alloc(8, s);
+        if (e == cudaSuccess) e = flag.alloc(n_surv, s);
+        if (e == cudaSuccess) e = acc.alloc(n_surv, s);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt.p, 0, 32, s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "fc_string_screen alloc", __FILE__, __LINE__);
+        if (!rc)
+            rc = tfd_keepfirst_dev(fp.p, surv.p, n_surv, p->n_quads, p->tfd_thresh, FC_NEAR_EPS, flag.p, acc.p, d_cnt.p,
+                                   d_ties.p, d_cnt.p + 1, tie_cap, s);
+        int n_kept = 0;
+        if (!rc) {
+            e = cudaMemcpyAsync(&n_kept, d_cnt.p, 4, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "n_kept readback", __FILE__, __LINE__);
+        }
+        if (!rc && n_kept > 0) {
+            // accepted rows (ascending) -> absolute pose indices
+            std::vector<int> h_acc(n_kept);
+            e = cudaMemcpy(h_acc.data(), acc.p, (size_t)n_kept * 4, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = cuda_fail(e, "acc readback", __FILE__, __LINE__);
+            r->kept.resize(n_kept);
+            for (int i = 0; i < n_kept && !rc; ++i) r->kept[i] = r->survivors[(size_t)h_acc[i]];
+            const size_t n_tot = (size_t)r->n_atoms;
+            if (!rc) {
+                e = d_kept.alloc(n_kept, s);
+                if (e == cudaSuccess) e = d_coords.alloc((size_t)n_kept * n_tot * 3, s);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(d_kept.p, r->kept.data(), (size_t)n_kept * 8, cudaMemcpyHostToDevice, s);
+                if (e != cudaSuccess) rc = cuda_fail(e, "kept upload", __FILE__, __LINE__);
+            }
+            if (!rc) {
+                string_materialize_kernel<<<n_kept, 128, 0, s>>>(c.dev, d_kept.p, n_kept, d_coords.p);
+                r->coords.resize((size_t)n_kept * n_tot * 3);
+                e = cudaGetLastError();
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(r->coords.data(), d_coords.p, r->coords.size() * 8, cudaMemcpyDeviceToHost, s);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+                if (e != cudaSuccess) rc = cuda_fail(e, "materialize", __FILE__, __LINE__);
+            }
+            r->n_kept = n_kept;
+        }
+        if (!rc) rc = fetch_ties(r, d_ties, d_cnt.p + 1, tie_cap, s);
+    }
+    if (rc) {
+        delete r;
+        return rc;
+    }
+    *out = r;
+    return FC_OK;
+}

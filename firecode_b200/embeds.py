@@ -1,0 +1,183 @@
+"""Embed entry points with the reference's names and calling convention
+(firecode/embeds.py: ``fn(embedder) -> ndarray (P, N, 3)``, sets ``embedder.constrained_indices``,
+logs through ``embedder.log`` and raises ``ZeroCandidatesError`` when nothing survives).
+
+All per-pose work (transforms, clash screen, similarity filters, coordinates of the survivors)
+runs in the CUDA library through the C-ABI; this module only extracts plain arrays from the
+embedder (firecode_b200.problem) and wraps the results.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib, conventions, problem
+from .errors import ZeroCandidatesError
+
+TIE_CLASH, TIE_TFD, TIE_RMSD, TIE_MAXDEV = 1, 2, 3, 4
+
+
+def pretty_num(n) -> str:
+    if n < 1e3:
+        return str(n)
+    if n < 1e6:
+        return str(round(n / 1e3, 2)) + " k"
+    return str(round(n / 1e6, 2)) + " M"
+
+
+@dataclass
+class ScreenReport:
+    """What the GPU screen did, kept on ``embedder.b200_report`` after an embed call."""
+
+    n_poses: int = 0
+    n_clash_pass: int = 0
+    n_fp64_rechecks: int = 0
+    n_kept: int = 0
+    kept_indices: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int64))
+    status: np.ndarray | None = None
+    ties: np.ndarray | None = None  # structured array (a, b, value, kind, decision)
+    n_ties_total: int = 0
+    conventions: dict = field(default_factory=conventions.as_dict)
+
+    def forced_decisions(self):
+        """Near-threshold decisions as the key -> bool mapping oracle.port.Ties understands."""
+        out = {}
+        if self.ties is None:
+            return out
+        for t in self.ties:
+            if t["kind"] == TIE_CLASH:
+                out[("clash", int(t["a"]))] = bool(t["decision"])
+            elif t["kind"] == TIE_TFD:
+                out[("tfd", int(t["a"]), int(t["b"]))] = bool(t["decision"])
+            elif t["kind"] == TIE_RMSD:
+                out[("rmsd", int(t["a"]), int(t["b"]))] = bool(t["decision"])
+            elif t["kind"] == TIE_MAXDEV:
+                out[("maxdev", int(t["a"]), int(t["b"]))] = bool(t["decision"])
+        return out
+
+
+TIE_DTYPE = np.dtype([("a", np.int64), ("b", np.int64), ("value", np.float64), ("kind", np.int32),
+                      ("decision", np.int32)])
+
+
+def _ptr(arr):
+    return None if arr is None else arr.ctypes.data_as(C.c_void_p)
+
+
+class _Result:
+    """RAII wrapper of the opaque fc_result handle."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+        counts = np.zeros(8, dtype=np.int64)
+        _lib.check(lib.fc_result_counts(handle, counts.ctypes.data_as(_lib.c_i64p)), "fc_result_counts")
+        (self.n_poses, self.n_clash_pass, self.n_rechecked, self.n_kept, self.n_ties, self.n_atoms,
+         self.n_surv, self.n_quads) = (int(x) for x in counts)
+
+    def _get(self, fn, shape, dtype):
+        out = np.zeros(shape, dtype=dtype)
+        if out.size:
+            _lib.check(getattr(self.lib, fn)(self.handle, _ptr(out)), fn)
+        return out
+
+    def status(self):
+        return self._get("fc_result_status", (self.n_poses,), np.uint8)
+
+    def survivors(self):
+        return self._get("fc_result_survivors", (self.n_surv,), np.int64)
+
+    def fingerprints(self):
+        return self._get("fc_result_fingerprints", (self.n_surv, self.n_quads), np.float64)
+
+    def kept_indices(self):
+        return self._get("fc_result_kept_indices", (self.n_kept,), np.int64)
+
+    def kept_coords(self):
+        return self._get("fc_result_kept_coords", (self.n_kept, self.n_atoms, 3), np.float64)
+
+    def ties(self, cap=1 << 20):
+        n = min(self.n_ties, cap)
+        out = np.zeros(max(n, 1), dtype=TIE_DTYPE)
+        total = self.lib.fc_result_ties(self.handle, _ptr(out), n)
+        return out[: min(n, max(total, 0))]
+
+    def close(self):
+        if self.handle:
+            self.lib.fc_result_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        self.close()
+
+
+def _string_problem_c(prob: problem.StringProblem, max_clashes=0):
+    """ctypes struct + the arrays it points into (kept alive by the caller)."""
+    keep = {
+        "coords1": np.ascontiguousarray(prob.coords[0], dtype=np.float64),
+        "coords2": np.ascontiguousarray(prob.coords[1], dtype=np.float64),
+        "centers1": np.ascontiguousarray(prob.centers[0], dtype=np.float64),
+        "vecs1": np.ascontiguousarray(prob.vecs[0], dtype=np.float64),
+        "centers2": np.ascontiguousarray(prob.centers[1], dtype=np.float64),
+        "vecs2": np.ascontiguousarray(prob.vecs[1], dtype=np.float64),
+        "angles": np.ascontiguousarray(prob.angles, dtype=np.float64),
+        "quadruplets": np.ascontiguousarray(prob.quadruplets, dtype=np.int64).reshape(-1, 4),
+    }
+    c = _lib.StringProblemC()
+    c.coords1, c.n_conf1, c.n_atoms1 = _ptr(keep["coords1"]), keep["coords1"].shape[0], keep["coords1"].shape[1]
+    c.coords2, c.n_conf2, c.n_atoms2 = _ptr(keep["coords2"]), keep["coords2"].shape[0], keep["coords2"].shape[1]
+    c.centers1, c.vecs1, c.k1 = _ptr(keep["centers1"]), _ptr(keep["vecs1"]), keep["centers1"].shape[1]
+    c.centers2, c.vecs2, c.k2 = _ptr(keep["centers2"]), _ptr(keep["vecs2"]), keep["centers2"].shape[1]
+    c.angles, c.n_angles = _ptr(keep["angles"]), len(keep["angles"])
+    c.quadruplets, c.n_quads = _ptr(keep["quadruplets"]), len(keep["quadruplets"])
+    c.thresh, c.max_clashes = float(prob.thresh), int(max_clashes)
+    c.rot_handedness = int(conventions.ROT_HANDEDNESS)
+    c.tfd_thresh = 10.0
+    return c, keep
+
+
+def string_screen(prob: problem.StringProblem):
+    """Run the string screen on the current CUDA device. Returns (poses, ScreenReport)."""
+    lib = _lib.load(require_device=True)
+    c, keep = _string_problem_c(prob)
+    handle = C.c_void_p()
+    _lib.check(lib.fc_string_screen(C.byref(c), C.byref(handle)), "fc_string_screen")
+    res = _Result(lib, handle)
+    try:
+        report = ScreenReport(n_poses=res.n_poses, n_clash_pass=res.n_clash_pass,
+                              n_fp64_rechecks=res.n_rechecked, n_kept=res.n_kept,
+                              kept_indices=res.kept_indices(), status=res.status(), ties=res.ties(),
+                              n_ties_total=res.n_ties)
+        poses = res.kept_coords()
+    finally:
+        res.close()
+    del keep
+    return poses, report
+
+
+def string_embed(embedder):
+    """Drop-in for firecode.embeds.string_embed (embeds.py:51-158)."""
+    assert len(embedder.objects) == 2
+    embedder.log(f"\n--> Performing string embed ({pretty_num(embedder.candidates)} candidates)")
+    prob = problem.string_problem(embedder)
+    poses, report = string_screen(prob)
+    embedder.b200_report = report
+    if len(poses) == 0:
+        s = (
+            "\n--> Cyclical embed did not find any suitable disposition of molecules.\n"
+            + "    This is probably because the two molecules cannot find a correct interlocking pose.\n"
+            + "    Try expanding the conformational space with the firecode_search> operator or see the SHRINK keyword."
+        )
+        embedder.log(s, p=False)
+        raise ZeroCandidatesError(s)
+    embedder.constrained_indices = np.repeat(prob.constrained[None], len(poses), axis=0)
+    return poses
+
+
+def get_embed(mols, conf_ids):
+    """Coordinates of every molecule placed by its ``rotation`` / ``position`` (embeds.py:808-817).
+    Host-side convenience for callers that assemble one structure; the screens never call it."""
+    return np.concatenate([(np.asarray(m.rotation) @ np.asarray(m.coords[c]).T).T + np.asarray(m.position)
+                           for m, c in zip(mols, conf_ids)])

@@ -1,0 +1,84 @@
+"""Host-side helpers of the embedding screen with the reference's names and semantics
+(firecode/utils.py).  Closed-form 3-vector geometry stays on the host; the
+per-pose work runs in the CUDA library.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .errors import TriangleError
+
+
+def cartesian_product(*arrays):
+    """Rows of the cartesian product in the reference's enumeration order (utils.py:219-221):
+    numpy meshgrid 'xy' indexing, i.e. for two inputs the FIRST index varies fastest, for three
+    inputs the order is (second outermost, first, third fastest) -- SURVEY.md quirk N1."""
+    grids = np.meshgrid(*[np.asarray(a) for a in arrays])
+    return np.stack(grids, -1).reshape(-1, len(arrays))
+
+
+def rot_mat_from_pointer(pointer, angle_deg):
+    """Rotation about ``pointer`` by ``angle_deg`` degrees through a unit quaternion (x, y, z, w);
+    handedness follows firecode_b200.conventions.ROT_HANDEDNESS (prism_pruner.algebra contract)."""
+    from . import conventions
+
+    p = np.asarray(pointer, dtype=float)
+    half = conventions.ROT_HANDEDNESS * float(angle_deg) * np.pi / 360.0
+    x, y, z = p / np.linalg.norm(p) * np.sin(half)
+    w = np.cos(half)
+    return np.array([
+        [x * x - y * y - z * z + w * w, 2 * (x * y - z * w), 2 * (x * z + y * w)],
+        [2 * (x * y + z * w), -x * x + y * y - z * z + w * w, 2 * (y * z - x * w)],
+        [2 * (x * z - y * w), 2 * (y * z + x * w), -x * x - y * y + z * z + w * w],
+    ])
+
+
+def rotation_matrix_from_vectors(vec1, vec2):
+    """Rotation taking the direction of vec1 onto vec2 (utils.py:224-249): Rodrigues form
+    I + K + K^2 (1-c)/s^2; antiparallel inputs give a half turn about z, parallel the identity."""
+    vec1 = np.asarray(vec1, dtype=float)
+    vec2 = np.asarray(vec2, dtype=float)
+    assert vec1.shape == (3,) and vec2.shape == (3,)
+    a = vec1 / np.linalg.norm(vec1)
+    b = vec2 / np.linalg.norm(vec2)
+    v = np.cross(a, b)
+    s = np.linalg.norm(v)
+    if s != 0:
+        c = float(np.dot(a, b))
+        k = np.array([[0.0, -v[2], v[1]], [v[2], 0.0, -v[0]], [-v[1], v[0], 0.0]])
+        return np.eye(3) + k + k @ k * ((1 - c) / s**2)
+    if np.linalg.norm(a + b) == 0:
+        return rot_mat_from_pointer(np.array([0.0, 0.0, 1.0]), 180)
+    return np.eye(3)
+
+
+def polygonize(lengths):
+    """Start/end points of the pivot vectors of a cyclical embed (utils.py:252-312).
+    Two lengths: two centred collinear segments, second orientation flips segment 2;
+    three lengths: the triangle with its 8 vertex-order orientations."""
+    lengths = np.asarray(lengths, dtype=float)
+    assert len(lengths) in (2, 3)
+    base = np.zeros((len(lengths), 2, 3))
+    if len(lengths) == 2:
+        for i in range(2):
+            base[i, 0, 0] = -lengths[i] / 2
+            base[i, 1, 0] = +lengths[i] / 2
+        out = np.stack([base, base.copy()])
+        out[1, 1] *= -1
+        return out
+    if not all(lengths[i] < lengths[i - 1] + lengths[i - 2] for i in (0, 1, 2)):
+        raise TriangleError(f"Impossible to build a triangle with sides {lengths}")
+    l0, l1, l2 = lengths
+    x = (l0**2 - l1**2 + l2**2) / (2 * (l0**2) ** 0.5)
+    y = (l2**2 - x**2) ** 0.5
+    base[0, 1] = (l0, 0, 0)
+    base[1, 0] = (l0, 0, 0)
+    base[1, 1] = (x, y, 0)
+    base[2, 0] = (x, y, 0)
+    out = np.stack([base.copy() for _ in range(8)])
+    flips = {1: (2,), 2: (1,), 3: (1, 2), 4: (0,), 5: (0, 1), 6: (0, 2), 7: (0, 1, 2)}
+    for t, vecs in flips.items():
+        for v in vecs:
+            out[t, v] = out[t, v][::-1].copy()
+    return out

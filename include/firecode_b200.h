@@ -91,6 +91,63 @@ int fc_clash_timing(int enable, double* ms_sum, int64_t* launches);
  * ceil(n / 32) words.  This is the buffer the ranks exchange with one NCCL all-gather. */
 int fc_pack_mask_dev(const uint8_t* status, int64_t n, uint32_t* bits, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Embed screens.  Results come back in an opaque fc_result (sizes are not known in advance).
+ * ---------------------------------------------------------------------------------------------- */
+#define FC_TIE_CLASH 1  /* min distance within FC_NEAR_EPS of the clash threshold            */
+#define FC_TIE_TFD 2    /* torsion-difference sum within FC_NEAR_EPS of its threshold        */
+#define FC_TIE_RMSD 3   /* RMSD within FC_NEAR_EPS of its threshold                          */
+#define FC_TIE_MAXDEV 4 /* max deviation within FC_NEAR_EPS of its threshold                 */
+
+/* one near-threshold decision: `a` is a pose / structure index, `b` the earlier pose / structure of
+ * the pair (-1 for clash decisions), `decision` = 1 when the CUDA path evaluated value < threshold */
+typedef struct fc_tie {
+    int64_t a, b;
+    double value;
+    int32_t kind, decision;
+} fc_tie;
+
+typedef struct fc_result fc_result;
+void fc_result_free(fc_result* r);
+/* out8 = {poses screened, clash survivors, FP64 rechecks, kept, near-threshold decisions,
+ *         atoms per pose, stage-1 survivors, quadruplets} */
+int fc_result_counts(const fc_result* r, int64_t* out8);
+int fc_result_status(const fc_result* r, uint8_t* out);         /* (poses screened) FC_STATUS_* */
+int fc_result_survivors(const fc_result* r, int64_t* out);      /* (survivors) pose indices      */
+int fc_result_fingerprints(const fc_result* r, double* out);    /* (survivors, quadruplets) deg  */
+int fc_result_kept_indices(const fc_result* r, int64_t* out);   /* (kept) pose indices, in order */
+int fc_result_kept_coords(const fc_result* r, double* out);     /* (kept, atoms per pose, 3)     */
+int fc_result_constrained(const fc_result* r, int32_t* out);    /* (kept, n_pairs, 2)            */
+int64_t fc_result_ties(const fc_result* r, fc_tie* out, int64_t cap); /* returns total recorded  */
+
+/* String embed: replaces embeds.py:51-158 `string_embed(embedder)`.
+ * Pose index = enumeration order of the reference loops (conformer pairs in cartesian_product
+ * order, utils.py:219-221, then orbital-centre pairs, then angles). */
+typedef struct fc_string_problem {
+    const double* coords1;  int32_t n_conf1, n_atoms1;  /* (n_conf1, n_atoms1, 3) Hypermolecule.coords */
+    const double* coords2;  int32_t n_conf2, n_atoms2;
+    const double* centers1; const double* vecs1; int32_t k1; /* (n_conf1, k1, 3) RAtom.center / orb_vecs */
+    const double* centers2; const double* vecs2; int32_t k2;
+    const double* angles;   int32_t n_angles;               /* embedder.systematic_angles, degrees      */
+    const int64_t* quadruplets; int32_t n_quads;            /* (n_quads, 4) torsion_module.py:385-408   */
+    double thresh;          /* options.clash_thresh */
+    int32_t max_clashes;    /* 0 in the embeds (embeds.py:139-141) */
+    int32_t rot_handedness; /* +1 / -1, prism_pruner rot_mat_from_pointer convention */
+    double tfd_thresh;      /* 10 degrees, torsion_module.py:1056 */
+} fc_string_problem;
+
+int64_t fc_string_n_poses(const fc_string_problem* p);
+/* whole screen on the current device */
+int fc_string_screen(const fc_string_problem* p, fc_result** out);
+/* sharded form: (1) clash screen + torsion fingerprints of poses [pose_lo, pose_hi) on this rank,
+ * (2) after the ranks all-gathered survivors and fingerprints, the ordered keep-first sweep,
+ * (3) coordinates of the kept poses. */
+int fc_string_stage1(const fc_string_problem* p, int64_t pose_lo, int64_t pose_hi, fc_result** out);
+int fc_tfd_keepfirst(const double* fingerprints, const int64_t* labels, int64_t n, int32_t n_quads,
+                     double thresh, uint8_t* keep_out, fc_tie* ties_out, int64_t tie_cap,
+                     int64_t* n_ties_out);
+int fc_string_materialize(const fc_string_problem* p, const int64_t* kept, int64_t n_kept, double* out);
+
 /* FP32 FMA-pipe peak probe used by bench.py for the roofline denominator: runs a dependent-free
  * FFMA2 loop on every SM and returns achieved TFLOP/s (2 flop per FMA lane). */
 int fc_probe_fp32_peak(double* tflops_out, double* ms_out, void* stream);

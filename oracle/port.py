@@ -69,3 +69,138 @@ def clash_batch(frag_a, frag_b, xf, thresh=1.0, max_clashes=0, conf_a=None, conf
         dmin[s:e] = d.reshape(e - s, -1).min(axis=1)
         closest[s:e] = np.abs(d - thresh).reshape(e - s, -1).min(axis=1)
     return mask, dmin, closest
+
+
+# ------------------------------------------------------------------------------------------------
+# shared helpers (reference arithmetic, float64)
+# ------------------------------------------------------------------------------------------------
+def _shim():
+    import os
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import prism_pruner.algebra as alg
+    import prism_pruner.rmsd as rmsd
+
+    return alg, rmsd
+
+
+def rotation_matrix_from_vectors(vec1, vec2):
+    """utils.py:224-249."""
+    alg, _ = _shim()
+    a = vec1 / np.linalg.norm(vec1)
+    b = vec2 / np.linalg.norm(vec2)
+    v = np.cross(a, b)
+    if np.linalg.norm(v) != 0:
+        c = np.dot(a, b)
+        s = np.linalg.norm(v)
+        kmat = np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+        return np.eye(3) + kmat + kmat.dot(kmat) * ((1 - c) / (s**2))
+    if np.linalg.norm(a + b) == 0:
+        return alg.rot_mat_from_pointer(np.array([0, 0, 1]), 180)
+    return np.eye(3)
+
+
+def align_vec_pair(ref, tgt):
+    """algebra.py:28-49: rotation taking the two tgt vectors onto the two ref vectors."""
+    B = np.zeros((3, 3))
+    for j in range(2):
+        B += np.outer(ref[j], tgt[j])
+    u, s, vh = np.linalg.svd(B)
+    if np.linalg.det(u @ vh) < 0:
+        u[:, -1] = -u[:, -1]
+    return np.ascontiguousarray(u @ vh)
+
+
+def torsion_fingerprint(coords, quadruplets):
+    """torsion_module.py:1070-1076."""
+    alg, _ = _shim()
+    out = np.zeros(len(quadruplets))
+    for i, (i1, i2, i3, i4) in enumerate(quadruplets):
+        out[i] = alg.dihedral([coords[i1], coords[i2], coords[i3], coords[i4]])
+    return out
+
+
+def tfd_sum(tfp1, tfp2):
+    """Sum of wrapped absolute torsion differences, torsion_module.py:1056-1067."""
+    deltas = np.abs(tfp1 - tfp2)
+    deltas = np.abs(deltas - (deltas > 180) * 360)
+    return float(np.sum(deltas))
+
+
+class Ties:
+    """Near-threshold bookkeeping shared by the ports.
+
+    A decision whose value lies within ``eps`` of its threshold is recorded in ``seen`` and, when
+    ``forced`` holds an entry for the same key, takes that decision instead of its own (this is
+    how a parity test conditions the oracle on the near-threshold decisions listed by the GPU)."""
+
+    def __init__(self, eps=0.0, forced=None):
+        self.eps = eps
+        self.forced = forced or {}
+        self.seen = {}
+
+    def decide(self, key, value, threshold, op):
+        own = bool(op(value, threshold))
+        if self.eps > 0 and abs(value - threshold) <= self.eps:
+            self.seen[key] = (value, own)
+            if key in self.forced:
+                return bool(self.forced[key])
+        return own
+
+
+# ------------------------------------------------------------------------------------------------
+# string embed -- firecode/embeds.py:51-158
+# ------------------------------------------------------------------------------------------------
+def string_transform(prob, c1, c2, a1, a2, angle):
+    """Rotation / position of molecule 2 for one tuple, embeds.py:121-135."""
+    alg, _ = _shim()
+    p1, p2 = prob.centers[0][c1][a1], prob.centers[1][c2][a2]
+    ref_vec, mol_vec = prob.vecs[0][c1][a1], prob.vecs[1][c2][a2]
+    rot = rotation_matrix_from_vectors(mol_vec, -ref_vec)
+    if angle != 0:
+        rot = alg.rot_mat_from_pointer(ref_vec, angle) @ rot
+    return rot, p1 - rot @ p2
+
+
+def string_embed(prob, ties=None, want_poses=True):
+    """Reference loop of string_embed on a StringProblem (firecode_b200.problem).
+
+    Returns dict: kept (indices of accepted tuples in enumeration order), poses (P, N1+N2, 3),
+    clash_pass (bool per tuple), dmin (per tuple), ties (Ties)."""
+    import operator
+
+    ties = ties or Ties()
+    n1 = prob.coords[0].shape[1]
+    n2 = prob.coords[1].shape[1]
+    accepted_tfp, accepted_idx, poses = [], [], []
+    n = prob.n_poses
+    clash_pass = np.zeros(n, dtype=bool)
+    dmin = np.zeros(n)
+    for pose in range(n):
+        c1, c2, a1, a2, angle = prob.decode(pose)
+        rot, pos = string_transform(prob, c1, c2, a1, a2, angle)
+        structure = np.concatenate([prob.coords[0][c1], (rot @ prob.coords[1][c2].T).T + pos])
+        d = cdist(structure[n1:], structure[:n1])
+        dmin[pose] = d.min()
+        # utils.py:551 with max_clashes = 0: no pair strictly below the threshold
+        ok = not ties.decide(("clash", pose), float(d.min()), prob.thresh, operator.lt)
+        clash_pass[pose] = ok
+        if not ok:
+            continue
+        tfp = torsion_fingerprint(structure, prob.quadruplets)
+        new = True
+        for ref_pose, ref in zip(accepted_idx, accepted_tfp):  # never-evicting cache (quirk N2)
+            if ties.decide(("tfd", pose, ref_pose), tfd_sum(tfp, ref), 10.0, operator.lt):
+                new = False
+                break
+        if new:
+            accepted_tfp.append(tfp)
+            accepted_idx.append(pose)
+            if want_poses:
+                poses.append(structure)
+    return {"kept": np.array(accepted_idx, dtype=np.int64),
+            "poses": np.array(poses).reshape(len(poses), n1 + n2, 3) if want_poses else None,
+            "clash_pass": clash_pass, "dmin": dmin, "ties": ties}
