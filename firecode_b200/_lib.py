@@ -45,6 +45,22 @@ class StringProblemC(C.Structure):
     ]
 
 
+class CyclicalProblemC(C.Structure):
+    """struct fc_cyclical_problem"""
+
+    _fields_ = [
+        ("n_mols", C.c_int32),
+        ("coords", VP * 3), ("n_conf", C.c_int32 * 3), ("n_atoms", C.c_int32 * 3),
+        ("reactive", VP * 3), ("n_reactive", C.c_int32 * 3),
+        ("n_groups", C.c_int64),
+        ("group_conf", VP), ("group_pivot", VP), ("group_mean", VP), ("group_vecs", VP),
+        ("group_dirs", VP), ("group_ids", VP), ("n_pairs", C.c_int32),
+        ("angles", VP), ("n_angles", C.c_int32),
+        ("thresh", C.c_double), ("max_clashes", C.c_int32), ("rot_handedness", C.c_int32),
+        ("rmsd_thresh", C.c_double),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/firecode_b200.h declares
 SIGNATURES = {
     "fc_result_free": (None, [VP]),
@@ -56,6 +72,7 @@ SIGNATURES = {
     "fc_result_kept_coords": (C.c_int, [VP, VP]),
     "fc_result_constrained": (C.c_int, [VP, VP]),
     "fc_result_ties": (C.c_int64, [VP, VP, C.c_int64]),
+    "fc_cyclical_screen": (C.c_int, [VP, C.POINTER(VP)]),
     "fc_string_n_poses": (C.c_int64, [VP]),
     "fc_string_screen": (C.c_int, [VP, C.POINTER(VP)]),
     "fc_string_stage1": (C.c_int, [VP, C.c_int64, C.c_int64, C.POINTER(VP)]),

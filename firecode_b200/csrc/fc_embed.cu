@@ -282,18 +282,41 @@ struct fc_result {
 };
 
 extern "C" void fc_result_free(fc_result* r) { delete r; }
-extern "C" int fc_result_counts(const fc_result* r, int64_t* out8) {
-    FC_REQUIRE(r && out8, "fc_result_counts: null pointer");
-    out8[0] = r->n_poses;
-    out8[1] = r->n_clash_pass;
-    out8[2] = r->n_rechecked;
-    out8[3] = r->n_kept;
-    out8[4] = r->ties_total;
-    out8[5] = r->n_atoms;
-    out8[6] = r->n_surv;
-    out8[7] = r->n_quads;
+extern "C" int fc_result_counts(const fc_result* r, int64_t* out10) {
+    FC_REQUIRE(r && out10, "fc_result_counts: null pointer");
+    out10[0] = r->n_poses;
+    out10[1] = r->n_clash_pass;
+    out10[2] = r->n_rechecked;
+    out10[3] = r->n_kept;
+    out10[4] = r->ties_total;
+    out10[5] = r->n_atoms;
+    out10[6] = r->n_surv;
+    out10[7] = r->n_quads;
+    out10[8] = r->n_pairs;
+    out10[9] = 0;
     return FC_OK;
 }
+
+namespace fc {
+fc_result* result_new() { return new fc_result(); }
+void result_set_cyclical(fc_result* r, int64_t n_poses, int64_t n_atoms, int64_t n_pass, std::vector<uint8_t>&& status,
+                         std::vector<int64_t>&& kept, std::vector<double>&& coords, std::vector<int32_t>&& constrained,
+                         int n_pairs, std::vector<fc_tie>&& ties, int64_t ties_total) {
+    r->n_poses = n_poses;
+    r->n_atoms = n_atoms;
+    r->n_clash_pass = n_pass;
+    r->n_surv = n_pass;
+    r->status = std::move(status);
+    for (uint8_t st : r->status) r->n_rechecked += (st & FC_STATUS_RECHECKED) ? 1 : 0;
+    r->kept = std::move(kept);
+    r->n_kept = (int64_t)r->kept.size();
+    r->coords = std::move(coords);
+    r->constrained = std::move(constrained);
+    r->n_pairs = n_pairs;
+    r->ties = std::move(ties);
+    r->ties_total = ties_total;
+}
+}  // namespace fc
 #define FC_COPY_OUT(vec, out)                                  \
     do {                                                       \
         FC_REQUIRE(r, "null result");                          \

@@ -72,10 +72,10 @@ class _Result:
 
     def __init__(self, lib, handle):
         self.lib, self.handle = lib, handle
-        counts = np.zeros(8, dtype=np.int64)
+        counts = np.zeros(10, dtype=np.int64)
         _lib.check(lib.fc_result_counts(handle, counts.ctypes.data_as(_lib.c_i64p)), "fc_result_counts")
         (self.n_poses, self.n_clash_pass, self.n_rechecked, self.n_kept, self.n_ties, self.n_atoms,
-         self.n_surv, self.n_quads) = (int(x) for x in counts)
+         self.n_surv, self.n_quads, self.n_pairs, _) = (int(x) for x in counts)
 
     def _get(self, fn, shape, dtype):
         out = np.zeros(shape, dtype=dtype)
@@ -97,6 +97,9 @@ class _Result:
 
     def kept_coords(self):
         return self._get("fc_result_kept_coords", (self.n_kept, self.n_atoms, 3), np.float64)
+
+    def constrained(self):
+        return self._get("fc_result_constrained", (self.n_kept, self.n_pairs, 2), np.int32)
 
     def ties(self, cap=1 << 20):
         n = min(self.n_ties, cap)
@@ -181,3 +184,128 @@ def get_embed(mols, conf_ids):
     Host-side convenience for callers that assemble one structure; the screens never call it."""
     return np.concatenate([(np.asarray(m.rotation) @ np.asarray(m.coords[c]).T).T + np.asarray(m.position)
                            for m, c in zip(mols, conf_ids)])
+
+
+# ------------------------------------------------------------------------------------------------
+# cyclical embed (bimolecular path)
+# ------------------------------------------------------------------------------------------------
+_SWAPS2 = ((0, 0), (0, 1))
+
+
+def _cyclical_couples(pivot_ids, v):
+    """Atom couples facing each other for orientation v (embeds.py:753-772, two molecules)."""
+    o = [list(ids)[::-1] if _SWAPS2[v][i] else list(ids) for i, ids in enumerate(pivot_ids)]
+    return [(int(o[0][0]), int(o[1][0])), (int(o[0][1]), int(o[1][1]))]
+
+
+def _pairings_ok(prob, couples):
+    """User pairings must all appear in the active arrangement (embeds.py:638-641).  An ndarray
+    ``internal_constraints`` never matches (embeds.py:820-826)."""
+    if not prob.pairings:
+        return True
+    internal = [] if prob.internal_constraints_is_array else [tuple(x) for x in prob.internal_constraints]
+    return all((tuple(pair) in couples) or (tuple(pair) in internal) for pair in prob.pairings)
+
+
+def cyclical_groups(prob: problem.CyclicalProblem):
+    """Group table of the bimolecular cyclical embed in the reference's loop order
+    (embeds.py:596-641): conformer pairs (first index fastest) x pivot pairs x 2 orientations,
+    minus pivot pairs whose norms differ by more than max_norm_delta and arrangements that miss a
+    user pairing."""
+    from .utils import cartesian_product, polygonize
+
+    assert prob.n_mols == 2
+    conf, pivot, mean, vecs, ids = [], [], [], [], []
+    n_conf = [len(c) for c in prob.coords]
+    norms_cache = [[np.linalg.norm(pv, axis=1) if len(pv) else np.zeros(0) for pv in prob.pivot_vec[m]]
+                   for m in range(2)]
+    for c0, c1 in cartesian_product(np.arange(n_conf[0]), np.arange(n_conf[1])):
+        k0, k1 = len(prob.pivot_vec[0][c0]), len(prob.pivot_vec[1][c1])
+        if k0 == 0 or k1 == 0:
+            continue
+        for p0, p1 in cartesian_product(np.arange(k0), np.arange(k1)):
+            norms = np.array([norms_cache[0][c0][p0], norms_cache[1][c1][p1]])
+            if abs(norms[0] - norms[1]) > prob.max_norm_delta:
+                continue
+            poly = polygonize(norms)
+            pid = [prob.pivot_ids[0][c0][p0], prob.pivot_ids[1][c1][p1]]
+            for v in range(2):
+                couples = _cyclical_couples(pid, v)
+                if not _pairings_ok(prob, couples):
+                    continue
+                conf.append((c0, c1))
+                pivot.append((prob.pivot_vec[0][c0][p0], prob.pivot_vec[1][c1][p1]))
+                mean.append((prob.pivot_mean[0][c0][p0], prob.pivot_mean[1][c1][p1]))
+                vecs.append(poly[v])
+                ids.append(couples)
+    g = len(conf)
+    return {
+        "conf": np.ascontiguousarray(np.array(conf, dtype=np.int32).reshape(g, 2)),
+        "pivot": np.ascontiguousarray(np.array(pivot, dtype=np.float64).reshape(g, 2, 3)),
+        "mean": np.ascontiguousarray(np.array(mean, dtype=np.float64).reshape(g, 2, 3)),
+        "vecs": np.ascontiguousarray(np.array(vecs, dtype=np.float64).reshape(g, 2, 2, 3)),
+        "dirs": np.ascontiguousarray(np.tile(np.array([[0.0, 1.0, 0.0], [0.0, -1.0, 0.0]]), (g, 1, 1))),
+        "ids": np.ascontiguousarray(np.array(ids, dtype=np.int32).reshape(g, 2, 2)),
+    }
+
+
+def cyclical_screen(prob: problem.CyclicalProblem, rmsd_thresh=1.0):
+    """Run the bimolecular cyclical screen on the current CUDA device.
+    Returns (poses, constrained_indices, ScreenReport)."""
+    lib = _lib.load(require_device=True)
+    groups = cyclical_groups(prob)
+    keep = {"coords": [np.ascontiguousarray(c, dtype=np.float64) for c in prob.coords],
+            "reactive": [np.ascontiguousarray(r, dtype=np.int64) for r in prob.reactive],
+            "angles": np.ascontiguousarray(prob.angles, dtype=np.float64).reshape(-1, 2), **groups}
+    c = _lib.CyclicalProblemC()
+    c.n_mols = 2
+    for m in range(2):
+        c.coords[m] = keep["coords"][m].ctypes.data
+        c.n_conf[m], c.n_atoms[m] = keep["coords"][m].shape[:2]
+        c.reactive[m] = keep["reactive"][m].ctypes.data
+        c.n_reactive[m] = len(keep["reactive"][m])
+    c.n_groups = len(groups["conf"])
+    c.group_conf, c.group_pivot, c.group_mean = _ptr(groups["conf"]), _ptr(groups["pivot"]), _ptr(groups["mean"])
+    c.group_vecs, c.group_dirs, c.group_ids = _ptr(groups["vecs"]), _ptr(groups["dirs"]), _ptr(groups["ids"])
+    c.n_pairs = 2
+    c.angles, c.n_angles = _ptr(keep["angles"]), len(keep["angles"])
+    c.thresh, c.max_clashes = float(prob.thresh), 0
+    c.rot_handedness = int(conventions.ROT_HANDEDNESS)
+    c.rmsd_thresh = float(rmsd_thresh)
+    handle = C.c_void_p()
+    _lib.check(lib.fc_cyclical_screen(C.byref(c), C.byref(handle)), "fc_cyclical_screen")
+    res = _Result(lib, handle)
+    try:
+        report = ScreenReport(n_poses=res.n_poses, n_clash_pass=res.n_clash_pass,
+                              n_fp64_rechecks=res.n_rechecked, n_kept=res.n_kept,
+                              kept_indices=res.kept_indices(), status=res.status(), ties=res.ties(),
+                              n_ties_total=res.n_ties)
+        poses = res.kept_coords()
+        constrained = res.constrained().astype(np.int64)
+    finally:
+        res.close()
+    del keep
+    return poses, constrained, report
+
+
+def cyclical_embed(embedder, max_norm_delta: float = 5.0):
+    """Drop-in for firecode.embeds.cyclical_embed (embeds.py:180-585) -- bimolecular systems
+    ("cyclical" and "chelotropic" embeds, embeds.py:184-185 -> 588-750)."""
+    if len(embedder.objects) != 2:
+        raise NotImplementedError(
+            "firecode_b200: the trimolecular cyclical embed (embeds.py:409-585) is a 'next' row of "
+            "the scope table and is not built yet")
+    embedder.log(f"\n--> Performing {embedder.embed} embed ({embedder.candidates} candidates)")
+    prob = problem.cyclical_problem(embedder, max_norm_delta=max_norm_delta)
+    poses, constrained, report = cyclical_screen(prob)
+    embedder.b200_report = report
+    embedder.constrained_indices = constrained
+    if len(poses) == 0:
+        s = (
+            "\n--> Cyclical embed did not find any suitable disposition of molecules.\n"
+            + "    This is probably because one molecule has two reactive centers at a great distance,\n"
+            + "    preventing the other two molecules from forming a closed, cyclical structure."
+        )
+        embedder.log(s, p=False)
+        raise ZeroCandidatesError(s)
+    return poses

@@ -109,9 +109,9 @@ typedef struct fc_tie {
 
 typedef struct fc_result fc_result;
 void fc_result_free(fc_result* r);
-/* out8 = {poses screened, clash survivors, FP64 rechecks, kept, near-threshold decisions,
- *         atoms per pose, stage-1 survivors, quadruplets} */
-int fc_result_counts(const fc_result* r, int64_t* out8);
+/* out10 = {poses screened, clash survivors, FP64 rechecks, kept, near-threshold decisions,
+ *          atoms per pose, stage-1 survivors, quadruplets, constrained pairs per pose, 0} */
+int fc_result_counts(const fc_result* r, int64_t* out10);
 int fc_result_status(const fc_result* r, uint8_t* out);         /* (poses screened) FC_STATUS_* */
 int fc_result_survivors(const fc_result* r, int64_t* out);      /* (survivors) pose indices      */
 int fc_result_fingerprints(const fc_result* r, double* out);    /* (survivors, quadruplets) deg  */
@@ -147,6 +147,31 @@ int fc_tfd_keepfirst(const double* fingerprints, const int64_t* labels, int64_t 
                      double thresh, uint8_t* keep_out, fc_tie* ties_out, int64_t tie_cap,
                      int64_t* n_ties_out);
 int fc_string_materialize(const fc_string_problem* p, const int64_t* kept, int64_t n_kept, double* out);
+
+/* Cyclical embed, bimolecular path: replaces embeds.py:588-750 `_fast_bimol_rigid_cyclical_embed`
+ * (what `cyclical_embed` runs for two molecules, embeds.py:184-185, "cyclical" and "chelotropic").
+ * A group is one (conformer pair, pivot pair, polygon orientation) combination that passed the
+ * reference's norm and pairing filters; the host enumerates groups in the reference's loop order
+ * (O(conformers x pivots) work) and the GPU expands every group into n_angles poses.
+ * Pose index = group * n_angles + angle index. */
+typedef struct fc_cyclical_problem {
+    int32_t n_mols;                       /* 2 */
+    const double* coords[3];  int32_t n_conf[3], n_atoms[3];
+    const int64_t* reactive[3]; int32_t n_reactive[3];   /* Hypermolecule.reactive_indices (1 or 2) */
+    int64_t n_groups;
+    const int32_t* group_conf;   /* (n_groups, n_mols) conformer of every molecule                 */
+    const double* group_pivot;   /* (n_groups, n_mols, 3) Pivot.pivot of the active pivot           */
+    const double* group_mean;    /* (n_groups, n_mols, 3) Pivot.meanpoint                           */
+    const double* group_vecs;    /* (n_groups, n_mols, 2, 3) polygonize start/end for orientation v */
+    const double* group_dirs;    /* (n_groups, n_mols, 3) alignment directions                      */
+    const int32_t* group_ids;    /* (n_groups, n_pairs, 2) atom couples to constrain (may be NULL)  */
+    int32_t n_pairs;
+    const double* angles; int32_t n_angles;   /* (n_angles, n_mols) embedder.systematic_angles      */
+    double thresh; int32_t max_clashes; int32_t rot_handedness;
+    double rmsd_thresh;          /* 1.0 in the embeds (embeds.py:724) */
+} fc_cyclical_problem;
+
+int fc_cyclical_screen(const fc_cyclical_problem* p, fc_result** out);
 
 /* FP32 FMA-pipe peak probe used by bench.py for the roofline denominator: runs a dependent-free
  * FFMA2 loop on every SM and returns achieved TFLOP/s (2 flop per FMA lane). */

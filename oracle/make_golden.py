@@ -1,0 +1,90 @@
+"""TEST INFRASTRUCTURE: generate tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, through oracle.loader) on its own test fixtures and on seeded synthetic embedders.
+
+    python -m oracle.make_golden
+
+Each file stores the plain-array problem (so the GPU box, which has no reference tree, can replay
+it) and the reference's outputs.  Shim conventions in force are stored alongside (PARITY UNPINNED
+for everything that goes through oracle/prism_pruner).
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import loader  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _conventions():
+    loader.install()
+    from prism_pruner import conventions
+
+    return json.dumps({k: v for k, v in vars(conventions).items() if k.isupper()})
+
+
+def pack_string_problem(prob):
+    return {
+        "coords1": prob.coords[0], "coords2": prob.coords[1], "centers1": prob.centers[0],
+        "centers2": prob.centers[1], "vecs1": prob.vecs[0], "vecs2": prob.vecs[1],
+        "angles": prob.angles, "quadruplets": prob.quadruplets, "thresh": np.float64(prob.thresh),
+        "constrained": prob.constrained,
+    }
+
+
+def pack_cyclical_problem(prob):
+    out = {"n_mols": np.int64(prob.n_mols), "angles": prob.angles, "thresh": np.float64(prob.thresh),
+           "pairings": np.array(prob.pairings, dtype=np.int64).reshape(-1, 2),
+           "internal_constraints": np.array(prob.internal_constraints, dtype=np.int64).reshape(-1, 2),
+           "internal_constraints_is_array": np.bool_(prob.internal_constraints_is_array),
+           "max_norm_delta": np.float64(prob.max_norm_delta)}
+    for m in range(prob.n_mols):
+        out[f"coords{m}"] = prob.coords[m]
+        out[f"reactive{m}"] = prob.reactive[m]
+        counts = np.array([len(p) for p in prob.pivot_vec[m]], dtype=np.int64)
+        out[f"pivot_counts{m}"] = counts
+        out[f"pivot_vec{m}"] = np.concatenate(prob.pivot_vec[m]).reshape(-1, 3)
+        out[f"pivot_mean{m}"] = np.concatenate(prob.pivot_mean[m]).reshape(-1, 3)
+        out[f"pivot_ids{m}"] = np.concatenate(prob.pivot_ids[m]).reshape(-1, 2)
+    return out
+
+
+def main():
+    loader.install()
+    from firecode.errors import ZeroCandidatesError
+
+    from firecode_b200 import problem
+
+    os.makedirs(GOLDEN, exist_ok=True)
+    conv = _conventions()
+    for name in ("embed_string", "embed_cyclical", "embed_chelotropic", "embed_trimolecular"):
+        with loader.embedder_from_dir(loader.fixture_dir(name), name + ".txt") as emb:
+            if emb.embed == "string":
+                data = pack_string_problem(problem.string_problem(emb))
+            else:
+                data = pack_cyclical_problem(problem.cyclical_problem(emb))
+            try:
+                structures, constrained = loader.run_reference_embed(emb)
+                zero = False
+            except ZeroCandidatesError:
+                n_tot = int(sum(emb.ids))
+                structures, constrained, zero = np.zeros((0, n_tot, 3)), np.zeros((0, 0, 2), dtype=int), True
+            np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), embed=np.array(emb.embed),
+                                candidates=np.int64(emb.candidates), ref_structures=structures,
+                                ref_constrained=np.asarray(constrained), zero_candidates=np.bool_(zero),
+                                conventions=np.array(conv), **data)
+            print(f"{name}: embed={emb.embed} candidates={emb.candidates} kept={len(structures)}"
+                  f"{' (ZeroCandidatesError)' if zero else ''}")
+
+
+if __name__ == "__main__":
+    main()

@@ -204,3 +204,145 @@ def string_embed(prob, ties=None, want_poses=True):
     return {"kept": np.array(accepted_idx, dtype=np.int64),
             "poses": np.array(poses).reshape(len(poses), n1 + n2, 3) if want_poses else None,
             "clash_pass": clash_pass, "dmin": dmin, "ties": ties}
+
+
+# ------------------------------------------------------------------------------------------------
+# cyclical embed, bimolecular fast path -- firecode/embeds.py:588-750
+# ------------------------------------------------------------------------------------------------
+def polygonize(lengths):
+    """utils.py:252-312 (two-segment case and triangle case)."""
+    from firecode_b200.utils import polygonize as _poly  # same closed form, pinned in tests
+
+    return _poly(lengths)
+
+
+def cyclical_reactive_indices(pivot_ids, n, n_mols):
+    """embeds.py:753-784: atom couples facing each other for orientation ``n``."""
+    def orient(i, ids):
+        return list(reversed(ids)) if swaps[n][i] else list(ids)
+
+    if n_mols == 2:
+        swaps = [(0, 0), (0, 1)]
+        o = [orient(i, ids) for i, ids in enumerate(pivot_ids)]
+        return [(int(o[0][0]), int(o[1][0])), (int(o[0][1]), int(o[1][1]))]
+    swaps = [(0, 0, 0), (0, 0, 1), (0, 1, 0), (0, 1, 1), (1, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1)]
+    o = [orient(i, ids) for i, ids in enumerate(pivot_ids)]
+    couples = [(o[0][1], o[1][0]), (o[1][1], o[2][0]), (o[2][1], o[0][0])]
+    return [tuple(sorted((int(a), int(b)))) for a, b in couples]
+
+
+def pairing_filter(prob, ids):
+    """embeds.py:473-476 / 638-641 including quirk N10 (tuple_in_collection never matches an
+    ndarray collection)."""
+    if not prob.pairings:
+        return True
+    def in_internal(pair):
+        if prob.internal_constraints_is_array:
+            return False  # list-of-lists never equals a tuple (embeds.py:820-826)
+        return tuple(pair) in [tuple(x) for x in prob.internal_constraints]
+    return all((tuple(pair) in [tuple(i) for i in ids]) or in_internal(pair) for pair in prob.pairings)
+
+
+def cyclical_molecule_transform(prob, i, conf, pivot_vec, pivot_mean, vec_pair, direction, angle):
+    """Rotation / position of molecule i for one angle, embeds.py:494-554 (= 649-709)."""
+    alg, _ = _shim()
+    start, end = vec_pair
+    reactive_coords = prob.coords[i][conf][prob.reactive[i]]
+    atomic_pivot_mean = np.mean(reactive_coords, axis=0)
+    mol_direction = pivot_mean - atomic_pivot_mean
+    if np.all(mol_direction == 0.0):
+        mol_direction = pivot_mean
+    alignment = align_vec_pair(np.array([end - start, direction]), np.array([pivot_vec, mol_direction]))
+    if len(reactive_coords) == 2:
+        axis = alignment @ (reactive_coords[0] - reactive_coords[1])
+    else:
+        axis = alignment @ pivot_vec
+    step = alg.rot_mat_from_pointer(axis, angle)
+    center = alignment @ atomic_pivot_mean
+    rotation = step @ alignment
+    pos = np.mean(vec_pair, axis=0) - alignment @ pivot_mean
+    position = center - step @ center + pos
+    return rotation, position
+
+
+def rmsd_and_max(p, q):
+    """prism_pruner.rmsd.rmsd_and_max(p, q, center=False) as called from utils.py:499."""
+    _, rmsd = _shim()
+    return rmsd.rmsd_and_max(p, q, center=False)
+
+
+def cyclical_groups_bimol(prob):
+    """Valid (conformer pair, pivot pair, orientation) groups in the reference's loop order.
+    Returns list of dicts: conf (c0, c1), piv (p0, p1), v, ids."""
+    from firecode_b200.utils import cartesian_product
+
+    groups = []
+    n_conf = [len(c) for c in prob.coords]
+    for conf_ids in cartesian_product(*[np.arange(n) for n in n_conf]):
+        counts = [len(prob.pivot_vec[m][conf_ids[m]]) for m in range(2)]
+        if min(counts) == 0:
+            continue
+        for pi in cartesian_product(*[np.arange(k) for k in counts]):
+            pv = [prob.pivot_vec[m][conf_ids[m]][pi[m]] for m in range(2)]
+            norms = np.linalg.norm(np.array(pv), axis=1)
+            if abs(norms[0] - norms[1]) > prob.max_norm_delta:  # embeds.py:624
+                continue
+            for v in range(2):
+                ids = cyclical_reactive_indices([prob.pivot_ids[m][conf_ids[m]][pi[m]] for m in range(2)], v, 2)
+                if pairing_filter(prob, ids):
+                    groups.append({"conf": tuple(int(c) for c in conf_ids), "piv": tuple(int(p) for p in pi),
+                                   "v": v, "ids": ids, "norms": norms})
+    return groups
+
+
+def cyclical_embed_bimol(prob, ties=None, rmsd_thr=1.0, want_poses=True):
+    """Reference loop of _fast_bimol_rigid_cyclical_embed on a CyclicalProblem.
+
+    Pose index = (index of the group in cyclical_groups_bimol order) * n_angles + angle index."""
+    import operator
+
+    ties = ties or Ties()
+    assert prob.n_mols == 2
+    groups = cyclical_groups_bimol(prob)
+    n_ang = len(prob.angles)
+    n0 = prob.coords[0].shape[1]
+    directions = np.array([[0, 1, 0], [0, -1, 0]])
+    kept, poses, constrained = [], [], []
+    clash_pass = np.zeros(len(groups) * n_ang, dtype=bool)
+    for g, grp in enumerate(groups):
+        c = grp["conf"]
+        vecs = polygonize(grp["norms"])[grp["v"]]
+        angular, angular_idx = [], []
+        for ai, angles in enumerate(prob.angles):
+            parts = []
+            for i in range(2):
+                rot, pos = cyclical_molecule_transform(
+                    prob, i, c[i], prob.pivot_vec[i][c[i]][grp["piv"][i]], prob.pivot_mean[i][c[i]][grp["piv"][i]],
+                    vecs[i], directions[i], angles[i])
+                parts.append((rot @ prob.coords[i][c[i]].T).T + pos)
+            structure = np.concatenate(parts)
+            pose = g * n_ang + ai
+            d = cdist(structure[n0:], structure[:n0])
+            ok = not ties.decide(("clash", pose), float(d.min()), prob.thresh, operator.lt)
+            clash_pass[pose] = ok
+            if not ok:
+                continue
+            similar = False
+            for ref_pose, ref in zip(angular_idx, angular):  # utils.py:494-504
+                r, m = rmsd_and_max(structure, ref)
+                if ties.decide(("rmsd", pose, ref_pose), r, rmsd_thr, operator.lt) and \
+                        ties.decide(("maxdev", pose, ref_pose), m, 2 * rmsd_thr, operator.lt):
+                    similar = True
+                    break
+            if not similar:
+                angular.append(structure)
+                angular_idx.append(pose)
+                kept.append(pose)
+                constrained.append(grp["ids"])
+                if want_poses:
+                    poses.append(structure)
+    n_tot = sum(c.shape[1] for c in prob.coords)
+    return {"kept": np.array(kept, dtype=np.int64), "groups": groups,
+            "poses": np.array(poses).reshape(len(poses), n_tot, 3) if want_poses else None,
+            "constrained": np.array(constrained, dtype=np.int64).reshape(len(kept), 2, 2),
+            "clash_pass": clash_pass, "ties": ties}

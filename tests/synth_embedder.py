@@ -85,15 +85,24 @@ class _Mol:
         return out
 
 
-def _pick_reactive(atoms, bonds, n, rng):
+def _pick_reactive(atoms, bonds, n, rng, coords=None):
+    """Reactive atoms on the periphery of the molecule (far from the centroid), so that embeds have
+    clash-free poses: the outermost heavy atom and, for n = 2, a heavy atom bonded to it."""
     heavy = [i for i, a in enumerate(atoms) if a != "H"]
-    deg = {i: 0 for i in range(len(atoms))}
+    nbrs = {i: [] for i in range(len(atoms))}
     for a, b in bonds:
-        deg[a] += 1
-        deg[b] += 1
-    cands = [i for i in heavy if deg[i] >= 1]
-    picks = list(rng.permutation(cands)[:n])
-    return [int(p) for p in sorted(picks)]
+        nbrs[a].append(b)
+        nbrs[b].append(a)
+    dist = np.linalg.norm(coords - coords.mean(axis=0), axis=1)
+    order = sorted(heavy, key=lambda i: -dist[i])
+    for first in order:
+        partners = [j for j in nbrs[first] if atoms[j] != "H"]
+        if n == 1:
+            return [int(first)]
+        if partners:
+            second = max(partners, key=lambda j: dist[j])
+            return sorted([int(first), int(second)])
+    raise RuntimeError("no reactive atoms found")
 
 
 def make_embedder(embed, n_conf, n_atoms, seed, n_mols=2, n_orb=2, n_reactive=1, orb_len=1.25,
@@ -105,7 +114,7 @@ def make_embedder(embed, n_conf, n_atoms, seed, n_mols=2, n_orb=2, n_reactive=1,
     mols, offset = [], 0
     for m in range(n_mols):
         atoms, coords, bonds, _ = synthetic.conformer_ensemble(rng, n_conf[m], n_atoms[m], n_torsions=4)
-        reactive = _pick_reactive(atoms, bonds, n_reactive, rng)
+        reactive = _pick_reactive(atoms, bonds, n_reactive, rng, coords[0])
         mols.append(_Mol(atoms, coords, bonds, reactive, orb_len, n_orb, rng, offset))
         offset += n_atoms[m]
     if angles is None:
