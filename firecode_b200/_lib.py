@@ -73,6 +73,9 @@ SIGNATURES = {
     "fc_result_constrained": (C.c_int, [VP, VP]),
     "fc_result_ties": (C.c_int64, [VP, VP, C.c_int64]),
     "fc_cyclical_screen": (C.c_int, [VP, C.POINTER(VP)]),
+    "fc_prune": (C.c_int, [VP, C.c_int64, C.c_int32, C.c_int32, VP, C.c_int32, VP, C.c_double, C.c_double,
+                           C.c_double, VP, C.c_double, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP,
+                           C.c_int64, c_i64p]),
     "fc_string_n_poses": (C.c_int64, [VP]),
     "fc_string_screen": (C.c_int, [VP, C.POINTER(VP)]),
     "fc_string_stage1": (C.c_int, [VP, C.c_int64, C.c_int64, C.POINTER(VP)]),

@@ -1,0 +1,491 @@
+// firecode_b200 -- ensemble similarity pruning (RMSD and moment-of-inertia flavours).
+//
+// Replaces prism_pruner.pruner.prune_by_rmsd / prune_by_moment_of_inertia as FIRECODE calls them
+// (/root/reference/firecode/embedder.py:1452,1472; ensemble.py:211,230; operators.py:613-624;
+// atropisomer_module.py:504).  prism_pruner is absent from the reference tree: the algorithm is the
+// one restated in oracle/prism_pruner/pruner.py (PARITY UNPINNED), whose in-tree
+// structural analogue is firecode/torsion_module.py:957-1043.
+//
+// Driver (host, per pass k of the K schedule): the array is cut in k contiguous chunks; inside each
+// chunk the similarity of every pair of ACTIVE structures is evaluated on the GPU into a symmetric
+// bit matrix (prune_pairs_kernel: 32x32 pair tiles, coordinates staged in shared memory, 3x3
+// covariance accumulated in FP64 registers, Jacobi eigen-solve in FP64 registers), then one CTA per
+// chunk resolves the order-dependent keep rule (prune_sweep_kernel).
+//   similar(i, j)  <=>  rmsd < max_rmsd  and  max deviation < max_dev      (heavy atoms, centred)
+//   MOI flavour    <=>  all three principal moments within max_deviation (relative to structure i)
+// Keep rules: "greedy" updates the mask in place (NMS sweep), "snapshot" reads the mask of the pass
+// start; "first" keeps the earlier structure of a similar pair, "last" the later one.
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "fc_embed.cuh"
+
+namespace fc {
+
+// ---------------------------------------------------------------------------------------------
+// per-structure preparation
+// ---------------------------------------------------------------------------------------------
+// heavy-atom coordinates centred on their mean: out (n, nh, 3); g[i] = sum |x|^2
+__global__ void prune_center_kernel(const double* __restrict__ coords, int n_atoms, const int* __restrict__ sel,
+                                    int nh, long long n, double* __restrict__ out, double* __restrict__ g) {
+    long long s = blockIdx.x;
+    if (s >= n) return;
+    const double* src = coords + (size_t)s * n_atoms * 3;
+    __shared__ double sm[3][32];
+    double acc[3] = {0, 0, 0};
+    for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+        const double* a = src + 3 * sel[k];
+        acc[0] += a[0]; acc[1] += a[1]; acc[2] += a[2];
+    }
+    for (int c = 0; c < 3; ++c) {
+        double v = acc[c];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) sm[c][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    double mean[3];
+    for (int c = 0; c < 3; ++c) {
+        double v = 0;
+        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) v += sm[c][w];
+        mean[c] = v / nh;
+    }
+    __syncthreads();
+    double gg = 0;
+    double* dst = out + (size_t)s * nh * 3;
+    for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+        const double* a = src + 3 * sel[k];
+        double x = a[0] - mean[0], y = a[1] - mean[1], z = a[2] - mean[2];
+        dst[3 * k] = x; dst[3 * k + 1] = y; dst[3 * k + 2] = z;
+        gg += x * x + y * y + z * z;
+    }
+    for (int o = 16; o > 0; o >>= 1) gg += __shfl_xor_sync(0xffffffffu, gg, o);
+    if ((threadIdx.x & 31) == 0) sm[0][threadIdx.x >> 5] = gg;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0;
+        for (int w = 0; w < (blockDim.x + 31) / 32; ++w) v += sm[0][w];
+        g[s] = v;
+    }
+}
+
+// principal moments of inertia (ascending) about the centre of mass: moi (n, 3)
+__global__ void prune_moi_kernel(const double* __restrict__ coords, const double* __restrict__ masses, int n_atoms,
+                                 long long n, double* __restrict__ moi) {
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const double* x = coords + (size_t)s * n_atoms * 3;
+    double com[3] = {0, 0, 0}, mt = 0;
+    for (int k = 0; k < n_atoms; ++k) {
+        com[0] += x[3 * k] * masses[k]; com[1] += x[3 * k + 1] * masses[k]; com[2] += x[3 * k + 2] * masses[k];
+        mt += masses[k];
+    }
+    com[0] /= mt; com[1] /= mt; com[2] /= mt;
+    double t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < n_atoms; ++k) {
+        double a = x[3 * k] - com[0], b = x[3 * k + 1] - com[1], c = x[3 * k + 2] - com[2], m = masses[k];
+        t[0] += m * (b * b + c * c); t[4] += m * (a * a + c * c); t[8] += m * (a * a + b * b);
+        t[1] -= m * a * b; t[2] -= m * a * c; t[5] -= m * b * c;
+    }
+    t[3] = t[1]; t[6] = t[2]; t[7] = t[5];
+    double w[3], v[9];
+    jacobi_eig3(t, w, v);
+    if (w[0] > w[1]) { double q = w[0]; w[0] = w[1]; w[1] = q; }
+    if (w[1] > w[2]) { double q = w[1]; w[1] = w[2]; w[2] = q; }
+    if (w[0] > w[1]) { double q = w[0]; w[0] = w[1]; w[1] = q; }
+    moi[3 * s] = w[0]; moi[3 * s + 1] = w[1]; moi[3 * s + 2] = w[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair tiles
+// ---------------------------------------------------------------------------------------------
+struct PruneTile {
+    int row0, col0;      // positions in the compacted active list
+    int chunk_begin;     // first active position of the chunk
+    int chunk_len;       // active members of the chunk
+    long long bit_off;   // word offset of the chunk's bit matrix
+};
+
+struct PruneArgs {
+    const double* xc;        // (n, nh, 3) centred heavy-atom coordinates
+    const double* g;         // (n)
+    const double* moi;       // (n, 3) or null
+    const double* energies;  // (n) or null
+    const int* active;       // compacted active list -> structure index
+    const PruneTile* tiles;
+    int nh;
+    int mode;                // 0 = rmsd, 1 = moi
+    double max_rmsd, max_dev, max_dE, moi_dev, eps;
+    unsigned* bits;
+    unsigned long long* n_eval;  // pairs fully evaluated
+    TieRecord* ties;
+    int* n_ties;
+    int tie_cap;
+};
+
+#define PR_TS 32        // structures per tile side
+#define PR_ATOMS 32     // atoms staged per step
+
+__device__ __forceinline__ void prune_set_bit(const PruneArgs& a, const PruneTile& t, int r, int c) {
+    // symmetric matrix over the chunk's active positions
+    int words = (t.chunk_len + 31) >> 5;
+    int rr = r - t.chunk_begin, cc = c - t.chunk_begin;
+    atomicOr(a.bits + t.bit_off + (long long)rr * words + (cc >> 5), 1u << (cc & 31));
+    atomicOr(a.bits + t.bit_off + (long long)cc * words + (rr >> 5), 1u << (rr & 31));
+}
+
+// 256 threads: thread (tx = column, ty) owns pairs (row ty + 8u, column tx), u = 0..3
+__global__ void __launch_bounds__(256) prune_pairs_kernel(PruneArgs a) {
+    const PruneTile t = a.tiles[blockIdx.x];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int chunk_end = t.chunk_begin + t.chunk_len;
+    const int col = t.col0 + tx;
+    const bool col_ok = col < chunk_end;
+    const int s_col = col_ok ? a.active[col] : -1;
+    int row[4], s_row[4];
+    bool pair_ok[4];
+    bool any = false;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        row[u] = t.row0 + ty + 8 * u;
+        bool ok = row[u] < chunk_end;
+        s_row[u] = ok ? a.active[row[u]] : -1;
+        pair_ok[u] = ok && col_ok && row[u] < col;  // each unordered pair once (upper triangle)
+        if (pair_ok[u] && a.energies) pair_ok[u] = fabs(a.energies[s_row[u]] - a.energies[s_col]) < a.max_dE;
+        any |= pair_ok[u];
+    }
+    if (a.mode == 1) {  // moment-of-inertia flavour: O(1) per pair
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!pair_ok[u]) continue;
+            const double* mi = a.moi + 3 * (size_t)s_row[u];
+            const double* mj = a.moi + 3 * (size_t)s_col;
+            bool sim = true;
+            for (int k = 0; k < 3; ++k) sim = sim && (fabs(mi[k] - mj[k]) / mi[k] < a.moi_dev);
+            if (sim) prune_set_bit(a, t, row[u], col);
+        }
+        return;
+    }
+    __shared__ double sR[PR_ATOMS][3][PR_TS];  // rows of the tile
+    __shared__ double sC[PR_ATOMS][3][PR_TS];  // columns of the tile
+    double h[4][9];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int e = 0; e < 9; ++e) h[u][e] = 0.0;
+    const int nh = a.nh;
+    for (int a0 = 0; a0 < nh; a0 += PR_ATOMS) {
+        const int na = min(PR_ATOMS, nh - a0);
+        __syncthreads();
+        // stage: element (structure s of the tile, atom k, coordinate c)
+        for (int e = threadIdx.x; e < PR_TS * na * 3; e += 256) {
+            int s = e / (na * 3), rem = e - s * (na * 3);
+            int k = rem / 3, c = rem - 3 * k;
+            int rpos = t.row0 + s, cpos = t.col0 + s;
+            sR[k][c][s] = rpos < chunk_end ? a.xc[((size_t)a.active[rpos] * nh + a0 + k) * 3 + c] : 0.0;
+            sC[k][c][s] = cpos < chunk_end ? a.xc[((size_t)a.active[cpos] * nh + a0 + k) * 3 + c] : 0.0;
+        }
+        __syncthreads();
+        if (!__syncthreads_or(any)) continue;
+        for (int k = 0; k < na; ++k) {
+            const double qx = sC[k][0][tx], qy = sC[k][1][tx], qz = sC[k][2][tx];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = ty + 8 * u;
+                const double px = sR[k][0][r], py = sR[k][1][r], pz = sR[k][2][r];
+                h[u][0] += px * qx; h[u][1] += px * qy; h[u][2] += px * qz;
+                h[u][3] += py * qx; h[u][4] += py * qy; h[u][5] += py * qz;
+                h[u][6] += pz * qx; h[u][7] += pz * qy; h[u][8] += pz * qz;
+            }
+        }
+    }
+    unsigned long long evals = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        if (!pair_ok[u]) continue;
+        const double e0 = a.g[s_row[u]] + a.g[s_col];
+        // cheap bound: sum of singular values <= sqrt(3) |H|_F  =>  rmsd^2 >= (e0 - 2 sqrt(3)|H|_F) / nh
+        double f2 = 0;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) f2 += h[u][e] * h[u][e];
+        const double thr2 = (a.max_rmsd + a.eps) * (a.max_rmsd + a.eps);
+        if ((e0 - 2.0 * sqrt(3.0 * f2)) / nh >= thr2) continue;
+        ++evals;
+        double sig[3];
+        M3 R = kabsch_from_cov(h[u], sig);
+        double msd = (e0 - 2.0 * (sig[0] + sig[1] + sig[2])) / nh;
+        if (msd < 0) msd = 0;
+        if (msd >= thr2) continue;
+        // the decision itself restates rmsd_and_max: rotate, difference, sum of squares, max norm
+        const double* p = a.xc + (size_t)s_row[u] * nh * 3;
+        const double* q = a.xc + (size_t)s_col * nh * 3;
+        double ss = 0, mx = 0;
+        for (int k = 0; k < nh; ++k) {
+            double x = p[3 * k], y = p[3 * k + 1], z = p[3 * k + 2];
+            double dx = (x * R.m[0] + y * R.m[3] + z * R.m[6]) - q[3 * k];
+            double dy = (x * R.m[1] + y * R.m[4] + z * R.m[7]) - q[3 * k + 1];
+            double dz = (x * R.m[2] + y * R.m[5] + z * R.m[8]) - q[3 * k + 2];
+            double d2 = dx * dx + dy * dy + dz * dz;
+            ss += d2;
+            mx = fmax(mx, d2);
+        }
+        const double rmsd = sqrt(ss / nh), maxdev = sqrt(mx);
+        const bool r_ok = rmsd < a.max_rmsd, m_ok = maxdev < a.max_dev;
+        if (a.ties) {
+            if (fabs(rmsd - a.max_rmsd) <= a.eps) {
+                int slot = atomicAdd(a.n_ties, 1);
+                if (slot < a.tie_cap) a.ties[slot] = TieRecord{s_col, s_row[u], rmsd, FC_TIE_RMSD, r_ok ? 1 : 0};
+            }
+            if (r_ok && fabs(maxdev - a.max_dev) <= a.eps) {
+                int slot = atomicAdd(a.n_ties, 1);
+                if (slot < a.tie_cap) a.ties[slot] = TieRecord{s_col, s_row[u], maxdev, FC_TIE_MAXDEV, m_ok ? 1 : 0};
+            }
+        }
+        if (r_ok && m_ok) prune_set_bit(a, t, row[u], col);
+    }
+    if (a.n_eval) {
+        for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(0xffffffffu, evals, o);
+        if (tx == 0 && evals) atomicAdd(a.n_eval, evals);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ordered resolution, one CTA per chunk
+// ---------------------------------------------------------------------------------------------
+struct PruneChunk {
+    int begin, len;        // positions in the compacted active list
+    long long bit_off;
+};
+
+// alive_out[pos] for every active position; greedy = NMS sweep, snapshot = mask of the pass start
+__global__ void __launch_bounds__(1024) prune_sweep_kernel(const PruneChunk* __restrict__ chunks,
+                                                           const unsigned* __restrict__ bits, int keep_first,
+                                                           int snapshot, unsigned char* __restrict__ alive_out) {
+    extern __shared__ unsigned s_alive[];
+    const PruneChunk c = chunks[blockIdx.x];
+    const int words = (c.len + 31) >> 5;
+    const unsigned* m = bits + c.bit_off;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) {
+        int rem = c.len - 32 * w;
+        s_alive[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+    }
+    __syncthreads();
+    if (snapshot) {
+        // position i is dropped if any position on its keeper side is similar to it
+        for (int i = threadIdx.x; i < c.len; i += blockDim.x) {
+            const unsigned* row = m + (long long)i * words;
+            bool hit = false;
+            if (keep_first) {      // keeper side = earlier positions
+                for (int w = 0; w <= (i >> 5) && !hit; ++w) {
+                    unsigned v = row[w];
+                    if (w == (i >> 5)) v &= (1u << (i & 31)) - 1u;
+                    hit = v != 0;
+                }
+            } else {               // keeper side = later positions
+                for (int w = i >> 5; w < words && !hit; ++w) {
+                    unsigned v = row[w];
+                    if (w == (i >> 5)) v &= ~((2u << (i & 31)) - 1u);
+                    hit = v != 0;
+                }
+            }
+            alive_out[c.begin + i] = hit ? 0 : 1;
+        }
+        return;
+    }
+    for (int step = 0; step < c.len; ++step) {
+        const int i = keep_first ? step : c.len - 1 - step;
+        const bool alive = (s_alive[i >> 5] >> (i & 31)) & 1u;   // uniform
+        if (alive) {
+            const unsigned* row = m + (long long)i * words;
+            for (int w = threadIdx.x; w < words; w += blockDim.x) {
+                unsigned v = row[w];
+                // only the side that i may still drop: later positions (keep-first) / earlier (keep-last)
+                if (keep_first) {
+                    if (w < (i >> 5)) v = 0;
+                    else if (w == (i >> 5)) v &= ~((2u << (i & 31)) - 1u);
+                } else {
+                    if (w > (i >> 5)) v = 0;
+                    else if (w == (i >> 5)) v &= (1u << (i & 31)) - 1u;
+                }
+                if (v) s_alive[w] &= ~v;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < c.len; i += blockDim.x) alive_out[c.begin + i] = (s_alive[i >> 5] >> (i & 31)) & 1u;
+}
+
+}  // namespace fc
+
+using namespace fc;
+
+static const int64_t kSchedule[] = {500000, 200000, 100000, 50000, 20000, 10000, 5000, 2000, 1000,
+                                    500,    200,    100,    50,    20,    10,    5,    2,    1};
+
+// mode 0: RMSD, mode 1: MOI.  `sel` = indices of the atoms used for the RMSD (heavy atoms).
+extern "C" int fc_prune(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
+                        int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
+                        const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
+                        int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
+                        int64_t tie_cap, int64_t* n_ties_out) {
+    FC_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && n_atoms > 0, "fc_prune: bad sizes");
+    if (n_ties_out) *n_ties_out = 0;
+    if (stats_out) stats_out[0] = stats_out[1] = stats_out[2] = stats_out[3] = 0;
+    if (n == 0) return FC_OK;
+    FC_REQUIRE(structures && mask_out, "fc_prune: null pointer");
+    FC_REQUIRE(mode == 0 || mode == 1, "fc_prune: unknown mode %d", mode);
+    if (mode == 0) {
+        FC_REQUIRE(sel && n_sel > 0, "fc_prune: RMSD pruning needs at least one selected atom");
+        for (int k = 0; k < n_sel; ++k) FC_REQUIRE(sel[k] >= 0 && sel[k] < n_atoms, "fc_prune: atom selection out of range");
+    } else {
+        FC_REQUIRE(masses, "fc_prune: MOI pruning needs masses");
+    }
+    sm_count();
+    cudaStream_t s;
+    FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int rc = FC_OK;
+    std::vector<uint8_t> mask((size_t)n, 1);
+    int64_t pairs_tiled = 0, passes = 0;
+    unsigned long long evals_total = 0;
+    int64_t ties_total = 0;
+    {
+        DevBuf<double> d_coords, d_xc, d_g, d_moi, d_mass, d_energy;
+        DevBuf<int> d_sel, d_active, d_nties;
+        DevBuf<unsigned> d_bits;
+        DevBuf<PruneTile> d_tiles;
+        DevBuf<PruneChunk> d_chunks;
+        DevBuf<unsigned char> d_alive;
+        DevBuf<unsigned long long> d_eval;
+        DevBuf<TieRecord> d_ties;
+        const int cap = (int)std::min<int64_t>(std::max<int64_t>(tie_cap, 1), 1 << 22);
+        cudaError_t e = cudaSuccess;
+#define PR(call) do { if (e == cudaSuccess) e = (call); } while (0)
+        PR(d_coords.alloc((size_t)n * n_atoms * 3, s));
+        PR(cudaMemcpyAsync(d_coords.p, structures, (size_t)n * n_atoms * 24, cudaMemcpyHostToDevice, s));
+        PR(d_nties.alloc(4, s));
+        PR(cudaMemsetAsync(d_nties.p, 0, 16, s));
+        PR(d_eval.alloc(2, s));
+        PR(cudaMemsetAsync(d_eval.p, 0, 16, s));
+        PR(d_ties.alloc(cap, s));
+        if (energies) {
+            PR(d_energy.alloc((size_t)n, s));
+            PR(cudaMemcpyAsync(d_energy.p, energies, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        }
+        if (mode == 0) {
+            PR(d_sel.alloc(n_sel, s));
+            PR(cudaMemcpyAsync(d_sel.p, sel, (size_t)n_sel * 4, cudaMemcpyHostToDevice, s));
+            PR(d_xc.alloc((size_t)n * n_sel * 3, s));
+            PR(d_g.alloc((size_t)n, s));
+            if (e == cudaSuccess) {
+                prune_center_kernel<<<(unsigned)n, 64, 0, s>>>(d_coords.p, n_atoms, d_sel.p, n_sel, n, d_xc.p, d_g.p);
+                e = cudaGetLastError();
+            }
+        } else {
+            PR(d_mass.alloc(n_atoms, s));
+            PR(cudaMemcpyAsync(d_mass.p, masses, (size_t)n_atoms * 8, cudaMemcpyHostToDevice, s));
+            PR(d_moi.alloc((size_t)n * 3, s));
+            if (e == cudaSuccess) {
+                prune_moi_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_coords.p, d_mass.p, n_atoms, n, d_moi.p);
+                e = cudaGetLastError();
+            }
+        }
+        PR(d_active.alloc((size_t)n, s));
+        PR(d_alive.alloc((size_t)n, s));
+        if (e != cudaSuccess) rc = cuda_fail(e, "fc_prune setup", __FILE__, __LINE__);
+
+        std::vector<int> active;
+        std::vector<PruneTile> tiles;
+        std::vector<PruneChunk> chunks;
+        std::vector<unsigned char> alive;
+        for (int64_t k : kSchedule) {
+            if (rc) break;
+            int64_t n_active = 0;
+            for (uint8_t b : mask) n_active += b;
+            if (!(k == 1 || (int64_t)min_per_chunk * k < n_active)) continue;
+            ++passes;
+            // compacted active list + chunks over the FULL array (chunk size n // k, last takes the rest)
+            active.clear();
+            chunks.clear();
+            tiles.clear();
+            const int64_t size = n / k;
+            long long bit_words = 0;
+            int max_len = 0;
+            for (int64_t c = 0; c < k; ++c) {
+                int64_t first = c * size, last = (c == k - 1) ? n : size * (c + 1);
+                int begin = (int)active.size();
+                for (int64_t i = first; i < last; ++i)
+                    if (mask[(size_t)i]) active.push_back((int)i);
+                int len = (int)active.size() - begin;
+                if (len < 2) continue;  // nothing to compare
+                PruneChunk ch{begin, len, bit_words};
+                int words = (len + 31) >> 5;
+                for (int r0 = 0; r0 < len; r0 += PR_TS)
+                    for (int c0 = r0; c0 < len; c0 += PR_TS)
+                        tiles.push_back(PruneTile{begin + r0, begin + c0, begin, len, bit_words});
+                bit_words += (long long)len * words;
+                max_len = std::max(max_len, len);
+                pairs_tiled += (int64_t)len * (len - 1) / 2;
+                chunks.push_back(ch);
+            }
+            if (chunks.empty()) continue;
+            e = d_bits.alloc((size_t)bit_words, s);
+            PR(cudaMemsetAsync(d_bits.p, 0, (size_t)bit_words * 4, s));
+            PR(d_tiles.alloc(tiles.size(), s));
+            PR(cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(PruneTile), cudaMemcpyHostToDevice, s));
+            PR(d_chunks.alloc(chunks.size(), s));
+            PR(cudaMemcpyAsync(d_chunks.p, chunks.data(), chunks.size() * sizeof(PruneChunk), cudaMemcpyHostToDevice, s));
+            PR(cudaMemcpyAsync(d_active.p, active.data(), active.size() * 4, cudaMemcpyHostToDevice, s));
+            PR(cudaMemsetAsync(d_alive.p, 1, active.size(), s));
+            if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pass setup", __FILE__, __LINE__); break; }
+            PruneArgs a{};
+            a.xc = d_xc.p; a.g = d_g.p; a.moi = d_moi.p; a.energies = energies ? d_energy.p : nullptr;
+            a.active = d_active.p; a.tiles = d_tiles.p; a.nh = n_sel; a.mode = mode;
+            a.max_rmsd = max_rmsd; a.max_dev = max_dev; a.max_dE = max_dE; a.moi_dev = moi_dev; a.eps = FC_NEAR_EPS;
+            a.bits = d_bits.p; a.n_eval = d_eval.p;
+            a.ties = ties_out ? d_ties.p : nullptr; a.n_ties = d_nties.p; a.tie_cap = cap;
+            prune_pairs_kernel<<<(unsigned)tiles.size(), 256, 0, s>>>(a);
+            size_t smem = (size_t)((max_len + 31) / 32) * 4;
+            if (smem > 48 * 1024)
+                PR(cudaFuncSetAttribute(prune_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            prune_sweep_kernel<<<(unsigned)chunks.size(), 1024, smem, s>>>(d_chunks.p, d_bits.p, keep_first ? 1 : 0,
+                                                                           snapshot ? 1 : 0, d_alive.p);
+            PR(cudaGetLastError());
+            alive.resize(active.size());
+            PR(cudaMemcpyAsync(alive.data(), d_alive.p, active.size(), cudaMemcpyDeviceToHost, s));
+            PR(cudaStreamSynchronize(s));
+            if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pass", __FILE__, __LINE__); break; }
+            for (size_t i = 0; i < active.size(); ++i)
+                if (!alive[i]) mask[(size_t)active[i]] = 0;
+        }
+        if (!rc) {
+            int n_t = 0;
+            e = cudaMemcpy(&n_t, d_nties.p, 4, cudaMemcpyDeviceToHost);
+            PR(cudaMemcpy(&evals_total, d_eval.p, 8, cudaMemcpyDeviceToHost));
+            ties_total = n_t;
+            int n_copy = (int)std::min<int64_t>(std::min<int64_t>(n_t, cap), tie_cap);
+            if (n_copy > 0 && ties_out && e == cudaSuccess) {
+                std::vector<TieRecord> tmp(n_copy);
+                e = cudaMemcpy(tmp.data(), d_ties.p, (size_t)n_copy * sizeof(TieRecord), cudaMemcpyDeviceToHost);
+                for (int i = 0; i < n_copy; ++i) {
+                    ties_out[i].a = tmp[i].a; ties_out[i].b = tmp[i].b; ties_out[i].value = tmp[i].value;
+                    ties_out[i].kind = tmp[i].kind; ties_out[i].decision = tmp[i].decision;
+                }
+            }
+            if (e != cudaSuccess) rc = cuda_fail(e, "fc_prune readback", __FILE__, __LINE__);
+        }
+#undef PR
+    }
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    if (rc) return rc;
+    memcpy(mask_out, mask.data(), (size_t)n);
+    if (n_ties_out) *n_ties_out = ties_total;
+    if (stats_out) {
+        stats_out[0] = passes;
+        stats_out[1] = pairs_tiled;               // pairs whose covariance was accumulated
+        stats_out[2] = (int64_t)evals_total;      // pairs that needed the eigen-solve
+        stats_out[3] = 0;
+    }
+    return FC_OK;
+}

@@ -135,3 +135,22 @@ def sweep_poses(rng, frag_a, frag_b, n_poses, shell=(-2.0, 4.0), dtype=np.float6
     radius = rng.uniform(base + shell[0], base + shell[1], size=(n_poses, 1))
     xf = np.concatenate([rot.reshape(n_poses, 9), direction * radius], axis=1)
     return np.ascontiguousarray(xf.astype(np.float32).astype(dtype))
+
+
+def random_rigid(rng, coords):
+    """Random rotation + translation of one structure."""
+    rot = random_rotations(rng, 1)[0]
+    return coords @ rot.T + rng.normal(scale=3.0, size=3)
+
+
+def pruning_ensemble(rng, n_struct, n_atoms, n_basins, jitter=(0.05, 0.4), n_torsions=8):
+    """C4-style ensemble: n_basins torsion-redraw conformers of one molecule, each copied with
+    Gaussian per-atom jitter (sigma drawn per copy from `jitter`) and a random rigid motion,
+    shuffled.  Returns (atoms, structures (n_struct, n_atoms, 3), basin id per structure)."""
+    atoms, basins, _, _ = conformer_ensemble(rng, n_basins, n_atoms, n_torsions=n_torsions)
+    basin_of = rng.integers(0, n_basins, size=n_struct)
+    out = np.empty((n_struct, n_atoms, 3))
+    for i, b in enumerate(basin_of):
+        sigma = rng.uniform(*jitter)
+        out[i] = random_rigid(rng, basins[b] + rng.normal(scale=sigma, size=(n_atoms, 3)))
+    return atoms, out, basin_of

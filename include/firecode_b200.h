@@ -173,6 +173,20 @@ typedef struct fc_cyclical_problem {
 
 int fc_cyclical_screen(const fc_cyclical_problem* p, fc_result** out);
 
+/* Ensemble similarity pruning: replaces prism_pruner.pruner.prune_by_rmsd (mode 0) and
+ * prune_by_moment_of_inertia (mode 1) as called at embedder.py:1452,1472; ensemble.py:211,230;
+ * operators.py:613-624; atropisomer_module.py:504.  Multi-pass chunked driver (k = 500000 ... 1,
+ * a pass runs when k == 1 or min_per_chunk * k < active structures; chunks of n / k structures).
+ *  structures (n, n_atoms, 3) f64 host;  sel (n_sel) atoms entering the RMSD (heavy atoms);
+ *  masses (n_atoms) for mode 1;  energies (n) or NULL: pairs with |dE| >= max_dE are not compared;
+ *  keep_first / snapshot: the two unpinned prism_pruner conventions;
+ *  mask_out (n) 1 = kept;  stats_out[4] = {passes, pairs tiled, pairs eigen-solved, 0}. */
+int fc_prune(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
+             int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
+             const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
+             int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
+             int64_t tie_cap, int64_t* n_ties_out);
+
 /* FP32 FMA-pipe peak probe used by bench.py for the roofline denominator: runs a dependent-free
  * FFMA2 loop on every SM and returns achieved TFLOP/s (2 flop per FMA lane). */
 int fc_probe_fp32_peak(double* tflops_out, double* ms_out, void* stream);

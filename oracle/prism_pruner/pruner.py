@@ -111,7 +111,7 @@ def _heavy_mask(atoms):
 
 
 def prune_by_rmsd(structures, atoms, max_rmsd=0.25, max_dev=None, energies=None, max_dE=0.0,
-                  debugfunction=None, logfunction=None, stats=None, **switches):
+                  debugfunction=None, logfunction=None, stats=None, ties=None, **switches):
     """Drop structures whose heavy-atom Kabsch RMSD to a kept one is < max_rmsd and whose largest
     atomic deviation is < max_dev (default 2 * max_rmsd). Returns (structures[mask], mask)."""
     structures = np.asarray(structures, dtype=float)
@@ -121,7 +121,13 @@ def prune_by_rmsd(structures, atoms, max_rmsd=0.25, max_dev=None, energies=None,
 
     def evaluate_sim(i, j):
         rmsd, maxdev = rmsd_and_max(work[i], work[j], center=True)
-        return rmsd < max_rmsd and maxdev < max_dev
+        if ties is None:
+            return rmsd < max_rmsd and maxdev < max_dev
+        # near-threshold bookkeeping for the parity tests (oracle.port.Ties): keys use (later, earlier)
+        import operator
+
+        return ties.decide(("rmsd", j, i), rmsd, max_rmsd, operator.lt) and \
+            ties.decide(("maxdev", j, i), maxdev, max_dev, operator.lt)
 
     mask = prune_mask(len(structures), evaluate_sim, energies, max_dE, stats=stats, **switches)
     if debugfunction is not None:
