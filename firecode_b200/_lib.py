@@ -76,6 +76,8 @@ SIGNATURES = {
     "fc_prune": (C.c_int, [VP, C.c_int64, C.c_int32, C.c_int32, VP, C.c_int32, VP, C.c_double, C.c_double,
                            C.c_double, VP, C.c_double, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP,
                            C.c_int64, c_i64p]),
+    "fc_torsion_scan": (C.c_int, [VP, C.c_int32, C.c_int32, VP, C.c_int32, VP, VP, C.c_int32, C.c_double,
+                                  C.c_int32, C.c_int32, C.c_int32, VP, VP, VP]),
     "fc_string_n_poses": (C.c_int64, [VP]),
     "fc_string_screen": (C.c_int, [VP, C.POINTER(VP)]),
     "fc_string_stage1": (C.c_int, [VP, C.c_int64, C.c_int64, C.POINTER(VP)]),

@@ -1,0 +1,149 @@
+// firecode_b200 -- batched rigid-subtree torsion rotation with clash filtering.
+//
+// Replaces the primitive pair used by the torsion drivers of the reference
+// (/root/reference/firecode/torsion_module.py:523-552, 813-856):
+//     new = rotate_dihedral(coords, torsion, angle, mask=mask)          [prism_pruner.utils]
+//     ok  = torsion_comp_check(new, torsion, mask, thresh)              [torsion_module.py:894-918]
+// applied to every (conformer, torsion, angle) item of a regular scan (the 36 x 10 degree schedule
+// of atropisomer_module.py:118 is one instance).  One CTA per item, all FP64:
+//   axis = sign * (x[i2] - x[i3]);  M = rot_mat_from_pointer(axis, angle);
+//   x[mask] = M (x[mask] - x[i3]) + x[i3];
+//   pass <=> #{(s, m): |x_s - x_m| < thresh, m moved, s static and not i2 / i3} <= max_clashes.
+#include "fc_embed.cuh"
+
+namespace fc {
+
+struct TorsionArgs {
+    const double* coords;        // (C, N, 3)
+    const int* torsions;         // (T, 4)
+    const unsigned char* masks;  // (T, N) 1 = atom rotates
+    const double* angles;        // (A)
+    int n_conf, n_atoms, n_tors, n_angles;
+    double thresh;
+    int max_clashes, handed, axis_sign;
+    double* out_coords;          // (C, T, A, N, 3) or null
+    unsigned char* status;       // (C, T, A) FC_STATUS_*
+    double* min_dist;            // (C, T, A) or null
+};
+
+__global__ void __launch_bounds__(128) torsion_scan_kernel(TorsionArgs p) {
+    extern __shared__ double sx[];  // rotated coordinates (N, 3)
+    const long long item = blockIdx.x;
+    const int ai = (int)(item % p.n_angles);
+    const int t = (int)((item / p.n_angles) % p.n_tors);
+    const int c = (int)(item / ((long long)p.n_angles * p.n_tors));
+    const double* x = p.coords + (size_t)c * p.n_atoms * 3;
+    const int* tor = p.torsions + 4 * t;
+    const unsigned char* mask = p.masks + (size_t)t * p.n_atoms;
+    const int i2 = tor[1], i3 = tor[2];
+    __shared__ M3 rot;
+    __shared__ double origin[3];
+    if (threadIdx.x == 0) {
+        double axis[3] = {p.axis_sign * (x[3 * i2] - x[3 * i3]), p.axis_sign * (x[3 * i2 + 1] - x[3 * i3 + 1]),
+                          p.axis_sign * (x[3 * i2 + 2] - x[3 * i3 + 2])};
+        rot = rot_from_pointer(axis, p.angles[ai], p.handed);
+        origin[0] = x[3 * i3]; origin[1] = x[3 * i3 + 1]; origin[2] = x[3 * i3 + 2];
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < p.n_atoms; a += blockDim.x) {
+        double v[3] = {x[3 * a], x[3 * a + 1], x[3 * a + 2]};
+        if (mask[a]) {
+            double d[3] = {v[0] - origin[0], v[1] - origin[1], v[2] - origin[2]}, r[3];
+            m3_apply(rot, d, r);
+            v[0] = r[0] + origin[0]; v[1] = r[1] + origin[1]; v[2] = r[2] + origin[2];
+        }
+        sx[3 * a] = v[0]; sx[3 * a + 1] = v[1]; sx[3 * a + 2] = v[2];
+    }
+    __syncthreads();
+    if (p.out_coords) {
+        double* o = p.out_coords + (size_t)item * p.n_atoms * 3;
+        for (int e = threadIdx.x; e < p.n_atoms * 3; e += blockDim.x) o[e] = sx[e];
+    }
+    // clash count between moved atoms and static atoms (bond atoms i2, i3 excluded)
+    int clashes = 0;
+    double dmin = 1e300;
+    const int n = p.n_atoms;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        int s = e / n, m = e - s * n;
+        if (!mask[m] || mask[s] || s == i2 || s == i3) continue;
+        double dx = sx[3 * s] - sx[3 * m], dy = sx[3 * s + 1] - sx[3 * m + 1], dz = sx[3 * s + 2] - sx[3 * m + 2];
+        double d = sqrt(dx * dx + dy * dy + dz * dz);
+        clashes += d < p.thresh ? 1 : 0;
+        dmin = fmin(dmin, d);
+    }
+    __shared__ int s_cnt[4];
+    __shared__ double s_min[4];
+    clashes = warp_sum(clashes);
+    dmin = warp_min(dmin);
+    if ((threadIdx.x & 31) == 0) { s_cnt[threadIdx.x >> 5] = clashes; s_min[threadIdx.x >> 5] = dmin; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        double mn = 1e300;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) { tot += s_cnt[w]; mn = fmin(mn, s_min[w]); }
+        unsigned char st = tot <= p.max_clashes ? FC_STATUS_PASS : 0;
+        if (fabs(mn - p.thresh) <= FC_NEAR_EPS) st |= FC_STATUS_NEAR;
+        p.status[item] = st;
+        if (p.min_dist) p.min_dist[item] = mn;
+    }
+}
+
+}  // namespace fc
+
+using namespace fc;
+
+extern "C" int fc_torsion_scan(const double* coords, int32_t n_conf, int32_t n_atoms, const int32_t* torsions,
+                               int32_t n_tors, const uint8_t* masks, const double* angles, int32_t n_angles,
+                               double thresh, int32_t max_clashes, int32_t rot_handedness, int32_t axis_sign,
+                               double* out_coords, uint8_t* status_out, double* min_dist_out) {
+    FC_REQUIRE(n_conf >= 0 && n_atoms > 0 && n_tors >= 0 && n_angles >= 0, "fc_torsion_scan: bad sizes");
+    const int64_t items = (int64_t)n_conf * n_tors * n_angles;
+    if (items == 0) return FC_OK;
+    FC_REQUIRE(items < ((int64_t)1 << 31), "fc_torsion_scan: too many items (%lld)", (long long)items);
+    FC_REQUIRE(coords && torsions && masks && angles && status_out, "fc_torsion_scan: null pointer");
+    for (int t = 0; t < n_tors * 4; ++t)
+        FC_REQUIRE(torsions[t] >= 0 && torsions[t] < n_atoms, "fc_torsion_scan: torsion index out of range");
+    sm_count();
+    cudaStream_t s;
+    FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int rc = FC_OK;
+    {
+        DevBuf<double> d_coords, d_angles, d_out, d_min;
+        DevBuf<int> d_tors;
+        DevBuf<unsigned char> d_masks, d_status;
+        cudaError_t e = cudaSuccess;
+#define TS(call) do { if (e == cudaSuccess) e = (call); } while (0)
+        TS(d_coords.alloc((size_t)n_conf * n_atoms * 3, s));
+        TS(cudaMemcpyAsync(d_coords.p, coords, (size_t)n_conf * n_atoms * 24, cudaMemcpyHostToDevice, s));
+        TS(d_tors.alloc((size_t)n_tors * 4, s));
+        TS(cudaMemcpyAsync(d_tors.p, torsions, (size_t)n_tors * 16, cudaMemcpyHostToDevice, s));
+        TS(d_masks.alloc((size_t)n_tors * n_atoms, s));
+        TS(cudaMemcpyAsync(d_masks.p, masks, (size_t)n_tors * n_atoms, cudaMemcpyHostToDevice, s));
+        TS(d_angles.alloc(n_angles, s));
+        TS(cudaMemcpyAsync(d_angles.p, angles, (size_t)n_angles * 8, cudaMemcpyHostToDevice, s));
+        TS(d_status.alloc((size_t)items, s));
+        if (out_coords) TS(d_out.alloc((size_t)items * n_atoms * 3, s));
+        if (min_dist_out) TS(d_min.alloc((size_t)items, s));
+        if (e == cudaSuccess) {
+            TorsionArgs a{d_coords.p, d_tors.p, d_masks.p, d_angles.p, n_conf, n_atoms, n_tors, n_angles, thresh,
+                          max_clashes, rot_handedness >= 0 ? 1 : -1, axis_sign >= 0 ? 1 : -1,
+                          out_coords ? d_out.p : nullptr, d_status.p, min_dist_out ? d_min.p : nullptr};
+            size_t smem = (size_t)n_atoms * 24;
+            if (smem > 48 * 1024)
+                TS(cudaFuncSetAttribute(torsion_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (e == cudaSuccess) {
+                torsion_scan_kernel<<<(unsigned)items, 128, smem, s>>>(a);
+                e = cudaGetLastError();
+            }
+        }
+        TS(cudaMemcpyAsync(status_out, d_status.p, (size_t)items, cudaMemcpyDeviceToHost, s));
+        if (out_coords) TS(cudaMemcpyAsync(out_coords, d_out.p, (size_t)items * n_atoms * 24, cudaMemcpyDeviceToHost, s));
+        if (min_dist_out) TS(cudaMemcpyAsync(min_dist_out, d_min.p, (size_t)items * 8, cudaMemcpyDeviceToHost, s));
+        TS(cudaStreamSynchronize(s));
+#undef TS
+        if (e != cudaSuccess) rc = cuda_fail(e, "fc_torsion_scan", __FILE__, __LINE__);
+    }
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    return rc;
+}

@@ -187,6 +187,18 @@ int fc_prune(const double* structures, int64_t n, int32_t n_atoms, int32_t mode,
              int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
              int64_t tie_cap, int64_t* n_ties_out);
 
+/* Batched torsion rotation with clash filtering: replaces the primitive pair
+ * prism_pruner.utils.rotate_dihedral + torsion_module.py:894-918 `torsion_comp_check` (used at
+ * torsion_module.py:523-552, 813-856) over every (conformer, torsion, angle) item.
+ *  coords (n_conf, n_atoms, 3); torsions (n_tors, 4) i1..i4; masks (n_tors, n_atoms) 1 = atom moves
+ *  (torsion_module.py:354-382); angles (n_angles) degrees.  Item order: conformer, torsion, angle.
+ *  out_coords (items, n_atoms, 3) optional; status_out (items) FC_STATUS_PASS | FC_STATUS_NEAR;
+ *  min_dist_out (items) optional: smallest moved-static distance. */
+int fc_torsion_scan(const double* coords, int32_t n_conf, int32_t n_atoms, const int32_t* torsions,
+                    int32_t n_tors, const uint8_t* masks, const double* angles, int32_t n_angles,
+                    double thresh, int32_t max_clashes, int32_t rot_handedness, int32_t axis_sign,
+                    double* out_coords, uint8_t* status_out, double* min_dist_out);
+
 /* FP32 FMA-pipe peak probe used by bench.py for the roofline denominator: runs a dependent-free
  * FFMA2 loop on every SM and returns achieved TFLOP/s (2 flop per FMA lane). */
 int fc_probe_fp32_peak(double* tflops_out, double* ms_out, void* stream);

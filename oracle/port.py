@@ -346,3 +346,53 @@ def cyclical_embed_bimol(prob, ties=None, rmsd_thr=1.0, want_poses=True):
             "poses": np.array(poses).reshape(len(poses), n_tot, 3) if want_poses else None,
             "constrained": np.array(constrained, dtype=np.int64).reshape(len(kept), 2, 2),
             "clash_pass": clash_pass, "ties": ties}
+
+
+# ------------------------------------------------------------------------------------------------
+# torsion rotation + clash -- torsion_module.py:354-382, 894-918 and prism_pruner.utils.rotate_dihedral
+# ------------------------------------------------------------------------------------------------
+def rotation_mask(graph, torsion):
+    """torsion_module.py:354-382 (the graph is left unchanged)."""
+    from networkx import shortest_path
+
+    _, i2, i3, i4 = torsion
+    graph.remove_edge(i2, i3)
+    reachable = shortest_path(graph, i4).keys()
+    graph.add_edge(i2, i3)
+    mask = np.array([i in reachable for i in graph.nodes], dtype=bool)
+    mask[i3] = False
+    return mask
+
+
+def torsion_comp_check(coords, torsion, mask, thresh=1.5, max_clashes=0):
+    """torsion_module.py:894-918."""
+    _, i2, i3, _ = torsion
+    antimask = ~mask
+    antimask[i2] = False
+    antimask[i3] = False
+    d = cdist(coords[antimask], coords[mask])
+    return int(np.count_nonzero(d < thresh)) <= max_clashes, (float(d.min()) if d.size else np.inf)
+
+
+def torsion_scan(coords, torsions, masks, angles, thresh=1.5, max_clashes=0):
+    """rotate_dihedral + torsion_comp_check over (conformer, torsion, angle)."""
+    import os
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    from prism_pruner.utils import rotate_dihedral
+
+    coords = np.asarray(coords, dtype=float)
+    c, n = coords.shape[:2]
+    out = np.zeros((c, len(torsions), len(angles), n, 3))
+    passed = np.zeros((c, len(torsions), len(angles)), dtype=bool)
+    dmin = np.zeros((c, len(torsions), len(angles)))
+    for ci in range(c):
+        for ti, (tor, mask) in enumerate(zip(torsions, masks)):
+            for ai, ang in enumerate(angles):
+                new = rotate_dihedral(coords[ci], tuple(int(t) for t in tor), ang, mask=np.asarray(mask, dtype=bool))
+                out[ci, ti, ai] = new
+                passed[ci, ti, ai], dmin[ci, ti, ai] = torsion_comp_check(new, tor, np.asarray(mask, dtype=bool), thresh, max_clashes)
+    return out, passed, dmin
