@@ -318,6 +318,10 @@ def run_cuda(args):
                "sample": f"{n_sample} poses of the same sweep ({wall:.1f} s wall): per-pose get_embed + "
                          "scipy cdist compenetration_check (oracle/port.py) on all host cores"}
 
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = run_extras()
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -339,10 +343,68 @@ def run_cuda(args):
         "e2e": e2e,
         "clocks": clocks,
         "gpu_launches": launches_per_step * args.steps,
+        "other_workloads": extras,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extras():
+    """Wall-clock throughput of the other BASELINE.json configs through the public host API
+    (host buffers in, results out), one GPU.  Secondary numbers: the headline is the C3 sweep."""
+    from firecode_b200 import embeds, problem, pruner, synthetic, torsion
+    from firecode_b200.synthetic_embedder import make_embedder
+    import networkx as nx
+
+    out = {}
+
+    def timed(fn, reps=2):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            r = fn()
+        return (time.perf_counter() - t0) / reps, r
+
+    # C1: string embed, 2 x (10 conformers, 30 atoms), 2 centres, 36 angles = 14 400 tuples
+    emb = make_embedder("string", 10, 30, seed=synthetic.SEED, n_orb=2)
+    prob = problem.string_problem(emb)
+    dt, (poses, rep) = timed(lambda: embeds.string_screen(prob))
+    out["C1_string_embed"] = {"poses_per_s": rep.n_poses / dt, "poses": rep.n_poses, "kept": rep.n_kept,
+                              "clash_pass": rep.n_clash_pass, "seconds": dt}
+    # C2-like bimolecular cyclical embed: 2 x (50 conformers, 60 atoms), 4 pivots each, 36 angle pairs
+    emb = make_embedder("cyclical", 50, 60, seed=synthetic.SEED + 1, n_reactive=2, n_orb=2)
+    cprob = problem.cyclical_problem(emb)
+    dt, (poses, cons, rep) = timed(lambda: embeds.cyclical_screen(cprob), reps=1)
+    out["C2_cyclical_embed_bimolecular"] = {"poses_per_s": rep.n_poses / dt, "poses": rep.n_poses, "kept": rep.n_kept,
+                                            "clash_pass": rep.n_clash_pass, "seconds": dt,
+                                            "note": "includes host-side group enumeration (python)"}
+    # C4-like RMSD pruning: 20 000 conformers of a 120-atom molecule (400 basins)
+    rng = np.random.default_rng(synthetic.SEED + 4)
+    atoms, structures, _ = synthetic.pruning_ensemble(rng, 20000, 120, 400)
+    dt, (kept, mask) = timed(lambda: pruner.prune_by_rmsd(structures, atoms, 0.5), reps=1)
+    rep = pruner.last_report
+    out["C4_rmsd_pruning_20k"] = {"rmsd_pairs_per_s": rep.pairs_tiled / dt, "pairs": rep.pairs_tiled,
+                                  "pairs_eigen_solved": rep.pairs_solved, "passes": rep.passes,
+                                  "kept": int(mask.sum()), "n": len(mask), "seconds": dt,
+                                  "conventions": {"keep": rep.keep, "pass_mode": rep.pass_mode}}
+    # C5: torsion scan, 1 000 conformers x 8 torsions x 36 steps of a 120-atom molecule
+    rng = np.random.default_rng(synthetic.SEED + 5)
+    atoms, coords, bonds, picks = synthetic.conformer_ensemble(rng, 1000, 120, n_torsions=8)
+    g = nx.Graph(); g.add_nodes_from(range(120)); g.add_edges_from(bonds)
+    tors = []
+    for p, ch in picks:
+        nb_p = [k for k in g.neighbors(p) if k != ch]; nb_c = [k for k in g.neighbors(ch) if k != p]
+        if nb_p and nb_c:
+            tors.append((nb_p[0], p, ch, nb_c[0]))
+    masks = [torsion.get_rotation_mask(g, t) for t in tors]
+    angles = np.arange(36) * 10.0
+    dt, res = timed(lambda: torsion.torsion_scan(coords, tors, masks, angles, thresh=1.5, want_coords=False))
+    n_items = len(coords) * len(tors) * len(angles)
+    out["C5_torsion_scan"] = {"structures_per_s": n_items / dt, "structures": n_items,
+                              "pass_fraction": float(res["passed"].mean()), "seconds": dt,
+                              "note": "mask only; coordinates of 288 k x 120 atoms are optional output"}
+    return out
 
 
 def main():
@@ -354,6 +416,7 @@ def main():
     ap.add_argument("--poses", type=int, default=N_POSES, help="poses per GPU per step")
     ap.add_argument("--e2e-poses", type=int, default=N_POSES)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (C1, C2, C4, C5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,170 @@
+"""Multi-GPU sharding of the embedding screen: one process per GPU (torch.distributed, NCCL over
+NVLink on the GPU box, gloo in the CPU tests).
+
+The path shards over independent units: contiguous ranges of the candidate-tuple
+index per rank, fragments replicated.  No data-path collective is needed for the clash screen; the
+only exchange steps are
+  * one all-gather of the per-rank survivor bitmasks (10 M poses = 1.25 MB in total), and
+  * for the string embed, one all-gather of the survivors' torsion fingerprints followed by the
+    ordered keep-first sweep, run redundantly on every rank so that the kept set is the
+    reference's and identical everywhere.
+Rank order = enumeration order, so concatenation reproduces the reference's pose order.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n_items: int, world: int, rank: int):
+    """Contiguous [lo, hi) range of rank ``rank``; the first n_items % world ranks get one more."""
+    base, rem = divmod(int(n_items), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+def world_info(group=None):
+    dist = _dist()
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def _device_for_backend(group=None):
+    import torch
+
+    dist = _dist()
+    backend = dist.get_backend(group)
+    return torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+
+
+def all_gather_varlen(x: np.ndarray, group=None) -> np.ndarray:
+    """All-gather numpy arrays whose first dimension differs per rank; returns their concatenation
+    in rank order (every rank gets the same result)."""
+    import torch
+
+    dist = _dist()
+    rank, world = world_info(group)
+    x = np.ascontiguousarray(x)
+    if world == 1:
+        return x
+    dev = _device_for_backend(group)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    mine = torch.tensor([x.shape[0]], dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, mine, group=group)
+    counts = counts.cpu().numpy()
+    row = int(np.prod(x.shape[1:])) if x.ndim > 1 else 1
+    cap = int(counts.max())
+    flat = np.zeros((cap, row), dtype=x.dtype)
+    flat[: x.shape[0]] = x.reshape(x.shape[0], row)
+    # bytes on the wire: dtype-agnostic and valid for both NCCL and gloo
+    send = torch.from_numpy(flat.view(np.uint8).reshape(-1)).to(dev)
+    recv = torch.empty(world * send.numel(), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    parts = recv.cpu().numpy().reshape(world, cap, row * x.dtype.itemsize)
+    out = [parts[r, : counts[r]].copy().view(x.dtype).reshape((counts[r],) + x.shape[1:]) for r in range(world)]
+    return np.concatenate(out, axis=0)
+
+
+def pack_bits(mask: np.ndarray) -> np.ndarray:
+    """bool (n,) -> uint32 (ceil(n/32),), bit (i & 31) of word i >> 5 (layout of fc_pack_mask_dev)."""
+    m = np.asarray(mask, dtype=bool)
+    pad = (-len(m)) % 32
+    m = np.concatenate([m, np.zeros(pad, dtype=bool)])
+    return np.packbits(m.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).ravel()
+
+
+def unpack_bits(words: np.ndarray, n: int) -> np.ndarray:
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    return np.unpackbits(w.view(np.uint8).reshape(-1, 4), axis=1, bitorder="little").ravel()[:n].astype(bool)
+
+
+def all_gather_mask(local_mask: np.ndarray, n_total: int, group=None) -> np.ndarray:
+    """Each rank holds the survivor mask of its shard_bounds range; returns the mask of all n_total
+    poses on every rank (bitmask all-gather + ordered concatenation)."""
+    rank, world = world_info(group)
+    if world == 1:
+        return np.asarray(local_mask, dtype=bool)
+    words = all_gather_varlen(pack_bits(local_mask), group)
+    out = np.zeros(n_total, dtype=bool)
+    off = 0
+    for r in range(world):
+        lo, hi = shard_bounds(n_total, world, r)
+        nw = (hi - lo + 31) // 32
+        out[lo:hi] = unpack_bits(words[off: off + nw], hi - lo)
+        off += nw
+    return out
+
+
+def clash_screen_sharded(frag_a, frag_b, xf, thresh, max_clashes=0, group=None, screen=None):
+    """Screen poses on all ranks: rank r takes poses shard_bounds(n, world, r).  ``screen`` is the
+    per-shard screen (default: the CUDA path, firecode_b200.clash.compenetration_check_batch)."""
+    rank, world = world_info(group)
+    xf = np.asarray(xf, dtype=np.float64).reshape(-1, 12)
+    lo, hi = shard_bounds(len(xf), world, rank)
+    if screen is None:
+        from .clash import compenetration_check_batch
+
+        def screen(a, b, x):
+            return compenetration_check_batch(a, b, x, thresh=thresh, max_clashes=max_clashes).mask
+    local = screen(frag_a, frag_b, xf[lo:hi]) if hi > lo else np.zeros(0, dtype=bool)
+    return all_gather_mask(local, len(xf), group)
+
+
+def ordered_keep_first(labels, fingerprints, keep_fn, group=None):
+    """Merge step of the sharded string embed: all ranks contribute the (pose index, fingerprint)
+    of their clash survivors; every rank gets all of them in pose order and runs the ordered
+    keep-first sweep ``keep_fn(fingerprints, labels) -> bool mask``."""
+    all_labels = all_gather_varlen(np.asarray(labels, dtype=np.int64), group)
+    all_fp = all_gather_varlen(np.asarray(fingerprints, dtype=np.float64), group)
+    assert np.all(np.diff(all_labels) > 0), "rank order must equal enumeration order"
+    keep = np.asarray(keep_fn(all_fp, all_labels), dtype=bool)
+    return all_labels[keep], all_labels, keep
+
+
+def string_embed_sharded(embedder, group=None):
+    """string_embed over all ranks of ``group`` (same result on every rank, equal to the
+    single-GPU / reference result)."""
+    import ctypes as C
+
+    from . import _lib, embeds, problem
+    from .errors import ZeroCandidatesError
+
+    rank, world = world_info(group)
+    if world == 1:
+        return embeds.string_embed(embedder)
+    lib = _lib.load(require_device=True)
+    prob = problem.string_problem(embedder)
+    c, keep_alive = embeds._string_problem_c(prob)
+    lo, hi = shard_bounds(prob.n_poses, world, rank)
+    handle = C.c_void_p()
+    _lib.check(lib.fc_string_stage1(C.byref(c), lo, hi, C.byref(handle)), "fc_string_stage1")
+    res = embeds._Result(lib, handle)
+    surv, fps = res.survivors(), res.fingerprints()
+    res.close()
+
+    def keep_fn(fp, labels):
+        out = np.zeros(len(labels), dtype=np.uint8)
+        n_ties = C.c_int64(0)
+        fp = np.ascontiguousarray(fp.reshape(len(labels), -1))
+        _lib.check(lib.fc_tfd_keepfirst(embeds._ptr(fp), embeds._ptr(labels), len(labels), fp.shape[1] if fp.size else 0,
+                                        10.0, embeds._ptr(out), None, 0, C.byref(n_ties)), "fc_tfd_keepfirst")
+        return out.astype(bool)
+
+    kept, _, _ = ordered_keep_first(surv, fps.reshape(len(surv), -1), keep_fn, group)
+    if len(kept) == 0:
+        raise ZeroCandidatesError("string embed: no pose survived")
+    n_tot = prob.coords[0].shape[1] + prob.coords[1].shape[1]
+    poses = np.zeros((len(kept), n_tot, 3))
+    kept = np.ascontiguousarray(kept, dtype=np.int64)
+    _lib.check(lib.fc_string_materialize(C.byref(c), embeds._ptr(kept), len(kept), embeds._ptr(poses)),
+               "fc_string_materialize")
+    embedder.constrained_indices = np.repeat(prob.constrained[None], len(poses), axis=0)
+    del keep_alive
+    return poses

@@ -1,0 +1,96 @@
+"""CPU tests of the host-side logic of the product (no GPU, no reference tree)."""
+
+import numpy as np
+import pytest
+from networkx import Graph
+
+from firecode_b200 import embeds, graphs, problem, synthetic, torsion, utils
+from firecode_b200.errors import TriangleError
+from synth_embedder import make_embedder
+
+
+def test_cartesian_product_order():
+    # first index fastest for two inputs
+    out = utils.cartesian_product(range(3), range(2))
+    assert out.tolist() == [[0, 0], [1, 0], [2, 0], [0, 1], [1, 1], [2, 1]]
+    out3 = utils.cartesian_product(range(2), range(2), range(2))
+    assert out3.tolist() == [[0, 0, 0], [0, 0, 1], [1, 0, 0], [1, 0, 1], [0, 1, 0], [0, 1, 1], [1, 1, 0], [1, 1, 1]]
+
+
+def test_rotation_helpers():
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        a, b = rng.normal(size=3), rng.normal(size=3)
+        r = utils.rotation_matrix_from_vectors(a, b)
+        assert np.allclose(r @ r.T, np.eye(3), atol=1e-12) and np.isclose(np.linalg.det(r), 1)
+        assert np.allclose(r @ (a / np.linalg.norm(a)), b / np.linalg.norm(b), atol=1e-12)
+    z = utils.rot_mat_from_pointer(np.array([0, 0, 2.0]), 90)
+    assert np.allclose(z @ np.array([1.0, 0, 0]), [0, 1, 0])  # right-handed about +z
+    a = np.array([1.0, 0, 0])
+    assert np.allclose(utils.rotation_matrix_from_vectors(a, a), np.eye(3))
+    assert np.allclose(utils.rotation_matrix_from_vectors(a, -a) @ a, -a)
+
+
+def test_polygonize():
+    two = utils.polygonize([2.0, 3.0])
+    assert two.shape == (2, 2, 2, 3)
+    assert np.allclose(two[0, 1], [[-1.5, 0, 0], [1.5, 0, 0]]) and np.allclose(two[1, 1], [[1.5, 0, 0], [-1.5, 0, 0]])
+    tri = utils.polygonize([3.0, 4.0, 5.0])
+    assert tri.shape == (8, 3, 2, 3)
+    for t in tri:  # every orientation is the same closed triangle
+        lengths = sorted(np.linalg.norm(t[:, 1] - t[:, 0], axis=1))
+        assert np.allclose(lengths, [3, 4, 5])
+    with pytest.raises(TriangleError):
+        utils.polygonize([1.0, 1.0, 3.0])
+
+
+def test_string_problem_extraction_and_decode():
+    emb = make_embedder("string", 3, 20, seed=1, n_orb=2)
+    prob = problem.string_problem(emb)
+    assert prob.n_poses == 3 * 3 * 4 * 36
+    assert prob.centers[0].shape == (3, 2, 3) and prob.quadruplets.shape[1] == 4
+    # decode follows the reference's loop nest: conformer pairs (first index fastest), centre pairs, angles
+    seen = [prob.decode(p)[:4] for p in range(0, prob.n_poses, 36)]
+    assert seen[0] == (0, 0, 0, 0) and seen[1] == (0, 0, 1, 0) and seen[4] == (1, 0, 0, 0)
+    assert prob.decode(37)[4] == 10.0
+
+
+def test_cyclical_groups_table():
+    emb = make_embedder("cyclical", 2, 16, seed=4, n_reactive=2, n_orb=2)
+    prob = problem.cyclical_problem(emb)
+    g = embeds.cyclical_groups(prob)
+    assert g["conf"].shape[1] == 2 and g["vecs"].shape[1:] == (2, 2, 3) and len(g["conf"]) == 2 * 2 * 16 * 2
+    # a pairing that no arrangement contains removes every group (the reference's quirk N10 included)
+    emb.pairings_table = {"a": (0, 1)}
+    prob2 = problem.cyclical_problem(emb)
+    assert len(embeds.cyclical_groups(prob2)["conf"]) == 0
+
+
+def test_rotation_mask_and_tiles():
+    g = Graph([(0, 1), (1, 2), (2, 3), (3, 4), (2, 5)])
+    mask = torsion.get_rotation_mask(g, (0, 1, 2, 3))
+    assert mask.tolist() == [False, False, False, True, True, True]
+    from firecode_b200 import clash
+
+    ca = np.array([0, 0, 0, 1, 1, 2]); cb = np.array([0, 0, 1, 1, 1, 0])
+    tiles = clash.build_tiles(ca, cb, 150)
+    assert tiles[:, 2].tolist() == [0, 2, 3, 5] and tiles[:, 3].tolist() == [2, 1, 2, 1]
+    p = clash.tile_poses(150)
+    big = clash.build_tiles(np.zeros(3 * p + 1, int), np.zeros(3 * p + 1, int), 150)
+    assert big[:, 3].tolist() == [p, p, p, 1]
+
+
+def test_sum_graph_and_quadruplets():
+    g1 = Graph([(0, 1), (1, 2)]); g2 = Graph([(0, 1), (1, 2)])
+    s = graphs.sum_graph((g1, g2), [(2, 3)])
+    assert sorted(s.edges()) == [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5)]
+    q = graphs.quadruplets(s)
+    assert q.shape == (3, 4)
+
+
+def test_synthetic_generators_are_seeded():
+    a = synthetic.conformer_ensemble(np.random.default_rng(3), 4, 30)[1]
+    b = synthetic.conformer_ensemble(np.random.default_rng(3), 4, 30)[1]
+    assert np.array_equal(a, b) and abs(a.reshape(-1, 3).mean(axis=0)).max() < 1e-9
+    xf = synthetic.sweep_poses(np.random.default_rng(1), a[0], a[1], 10)
+    assert np.array_equal(xf, xf.astype(np.float32).astype(np.float64))
