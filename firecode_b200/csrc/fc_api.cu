@@ -211,12 +211,13 @@ extern "C" int fc_clash_batch(const double* a_coords, int n_conf_a, int n_a, con
                                      d_min ? d_min + first : nullptr, d_near_count, d_near_idx,
                                      d_near_dist, near_cap, first, (void*)s);
             if (rc != FC_OK) goto done;
-            FC_TRY(cudaMemcpyAsync(status + first, d_status + first, (size_t)n, cudaMemcpyDeviceToHost, s));
-            if (min_dist)
-                FC_TRY(cudaMemcpyAsync(min_dist + first, d_min + first, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
         }
     }
     for (int i = 0; i < kBuf; ++i) FC_TRY(cudaStreamSynchronize(st[i]));
+    // results come back in one piece: a per-chunk copy into pageable host memory would block the
+    // host thread and serialise the H2D / kernel pipeline
+    FC_TRY(cudaMemcpy(status, d_status, (size_t)n_poses, cudaMemcpyDeviceToHost));
+    if (min_dist) FC_TRY(cudaMemcpy(min_dist, d_min, (size_t)n_poses * 4, cudaMemcpyDeviceToHost));
     {
         int32_t n_near = 0;
         FC_TRY(cudaMemcpy(&n_near, d_near_count, 4, cudaMemcpyDeviceToHost));
