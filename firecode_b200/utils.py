@@ -82,3 +82,40 @@ def polygonize(lengths):
         for v in vecs:
             out[t, v] = out[t, v][::-1].copy()
     return out
+
+
+def compenetration_check(coords, graph=None, ids=None, thresh=1.0, max_clashes=0):
+    """Single-structure form of the clash test (utils.py:507-575), evaluated on the GPU.
+
+    ids of length 2: ``#{|m2_j - m1_i| < thresh} <= max_clashes`` (utils.py:544-551);
+    ids of length 3: the three blocks (m2,m1), (m3,m2), (m1,m3) with ``<=`` (utils.py:553-575).
+    The hot path never calls this per pose -- the screens batch it (firecode_b200.clash)."""
+    from .clash import compenetration_check_batch
+
+    coords = np.ascontiguousarray(np.asarray(coords, dtype=np.float64))
+    if ids is None:
+        raise NotImplementedError(
+            "firecode_b200: the non-fragment branch of compenetration_check (utils.py:523-542, a "
+            "set-up time check outside the embedding screen) is not built")
+    eye = np.array([[1.0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]])
+    if len(ids) == 2:
+        m1, m2 = coords[: ids[0]], coords[ids[0]:]
+        return bool(compenetration_check_batch(m1, m2, eye, thresh=thresh, max_clashes=max_clashes).mask[0])
+    if max_clashes != 0:
+        raise NotImplementedError("firecode_b200: trimolecular clash test with max_clashes > 0 is not built")
+    n1, n2 = ids[0], ids[0] + ids[1]
+    m1, m2, m3 = coords[:n1], coords[n1:n2], coords[n2:]
+    for a, b in ((m1, m2), (m2, m3), (m3, m1)):
+        if not compenetration_check_batch(a, b, eye, thresh=thresh, max_clashes=0, strict=False).mask[0]:
+            return False
+    return True
+
+
+def rmsd_similarity(ref, structures, rmsd_thr=0.5):
+    """True if any structure has uncentred all-atom Kabsch RMSD < rmsd_thr and max deviation
+    < 2 * rmsd_thr to ``ref`` (utils.py:494-504).  Evaluated on the GPU through the pruning kernel
+    is not possible (that one centres); the screens run this filter inside fc_cyclical_screen, and
+    this single-call form is kept for API parity only."""
+    raise NotImplementedError(
+        "firecode_b200: rmsd_similarity is fused into the cyclical screen (fc_cyclical_screen); a "
+        "stand-alone entry point is not built")

@@ -108,3 +108,16 @@ def test_adversarial_near_threshold(gpu):
     lut = dict(zip(res.near_idx.tolist(), res.near_dist.tolist()))
     for p in np.flatnonzero(near)[:50]:
         assert abs(lut[p] - dmin2[p]) < 1e-9
+
+
+def test_single_structure_api(gpu):
+    """utils.compenetration_check keeps the reference signature (utils.py:507-513)."""
+    from firecode_b200.utils import compenetration_check
+
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        coords = rng.normal(scale=2.5, size=(30, 3))
+        for ids in ((12, 18), (10, 10, 10)):
+            assert compenetration_check(coords, ids=ids, thresh=1.2) == port.compenetration_check(coords, ids=ids, thresh=1.2)
+        assert compenetration_check(coords, ids=(12, 18), thresh=1.2, max_clashes=2) == \
+            port.compenetration_check(coords, ids=(12, 18), thresh=1.2, max_clashes=2)
