@@ -61,6 +61,23 @@ class CyclicalProblemC(C.Structure):
     ]
 
 
+class Cyclical3ProblemC(C.Structure):
+    """struct fc_cyclical3_problem"""
+
+    _fields_ = [
+        ("coords", VP * 3), ("n_conf", C.c_int32 * 3), ("n_atoms", C.c_int32 * 3),
+        ("reactive", VP * 3), ("n_reactive", C.c_int32 * 3),
+        ("pivot_offsets", VP * 3), ("pivot_vec", VP * 3), ("pivot_mean", VP * 3), ("pivot_ids", VP * 3),
+        ("ratoms0", VP * 3), ("n_ratoms0", C.c_int32 * 3),
+        ("angles", VP), ("n_angles", C.c_int32),
+        ("pairings", VP), ("n_pairings", C.c_int32),
+        ("internal", VP), ("n_internal", C.c_int32),
+        ("thresh", C.c_double), ("rot_handedness", C.c_int32), ("rmsd_thresh", C.c_double),
+        ("conf_tuple_lo", C.c_int64), ("conf_tuple_hi", C.c_int64),
+        ("flags", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/firecode_b200.h declares
 SIGNATURES = {
     "fc_result_free": (None, [VP]),
@@ -73,6 +90,8 @@ SIGNATURES = {
     "fc_result_constrained": (C.c_int, [VP, VP]),
     "fc_result_ties": (C.c_int64, [VP, VP, C.c_int64]),
     "fc_cyclical_screen": (C.c_int, [VP, C.POINTER(VP)]),
+    "fc_cyclical3_screen": (C.c_int, [VP, C.POINTER(VP)]),
+    "fc_result_groups": (C.c_int, [VP, VP, VP]),
     "fc_prune": (C.c_int, [VP, C.c_int64, C.c_int32, C.c_int32, VP, C.c_int32, VP, C.c_double, C.c_double,
                            C.c_double, VP, C.c_double, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP,
                            C.c_int64, c_i64p]),

@@ -268,19 +268,6 @@ using namespace fc;
 // ---------------------------------------------------------------------------------------------
 // result object
 // ---------------------------------------------------------------------------------------------
-struct fc_result {
-    int64_t n_poses = 0, n_clash_pass = 0, n_rechecked = 0, n_kept = 0, n_atoms = 0, n_surv = 0, n_quads = 0;
-    std::vector<uint8_t> status;         // per screened pose
-    std::vector<int64_t> survivors;      // clash survivors (absolute pose index)
-    std::vector<double> fingerprints;    // (n_surv, n_quads), stage-1 results only
-    std::vector<int64_t> kept;           // absolute pose index, reference order
-    std::vector<double> coords;          // (n_kept, n_atoms, 3)
-    std::vector<int32_t> constrained;    // (n_kept, n_pairs, 2)
-    int n_pairs = 0;
-    std::vector<fc_tie> ties;
-    int64_t ties_total = 0;
-};
-
 extern "C" void fc_result_free(fc_result* r) { delete r; }
 extern "C" int fc_result_counts(const fc_result* r, int64_t* out10) {
     FC_REQUIRE(r && out10, "fc_result_counts: null pointer");
@@ -293,7 +280,7 @@ extern "C" int fc_result_counts(const fc_result* r, int64_t* out10) {
     out10[6] = r->n_surv;
     out10[7] = r->n_quads;
     out10[8] = r->n_pairs;
-    out10[9] = 0;
+    out10[9] = r->n_groups;
     return FC_OK;
 }
 
@@ -332,6 +319,12 @@ extern "C" int fc_result_fingerprints(const fc_result* r, double* out) { FC_COPY
 extern "C" int fc_result_kept_indices(const fc_result* r, int64_t* out) { FC_COPY_OUT(r->kept, out); }
 extern "C" int fc_result_kept_coords(const fc_result* r, double* out) { FC_COPY_OUT(r->coords, out); }
 extern "C" int fc_result_constrained(const fc_result* r, int32_t* out) { FC_COPY_OUT(r->constrained, out); }
+extern "C" int fc_result_groups(const fc_result* r, int32_t* choice, double* gap) {
+    FC_REQUIRE(r, "null result");
+    if (choice && !r->group_choice.empty()) memcpy(choice, r->group_choice.data(), r->group_choice.size() * 4);
+    if (gap && !r->group_gap.empty()) memcpy(gap, r->group_gap.data(), r->group_gap.size() * 8);
+    return FC_OK;
+}
 extern "C" int64_t fc_result_ties(const fc_result* r, fc_tie* out, int64_t cap) {
     if (!r) return -1;
     int64_t n = std::min<int64_t>(cap, (int64_t)r->ties.size());

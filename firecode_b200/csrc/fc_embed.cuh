@@ -1,7 +1,28 @@
 // firecode_b200 -- internal declarations shared by the embed pipelines (string / cyclical).
 #pragma once
 
+#include <vector>
+
 #include "fc_math.cuh"
+
+// result object behind the opaque fc_result handle of the C-ABI (filled by the embed drivers)
+struct fc_result {
+    int64_t n_poses = 0, n_clash_pass = 0, n_rechecked = 0, n_kept = 0, n_atoms = 0, n_surv = 0, n_quads = 0;
+    std::vector<uint8_t> status;         // per screened pose
+    std::vector<int64_t> survivors;      // clash survivors (absolute pose index)
+    std::vector<double> fingerprints;    // (n_surv, n_quads), stage-1 results only
+    std::vector<int64_t> kept;           // absolute pose index, reference order
+    std::vector<double> coords;          // (n_kept, n_atoms, 3)
+    std::vector<int32_t> constrained;    // (n_kept, n_pairs, 2)
+    int n_pairs = 0;
+    std::vector<fc_tie> ties;
+    int64_t ties_total = 0;
+    // trimolecular cyclical embed: per group, the grid-search candidate _adjust_directions chose and
+    // the cost gap to the runner-up (embeds.py:403-405)
+    int64_t n_groups = 0;
+    std::vector<int32_t> group_choice;
+    std::vector<double> group_gap;
+};
 
 namespace fc {
 
@@ -37,6 +58,8 @@ struct TieRecord {
     int kind;      // FC_TIE_*
     int decision;  // the decision the CUDA path took (1 = "below threshold")
 };
+
+fc_result* result_new();
 
 // order-preserving compaction of the poses whose status has FC_STATUS_PASS set (CUB DeviceSelect)
 int compact_pass(const uint8_t* status, long long n, long long base, long long* out_idx, int* out_count,

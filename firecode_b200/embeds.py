@@ -41,6 +41,9 @@ class ScreenReport:
     ties: np.ndarray | None = None  # structured array (a, b, value, kind, decision)
     n_ties_total: int = 0
     conventions: dict = field(default_factory=conventions.as_dict)
+    n_mols: int = 2
+    group_choice: np.ndarray | None = None  # trimolecular: grid-search candidate per group
+    group_gap: np.ndarray | None = None     # ... and its cost gap to the runner-up (degrees)
 
     def forced_decisions(self):
         """Near-threshold decisions as the key -> bool mapping oracle.port.Ties understands."""
@@ -48,7 +51,9 @@ class ScreenReport:
         if self.ties is None:
             return out
         for t in self.ties:
-            if t["kind"] == TIE_CLASH:
+            if t["kind"] == TIE_CLASH and self.n_mols == 3:
+                out[("clash3", int(t["a"]), -1 - int(t["b"]))] = bool(t["decision"])  # b = -1 - block
+            elif t["kind"] == TIE_CLASH:
                 out[("clash", int(t["a"]))] = bool(t["decision"])
             elif t["kind"] == TIE_TFD:
                 out[("tfd", int(t["a"]), int(t["b"]))] = bool(t["decision"])
@@ -75,7 +80,7 @@ class _Result:
         counts = np.zeros(10, dtype=np.int64)
         _lib.check(lib.fc_result_counts(handle, counts.ctypes.data_as(_lib.c_i64p)), "fc_result_counts")
         (self.n_poses, self.n_clash_pass, self.n_rechecked, self.n_kept, self.n_ties, self.n_atoms,
-         self.n_surv, self.n_quads, self.n_pairs, _) = (int(x) for x in counts)
+         self.n_surv, self.n_quads, self.n_pairs, self.n_groups) = (int(x) for x in counts)
 
     def _get(self, fn, shape, dtype):
         out = np.zeros(shape, dtype=dtype)
@@ -100,6 +105,13 @@ class _Result:
 
     def constrained(self):
         return self._get("fc_result_constrained", (self.n_kept, self.n_pairs, 2), np.int32)
+
+    def groups(self):
+        choice = np.zeros(self.n_groups, dtype=np.int32)
+        gap = np.zeros(self.n_groups, dtype=np.float64)
+        if self.n_groups:
+            _lib.check(self.lib.fc_result_groups(self.handle, _ptr(choice), _ptr(gap)), "fc_result_groups")
+        return choice, gap
 
     def ties(self, cap=1 << 20):
         n = min(self.n_ties, cap)
@@ -288,16 +300,78 @@ def cyclical_screen(prob: problem.CyclicalProblem, rmsd_thresh=1.0):
     return poses, constrained, report
 
 
+def _csr(per_conf, width, dtype):
+    """list over conformers of (P, width) arrays -> (offsets (C+1,), rows (sum P, width))."""
+    counts = np.array([len(a) for a in per_conf], dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    rows = (np.concatenate([np.asarray(a, dtype=dtype).reshape(-1, width) for a in per_conf])
+            if len(per_conf) else np.zeros((0, width), dtype=dtype))
+    return np.ascontiguousarray(offsets), np.ascontiguousarray(rows.reshape(-1, width).astype(dtype))
+
+
+def cyclical3_screen(prob: problem.CyclicalProblem, rmsd_thresh=1.0, conf_tuple_range=None, want_status=True,
+                     want_coords=True):
+    """Run the trimolecular cyclical screen (embeds.py:409-585) on the current CUDA device.
+    ``conf_tuple_range`` = (lo, hi) restricts the call to a slice of the conformer-triple enumeration
+    (multi-GPU sharding: groups never straddle a slice).  Returns (poses, constrained, ScreenReport)."""
+    lib = _lib.load(require_device=True)
+    assert prob.n_mols == 3
+    keep = {"coords": [np.ascontiguousarray(c, dtype=np.float64) for c in prob.coords],
+            "reactive": [np.ascontiguousarray(r, dtype=np.int64) for r in prob.reactive],
+            "ratoms0": [np.ascontiguousarray(r, dtype=np.int64).reshape(-1, 2) for r in prob.ratoms0],
+            "angles": np.ascontiguousarray(prob.angles, dtype=np.float64).reshape(-1, 3),
+            "pairings": np.ascontiguousarray(np.array(prob.pairings, dtype=np.int64).reshape(-1, 2)),
+            "internal": np.ascontiguousarray(np.array(
+                [] if prob.internal_constraints_is_array else prob.internal_constraints, dtype=np.int64).reshape(-1, 2)),
+            "csr": []}
+    c = _lib.Cyclical3ProblemC()
+    for m in range(3):
+        c.coords[m] = keep["coords"][m].ctypes.data
+        c.n_conf[m], c.n_atoms[m] = keep["coords"][m].shape[:2]
+        c.reactive[m] = keep["reactive"][m].ctypes.data
+        c.n_reactive[m] = len(keep["reactive"][m])
+        off, vec = _csr(prob.pivot_vec[m], 3, np.float64)
+        _, mean = _csr(prob.pivot_mean[m], 3, np.float64)
+        _, ids = _csr(prob.pivot_ids[m], 2, np.int64)
+        keep["csr"].append((off, vec, mean, ids))
+        c.pivot_offsets[m], c.pivot_vec[m] = off.ctypes.data, vec.ctypes.data
+        c.pivot_mean[m], c.pivot_ids[m] = mean.ctypes.data, ids.ctypes.data
+        c.ratoms0[m], c.n_ratoms0[m] = keep["ratoms0"][m].ctypes.data, len(keep["ratoms0"][m])
+    c.angles, c.n_angles = _ptr(keep["angles"]), len(keep["angles"])
+    c.pairings, c.n_pairings = _ptr(keep["pairings"]), len(keep["pairings"])
+    c.internal, c.n_internal = _ptr(keep["internal"]), len(keep["internal"])
+    c.thresh, c.rot_handedness, c.rmsd_thresh = float(prob.thresh), int(conventions.ROT_HANDEDNESS), float(rmsd_thresh)
+    c.conf_tuple_lo, c.conf_tuple_hi = (0, 0) if conf_tuple_range is None else (int(conf_tuple_range[0]), int(conf_tuple_range[1]))
+    c.flags = (0 if want_status else 1) | (0 if want_coords else 2)
+    handle = C.c_void_p()
+    _lib.check(lib.fc_cyclical3_screen(C.byref(c), C.byref(handle)), "fc_cyclical3_screen")
+    res = _Result(lib, handle)
+    try:
+        choice, gap = res.groups()
+        report = ScreenReport(n_poses=res.n_poses, n_clash_pass=res.n_clash_pass,
+                              n_fp64_rechecks=res.n_rechecked, n_kept=res.n_kept,
+                              kept_indices=res.kept_indices(), status=res.status() if want_status else None,
+                              ties=res.ties(), n_ties_total=res.n_ties, n_mols=3, group_choice=choice, group_gap=gap)
+        n_tot = sum(int(x.shape[1]) for x in keep["coords"])
+        poses = res.kept_coords() if want_coords else np.zeros((0, n_tot, 3))
+        constrained = res.constrained().astype(np.int64)
+    finally:
+        res.close()
+    del keep
+    return poses, constrained, report
+
+
 def cyclical_embed(embedder, max_norm_delta: float = 5.0):
-    """Drop-in for firecode.embeds.cyclical_embed (embeds.py:180-585) -- bimolecular systems
-    ("cyclical" and "chelotropic" embeds, embeds.py:184-185 -> 588-750)."""
-    if len(embedder.objects) != 2:
-        raise NotImplementedError(
-            "firecode_b200: the trimolecular cyclical embed (embeds.py:409-585) is a 'next' row of "
-            "the scope table and is not built yet")
-    embedder.log(f"\n--> Performing {embedder.embed} embed ({embedder.candidates} candidates)")
+    """Drop-in for firecode.embeds.cyclical_embed (embeds.py:180-585): two molecules ("cyclical" and
+    "chelotropic" embeds, embeds.py:184-185 -> 588-750) or three (embeds.py:409-585)."""
+    if len(embedder.objects) not in (2, 3):
+        raise ValueError("cyclical_embed needs two or three molecules")
+    embedder.log(f"\n--> Performing {embedder.embed} embed ({pretty_num(embedder.candidates)} candidates)")
     prob = problem.cyclical_problem(embedder, max_norm_delta=max_norm_delta)
-    poses, constrained, report = cyclical_screen(prob)
+    if len(embedder.objects) == 3:
+        poses, constrained, report = cyclical3_screen(prob)
+    else:
+        poses, constrained, report = cyclical_screen(prob)
     embedder.b200_report = report
     embedder.constrained_indices = constrained
     if len(poses) == 0:

@@ -88,6 +88,17 @@ class CyclicalProblem:
     internal_constraints_is_array: bool
     internal_constraints: list
     max_norm_delta: float = 5.0
+    ratoms0: list = None      # per molecule (K,2) int: [index, cumnum] of reactive_atoms_classes_dict[0]
+                              # in dict order (read by _adjust_directions, embeds.py:330-337)
+    ids: list = None          # embedder.ids (atoms per molecule)
+
+    def __post_init__(self):
+        if self.ids is None:
+            self.ids = [int(c.shape[1]) for c in self.coords]
+        if self.ratoms0 is None:
+            off = np.concatenate([[0], np.cumsum(self.ids)[:-1]])
+            self.ratoms0 = [np.array([[int(i), int(i) + int(off[m])] for i in self.reactive[m]],
+                                     dtype=np.int64).reshape(-1, 2) for m in range(len(self.coords))]
 
     @property
     def n_mols(self) -> int:
@@ -105,6 +116,10 @@ def cyclical_problem(embedder, max_norm_delta: float = 5.0) -> CyclicalProblem:
                             dtype=np.int64).reshape(-1, 2) for plist in m.pivots])
     table = getattr(embedder, "pairings_table", None) or {}
     ic = getattr(embedder, "internal_constraints", [])
+    ratoms0 = None
+    if all(hasattr(m, "reactive_atoms_classes_dict") for m in mols):
+        ratoms0 = [np.array([[int(idx), int(ra.cumnum)] for idx, ra in m.reactive_atoms_classes_dict[0].items()],
+                            dtype=np.int64).reshape(-1, 2) for m in mols]
     return CyclicalProblem(
         coords=coords, reactive=[np.asarray(m.reactive_indices, dtype=np.int64) for m in mols],
         pivot_vec=pv, pivot_mean=pm, pivot_ids=pi,
@@ -113,4 +128,5 @@ def cyclical_problem(embedder, max_norm_delta: float = 5.0) -> CyclicalProblem:
         pairings=[tuple(int(x) for x in pair) for pair in table.values()],
         internal_constraints_is_array=isinstance(ic, np.ndarray),
         internal_constraints=np.asarray(ic).tolist() if len(ic) else [],
-        max_norm_delta=float(max_norm_delta))
+        max_norm_delta=float(max_norm_delta), ratoms0=ratoms0,
+        ids=[int(x) for x in embedder.ids])

@@ -110,7 +110,7 @@ typedef struct fc_tie {
 typedef struct fc_result fc_result;
 void fc_result_free(fc_result* r);
 /* out10 = {poses screened, clash survivors, FP64 rechecks, kept, near-threshold decisions,
- *          atoms per pose, stage-1 survivors, quadruplets, constrained pairs per pose, 0} */
+ *          atoms per pose, stage-1 survivors, quadruplets, constrained pairs per pose, groups} */
 int fc_result_counts(const fc_result* r, int64_t* out10);
 int fc_result_status(const fc_result* r, uint8_t* out);         /* (poses screened) FC_STATUS_* */
 int fc_result_survivors(const fc_result* r, int64_t* out);      /* (survivors) pose indices      */
@@ -119,6 +119,9 @@ int fc_result_kept_indices(const fc_result* r, int64_t* out);   /* (kept) pose i
 int fc_result_kept_coords(const fc_result* r, double* out);     /* (kept, atoms per pose, 3)     */
 int fc_result_constrained(const fc_result* r, int32_t* out);    /* (kept, n_pairs, 2)            */
 int64_t fc_result_ties(const fc_result* r, fc_tie* out, int64_t cap); /* returns total recorded  */
+/* trimolecular embeds: per group the grid-search candidate (0..342) chosen by the restated
+ * _adjust_directions (embeds.py:403-405) and the cost gap (degrees) to the runner-up */
+int fc_result_groups(const fc_result* r, int32_t* choice, double* gap);
 
 /* String embed: replaces embeds.py:51-158 `string_embed(embedder)`.
  * Pose index = enumeration order of the reference loops (conformer pairs in cartesian_product
@@ -172,6 +175,40 @@ typedef struct fc_cyclical_problem {
 } fc_cyclical_problem;
 
 int fc_cyclical_screen(const fc_cyclical_problem* p, fc_result** out);
+
+/* Cyclical embed, trimolecular body: replaces embeds.py:409-585 (`cyclical_embed` for three
+ * molecules) including `_get_directions` (embeds.py:188-254) and the stateful 343-point grid search
+ * `_adjust_directions` (embeds.py:256-407).  The library enumerates (conformer triple, pivot
+ * triple) super-groups in the reference's loop order (cartesian_product order, utils.py:219-221:
+ * third index fastest, then the first, the second outermost), drops impossible triangles
+ * (embeds.py:447-462), applies the pairing filter per polygon orientation (embeds.py:473-476) and
+ * expands every surviving (super-group, orientation) group into n_angles poses.
+ * Pose index = group * n_angles + angle index, groups numbered in loop order.
+ * Clash test = the three-block `<=` branch utils.py:553-575 with max_clashes = 0; because block
+ * (i, j) only depends on the angles of molecules i and j, each block is screened once per distinct
+ * (angle_i, angle_j) pair of the angle table (36 instead of 216 for the default 6x6x6 grid).
+ * Pivot tables are CSR over conformers: rows pivot_offsets[m][c] .. pivot_offsets[m][c+1]. */
+typedef struct fc_cyclical3_problem {
+    const double* coords[3];  int32_t n_conf[3], n_atoms[3];
+    const int64_t* reactive[3]; int32_t n_reactive[3];   /* Hypermolecule.reactive_indices (1 or 2)  */
+    const int64_t* pivot_offsets[3];  /* (n_conf + 1)                                                */
+    const double* pivot_vec[3];       /* (rows, 3) Pivot.pivot                                       */
+    const double* pivot_mean[3];      /* (rows, 3) Pivot.meanpoint                                   */
+    const int64_t* pivot_ids[3];      /* (rows, 2) start_atom.cumnum, end_atom.cumnum                */
+    const int64_t* ratoms0[3]; int32_t n_ratoms0[3];  /* (k, 2) {index, cumnum} of conformer 0's
+                                                         reactive atoms, dict order (embeds.py:330)  */
+    const double* angles; int32_t n_angles;           /* (n_angles, 3) embedder.systematic_angles    */
+    const int64_t* pairings; int32_t n_pairings;      /* (n, 2) embedder.pairings_table.values()     */
+    const int64_t* internal; int32_t n_internal;      /* (n, 2) internal constraints a pairing may
+                                                         match (empty for the ndarray quirk N10)     */
+    double thresh; int32_t rot_handedness; double rmsd_thresh;
+    int64_t conf_tuple_lo, conf_tuple_hi; /* slice of the conformer-triple enumeration (hi <= 0: all) */
+    int32_t flags;                        /* FC_CYC3_* */
+} fc_cyclical3_problem;
+#define FC_CYC3_NO_STATUS 1 /* do not return the per-pose status bytes  */
+#define FC_CYC3_NO_COORDS 2 /* do not materialise the kept poses        */
+
+int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** out);
 
 /* Ensemble similarity pruning: replaces prism_pruner.pruner.prune_by_rmsd (mode 0) and
  * prune_by_moment_of_inertia (mode 1) as called at embedder.py:1452,1472; ensemble.py:211,230;

@@ -46,8 +46,9 @@ def pack_cyclical_problem(prob):
            "pairings": np.array(prob.pairings, dtype=np.int64).reshape(-1, 2),
            "internal_constraints": np.array(prob.internal_constraints, dtype=np.int64).reshape(-1, 2),
            "internal_constraints_is_array": np.bool_(prob.internal_constraints_is_array),
-           "max_norm_delta": np.float64(prob.max_norm_delta)}
+           "max_norm_delta": np.float64(prob.max_norm_delta), "ids": np.array(prob.ids, dtype=np.int64)}
     for m in range(prob.n_mols):
+        out[f"ratoms0_{m}"] = np.asarray(prob.ratoms0[m], dtype=np.int64).reshape(-1, 2)
         out[f"coords{m}"] = prob.coords[m]
         out[f"reactive{m}"] = prob.reactive[m]
         counts = np.array([len(p) for p in prob.pivot_vec[m]], dtype=np.int64)
@@ -56,6 +57,12 @@ def pack_cyclical_problem(prob):
         out[f"pivot_mean{m}"] = np.concatenate(prob.pivot_mean[m]).reshape(-1, 3)
         out[f"pivot_ids{m}"] = np.concatenate(prob.pivot_ids[m]).reshape(-1, 2)
     return out
+
+
+SYNTH_TRIMOL = {
+    "synth_trimol_a": dict(n_conf=2, n_atoms=12, seed=3, n_mols=3, n_reactive=2, n_orb=1),
+    "synth_trimol_b": dict(n_conf=[1, 2, 1], n_atoms=[16, 12, 14], seed=21, n_mols=3, n_reactive=1, n_orb=2),
+}
 
 
 def main():
@@ -84,6 +91,23 @@ def main():
                                 conventions=np.array(conv), **data)
             print(f"{name}: embed={emb.embed} candidates={emb.candidates} kept={len(structures)}"
                   f"{' (ZeroCandidatesError)' if zero else ''}")
+    # seeded synthetic trimolecular embedders through the UNMODIFIED reference cyclical_embed
+    # (the reference's own trimolecular fixture yields zero candidates)
+    import contextlib
+    import io
+
+    from firecode.embeds import cyclical_embed
+    from synth_embedder import make_embedder
+
+    for name, kw in SYNTH_TRIMOL.items():
+        emb = make_embedder("cyclical", **kw)
+        data = pack_cyclical_problem(problem.cyclical_problem(emb))
+        with contextlib.redirect_stdout(io.StringIO()):
+            structures = cyclical_embed(emb)
+        np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), embed=np.array("cyclical"),
+                            ref_structures=structures, ref_constrained=np.asarray(emb.constrained_indices),
+                            zero_candidates=np.bool_(False), conventions=np.array(conv), **data)
+        print(f"{name}: kept={len(structures)}")
 
 
 if __name__ == "__main__":

@@ -349,6 +349,235 @@ def cyclical_embed_bimol(prob, ties=None, rmsd_thr=1.0, want_poses=True):
 
 
 # ------------------------------------------------------------------------------------------------
+# cyclical embed, trimolecular body -- firecode/embeds.py:188-585
+# ------------------------------------------------------------------------------------------------
+def triangle_vertices(norms):
+    """Planar triangle (0,0), (l0,0), (x,y) used by embeds.py:198-209 and 288-299."""
+    vertices = np.zeros((3, 2))
+    vertices[1] = np.array([norms[0], 0])
+    a = np.power(norms[0], 2)
+    b = np.power(norms[1], 2)
+    c = np.power(norms[2], 2)
+    x = (a - b + c) / (2 * a**0.5)
+    y = (c - x**2) ** 0.5
+    vertices[2] = np.array([x, y])
+    return vertices
+
+
+def get_directions3(norms):
+    """embeds.py:188-254 for three molecules.  ``norms`` is mutated in place in the right-triangle
+    case (embeds.py:232-237, quirk N7) exactly as the reference does."""
+    alg, _ = _shim()
+    vertices = triangle_vertices(norms)
+    a = vertices[1, 0]
+    b = vertices[2, 0]
+    c = vertices[2, 1]
+    x = a / 2
+    y = (b**2 + c**2 - a * b) / (2 * c)
+    cc = np.array([x, y])
+    v0, v1, v2 = vertices
+    meanpoint1 = np.mean((v0, v1), axis=0)
+    meanpoint2 = np.mean((v1, v2), axis=0)
+    meanpoint3 = np.mean((v2, v0), axis=0)
+    dir1 = cc - meanpoint1
+    dir2 = cc - meanpoint2
+    dir3 = cc - meanpoint3
+    if np.any([np.all(d == 0) for d in (dir1, dir2, dir3)]):
+        norms[0] += 1e-5
+        dir1, dir2, dir3 = [t[:-1] for t in get_directions3(norms)]
+    angle0_obtuse = alg.vec_angle(v1 - v0, v2 - v0) > 90
+    angle1_obtuse = alg.vec_angle(v0 - v1, v2 - v1) > 90
+    angle2_obtuse = alg.vec_angle(v0 - v2, v1 - v2) > 90
+    dir1 = -dir1 if angle2_obtuse else dir1
+    dir2 = -dir2 if angle0_obtuse else dir2
+    dir3 = -dir3 if angle1_obtuse else dir3
+    dir1 = alg.normalize(np.concatenate((dir1, [0])))
+    dir2 = alg.normalize(np.concatenate((dir2, [0])))
+    dir3 = alg.normalize(np.concatenate((dir3, [0])))
+    return np.vstack((dir1, dir2, dir3))
+
+
+def facing_table(prob, constrained_indices):
+    """r[m, partner] = index (in molecule m) of the reactive atom facing ``partner``
+    (embeds.py:328-353; matched through the cumnum of conformer 0's reactive atoms)."""
+    pairings = [[(-1, -1), (-1, -1)] for _ in constrained_indices]
+    for i, c in enumerate(constrained_indices):
+        for m in range(prob.n_mols):
+            for index, cumnum in prob.ratoms0[m]:
+                if cumnum == c[0]:
+                    pairings[i][0] = (m, int(index))
+                if cumnum == c[1]:
+                    pairings[i][1] = (m, int(index))
+    r = np.zeros((3, 3), dtype=int)
+    for first, second in pairings:
+        r[first[0], second[0]] = first[1]
+        r[second[0], first[0]] = second[1]
+    return r
+
+
+def adjust_directions(prob, norms, directions, constrained_indices, triangle_vectors, pivot_vec, pivot_mean,
+                      conf_ids, choice=None):
+    """embeds.py:256-407.  Returns (directions (3,3), index of the chosen candidate, cost gap to the
+    runner-up).  ``choice`` forces the candidate (parity tests condition the oracle on a listed
+    near-tie of the 343-point grid search)."""
+    alg, _ = _shim()
+    from firecode_b200.utils import cartesian_product
+
+    p0, p1, p2 = [end - start for start, end in triangle_vectors]
+    p0_mean, p1_mean, p2_mean = [np.mean((end, start), axis=0) for start, end in triangle_vectors]
+    vertices = triangle_vertices(norms)
+    v0, v1, v2 = [np.concatenate((v, [0])) for v in vertices]
+    rot, pos = [], []
+    for i in (0, 1, 2):
+        start, end = triangle_vectors[i]
+        mol_direction = pivot_mean[i] - np.mean(prob.coords[i][conf_ids[i]][prob.reactive[i]], axis=0)
+        if np.all(mol_direction == 0.0):
+            mol_direction = pivot_mean[i]
+        rot.append(align_vec_pair(np.array([end - start, directions[i]]), np.array([pivot_vec[i], mol_direction])))
+        pos.append(np.mean(triangle_vectors[i], axis=0) - rot[i] @ pivot_mean[i])
+    r = facing_table(prob, constrained_indices)
+    # reactive atom positions are read from CONFORMER 0 (embeds.py:359-366, quirk N6)
+    a01 = rot[0] @ prob.coords[0][0][r[0, 1]] + pos[0]
+    a02 = rot[0] @ prob.coords[0][0][r[0, 2]] + pos[0]
+    a10 = rot[1] @ prob.coords[1][0][r[1, 0]] + pos[1]
+    a12 = rot[1] @ prob.coords[1][0][r[1, 2]] + pos[1]
+    a20 = rot[2] @ prob.coords[2][0][r[2, 0]] + pos[2]
+    a21 = rot[2] @ prob.coords[2][0][r[2, 1]] + pos[2]
+    steps = 6
+    angle_range = 30
+    step_angle = 2 * angle_range / steps
+    angles_list = cartesian_product(*[range(steps + 1) for _ in range(3)]) * step_angle - angle_range
+    costs, dirs = [], []
+    for angles in angles_list:
+        rot0 = alg.rot_mat_from_pointer(p0, angles[0])
+        new_a01 = rot0 @ a01
+        new_a02 = rot0 @ a02
+        d0 = p0_mean - np.mean((new_a01, new_a02), axis=0)
+        rot1 = alg.rot_mat_from_pointer(p1, angles[1])
+        new_a10 = rot1 @ a10
+        new_a12 = rot1 @ a12
+        d1 = p1_mean - np.mean((new_a10, new_a12), axis=0)
+        rot2 = alg.rot_mat_from_pointer(p2, angles[2])
+        new_a20 = rot2 @ a20
+        new_a21 = rot2 @ a21
+        d2 = p2_mean - np.mean((new_a20, new_a21), axis=0)
+        cost = 0
+        cost += alg.vec_angle(v0 - new_a02, new_a20 - v0)
+        cost += alg.vec_angle(v1 - new_a01, new_a10 - v1)
+        cost += alg.vec_angle(v2 - new_a21, new_a12 - v2)
+        costs.append(cost)
+        dirs.append((d0, d1, d2))
+    order = sorted(range(len(costs)), key=lambda k: costs[k])  # stable: first minimum wins (embeds.py:405)
+    best = order[0]
+    gap = costs[order[1]] - costs[best]
+    if choice is not None:
+        best = int(choice)
+    return np.array(dirs[best]), best, float(gap)
+
+
+def cyclical_groups_trimol(prob):
+    """(conformer triple, pivot triple) super-groups that form a triangle, in the reference's loop
+    order (embeds.py:414-462), each with its 8 orientations' atom couples and pairing-filter flags."""
+    from firecode_b200.utils import cartesian_product
+
+    out = []
+    n_conf = [len(c) for c in prob.coords]
+    for conf_ids in cartesian_product(*[np.arange(n) for n in n_conf]):
+        counts = [len(prob.pivot_vec[m][conf_ids[m]]) for m in range(3)]
+        if min(counts) == 0:
+            continue
+        for pi in cartesian_product(*[np.arange(k) for k in counts]):
+            pv = [prob.pivot_vec[m][conf_ids[m]][pi[m]] for m in range(3)]
+            norms = np.linalg.norm(np.array(pv), axis=1)
+            if not all(norms[i] < norms[i - 1] + norms[i - 2] for i in (0, 1, 2)):  # embeds.py:447
+                continue
+            pid = [prob.pivot_ids[m][conf_ids[m]][pi[m]] for m in range(3)]
+            ids = [cyclical_reactive_indices(pid, v, 3) for v in range(8)]
+            out.append({"conf": tuple(int(c) for c in conf_ids), "piv": tuple(int(p) for p in pi),
+                        "norms": norms, "ids": ids, "active": [pairing_filter(prob, i) for i in ids]})
+    return out
+
+
+def cyclical_embed_trimol(prob, ties=None, rmsd_thr=1.0, want_poses=True, forced_choice=None, choice_eps=0.0):
+    """Reference loop of cyclical_embed for three molecules (embeds.py:409-585) on a CyclicalProblem.
+
+    Group = (super-group, orientation v) passing the pairing filter, numbered in loop order;
+    pose index = group * n_angles + angle index.  ``forced_choice`` {group: candidate} overrides the
+    grid-search argmin of _adjust_directions where its runner-up gap is below ``choice_eps``."""
+    import operator
+
+    ties = ties or Ties()
+    assert prob.n_mols == 3
+    supers = cyclical_groups_trimol(prob)
+    n_ang = len(prob.angles)
+    kept, poses, constrained, groups, clash_pass = [], [], [], [], []
+    near_choice = {}
+    for sg in supers:
+        c = sg["conf"]
+        pv = [prob.pivot_vec[m][c[m]][sg["piv"][m]] for m in range(3)]
+        pm = [prob.pivot_mean[m][c[m]][sg["piv"][m]] for m in range(3)]
+        norms = sg["norms"].copy()
+        polygon_vectors = polygonize(norms)          # embeds.py:453 (before any perturbation of norms)
+        directions = get_directions3(norms)          # may perturb norms[0] in place (N7)
+        for v in range(8):
+            if not sg["active"][v]:
+                continue
+            g = len(groups)
+            vecs = polygon_vectors[v]
+            ids = sg["ids"][v]
+            force = None
+            directions_in = directions
+            directions, best, gap = adjust_directions(prob, norms, directions_in, ids, vecs, pv, pm, c)
+            if gap <= choice_eps:
+                near_choice[g] = (best, gap)
+                if forced_choice is not None and g in forced_choice and forced_choice[g] != best:
+                    force = forced_choice[g]
+                    directions, best, gap = adjust_directions(prob, norms, directions_in, ids, vecs, pv, pm, c,
+                                                              choice=force)
+            groups.append({"conf": c, "piv": sg["piv"], "v": v, "ids": ids, "directions": directions.copy(),
+                           "choice": best, "gap": gap})
+            angular, angular_idx = [], []
+            for ai, angles in enumerate(prob.angles):
+                parts = []
+                for i in range(3):
+                    rot, pos = cyclical_molecule_transform(prob, i, c[i], pv[i], pm[i], vecs[i], directions[i],
+                                                           angles[i])
+                    parts.append((rot @ prob.coords[i][c[i]].T).T + pos)
+                structure = np.concatenate(parts)
+                pose = g * n_ang + ai
+                n1, n2 = prob.ids[0], prob.ids[0] + prob.ids[1]
+                m1, m2, m3 = structure[:n1], structure[n1:n2], structure[n2:]
+                ok = True
+                for blk, (x, y) in enumerate(((m2, m1), (m3, m2), (m1, m3))):   # utils.py:563-571
+                    d = float(cdist(x, y).min())
+                    if ties.decide(("clash3", pose, blk), d, prob.thresh, operator.le):
+                        ok = False
+                        break
+                clash_pass.append(ok)
+                if not ok:
+                    continue
+                similar = False
+                for ref_pose, ref in zip(angular_idx, angular):  # utils.py:494-504
+                    r, m = rmsd_and_max(structure, ref)
+                    if ties.decide(("rmsd", pose, ref_pose), r, rmsd_thr, operator.lt) and \
+                            ties.decide(("maxdev", pose, ref_pose), m, 2 * rmsd_thr, operator.lt):
+                        similar = True
+                        break
+                if not similar:
+                    angular.append(structure)
+                    angular_idx.append(pose)
+                    kept.append(pose)
+                    constrained.append(ids)
+                    if want_poses:
+                        poses.append(structure)
+    n_tot = sum(c.shape[1] for c in prob.coords)
+    return {"kept": np.array(kept, dtype=np.int64), "groups": groups,
+            "poses": np.array(poses).reshape(len(poses), n_tot, 3) if want_poses else None,
+            "constrained": np.array(constrained, dtype=np.int64).reshape(len(kept), 3, 2),
+            "clash_pass": np.array(clash_pass, dtype=bool), "ties": ties, "near_choice": near_choice}
+
+
+# ------------------------------------------------------------------------------------------------
 # torsion rotation + clash -- torsion_module.py:354-382, 894-918 and prism_pruner.utils.rotate_dihedral
 # ------------------------------------------------------------------------------------------------
 def rotation_mask(graph, torsion):
