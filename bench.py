@@ -379,6 +379,17 @@ def run_extras():
     out["C2_cyclical_embed_bimolecular"] = {"poses_per_s": rep.n_poses / dt, "poses": rep.n_poses, "kept": rep.n_kept,
                                             "clash_pass": rep.n_clash_pass, "seconds": dt,
                                             "note": "includes host-side group enumeration (python)"}
+    # C2 (BASELINE.json configs[1]): trimolecular cyclical embed, 3 x (50 conformers, 60 atoms), one pivot per
+    # molecule, 8 orientations, 216 angle triples = 125 000 conformer triples -> 1 M groups -> 216 M poses
+    emb = make_embedder("cyclical", 50, 60, seed=synthetic.SEED + 2, n_mols=3, n_reactive=2, n_orb=1)
+    tprob = problem.cyclical_problem(emb)
+    dt, (poses, cons, rep) = timed(lambda: embeds.cyclical3_screen(tprob, want_status=False, want_coords=False), reps=1)
+    out["C2_cyclical_embed_trimolecular"] = {
+        "poses_per_s": rep.n_poses / dt, "poses": rep.n_poses, "groups": int(len(rep.group_choice)),
+        "kept": rep.n_kept, "clash_pass": rep.n_clash_pass, "seconds": dt,
+        "min_direction_search_gap_deg": float(rep.group_gap.min()) if len(rep.group_gap) else None,
+        "note": "full C2: group enumeration (C++), stateful 343-point direction search, 3 block screens over 36 "
+                "distinct angle pairs each, keep-first RMSD; kept-pose coordinates not materialised"}
     # C4-like RMSD pruning: 20 000 conformers of a 120-atom molecule (400 basins)
     rng = np.random.default_rng(synthetic.SEED + 4)
     atoms, structures, _ = synthetic.pruning_ensemble(rng, 20000, 120, 400)

@@ -168,3 +168,49 @@ def string_embed_sharded(embedder, group=None):
     embedder.constrained_indices = np.repeat(prob.constrained[None], len(poses), axis=0)
     del keep_alive
     return poses
+
+
+def cyclical_embed_sharded(embedder, group=None, screen=None, max_norm_delta=5.0):
+    """cyclical_embed (embeds.py:180-585) over all ranks of ``group``.
+
+    Units are whole groups: conformer-triple ranges for three molecules (the stateful direction
+    search never crosses a conformer triple), slices of the host group table for two.  Each rank
+    screens its units, then kept pose indices, coordinates and constrained indices are all-gathered
+    in rank order = the reference's enumeration order; every rank returns the same arrays.
+    ``screen(prob, lo, hi) -> (poses, constrained, n_poses_screened, kept_local)`` replaces the CUDA
+    path in the CPU tests."""
+    from . import embeds, problem
+    from .errors import ZeroCandidatesError
+
+    rank, world = world_info(group)
+    prob = problem.cyclical_problem(embedder, max_norm_delta=max_norm_delta)
+    if prob.n_mols == 3:
+        n_units = int(np.prod([len(c) for c in prob.coords]))
+        if screen is None:
+            def screen(pb, lo, hi):
+                poses, cons, rep = embeds.cyclical3_screen(pb, conf_tuple_range=(lo, hi), want_status=False)
+                return poses, cons, rep.n_poses, rep.kept_indices
+    else:
+        groups = embeds.cyclical_groups(prob)
+        n_units = len(groups["conf"])
+        if screen is None:
+            def screen(pb, lo, hi):
+                poses, cons, rep = embeds.cyclical_screen(pb, group_range=(lo, hi), groups=groups)
+                return poses, cons, rep.n_poses, rep.kept_indices
+    lo, hi = shard_bounds(n_units, world, rank)
+    n_tot = sum(int(c.shape[1]) for c in prob.coords)
+    if hi > lo:
+        poses, cons, n_local, kept_local = screen(prob, lo, hi)
+    else:
+        poses, cons, n_local, kept_local = (np.zeros((0, n_tot, 3)), np.zeros((0, prob.n_mols, 2), dtype=np.int64), 0,
+                                            np.zeros(0, dtype=np.int64))
+    counts = all_gather_varlen(np.array([n_local], dtype=np.int64), group)
+    base = int(counts[:rank].sum())
+    kept = all_gather_varlen(np.asarray(kept_local, dtype=np.int64) + base, group)
+    poses = all_gather_varlen(np.asarray(poses, dtype=np.float64).reshape(-1, n_tot, 3), group)
+    cons = all_gather_varlen(np.asarray(cons, dtype=np.int64).reshape(len(kept_local), prob.n_mols, 2), group)
+    embedder.constrained_indices = cons
+    embedder.b200_kept_indices = kept
+    if len(poses) == 0:
+        raise ZeroCandidatesError("cyclical embed: no pose survived")
+    return poses

@@ -261,11 +261,14 @@ def cyclical_groups(prob: problem.CyclicalProblem):
     }
 
 
-def cyclical_screen(prob: problem.CyclicalProblem, rmsd_thresh=1.0):
-    """Run the bimolecular cyclical screen on the current CUDA device.
+def cyclical_screen(prob: problem.CyclicalProblem, rmsd_thresh=1.0, group_range=None, groups=None):
+    """Run the bimolecular cyclical screen on the current CUDA device.  ``group_range`` = (lo, hi)
+    restricts the call to a slice of the group table (multi-GPU sharding).
     Returns (poses, constrained_indices, ScreenReport)."""
     lib = _lib.load(require_device=True)
-    groups = cyclical_groups(prob)
+    groups = groups if groups is not None else cyclical_groups(prob)
+    if group_range is not None:
+        groups = {k: np.ascontiguousarray(v[group_range[0]:group_range[1]]) for k, v in groups.items()}
     keep = {"coords": [np.ascontiguousarray(c, dtype=np.float64) for c in prob.coords],
             "reactive": [np.ascontiguousarray(r, dtype=np.int64) for r in prob.reactive],
             "angles": np.ascontiguousarray(prob.angles, dtype=np.float64).reshape(-1, 2), **groups}

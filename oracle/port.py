@@ -475,14 +475,16 @@ def adjust_directions(prob, norms, directions, constrained_indices, triangle_vec
     return np.array(dirs[best]), best, float(gap)
 
 
-def cyclical_groups_trimol(prob):
+def cyclical_groups_trimol(prob, conf_tuple_range=None):
     """(conformer triple, pivot triple) super-groups that form a triangle, in the reference's loop
     order (embeds.py:414-462), each with its 8 orientations' atom couples and pairing-filter flags."""
     from firecode_b200.utils import cartesian_product
 
     out = []
     n_conf = [len(c) for c in prob.coords]
-    for conf_ids in cartesian_product(*[np.arange(n) for n in n_conf]):
+    for t, conf_ids in enumerate(cartesian_product(*[np.arange(n) for n in n_conf])):
+        if conf_tuple_range is not None and not (conf_tuple_range[0] <= t < conf_tuple_range[1]):
+            continue
         counts = [len(prob.pivot_vec[m][conf_ids[m]]) for m in range(3)]
         if min(counts) == 0:
             continue
@@ -498,7 +500,8 @@ def cyclical_groups_trimol(prob):
     return out
 
 
-def cyclical_embed_trimol(prob, ties=None, rmsd_thr=1.0, want_poses=True, forced_choice=None, choice_eps=0.0):
+def cyclical_embed_trimol(prob, ties=None, rmsd_thr=1.0, want_poses=True, forced_choice=None, choice_eps=0.0,
+                          conf_tuple_range=None):
     """Reference loop of cyclical_embed for three molecules (embeds.py:409-585) on a CyclicalProblem.
 
     Group = (super-group, orientation v) passing the pairing filter, numbered in loop order;
@@ -508,7 +511,7 @@ def cyclical_embed_trimol(prob, ties=None, rmsd_thr=1.0, want_poses=True, forced
 
     ties = ties or Ties()
     assert prob.n_mols == 3
-    supers = cyclical_groups_trimol(prob)
+    supers = cyclical_groups_trimol(prob, conf_tuple_range)
     n_ang = len(prob.angles)
     kept, poses, constrained, groups, clash_pass = [], [], [], [], []
     near_choice = {}

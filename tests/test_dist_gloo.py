@@ -72,6 +72,19 @@ def _worker(rank, world, port, q):
         kept, all_labels, _ = fdist.ordered_keep_first(labels, fps, keep_fn)
         assert np.array_equal(all_labels, np.flatnonzero(ref["clash_pass"]))
         assert np.array_equal(kept, ref["kept"])
+
+        # 4) cyclical embeds sharded over whole groups == single-process oracle (tri- and bimolecular)
+        emb3 = make_embedder("cyclical", [2, 1, 1], 10, seed=17, n_mols=3, n_reactive=2, n_orb=1)
+        prob3 = problem.cyclical_problem(emb3)
+        ref3 = oport.cyclical_embed_trimol(prob3)
+
+        def screen3(pb, lo, hi):
+            o = oport.cyclical_embed_trimol(pb, conf_tuple_range=(lo, hi))
+            return o["poses"], o["constrained"], len(o["clash_pass"]), o["kept"]
+
+        poses3 = fdist.cyclical_embed_sharded(emb3, screen=screen3)
+        assert np.array_equal(poses3, ref3["poses"]) and np.array_equal(emb3.b200_kept_indices, ref3["kept"])
+        assert np.array_equal(emb3.constrained_indices, ref3["constrained"])
         q.put((rank, "ok"))
     except Exception as exc:  # pragma: no cover
         import traceback
