@@ -160,6 +160,7 @@ struct ClashArgs {
     int n_a_pad, n_b_pad, chunks, poses;
     float thr2;
     int count_mode;  // max_clashes > 0: FP32 pass may only prove "no pair can clash"
+    int use_tma;     // transforms of a tile arrive by cp.async.bulk (xf 16-byte aligned)
     uint8_t* status;
     float* min_dist;
     int* unc_count;
@@ -171,48 +172,93 @@ struct ClashLaunch {
     static constexpr int kMaxThreads = TB >= 25 ? 256 : (TB >= 20 ? 384 : 512);
 };
 
-__device__ __forceinline__ f32x2 fma2v(f32x2 a, f32x2 b, f32x2 c) {  // volatile: keeps program order
-    f32x2 d;
-    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
+// ---- TMA (bulk async copy) + mbarrier plumbing for the per-tile transform block ----------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
 }
 
-// VAR bit0: chain-major program order (volatile FFMA2), bit1: FMNMX3 instead of two FMNMX
-template <int TB, int VAR>
+// tile -> (conformers, first pose, pose count)
+__device__ __forceinline__ void clash_tile(const ClashArgs& p, long long tile, int& conf_a, int& conf_b, long long& first,
+                                           int& count) {
+    conf_a = 0;
+    conf_b = 0;
+    if (p.tiles) {
+        int4 t = p.tiles[tile];
+        conf_a = t.x;
+        conf_b = t.y;
+        first = t.z;
+        count = t.w;
+    } else {
+        first = tile * p.poses;
+        long long left = p.n_poses - first;
+        count = left < p.poses ? (int)left : p.poses;
+    }
+}
+
+// UNR: unroll factor of the loop over A atom pairs (ptxas orders the FFMA2s of one A pair component-major
+// over all TB chains and fuses the two minima into FMNMX3 whatever the source order is)
+template <int TB, int UNR, int PF>
 __global__ void __launch_bounds__(ClashLaunch<TB>::kMaxThreads, 1) clash_f32_kernel(ClashArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ulonglong2* sA = reinterpret_cast<ulonglong2*>(smem_raw);                  // n_a_pad entries
-    float4* sB = reinterpret_cast<float4*>(smem_raw + (size_t)p.n_a_pad * 16);  // n_b_pad entries
-    int* sMin = reinterpret_cast<int*>(smem_raw + (size_t)p.n_a_pad * 16 + (size_t)p.n_b_pad * 16);
+    float4* sB = reinterpret_cast<float4*>(smem_raw + (size_t)(p.n_a_pad + 2) * 16);  // n_b_pad entries
+    size_t off = (size_t)(p.n_a_pad + 2) * 16 + (size_t)p.n_b_pad * 16;
+    double* sXf = reinterpret_cast<double*>(smem_raw + off);                   // 2 x poses x 12 transforms
+    off += (size_t)2 * p.poses * 96;
+    unsigned long long* sBar = reinterpret_cast<unsigned long long*>(smem_raw + off);  // 2 mbarriers
+    off += 16;
+    int* sMin = reinterpret_cast<int*>(smem_raw + off);
 
     const int tid = threadIdx.x;
     const int pose_local = tid / p.chunks;
     const int chunk = tid - pose_local * p.chunks;
     const bool lane_used = pose_local < p.poses;
+    const unsigned bar0 = smem_u32(sBar), xf0 = smem_u32(sXf);
 
     int cur_a = -1, cur_b = -1;
     for (int i = tid; i < p.poses; i += blockDim.x) sMin[i] = 0x7fffffff;
-
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        int conf_a = 0, conf_b = 0, count;
-        long long first;
-        if (p.tiles) {
-            int4 t = p.tiles[tile];
-            conf_a = t.x;
-            conf_b = t.y;
-            first = t.z;
-            count = t.w;
-        } else {
-            first = tile * p.poses;
-            long long left = p.n_poses - first;
-            count = left < p.poses ? (int)left : p.poses;
+    if (p.use_tma && tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((long long)blockIdx.x < p.n_tiles) {  // transforms of the first tile
+            int ca, cb, cnt;
+            long long fst;
+            clash_tile(p, blockIdx.x, ca, cb, fst, cnt);
+            tma_load_1d(xf0, p.xf + fst * 12, (unsigned)cnt * 96u, bar0);
         }
+    }
+    __syncthreads();
+
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        int conf_a, conf_b, count;
+        long long first;
+        clash_tile(p, tile, conf_a, conf_b, first, count);
         if (conf_a != cur_a || conf_b != cur_b) {
             __syncthreads();  // everybody is done with the previous tables
             if (conf_a != cur_a) {
                 const ulonglong2* src =
                     reinterpret_cast<const ulonglong2*>(p.a_tab) + (size_t)conf_a * p.n_a_pad;
                 for (int i = tid; i < p.n_a_pad; i += blockDim.x) sA[i] = src[i];
+                if (tid < 2) sA[p.n_a_pad + tid] = make_ulonglong2(0ull, 0ull);
             }
             if (conf_b != cur_b) {
                 const float4* src = p.b_tab + (size_t)conf_b * p.n_b_pad;
@@ -221,17 +267,39 @@ __global__ void __launch_bounds__(ClashLaunch<TB>::kMaxThreads, 1) clash_f32_ker
             cur_a = conf_a;
             cur_b = conf_b;
         }
-        __syncthreads();  // tables + sMin reset visible
+        __syncthreads();  // tables + sMin reset visible; previous tile's transform buffer is free
+        const int buf = it & 1;
+        if (p.use_tma) {
+            if (tid == 0 && tile + gridDim.x < p.n_tiles) {  // prefetch the next tile's transforms
+                int ca, cb, cnt;
+                long long fst;
+                clash_tile(p, tile + gridDim.x, ca, cb, fst, cnt);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tma_load_1d(xf0 + (unsigned)(buf ^ 1) * (unsigned)p.poses * 96u, p.xf + fst * 12, (unsigned)cnt * 96u,
+                            bar0 + 8u * (unsigned)(buf ^ 1));
+            }
+            mbar_wait(bar0 + 8u * (unsigned)buf, (unsigned)(it >> 1) & 1u);
+        }
 
         const bool active = lane_used && pose_local < count;
         const long long pose = first + pose_local;
         float tnorm = 0.f;
         if (active) {
             // ---- transform this thread's TB atoms of fragment B --------------------------------
-            const double* x = p.xf + pose * 12;
             float r[12];
+            if (p.use_tma) {
+                const double* x = sXf + (size_t)buf * p.poses * 12 + (size_t)pose_local * 12;
 #pragma unroll
-            for (int k = 0; k < 12; ++k) r[k] = (float)__ldg(x + k);
+                for (int k = 0; k < 12; k += 2) {
+                    double2 v = *reinterpret_cast<const double2*>(x + k);
+                    r[k] = (float)v.x;
+                    r[k + 1] = (float)v.y;
+                }
+            } else {
+                const double* x = p.xf + pose * 12;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) r[k] = (float)__ldg(x + k);
+            }
             tnorm = sqrtf(fmaf(r[9], r[9], fmaf(r[10], r[10], r[11] * r[11])));
 
             float bx[TB], by[TB], bz[TB], m[TB];
@@ -246,24 +314,36 @@ __global__ void __launch_bounds__(ClashLaunch<TB>::kMaxThreads, 1) clash_f32_ker
 
             // ---- all atom pairs: two A atoms per step, broadcast from shared memory ------------
             const int n_pairs = p.n_a_pad >> 1;
-#pragma unroll 2
-            for (int i = 0; i < n_pairs; ++i) {
-                ulonglong2 u0 = sA[2 * i], u1 = sA[2 * i + 1];
+            if (PF) {
+                // A pair of step i + 1 is fetched into its own registers while step i computes, so the
+                // first FFMA2 of a step never waits for shared memory (sA holds one padding pair)
+                ulonglong2 u0 = sA[0], u1 = sA[1];
+#pragma unroll UNR
+                for (int i = 0; i < n_pairs; ++i) {
+                    ulonglong2 v0 = sA[2 * i + 2], v1 = sA[2 * i + 3];
 #pragma unroll
-                for (int j = 0; j < TB; ++j) {
-                    f32x2 e;
-                    if (VAR & 1)
-                        e = fma2v(u0.x, pack2(bx[j], bx[j]),
-                                  fma2v(u0.y, pack2(by[j], by[j]), fma2v(u1.x, pack2(bz[j], bz[j]), u1.y)));
-                    else
-                        e = fma2(u0.x, pack2(bx[j], bx[j]),
-                                 fma2(u0.y, pack2(by[j], by[j]), fma2(u1.x, pack2(bz[j], bz[j]), u1.y)));
-                    float lo, hi;
-                    unpack2(e, lo, hi);
-                    if (VAR & 2)
-                        m[j] = min3(m[j], lo, hi);
-                    else
+                    for (int j = 0; j < TB; ++j) {
+                        f32x2 e = fma2(u0.x, pack2(bx[j], bx[j]),
+                                       fma2(u0.y, pack2(by[j], by[j]), fma2(u1.x, pack2(bz[j], bz[j]), u1.y)));
+                        float lo, hi;
+                        unpack2(e, lo, hi);
                         m[j] = fminf(fminf(m[j], lo), hi);
+                    }
+                    u0 = v0;
+                    u1 = v1;
+                }
+            } else {
+#pragma unroll UNR
+                for (int i = 0; i < n_pairs; ++i) {
+                    ulonglong2 u0 = sA[2 * i], u1 = sA[2 * i + 1];
+#pragma unroll
+                    for (int j = 0; j < TB; ++j) {
+                        f32x2 e = fma2(u0.x, pack2(bx[j], bx[j]),
+                                       fma2(u0.y, pack2(by[j], by[j]), fma2(u1.x, pack2(bz[j], bz[j]), u1.y)));
+                        float lo, hi;
+                        unpack2(e, lo, hi);
+                        m[j] = fminf(fminf(m[j], lo), hi);
+                    }
                 }
             }
             float lane_min = 3.0e38f;
@@ -399,10 +479,10 @@ static void timing_flush() {
     }
 }
 
-template <int TB, int VAR>
+template <int TB, int UNR, int PF>
 static cudaError_t launch_f32v(const ClashArgs& args, int threads, size_t smem, int grid,
                                cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(clash_f32_kernel<TB, VAR>,
+    cudaError_t e = cudaFuncSetAttribute(clash_f32_kernel<TB, UNR, PF>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (g_time_on) {
@@ -413,7 +493,7 @@ static cudaError_t launch_f32v(const ClashArgs& args, int threads, size_t smem, 
         }
         cudaEventRecord(g_ev0, s);
     }
-    clash_f32_kernel<TB, VAR><<<grid, threads, smem, s>>>(args);
+    clash_f32_kernel<TB, UNR, PF><<<grid, threads, smem, s>>>(args);
     e = cudaGetLastError();
     if (g_time_on) {
         cudaEventRecord(g_ev1, s);
@@ -425,16 +505,17 @@ static cudaError_t launch_f32v(const ClashArgs& args, int threads, size_t smem, 
 template <int TB>
 static cudaError_t launch_f32(const ClashArgs& args, int threads, size_t smem, int grid,
                               cudaStream_t s) {
-    static int var = -1;
-    if (var < 0) {
-        const char* v = getenv("FC_CLASH_VARIANT");
-        var = v ? atoi(v) & 3 : 1;  // default: chain-major order (measured fastest on B200)
+    static int unr = -1;
+    if (unr < 0) {
+        const char* v = getenv("FC_CLASH_UNROLL");
+        unr = v ? atoi(v) : 11;  // default: A pairs register-prefetched, no unrolling (measured fastest on B200)
     }
-    switch (var) {
-        case 1: return launch_f32v<TB, 1>(args, threads, smem, grid, s);
-        case 2: return launch_f32v<TB, 2>(args, threads, smem, grid, s);
-        case 3: return launch_f32v<TB, 3>(args, threads, smem, grid, s);
-        default: return launch_f32v<TB, 0>(args, threads, smem, grid, s);
+    switch (unr) {
+        case 1: return launch_f32v<TB, 1, 0>(args, threads, smem, grid, s);
+        case 2: return launch_f32v<TB, 2, 0>(args, threads, smem, grid, s);
+        case 13: return launch_f32v<TB, 3, 1>(args, threads, smem, grid, s);
+        case 15: return launch_f32v<TB, 5, 1>(args, threads, smem, grid, s);
+        default: return launch_f32v<TB, 1, 1>(args, threads, smem, grid, s);
     }
 }
 
@@ -488,7 +569,7 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     if (!tiles) n_tiles = (n_poses + g.poses - 1) / g.poses;
     FC_REQUIRE(n_tiles > 0, "fc_clash_screen_dev: empty tile list");
 
-    size_t smem = (size_t)n_a_pad * 16 + (size_t)n_b_pad * 16 + (size_t)g.poses * 4;
+    size_t smem = (size_t)(n_a_pad + 2) * 16 + (size_t)n_b_pad * 16 + (size_t)2 * g.poses * 96 + 16 + (size_t)g.poses * 4;
     FC_REQUIRE(smem <= 227 * 1024, "fc_clash_screen_dev: fragments need %zu B of shared memory", smem);
 
     // stream-ordered scratch
@@ -521,6 +602,10 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     a.poses = g.poses;
     a.thr2 = (float)(thresh * thresh);
     a.count_mode = max_clashes > 0;
+    {
+        const char* v = getenv("FC_CLASH_TMA");
+        a.use_tma = ((reinterpret_cast<uintptr_t>(xf) & 15) == 0) && !(v && atoi(v) == 0);
+    }
     a.status = status;
     a.min_dist = min_dist;
     a.unc_count = (int*)(scratch + off_cnt);
