@@ -78,6 +78,9 @@ class Cyclical3ProblemC(C.Structure):
     ]
 
 
+# int (*fc_allgather_fn)(const void* send, int64_t send_bytes, const void** recv, int64_t* recv_bytes, void* ctx)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, VP, C.c_int64, C.POINTER(VP), C.POINTER(C.c_int64), VP)
+
 # name -> (restype, argtypes); must list every symbol include/firecode_b200.h declares
 SIGNATURES = {
     "fc_result_free": (None, [VP]),
@@ -95,6 +98,9 @@ SIGNATURES = {
     "fc_prune": (C.c_int, [VP, C.c_int64, C.c_int32, C.c_int32, VP, C.c_int32, VP, C.c_double, C.c_double,
                            C.c_double, VP, C.c_double, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP,
                            C.c_int64, c_i64p]),
+    "fc_prune_sharded": (C.c_int, [VP, C.c_int64, C.c_int32, C.c_int32, VP, C.c_int32, VP, C.c_double, C.c_double,
+                                   C.c_double, VP, C.c_double, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP,
+                                   C.c_int64, c_i64p, C.c_int32, C.c_int32, ALLGATHER_FN, VP]),
     "fc_torsion_scan": (C.c_int, [VP, C.c_int32, C.c_int32, VP, C.c_int32, VP, VP, C.c_int32, C.c_double,
                                   C.c_int32, C.c_int32, C.c_int32, VP, VP, VP]),
     "fc_string_n_poses": (C.c_int64, [VP]),

@@ -104,7 +104,6 @@ struct PruneTile {
     int row0, col0;      // positions in the compacted active list
     int chunk_begin;     // first active position of the chunk
     int chunk_len;       // active members of the chunk
-    long long bit_off;   // word offset of the chunk's bit matrix
 };
 
 struct PruneArgs {
@@ -117,7 +116,9 @@ struct PruneArgs {
     int nh;
     int mode;                // 0 = rmsd, 1 = moi
     double max_rmsd, max_dev, max_dE, moi_dev, eps;
-    unsigned* bits;
+    int2* pairs;                 // similar pairs found in this pass (structure indices, x < y)
+    unsigned long long* n_pairs; // ... their number (may exceed pair_cap: the pass is then repeated)
+    long long pair_cap;
     unsigned long long* n_eval;  // pairs fully evaluated
     TieRecord* ties;
     int* n_ties;
@@ -127,12 +128,10 @@ struct PruneArgs {
 #define PR_TS 32        // structures per tile side
 #define PR_ATOMS 32     // atoms staged per step
 
-__device__ __forceinline__ void prune_set_bit(const PruneArgs& a, const PruneTile& t, int r, int c) {
-    // symmetric matrix over the chunk's active positions
-    int words = (t.chunk_len + 31) >> 5;
-    int rr = r - t.chunk_begin, cc = c - t.chunk_begin;
-    atomicOr(a.bits + t.bit_off + (long long)rr * words + (cc >> 5), 1u << (cc & 31));
-    atomicOr(a.bits + t.bit_off + (long long)cc * words + (rr >> 5), 1u << (rr & 31));
+// similar pairs go to a compact list (sparse: survivors of earlier passes are mutually dissimilar)
+__device__ __forceinline__ void prune_push_pair(const PruneArgs& a, int s_lo, int s_hi) {
+    unsigned long long slot = atomicAdd(a.n_pairs, 1ull);
+    if ((long long)slot < a.pair_cap) a.pairs[slot] = make_int2(s_lo, s_hi);
 }
 
 // 256 threads: thread (tx = column, ty) owns pairs (row ty + 8u, column tx), u = 0..3
@@ -163,7 +162,7 @@ __global__ void __launch_bounds__(256) prune_pairs_kernel(PruneArgs a) {
             const double* mj = a.moi + 3 * (size_t)s_col;
             bool sim = true;
             for (int k = 0; k < 3; ++k) sim = sim && (fabs(mi[k] - mj[k]) / mi[k] < a.moi_dev);
-            if (sim) prune_set_bit(a, t, row[u], col);
+            if (sim) prune_push_pair(a, s_row[u], s_col);
         }
         return;
     }
@@ -242,7 +241,7 @@ __global__ void __launch_bounds__(256) prune_pairs_kernel(PruneArgs a) {
                 if (slot < a.tie_cap) a.ties[slot] = TieRecord{s_col, s_row[u], maxdev, FC_TIE_MAXDEV, m_ok ? 1 : 0};
             }
         }
-        if (r_ok && m_ok) prune_set_bit(a, t, row[u], col);
+        if (r_ok && m_ok) prune_push_pair(a, s_row[u], s_col);
     }
     if (a.n_eval) {
         for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(0xffffffffu, evals, o);
@@ -250,86 +249,61 @@ __global__ void __launch_bounds__(256) prune_pairs_kernel(PruneArgs a) {
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// ordered resolution, one CTA per chunk
-// ---------------------------------------------------------------------------------------------
-struct PruneChunk {
-    int begin, len;        // positions in the compacted active list
-    long long bit_off;
-};
-
-// alive_out[pos] for every active position; greedy = NMS sweep, snapshot = mask of the pass start
-__global__ void __launch_bounds__(1024) prune_sweep_kernel(const PruneChunk* __restrict__ chunks,
-                                                           const unsigned* __restrict__ bits, int keep_first,
-                                                           int snapshot, unsigned char* __restrict__ alive_out) {
-    extern __shared__ unsigned s_alive[];
-    const PruneChunk c = chunks[blockIdx.x];
-    const int words = (c.len + 31) >> 5;
-    const unsigned* m = bits + c.bit_off;
-    for (int w = threadIdx.x; w < words; w += blockDim.x) {
-        int rem = c.len - 32 * w;
-        s_alive[w] = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
-    }
-    __syncthreads();
-    if (snapshot) {
-        // position i is dropped if any position on its keeper side is similar to it
-        for (int i = threadIdx.x; i < c.len; i += blockDim.x) {
-            const unsigned* row = m + (long long)i * words;
-            bool hit = false;
-            if (keep_first) {      // keeper side = earlier positions
-                for (int w = 0; w <= (i >> 5) && !hit; ++w) {
-                    unsigned v = row[w];
-                    if (w == (i >> 5)) v &= (1u << (i & 31)) - 1u;
-                    hit = v != 0;
-                }
-            } else {               // keeper side = later positions
-                for (int w = i >> 5; w < words && !hit; ++w) {
-                    unsigned v = row[w];
-                    if (w == (i >> 5)) v &= ~((2u << (i & 31)) - 1u);
-                    hit = v != 0;
-                }
-            }
-            alive_out[c.begin + i] = hit ? 0 : 1;
-        }
-        return;
-    }
-    for (int step = 0; step < c.len; ++step) {
-        const int i = keep_first ? step : c.len - 1 - step;
-        const bool alive = (s_alive[i >> 5] >> (i & 31)) & 1u;   // uniform
-        if (alive) {
-            const unsigned* row = m + (long long)i * words;
-            for (int w = threadIdx.x; w < words; w += blockDim.x) {
-                unsigned v = row[w];
-                // only the side that i may still drop: later positions (keep-first) / earlier (keep-last)
-                if (keep_first) {
-                    if (w < (i >> 5)) v = 0;
-                    else if (w == (i >> 5)) v &= ~((2u << (i & 31)) - 1u);
-                } else {
-                    if (w > (i >> 5)) v = 0;
-                    else if (w == (i >> 5)) v &= (1u << (i & 31)) - 1u;
-                }
-                if (v) s_alive[w] &= ~v;
-            }
-        }
-        __syncthreads();
-    }
-    for (int i = threadIdx.x; i < c.len; i += blockDim.x) alive_out[c.begin + i] = (s_alive[i >> 5] >> (i & 31)) & 1u;
-}
-
 }  // namespace fc
 
 using namespace fc;
 
+
+
 static const int64_t kSchedule[] = {500000, 200000, 100000, 50000, 20000, 10000, 5000, 2000, 1000,
                                     500,    200,    100,    50,    20,    10,    5,    2,    1};
 
+// Ordered resolution of one pass on the host: O(similar pairs).  Chunks are contiguous index ranges and
+// pairs never cross chunks, so one sweep in index order resolves every chunk.
+//   greedy   : NMS sweep -- a structure that is still alive drops every similar structure on its
+//              droppable side (later ones for keep-first, earlier ones for keep-last);
+//   snapshot : a structure is dropped if any structure on its keeper side that was active at the start of
+//              the pass is similar to it.
+static void prune_resolve(std::vector<uint8_t>& mask, const std::vector<int2>& pairs, bool keep_first, bool snapshot) {
+    if (pairs.empty()) return;
+    if (snapshot) {
+        for (const int2& p : pairs) mask[(size_t)(keep_first ? p.y : p.x)] = 0;
+        return;
+    }
+    const size_t n = mask.size();
+    std::vector<int64_t> off(n + 1, 0);
+    for (const int2& p : pairs) off[(size_t)(keep_first ? p.x : p.y) + 1] += 1;
+    for (size_t i = 0; i < n; ++i) off[i + 1] += off[i];
+    std::vector<int> adj(pairs.size());
+    std::vector<int64_t> fill(off.begin(), off.end() - 1);
+    for (const int2& p : pairs) {
+        if (keep_first) adj[(size_t)fill[(size_t)p.x]++] = p.y;
+        else adj[(size_t)fill[(size_t)p.y]++] = p.x;
+    }
+    if (keep_first) {
+        for (size_t i = 0; i < n; ++i)
+            if (mask[i])
+                for (int64_t e = off[i]; e < off[i + 1]; ++e) mask[(size_t)adj[(size_t)e]] = 0;
+    } else {
+        for (size_t i = n; i-- > 0;)
+            if (mask[i])
+                for (int64_t e = off[i]; e < off[i + 1]; ++e) mask[(size_t)adj[(size_t)e]] = 0;
+    }
+}
+
 // mode 0: RMSD, mode 1: MOI.  `sel` = indices of the atoms used for the RMSD (heavy atoms).
-extern "C" int fc_prune(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
-                        int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
-                        const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
-                        int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
-                        int64_t tie_cap, int64_t* n_ties_out) {
+// rank / world / gather: pair tiles of every pass are dealt round-robin to the ranks; the similar pairs each
+// rank finds are all-gathered through `gather` (NCCL or gloo behind the host language) and every rank resolves
+// the pass on the union, so all ranks hold the same mask after every pass.
+extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
+                                int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
+                                const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
+                                int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
+                                int64_t tie_cap, int64_t* n_ties_out, int32_t rank, int32_t world,
+                                fc_allgather_fn gather, void* gather_ctx) {
     FC_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && n_atoms > 0, "fc_prune: bad sizes");
+    FC_REQUIRE(world >= 1 && rank >= 0 && rank < world, "fc_prune: bad rank / world");
+    FC_REQUIRE(world == 1 || gather, "fc_prune: a multi-rank call needs an all-gather callback");
     if (n_ties_out) *n_ties_out = 0;
     if (stats_out) stats_out[0] = stats_out[1] = stats_out[2] = stats_out[3] = 0;
     if (n == 0) return FC_OK;
@@ -346,16 +320,14 @@ extern "C" int fc_prune(const double* structures, int64_t n, int32_t n_atoms, in
     FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     int rc = FC_OK;
     std::vector<uint8_t> mask((size_t)n, 1);
-    int64_t pairs_tiled = 0, passes = 0;
+    int64_t pairs_tiled = 0, passes = 0, pairs_skipped = 0, similar_total = 0;
     unsigned long long evals_total = 0;
     int64_t ties_total = 0;
     {
         DevBuf<double> d_coords, d_xc, d_g, d_moi, d_mass, d_energy;
         DevBuf<int> d_sel, d_active, d_nties;
-        DevBuf<unsigned> d_bits;
+        DevBuf<int2> d_pairs;
         DevBuf<PruneTile> d_tiles;
-        DevBuf<PruneChunk> d_chunks;
-        DevBuf<unsigned char> d_alive;
         DevBuf<unsigned long long> d_eval;
         DevBuf<TieRecord> d_ties;
         const int cap = (int)std::min<int64_t>(std::max<int64_t>(tie_cap, 1), 1 << 22);
@@ -365,8 +337,8 @@ extern "C" int fc_prune(const double* structures, int64_t n, int32_t n_atoms, in
         PR(cudaMemcpyAsync(d_coords.p, structures, (size_t)n * n_atoms * 24, cudaMemcpyHostToDevice, s));
         PR(d_nties.alloc(4, s));
         PR(cudaMemsetAsync(d_nties.p, 0, 16, s));
-        PR(d_eval.alloc(2, s));
-        PR(cudaMemsetAsync(d_eval.p, 0, 16, s));
+        PR(d_eval.alloc(4, s));  // [0] eigen-solves, [1] similar pairs of the current pass
+        PR(cudaMemsetAsync(d_eval.p, 0, 32, s));
         PR(d_ties.alloc(cap, s));
         if (energies) {
             PR(d_energy.alloc((size_t)n, s));
@@ -391,13 +363,12 @@ extern "C" int fc_prune(const double* structures, int64_t n, int32_t n_atoms, in
             }
         }
         PR(d_active.alloc((size_t)n, s));
-        PR(d_alive.alloc((size_t)n, s));
         if (e != cudaSuccess) rc = cuda_fail(e, "fc_prune setup", __FILE__, __LINE__);
 
         std::vector<int> active;
         std::vector<PruneTile> tiles;
-        std::vector<PruneChunk> chunks;
-        std::vector<unsigned char> alive;
+        std::vector<int2> pairs, all_pairs;
+        int64_t prev_size = 0, prev_k = 0;  // chunking of the last executed pass
         for (int64_t k : kSchedule) {
             if (rc) break;
             int64_t n_active = 0;
@@ -406,11 +377,9 @@ extern "C" int fc_prune(const double* structures, int64_t n, int32_t n_atoms, in
             ++passes;
             // compacted active list + chunks over the FULL array (chunk size n // k, last takes the rest)
             active.clear();
-            chunks.clear();
             tiles.clear();
             const int64_t size = n / k;
-            long long bit_words = 0;
-            int max_len = 0;
+            int64_t tile_no = 0;
             for (int64_t c = 0; c < k; ++c) {
                 int64_t first = c * size, last = (c == k - 1) ? n : size * (c + 1);
                 int begin = (int)active.size();
@@ -418,45 +387,76 @@ extern "C" int fc_prune(const double* structures, int64_t n, int32_t n_atoms, in
                     if (mask[(size_t)i]) active.push_back((int)i);
                 int len = (int)active.size() - begin;
                 if (len < 2) continue;  // nothing to compare
-                PruneChunk ch{begin, len, bit_words};
-                int words = (len + 31) >> 5;
                 for (int r0 = 0; r0 < len; r0 += PR_TS)
-                    for (int c0 = r0; c0 < len; c0 += PR_TS)
-                        tiles.push_back(PruneTile{begin + r0, begin + c0, begin, len, bit_words});
-                bit_words += (long long)len * words;
-                max_len = std::max(max_len, len);
-                pairs_tiled += (int64_t)len * (len - 1) / 2;
-                chunks.push_back(ch);
+                    for (int c0 = r0; c0 < len; c0 += PR_TS) {
+                        const int rows = std::min(PR_TS, len - r0), cols = std::min(PR_TS, len - c0);
+                        const int64_t tile_pairs = r0 == c0 ? (int64_t)rows * (rows - 1) / 2 : (int64_t)rows * cols;
+                        // survivors that shared a chunk in an earlier pass are known to be dissimilar
+                        if (prev_size > 0) {
+                            const int64_t lo_idx = active[(size_t)(begin + r0)], hi_idx = active[(size_t)(begin + c0 + cols - 1)];
+                            const int64_t ca = std::min(lo_idx / prev_size, prev_k - 1), cb = std::min(hi_idx / prev_size, prev_k - 1);
+                            if (ca == cb) { pairs_skipped += tile_pairs; continue; }
+                        }
+                        if (tile_no++ % world != rank) continue;
+                        pairs_tiled += tile_pairs;
+                        tiles.push_back(PruneTile{begin + r0, begin + c0, begin, len});
+                    }
             }
-            if (chunks.empty()) continue;
-            e = d_bits.alloc((size_t)bit_words, s);
-            PR(cudaMemsetAsync(d_bits.p, 0, (size_t)bit_words * 4, s));
-            PR(d_tiles.alloc(tiles.size(), s));
-            PR(cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(PruneTile), cudaMemcpyHostToDevice, s));
-            PR(d_chunks.alloc(chunks.size(), s));
-            PR(cudaMemcpyAsync(d_chunks.p, chunks.data(), chunks.size() * sizeof(PruneChunk), cudaMemcpyHostToDevice, s));
-            PR(cudaMemcpyAsync(d_active.p, active.data(), active.size() * 4, cudaMemcpyHostToDevice, s));
-            PR(cudaMemsetAsync(d_alive.p, 1, active.size(), s));
-            if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pass setup", __FILE__, __LINE__); break; }
-            PruneArgs a{};
-            a.xc = d_xc.p; a.g = d_g.p; a.moi = d_moi.p; a.energies = energies ? d_energy.p : nullptr;
-            a.active = d_active.p; a.tiles = d_tiles.p; a.nh = n_sel; a.mode = mode;
-            a.max_rmsd = max_rmsd; a.max_dev = max_dev; a.max_dE = max_dE; a.moi_dev = moi_dev; a.eps = FC_NEAR_EPS;
-            a.bits = d_bits.p; a.n_eval = d_eval.p;
-            a.ties = ties_out ? d_ties.p : nullptr; a.n_ties = d_nties.p; a.tie_cap = cap;
-            prune_pairs_kernel<<<(unsigned)tiles.size(), 256, 0, s>>>(a);
-            size_t smem = (size_t)((max_len + 31) / 32) * 4;
-            if (smem > 48 * 1024)
-                PR(cudaFuncSetAttribute(prune_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            prune_sweep_kernel<<<(unsigned)chunks.size(), 1024, smem, s>>>(d_chunks.p, d_bits.p, keep_first ? 1 : 0,
-                                                                           snapshot ? 1 : 0, d_alive.p);
-            PR(cudaGetLastError());
-            alive.resize(active.size());
-            PR(cudaMemcpyAsync(alive.data(), d_alive.p, active.size(), cudaMemcpyDeviceToHost, s));
-            PR(cudaStreamSynchronize(s));
-            if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pass", __FILE__, __LINE__); break; }
-            for (size_t i = 0; i < active.size(); ++i)
-                if (!alive[i]) mask[(size_t)active[i]] = 0;
+            prev_size = size;
+            prev_k = k;
+            pairs.clear();
+            if (!tiles.empty()) {
+                e = d_tiles.alloc(tiles.size(), s);
+                PR(cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(PruneTile), cudaMemcpyHostToDevice, s));
+                PR(cudaMemcpyAsync(d_active.p, active.data(), active.size() * 4, cudaMemcpyHostToDevice, s));
+                if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pass setup", __FILE__, __LINE__); break; }
+                long long pair_cap = std::max<long long>(1 << 20, 8 * (long long)active.size());
+                for (int attempt = 0; attempt < 2 && !rc; ++attempt) {
+                    if (d_pairs.n < (size_t)pair_cap) PR(d_pairs.alloc((size_t)pair_cap, s));
+                    PR(cudaMemsetAsync(d_eval.p + 1, 0, 8, s));
+                    if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pair list", __FILE__, __LINE__); break; }
+                    PruneArgs a{};
+                    a.xc = d_xc.p; a.g = d_g.p; a.moi = d_moi.p; a.energies = energies ? d_energy.p : nullptr;
+                    a.active = d_active.p; a.tiles = d_tiles.p; a.nh = n_sel; a.mode = mode;
+                    a.max_rmsd = max_rmsd; a.max_dev = max_dev; a.max_dE = max_dE; a.moi_dev = moi_dev; a.eps = FC_NEAR_EPS;
+                    a.pairs = d_pairs.p; a.n_pairs = d_eval.p + 1; a.pair_cap = pair_cap;
+                    a.n_eval = attempt == 0 ? d_eval.p : nullptr;
+                    a.ties = (ties_out && attempt == 0) ? d_ties.p : nullptr; a.n_ties = d_nties.p; a.tie_cap = cap;
+                    prune_pairs_kernel<<<(unsigned)tiles.size(), 256, 0, s>>>(a);
+                    PR(cudaGetLastError());
+                    unsigned long long found = 0;
+                    PR(cudaMemcpyAsync(&found, d_eval.p + 1, 8, cudaMemcpyDeviceToHost, s));
+                    PR(cudaStreamSynchronize(s));
+                    if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pass", __FILE__, __LINE__); break; }
+                    if ((long long)found > pair_cap) {  // list too small: repeat the pass with the exact size
+                        pair_cap = (long long)found;
+                        continue;
+                    }
+                    pairs.resize((size_t)found);
+                    if (found) {
+                        e = cudaMemcpy(pairs.data(), d_pairs.p, (size_t)found * sizeof(int2), cudaMemcpyDeviceToHost);
+                        if (e != cudaSuccess) rc = cuda_fail(e, "fc_prune pair readback", __FILE__, __LINE__);
+                    }
+                    break;
+                }
+                if (rc) break;
+            }
+            const std::vector<int2>* use = &pairs;
+            if (world > 1) {
+                const void* recv = nullptr;
+                int64_t recv_bytes = 0;
+                int grc = gather(pairs.data(), (int64_t)(pairs.size() * sizeof(int2)), &recv, &recv_bytes, gather_ctx);
+                if (grc != 0 || recv_bytes < 0 || recv_bytes % (int64_t)sizeof(int2)) {
+                    set_error("fc_prune: all-gather callback failed (%d)", grc);
+                    rc = FC_ERR_INVALID;
+                    break;
+                }
+                all_pairs.resize((size_t)(recv_bytes / (int64_t)sizeof(int2)));
+                if (recv_bytes) memcpy(all_pairs.data(), recv, (size_t)recv_bytes);
+                use = &all_pairs;
+            }
+            similar_total += (int64_t)use->size();
+            prune_resolve(mask, *use, keep_first != 0, snapshot != 0);
         }
         if (!rc) {
             int n_t = 0;
@@ -483,9 +483,19 @@ extern "C" int fc_prune(const double* structures, int64_t n, int32_t n_atoms, in
     if (n_ties_out) *n_ties_out = ties_total;
     if (stats_out) {
         stats_out[0] = passes;
-        stats_out[1] = pairs_tiled;               // pairs whose covariance was accumulated
-        stats_out[2] = (int64_t)evals_total;      // pairs that needed the eigen-solve
-        stats_out[3] = 0;
+        stats_out[1] = pairs_tiled;               // pairs whose covariance was accumulated (on this rank)
+        stats_out[2] = (int64_t)evals_total;      // pairs that needed the eigen-solve (on this rank)
+        stats_out[3] = pairs_skipped;             // pairs known dissimilar from an earlier pass, not re-evaluated
     }
     return FC_OK;
+}
+
+extern "C" int fc_prune(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
+                        int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
+                        const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
+                        int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
+                        int64_t tie_cap, int64_t* n_ties_out) {
+    return fc_prune_sharded(structures, n, n_atoms, mode, sel, n_sel, masses, max_rmsd, max_dev, moi_dev, energies,
+                            max_dE, keep_first, snapshot, min_per_chunk, mask_out, stats_out, ties_out, tie_cap,
+                            n_ties_out, 0, 1, nullptr, nullptr);
 }

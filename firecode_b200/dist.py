@@ -214,3 +214,17 @@ def cyclical_embed_sharded(embedder, group=None, screen=None, max_norm_delta=5.0
     if len(poses) == 0:
         raise ZeroCandidatesError("cyclical embed: no pose survived")
     return poses
+
+
+def prune_sharded(structures, atoms, kind="rmsd", group=None, **kw):
+    """prune_by_rmsd / prune_by_moment_of_inertia over all ranks of ``group``: pair tiles of every pass
+    are dealt round-robin to the ranks (structures replicated), the similar pairs each rank finds are
+    all-gathered (8 bytes per pair) and every rank resolves the pass on the union -- the deterministic
+    ordered merge -- so all ranks return the same (structures[mask], mask) as a single-GPU call."""
+    from . import pruner
+
+    rank, world = world_info(group)
+    fn = pruner.prune_by_rmsd if kind == "rmsd" else pruner.prune_by_moment_of_inertia
+    if world == 1:
+        return fn(structures, atoms, **kw)
+    return fn(structures, atoms, shard=(rank, world, lambda buf: all_gather_varlen(buf, group)), **kw)

@@ -25,6 +25,7 @@ class PruneReport:
     passes: int = 0
     pairs_tiled: int = 0     # active pairs whose 3x3 covariance was accumulated
     pairs_solved: int = 0    # pairs that needed the FP64 eigen-solve
+    pairs_skipped: int = 0   # pairs known dissimilar from an earlier pass (same chunk survivors)
     ties: np.ndarray | None = None
     n_ties_total: int = 0
     keep: str = "first"
@@ -35,7 +36,9 @@ last_report: PruneReport | None = None
 
 
 def _run(structures, mode, sel, masses, max_rmsd, max_dev, moi_dev, energies, max_dE, keep, pass_mode,
-         tie_cap=1 << 16):
+         tie_cap=1 << 16, shard=None):
+    """``shard`` = (rank, world, allgather) runs the multi-GPU form: allgather(bytes ndarray) must
+    return the rank-order concatenation of every rank's buffer (firecode_b200.dist supplies it)."""
     global last_report
     lib = _lib.load(require_device=True)
     keep = conventions.PRUNE_KEEP if keep is None else keep
@@ -53,13 +56,36 @@ def _run(structures, mode, sel, masses, max_rmsd, max_dev, moi_dev, energies, ma
     e_arr = None if energies is None else np.ascontiguousarray(energies, dtype=np.float64)
     if e_arr is not None:
         assert len(e_arr) == n
-    rc = lib.fc_prune(_ptr(x), n, n_atoms, mode, _ptr(sel_arr), 0 if sel_arr is None else len(sel_arr),
-                      _ptr(mass_arr), float(max_rmsd), float(max_dev), float(moi_dev), _ptr(e_arr),
-                      float(max_dE), 1 if keep == "first" else 0, 1 if pass_mode == "snapshot" else 0,
-                      int(conventions.PRUNE_MIN_PER_CHUNK), _ptr(mask), _ptr(stats), _ptr(ties), tie_cap,
-                      C.byref(n_ties))
+    args = (_ptr(x), n, n_atoms, mode, _ptr(sel_arr), 0 if sel_arr is None else len(sel_arr),
+            _ptr(mass_arr), float(max_rmsd), float(max_dev), float(moi_dev), _ptr(e_arr),
+            float(max_dE), 1 if keep == "first" else 0, 1 if pass_mode == "snapshot" else 0,
+            int(conventions.PRUNE_MIN_PER_CHUNK), _ptr(mask), _ptr(stats), _ptr(ties), tie_cap, C.byref(n_ties))
+    if shard is None:
+        rc = lib.fc_prune(*args)
+    else:
+        rank, world, allgather = shard
+        hold = {}
+
+        def _gather(send, send_bytes, recv, recv_bytes, ctx):
+            try:
+                buf = np.ctypeslib.as_array(C.cast(send, C.POINTER(C.c_uint8)), shape=(send_bytes,)).copy() \
+                    if send_bytes else np.zeros(0, dtype=np.uint8)
+                out = np.ascontiguousarray(allgather(buf), dtype=np.uint8)
+                hold["buf"] = out  # owned here until the next call
+                recv[0] = out.ctypes.data if out.size else None
+                recv_bytes[0] = out.size
+                return 0
+            except Exception:  # pragma: no cover - reported through the C-ABI error path
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        cb = _lib.ALLGATHER_FN(_gather)
+        rc = lib.fc_prune_sharded(*args, int(rank), int(world), cb, None)
     _lib.check(rc, "fc_prune")
     last_report = PruneReport(passes=int(stats[0]), pairs_tiled=int(stats[1]), pairs_solved=int(stats[2]),
+                              pairs_skipped=int(stats[3]),
                               ties=ties[: min(int(n_ties.value), tie_cap)], n_ties_total=int(n_ties.value),
                               keep=keep, pass_mode=pass_mode)
     mask = mask.astype(bool)
@@ -67,7 +93,7 @@ def _run(structures, mode, sel, masses, max_rmsd, max_dev, moi_dev, energies, ma
 
 
 def prune_by_rmsd(structures, atoms, max_rmsd=0.25, max_dev=None, energies=None, max_dE=0.0,
-                  debugfunction=None, logfunction=None, keep=None, pass_mode=None):
+                  debugfunction=None, logfunction=None, keep=None, pass_mode=None, shard=None):
     """Heavy-atom, centred Kabsch RMSD pruning: a structure is dropped when a kept one has
     rmsd < max_rmsd and max atomic deviation < max_dev (default 2 * max_rmsd)."""
     atoms = np.asarray(atoms)
@@ -76,19 +102,19 @@ def prune_by_rmsd(structures, atoms, max_rmsd=0.25, max_dev=None, energies=None,
         sel = np.flatnonzero(np.array([str(a) != "H" for a in atoms]))
     else:
         sel = np.arange(len(atoms))
-    out, mask = _run(structures, 0, sel, None, max_rmsd, max_dev, 0.0, energies, max_dE, keep, pass_mode)
+    out, mask = _run(structures, 0, sel, None, max_rmsd, max_dev, 0.0, energies, max_dE, keep, pass_mode, shard=shard)
     if debugfunction is not None:
         debugfunction(f"DEBUG: prune_by_rmsd (firecode_b200) - kept {int(mask.sum())}/{len(mask)}")
     return out, mask
 
 
 def prune_by_moment_of_inertia(structures, atoms, max_deviation=None, energies=None, max_dE=0.0,
-                               debugfunction=None, logfunction=None, keep=None, pass_mode=None):
+                               debugfunction=None, logfunction=None, keep=None, pass_mode=None, shard=None):
     """Drop structures whose three principal moments of inertia are all within ``max_deviation``
     (relative, default 1 %) of a kept structure (CHANGELOG.md:256)."""
     max_deviation = conventions.MOI_MAX_DEVIATION if max_deviation is None else max_deviation
     masses = np.array([MASSES[str(a)] for a in np.asarray(atoms)])
-    out, mask = _run(structures, 1, None, masses, 0.0, 0.0, max_deviation, energies, max_dE, keep, pass_mode)
+    out, mask = _run(structures, 1, None, masses, 0.0, 0.0, max_deviation, energies, max_dE, keep, pass_mode, shard=shard)
     if debugfunction is not None:
         debugfunction(f"DEBUG: prune_by_moment_of_inertia (firecode_b200) - kept {int(mask.sum())}/{len(mask)}")
     return out, mask

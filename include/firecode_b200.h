@@ -217,12 +217,29 @@ int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** out);
  *  structures (n, n_atoms, 3) f64 host;  sel (n_sel) atoms entering the RMSD (heavy atoms);
  *  masses (n_atoms) for mode 1;  energies (n) or NULL: pairs with |dE| >= max_dE are not compared;
  *  keep_first / snapshot: the two unpinned prism_pruner conventions;
- *  mask_out (n) 1 = kept;  stats_out[4] = {passes, pairs tiled, pairs eigen-solved, 0}. */
+ *  mask_out (n) 1 = kept;  stats_out[4] = {passes, pairs whose covariance was accumulated, pairs
+ *  eigen-solved, pairs skipped because both structures survived an earlier pass in the same chunk
+ *  (such survivors are mutually dissimilar by construction)}.  Similar pairs are collected in a
+ *  compact list; the order-dependent keep rule of a pass is resolved on the host in O(list). */
 int fc_prune(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
              int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
              const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
              int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
              int64_t tie_cap, int64_t* n_ties_out);
+
+/* Multi-GPU form: the pair tiles of every pass are dealt round-robin to `world` ranks (structures
+ * replicated); the similar pairs found by each rank are all-gathered through `gather` -- the host
+ * language implements it with NCCL / gloo -- and every rank resolves the pass on the union, so all
+ * ranks return the same mask.  gather(send, send_bytes, &recv, &recv_bytes, ctx) must return 0 and
+ * hand back the rank-order concatenation of all ranks' buffers (owned by the callee until the next
+ * call).  stats_out counts this rank's share. */
+typedef int (*fc_allgather_fn)(const void* send, int64_t send_bytes, const void** recv, int64_t* recv_bytes, void* ctx);
+int fc_prune_sharded(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
+                     int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
+                     const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
+                     int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
+                     int64_t tie_cap, int64_t* n_ties_out, int32_t rank, int32_t world,
+                     fc_allgather_fn gather, void* gather_ctx);
 
 /* Batched torsion rotation with clash filtering: replaces the primitive pair
  * prism_pruner.utils.rotate_dihedral + torsion_module.py:894-918 `torsion_comp_check` (used at

@@ -71,3 +71,79 @@ def test_prune_edge_cases(gpu):
     assert mask.shape == (0,) and out.shape == (0, 10, 3)
     s2, m2 = pruner.prune(structures, atoms, max_rmsd=0.5)
     assert m2.sum() == 1
+
+
+def _shard_worker(rank, world, port, q):
+    import os
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # both ranks share cuda:0; gloo carries the lists
+    try:
+        from firecode_b200 import dist as fdist
+        from firecode_b200 import pruner as pr
+        from firecode_b200 import synthetic as syn
+
+        rng = np.random.default_rng(77)
+        atoms, structures, _ = syn.pruning_ensemble(rng, 3000, 20, 200, jitter=(0.02, 0.4))
+        out = {}
+        for keep, mode in (("first", "greedy"), ("last", "snapshot")):
+            _, mask = fdist.prune_sharded(structures, atoms, "rmsd", max_rmsd=0.4, keep=keep, pass_mode=mode)
+            out[(keep, mode)] = (mask, pr.last_report.pairs_tiled)
+        _, mmask = fdist.prune_sharded(structures, atoms, "moi")
+        out["moi"] = (mmask, pr.last_report.pairs_tiled)
+        q.put((rank, out))
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, "FAIL: " + traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_prune_sharded_two_ranks_equals_single(gpu):
+    """Pair tiles dealt to two ranks + all-gather of the similar-pair lists + ordered resolve on every
+    rank reproduces the single-GPU mask (and each rank evaluates about half of the pairs)."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(not isinstance(v, str) for v in results.values()), results
+    rng = np.random.default_rng(77)
+    atoms, structures, _ = synthetic.pruning_ensemble(rng, 3000, 20, 200, jitter=(0.02, 0.4))
+    for keep, mode in (("first", "greedy"), ("last", "snapshot")):
+        _, single = pruner.prune_by_rmsd(structures, atoms, 0.4, keep=keep, pass_mode=mode)
+        total = pruner.last_report.pairs_tiled
+        for r in (0, 1):
+            assert np.array_equal(results[r][(keep, mode)][0], single)
+        assert results[0][(keep, mode)][1] + results[1][(keep, mode)][1] == total
+        assert abs(results[0][(keep, mode)][1] - total / 2) < 0.2 * total
+    _, single = pruner.prune_by_moment_of_inertia(structures, atoms)
+    assert np.array_equal(results[0]["moi"][0], single) and np.array_equal(results[1]["moi"][0], single)
+
+
+def test_prune_skips_pairs_known_from_earlier_passes(gpu):
+    rng = np.random.default_rng(5)
+    atoms, structures, _ = synthetic.pruning_ensemble(rng, 4000, 16, 2000, jitter=(0.02, 0.1))
+    _, mask = pruner.prune_by_rmsd(structures, atoms, 0.3)
+    rep = pruner.last_report
+    assert rep.passes >= 4 and rep.pairs_skipped > 0
+    _, ref_mask = ref_pruner.prune_by_rmsd(structures, atoms, 0.3, ties=port.Ties(eps=1e-6, forced=_forced(rep)))
+    assert np.array_equal(mask, ref_mask)
