@@ -121,6 +121,8 @@ SIGNATURES = {
     "fc_clash_geometry": (C.c_int, [C.c_int, c_i32p]),
     "fc_clash_timing": (C.c_int, [C.c_int, c_dp, c_i64p]),
     "fc_pack_mask_dev": (C.c_int, [VP, C.c_int64, VP, VP]),
+    "fc_rmsd_and_max_batch": (C.c_int, [VP, VP, C.c_int64, C.c_int32, C.c_int32, VP, VP]),
+    "fc_self_clash_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_double, VP, VP]),
     "fc_probe_fp32_peak": (C.c_int, [c_dp, c_dp, VP]),
 }
 

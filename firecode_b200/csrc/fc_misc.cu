@@ -1,0 +1,169 @@
+// firecode_b200 -- small batched helpers that keep the reference's single-structure entry points on the GPU.
+//
+//  * fc_rmsd_and_max_batch: prism_pruner.rmsd.rmsd_and_max(ref, structure, center) for a batch of
+//    structures against one reference -- the arithmetic of firecode/utils.py:494-504 `rmsd_similarity`
+//    (center = 0, all atoms) and of embedder.py:1784-1786 (center = 1).  One warp per structure, FP64
+//    covariance by warp shuffles, Jacobi-based Kabsch in registers, second pass for RMSD / max deviation.
+//  * fc_self_clash_batch: the non-fragment branch of firecode/utils.py:523-542 `compenetration_check`
+//    (ids = None) and firecode/algebra.py:52-54 `count_clashes`: per structure the number of ORDERED atom
+//    pairs with 0 < d < 0.5 A and the number of ordered pairs i != j with d < thresh that are not bonded.
+#include "fc_embed.cuh"
+
+namespace fc {
+
+__device__ __forceinline__ double misc_wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double misc_wmax(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(128) rmsd_and_max_kernel(const double* __restrict__ ref, const double* __restrict__ xs,
+                                                           long long n, int n_atoms, int center,
+                                                           double* __restrict__ rmsd_out, double* __restrict__ maxdev_out) {
+    const int lane = threadIdx.x & 31;
+    const long long s = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= n) return;
+    const double* q = xs + (size_t)s * n_atoms * 3;
+    double mp[3] = {0, 0, 0}, mq[3] = {0, 0, 0};
+    if (center) {
+        for (int k = lane; k < n_atoms; k += 32)
+            for (int c = 0; c < 3; ++c) { mp[c] += ref[3 * k + c]; mq[c] += q[3 * k + c]; }
+        for (int c = 0; c < 3; ++c) { mp[c] = misc_wsum(mp[c]) / n_atoms; mq[c] = misc_wsum(mq[c]) / n_atoms; }
+    }
+    double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = lane; k < n_atoms; k += 32) {
+        double x[3] = {ref[3 * k] - mp[0], ref[3 * k + 1] - mp[1], ref[3 * k + 2] - mp[2]};
+        double y[3] = {q[3 * k] - mq[0], q[3 * k + 1] - mq[1], q[3 * k + 2] - mq[2]};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) h[3 * r + c] += x[r] * y[c];
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) h[e] = misc_wsum(h[e]);
+    M3 R = kabsch_from_cov(h, nullptr);
+    double ss = 0.0, mx = 0.0;
+    for (int k = lane; k < n_atoms; k += 32) {
+        double x[3] = {ref[3 * k] - mp[0], ref[3 * k + 1] - mp[1], ref[3 * k + 2] - mp[2]};
+        double y[3] = {q[3 * k] - mq[0], q[3 * k + 1] - mq[1], q[3 * k + 2] - mq[2]};
+        double dx = (x[0] * R.m[0] + x[1] * R.m[3] + x[2] * R.m[6]) - y[0];
+        double dy = (x[0] * R.m[1] + x[1] * R.m[4] + x[2] * R.m[7]) - y[1];
+        double dz = (x[0] * R.m[2] + x[1] * R.m[5] + x[2] * R.m[8]) - y[2];
+        double d2 = dx * dx + dy * dy + dz * dz;
+        ss += d2;
+        mx = fmax(mx, d2);
+    }
+    ss = misc_wsum(ss);
+    mx = misc_wmax(mx);
+    if (lane == 0) {
+        rmsd_out[s] = sqrt(ss / n_atoms);
+        maxdev_out[s] = sqrt(mx);
+    }
+}
+
+// one CTA per structure; FP64 distances as scipy cdist computes them (sqrt of the summed squares)
+__global__ void __launch_bounds__(256) self_clash_kernel(const double* __restrict__ coords, int n_atoms,
+                                                         const unsigned char* __restrict__ bonded, double thresh,
+                                                         long long* __restrict__ close_out, long long* __restrict__ nonbonded_out) {
+    const double* x = coords + (size_t)blockIdx.x * n_atoms * 3;
+    long long close = 0, nb = 0;
+    const long long total = (long long)n_atoms * n_atoms;
+    for (long long e = threadIdx.x; e < total; e += blockDim.x) {
+        int i = (int)(e / n_atoms), j = (int)(e - (long long)i * n_atoms);
+        if (i == j) continue;
+        double dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
+        double d = sqrt(dx * dx + dy * dy + dz * dz);
+        close += (d < 0.5 && d > 0.0) ? 1 : 0;
+        if (d < thresh && !(bonded && bonded[(size_t)i * n_atoms + j])) nb += 1;
+    }
+    __shared__ long long s_c[8], s_n[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        close += __shfl_xor_sync(0xffffffffu, close, o);
+        nb += __shfl_xor_sync(0xffffffffu, nb, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5] = close; s_n[threadIdx.x >> 5] = nb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long c = 0, m = 0;
+        for (int w = 0; w < 8; ++w) { c += s_c[w]; m += s_n[w]; }
+        close_out[blockIdx.x] = c;
+        nonbonded_out[blockIdx.x] = m;
+    }
+}
+
+}  // namespace fc
+
+using namespace fc;
+
+extern "C" int fc_rmsd_and_max_batch(const double* ref, const double* structures, int64_t n, int32_t n_atoms,
+                                     int32_t center, double* rmsd_out, double* maxdev_out) {
+    FC_REQUIRE(n >= 0 && n_atoms > 0, "fc_rmsd_and_max_batch: bad sizes");
+    if (n == 0) return FC_OK;
+    FC_REQUIRE(ref && structures && rmsd_out && maxdev_out, "fc_rmsd_and_max_batch: null pointer");
+    sm_count();
+    cudaStream_t s;
+    FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaError_t e = cudaSuccess;
+    {
+        DevBuf<double> d_ref, d_x, d_r, d_m;
+#define MS(call) do { if (e == cudaSuccess) e = (call); } while (0)
+        MS(d_ref.alloc((size_t)n_atoms * 3, s));
+        MS(d_x.alloc((size_t)n * n_atoms * 3, s));
+        MS(d_r.alloc((size_t)n, s));
+        MS(d_m.alloc((size_t)n, s));
+        MS(cudaMemcpyAsync(d_ref.p, ref, (size_t)n_atoms * 24, cudaMemcpyHostToDevice, s));
+        MS(cudaMemcpyAsync(d_x.p, structures, (size_t)n * n_atoms * 24, cudaMemcpyHostToDevice, s));
+        if (e == cudaSuccess) {
+            rmsd_and_max_kernel<<<(unsigned)((n + 3) / 4), 128, 0, s>>>(d_ref.p, d_x.p, n, n_atoms, center, d_r.p, d_m.p);
+            e = cudaGetLastError();
+        }
+        MS(cudaMemcpyAsync(rmsd_out, d_r.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        MS(cudaMemcpyAsync(maxdev_out, d_m.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        MS(cudaStreamSynchronize(s));
+    }
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    if (e != cudaSuccess) return cuda_fail(e, "fc_rmsd_and_max_batch", __FILE__, __LINE__);
+    return FC_OK;
+}
+
+extern "C" int fc_self_clash_batch(const double* coords, int64_t n, int32_t n_atoms, const uint8_t* bonded, double thresh,
+                                   int64_t* close_pairs_out, int64_t* nonbonded_out) {
+    FC_REQUIRE(n >= 0 && n_atoms > 0 && n < ((int64_t)1 << 31), "fc_self_clash_batch: bad sizes");
+    if (n == 0) return FC_OK;
+    FC_REQUIRE(coords && close_pairs_out && nonbonded_out, "fc_self_clash_batch: null pointer");
+    sm_count();
+    cudaStream_t s;
+    FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaError_t e = cudaSuccess;
+    {
+        DevBuf<double> d_x;
+        DevBuf<unsigned char> d_b;
+        DevBuf<long long> d_c, d_n;
+        MS(d_x.alloc((size_t)n * n_atoms * 3, s));
+        MS(d_c.alloc((size_t)n, s));
+        MS(d_n.alloc((size_t)n, s));
+        MS(cudaMemcpyAsync(d_x.p, coords, (size_t)n * n_atoms * 24, cudaMemcpyHostToDevice, s));
+        if (bonded) {
+            MS(d_b.alloc((size_t)n_atoms * n_atoms, s));
+            MS(cudaMemcpyAsync(d_b.p, bonded, (size_t)n_atoms * n_atoms, cudaMemcpyHostToDevice, s));
+        }
+        if (e == cudaSuccess) {
+            self_clash_kernel<<<(unsigned)n, 256, 0, s>>>(d_x.p, n_atoms, bonded ? d_b.p : nullptr, thresh, d_c.p, d_n.p);
+            e = cudaGetLastError();
+        }
+        MS(cudaMemcpyAsync(close_pairs_out, d_c.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        MS(cudaMemcpyAsync(nonbonded_out, d_n.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        MS(cudaStreamSynchronize(s));
+#undef MS
+    }
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    if (e != cudaSuccess) return cuda_fail(e, "fc_self_clash_batch", __FILE__, __LINE__);
+    return FC_OK;
+}

@@ -94,9 +94,23 @@ def compenetration_check(coords, graph=None, ids=None, thresh=1.0, max_clashes=0
 
     coords = np.ascontiguousarray(np.asarray(coords, dtype=np.float64))
     if ids is None:
-        raise NotImplementedError(
-            "firecode_b200: the non-fragment branch of compenetration_check (utils.py:523-542, a "
-            "set-up time check outside the embedding screen) is not built")
+        # not fragment-based (utils.py:523-542): quick count of pairs closer than 0.5 A, then -- given
+        # a graph -- the non-bonded pairs below thresh.  The reference loop counts ORDERED pairs and
+        # tests the running count at the top of each iteration; its last iteration is always the
+        # diagonal entry (N-1, N-1), so it returns False iff the full count exceeds max_clashes.
+        from .algebra import self_clash_counts
+
+        bonded = None
+        if graph is not None:
+            bonded = np.zeros((len(coords), len(coords)), dtype=np.uint8)
+            for a, b in graph.edges:
+                bonded[a, b] = bonded[b, a] = 1
+        close, nonbonded = self_clash_counts(coords[None], bonded, thresh)
+        if close[0] > max_clashes:
+            return False
+        if graph is None:
+            return True
+        return not (nonbonded[0] > max_clashes)
     eye = np.array([[1.0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]])
     if len(ids) == 2:
         m1, m2 = coords[: ids[0]], coords[ids[0]:]
@@ -113,9 +127,13 @@ def compenetration_check(coords, graph=None, ids=None, thresh=1.0, max_clashes=0
 
 def rmsd_similarity(ref, structures, rmsd_thr=0.5):
     """True if any structure has uncentred all-atom Kabsch RMSD < rmsd_thr and max deviation
-    < 2 * rmsd_thr to ``ref`` (utils.py:494-504).  Evaluated on the GPU through the pruning kernel
-    is not possible (that one centres); the screens run this filter inside fc_cyclical_screen, and
-    this single-call form is kept for API parity only."""
-    raise NotImplementedError(
-        "firecode_b200: rmsd_similarity is fused into the cyclical screen (fc_cyclical_screen); a "
-        "stand-alone entry point is not built")
+    < 2 * rmsd_thr to ``ref`` (utils.py:494-504).  The embeds run this filter fused inside
+    fc_cyclical_screen / fc_cyclical3_screen; this stand-alone form evaluates the whole batch of
+    structures in one call of fc_rmsd_and_max_batch."""
+    from .algebra import rmsd_and_max_batch
+
+    structures = np.asarray(structures, dtype=np.float64)
+    if structures.size == 0:
+        return False
+    rmsd, maxdev = rmsd_and_max_batch(ref, structures, center=False)
+    return bool(np.any((rmsd < rmsd_thr) & (maxdev < 2 * rmsd_thr)))

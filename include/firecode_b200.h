@@ -253,6 +253,19 @@ int fc_torsion_scan(const double* coords, int32_t n_conf, int32_t n_atoms, const
                     double thresh, int32_t max_clashes, int32_t rot_handedness, int32_t axis_sign,
                     double* out_coords, uint8_t* status_out, double* min_dist_out);
 
+/* prism_pruner.rmsd.rmsd_and_max(ref, structure, center) for n structures against one reference: the
+ * arithmetic of utils.py:494-504 `rmsd_similarity` (center = 0, all atoms) and embedder.py:1784-1786
+ * (center = 1).  ref (n_atoms, 3), structures (n, n_atoms, 3) host; outputs (n). */
+int fc_rmsd_and_max_batch(const double* ref, const double* structures, int64_t n, int32_t n_atoms,
+                          int32_t center, double* rmsd_out, double* maxdev_out);
+
+/* Non-fragment branch of utils.py:523-542 `compenetration_check(coords, graph)` and algebra.py:52-54
+ * `count_clashes` for n structures: close_pairs_out[s] = ordered atom pairs with 0 < d < 0.5 A,
+ * nonbonded_out[s] = ordered pairs i != j with d < thresh and bonded[i * n_atoms + j] == 0
+ * (bonded may be NULL). */
+int fc_self_clash_batch(const double* coords, int64_t n, int32_t n_atoms, const uint8_t* bonded, double thresh,
+                        int64_t* close_pairs_out, int64_t* nonbonded_out);
+
 /* FP32 FMA-pipe peak probe used by bench.py for the roofline denominator: runs a dependent-free
  * FFMA2 loop on every SM and returns achieved TFLOP/s (2 flop per FMA lane). */
 int fc_probe_fp32_peak(double* tflops_out, double* ms_out, void* stream);

@@ -121,3 +121,53 @@ def test_single_structure_api(gpu):
             assert compenetration_check(coords, ids=ids, thresh=1.2) == port.compenetration_check(coords, ids=ids, thresh=1.2)
         assert compenetration_check(coords, ids=(12, 18), thresh=1.2, max_clashes=2) == \
             port.compenetration_check(coords, ids=(12, 18), thresh=1.2, max_clashes=2)
+
+
+def test_nonfragment_branch_and_rmsd_similarity(gpu):
+    """utils.compenetration_check(ids=None) (utils.py:523-542), algebra.count_clashes and
+    utils.rmsd_similarity (utils.py:494-504) against plain numpy restatements."""
+    import networkx as nx
+    from scipy.spatial.distance import cdist
+
+    from firecode_b200 import algebra, synthetic
+    from firecode_b200.utils import compenetration_check, rmsd_similarity
+    from oracle.prism_pruner.rmsd import rmsd_and_max
+
+    rng = np.random.default_rng(11)
+    for trial in range(12):
+        atoms, coords, bonds, _ = synthetic.molecule_cloud(rng, 25)
+        coords = coords + rng.normal(scale=0.25 * (trial % 3), size=coords.shape)
+        g = nx.Graph()
+        g.add_nodes_from(range(len(coords)))
+        g.add_edges_from(bonds)
+        d = cdist(coords, coords)
+        n_close = int(np.count_nonzero((d < 0.5) & (d > 0)))
+        assert algebra.count_clashes(coords) == n_close
+        for mc in (0, 3):
+            # reference semantics restated: running count tested at the top of each argwhere iteration
+            def ref_check(graph):
+                if n_close > mc:
+                    return False
+                if graph is None:
+                    return True
+                clashes = 0
+                for i1, i2 in np.argwhere(d < 1.3):
+                    if clashes > mc:
+                        return False
+                    if i1 != i2 and (i1, i2) not in graph.edges:
+                        clashes += 1
+                return True
+            assert compenetration_check(coords, thresh=1.3, max_clashes=mc) == ref_check(None)
+            assert compenetration_check(coords, graph=g, thresh=1.3, max_clashes=mc) == ref_check(g)
+    ref = rng.normal(size=(30, 3)) * 3
+    structs = np.array([ref + rng.normal(scale=s, size=ref.shape) for s in (0.9, 0.6, 0.2, 1.5)])
+    r, m = algebra.rmsd_and_max_batch(ref, structs)
+    for k in range(len(structs)):
+        rr, mm = rmsd_and_max(ref, structs[k], center=False)
+        assert abs(r[k] - rr) < 1e-9 and abs(m[k] - mm) < 1e-9
+    rc, mc_ = algebra.rmsd_and_max_batch(ref, structs + 5.0, center=True)
+    assert np.allclose(rc, [rmsd_and_max(ref, s + 5.0, center=True)[0] for s in structs], atol=1e-9)
+    for thr in (0.1, 0.5, 1.0):
+        want = any(rmsd_and_max(ref, s)[0] < thr and rmsd_and_max(ref, s)[1] < 2 * thr for s in structs)
+        assert rmsd_similarity(ref, structs, rmsd_thr=thr) == want
+    assert rmsd_similarity(ref, np.zeros((0, 30, 3))) is False
