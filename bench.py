@@ -429,10 +429,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (C1, C2, C4, C5)")
     args = ap.parse_args()
+    # the driver parses ONE JSON line from stdout: libraries that write to fd 1 (NCCL prints its version
+    # banner there) are diverted to stderr, and only the result line goes to the real stdout
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_cuda(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
