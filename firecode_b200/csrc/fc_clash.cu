@@ -386,6 +386,215 @@ __global__ void __launch_bounds__(ClashLaunch<TB>::kMaxThreads, 1) clash_f32_ker
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cell-list screen: the same decision without touching far atom pairs.
+// ---------------------------------------------------------------------------------------------
+// Fragment A (per conformer) is binned once per call into a G^3 grid over the bounding box of the whole
+// ensemble, padded by the clash radius.  A cell record (16 bytes, one LDG.128) holds the number of
+// candidate atoms and up to 15 of their indices: every atom whose distance to the cell CENTRE is at
+// most  rc = thresh + kCellPad + h*sqrt(3)/2  -- a superset of the atoms within thresh + kCellPad of ANY
+// point of the cell, hence of every atom that can decide the pose (the FP32 band is far below kCellPad;
+// poses whose band is not are sent to the FP64 recheck).  A query (pose, atom of B) transforms the atom,
+// finds its cell and evaluates only the listed atoms, in the difference form; cells with more than 15
+// candidates (count byte 255) fall back to scanning all atoms of A for that query.
+// One thread per pose, one warp per 32 consecutive poses; fragments and grid are read through L1/L2
+// (150 atoms = 2.4 KB, grid = G^3 * 16 B per conformer).  The FP32 band / FP64 recheck protocol of the
+// all-pairs kernel is unchanged, so both paths produce identical status bytes.
+constexpr float kCellPad = 0.05f;
+
+struct CellMeta {        // written by clash_bbox_kernel, read by the grid / query kernels
+    float ox, oy, oz;    // grid origin
+    float h, inv_h;      // cell edge
+    float rc2;           // squared candidate radius around a cell centre
+    int g;               // cells per axis
+};
+
+__global__ void __launch_bounds__(256) clash_bbox_kernel(const double* __restrict__ a_coords, long long n_atoms_total,
+                                                         float thresh, int g, CellMeta* __restrict__ meta) {
+    __shared__ float s_lo[3][8], s_hi[3][8];
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (long long i = threadIdx.x; i < n_atoms_total; i += blockDim.x)
+        for (int c = 0; c < 3; ++c) {
+            float v = (float)a_coords[3 * i + c];
+            lo[c] = fminf(lo[c], v);
+            hi[c] = fmaxf(hi[c], v);
+        }
+    for (int c = 0; c < 3; ++c) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        if ((threadIdx.x & 31) == 0) { s_lo[c][threadIdx.x >> 5] = lo[c]; s_hi[c][threadIdx.x >> 5] = hi[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float ext = 0.f, l[3];
+        const float pad = thresh + kCellPad + 0.01f;
+        for (int c = 0; c < 3; ++c) {
+            float a = 3e38f, b = -3e38f;
+            for (int w = 0; w < 8; ++w) { a = fminf(a, s_lo[c][w]); b = fmaxf(b, s_hi[c][w]); }
+            l[c] = a - pad;
+            ext = fmaxf(ext, (b + pad) - l[c]);
+        }
+        CellMeta m;
+        m.ox = l[0]; m.oy = l[1]; m.oz = l[2];
+        m.h = ext / (float)g * 1.0001f;
+        m.inv_h = 1.0f / m.h;
+        float rc = thresh + kCellPad + m.h * 0.8661f + 1e-3f;
+        m.rc2 = rc * rc;
+        m.g = g;
+        *meta = m;
+    }
+}
+
+// a_xyz: [conf][n_a] float4 {x, y, z, 0};  grid: [conf][g^3] uint4 = {count, idx0..14} as bytes
+__global__ void __launch_bounds__(128) clash_grid_kernel(const double* __restrict__ a_coords, int n_a,
+                                                         const CellMeta* __restrict__ meta, float4* __restrict__ a_xyz,
+                                                         uint4* __restrict__ grid) {
+    extern __shared__ double s_a[];  // n_a * 3
+    const int conf = blockIdx.y;
+    const double* src = a_coords + (size_t)conf * n_a * 3;
+    for (int i = threadIdx.x; i < n_a * 3; i += blockDim.x) s_a[i] = src[i];
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < n_a; i += blockDim.x)
+            a_xyz[(size_t)conf * n_a + i] = make_float4((float)src[3 * i], (float)src[3 * i + 1], (float)src[3 * i + 2], 0.f);
+    __syncthreads();
+    const CellMeta m = *meta;
+    const int g = m.g;
+    const long long n_cells = (long long)g * g * g;
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    const int cx = (int)(cell % g), cy = (int)((cell / g) % g), cz = (int)(cell / ((long long)g * g));
+    const double px = (double)m.ox + ((double)cx + 0.5) * (double)m.h;
+    const double py = (double)m.oy + ((double)cy + 0.5) * (double)m.h;
+    const double pz = (double)m.oz + ((double)cz + 0.5) * (double)m.h;
+    unsigned bytes[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) bytes[k] = 0;
+    int count = 0;
+    for (int i = 0; i < n_a; ++i) {
+        double dx = s_a[3 * i] - px, dy = s_a[3 * i + 1] - py, dz = s_a[3 * i + 2] - pz;
+        if (dx * dx + dy * dy + dz * dz <= (double)m.rc2) {
+            if (count < 15) {
+#pragma unroll
+                for (int k = 1; k < 16; ++k)
+                    if (k == count + 1) bytes[k] = (unsigned)i;
+            }
+            ++count;
+        }
+    }
+    bytes[0] = count > 15 ? 255u : (unsigned)count;
+    uint4 rec;
+    rec.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (bytes[3] << 24);
+    rec.y = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | (bytes[7] << 24);
+    rec.z = bytes[8] | (bytes[9] << 8) | (bytes[10] << 16) | (bytes[11] << 24);
+    rec.w = bytes[12] | (bytes[13] << 8) | (bytes[14] << 16) | (bytes[15] << 24);
+    grid[(size_t)conf * n_cells + cell] = rec;
+}
+
+struct CellArgs {
+    const float4* a_xyz;
+    const float* a_rad;
+    const float4* b_tab;
+    const float* b_rad;
+    const uint4* grid;
+    const CellMeta* meta;
+    const double* xf;
+    const int4* tiles;
+    long long n_tiles, n_poses;
+    int n_a, n_b, n_b_pad, tile_poses;
+    float thr2;
+    int count_mode;
+    uint8_t* status;
+    int* unc_count;
+    UncEntry* unc_list;
+};
+
+__global__ void __launch_bounds__(128) clash_cell_kernel(CellArgs p) {
+    const long long pose = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pose >= p.n_poses) return;
+    int conf_a = 0, conf_b = 0;
+    if (p.tiles) {  // tiles are sorted by first pose: binary search
+        long long lo = 0, hi = p.n_tiles - 1;
+        while (lo < hi) {
+            long long mid = (lo + hi + 1) >> 1;
+            if ((long long)p.tiles[mid].z <= pose) lo = mid;
+            else hi = mid - 1;
+        }
+        int4 t = p.tiles[lo];
+        if (pose >= (long long)t.z + t.w) return;  // pose not covered by any tile
+        conf_a = t.x;
+        conf_b = t.y;
+    }
+    const CellMeta m = *p.meta;
+    const int g = m.g;
+    const double* x = p.xf + pose * 12;
+    float r[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) r[k] = (float)__ldg(x + k);
+    const float tnorm = sqrtf(fmaf(r[9], r[9], fmaf(r[10], r[10], r[11] * r[11])));
+    const float4* bt = p.b_tab + (size_t)conf_b * p.n_b_pad;
+    const float4* at = p.a_xyz + (size_t)conf_a * p.n_a;
+    const uint4* gr = p.grid + (size_t)conf_a * g * g * g;
+    float dmin2 = 3.0e38f;
+    for (int j = 0; j < p.n_b; ++j) {
+        const float4 b = __ldg(bt + j);
+        const float bx = fmaf(r[0], b.x, fmaf(r[1], b.y, fmaf(r[2], b.z, r[9])));
+        const float by = fmaf(r[3], b.x, fmaf(r[4], b.y, fmaf(r[5], b.z, r[10])));
+        const float bz = fmaf(r[6], b.x, fmaf(r[7], b.y, fmaf(r[8], b.z, r[11])));
+        const float fx = (bx - m.ox) * m.inv_h, fy = (by - m.oy) * m.inv_h, fz = (bz - m.oz) * m.inv_h;
+        // unsigned compare also rejects negative coordinates
+        const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+        if ((unsigned)cx >= (unsigned)g || (unsigned)cy >= (unsigned)g || (unsigned)cz >= (unsigned)g) continue;
+        const uint4 rec = __ldg(gr + ((size_t)cz * g + cy) * g + cx);
+        const unsigned count = rec.x & 0xffu;
+        if (count == 0) continue;
+        if (count == 255u) {  // crowded cell: all atoms of A
+            for (int i = 0; i < p.n_a; ++i) {
+                const float4 a = __ldg(at + i);
+                const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
+                dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+            }
+            continue;
+        }
+        unsigned long long q0 = (((unsigned long long)rec.y << 32) | rec.x) >> 8;  // indices 0..6
+        unsigned long long q1 = ((unsigned long long)rec.w << 32) | rec.z;         // indices 7..14
+        q0 |= q1 << 56;
+        q1 >>= 8;
+        for (unsigned c = 0; c < count; ++c) {
+            const unsigned ai = (unsigned)(q0 & 0xffull);
+            q0 = (q0 >> 8) | (q1 << 56);
+            q1 >>= 8;
+            const float4 a = __ldg(at + ai);
+            const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
+            dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+        }
+    }
+    // same band as the all-pairs kernel (the difference form is at least as accurate as the Gram form)
+    const float ext = p.a_rad[conf_a] + p.b_rad[conf_b] + tnorm;
+    const float band = fmaf(1.5e-6f * ext, ext, 1e-6f);
+    uint8_t st;
+    bool uncertain;
+    if (p.count_mode) {
+        uncertain = !(dmin2 > p.thr2 + band);
+        st = FC_STATUS_PASS;
+    } else {
+        uncertain = fabsf(dmin2 - p.thr2) <= band;
+        st = dmin2 > p.thr2 ? FC_STATUS_PASS : 0;
+    }
+    // the candidate lists only cover thresh + kCellPad: a band that large cannot be trusted to them
+    if (band > 2.0f * kCellPad * sqrtf(p.thr2) * 0.5f) uncertain = true;
+    if (uncertain) {
+        int slot = atomicAdd(p.unc_count, 1);
+        UncEntry e;
+        e.pose = pose;
+        e.conf_a = conf_a;
+        e.conf_b = conf_b;
+        p.unc_list[slot] = e;
+    }
+    p.status[pose] = st;
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP64 recheck: one warp per undecided pose, reference arithmetic (utils.py:544-575)
 // ---------------------------------------------------------------------------------------------
 struct RecheckArgs {
@@ -479,26 +688,31 @@ static void timing_flush() {
     }
 }
 
+static void timing_begin(cudaStream_t s) {
+    if (!g_time_on) return;
+    timing_flush();
+    if (!g_ev0) {
+        cudaEventCreate(&g_ev0);
+        cudaEventCreate(&g_ev1);
+    }
+    cudaEventRecord(g_ev0, s);
+}
+static void timing_end(cudaStream_t s) {
+    if (!g_time_on) return;
+    cudaEventRecord(g_ev1, s);
+    g_ev_pending = true;
+}
+
 template <int TB, int UNR, int PF>
 static cudaError_t launch_f32v(const ClashArgs& args, int threads, size_t smem, int grid,
                                cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(clash_f32_kernel<TB, UNR, PF>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (g_time_on) {
-        timing_flush();
-        if (!g_ev0) {
-            cudaEventCreate(&g_ev0);
-            cudaEventCreate(&g_ev1);
-        }
-        cudaEventRecord(g_ev0, s);
-    }
+    timing_begin(s);
     clash_f32_kernel<TB, UNR, PF><<<grid, threads, smem, s>>>(args);
     e = cudaGetLastError();
-    if (g_time_on) {
-        cudaEventRecord(g_ev1, s);
-        g_ev_pending = true;
-    }
+    timing_end(s);
     return e;
 }
 
@@ -572,12 +786,35 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     size_t smem = (size_t)(n_a_pad + 2) * 16 + (size_t)n_b_pad * 16 + (size_t)2 * g.poses * 96 + 16 + (size_t)g.poses * 4;
     FC_REQUIRE(smem <= 227 * 1024, "fc_clash_screen_dev: fragments need %zu B of shared memory", smem);
 
+    // ---- path: all atom pairs (Gram-form FP32 kernel) or cell lists over fragment A -----------------
+    int cell_g = 0;
+    {
+        // FC_CLASH_MODE: 0 = all pairs, 1 = cell lists whenever possible, unset = automatic
+        const char* v = getenv("FC_CLASH_MODE");
+        const int mode = (v && *v) ? (atoi(v) ? 1 : 0) : 2;
+        const bool possible = !min_dist && n_a <= 254 && thresh > 0.0 && thresh < 1e3;
+        const bool wanted = mode == 1 || (mode == 2 && n_poses >= 16384);
+        if (possible && wanted) {
+            const size_t budget = (size_t)512 << 20;
+            for (int g_try : {64, 48, 32}) {
+                if ((size_t)n_conf_a * g_try * g_try * g_try * 16 <= budget) {
+                    cell_g = g_try;
+                    break;
+                }
+            }
+        }
+    }
+    const size_t n_cells = (size_t)cell_g * cell_g * cell_g;
+
     // stream-ordered scratch
     size_t a_bytes = (size_t)n_conf_a * n_a_pad * 16, b_bytes = (size_t)n_conf_b * n_b_pad * 16;
     size_t off_a = 0, off_b = off_a + a_bytes, off_ra = off_b + b_bytes;
     size_t off_rb = off_ra + (size_t)n_conf_a * 4, off_cnt = (off_rb + (size_t)n_conf_b * 4 + 15) / 16 * 16;
     size_t off_list = off_cnt + 16;
-    size_t total = off_list + (size_t)n_poses * sizeof(UncEntry);
+    size_t off_axyz = (off_list + (size_t)n_poses * sizeof(UncEntry) + 15) / 16 * 16;
+    size_t off_meta = off_axyz + (cell_g ? (size_t)n_conf_a * n_a * 16 : 0);
+    size_t off_grid = off_meta + (cell_g ? 64 : 0);
+    size_t total = off_grid + (cell_g ? (size_t)n_conf_a * n_cells * 16 : 0);
     unsigned char* scratch = nullptr;
     FC_CUDA(cudaMallocAsync((void**)&scratch, total, s));
 
@@ -611,6 +848,38 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     a.unc_count = (int*)(scratch + off_cnt);
     a.unc_list = (UncEntry*)(scratch + off_list);
 
+    if (cell_g) {
+        CellMeta* meta = (CellMeta*)(scratch + off_meta);
+        float4* a_xyz = (float4*)(scratch + off_axyz);
+        uint4* grid_tab = (uint4*)(scratch + off_grid);
+        clash_bbox_kernel<<<1, 256, 0, s>>>(a_coords, (long long)n_conf_a * n_a, (float)thresh, cell_g, meta);
+        dim3 gg((unsigned)((n_cells + 127) / 128), (unsigned)n_conf_a);
+        clash_grid_kernel<<<gg, 128, (size_t)n_a * 24, s>>>(a_coords, n_a, meta, a_xyz, grid_tab);
+        CellArgs c;
+        c.a_xyz = a_xyz;
+        c.a_rad = a.a_rad;
+        c.b_tab = a.b_tab;
+        c.b_rad = a.b_rad;
+        c.grid = grid_tab;
+        c.meta = meta;
+        c.xf = xf;
+        c.tiles = (const int4*)tiles;
+        c.n_tiles = n_tiles;
+        c.n_poses = n_poses;
+        c.n_a = n_a;
+        c.n_b = n_b;
+        c.n_b_pad = n_b_pad;
+        c.tile_poses = g.poses;
+        c.thr2 = a.thr2;
+        c.count_mode = a.count_mode;
+        c.status = status;
+        c.unc_count = a.unc_count;
+        c.unc_list = a.unc_list;
+        timing_begin(s);
+        clash_cell_kernel<<<(unsigned)((n_poses + 127) / 128), 128, 0, s>>>(c);
+        timing_end(s);
+    }
+
     // persistent grid: resident CTAs per SM follow from the register/thread budget
     int ctas_per_sm = tb_max_threads(g.tb) / g.threads;
     if (ctas_per_sm > 8) ctas_per_sm = 8;
@@ -619,6 +888,9 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     if (grid_ll > n_tiles) grid_ll = n_tiles;
     int grid = (int)grid_ll;
     cudaError_t e;
+    if (cell_g) {
+        e = cudaGetLastError();
+    } else
     switch (g.tb) {
         case 2: e = launch_f32<2>(a, g.threads, smem, grid, s); break;
         case 4: e = launch_f32<4>(a, g.threads, smem, grid, s); break;

@@ -171,3 +171,47 @@ def test_nonfragment_branch_and_rmsd_similarity(gpu):
         want = any(rmsd_and_max(ref, s)[0] < thr and rmsd_and_max(ref, s)[1] < 2 * thr for s in structs)
         assert rmsd_similarity(ref, structs, rmsd_thr=thr) == want
     assert rmsd_similarity(ref, np.zeros((0, 30, 3))) is False
+
+
+@pytest.mark.parametrize("n_a,n_b,thresh", [(150, 150, 1.5), (60, 33, 1.2), (254, 40, 2.0), (17, 150, 0.9)])
+def test_cell_list_path_equals_all_pairs_and_oracle(gpu, monkeypatch, n_a, n_b, thresh):
+    """The cell-list screen (FC_CLASH_MODE=1) and the all-pairs kernel (FC_CLASH_MODE=0) write identical
+    status bytes; both equal the oracle."""
+    from firecode_b200 import synthetic
+
+    rng = np.random.default_rng(n_a * 1000 + n_b)
+    _, a, _, _ = synthetic.molecule_cloud(rng, n_a)
+    _, b, _, _ = synthetic.molecule_cloud(rng, n_b)
+    xf = synthetic.sweep_poses(rng, a, b, 40000)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("FC_CLASH_MODE", mode)
+        for mc in (0, 2):
+            out[(mode, mc)] = compenetration_check_batch(a, b, xf, thresh=thresh, max_clashes=mc)
+    for mc in (0, 2):
+        assert np.array_equal(out[("0", mc)].status & 1, out[("1", mc)].status & 1)
+        ref_mask, dmin, closest = port.clash_batch(a, b, xf[:6000], thresh=thresh, max_clashes=mc)
+        safe = closest > 1e-6
+        assert np.array_equal(out[("1", mc)].mask[:6000][safe], ref_mask[safe])
+    assert 0.05 < out[("1", 0)].mask.mean() < 0.95
+
+
+def test_cell_list_path_with_conformer_tiles(gpu, monkeypatch):
+    """Explicit tile lists (several conformers of both fragments) through the cell-list path."""
+    from firecode_b200 import synthetic
+
+    rng = np.random.default_rng(5)
+    _, ca, _, _ = synthetic.conformer_ensemble(rng, 3, 40, n_torsions=4)
+    _, cb, _, _ = synthetic.conformer_ensemble(rng, 2, 35, n_torsions=4)
+    xf = synthetic.sweep_poses(rng, ca[0], cb[0], 3000)
+    conf_a = rng.integers(0, 3, size=3000)
+    conf_b = rng.integers(0, 2, size=3000)
+    order = np.lexsort((conf_b, conf_a))
+    conf_a, conf_b = conf_a[order], conf_b[order]
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("FC_CLASH_MODE", mode)
+        res[mode] = compenetration_check_batch(ca, cb, xf, thresh=1.4, conf_a=conf_a, conf_b=conf_b)
+    assert np.array_equal(res["0"].status & 1, res["1"].status & 1)
+    ref_mask, _, closest = port.clash_batch(ca, cb, xf, thresh=1.4, conf_a=conf_a, conf_b=conf_b)
+    assert np.array_equal(res["1"].mask[closest > 1e-6], ref_mask[closest > 1e-6])
