@@ -447,9 +447,10 @@ __global__ void __launch_bounds__(256) clash_bbox_kernel(const double* __restric
 }
 
 // a_xyz: [conf][n_a] float4 {x, y, z, 0};  grid: [conf][g^3] uint4 = {count, idx0..14} as bytes
+// occ:   [conf][g^3 / 32] one bit per cell: the cell has candidates (32 KB per conformer for g = 64: L1-resident)
 __global__ void __launch_bounds__(128) clash_grid_kernel(const double* __restrict__ a_coords, int n_a,
                                                          const CellMeta* __restrict__ meta, float4* __restrict__ a_xyz,
-                                                         uint4* __restrict__ grid) {
+                                                         uint4* __restrict__ grid, unsigned* __restrict__ occ) {
     extern __shared__ double s_a[];  // n_a * 3
     const int conf = blockIdx.y;
     const double* src = a_coords + (size_t)conf * n_a * 3;
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(128) clash_grid_kernel(const double* __restric
     const CellMeta m = *meta;
     const int g = m.g;
     const long long n_cells = (long long)g * g * g;
-    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // g^3 is a multiple of 128
     if (cell >= n_cells) return;
     const int cx = (int)(cell % g), cy = (int)((cell / g) % g), cz = (int)(cell / ((long long)g * g));
     const double px = (double)m.ox + ((double)cx + 0.5) * (double)m.h;
@@ -489,6 +490,8 @@ __global__ void __launch_bounds__(128) clash_grid_kernel(const double* __restric
     rec.z = bytes[8] | (bytes[9] << 8) | (bytes[10] << 16) | (bytes[11] << 24);
     rec.w = bytes[12] | (bytes[13] << 8) | (bytes[14] << 16) | (bytes[15] << 24);
     grid[(size_t)conf * n_cells + cell] = rec;
+    const unsigned any = __ballot_sync(0xffffffffu, count > 0);
+    if ((threadIdx.x & 31) == 0) occ[((size_t)conf * n_cells + cell) >> 5] = any;
 }
 
 struct CellArgs {
@@ -497,6 +500,7 @@ struct CellArgs {
     const float4* b_tab;
     const float* b_rad;
     const uint4* grid;
+    const unsigned* occ;
     const CellMeta* meta;
     const double* xf;
     const int4* tiles;
@@ -535,43 +539,79 @@ __global__ void __launch_bounds__(128) clash_cell_kernel(CellArgs p) {
     const float4* bt = p.b_tab + (size_t)conf_b * p.n_b_pad;
     const float4* at = p.a_xyz + (size_t)conf_a * p.n_a;
     const uint4* gr = p.grid + (size_t)conf_a * g * g * g;
-    float dmin2 = 3.0e38f;
-    for (int j = 0; j < p.n_b; ++j) {
-        const float4 b = __ldg(bt + j);
-        const float bx = fmaf(r[0], b.x, fmaf(r[1], b.y, fmaf(r[2], b.z, r[9])));
-        const float by = fmaf(r[3], b.x, fmaf(r[4], b.y, fmaf(r[5], b.z, r[10])));
-        const float bz = fmaf(r[6], b.x, fmaf(r[7], b.y, fmaf(r[8], b.z, r[11])));
-        const float fx = (bx - m.ox) * m.inv_h, fy = (by - m.oy) * m.inv_h, fz = (bz - m.oz) * m.inv_h;
-        // unsigned compare also rejects negative coordinates
-        const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
-        if ((unsigned)cx >= (unsigned)g || (unsigned)cy >= (unsigned)g || (unsigned)cz >= (unsigned)g) continue;
-        const uint4 rec = __ldg(gr + ((size_t)cz * g + cy) * g + cx);
-        const unsigned count = rec.x & 0xffu;
-        if (count == 0) continue;
-        if (count == 255u) {  // crowded cell: all atoms of A
-            for (int i = 0; i < p.n_a; ++i) {
-                const float4 a = __ldg(at + i);
-                const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
-                dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-            }
-            continue;
-        }
-        unsigned long long q0 = (((unsigned long long)rec.y << 32) | rec.x) >> 8;  // indices 0..6
-        unsigned long long q1 = ((unsigned long long)rec.w << 32) | rec.z;         // indices 7..14
-        q0 |= q1 << 56;
-        q1 >>= 8;
-        for (unsigned c = 0; c < count; ++c) {
-            const unsigned ai = (unsigned)(q0 & 0xffull);
-            q0 = (q0 >> 8) | (q1 << 56);
-            q1 >>= 8;
-            const float4 a = __ldg(at + ai);
-            const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
-            dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-        }
-    }
+    const unsigned* oc = p.occ + (((size_t)conf_a * g * g * g) >> 5);
     // same band as the all-pairs kernel (the difference form is at least as accurate as the Gram form)
     const float ext = p.a_rad[conf_a] + p.b_rad[conf_b] + tnorm;
     const float band = fmaf(1.5e-6f * ext, ext, 1e-6f);
+    // once the minimum is below this value the pose is decided (certain clash, or -- with max_clashes > 0 --
+    // certain to need the FP64 count): the remaining atoms are skipped
+    const float settle = p.count_mode ? p.thr2 + band : p.thr2 - band;
+    float dmin2 = 3.0e38f;
+    for (int j0 = 0; j0 < p.n_b && !(dmin2 < settle); j0 += 256) {
+        const int jn = min(256, p.n_b - j0);
+        // ---- phase 1: flag the atoms of B that land in a cell with candidates (no distances yet), so that
+        //      the lanes of a warp do not wait for each other's candidate loops on every atom
+        unsigned flag[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            if (32 * w >= jn) break;
+            const int kn = min(32, jn - 32 * w);
+            unsigned bits = 0u;
+#pragma unroll 4
+            for (int k = 0; k < kn; ++k) {
+                const float4 b = __ldg(bt + j0 + 32 * w + k);
+                const float bx = fmaf(r[0], b.x, fmaf(r[1], b.y, fmaf(r[2], b.z, r[9])));
+                const float by = fmaf(r[3], b.x, fmaf(r[4], b.y, fmaf(r[5], b.z, r[10])));
+                const float bz = fmaf(r[6], b.x, fmaf(r[7], b.y, fmaf(r[8], b.z, r[11])));
+                const int cx = __float2int_rd((bx - m.ox) * m.inv_h), cy = __float2int_rd((by - m.oy) * m.inv_h),
+                          cz = __float2int_rd((bz - m.oz) * m.inv_h);
+                // unsigned compare also rejects negative coordinates; branch-free so that the loads of
+                // several atoms are in flight together
+                const bool inside = (unsigned)cx < (unsigned)g && (unsigned)cy < (unsigned)g && (unsigned)cz < (unsigned)g;
+                const unsigned cell = inside ? (unsigned)((cz * g + cy) * g + cx) : 0u;
+                const unsigned word = __ldg(oc + (cell >> 5));
+                bits |= (inside ? ((word >> (cell & 31u)) & 1u) : 0u) << k;
+            }
+            flag[w] = bits;
+        }
+        // ---- phase 2: distances to the candidate atoms of the flagged atoms only
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            unsigned bits = flag[w];
+            while (bits && !(dmin2 < settle)) {
+                const int k = __ffs(bits) - 1;
+                bits &= bits - 1u;
+                const float4 b = __ldg(bt + j0 + 32 * w + k);
+                const float bx = fmaf(r[0], b.x, fmaf(r[1], b.y, fmaf(r[2], b.z, r[9])));
+                const float by = fmaf(r[3], b.x, fmaf(r[4], b.y, fmaf(r[5], b.z, r[10])));
+                const float bz = fmaf(r[6], b.x, fmaf(r[7], b.y, fmaf(r[8], b.z, r[11])));
+                const int cx = __float2int_rd((bx - m.ox) * m.inv_h), cy = __float2int_rd((by - m.oy) * m.inv_h),
+                          cz = __float2int_rd((bz - m.oz) * m.inv_h);
+                const uint4 rec = __ldg(gr + ((size_t)cz * g + cy) * g + cx);
+                const unsigned count = rec.x & 0xffu;
+                if (count == 255u) {  // crowded cell: all atoms of A
+                    for (int i = 0; i < p.n_a; ++i) {
+                        const float4 a = __ldg(at + i);
+                        const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
+                        dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                    }
+                    continue;
+                }
+                unsigned long long q0 = (((unsigned long long)rec.y << 32) | rec.x) >> 8;  // indices 0..6
+                unsigned long long q1 = ((unsigned long long)rec.w << 32) | rec.z;         // indices 7..14
+                q0 |= q1 << 56;
+                q1 >>= 8;
+                for (unsigned c = 0; c < count; ++c) {
+                    const unsigned ai = (unsigned)(q0 & 0xffull);
+                    q0 = (q0 >> 8) | (q1 << 56);
+                    q1 >>= 8;
+                    const float4 a = __ldg(at + ai);
+                    const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
+                    dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                }
+            }
+        }
+    }
     uint8_t st;
     bool uncertain;
     if (p.count_mode) {
@@ -814,7 +854,8 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     size_t off_axyz = (off_list + (size_t)n_poses * sizeof(UncEntry) + 15) / 16 * 16;
     size_t off_meta = off_axyz + (cell_g ? (size_t)n_conf_a * n_a * 16 : 0);
     size_t off_grid = off_meta + (cell_g ? 64 : 0);
-    size_t total = off_grid + (cell_g ? (size_t)n_conf_a * n_cells * 16 : 0);
+    size_t off_occ = off_grid + (cell_g ? (size_t)n_conf_a * n_cells * 16 : 0);
+    size_t total = off_occ + (cell_g ? (size_t)n_conf_a * n_cells / 8 : 0);
     unsigned char* scratch = nullptr;
     FC_CUDA(cudaMallocAsync((void**)&scratch, total, s));
 
@@ -854,13 +895,15 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
         uint4* grid_tab = (uint4*)(scratch + off_grid);
         clash_bbox_kernel<<<1, 256, 0, s>>>(a_coords, (long long)n_conf_a * n_a, (float)thresh, cell_g, meta);
         dim3 gg((unsigned)((n_cells + 127) / 128), (unsigned)n_conf_a);
-        clash_grid_kernel<<<gg, 128, (size_t)n_a * 24, s>>>(a_coords, n_a, meta, a_xyz, grid_tab);
+        unsigned* occ = (unsigned*)(scratch + off_occ);
+        clash_grid_kernel<<<gg, 128, (size_t)n_a * 24, s>>>(a_coords, n_a, meta, a_xyz, grid_tab, occ);
         CellArgs c;
         c.a_xyz = a_xyz;
         c.a_rad = a.a_rad;
         c.b_tab = a.b_tab;
         c.b_rad = a.b_rad;
         c.grid = grid_tab;
+        c.occ = occ;
         c.meta = meta;
         c.xf = xf;
         c.tiles = (const int4*)tiles;
