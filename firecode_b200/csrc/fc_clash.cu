@@ -547,68 +547,73 @@ __global__ void __launch_bounds__(128) clash_cell_kernel(CellArgs p) {
     // certain to need the FP64 count): the remaining atoms are skipped
     const float settle = p.count_mode ? p.thr2 + band : p.thr2 - band;
     float dmin2 = 3.0e38f;
-    for (int j0 = 0; j0 < p.n_b && !(dmin2 < settle); j0 += 256) {
-        const int jn = min(256, p.n_b - j0);
+    // grid coordinates straight from the atom: (R b + t - o) / h, with the float->int conversion done by the
+    // FP32 adder (adding 1.5 * 2^23 leaves round-to-nearest(x - 0.5) in the low mantissa bits; which of two
+    // cells a point ON a cell face goes to is irrelevant, the candidate lists carry that slack, and both
+    // phases use the same arithmetic).  F2I would run on the quarter-rate conversion unit.
+    float q[12];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) q[k] = r[k] * m.inv_h;
+    q[9] = (r[9] - m.ox) * m.inv_h;
+    q[10] = (r[10] - m.oy) * m.inv_h;
+    q[11] = (r[11] - m.oz) * m.inv_h;
+    const int kMagicBits = 0x4B400000;
+    for (int j0 = 0; j0 < p.n_b && !(dmin2 < settle); j0 += 64) {
+        const int jn = min(64, p.n_b - j0);
         // ---- phase 1: flag the atoms of B that land in a cell with candidates (no distances yet), so that
         //      the lanes of a warp do not wait for each other's candidate loops on every atom
-        unsigned flag[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            if (32 * w >= jn) break;
-            const int kn = min(32, jn - 32 * w);
-            unsigned bits = 0u;
+        unsigned long long bits = 0ull;
 #pragma unroll 4
-            for (int k = 0; k < kn; ++k) {
-                const float4 b = __ldg(bt + j0 + 32 * w + k);
-                const float bx = fmaf(r[0], b.x, fmaf(r[1], b.y, fmaf(r[2], b.z, r[9])));
-                const float by = fmaf(r[3], b.x, fmaf(r[4], b.y, fmaf(r[5], b.z, r[10])));
-                const float bz = fmaf(r[6], b.x, fmaf(r[7], b.y, fmaf(r[8], b.z, r[11])));
-                const int cx = __float2int_rd((bx - m.ox) * m.inv_h), cy = __float2int_rd((by - m.oy) * m.inv_h),
-                          cz = __float2int_rd((bz - m.oz) * m.inv_h);
-                // unsigned compare also rejects negative coordinates; branch-free so that the loads of
-                // several atoms are in flight together
-                const bool inside = (unsigned)cx < (unsigned)g && (unsigned)cy < (unsigned)g && (unsigned)cz < (unsigned)g;
-                const unsigned cell = inside ? (unsigned)((cz * g + cy) * g + cx) : 0u;
-                const unsigned word = __ldg(oc + (cell >> 5));
-                bits |= (inside ? ((word >> (cell & 31u)) & 1u) : 0u) << k;
-            }
-            flag[w] = bits;
+        for (int k = 0; k < jn; ++k) {
+            const float4 b = __ldg(bt + j0 + k);
+            const float gx = fmaf(q[0], b.x, fmaf(q[1], b.y, fmaf(q[2], b.z, q[9])));
+            const float gy = fmaf(q[3], b.x, fmaf(q[4], b.y, fmaf(q[5], b.z, q[10])));
+            const float gz = fmaf(q[6], b.x, fmaf(q[7], b.y, fmaf(q[8], b.z, q[11])));
+            const int cx = __float_as_int((gx - 0.5f) + 12582912.0f) - kMagicBits;
+            const int cy = __float_as_int((gy - 0.5f) + 12582912.0f) - kMagicBits;
+            const int cz = __float_as_int((gz - 0.5f) + 12582912.0f) - kMagicBits;
+            // unsigned compare also rejects negative coordinates; branch-free so that the loads of
+            // several atoms are in flight together
+            const bool inside = (unsigned)cx < (unsigned)g && (unsigned)cy < (unsigned)g && (unsigned)cz < (unsigned)g;
+            const unsigned cell = inside ? (unsigned)((cz * g + cy) * g + cx) : 0u;
+            const unsigned word = __ldg(oc + (cell >> 5));
+            bits |= (unsigned long long)(inside ? ((word >> (cell & 31u)) & 1u) : 0u) << k;
         }
         // ---- phase 2: distances to the candidate atoms of the flagged atoms only
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            unsigned bits = flag[w];
-            while (bits && !(dmin2 < settle)) {
-                const int k = __ffs(bits) - 1;
-                bits &= bits - 1u;
-                const float4 b = __ldg(bt + j0 + 32 * w + k);
-                const float bx = fmaf(r[0], b.x, fmaf(r[1], b.y, fmaf(r[2], b.z, r[9])));
-                const float by = fmaf(r[3], b.x, fmaf(r[4], b.y, fmaf(r[5], b.z, r[10])));
-                const float bz = fmaf(r[6], b.x, fmaf(r[7], b.y, fmaf(r[8], b.z, r[11])));
-                const int cx = __float2int_rd((bx - m.ox) * m.inv_h), cy = __float2int_rd((by - m.oy) * m.inv_h),
-                          cz = __float2int_rd((bz - m.oz) * m.inv_h);
-                const uint4 rec = __ldg(gr + ((size_t)cz * g + cy) * g + cx);
-                const unsigned count = rec.x & 0xffu;
-                if (count == 255u) {  // crowded cell: all atoms of A
-                    for (int i = 0; i < p.n_a; ++i) {
-                        const float4 a = __ldg(at + i);
-                        const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
-                        dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-                    }
-                    continue;
-                }
-                unsigned long long q0 = (((unsigned long long)rec.y << 32) | rec.x) >> 8;  // indices 0..6
-                unsigned long long q1 = ((unsigned long long)rec.w << 32) | rec.z;         // indices 7..14
-                q0 |= q1 << 56;
-                q1 >>= 8;
-                for (unsigned c = 0; c < count; ++c) {
-                    const unsigned ai = (unsigned)(q0 & 0xffull);
-                    q0 = (q0 >> 8) | (q1 << 56);
-                    q1 >>= 8;
-                    const float4 a = __ldg(at + ai);
+        while (bits && !(dmin2 < settle)) {
+            const int k = __ffsll((long long)bits) - 1;
+            bits &= bits - 1ull;
+            const float4 b = __ldg(bt + j0 + k);
+            const float gx = fmaf(q[0], b.x, fmaf(q[1], b.y, fmaf(q[2], b.z, q[9])));
+            const float gy = fmaf(q[3], b.x, fmaf(q[4], b.y, fmaf(q[5], b.z, q[10])));
+            const float gz = fmaf(q[6], b.x, fmaf(q[7], b.y, fmaf(q[8], b.z, q[11])));
+            const int cx = __float_as_int((gx - 0.5f) + 12582912.0f) - kMagicBits;
+            const int cy = __float_as_int((gy - 0.5f) + 12582912.0f) - kMagicBits;
+            const int cz = __float_as_int((gz - 0.5f) + 12582912.0f) - kMagicBits;
+            const float bx = fmaf(r[0], b.x, fmaf(r[1], b.y, fmaf(r[2], b.z, r[9])));
+            const float by = fmaf(r[3], b.x, fmaf(r[4], b.y, fmaf(r[5], b.z, r[10])));
+            const float bz = fmaf(r[6], b.x, fmaf(r[7], b.y, fmaf(r[8], b.z, r[11])));
+            const uint4 rec = __ldg(gr + ((size_t)cz * g + cy) * g + cx);
+            const unsigned count = rec.x & 0xffu;
+            if (count == 255u) {  // crowded cell: all atoms of A
+                for (int i = 0; i < p.n_a; ++i) {
+                    const float4 a = __ldg(at + i);
                     const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
                     dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
                 }
+                continue;
+            }
+            unsigned long long q0 = (((unsigned long long)rec.y << 32) | rec.x) >> 8;  // indices 0..6
+            unsigned long long q1 = ((unsigned long long)rec.w << 32) | rec.z;         // indices 7..14
+            q0 |= q1 << 56;
+            q1 >>= 8;
+            for (unsigned c = 0; c < count; ++c) {
+                const unsigned ai = (unsigned)(q0 & 0xffull);
+                q0 = (q0 >> 8) | (q1 << 56);
+                q1 >>= 8;
+                const float4 a = __ldg(at + ai);
+                const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
+                dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
             }
         }
     }
