@@ -406,6 +406,8 @@ struct CellMeta {        // written by clash_bbox_kernel, read by the grid / que
     float h, inv_h;      // cell edge
     float rc2;           // squared candidate radius around a cell centre
     int g;               // cells per axis
+    int gmask;           // 2^ceil(log2 g) - 1
+    unsigned cell_bias;  // 0x4B400000 * (g*g + g + 1) mod 2^32 (biased -> linear cell index)
 };
 
 __global__ void __launch_bounds__(256) clash_bbox_kernel(const double* __restrict__ a_coords, long long n_atoms_total,
@@ -442,6 +444,10 @@ __global__ void __launch_bounds__(256) clash_bbox_kernel(const double* __restric
         float rc = thresh + kCellPad + m.h * 0.8661f + 1e-3f;
         m.rc2 = rc * rc;
         m.g = g;
+        int pw = 1;
+        while (pw < g) pw <<= 1;
+        m.gmask = pw - 1;
+        m.cell_bias = 0x4B400000u * (unsigned)(g * g + g + 1);
         *meta = m;
     }
 }
@@ -491,7 +497,8 @@ __global__ void __launch_bounds__(128) clash_grid_kernel(const double* __restric
     rec.w = bytes[12] | (bytes[13] << 8) | (bytes[14] << 16) | (bytes[15] << 24);
     grid[(size_t)conf * n_cells + cell] = rec;
     const unsigned any = __ballot_sync(0xffffffffu, count > 0);
-    if ((threadIdx.x & 31) == 0) occ[((size_t)conf * n_cells + cell) >> 5] = any;
+    if ((threadIdx.x & 31) == 0) occ[(size_t)conf * (n_cells / 32 + 1) + (cell >> 5)] = any;
+    if (cell == 0) occ[(size_t)conf * (n_cells / 32 + 1) + n_cells / 32] = 0u;  // spare word: the dummy cell
 }
 
 struct CellArgs {
@@ -539,7 +546,7 @@ __global__ void __launch_bounds__(128) clash_cell_kernel(CellArgs p) {
     const float4* bt = p.b_tab + (size_t)conf_b * p.n_b_pad;
     const float4* at = p.a_xyz + (size_t)conf_a * p.n_a;
     const uint4* gr = p.grid + (size_t)conf_a * g * g * g;
-    const unsigned* oc = p.occ + (((size_t)conf_a * g * g * g) >> 5);
+    const unsigned* oc = p.occ + ((size_t)conf_a * ((size_t)g * g * g / 32 + 1));
     // same band as the all-pairs kernel (the difference form is at least as accurate as the Gram form)
     const float ext = p.a_rad[conf_a] + p.b_rad[conf_b] + tnorm;
     const float band = fmaf(1.5e-6f * ext, ext, 1e-6f);
@@ -554,42 +561,41 @@ __global__ void __launch_bounds__(128) clash_cell_kernel(CellArgs p) {
     float q[12];
 #pragma unroll
     for (int k = 0; k < 9; ++k) q[k] = r[k] * m.inv_h;
-    q[9] = (r[9] - m.ox) * m.inv_h;
-    q[10] = (r[10] - m.oy) * m.inv_h;
-    q[11] = (r[11] - m.oz) * m.inv_h;
-    const int kMagicBits = 0x4B400000;
-    for (int j0 = 0; j0 < p.n_b && !(dmin2 < settle); j0 += 64) {
-        const int jn = min(64, p.n_b - j0);
+    q[9] = (r[9] - m.ox) * m.inv_h - 0.5f;
+    q[10] = (r[10] - m.oy) * m.inv_h - 0.5f;
+    q[11] = (r[11] - m.oz) * m.inv_h - 0.5f;
+    const unsigned kMagicBits = 0x4B400000u;
+    const unsigned range_mask = ~(unsigned)(m.gmask);  // bits that must equal kMagicBits for 0 <= n < 2^k
+    const unsigned dummy_cell = (unsigned)g * g * g;    // one spare, always-empty word behind the bit-grid
+    for (int j0 = 0; j0 < p.n_b && !(dmin2 < settle); j0 += 32) {
+        const int jn = min(32, p.n_b - j0);
         // ---- phase 1: flag the atoms of B that land in a cell with candidates (no distances yet), so that
-        //      the lanes of a warp do not wait for each other's candidate loops on every atom
-        unsigned long long bits = 0ull;
+        //      the lanes of a warp do not wait for each other's candidate loops on every atom.  Integer work
+        //      is kept minimal: the ALU pipe (16 lanes) is what bounds this loop.
+        unsigned bits = 0u;
 #pragma unroll 4
         for (int k = 0; k < jn; ++k) {
             const float4 b = __ldg(bt + j0 + k);
-            const float gx = fmaf(q[0], b.x, fmaf(q[1], b.y, fmaf(q[2], b.z, q[9])));
-            const float gy = fmaf(q[3], b.x, fmaf(q[4], b.y, fmaf(q[5], b.z, q[10])));
-            const float gz = fmaf(q[6], b.x, fmaf(q[7], b.y, fmaf(q[8], b.z, q[11])));
-            const int cx = __float_as_int((gx - 0.5f) + 12582912.0f) - kMagicBits;
-            const int cy = __float_as_int((gy - 0.5f) + 12582912.0f) - kMagicBits;
-            const int cz = __float_as_int((gz - 0.5f) + 12582912.0f) - kMagicBits;
-            // unsigned compare also rejects negative coordinates; branch-free so that the loads of
-            // several atoms are in flight together
-            const bool inside = (unsigned)cx < (unsigned)g && (unsigned)cy < (unsigned)g && (unsigned)cz < (unsigned)g;
-            const unsigned cell = inside ? (unsigned)((cz * g + cy) * g + cx) : 0u;
+            const unsigned ix = __float_as_uint(fmaf(q[0], b.x, fmaf(q[1], b.y, fmaf(q[2], b.z, q[9]))) + 12582912.0f);
+            const unsigned iy = __float_as_uint(fmaf(q[3], b.x, fmaf(q[4], b.y, fmaf(q[5], b.z, q[10]))) + 12582912.0f);
+            const unsigned iz = __float_as_uint(fmaf(q[6], b.x, fmaf(q[7], b.y, fmaf(q[8], b.z, q[11]))) + 12582912.0f);
+            // all three of the form kMagicBits + n with n < 2^k  <=>  their OR is (a point that is really inside
+            // always passes; a far-away point that slips through only costs a phase-2 visit, which re-checks)
+            const bool inside = ((ix | iy | iz) & range_mask) == kMagicBits;
+            const unsigned cell = inside ? (iz * (unsigned)(g * g) + iy * (unsigned)g + ix - m.cell_bias) : dummy_cell;
             const unsigned word = __ldg(oc + (cell >> 5));
-            bits |= (unsigned long long)(inside ? ((word >> (cell & 31u)) & 1u) : 0u) << k;
+            bits = __funnelshift_r(bits, __funnelshift_r(word, 0u, cell), 1);  // bit (cell & 31) of word -> top of bits
         }
+        bits >>= (32 - jn);
         // ---- phase 2: distances to the candidate atoms of the flagged atoms only
         while (bits && !(dmin2 < settle)) {
-            const int k = __ffsll((long long)bits) - 1;
-            bits &= bits - 1ull;
+            const int k = __ffs(bits) - 1;
+            bits &= bits - 1u;
             const float4 b = __ldg(bt + j0 + k);
-            const float gx = fmaf(q[0], b.x, fmaf(q[1], b.y, fmaf(q[2], b.z, q[9])));
-            const float gy = fmaf(q[3], b.x, fmaf(q[4], b.y, fmaf(q[5], b.z, q[10])));
-            const float gz = fmaf(q[6], b.x, fmaf(q[7], b.y, fmaf(q[8], b.z, q[11])));
-            const int cx = __float_as_int((gx - 0.5f) + 12582912.0f) - kMagicBits;
-            const int cy = __float_as_int((gy - 0.5f) + 12582912.0f) - kMagicBits;
-            const int cz = __float_as_int((gz - 0.5f) + 12582912.0f) - kMagicBits;
+            const int cx = (int)(__float_as_uint(fmaf(q[0], b.x, fmaf(q[1], b.y, fmaf(q[2], b.z, q[9]))) + 12582912.0f) - kMagicBits);
+            const int cy = (int)(__float_as_uint(fmaf(q[3], b.x, fmaf(q[4], b.y, fmaf(q[5], b.z, q[10]))) + 12582912.0f) - kMagicBits);
+            const int cz = (int)(__float_as_uint(fmaf(q[6], b.x, fmaf(q[7], b.y, fmaf(q[8], b.z, q[11]))) + 12582912.0f) - kMagicBits);
+            if ((unsigned)cx >= (unsigned)g || (unsigned)cy >= (unsigned)g || (unsigned)cz >= (unsigned)g) continue;
             const float bx = fmaf(r[0], b.x, fmaf(r[1], b.y, fmaf(r[2], b.z, r[9])));
             const float by = fmaf(r[3], b.x, fmaf(r[4], b.y, fmaf(r[5], b.z, r[10])));
             const float bz = fmaf(r[6], b.x, fmaf(r[7], b.y, fmaf(r[8], b.z, r[11])));
@@ -841,7 +847,7 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
         const bool wanted = mode == 1 || (mode == 2 && n_poses >= 16384);
         if (possible && wanted) {
             const size_t budget = (size_t)512 << 20;
-            for (int g_try : {64, 48, 32}) {
+            for (int g_try : {64, 32}) {  // powers of two: the flag phase range-checks with one mask
                 if ((size_t)n_conf_a * g_try * g_try * g_try * 16 <= budget) {
                     cell_g = g_try;
                     break;
@@ -860,7 +866,7 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     size_t off_meta = off_axyz + (cell_g ? (size_t)n_conf_a * n_a * 16 : 0);
     size_t off_grid = off_meta + (cell_g ? 64 : 0);
     size_t off_occ = off_grid + (cell_g ? (size_t)n_conf_a * n_cells * 16 : 0);
-    size_t total = off_occ + (cell_g ? (size_t)n_conf_a * n_cells / 8 : 0);
+    size_t total = off_occ + (cell_g ? (size_t)n_conf_a * (n_cells / 32 + 1) * 4 : 0);
     unsigned char* scratch = nullptr;
     FC_CUDA(cudaMallocAsync((void**)&scratch, total, s));
 
