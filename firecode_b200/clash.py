@@ -19,12 +19,20 @@ NEAR_EPS = 1e-6
 
 @dataclass
 class ClashResult:
-    mask: np.ndarray  # (n_poses,) bool, True = passes (no compenetration)
     status: np.ndarray  # (n_poses,) uint8 FC_STATUS_* bits
     min_dist: np.ndarray | None  # (n_poses,) f32 estimate (exact f64->f32 for rechecked poses)
+    n_pass: int = 0
     n_rechecked: int = 0
     near_idx: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int64))
     near_dist: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.float64))
+    _mask: np.ndarray | None = None
+
+    @property
+    def mask(self) -> np.ndarray:
+        """(n_poses,) bool, True = passes (no compenetration); derived from ``status`` on first use."""
+        if self._mask is None:
+            self._mask = (self.status & STATUS_PASS).astype(bool)
+        return self._mask
 
 
 def tile_poses(n_b: int) -> int:
@@ -84,8 +92,8 @@ def compenetration_check_batch(frag_a, frag_b, xf, thresh=1.0, max_clashes=0, co
         assert len(ca) == n and len(cb) == n
         assert n == 0 or (ca.min() >= 0 and ca.max() < a.shape[0] and cb.min() >= 0 and cb.max() < b.shape[0])
         tiles = build_tiles(ca, cb, b.shape[1])
-    status = np.zeros(n, dtype=np.uint8)
-    min_dist = np.zeros(n, dtype=np.float32) if want_min_dist else None
+    status = np.empty(n, dtype=np.uint8)
+    min_dist = np.empty(n, dtype=np.float32) if want_min_dist else None
     counts = np.zeros(3, dtype=np.int64)
     near_idx = np.zeros(max(near_cap, 1), dtype=np.int64)
     near_dist = np.zeros(max(near_cap, 1), dtype=np.float64)
@@ -100,7 +108,7 @@ def compenetration_check_batch(frag_a, frag_b, xf, thresh=1.0, max_clashes=0, co
     _lib.check(rc, "fc_clash_batch")
     n_near = int(min(counts[2], near_cap))
     order = np.argsort(near_idx[:n_near], kind="stable")
-    return ClashResult(mask=(status & STATUS_PASS).astype(bool), status=status, min_dist=min_dist,
+    return ClashResult(status=status, min_dist=min_dist, n_pass=int(counts[0]),
                        n_rechecked=int(counts[1]), near_idx=near_idx[:n_near][order],
                        near_dist=near_dist[:n_near][order])
 

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "fc_common.cuh"
@@ -151,7 +152,25 @@ extern "C" int fc_clash_batch(const double* a_coords, int n_conf_a, int n_a, con
         }
     }
 
+    // grow-only pinned staging buffer for the status bytes (per host thread)
+    static thread_local uint8_t* h_stage = nullptr;
+    static thread_local size_t h_stage_cap = 0;
+    if (h_stage_cap < (size_t)n_poses) {
+        if (h_stage) cudaFreeHost(h_stage);
+        h_stage = nullptr;
+        h_stage_cap = 0;
+        size_t want = std::max<size_t>((size_t)n_poses, (size_t)1 << 20);
+        cudaError_t he = cudaHostAlloc((void**)&h_stage, want, cudaHostAllocDefault);
+        if (he != cudaSuccess) return cuda_fail(he, "cudaHostAlloc(status staging)", __FILE__, __LINE__);
+        h_stage_cap = want;
+    }
+    const bool trace = getenv("FC_CLASH_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_setup = 0, t_issued = 0, t_synced = 0;
     const int kBuf = 2;
+    int64_t cnt_pass = 0, cnt_re = 0, cnt_near = 0;
+    cudaEvent_t ev_done[kBuf] = {nullptr, nullptr};
     cudaStream_t st[kBuf];
     double* d_xf[kBuf] = {nullptr, nullptr};
     uint8_t* d_status = nullptr;
@@ -180,6 +199,7 @@ extern "C" int fc_clash_batch(const double* a_coords, int n_conf_a, int n_a, con
     ev_setup = nullptr;
     for (int i = 0; i < kBuf; ++i) FC_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
     FC_TRY(cudaEventCreateWithFlags(&ev_setup, cudaEventDisableTiming));
+    for (int i = 0; i < kBuf; ++i) FC_TRY(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
     FC_TRY(cudaMallocAsync((void**)&d_a, (size_t)n_conf_a * n_a * 24, st[0]));
     FC_TRY(cudaMallocAsync((void**)&d_b, (size_t)n_conf_b * n_b * 24, st[0]));
     FC_TRY(cudaMallocAsync((void**)&d_status, (size_t)n_poses, st[0]));
@@ -200,23 +220,60 @@ extern "C" int fc_clash_batch(const double* a_coords, int n_conf_a, int n_a, con
     FC_TRY(cudaEventRecord(ev_setup, st[0]));
     for (int i = 1; i < kBuf; ++i) FC_TRY(cudaStreamWaitEvent(st[i], ev_setup, 0));
 
+    t_setup = now();
     {
+        // chunk c rides stream c % 2.  While the H2D engine moves the next chunk's transforms the host
+        // thread drains a finished chunk: status bytes pinned staging -> caller's buffer (first touch of the
+        // caller's pages happens here, hidden behind the transfers) and the pass / recheck / near counts.
+        auto drain = [&](int64_t first, int64_t n) {
+            memcpy(status + first, h_stage + first, (size_t)n);
+            int64_t i = first;
+            const int64_t end = first + n;
+            for (; i + 8 <= end; i += 8) {  // eight status bytes per step
+                uint64_t w;
+                memcpy(&w, h_stage + i, 8);
+                cnt_pass += __builtin_popcountll(w & 0x0101010101010101ull);
+                cnt_re += __builtin_popcountll(w & 0x0202020202020202ull);
+                cnt_near += __builtin_popcountll(w & 0x0404040404040404ull);
+            }
+            for (; i < end; ++i) {
+                cnt_pass += h_stage[i] & FC_STATUS_PASS;
+                cnt_re += (h_stage[i] & FC_STATUS_RECHECKED) ? 1 : 0;
+                cnt_near += (h_stage[i] & FC_STATUS_NEAR) ? 1 : 0;
+            }
+        };
+        int64_t pend_first[kBuf] = {-1, -1}, pend_n[kBuf] = {0, 0};
         int b = 0;
         for (int64_t first = 0; first < n_poses; first += chunk, b = (b + 1) % kBuf) {
             int64_t n = std::min<int64_t>(chunk, n_poses - first);
             cudaStream_t s = st[b];
+            if (pend_first[b] >= 0) {  // the chunk that used this stream two steps ago
+                FC_TRY(cudaEventSynchronize(ev_done[b]));
+                drain(pend_first[b], pend_n[b]);
+            }
             FC_TRY(cudaMemcpyAsync(d_xf[b], xf + first * 12, (size_t)n * 96, cudaMemcpyHostToDevice, s));
             rc = fc_clash_screen_dev(d_a, n_conf_a, n_a, d_b, n_conf_b, n_b, d_xf[b], n, d_tiles,
                                      n_tiles, thresh, max_clashes, strict, d_status + first,
                                      d_min ? d_min + first : nullptr, d_near_count, d_near_idx,
                                      d_near_dist, near_cap, first, (void*)s);
             if (rc != FC_OK) goto done;
+            FC_TRY(cudaMemcpyAsync(h_stage + first, d_status + first, (size_t)n, cudaMemcpyDeviceToHost, s));
+            FC_TRY(cudaEventRecord(ev_done[b], s));
+            pend_first[b] = first;
+            pend_n[b] = n;
+        }
+        t_issued = now();
+        // remaining chunks in issue order
+        for (int k = 0; k < kBuf; ++k, b = (b + 1) % kBuf) {
+            if (pend_first[b] < 0) continue;
+            FC_TRY(cudaEventSynchronize(ev_done[b]));
+            drain(pend_first[b], pend_n[b]);
         }
     }
     for (int i = 0; i < kBuf; ++i) FC_TRY(cudaStreamSynchronize(st[i]));
-    // results come back in one piece: a per-chunk copy into pageable host memory would block the
-    // host thread and serialise the H2D / kernel pipeline
-    FC_TRY(cudaMemcpy(status, d_status, (size_t)n_poses, cudaMemcpyDeviceToHost));
+    t_synced = now();
+    // status bytes came back chunk by chunk into the pinned staging buffer (the copies ride the D2H engine
+    // while the next chunk's transforms ride the H2D engine); one pass copies them out and counts
     if (min_dist) FC_TRY(cudaMemcpy(min_dist, d_min, (size_t)n_poses * 4, cudaMemcpyDeviceToHost));
     {
         int32_t n_near = 0;
@@ -228,17 +285,14 @@ extern "C" int fc_clash_batch(const double* a_coords, int n_conf_a, int n_a, con
         if (n_copy > 0 && near_dist)
             FC_TRY(cudaMemcpy(near_dist, d_near_dist, (size_t)n_copy * 8, cudaMemcpyDeviceToHost));
         if (counts) {
-            int64_t pass = 0, re = 0, near = 0;
-            for (int64_t i = 0; i < n_poses; ++i) {
-                pass += status[i] & FC_STATUS_PASS;
-                re += (status[i] & FC_STATUS_RECHECKED) ? 1 : 0;
-                near += (status[i] & FC_STATUS_NEAR) ? 1 : 0;
-            }
-            counts[0] = pass;
-            counts[1] = re;
-            counts[2] = near;
+            counts[0] = cnt_pass;
+            counts[1] = cnt_re;
+            counts[2] = cnt_near;
         }
     }
+    if (trace)
+        fprintf(stderr, "fc_clash_batch: setup %.2f ms, issue %.2f ms, wait %.2f ms, readback %.2f ms\n", t_setup - t_begin,
+                t_issued - t_setup, t_synced - t_issued, now() - t_synced);
 done:
     if (st[0]) {
         for (int i = 0; i < kBuf; ++i) {
@@ -253,6 +307,8 @@ done:
     for (int i = 0; i < kBuf; ++i)
         if (st[i]) cudaStreamDestroy(st[i]);
     if (ev_setup) cudaEventDestroy(ev_setup);
+    for (int i = 0; i < kBuf; ++i)
+        if (ev_done[i]) cudaEventDestroy(ev_done[i]);
     return rc;
 #undef FC_TRY
 }
