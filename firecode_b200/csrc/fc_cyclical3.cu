@@ -22,6 +22,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <utility>
 #include <vector>
@@ -305,6 +306,24 @@ __global__ void cyc3_pair_xf_kernel(Cyc3Dev p, int mi, int mj, const double* __r
     o[9] = trel[0]; o[10] = trel[1]; o[11] = trel[2];
 }
 
+// absolute transform (R row-major, t) of molecule m of group g for each DISTINCT angle of that molecule's column
+__global__ void cyc3_abs_xf_kernel(Cyc3Dev p, const double* __restrict__ uang, int u_max, int n_u0, int n_u1, int n_u2,
+                                   double* __restrict__ xf_abs) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)p.n_groups * 3 * u_max) return;
+    const int u = (int)(i % u_max);
+    const int m = (int)((i / u_max) % 3);
+    const long long g = i / ((long long)u_max * 3);
+    const int n_u = m == 0 ? n_u0 : (m == 1 ? n_u1 : n_u2);
+    if (u >= n_u) return;
+    M3 r;
+    double t[3];
+    cyc3_mol_xf(p, g, m, uang[m * u_max + u], r, t);
+    double* o = xf_abs + i * 12;
+    for (int k = 0; k < 9; ++k) o[k] = r.m[k];
+    o[9] = t[0]; o[10] = t[1]; o[11] = t[2];
+}
+
 __device__ __forceinline__ void cyc3_atom(const Cyc3Dev& p, const int* conf, const M3* rot, const double (*t)[3],
                                           int atom, double* out) {
     int m = atom < p.n_atoms[0] ? 0 : (atom < p.n_atoms[0] + p.n_atoms[1] ? 1 : 2);
@@ -332,6 +351,9 @@ struct Cyc3SimArgs {
     const uint8_t* st[3];   // per pair: status over (group, distinct angle pair)
     const int* umap[3];     // per pair: angle index -> distinct angle pair
     int n_u[3];
+    const double* xf_abs;   // (G, 3, u_max, 12): absolute transform of every molecule for its distinct angles
+    const int* amap[3];     // per molecule: angle index -> distinct angle of that molecule
+    int u_max;
     uint8_t* status;        // per pose, out: combined FC_STATUS_* bits
     uint8_t* keep;          // per pose, out
     double rmsd_thr, eps;
@@ -351,7 +373,31 @@ __device__ __forceinline__ void push_tie3(const Cyc3SimArgs& a, long long pose, 
     }
 }
 
-// one warp per group: combine the three block screens, then keep-first over the survivors
+// combined status of every pose: PASS iff all three block screens pass (utils.py:553-575 with max_clashes = 0),
+// RECHECKED / NEAR if any block was; also counts passes and rechecks
+__global__ void __launch_bounds__(256) cyc3_combine_kernel(Cyc3SimArgs a, long long n_poses, unsigned long long* __restrict__ counts) {
+    const long long pose = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint8_t comb = 0;
+    if (pose < n_poses) {
+        const int n_ang = a.p.n_angles;
+        const long long g = pose / n_ang;
+        const int ai = (int)(pose - g * n_ang);
+        uint8_t s0 = a.st[0][g * a.n_u[0] + a.umap[0][ai]];
+        uint8_t s1 = a.st[1][g * a.n_u[1] + a.umap[1][ai]];
+        uint8_t s2 = a.st[2][g * a.n_u[2] + a.umap[2][ai]];
+        comb = (uint8_t)((s0 & s1 & s2 & FC_STATUS_PASS) | ((s0 | s1 | s2) & (FC_STATUS_RECHECKED | FC_STATUS_NEAR)));
+        a.status[pose] = comb;
+        a.keep[pose] = 0;
+    }
+    const unsigned pass = __ballot_sync(0xffffffffu, comb & FC_STATUS_PASS);
+    const unsigned rech = __ballot_sync(0xffffffffu, comb & FC_STATUS_RECHECKED);
+    if ((threadIdx.x & 31) == 0 && (pass | rech)) {
+        if (pass) atomicAdd(counts, (unsigned long long)__popc(pass));
+        if (rech) atomicAdd(counts + 1, (unsigned long long)__popc(rech));
+    }
+}
+
+// one warp per group: keep-first over the clash survivors in angle order
 __global__ void __launch_bounds__(128) cyc3_group_similarity_kernel(Cyc3SimArgs a) {
     const Cyc3Dev& p = a.p;
     const int lane = threadIdx.x & 31;
@@ -364,68 +410,99 @@ __global__ void __launch_bounds__(128) cyc3_group_similarity_kernel(Cyc3SimArgs 
     extern __shared__ int s_acc_all[];
     int* s_acc = s_acc_all + (threadIdx.x >> 5) * n_ang;
     int n_acc = 0;
-    for (int ai = 0; ai < n_ang; ++ai) {
-        const long long pose = g * n_ang + ai;
-        uint8_t s0 = a.st[0][g * a.n_u[0] + a.umap[0][ai]];
-        uint8_t s1 = a.st[1][g * a.n_u[1] + a.umap[1][ai]];
-        uint8_t s2 = a.st[2][g * a.n_u[2] + a.umap[2][ai]];
-        uint8_t comb = (uint8_t)((s0 & s1 & s2 & FC_STATUS_PASS) | ((s0 | s1 | s2) & (FC_STATUS_RECHECKED | FC_STATUS_NEAR)));
-        if (lane == 0) a.status[pose] = comb;
-        if (!(comb & FC_STATUS_PASS)) {
-            if (lane == 0) a.keep[pose] = 0;
-            continue;
-        }
-        M3 rp[3];
-        double tp[3][3];
-        for (int m = 0; m < 3; ++m) cyc3_mol_xf(p, g, m, p.angles[3 * ai + m], rp[m], tp[m]);
-        bool similar = false;
-        for (int k = 0; k < n_acc && !similar; ++k) {
-            const int aj = s_acc[k];
-            M3 rq[3];
-            double tq[3][3];
-            for (int m = 0; m < 3; ++m) cyc3_mol_xf(p, g, m, p.angles[3 * aj + m], rq[m], tq[m]);
-            double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            for (int at = lane; at < n_tot; at += 32) {
-                double x[3], y[3];
-                cyc3_atom(p, conf, rp, tp, at, x);
-                cyc3_atom(p, conf, rq, tq, at, y);
+    for (int base = 0; base < n_ang; base += 32) {
+        const int mine = base + lane;
+        const bool ok = mine < n_ang && (a.status[g * n_ang + mine] & FC_STATUS_PASS);
+        unsigned survivors = __ballot_sync(0xffffffffu, ok);
+        while (survivors) {
+            const int ai = base + __ffs(survivors) - 1;
+            survivors &= survivors - 1u;
+            const long long pose = g * n_ang + ai;
+            const double* xp[3];
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+            for (int m = 0; m < 3; ++m) xp[m] = a.xf_abs + (((size_t)g * 3 + m) * a.u_max + a.amap[m][ai]) * 12;
+            bool similar = false;
+            for (int k = 0; k < n_acc && !similar; ++k) {
+                const int aj = s_acc[k];
+                // H = p^T q over all atoms, uncentred (rmsd_and_max(center=False)); molecule loops are unrolled so
+                // that the transforms stay in registers
+                double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                double gsum = 0.0;  // |p|^2 + |q|^2
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) h[3 * r + c] += x[r] * y[c];
-            }
+                for (int m = 0; m < 3; ++m) {
+                    const double* xq = a.xf_abs + (((size_t)g * 3 + m) * a.u_max + a.amap[m][aj]) * 12;
+                    double rp[12], rq[12];
 #pragma unroll
-            for (int e = 0; e < 9; ++e) h[e] = wsum_d(h[e]);
-            M3 R = kabsch_from_cov(h, nullptr);
-            double ss = 0.0, mx = 0.0;
-            for (int at = lane; at < n_tot; at += 32) {
-                double x[3], y[3];
-                cyc3_atom(p, conf, rp, tp, at, x);
-                cyc3_atom(p, conf, rq, tq, at, y);
-                double dx = (x[0] * R.m[0] + x[1] * R.m[3] + x[2] * R.m[6]) - y[0];
-                double dy = (x[0] * R.m[1] + x[1] * R.m[4] + x[2] * R.m[7]) - y[1];
-                double dz = (x[0] * R.m[2] + x[1] * R.m[5] + x[2] * R.m[8]) - y[2];
-                double d2 = dx * dx + dy * dy + dz * dz;
-                ss += d2;
-                mx = fmax(mx, d2);
+                    for (int e = 0; e < 12; ++e) { rp[e] = xp[m][e]; rq[e] = xq[e]; }
+                    const double* base = p.coords[m] + (size_t)conf[m] * p.n_atoms[m] * 3;
+                    for (int at = lane; at < p.n_atoms[m]; at += 32) {
+                        const double bx = base[3 * at], by = base[3 * at + 1], bz = base[3 * at + 2];
+                        const double x[3] = {(rp[0] * bx + rp[1] * by + rp[2] * bz) + rp[9], (rp[3] * bx + rp[4] * by + rp[5] * bz) + rp[10],
+                                             (rp[6] * bx + rp[7] * by + rp[8] * bz) + rp[11]};
+                        const double y[3] = {(rq[0] * bx + rq[1] * by + rq[2] * bz) + rq[9], (rq[3] * bx + rq[4] * by + rq[5] * bz) + rq[10],
+                                             (rq[6] * bx + rq[7] * by + rq[8] * bz) + rq[11]};
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            gsum += x[r] * x[r] + y[r] * y[r];
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) h[3 * r + c] += x[r] * y[c];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 9; ++e) h[e] = wsum_d(h[e]);
+                gsum = wsum_d(gsum);
+                // screen: RMSD from the closed-form singular values; clearly dissimilar pairs (the common case
+                // among kept poses) skip the Jacobi solve and the second pass over the atoms
+                {
+                    const double msd = (gsum - 2.0 * singular_sum3(h)) / n_tot;
+                    const double lim = a.rmsd_thr + 1e-4;
+                    if (msd > lim * lim) continue;
+                }
+                M3 R = kabsch_from_cov(h, nullptr);
+                double ss = 0.0, mx = 0.0;
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    const double* xq = a.xf_abs + (((size_t)g * 3 + m) * a.u_max + a.amap[m][aj]) * 12;
+                    double rp[12], rq[12];
+#pragma unroll
+                    for (int e = 0; e < 12; ++e) { rp[e] = xp[m][e]; rq[e] = xq[e]; }
+                    const double* base = p.coords[m] + (size_t)conf[m] * p.n_atoms[m] * 3;
+                    for (int at = lane; at < p.n_atoms[m]; at += 32) {
+                        const double bx = base[3 * at], by = base[3 * at + 1], bz = base[3 * at + 2];
+                        const double x[3] = {(rp[0] * bx + rp[1] * by + rp[2] * bz) + rp[9], (rp[3] * bx + rp[4] * by + rp[5] * bz) + rp[10],
+                                             (rp[6] * bx + rp[7] * by + rp[8] * bz) + rp[11]};
+                        const double y[3] = {(rq[0] * bx + rq[1] * by + rq[2] * bz) + rq[9], (rq[3] * bx + rq[4] * by + rq[5] * bz) + rq[10],
+                                             (rq[6] * bx + rq[7] * by + rq[8] * bz) + rq[11]};
+                        // diff = p @ R - q
+                        const double dx = (x[0] * R.m[0] + x[1] * R.m[3] + x[2] * R.m[6]) - y[0];
+                        const double dy = (x[0] * R.m[1] + x[1] * R.m[4] + x[2] * R.m[7]) - y[1];
+                        const double dz = (x[0] * R.m[2] + x[1] * R.m[5] + x[2] * R.m[8]) - y[2];
+                        const double d2 = dx * dx + dy * dy + dz * dz;
+                        ss += d2;
+                        mx = fmax(mx, d2);
+                    }
+                }
+                ss = wsum_d(ss);
+                mx = wmax_d(mx);
+                const double rmsd = sqrt(ss / n_tot), maxdev = sqrt(mx);
+                const bool rm_ok = rmsd < a.rmsd_thr, md_ok = maxdev < 2.0 * a.rmsd_thr;
+                if (lane == 0) {
+                    const long long ref = g * n_ang + aj;
+                    if (fabs(rmsd - a.rmsd_thr) <= a.eps) push_tie3(a, pose, ref, rmsd, FC_TIE_RMSD, rm_ok);
+                    if (fabs(maxdev - 2.0 * a.rmsd_thr) <= a.eps) push_tie3(a, pose, ref, maxdev, FC_TIE_MAXDEV, md_ok);
+                }
+                similar = rm_ok && md_ok;
             }
-            ss = wsum_d(ss);
-            mx = wmax_d(mx);
-            const double rmsd = sqrt(ss / n_tot), maxdev = sqrt(mx);
-            const bool rm_ok = rmsd < a.rmsd_thr, md_ok = maxdev < 2.0 * a.rmsd_thr;
-            if (lane == 0) {
-                const long long ref = g * n_ang + aj;
-                if (fabs(rmsd - a.rmsd_thr) <= a.eps) push_tie3(a, pose, ref, rmsd, FC_TIE_RMSD, rm_ok);
-                if (fabs(maxdev - 2.0 * a.rmsd_thr) <= a.eps) push_tie3(a, pose, ref, maxdev, FC_TIE_MAXDEV, md_ok);
+            if (!similar) {
+                if (lane == 0) {
+                    s_acc[n_acc] = ai;
+                    a.keep[pose] = FC_STATUS_PASS;
+                }
+                ++n_acc;
+                __syncwarp();
             }
-            similar = rm_ok && md_ok;
         }
-        if (!similar) {
-            if (lane == 0) s_acc[n_acc] = ai;
-            ++n_acc;
-            __syncwarp();
-        }
-        if (lane == 0) a.keep[pose] = similar ? 0 : FC_STATUS_PASS;
     }
 }
 
@@ -484,6 +561,10 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
         for (int k = 0; k < p->n_ratoms0[m]; ++k)
             FC_REQUIRE(p->ratoms0[m][2 * k] >= 0 && p->ratoms0[m][2 * k] < p->n_atoms[m], "reactive atom index out of range");
     }
+    const bool trace = getenv("FC_CLASH_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    double t_enum = 0, t_dir = 0, t_clash = 0, t_sim = 0, t_host = 0, t_mat = 0;
     const int A = p->n_angles;
     const int64_t n_tot = (int64_t)p->n_atoms[0] + p->n_atoms[1] + p->n_atoms[2];
     const int n0 = p->n_conf[0], n1 = p->n_conf[1], n2 = p->n_conf[2];
@@ -589,6 +670,7 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
         }
     }
     const int64_t G = (int64_t)groups.size();
+    t_enum = now() - t0;
     fc_result* r = result_new();
     r->n_atoms = n_tot;
     r->n_pairs = 3;
@@ -618,6 +700,27 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
         }
     }
 
+    // distinct angles per molecule column (6 for the default grid): absolute transforms are tabulated per group
+    std::vector<double> uang_m[3];
+    std::vector<int> amap[3];
+    int u_max = 1;
+    for (int m = 0; m < 3; ++m) {
+        std::map<double, int> seen;
+        amap[m].resize(A);
+        for (int ai = 0; ai < A; ++ai) {
+            const double v = p->angles[3 * ai + m];
+            auto it = seen.find(v);
+            if (it == seen.end()) {
+                it = seen.emplace(v, (int)seen.size()).first;
+                uang_m[m].push_back(v);
+            }
+            amap[m][ai] = it->second;
+        }
+        u_max = std::max(u_max, (int)uang_m[m].size());
+    }
+    std::vector<double> uang((size_t)3 * u_max, 0.0);
+    for (int m = 0; m < 3; ++m) std::copy(uang_m[m].begin(), uang_m[m].end(), uang.begin() + (size_t)m * u_max);
+
     sm_count();
     cudaStream_t s;
     FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -629,7 +732,8 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
     {
         DevBuf<double> d_coords[3], d_pvec[3], d_pmean[3], d_pnorm[3], d_angles, d_ua[3], d_xf, d_out, d_near_dist, d_gap;
         DevBuf<long long> d_react[3], d_kept;
-        DevBuf<int> d_umap[3], d_choice, d_cnt;
+        DevBuf<int> d_umap[3], d_amap[3], d_choice, d_cnt;
+        DevBuf<double> d_uang, d_xf_abs;
         DevBuf<Cyc3Super> d_supers;
         DevBuf<Cyc3Group> d_groups;
         DevBuf<Cyc3Xf> d_gx;
@@ -663,6 +767,12 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
             CY(cudaMemcpyAsync(d_ua[k].p, ua[k].data(), ua[k].size() * 8, cudaMemcpyHostToDevice, s));
             CY(d_umap[k].alloc(A, s));
             CY(cudaMemcpyAsync(d_umap[k].p, umap[k].data(), (size_t)A * 4, cudaMemcpyHostToDevice, s));
+        }
+        CY(d_uang.alloc(uang.size(), s));
+        CY(cudaMemcpyAsync(d_uang.p, uang.data(), uang.size() * 8, cudaMemcpyHostToDevice, s));
+        for (int m = 0; m < 3; ++m) {
+            CY(d_amap[m].alloc(A, s));
+            CY(cudaMemcpyAsync(d_amap[m].p, amap[m].data(), (size_t)A * 4, cudaMemcpyHostToDevice, s));
         }
         CY(d_ties.alloc(tie_cap, s));
         CY(d_cnt.alloc(8, s));
@@ -720,8 +830,10 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
             d.angles = d_angles.p; d.n_angles = A;
             d.handed = p->rot_handedness >= 0 ? 1 : -1;
             d.gx = d_gx.p; d.choice = d_choice.p; d.gap = d_gap.p;
+            double tc = now();
             cyc3_directions_kernel<<<(unsigned)((cs.size() + 3) / 4), 128, 0, s>>>(d);
             e = cudaGetLastError();
+            if (trace) { cudaStreamSynchronize(s); t_dir += now() - tc; tc = now(); }
             if (e != cudaSuccess) { rc = cuda_fail(e, "cyc3_directions_kernel", __FILE__, __LINE__); break; }
 
             // ---- three block screens over (group, distinct angle pair) -------------------------
@@ -795,34 +907,54 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
                 }
             }
             if (rc) break;
+            if (trace) { cudaStreamSynchronize(s); t_clash += now() - tc; tc = now(); }
 
             // ---- combine + in-group similarity -------------------------------------------------
             Cyc3SimArgs a{};
             a.p = d;
             for (int k = 0; k < 3; ++k) { a.st[k] = d_st[k].p; a.umap[k] = d_umap[k].p; a.n_u[k] = n_u[k]; }
+            {
+                const long long n_abs = (long long)cg * 3 * u_max;
+                CY(d_xf_abs.alloc((size_t)n_abs * 12, s));
+                if (e != cudaSuccess) { rc = cuda_fail(e, "transform table", __FILE__, __LINE__); break; }
+                cyc3_abs_xf_kernel<<<(unsigned)((n_abs + 127) / 128), 128, 0, s>>>(d, d_uang.p, u_max, (int)uang_m[0].size(),
+                                                                                  (int)uang_m[1].size(), (int)uang_m[2].size(), d_xf_abs.p);
+            }
+            a.xf_abs = d_xf_abs.p;
+            for (int m = 0; m < 3; ++m) a.amap[m] = d_amap[m].p;
+            a.u_max = u_max;
             a.status = d_status.p; a.keep = d_keep.p;
             a.rmsd_thr = p->rmsd_thresh; a.eps = FC_NEAR_EPS;
             a.ties = d_ties.p; a.n_ties = d_cnt.p + 1; a.tie_cap = tie_cap;
             a.pose_base = g_lo * A;
+            CY(cudaMemsetAsync(d_cnt.p + 2, 0, 16, s));  // [2..5]: pass / recheck counters (2 x u64)
+            cyc3_combine_kernel<<<(unsigned)((cposes + 255) / 256), 256, 0, s>>>(a, cposes, (unsigned long long*)(d_cnt.p + 2));
             const int warps = 4;
             cyc3_group_similarity_kernel<<<(unsigned)((cg + warps - 1) / warps), warps * 32, (size_t)warps * A * sizeof(int), s>>>(a);
             e = cudaGetLastError();
-            h_status.resize((size_t)cposes);
-            h_keep.resize((size_t)cposes);
-            CY(cudaMemcpyAsync(h_status.data(), d_status.p, (size_t)cposes, cudaMemcpyDeviceToHost, s));
-            CY(cudaMemcpyAsync(h_keep.data(), d_keep.p, (size_t)cposes, cudaMemcpyDeviceToHost, s));
+            // kept poses: order-preserving compaction of the keep flags on the device
+            CY(d_kept.alloc((size_t)cposes, s));
+            if (e == cudaSuccess && compact_pass(d_keep.p, cposes, 0, d_kept.p, d_cnt.p, s) != FC_OK) { rc = FC_ERR_CUDA; break; }
+            if (want_status) {
+                h_status.resize((size_t)cposes);
+                CY(cudaMemcpyAsync(h_status.data(), d_status.p, (size_t)cposes, cudaMemcpyDeviceToHost, s));
+            }
             CY(cudaMemcpyAsync(r->group_choice.data() + g_lo, d_choice.p, (size_t)cg * 4, cudaMemcpyDeviceToHost, s));
             CY(cudaMemcpyAsync(r->group_gap.data() + g_lo, d_gap.p, (size_t)cg * 8, cudaMemcpyDeviceToHost, s));
-            int h_cnt[2] = {0, 0};
-            CY(cudaMemcpyAsync(h_cnt, d_cnt.p, 8, cudaMemcpyDeviceToHost, s));
+            int h_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            CY(cudaMemcpyAsync(h_cnt, d_cnt.p, 32, cudaMemcpyDeviceToHost, s));
             CY(cudaStreamSynchronize(s));
             if (e != cudaSuccess) { rc = cuda_fail(e, "similarity stage", __FILE__, __LINE__); break; }
-            std::vector<int64_t> ckept;
-            for (int64_t i = 0; i < cposes; ++i) {
-                const uint8_t st = h_status[(size_t)i];
-                r->n_clash_pass += st & FC_STATUS_PASS;
-                r->n_rechecked += (st & FC_STATUS_RECHECKED) ? 1 : 0;
-                if (h_keep[(size_t)i]) ckept.push_back(i);
+            if (trace) { t_sim += now() - tc; tc = now(); }
+            unsigned long long pc[2];
+            memcpy(pc, h_cnt + 2, 16);
+            r->n_clash_pass += (int64_t)pc[0];
+            r->n_rechecked += (int64_t)pc[1];
+            std::vector<int64_t> ckept((size_t)h_cnt[0]);
+            if (h_cnt[0] > 0) {
+                static_assert(sizeof(long long) == sizeof(int64_t), "index width");
+                e = cudaMemcpy(ckept.data(), d_kept.p, (size_t)h_cnt[0] * 8, cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess) { rc = cuda_fail(e, "kept readback", __FILE__, __LINE__); break; }
             }
             if (want_status) memcpy(r->status.data() + g_lo * A, h_status.data(), (size_t)cposes);
             {
@@ -839,14 +971,13 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
                     }
                 }
             }
+            if (trace) { t_host += now() - tc; tc = now(); }
             // ---- kept poses of this chunk ----------------------------------------------------------
             if (!ckept.empty()) {
                 const int n_kept = (int)ckept.size();
                 const size_t base = r->kept.size();
                 if (want_coords) {
-                    e = d_kept.alloc(n_kept, s);
-                    CY(d_out.alloc((size_t)n_kept * n_tot * 3, s));
-                    CY(cudaMemcpyAsync(d_kept.p, ckept.data(), (size_t)n_kept * 8, cudaMemcpyHostToDevice, s));
+                    e = d_out.alloc((size_t)n_kept * n_tot * 3, s);
                     if (e == cudaSuccess) {
                         cyc3_materialize_kernel<<<n_kept, 128, 0, s>>>(d, d_kept.p, n_kept, d_out.p);
                         e = cudaGetLastError();
@@ -864,6 +995,7 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
                     memcpy(&r->constrained[(base + k) * 6], hgroups[(size_t)gg].ids, 24);
                 }
             }
+            if (trace) { t_mat += now() - tc; }
             sg_lo = sg_hi;
         }
 #undef CY
@@ -874,6 +1006,9 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
         fc_result_free(r);
         return rc;
     }
+    if (trace)
+        fprintf(stderr, "fc_cyclical3_screen: total %.1f ms: enumerate %.1f, directions %.1f, block screens %.1f, similarity+D2H %.1f, "
+                "host scan %.1f, kept/materialise %.1f\n", now() - t0, t_enum, t_dir, t_clash, t_sim, t_host, t_mat);
     r->n_kept = (int64_t)r->kept.size();
     r->n_surv = r->n_clash_pass;
     *out = r;

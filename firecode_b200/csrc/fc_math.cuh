@@ -157,6 +157,41 @@ __host__ __device__ inline void jacobi_eig3(const double* a_in, double* w, doubl
     w[0] = a[0]; w[1] = a[4]; w[2] = a[8];
 }
 
+// Sum of the singular values of a 3x3 matrix H with the sign of the smallest set by det(H) -- the quantity the
+// Kabsch RMSD needs, msd = (|p|^2 + |q|^2 - 2 * sum) / n -- from the closed-form (trigonometric) eigenvalues of
+// H^T H.  About ten times cheaper than the Jacobi solve; used as a SCREEN only: callers fall back to
+// kabsch_from_cov when the value lands within a guard band of their threshold (the smallest singular value
+// carries an absolute error of about 3e-8 * sigma_1).
+__host__ __device__ inline double singular_sum3(const double* h) {
+    double k[6];  // upper triangle of H^T H: 00 01 02 11 12 22
+    k[0] = h[0] * h[0] + h[3] * h[3] + h[6] * h[6];
+    k[1] = h[0] * h[1] + h[3] * h[4] + h[6] * h[7];
+    k[2] = h[0] * h[2] + h[3] * h[5] + h[6] * h[8];
+    k[3] = h[1] * h[1] + h[4] * h[4] + h[7] * h[7];
+    k[4] = h[1] * h[2] + h[4] * h[5] + h[7] * h[8];
+    k[5] = h[2] * h[2] + h[5] * h[5] + h[8] * h[8];
+    double e1, e2, e3;
+    const double p1 = k[1] * k[1] + k[2] * k[2] + k[4] * k[4];
+    const double q = (k[0] + k[3] + k[5]) / 3.0;
+    const double b0 = k[0] - q, b3 = k[3] - q, b5 = k[5] - q;
+    const double p2 = b0 * b0 + b3 * b3 + b5 * b5 + 2.0 * p1;
+    if (p2 <= 0.0) {
+        e1 = e2 = e3 = q;
+    } else {
+        const double p = sqrt(p2 / 6.0), ip = 1.0 / p;
+        const double c0 = b0 * ip, c3 = b3 * ip, c5 = b5 * ip, c1 = k[1] * ip, c2 = k[2] * ip, c4 = k[4] * ip;
+        double r = 0.5 * (c0 * (c3 * c5 - c4 * c4) - c1 * (c1 * c5 - c4 * c2) + c2 * (c1 * c4 - c3 * c2));
+        r = fmin(1.0, fmax(-1.0, r));
+        const double phi = acos(r) / 3.0;
+        e1 = q + 2.0 * p * cos(phi);
+        e3 = q + 2.0 * p * cos(phi + 2.0943951023931954923);
+        e2 = 3.0 * q - e1 - e3;
+    }
+    const double det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) + h[2] * (h[3] * h[7] - h[4] * h[6]);
+    const double s3 = sqrt(fmax(e3, 0.0));
+    return sqrt(fmax(e1, 0.0)) + sqrt(fmax(e2, 0.0)) + (det < 0.0 ? -s3 : s3);
+}
+
 // Kabsch rotation for a 3x3 cross-covariance H (row-major): returns the proper rotation R = U D V^T
 // of the SVD H = U S V^T with D = diag(1, 1, det(U V^T)) -- what numpy's svd + sign fix yields in
 // firecode/algebra.py:42-49 (align_vec_pair, H = ref^T tgt) and prism_pruner.rmsd.get_alignment_
