@@ -201,17 +201,25 @@ __global__ void __launch_bounds__(128) cyc_group_similarity_kernel(CycSimArgs a)
             cyc_mol_xf(p, g, 1, aj, rq[1], tq[1]);
             // H = p^T q over all atoms, uncentred (rmsd_and_max(center=False))
             double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            double gsum = 0.0;  // |p|^2 + |q|^2
             for (int at = lane; at < n_tot; at += 32) {
                 double x[3], y[3];
                 cyc_atom(p, conf, rp, tp, at, x);
                 cyc_atom(p, conf, rq, tq, at, y);
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+                for (int r = 0; r < 3; ++r) {
+                    gsum += x[r] * x[r] + y[r] * y[r];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) h[3 * r + c] += x[r] * y[c];
+                }
             }
 #pragma unroll
             for (int e = 0; e < 9; ++e) h[e] = warp_sum_d(h[e]);
+            gsum = warp_sum_d(gsum);
+            {   // closed-form singular values: clearly dissimilar pairs skip the Jacobi solve and the second pass
+                const double lim = a.rmsd_thr + 1e-4;
+                if ((gsum - 2.0 * singular_sum3(h)) / n_tot > lim * lim) continue;
+            }
             M3 R = kabsch_from_cov(h, nullptr);
             double ss = 0.0, mx = 0.0;
             for (int at = lane; at < n_tot; at += 32) {

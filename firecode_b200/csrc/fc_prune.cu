@@ -210,6 +210,10 @@ __global__ void __launch_bounds__(256) prune_pairs_kernel(PruneArgs a) {
         for (int e = 0; e < 9; ++e) f2 += h[u][e] * h[u][e];
         const double thr2 = (a.max_rmsd + a.eps) * (a.max_rmsd + a.eps);
         if ((e0 - 2.0 * sqrt(3.0 * f2)) / nh >= thr2) continue;
+        {   // closed-form singular values: clearly dissimilar pairs never reach the Jacobi solve
+            const double lim = a.max_rmsd + 1e-4;
+            if ((e0 - 2.0 * singular_sum3(h[u])) / nh > lim * lim) continue;
+        }
         ++evals;
         double sig[3];
         M3 R = kabsch_from_cov(h[u], sig);
