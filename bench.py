@@ -459,6 +459,18 @@ def run_extras():
                                   "pairs_eigen_solved": rep.pairs_solved, "passes": rep.passes,
                                   "kept": int(mask.sum()), "n": len(mask), "seconds": dt,
                                   "conventions": {"keep": rep.keep, "pass_mode": rep.pass_mode}}
+    # C4 (BASELINE.json configs[3]) at full size: 200 000 conformers of a 120-atom molecule (2 000 basins)
+    rng = np.random.default_rng(synthetic.SEED + 4)
+    atoms, structures, _ = synthetic.pruning_ensemble(rng, 200000, 120, 2000)
+    dt, (kept, mask) = timed(lambda: pruner.prune_by_rmsd(structures, atoms, 0.5), reps=1)
+    rep = pruner.last_report
+    out["C4_rmsd_pruning_200k"] = {"rmsd_pairs_per_s": rep.pairs_tiled / dt, "pairs": rep.pairs_tiled,
+                                   "pairs_skipped_known_dissimilar": rep.pairs_skipped,
+                                   "pairs_eigen_solved": rep.pairs_solved, "passes": rep.passes,
+                                   "kept": int(mask.sum()), "n": len(mask), "seconds": dt,
+                                   "h2d_bytes": int(structures.nbytes),
+                                   "conventions": {"keep": rep.keep, "pass_mode": rep.pass_mode}}
+    del structures, kept, mask
     # C5: torsion scan, 1 000 conformers x 8 torsions x 36 steps of a 120-atom molecule
     rng = np.random.default_rng(synthetic.SEED + 5)
     atoms, coords, bonds, picks = synthetic.conformer_ensemble(rng, 1000, 120, n_torsions=8)

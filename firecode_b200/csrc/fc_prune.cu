@@ -15,6 +15,7 @@
 //   MOI flavour    <=>  all three principal moments within max_deviation (relative to structure i)
 // Keep rules: "greedy" updates the mask in place (NMS sweep), "snapshot" reads the mask of the pass
 // start; "first" keeps the earlier structure of a similar pair, "last" the later one.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -28,8 +29,10 @@ namespace fc {
 // per-structure preparation
 // ---------------------------------------------------------------------------------------------
 // heavy-atom coordinates centred on their mean: out (n, nh, 3); g[i] = sum |x|^2
+// outf: the same coordinates as float4 {x, y, z, 0} for the FP32 screen
 __global__ void prune_center_kernel(const double* __restrict__ coords, int n_atoms, const int* __restrict__ sel,
-                                    int nh, long long n, double* __restrict__ out, double* __restrict__ g) {
+                                    int nh, long long n, double* __restrict__ out, double* __restrict__ g,
+                                    float4* __restrict__ outf) {
     long long s = blockIdx.x;
     if (s >= n) return;
     const double* src = coords + (size_t)s * n_atoms * 3;
@@ -58,6 +61,7 @@ __global__ void prune_center_kernel(const double* __restrict__ coords, int n_ato
         const double* a = src + 3 * sel[k];
         double x = a[0] - mean[0], y = a[1] - mean[1], z = a[2] - mean[2];
         dst[3 * k] = x; dst[3 * k + 1] = y; dst[3 * k + 2] = z;
+        outf[(size_t)s * nh + k] = make_float4((float)x, (float)y, (float)z, 0.f);
         gg += x * x + y * y + z * z;
     }
     for (int o = 16; o > 0; o >>= 1) gg += __shfl_xor_sync(0xffffffffu, gg, o);
@@ -116,6 +120,10 @@ struct PruneArgs {
     int nh;
     int mode;                // 0 = rmsd, 1 = moi
     double max_rmsd, max_dev, max_dE, moi_dev, eps;
+    const float4* xcf;           // (n, nh) centred heavy-atom coordinates, FP32
+    int2* cand;                  // pairs the FP32 screen could not rule out (structure indices, x < y)
+    unsigned long long* n_cand;
+    long long cand_cap;
     int2* pairs;                 // similar pairs found in this pass (structure indices, x < y)
     unsigned long long* n_pairs; // ... their number (may exceed pair_cap: the pass is then repeated)
     long long pair_cap;
@@ -253,6 +261,170 @@ __global__ void __launch_bounds__(256) prune_pairs_kernel(PruneArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// FP32 screen + FP64 exact evaluation of the pairs it cannot rule out
+// ---------------------------------------------------------------------------------------------
+// closed-form singular-value sum in FP32 (see singular_sum3): good to a few 1e-3 A on the RMSD, which is all
+// the screen needs -- its guard band is kScreenBand
+__device__ __forceinline__ float singular_sum3f(const float* h) {
+    float k0 = h[0] * h[0] + h[3] * h[3] + h[6] * h[6], k1 = h[0] * h[1] + h[3] * h[4] + h[6] * h[7];
+    float k2 = h[0] * h[2] + h[3] * h[5] + h[6] * h[8], k3 = h[1] * h[1] + h[4] * h[4] + h[7] * h[7];
+    float k4 = h[1] * h[2] + h[4] * h[5] + h[7] * h[8], k5 = h[2] * h[2] + h[5] * h[5] + h[8] * h[8];
+    float e1, e2, e3;
+    const float p1 = k1 * k1 + k2 * k2 + k4 * k4;
+    const float q = (k0 + k3 + k5) * (1.0f / 3.0f);
+    const float b0 = k0 - q, b3 = k3 - q, b5 = k5 - q;
+    const float p2 = b0 * b0 + b3 * b3 + b5 * b5 + 2.0f * p1;
+    if (!(p2 > 0.f)) {
+        e1 = e2 = e3 = q;
+    } else {
+        const float p = sqrtf(p2 * (1.0f / 6.0f)), ip = 1.0f / p;
+        const float c0 = b0 * ip, c3 = b3 * ip, c5 = b5 * ip, c1 = k1 * ip, c2 = k2 * ip, c4 = k4 * ip;
+        float r = 0.5f * (c0 * (c3 * c5 - c4 * c4) - c1 * (c1 * c5 - c4 * c2) + c2 * (c1 * c4 - c3 * c2));
+        r = fminf(1.0f, fmaxf(-1.0f, r));
+        const float phi = acosf(r) * (1.0f / 3.0f);
+        e1 = q + 2.0f * p * cosf(phi);
+        e3 = q + 2.0f * p * cosf(phi + 2.0943951f);
+        e2 = 3.0f * q - e1 - e3;
+    }
+    const float det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) + h[2] * (h[3] * h[7] - h[4] * h[6]);
+    const float s3 = sqrtf(fmaxf(e3, 0.f));
+    return sqrtf(fmaxf(e1, 0.f)) + sqrtf(fmaxf(e2, 0.f)) + (det < 0.f ? -s3 : s3);
+}
+
+constexpr float kScreenBand = 0.05f;   // A: FP32 covariance + FP32 closed form are good to a few 1e-3 A
+#define PS_ATOMS 64                    // atoms staged per step
+
+// 128 threads per 32 x 32 pair tile: thread (tc, tr) owns rows 4 tr .. 4 tr + 3 and columns 2 tc, 2 tc + 1
+// (8 pairs, 72 FP32 accumulators); per atom 4 broadcast LDS.128 (rows) + 2 LDS.128 (columns) feed 72 FFMA.
+__global__ void __launch_bounds__(128) prune_screen_f32_kernel(PruneArgs a) {
+    const PruneTile t = a.tiles[blockIdx.x];
+    const int tc = threadIdx.x & 15, tr = threadIdx.x >> 4;
+    const int chunk_end = t.chunk_begin + t.chunk_len;
+    extern __shared__ float4 s_stage[];  // [PS_ATOMS][32] rows, then [PS_ATOMS][32] columns
+    float4* sR = s_stage;
+    float4* sC = s_stage + PS_ATOMS * PR_TS;
+    float h[8][9];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int e = 0; e < 9; ++e) h[u][e] = 0.f;
+    const int nh = a.nh;
+    for (int a0 = 0; a0 < nh; a0 += PS_ATOMS) {
+        const int na = min(PS_ATOMS, nh - a0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < PR_TS * na; e += 128) {
+            const int sidx = e / na, k = e - sidx * na;  // consecutive threads read consecutive atoms of a structure
+            const int rpos = t.row0 + sidx, cpos = t.col0 + sidx;
+            sR[k * PR_TS + sidx] = rpos < chunk_end ? a.xcf[(size_t)a.active[rpos] * nh + a0 + k] : make_float4(0.f, 0.f, 0.f, 0.f);
+            sC[k * PR_TS + sidx] = cpos < chunk_end ? a.xcf[(size_t)a.active[cpos] * nh + a0 + k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int k = 0; k < na; ++k) {
+            const float4 q0 = sC[k * PR_TS + 2 * tc], q1 = sC[k * PR_TS + 2 * tc + 1];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 pr = sR[k * PR_TS + 4 * tr + i];
+                float* h0 = h[2 * i];
+                float* h1 = h[2 * i + 1];
+                h0[0] = fmaf(pr.x, q0.x, h0[0]); h0[1] = fmaf(pr.x, q0.y, h0[1]); h0[2] = fmaf(pr.x, q0.z, h0[2]);
+                h0[3] = fmaf(pr.y, q0.x, h0[3]); h0[4] = fmaf(pr.y, q0.y, h0[4]); h0[5] = fmaf(pr.y, q0.z, h0[5]);
+                h0[6] = fmaf(pr.z, q0.x, h0[6]); h0[7] = fmaf(pr.z, q0.y, h0[7]); h0[8] = fmaf(pr.z, q0.z, h0[8]);
+                h1[0] = fmaf(pr.x, q1.x, h1[0]); h1[1] = fmaf(pr.x, q1.y, h1[1]); h1[2] = fmaf(pr.x, q1.z, h1[2]);
+                h1[3] = fmaf(pr.y, q1.x, h1[3]); h1[4] = fmaf(pr.y, q1.y, h1[4]); h1[5] = fmaf(pr.y, q1.z, h1[5]);
+                h1[6] = fmaf(pr.z, q1.x, h1[6]); h1[7] = fmaf(pr.z, q1.y, h1[7]); h1[8] = fmaf(pr.z, q1.z, h1[8]);
+            }
+        }
+    }
+    const float lim = (float)a.max_rmsd + kScreenBand;
+    const float thr2 = lim * lim;
+    const float inv_nh = 1.0f / (float)nh;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int row = t.row0 + 4 * tr + (u >> 1), col = t.col0 + 2 * tc + (u & 1);
+        if (!(row < chunk_end && col < chunk_end && row < col)) continue;  // each unordered pair once
+        const int s_row = a.active[row], s_col = a.active[col];
+        if (a.energies && !(fabs(a.energies[s_row] - a.energies[s_col]) < a.max_dE)) continue;
+        const float e0 = (float)(a.g[s_row] + a.g[s_col]);
+        // cheap bound first: sum of singular values <= sqrt(3) |H|_F
+        float f2 = 0.f;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) f2 = fmaf(h[u][e], h[u][e], f2);
+        if ((e0 - 2.0f * sqrtf(3.0f * f2)) * inv_nh >= thr2) continue;
+        if ((e0 - 2.0f * singular_sum3f(h[u])) * inv_nh > thr2) continue;
+        const unsigned long long slot = atomicAdd(a.n_cand, 1ull);
+        if ((long long)slot < a.cand_cap) a.cand[slot] = make_int2(s_row, s_col);
+    }
+}
+
+__device__ __forceinline__ double prune_wsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// one warp per candidate pair: the FP64 evaluation that restates rmsd_and_max (centred heavy atoms)
+__global__ void __launch_bounds__(256) prune_exact_kernel(PruneArgs a, long long n_cand) {
+    const int lane = threadIdx.x & 31;
+    const long long c = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n_cand) return;
+    const int2 pr = a.cand[c];
+    const int nh = a.nh;
+    const double* p = a.xc + (size_t)pr.x * nh * 3;
+    const double* q = a.xc + (size_t)pr.y * nh * 3;
+    double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = lane; k < nh; k += 32) {
+        const double px = p[3 * k], py = p[3 * k + 1], pz = p[3 * k + 2];
+        const double qx = q[3 * k], qy = q[3 * k + 1], qz = q[3 * k + 2];
+        h[0] += px * qx; h[1] += px * qy; h[2] += px * qz;
+        h[3] += py * qx; h[4] += py * qy; h[5] += py * qz;
+        h[6] += pz * qx; h[7] += pz * qy; h[8] += pz * qz;
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) h[e] = prune_wsum(h[e]);
+    const double e0 = a.g[pr.x] + a.g[pr.y];
+    const double thr2 = (a.max_rmsd + a.eps) * (a.max_rmsd + a.eps);
+    {
+        const double lim = a.max_rmsd + 1e-4;
+        if ((e0 - 2.0 * singular_sum3(h)) / nh > lim * lim) return;
+    }
+    if (lane == 0 && a.n_eval) atomicAdd(a.n_eval, 1ull);
+    double sig[3];
+    M3 R = kabsch_from_cov(h, sig);
+    double msd = (e0 - 2.0 * (sig[0] + sig[1] + sig[2])) / nh;
+    if (msd < 0) msd = 0;
+    if (msd >= thr2) return;
+    double ss = 0, mx = 0;
+    for (int k = lane; k < nh; k += 32) {
+        const double x = p[3 * k], y = p[3 * k + 1], z = p[3 * k + 2];
+        const double dx = (x * R.m[0] + y * R.m[3] + z * R.m[6]) - q[3 * k];
+        const double dy = (x * R.m[1] + y * R.m[4] + z * R.m[7]) - q[3 * k + 1];
+        const double dz = (x * R.m[2] + y * R.m[5] + z * R.m[8]) - q[3 * k + 2];
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        ss += d2;
+        mx = fmax(mx, d2);
+    }
+    ss = prune_wsum(ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane != 0) return;
+    const double rmsd = sqrt(ss / nh), maxdev = sqrt(mx);
+    const bool r_ok = rmsd < a.max_rmsd, m_ok = maxdev < a.max_dev;
+    if (a.ties) {
+        if (fabs(rmsd - a.max_rmsd) <= a.eps) {
+            int slot = atomicAdd(a.n_ties, 1);
+            if (slot < a.tie_cap) a.ties[slot] = TieRecord{pr.y, pr.x, rmsd, FC_TIE_RMSD, r_ok ? 1 : 0};
+        }
+        if (r_ok && fabs(maxdev - a.max_dev) <= a.eps) {
+            int slot = atomicAdd(a.n_ties, 1);
+            if (slot < a.tie_cap) a.ties[slot] = TieRecord{pr.y, pr.x, maxdev, FC_TIE_MAXDEV, m_ok ? 1 : 0};
+        }
+    }
+    if (r_ok && m_ok) prune_push_pair(a, pr.x, pr.y);
+}
+
 }  // namespace fc
 
 using namespace fc;
@@ -330,7 +502,8 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
     {
         DevBuf<double> d_coords, d_xc, d_g, d_moi, d_mass, d_energy;
         DevBuf<int> d_sel, d_active, d_nties;
-        DevBuf<int2> d_pairs;
+        DevBuf<int2> d_pairs, d_cand;
+        DevBuf<float4> d_xcf;
         DevBuf<PruneTile> d_tiles;
         DevBuf<unsigned long long> d_eval;
         DevBuf<TieRecord> d_ties;
@@ -341,7 +514,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
         PR(cudaMemcpyAsync(d_coords.p, structures, (size_t)n * n_atoms * 24, cudaMemcpyHostToDevice, s));
         PR(d_nties.alloc(4, s));
         PR(cudaMemsetAsync(d_nties.p, 0, 16, s));
-        PR(d_eval.alloc(4, s));  // [0] eigen-solves, [1] similar pairs of the current pass
+        PR(d_eval.alloc(4, s));  // [0] eigen-solves, [1] similar pairs, [2] screen candidates of the current pass
         PR(cudaMemsetAsync(d_eval.p, 0, 32, s));
         PR(d_ties.alloc(cap, s));
         if (energies) {
@@ -352,9 +525,10 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
             PR(d_sel.alloc(n_sel, s));
             PR(cudaMemcpyAsync(d_sel.p, sel, (size_t)n_sel * 4, cudaMemcpyHostToDevice, s));
             PR(d_xc.alloc((size_t)n * n_sel * 3, s));
+            PR(d_xcf.alloc((size_t)n * n_sel, s));
             PR(d_g.alloc((size_t)n, s));
             if (e == cudaSuccess) {
-                prune_center_kernel<<<(unsigned)n, 64, 0, s>>>(d_coords.p, n_atoms, d_sel.p, n_sel, n, d_xc.p, d_g.p);
+                prune_center_kernel<<<(unsigned)n, 64, 0, s>>>(d_coords.p, n_atoms, d_sel.p, n_sel, n, d_xc.p, d_g.p, d_xcf.p);
                 e = cudaGetLastError();
             }
         } else {
@@ -415,20 +589,48 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                 PR(cudaMemcpyAsync(d_active.p, active.data(), active.size() * 4, cudaMemcpyHostToDevice, s));
                 if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pass setup", __FILE__, __LINE__); break; }
                 long long pair_cap = std::max<long long>(1 << 20, 8 * (long long)active.size());
-                for (int attempt = 0; attempt < 2 && !rc; ++attempt) {
+                long long cand_cap = std::max<long long>(1 << 21, 16 * (long long)active.size());
+                const char* env64 = getenv("FC_PRUNE_FP64");
+                const bool two_stage = mode == 0 && !(env64 && atoi(env64));
+                bool counted = false;  // ties / eigen-solve statistics are recorded by one exact run only
+                for (int attempt = 0; attempt < 4 && !rc; ++attempt) {
                     if (d_pairs.n < (size_t)pair_cap) PR(d_pairs.alloc((size_t)pair_cap, s));
-                    PR(cudaMemsetAsync(d_eval.p + 1, 0, 8, s));
+                    if (two_stage && d_cand.n < (size_t)cand_cap) PR(d_cand.alloc((size_t)cand_cap, s));
+                    PR(cudaMemsetAsync(d_eval.p + 1, 0, 16, s));
                     if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pair list", __FILE__, __LINE__); break; }
                     PruneArgs a{};
-                    a.xc = d_xc.p; a.g = d_g.p; a.moi = d_moi.p; a.energies = energies ? d_energy.p : nullptr;
+                    a.xc = d_xc.p; a.xcf = d_xcf.p; a.g = d_g.p; a.moi = d_moi.p; a.energies = energies ? d_energy.p : nullptr;
                     a.active = d_active.p; a.tiles = d_tiles.p; a.nh = n_sel; a.mode = mode;
                     a.max_rmsd = max_rmsd; a.max_dev = max_dev; a.max_dE = max_dE; a.moi_dev = moi_dev; a.eps = FC_NEAR_EPS;
                     a.pairs = d_pairs.p; a.n_pairs = d_eval.p + 1; a.pair_cap = pair_cap;
-                    a.n_eval = attempt == 0 ? d_eval.p : nullptr;
-                    a.ties = (ties_out && attempt == 0) ? d_ties.p : nullptr; a.n_ties = d_nties.p; a.tie_cap = cap;
-                    prune_pairs_kernel<<<(unsigned)tiles.size(), 256, 0, s>>>(a);
-                    PR(cudaGetLastError());
+                    a.cand = d_cand.p; a.n_cand = d_eval.p + 2; a.cand_cap = cand_cap;
+                    a.n_eval = !counted ? d_eval.p : nullptr;
+                    a.ties = (ties_out && !counted) ? d_ties.p : nullptr; a.n_ties = d_nties.p; a.tie_cap = cap;
                     unsigned long long found = 0;
+                    if (two_stage) {
+                        // FP32 screen of every pair of the tiles -> candidates; FP64 exact evaluation of the candidates
+                        const size_t smem = (size_t)2 * PS_ATOMS * PR_TS * sizeof(float4);
+                        PR(cudaFuncSetAttribute(prune_screen_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        prune_screen_f32_kernel<<<(unsigned)tiles.size(), 128, smem, s>>>(a);
+                        PR(cudaGetLastError());
+                        unsigned long long n_cand = 0;
+                        PR(cudaMemcpyAsync(&n_cand, d_eval.p + 2, 8, cudaMemcpyDeviceToHost, s));
+                        PR(cudaStreamSynchronize(s));
+                        if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune screen", __FILE__, __LINE__); break; }
+                        if ((long long)n_cand > cand_cap) {  // list too small: repeat with the exact size
+                            cand_cap = (long long)n_cand;
+                            continue;
+                        }
+                        if (n_cand) {
+                            prune_exact_kernel<<<(unsigned)((n_cand + 7) / 8), 256, 0, s>>>(a, (long long)n_cand);
+                            PR(cudaGetLastError());
+                            counted = true;
+                        }
+                    } else {
+                        prune_pairs_kernel<<<(unsigned)tiles.size(), 256, 0, s>>>(a);
+                        PR(cudaGetLastError());
+                        counted = true;
+                    }
                     PR(cudaMemcpyAsync(&found, d_eval.p + 1, 8, cudaMemcpyDeviceToHost, s));
                     PR(cudaStreamSynchronize(s));
                     if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pass", __FILE__, __LINE__); break; }
