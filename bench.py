@@ -303,10 +303,13 @@ def run_cuda(args):
     for _ in range(2):
         clash.compenetration_check_batch(a, b, xf_np[: e2e_poses // 4], thresh=THRESH)
     barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    per_step = []
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
+        t1 = time.perf_counter()
         res = clash.compenetration_check_batch(a, b, xf_np, thresh=THRESH)
+        per_step.append((time.perf_counter() - t1) * 1e3)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if world > 1:
@@ -326,7 +329,8 @@ def run_cuda(args):
     e2e = {"value": world * e2e_poses / e2e_s, "unit": UNIT, "h2d_gbs_pinned_measured": h2d_gbs,
            "h2d_bound_poses_per_s": world * h2d_gbs * 1e9 / 96.0,
            "h2d_bytes_per_step": int(e2e_poses * 96 + (len(a) + len(b)) * 24),
-           "d2h_bytes_per_step": int(e2e_poses), "poses_per_step": e2e_poses,
+           "d2h_bytes_per_step": int(e2e_poses), "poses_per_step": e2e_poses, "steps": e2e_steps,
+           "ms_per_step_each": [round(x, 2) for x in per_step],
            "api": "firecode_b200.clash.compenetration_check_batch -> C-ABI fc_clash_batch (pinned host buffers)"}
 
     if rank != 0:
