@@ -228,3 +228,21 @@ def prune_sharded(structures, atoms, kind="rmsd", group=None, **kw):
     if world == 1:
         return fn(structures, atoms, **kw)
     return fn(structures, atoms, shard=(rank, world, lambda buf: all_gather_varlen(buf, group)), **kw)
+
+
+def torsion_scan_sharded(coords, torsions, masks, angles, group=None, scan=None, **kw):
+    """Torsion scan (rotate_dihedral + torsion_comp_check over conformer x torsion x angle) with the
+    conformers sharded over the ranks; the pass masks are all-gathered in rank order (= item order).
+    Returns the (n_conf, n_tors, n_angles) bool array on every rank."""
+    rank, world = world_info(group)
+    coords = np.asarray(coords, dtype=np.float64)
+    lo, hi = shard_bounds(len(coords), world, rank)
+    if scan is None:
+        from .torsion import torsion_scan
+
+        def scan(x):
+            return torsion_scan(x, torsions, masks, angles, want_coords=False, **kw)["passed"]
+    shape = (len(torsions), len(np.atleast_1d(angles)))
+    local = np.asarray(scan(coords[lo:hi]), dtype=bool).reshape((hi - lo,) + shape) if hi > lo else np.zeros((0,) + shape, bool)
+    flat = all_gather_varlen(local.reshape(-1).astype(np.uint8), group).astype(bool)  # rank order = conformer order
+    return flat.reshape((len(coords),) + shape)

@@ -221,43 +221,65 @@ def _pairings_ok(prob, couples):
 
 def cyclical_groups(prob: problem.CyclicalProblem):
     """Group table of the bimolecular cyclical embed in the reference's loop order
-    (embeds.py:596-641): conformer pairs (first index fastest) x pivot pairs x 2 orientations,
-    minus pivot pairs whose norms differ by more than max_norm_delta and arrangements that miss a
-    user pairing."""
-    from .utils import cartesian_product, polygonize
-
+    (embeds.py:596-641): conformer pairs (first index fastest) x pivot pairs (first index fastest) x
+    2 orientations, minus pivot pairs whose norms differ by more than max_norm_delta and arrangements
+    that miss a user pairing.  Vectorised over all groups (numpy); O(groups) memory."""
     assert prob.n_mols == 2
-    conf, pivot, mean, vecs, ids = [], [], [], [], []
     n_conf = [len(c) for c in prob.coords]
-    norms_cache = [[np.linalg.norm(pv, axis=1) if len(pv) else np.zeros(0) for pv in prob.pivot_vec[m]]
-                   for m in range(2)]
-    for c0, c1 in cartesian_product(np.arange(n_conf[0]), np.arange(n_conf[1])):
-        k0, k1 = len(prob.pivot_vec[0][c0]), len(prob.pivot_vec[1][c1])
-        if k0 == 0 or k1 == 0:
-            continue
-        for p0, p1 in cartesian_product(np.arange(k0), np.arange(k1)):
-            norms = np.array([norms_cache[0][c0][p0], norms_cache[1][c1][p1]])
-            if abs(norms[0] - norms[1]) > prob.max_norm_delta:
+    off, vec, mean, pid, norm = [], [], [], [], []
+    for m in range(2):
+        o, v = _csr(prob.pivot_vec[m], 3, np.float64)
+        _, mp = _csr(prob.pivot_mean[m], 3, np.float64)
+        _, ids = _csr(prob.pivot_ids[m], 2, np.int64)
+        off.append(o); vec.append(v); mean.append(mp); pid.append(ids)
+        # np.linalg.norm(axis=1): sqrt((x*x + y*y) + z*z)
+        norm.append(np.sqrt((v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2]))
+    # conformer pairs, first index fastest (cartesian_product of two ranges, quirk N1)
+    c0 = np.tile(np.arange(n_conf[0], dtype=np.int64), n_conf[1])
+    c1 = np.repeat(np.arange(n_conf[1], dtype=np.int64), n_conf[0])
+    k0 = (off[0][1:] - off[0][:-1])[c0]
+    k1 = (off[1][1:] - off[1][:-1])[c1]
+    per_pair = k0 * k1
+    total = int(per_pair.sum())
+    pair = np.repeat(np.arange(len(c0), dtype=np.int64), per_pair)
+    first = np.concatenate([[0], np.cumsum(per_pair)[:-1]])
+    q = np.arange(total, dtype=np.int64) - first[pair]
+    kk0 = np.maximum(k0[pair], 1)
+    p0, p1 = q % kk0, q // kk0                      # pivot pairs, first index fastest
+    r0, r1 = off[0][c0[pair]] + p0, off[1][c1[pair]] + p1
+    n0, n1 = norm[0][r0], norm[1][r1]
+    ok = ~(np.abs(n0 - n1) > prob.max_norm_delta)   # embeds.py:624
+    pair, r0, r1, n0, n1 = pair[ok], r0[ok], r1[ok], n0[ok], n1[ok]
+    g2 = len(pair)
+    # two orientations per surviving pivot pair, v fastest
+    rep = lambda x: np.repeat(x, 2, axis=0)  # noqa: E731
+    v = np.tile(np.array([0, 1]), g2)
+    pair, r0, r1, n0, n1 = rep(pair), rep(r0), rep(r1), rep(n0), rep(n1)
+    a0, a1 = pid[0][r0], pid[1][r1]                 # (G, 2) start / end cumnum
+    swap = v == 1                                   # swaps = [(0, 0), (0, 1)] (embeds.py:767)
+    b1 = np.where(swap[:, None], a1[:, ::-1], a1)
+    couples = np.stack([np.stack([a0[:, 0], b1[:, 0]], axis=1), np.stack([a0[:, 1], b1[:, 1]], axis=1)], axis=1)
+    if prob.pairings:
+        internal = [] if prob.internal_constraints_is_array else [tuple(x) for x in prob.internal_constraints]
+        keep = np.ones(len(v), dtype=bool)
+        for a, b in prob.pairings:
+            if (a, b) in internal:
                 continue
-            poly = polygonize(norms)
-            pid = [prob.pivot_ids[0][c0][p0], prob.pivot_ids[1][c1][p1]]
-            for v in range(2):
-                couples = _cyclical_couples(pid, v)
-                if not _pairings_ok(prob, couples):
-                    continue
-                conf.append((c0, c1))
-                pivot.append((prob.pivot_vec[0][c0][p0], prob.pivot_vec[1][c1][p1]))
-                mean.append((prob.pivot_mean[0][c0][p0], prob.pivot_mean[1][c1][p1]))
-                vecs.append(poly[v])
-                ids.append(couples)
-    g = len(conf)
+            keep &= ((couples[:, 0, 0] == a) & (couples[:, 0, 1] == b)) | ((couples[:, 1, 0] == a) & (couples[:, 1, 1] == b))
+        pair, r0, r1, n0, n1, v, couples = pair[keep], r0[keep], r1[keep], n0[keep], n1[keep], v[keep], couples[keep]
+    g = len(v)
+    # polygonize for two lengths (utils.py:262-271): centred collinear segments, orientation 1 flips segment 2
+    vecs = np.zeros((g, 2, 2, 3))
+    vecs[:, 0, 0, 0], vecs[:, 0, 1, 0] = -n0 / 2, n0 / 2
+    vecs[:, 1, 0, 0], vecs[:, 1, 1, 0] = -n1 / 2, n1 / 2
+    vecs[v == 1, 1] *= -1
     return {
-        "conf": np.ascontiguousarray(np.array(conf, dtype=np.int32).reshape(g, 2)),
-        "pivot": np.ascontiguousarray(np.array(pivot, dtype=np.float64).reshape(g, 2, 3)),
-        "mean": np.ascontiguousarray(np.array(mean, dtype=np.float64).reshape(g, 2, 3)),
-        "vecs": np.ascontiguousarray(np.array(vecs, dtype=np.float64).reshape(g, 2, 2, 3)),
+        "conf": np.ascontiguousarray(np.stack([c0[pair], c1[pair]], axis=1).astype(np.int32).reshape(g, 2)),
+        "pivot": np.ascontiguousarray(np.stack([vec[0][r0], vec[1][r1]], axis=1).reshape(g, 2, 3)),
+        "mean": np.ascontiguousarray(np.stack([mean[0][r0], mean[1][r1]], axis=1).reshape(g, 2, 3)),
+        "vecs": np.ascontiguousarray(vecs),
         "dirs": np.ascontiguousarray(np.tile(np.array([[0.0, 1.0, 0.0], [0.0, -1.0, 0.0]]), (g, 1, 1))),
-        "ids": np.ascontiguousarray(np.array(ids, dtype=np.int32).reshape(g, 2, 2)),
+        "ids": np.ascontiguousarray(couples.astype(np.int32).reshape(g, 2, 2)),
     }
 
 

@@ -85,6 +85,23 @@ def _worker(rank, world, port, q):
         poses3 = fdist.cyclical_embed_sharded(emb3, screen=screen3)
         assert np.array_equal(poses3, ref3["poses"]) and np.array_equal(emb3.b200_kept_indices, ref3["kept"])
         assert np.array_equal(emb3.constrained_indices, ref3["constrained"])
+
+        # 5) torsion scan sharded over conformers == single-process oracle
+        import networkx as nx
+
+        rng = np.random.default_rng(3)
+        atoms, cc, bonds, picks = synthetic.conformer_ensemble(rng, 5, 24, n_torsions=3)
+        g = nx.Graph(); g.add_nodes_from(range(24)); g.add_edges_from(bonds)
+        tors = []
+        for p_, ch in picks:
+            nb_p = [k for k in g.neighbors(p_) if k != ch]; nb_c = [k for k in g.neighbors(ch) if k != p_]
+            if nb_p and nb_c:
+                tors.append((nb_p[0], p_, ch, nb_c[0]))
+        tmasks = [oport.rotation_mask(g, t) for t in tors]
+        angs = np.arange(6) * 60.0
+        full = oport.torsion_scan(cc, tors, tmasks, angs)[1]
+        got = fdist.torsion_scan_sharded(cc, tors, tmasks, angs, scan=lambda x: oport.torsion_scan(x, tors, tmasks, angs)[1])
+        assert np.array_equal(got, full)
         q.put((rank, "ok"))
     except Exception as exc:  # pragma: no cover
         import traceback

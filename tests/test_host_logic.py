@@ -94,3 +94,30 @@ def test_synthetic_generators_are_seeded():
     assert np.array_equal(a, b) and abs(a.reshape(-1, 3).mean(axis=0)).max() < 1e-9
     xf = synthetic.sweep_poses(np.random.default_rng(1), a[0], a[1], 10)
     assert np.array_equal(xf, xf.astype(np.float32).astype(np.float64))
+
+
+def test_vectorised_bimolecular_group_table_equals_loop_restatement():
+    """embeds.cyclical_groups (numpy, all groups at once) against the loop restatement of
+    embeds.py:596-641 in oracle.port, with and without a user pairing."""
+    from firecode_b200 import embeds, problem
+    from firecode_b200.utils import polygonize
+    from oracle import port
+    from synth_embedder import make_embedder
+
+    for kw in (dict(n_conf=3, n_atoms=24, seed=11, n_reactive=2, n_orb=2),
+               dict(n_conf=[4, 2], n_atoms=20, seed=13, n_reactive=1, n_orb=2)):
+        emb = make_embedder("cyclical", **kw)
+        prob = problem.cyclical_problem(emb)
+        first = [tuple(int(x) for x in port.cyclical_groups_bimol(prob)[1]["ids"][0])]
+        for pairings in ([], first):
+            prob.pairings = pairings
+            table = embeds.cyclical_groups(prob)
+            ref = port.cyclical_groups_bimol(prob)
+            assert len(ref) == len(table["conf"]) > 0
+            for i, r in enumerate(ref):
+                assert tuple(table["conf"][i]) == r["conf"]
+                assert [tuple(x) for x in table["ids"][i]] == [tuple(x) for x in r["ids"]]
+                assert np.array_equal(table["vecs"][i], polygonize(r["norms"])[r["v"]])
+                for m in range(2):
+                    assert np.array_equal(table["pivot"][i][m], prob.pivot_vec[m][r["conf"][m]][r["piv"][m]])
+                    assert np.array_equal(table["mean"][i][m], prob.pivot_mean[m][r["conf"][m]][r["piv"][m]])
