@@ -215,3 +215,41 @@ def test_cell_list_path_with_conformer_tiles(gpu, monkeypatch):
     assert np.array_equal(res["0"].status & 1, res["1"].status & 1)
     ref_mask, _, closest = port.clash_batch(ca, cb, xf, thresh=1.4, conf_a=conf_a, conf_b=conf_b)
     assert np.array_equal(res["1"].mask[closest > 1e-6], ref_mask[closest > 1e-6])
+
+
+def test_cell_list_path_edge_geometries(gpu, monkeypatch):
+    """Cell-list path corner cases: many conformers of A (32^3 grids), a fragment B larger than one flag
+    block, a fragment A too large for byte indices (falls back to all pairs), very small / large thresholds."""
+    from firecode_b200 import synthetic
+
+    rng = np.random.default_rng(123)
+    monkeypatch.setenv("FC_CLASH_MODE", "1")
+    # 130 conformers of A -> the 64^3 grids would exceed the budget -> 32^3
+    _, ca, _, _ = synthetic.conformer_ensemble(rng, 130, 20, n_torsions=3)
+    _, b, _, _ = synthetic.molecule_cloud(rng, 70)
+    xf = synthetic.sweep_poses(rng, ca[0], b, 5200)
+    conf_a = np.sort(rng.integers(0, 130, size=5200))
+    res = compenetration_check_batch(ca, b, xf, thresh=1.5, conf_a=conf_a)
+    ref_mask, _, closest = port.clash_batch(ca, b, xf, thresh=1.5, conf_a=conf_a)
+    assert np.array_equal(res.mask[closest > 1e-6], ref_mask[closest > 1e-6])
+    # B with 300 atoms (ten flag blocks), A with 300 atoms (all-pairs fallback: indices do not fit a byte)
+    _, a300, _, _ = synthetic.molecule_cloud(rng, 300)
+    _, b300, _, _ = synthetic.molecule_cloud(rng, 300)
+    _, a40, _, _ = synthetic.molecule_cloud(rng, 40)
+    for fa, fb in ((a40, b300), (a300, a40)):
+        xf = synthetic.sweep_poses(rng, fa, fb, 3000)
+        res = compenetration_check_batch(fa, fb, xf, thresh=1.5)
+        ref_mask, _, closest = port.clash_batch(fa, fb, xf, thresh=1.5, chunk=256)
+        assert np.array_equal(res.mask[closest > 1e-6], ref_mask[closest > 1e-6])
+    # thresholds far from the usual 1.5 A
+    xf = synthetic.sweep_poses(rng, a40, b, 4000)
+    for thr in (0.05, 0.7, 4.0, 9.0):
+        res = compenetration_check_batch(a40, b, xf, thresh=thr)
+        ref_mask, _, closest = port.clash_batch(a40, b, xf, thresh=thr)
+        assert np.array_equal(res.mask[closest > 1e-6], ref_mask[closest > 1e-6]), thr
+    # poses far away from A (everything outside the grid) and exactly on top of it
+    far = xf.copy()
+    far[:, 9:] += 500.0
+    assert compenetration_check_batch(a40, b, far, thresh=1.5).mask.all()
+    on_top = np.tile(np.array([[1.0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]]), (64, 1))
+    assert not compenetration_check_batch(a40, a40, on_top, thresh=1.5).mask.any()
