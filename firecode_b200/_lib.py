@@ -115,6 +115,10 @@ SIGNATURES = {
     "fc_clash_screen_dev": (C.c_int, [VP, C.c_int, C.c_int, VP, C.c_int, C.c_int, VP, C.c_int64, VP,
                                       C.c_int64, C.c_double, C.c_int, C.c_int, VP, VP, VP, VP, VP,
                                       C.c_int64, C.c_int64, VP]),
+    "fc_clash_prepare_dev": (C.c_int, [VP, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(VP), VP]),
+    "fc_clash_screen_prepared_dev": (C.c_int, [VP, VP, VP, C.c_int, C.c_int, VP, C.c_int64, VP, C.c_int64, C.c_int,
+                                               C.c_int, VP, VP, VP, VP, VP, C.c_int64, C.c_int64, VP]),
+    "fc_clash_prep_free": (None, [VP, VP]),
     "fc_clash_batch": (C.c_int, [VP, C.c_int, C.c_int, VP, C.c_int, C.c_int, VP, C.c_int64, VP,
                                  C.c_int64, C.c_double, C.c_int, C.c_int, VP, VP, VP, VP, VP,
                                  C.c_int64]),

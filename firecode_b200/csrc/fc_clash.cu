@@ -814,14 +814,96 @@ extern "C" int fc_clash_tile_poses(int n_b) {
     return g.poses;
 }
 
-extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a,
-                                   const double* b_coords, int n_conf_b, int n_b, const double* xf,
-                                   int64_t n_poses, const int32_t* tiles, int64_t n_tiles,
-                                   double thresh, int max_clashes, int strict, uint8_t* status,
-                                   float* min_dist, int32_t* near_count, int64_t* near_idx,
-                                   double* near_dist, int64_t near_cap, int64_t pose_index_base,
-                                   void* stream) {
-    FC_REQUIRE(n_a > 0 && n_b > 0 && n_conf_a > 0 && n_conf_b > 0, "fc_clash_screen_dev: empty fragment");
+// A-side tables of a screen, reusable across calls that share fragment A and the threshold
+struct fc_clash_prep {
+    int n_conf_a = 0, n_a = 0, n_a_pad = 0, cell_g = 0;
+    double thresh = 0.0;
+    unsigned char* buf = nullptr;  // stream-ordered allocation holding everything below
+    const float4* a_tab = nullptr;  // Gram-form atom pairs (all-pairs kernel)
+    const float* a_rad = nullptr;
+    const float4* a_xyz = nullptr;  // cell-list tables (cell_g > 0)
+    const CellMeta* meta = nullptr;
+    const uint4* grid = nullptr;
+    const unsigned* occ = nullptr;
+};
+
+extern "C" int fc_clash_prepare_dev(const double* a_coords, int n_conf_a, int n_a, double thresh, int want_cells,
+                                    fc_clash_prep** out, void* stream) {
+    FC_REQUIRE(out, "fc_clash_prepare_dev: null output");
+    *out = nullptr;
+    FC_REQUIRE(a_coords && n_conf_a > 0 && n_a > 0, "fc_clash_prepare_dev: empty fragment");
+    cudaStream_t s = (cudaStream_t)stream;
+    sm_count();
+    fc_clash_prep* p = new fc_clash_prep();
+    p->n_conf_a = n_conf_a;
+    p->n_a = n_a;
+    p->n_a_pad = (n_a + 1) / 2 * 2;
+    p->thresh = thresh;
+    if (want_cells && n_a <= 254 && thresh > 0.0 && thresh < 1e3) {
+        const size_t budget = (size_t)512 << 20;
+        for (int g_try : {64, 32}) {  // powers of two: the flag phase range-checks with one mask
+            if ((size_t)n_conf_a * g_try * g_try * g_try * 16 <= budget) {
+                p->cell_g = g_try;
+                break;
+            }
+        }
+    }
+    const int cell_g = p->cell_g;
+    const size_t n_cells = (size_t)cell_g * cell_g * cell_g;
+    size_t off_a = 0;
+    size_t off_ra = off_a + (size_t)n_conf_a * p->n_a_pad * 16;
+    size_t off_axyz = (off_ra + (size_t)n_conf_a * 4 + 15) / 16 * 16;
+    size_t off_meta = off_axyz + (cell_g ? (size_t)n_conf_a * n_a * 16 : 0);
+    size_t off_grid = off_meta + (cell_g ? 64 : 0);
+    size_t off_occ = off_grid + (cell_g ? (size_t)n_conf_a * n_cells * 16 : 0);
+    size_t total = off_occ + (cell_g ? (size_t)n_conf_a * (n_cells / 32 + 1) * 4 : 0);
+    cudaError_t e = cudaMallocAsync((void**)&p->buf, total, s);
+    if (e != cudaSuccess) {
+        delete p;
+        return cuda_fail(e, "fc_clash_prepare_dev: cudaMallocAsync", __FILE__, __LINE__);
+    }
+    clash_prep_kernel<<<n_conf_a, 128, 0, s>>>(a_coords, n_conf_a, n_a, p->n_a_pad, 1, (float4*)(p->buf + off_a),
+                                               (float*)(p->buf + off_ra));
+    p->a_tab = (const float4*)(p->buf + off_a);
+    p->a_rad = (const float*)(p->buf + off_ra);
+    if (cell_g) {
+        CellMeta* meta = (CellMeta*)(p->buf + off_meta);
+        float4* a_xyz = (float4*)(p->buf + off_axyz);
+        uint4* grid_tab = (uint4*)(p->buf + off_grid);
+        unsigned* occ = (unsigned*)(p->buf + off_occ);
+        clash_bbox_kernel<<<1, 256, 0, s>>>(a_coords, (long long)n_conf_a * n_a, (float)thresh, cell_g, meta);
+        dim3 gg((unsigned)((n_cells + 127) / 128), (unsigned)n_conf_a);
+        clash_grid_kernel<<<gg, 128, (size_t)n_a * 24, s>>>(a_coords, n_a, meta, a_xyz, grid_tab, occ);
+        p->a_xyz = a_xyz;
+        p->meta = meta;
+        p->grid = grid_tab;
+        p->occ = occ;
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cudaFreeAsync(p->buf, s);
+        delete p;
+        return cuda_fail(e, "fc_clash_prepare_dev kernels", __FILE__, __LINE__);
+    }
+    *out = p;
+    return FC_OK;
+}
+
+extern "C" void fc_clash_prep_free(fc_clash_prep* p, void* stream) {
+    if (!p) return;
+    if (p->buf) cudaFreeAsync(p->buf, (cudaStream_t)stream);
+    delete p;
+}
+
+extern "C" int fc_clash_screen_prepared_dev(const fc_clash_prep* prep, const double* a_coords, const double* b_coords,
+                                            int n_conf_b, int n_b, const double* xf, int64_t n_poses,
+                                            const int32_t* tiles, int64_t n_tiles, int max_clashes, int strict,
+                                            uint8_t* status, float* min_dist, int32_t* near_count, int64_t* near_idx,
+                                            double* near_dist, int64_t near_cap, int64_t pose_index_base, void* stream) {
+    FC_REQUIRE(prep, "fc_clash_screen_prepared_dev: null preparation");
+    const int n_conf_a = prep->n_conf_a, n_a = prep->n_a;
+    const double thresh = prep->thresh;
+    FC_REQUIRE(n_b > 0 && n_conf_b > 0, "fc_clash_screen_dev: empty fragment");
     FC_REQUIRE(n_poses >= 0 && max_clashes >= 0, "fc_clash_screen_dev: negative size");
     if (n_poses == 0) return FC_OK;
     FC_REQUIRE(a_coords && b_coords && xf && status, "fc_clash_screen_dev: null pointer");
@@ -829,7 +911,7 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     const int sms = sm_count();  // also configures the stream-ordered memory pool on first use
     ClashGeom g = choose_geom(n_b);
     FC_REQUIRE(g.tb > 0, "fc_clash_screen_dev: fragment B too large (%d atoms)", n_b);
-    const int n_a_pad = (n_a + 1) / 2 * 2;
+    const int n_a_pad = prep->n_a_pad;
     const int n_b_pad = g.chunks * g.tb;
     if (!tiles) n_tiles = (n_poses + g.poses - 1) / g.poses;
     FC_REQUIRE(n_tiles > 0, "fc_clash_screen_dev: empty tile list");
@@ -843,42 +925,26 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
         // FC_CLASH_MODE: 0 = all pairs, 1 = cell lists whenever possible, unset = automatic
         const char* v = getenv("FC_CLASH_MODE");
         const int mode = (v && *v) ? (atoi(v) ? 1 : 0) : 2;
-        const bool possible = !min_dist && n_a <= 254 && thresh > 0.0 && thresh < 1e3;
+        const bool possible = !min_dist && prep->cell_g > 0;
         const bool wanted = mode == 1 || (mode == 2 && n_poses >= 16384);
-        if (possible && wanted) {
-            const size_t budget = (size_t)512 << 20;
-            for (int g_try : {64, 32}) {  // powers of two: the flag phase range-checks with one mask
-                if ((size_t)n_conf_a * g_try * g_try * g_try * 16 <= budget) {
-                    cell_g = g_try;
-                    break;
-                }
-            }
-        }
+        if (possible && wanted) cell_g = prep->cell_g;
     }
-    const size_t n_cells = (size_t)cell_g * cell_g * cell_g;
 
-    // stream-ordered scratch
-    size_t a_bytes = (size_t)n_conf_a * n_a_pad * 16, b_bytes = (size_t)n_conf_b * n_b_pad * 16;
-    size_t off_a = 0, off_b = off_a + a_bytes, off_ra = off_b + b_bytes;
-    size_t off_rb = off_ra + (size_t)n_conf_a * 4, off_cnt = (off_rb + (size_t)n_conf_b * 4 + 15) / 16 * 16;
+    // stream-ordered scratch: B tables, undecided-pose list
+    size_t b_bytes = (size_t)n_conf_b * n_b_pad * 16;
+    size_t off_b = 0, off_rb = off_b + b_bytes, off_cnt = (off_rb + (size_t)n_conf_b * 4 + 15) / 16 * 16;
     size_t off_list = off_cnt + 16;
-    size_t off_axyz = (off_list + (size_t)n_poses * sizeof(UncEntry) + 15) / 16 * 16;
-    size_t off_meta = off_axyz + (cell_g ? (size_t)n_conf_a * n_a * 16 : 0);
-    size_t off_grid = off_meta + (cell_g ? 64 : 0);
-    size_t off_occ = off_grid + (cell_g ? (size_t)n_conf_a * n_cells * 16 : 0);
-    size_t total = off_occ + (cell_g ? (size_t)n_conf_a * (n_cells / 32 + 1) * 4 : 0);
+    size_t total = off_list + (size_t)n_poses * sizeof(UncEntry);
     unsigned char* scratch = nullptr;
     FC_CUDA(cudaMallocAsync((void**)&scratch, total, s));
 
-    clash_prep_kernel<<<n_conf_a, 128, 0, s>>>(a_coords, n_conf_a, n_a, n_a_pad, 1,
-                                               (float4*)(scratch + off_a), (float*)(scratch + off_ra));
     clash_prep_kernel<<<n_conf_b, 128, 0, s>>>(b_coords, n_conf_b, n_b, n_b_pad, 0,
                                                (float4*)(scratch + off_b), (float*)(scratch + off_rb));
     FC_CUDA(cudaMemsetAsync(scratch + off_cnt, 0, 16, s));
 
     ClashArgs a;
-    a.a_tab = (const float4*)(scratch + off_a);
-    a.a_rad = (const float*)(scratch + off_ra);
+    a.a_tab = prep->a_tab;
+    a.a_rad = prep->a_rad;
     a.b_tab = (const float4*)(scratch + off_b);
     a.b_rad = (const float*)(scratch + off_rb);
     a.xf = xf;
@@ -901,21 +967,14 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     a.unc_list = (UncEntry*)(scratch + off_list);
 
     if (cell_g) {
-        CellMeta* meta = (CellMeta*)(scratch + off_meta);
-        float4* a_xyz = (float4*)(scratch + off_axyz);
-        uint4* grid_tab = (uint4*)(scratch + off_grid);
-        clash_bbox_kernel<<<1, 256, 0, s>>>(a_coords, (long long)n_conf_a * n_a, (float)thresh, cell_g, meta);
-        dim3 gg((unsigned)((n_cells + 127) / 128), (unsigned)n_conf_a);
-        unsigned* occ = (unsigned*)(scratch + off_occ);
-        clash_grid_kernel<<<gg, 128, (size_t)n_a * 24, s>>>(a_coords, n_a, meta, a_xyz, grid_tab, occ);
         CellArgs c;
-        c.a_xyz = a_xyz;
+        c.a_xyz = prep->a_xyz;
         c.a_rad = a.a_rad;
         c.b_tab = a.b_tab;
         c.b_rad = a.b_rad;
-        c.grid = grid_tab;
-        c.occ = occ;
-        c.meta = meta;
+        c.grid = prep->grid;
+        c.occ = prep->occ;
+        c.meta = prep->meta;
         c.xf = xf;
         c.tiles = (const int4*)tiles;
         c.n_tiles = n_tiles;
@@ -987,4 +1046,28 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     if (e != cudaSuccess) return cuda_fail(e, "clash_recheck_f64_kernel launch", __FILE__, __LINE__);
     if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFreeAsync", __FILE__, __LINE__);
     return FC_OK;
+}
+
+extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a,
+                                   const double* b_coords, int n_conf_b, int n_b, const double* xf,
+                                   int64_t n_poses, const int32_t* tiles, int64_t n_tiles,
+                                   double thresh, int max_clashes, int strict, uint8_t* status,
+                                   float* min_dist, int32_t* near_count, int64_t* near_idx,
+                                   double* near_dist, int64_t near_cap, int64_t pose_index_base,
+                                   void* stream) {
+    FC_REQUIRE(n_a > 0 && n_b > 0 && n_conf_a > 0 && n_conf_b > 0, "fc_clash_screen_dev: empty fragment");
+    FC_REQUIRE(n_poses >= 0 && max_clashes >= 0, "fc_clash_screen_dev: negative size");
+    if (n_poses == 0) return FC_OK;
+    FC_REQUIRE(a_coords && b_coords && xf && status, "fc_clash_screen_dev: null pointer");
+    fc_clash_prep* prep = nullptr;
+    const char* v = getenv("FC_CLASH_MODE");
+    const int mode = (v && *v) ? (atoi(v) ? 1 : 0) : 2;
+    const int want_cells = !min_dist && (mode == 1 || (mode == 2 && n_poses >= 16384));
+    int rc = fc_clash_prepare_dev(a_coords, n_conf_a, n_a, thresh, want_cells, &prep, stream);
+    if (rc) return rc;
+    rc = fc_clash_screen_prepared_dev(prep, a_coords, b_coords, n_conf_b, n_b, xf, n_poses, tiles, n_tiles, max_clashes,
+                                      strict, status, min_dist, near_count, near_idx, near_dist, near_cap,
+                                      pose_index_base, stream);
+    fc_clash_prep_free(prep, stream);
+    return rc;
 }

@@ -23,7 +23,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <functional>
 #include <map>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -589,85 +591,116 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
         }
     }
 
-    // ---- enumerate super-groups and groups -----------------------------------------------------
+    // ---- enumerate super-groups and groups (host threads over contiguous conformer-triple ranges; the
+    //      concatenation in range order is the reference's loop order) ------------------------------------
+    struct EnumPart {
+        std::vector<Cyc3Super> supers;
+        std::vector<Cyc3Group> groups;
+        std::vector<HostGroup> hgroups;
+        bool bad = false;
+    };
+    static const int swaps[8][3] = {{0, 0, 0}, {0, 0, 1}, {0, 1, 0}, {0, 1, 1}, {1, 0, 0}, {1, 1, 0}, {1, 0, 1}, {1, 1, 1}};
+    auto enumerate = [&](int64_t ta, int64_t tb, EnumPart& L) {
+        for (int64_t t = ta; t < tb; ++t) {
+            // cartesian_product of three ranges: third fastest, first middle, second outermost
+            const int c2 = (int)(t % n2), c0 = (int)((t / n2) % n0), c1 = (int)(t / ((int64_t)n2 * n0));
+            const int conf[3] = {c0, c1, c2};
+            int64_t lo[3], cnt[3];
+            for (int m = 0; m < 3; ++m) {
+                lo[m] = p->pivot_offsets[m][conf[m]];
+                cnt[m] = p->pivot_offsets[m][conf[m] + 1] - lo[m];
+            }
+            if (cnt[0] <= 0 || cnt[1] <= 0 || cnt[2] <= 0) continue;
+            const int64_t n_pt = cnt[0] * cnt[1] * cnt[2];
+            for (int64_t q = 0; q < n_pt; ++q) {
+                const int64_t q2 = q % cnt[2], q0 = (q / cnt[2]) % cnt[0], q1 = q / (cnt[2] * cnt[0]);
+                const int64_t row[3] = {lo[0] + q0, lo[1] + q1, lo[2] + q2};
+                const double nn[3] = {pnorm[0][(size_t)row[0]], pnorm[1][(size_t)row[1]], pnorm[2][(size_t)row[2]]};
+                // embeds.py:447: all(norms[i] < norms[i-1] + norms[i-2] for i in (0, 1, 2))
+                if (!(nn[0] < nn[2] + nn[1] && nn[1] < nn[0] + nn[2] && nn[2] < nn[1] + nn[0])) continue;
+                Cyc3Super sg;
+                for (int m = 0; m < 3; ++m) { sg.conf[m] = conf[m]; sg.piv[m] = (int)row[m]; }
+                sg.first_group = (int)L.groups.size();
+                sg.active = 0;
+                for (int v = 0; v < 8; ++v) {
+                    int64_t o[3][2];
+                    for (int m = 0; m < 3; ++m) {
+                        const int64_t* id = p->pivot_ids[m] + 2 * row[m];
+                        o[m][0] = swaps[v][m] ? id[1] : id[0];
+                        o[m][1] = swaps[v][m] ? id[0] : id[1];
+                    }
+                    int64_t cp[3][2] = {{o[0][1], o[1][0]}, {o[1][1], o[2][0]}, {o[2][1], o[0][0]}};
+                    for (int k = 0; k < 3; ++k)
+                        if (cp[k][0] > cp[k][1]) std::swap(cp[k][0], cp[k][1]);
+                    bool ok = true;
+                    for (int i = 0; i < p->n_pairings && ok; ++i) {
+                        const int64_t a = p->pairings[2 * i], b = p->pairings[2 * i + 1];
+                        bool in_ids = false;
+                        for (int k = 0; k < 3; ++k) in_ids = in_ids || (cp[k][0] == a && cp[k][1] == b);
+                        ok = in_ids || pair_in(p->internal, p->n_internal, a, b);
+                    }
+                    if (!ok) continue;
+                    sg.active |= 1 << v;
+                    Cyc3Group gr;
+                    gr.super = (int)L.supers.size();
+                    gr.v = v;
+                    // facing table r[m][partner] (embeds.py:328-353)
+                    int pr[3][2][2];  // [couple][end] -> (mol, index)
+                    for (int k = 0; k < 3; ++k)
+                        for (int e = 0; e < 2; ++e) {
+                            pr[k][e][0] = -1; pr[k][e][1] = -1;
+                            for (int m = 0; m < 3; ++m)
+                                for (int j = 0; j < p->n_ratoms0[m]; ++j)
+                                    if (p->ratoms0[m][2 * j + 1] == cp[k][e]) { pr[k][e][0] = m; pr[k][e][1] = (int)p->ratoms0[m][2 * j]; }
+                        }
+                    int rt[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+                    for (int k = 0; k < 3; ++k) {
+                        // python negative indices wrap: -1 -> 2
+                        int m0 = pr[k][0][0] < 0 ? 2 : pr[k][0][0], m1 = pr[k][1][0] < 0 ? 2 : pr[k][1][0];
+                        rt[m0][m1] = pr[k][0][1];
+                        rt[m1][m0] = pr[k][1][1];
+                    }
+                    const int rr[6] = {rt[0][1], rt[0][2], rt[1][0], rt[1][2], rt[2][0], rt[2][1]};
+                    for (int k = 0; k < 6; ++k) {
+                        int mol = k / 2;
+                        // an unmatched couple leaves -1 (python: coords[0][-1] = last atom)
+                        gr.r[k] = rr[k] < 0 ? p->n_atoms[mol] + rr[k] : rr[k];
+                        if (!(gr.r[k] >= 0 && gr.r[k] < p->n_atoms[mol])) { L.bad = true; return; }
+                    }
+                    L.groups.push_back(gr);
+                    HostGroup hg;
+                    for (int k = 0; k < 3; ++k) { hg.ids[2 * k] = (int)cp[k][0]; hg.ids[2 * k + 1] = (int)cp[k][1]; }
+                    L.hgroups.push_back(hg);
+                }
+                if (sg.active) L.supers.push_back(sg);
+                if (L.groups.size() >= ((size_t)1 << 30)) { L.bad = true; return; }
+            }
+        }
+    };
+    const int64_t span = t_hi - t_lo;
+    int n_threads = (int)std::min<int64_t>(std::max(1u, std::min(8u, std::thread::hardware_concurrency())), std::max<int64_t>(1, span / 512));
+    std::vector<EnumPart> parts((size_t)n_threads);
+    {
+        std::vector<std::thread> workers;
+        for (int w = 0; w < n_threads; ++w) {
+            const int64_t ta = t_lo + span * w / n_threads, tb = t_lo + span * (w + 1) / n_threads;
+            if (w + 1 == n_threads) enumerate(ta, tb, parts[(size_t)w]);
+            else workers.emplace_back(enumerate, ta, tb, std::ref(parts[(size_t)w]));
+        }
+        for (auto& th : workers) th.join();
+    }
     std::vector<Cyc3Super> supers;
     std::vector<Cyc3Group> groups;
     std::vector<HostGroup> hgroups;
-    static const int swaps[8][3] = {{0, 0, 0}, {0, 0, 1}, {0, 1, 0}, {0, 1, 1}, {1, 0, 0}, {1, 1, 0}, {1, 0, 1}, {1, 1, 1}};
-    for (int64_t t = t_lo; t < t_hi; ++t) {
-        // cartesian_product of three ranges: third fastest, first middle, second outermost
-        const int c2 = (int)(t % n2), c0 = (int)((t / n2) % n0), c1 = (int)(t / ((int64_t)n2 * n0));
-        const int conf[3] = {c0, c1, c2};
-        int64_t lo[3], cnt[3];
-        for (int m = 0; m < 3; ++m) {
-            lo[m] = p->pivot_offsets[m][conf[m]];
-            cnt[m] = p->pivot_offsets[m][conf[m] + 1] - lo[m];
-        }
-        if (cnt[0] <= 0 || cnt[1] <= 0 || cnt[2] <= 0) continue;
-        const int64_t n_pt = cnt[0] * cnt[1] * cnt[2];
-        for (int64_t q = 0; q < n_pt; ++q) {
-            const int64_t q2 = q % cnt[2], q0 = (q / cnt[2]) % cnt[0], q1 = q / (cnt[2] * cnt[0]);
-            const int64_t row[3] = {lo[0] + q0, lo[1] + q1, lo[2] + q2};
-            const double nn[3] = {pnorm[0][(size_t)row[0]], pnorm[1][(size_t)row[1]], pnorm[2][(size_t)row[2]]};
-            // embeds.py:447: all(norms[i] < norms[i-1] + norms[i-2] for i in (0, 1, 2))
-            if (!(nn[0] < nn[2] + nn[1] && nn[1] < nn[0] + nn[2] && nn[2] < nn[1] + nn[0])) continue;
-            Cyc3Super sg;
-            for (int m = 0; m < 3; ++m) { sg.conf[m] = conf[m]; sg.piv[m] = (int)row[m]; }
-            sg.first_group = (int)groups.size();
-            sg.active = 0;
-            for (int v = 0; v < 8; ++v) {
-                int64_t o[3][2];
-                for (int m = 0; m < 3; ++m) {
-                    const int64_t* id = p->pivot_ids[m] + 2 * row[m];
-                    o[m][0] = swaps[v][m] ? id[1] : id[0];
-                    o[m][1] = swaps[v][m] ? id[0] : id[1];
-                }
-                int64_t cp[3][2] = {{o[0][1], o[1][0]}, {o[1][1], o[2][0]}, {o[2][1], o[0][0]}};
-                for (int k = 0; k < 3; ++k)
-                    if (cp[k][0] > cp[k][1]) std::swap(cp[k][0], cp[k][1]);
-                bool ok = true;
-                for (int i = 0; i < p->n_pairings && ok; ++i) {
-                    const int64_t a = p->pairings[2 * i], b = p->pairings[2 * i + 1];
-                    bool in_ids = false;
-                    for (int k = 0; k < 3; ++k) in_ids = in_ids || (cp[k][0] == a && cp[k][1] == b);
-                    ok = in_ids || pair_in(p->internal, p->n_internal, a, b);
-                }
-                if (!ok) continue;
-                sg.active |= 1 << v;
-                Cyc3Group gr;
-                gr.super = (int)supers.size();
-                gr.v = v;
-                // facing table r[m][partner] (embeds.py:328-353)
-                int pr[3][2][2];  // [couple][end] -> (mol, index)
-                for (int k = 0; k < 3; ++k)
-                    for (int e = 0; e < 2; ++e) {
-                        pr[k][e][0] = -1; pr[k][e][1] = -1;
-                        for (int m = 0; m < 3; ++m)
-                            for (int j = 0; j < p->n_ratoms0[m]; ++j)
-                                if (p->ratoms0[m][2 * j + 1] == cp[k][e]) { pr[k][e][0] = m; pr[k][e][1] = (int)p->ratoms0[m][2 * j]; }
-                    }
-                int rt[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-                for (int k = 0; k < 3; ++k) {
-                    // python negative indices wrap: -1 -> 2
-                    int m0 = pr[k][0][0] < 0 ? 2 : pr[k][0][0], m1 = pr[k][1][0] < 0 ? 2 : pr[k][1][0];
-                    rt[m0][m1] = pr[k][0][1];
-                    rt[m1][m0] = pr[k][1][1];
-                }
-                const int rr[6] = {rt[0][1], rt[0][2], rt[1][0], rt[1][2], rt[2][0], rt[2][1]};
-                for (int k = 0; k < 6; ++k) {
-                    int mol = k / 2;
-                    // an unmatched couple leaves -1 (python: coords[0][-1] = last atom)
-                    gr.r[k] = rr[k] < 0 ? p->n_atoms[mol] + rr[k] : rr[k];
-                    FC_REQUIRE(gr.r[k] >= 0 && gr.r[k] < p->n_atoms[mol], "facing atom out of range");
-                }
-                groups.push_back(gr);
-                HostGroup hg;
-                for (int k = 0; k < 3; ++k) { hg.ids[2 * k] = (int)cp[k][0]; hg.ids[2 * k + 1] = (int)cp[k][1]; }
-                hgroups.push_back(hg);
-            }
-            if (sg.active) supers.push_back(sg);
-            FC_REQUIRE(groups.size() < ((size_t)1 << 30), "too many groups for one call");
-        }
+    for (EnumPart& L : parts) {
+        FC_REQUIRE(!L.bad, "fc_cyclical3_screen: facing atom out of range or too many groups");
+        const int s_off = (int)supers.size(), g_off = (int)groups.size();
+        for (Cyc3Super& x : L.supers) x.first_group += g_off;
+        for (Cyc3Group& x : L.groups) x.super += s_off;
+        supers.insert(supers.end(), L.supers.begin(), L.supers.end());
+        groups.insert(groups.end(), L.groups.begin(), L.groups.end());
+        hgroups.insert(hgroups.end(), L.hgroups.begin(), L.hgroups.end());
+        FC_REQUIRE(groups.size() < ((size_t)1 << 30), "too many groups for one call");
     }
     const int64_t G = (int64_t)groups.size();
     t_enum = now() - t0;
@@ -781,6 +814,12 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
         CY(d_near_dist.alloc(near_cap, s));
         if (e != cudaSuccess) rc = cuda_fail(e, "fc_cyclical3_screen setup", __FILE__, __LINE__);
 
+        // fragment-A tables of the three block screens (A = molecule 0, 1, 2 of the blocks (0,1), (1,2), (2,0)):
+        // built once, reused by every chunk
+        fc_clash_prep* prep[3] = {nullptr, nullptr, nullptr};
+        for (int k = 0; k < 3 && !rc; ++k)
+            rc = fc_clash_prepare_dev(d_coords[k].p, p->n_conf[k], p->n_atoms[k], p->thresh, 1, &prep[k], (void*)s);
+
         // ---- chunks of whole super-groups ------------------------------------------------------
         const int64_t max_chunk_groups = std::max<int64_t>(64, ((int64_t)12 << 20) / A);  // ~12 M poses per chunk
         size_t sg_lo = 0;
@@ -870,10 +909,9 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
                 CY(d_tiles.alloc(tl.size(), s));
                 CY(cudaMemcpyAsync(d_tiles.p, tl.data(), tl.size() * 4, cudaMemcpyHostToDevice, s));
                 if (e != cudaSuccess) { rc = cuda_fail(e, "tile upload", __FILE__, __LINE__); break; }
-                rc = fc_clash_screen_dev(d_coords[mi].p, p->n_conf[mi], p->n_atoms[mi], d_coords[mj].p, p->n_conf[mj],
-                                         p->n_atoms[mj], d_xf.p, n_pp, d_tiles.p, (int64_t)tl.size() / 4, p->thresh, 0,
-                                         /*strict=*/0, d_st[k].p, nullptr, d_near_count.p, d_near_idx.p, d_near_dist.p,
-                                         near_cap, 0, (void*)s);
+                rc = fc_clash_screen_prepared_dev(prep[mi], d_coords[mi].p, d_coords[mj].p, p->n_conf[mj], p->n_atoms[mj], d_xf.p,
+                                                  n_pp, d_tiles.p, (int64_t)tl.size() / 4, 0, /*strict=*/0, d_st[k].p, nullptr,
+                                                  d_near_count.p, d_near_idx.p, d_near_dist.p, near_cap, 0, (void*)s);
                 if (rc) break;
                 // near-threshold block decisions -> one tie per affected pose (b = -1 - block)
                 int n_near = 0;
@@ -998,6 +1036,7 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
             if (trace) { t_mat += now() - tc; }
             sg_lo = sg_hi;
         }
+        for (int k = 0; k < 3; ++k) fc_clash_prep_free(prep[k], (void*)s);
 #undef CY
     }
     cudaStreamSynchronize(s);

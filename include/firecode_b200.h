@@ -69,6 +69,20 @@ int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a, const dou
                         int64_t* near_idx, double* near_dist, int64_t near_cap,
                         int64_t pose_index_base, void* stream);
 
+/* Fragment A's tables (FP32 atom-pair layout, bounding radii and -- with want_cells -- the cell grid,
+ * candidate records and occupancy bits) can be built once and reused by several screens that share
+ * fragment A and the threshold (the trimolecular embed screens every molecule against many chunks).
+ * All calls are stream-ordered; free the preparation on the same stream after the last screen. */
+typedef struct fc_clash_prep fc_clash_prep;
+int fc_clash_prepare_dev(const double* a_coords, int n_conf_a, int n_a, double thresh, int want_cells,
+                         fc_clash_prep** out, void* stream);
+int fc_clash_screen_prepared_dev(const fc_clash_prep* prep, const double* a_coords, const double* b_coords,
+                                 int n_conf_b, int n_b, const double* xf, int64_t n_poses,
+                                 const int32_t* tiles, int64_t n_tiles, int max_clashes, int strict,
+                                 uint8_t* status, float* min_dist, int32_t* near_count, int64_t* near_idx,
+                                 double* near_dist, int64_t near_cap, int64_t pose_index_base, void* stream);
+void fc_clash_prep_free(fc_clash_prep* prep, void* stream);
+
 /* Host-pointer entry: same arguments in host memory; copies are pipelined in chunks with the
  * kernels.  counts[0] = passing poses, counts[1] = poses decided by the FP64 recheck,
  * counts[2] = near-threshold poses (near_idx/near_dist hold the first near_cap of them). */
