@@ -356,6 +356,7 @@ struct Cyc3SimArgs {
     const double* xf_abs;   // (G, 3, u_max, 12): absolute transform of every molecule for its distinct angles
     const int* amap[3];     // per molecule: angle index -> distinct angle of that molecule
     int u_max;
+    const double* mom[3];   // per molecule (n_conf, 10): sum b b^T (00 01 02 11 12 22), sum b (3), n_atoms
     uint8_t* status;        // per pose, out: combined FC_STATUS_* bits
     uint8_t* keep;          // per pose, out
     double rmsd_thr, eps;
@@ -373,6 +374,58 @@ __device__ __forceinline__ void push_tie3(const Cyc3SimArgs& a, long long pose, 
         r.a = pose + a.pose_base; r.b = ref + a.pose_base; r.value = value; r.kind = kind; r.decision = decision ? 1 : 0;
         a.ties[slot] = r;
     }
+}
+
+// second / first moments of every conformer: with them the cross-covariance of two poses of the same
+// conformers needs no loop over atoms,
+//   sum (Rp b + tp)(Rq b + tq)^T = Rp M Rq^T + (Rp s) tq^T + tp (Rq s)^T + n tp tq^T,   M = sum b b^T, s = sum b
+__global__ void cyc3_moments_kernel(const double* __restrict__ coords, int n_conf, int n_atoms, double* __restrict__ mom) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n_conf) return;
+    const double* x = coords + (size_t)c * n_atoms * 3;
+    double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = lane; k < n_atoms; k += 32) {
+        const double a = x[3 * k], b = x[3 * k + 1], d = x[3 * k + 2];
+        v[0] += a * a; v[1] += a * b; v[2] += a * d; v[3] += b * b; v[4] += b * d; v[5] += d * d;
+        v[6] += a; v[7] += b; v[8] += d;
+    }
+#pragma unroll
+    for (int e = 0; e < 9; ++e) v[e] = wsum_d(v[e]);
+    if (lane == 0) {
+        double* o = mom + (size_t)c * 10;
+        for (int e = 0; e < 9; ++e) o[e] = v[e];
+        o[9] = (double)n_atoms;
+    }
+}
+
+// cross-covariance H (+=) and |p|^2 + |q|^2 (+=) of one molecule placed by (rp, tp) and (rq, tq), from its moments
+__device__ __forceinline__ void cov_from_moments(const double* mo, const double* rp, const double* rq, double* h, double& gsum) {
+    const double M[9] = {mo[0], mo[1], mo[2], mo[1], mo[3], mo[4], mo[2], mo[4], mo[5]};
+    const double n = mo[9];
+    double A[9];  // Rp M
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) A[3 * i + j] = rp[3 * i] * M[j] + rp[3 * i + 1] * M[3 + j] + rp[3 * i + 2] * M[6 + j];
+    double u[3], w[3];  // Rp s, Rq s
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        u[i] = rp[3 * i] * mo[6] + rp[3 * i + 1] * mo[7] + rp[3 * i + 2] * mo[8];
+        w[i] = rq[3 * i] * mo[6] + rq[3 * i + 1] * mo[7] + rq[3 * i + 2] * mo[8];
+    }
+    const double* tp = rp + 9;
+    const double* tq = rq + 9;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            h[3 * i + j] += (A[3 * i] * rq[3 * j] + A[3 * i + 1] * rq[3 * j + 1] + A[3 * i + 2] * rq[3 * j + 2]) + u[i] * tq[j] +
+                            tp[i] * w[j] + n * tp[i] * tq[j];
+    // sum |R b + t|^2 = tr(M) + 2 t.(R s) + n |t|^2 (R orthogonal)
+    const double tr = mo[0] + mo[3] + mo[5];
+    gsum += 2.0 * tr + 2.0 * (tp[0] * u[0] + tp[1] * u[1] + tp[2] * u[2]) + 2.0 * (tq[0] * w[0] + tq[1] * w[1] + tq[2] * w[2]) +
+            n * (tp[0] * tp[0] + tp[1] * tp[1] + tp[2] * tp[2] + tq[0] * tq[0] + tq[1] * tq[1] + tq[2] * tq[2]);
 }
 
 // combined status of every pose: PASS iff all three block screens pass (utils.py:553-575 with max_clashes = 0),
@@ -424,77 +477,100 @@ __global__ void __launch_bounds__(128) cyc3_group_similarity_kernel(Cyc3SimArgs 
 #pragma unroll
             for (int m = 0; m < 3; ++m) xp[m] = a.xf_abs + (((size_t)g * 3 + m) * a.u_max + a.amap[m][ai]) * 12;
             bool similar = false;
-            for (int k = 0; k < n_acc && !similar; ++k) {
-                const int aj = s_acc[k];
-                // H = p^T q over all atoms, uncentred (rmsd_and_max(center=False)); molecule loops are unrolled so
-                // that the transforms stay in registers
-                double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-                double gsum = 0.0;  // |p|^2 + |q|^2
+            for (int k0 = 0; k0 < n_acc && !similar; k0 += 32) {
+                // ---- screen, one accepted pose per lane: covariance from the conformers' moments (no atom loop),
+                //      closed-form singular values; kept poses are mutually dissimilar, so this is where almost
+                //      every comparison ends
+                const int k = k0 + lane;
+                bool need = false;
+                if (k < n_acc) {
+                    const int ak = s_acc[k];
+                    double hs[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    double gs = 0.0;
 #pragma unroll
-                for (int m = 0; m < 3; ++m) {
-                    const double* xq = a.xf_abs + (((size_t)g * 3 + m) * a.u_max + a.amap[m][aj]) * 12;
-                    double rp[12], rq[12];
+                    for (int m = 0; m < 3; ++m) {
+                        const double* xq = a.xf_abs + (((size_t)g * 3 + m) * a.u_max + a.amap[m][ak]) * 12;
+                        double rp[12], rq[12];
 #pragma unroll
-                    for (int e = 0; e < 12; ++e) { rp[e] = xp[m][e]; rq[e] = xq[e]; }
-                    const double* base = p.coords[m] + (size_t)conf[m] * p.n_atoms[m] * 3;
-                    for (int at = lane; at < p.n_atoms[m]; at += 32) {
-                        const double bx = base[3 * at], by = base[3 * at + 1], bz = base[3 * at + 2];
-                        const double x[3] = {(rp[0] * bx + rp[1] * by + rp[2] * bz) + rp[9], (rp[3] * bx + rp[4] * by + rp[5] * bz) + rp[10],
-                                             (rp[6] * bx + rp[7] * by + rp[8] * bz) + rp[11]};
-                        const double y[3] = {(rq[0] * bx + rq[1] * by + rq[2] * bz) + rq[9], (rq[3] * bx + rq[4] * by + rq[5] * bz) + rq[10],
-                                             (rq[6] * bx + rq[7] * by + rq[8] * bz) + rq[11]};
-#pragma unroll
-                        for (int r = 0; r < 3; ++r) {
-                            gsum += x[r] * x[r] + y[r] * y[r];
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) h[3 * r + c] += x[r] * y[c];
+                        for (int e = 0; e < 12; ++e) { rp[e] = xp[m][e]; rq[e] = xq[e]; }
+                        cov_from_moments(a.mom[m] + (size_t)conf[m] * 10, rp, rq, hs, gs);
+                    }
+                    const double lim = a.rmsd_thr + 1e-4;
+                    need = !((gs - 2.0 * singular_sum3(hs)) / n_tot > lim * lim);
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, need);
+                // ---- exact evaluation (whole warp per pair, atoms over the lanes) of the few pairs left, in order
+                while (todo && !similar) {
+                    const int aj = s_acc[k0 + __ffs(todo) - 1];
+                    todo &= todo - 1u;
+                    double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    double gsum = 0.0;  // |p|^2 + |q|^2
+    #pragma unroll
+                    for (int m = 0; m < 3; ++m) {
+                        const double* xq = a.xf_abs + (((size_t)g * 3 + m) * a.u_max + a.amap[m][aj]) * 12;
+                        double rp[12], rq[12];
+    #pragma unroll
+                        for (int e = 0; e < 12; ++e) { rp[e] = xp[m][e]; rq[e] = xq[e]; }
+                        const double* base = p.coords[m] + (size_t)conf[m] * p.n_atoms[m] * 3;
+                        for (int at = lane; at < p.n_atoms[m]; at += 32) {
+                            const double bx = base[3 * at], by = base[3 * at + 1], bz = base[3 * at + 2];
+                            const double x[3] = {(rp[0] * bx + rp[1] * by + rp[2] * bz) + rp[9], (rp[3] * bx + rp[4] * by + rp[5] * bz) + rp[10],
+                                                 (rp[6] * bx + rp[7] * by + rp[8] * bz) + rp[11]};
+                            const double y[3] = {(rq[0] * bx + rq[1] * by + rq[2] * bz) + rq[9], (rq[3] * bx + rq[4] * by + rq[5] * bz) + rq[10],
+                                                 (rq[6] * bx + rq[7] * by + rq[8] * bz) + rq[11]};
+    #pragma unroll
+                            for (int r = 0; r < 3; ++r) {
+                                gsum += x[r] * x[r] + y[r] * y[r];
+    #pragma unroll
+                                for (int c = 0; c < 3; ++c) h[3 * r + c] += x[r] * y[c];
+                            }
                         }
                     }
-                }
-#pragma unroll
-                for (int e = 0; e < 9; ++e) h[e] = wsum_d(h[e]);
-                gsum = wsum_d(gsum);
-                // screen: RMSD from the closed-form singular values; clearly dissimilar pairs (the common case
-                // among kept poses) skip the Jacobi solve and the second pass over the atoms
-                {
-                    const double msd = (gsum - 2.0 * singular_sum3(h)) / n_tot;
-                    const double lim = a.rmsd_thr + 1e-4;
-                    if (msd > lim * lim) continue;
-                }
-                M3 R = kabsch_from_cov(h, nullptr);
-                double ss = 0.0, mx = 0.0;
-#pragma unroll
-                for (int m = 0; m < 3; ++m) {
-                    const double* xq = a.xf_abs + (((size_t)g * 3 + m) * a.u_max + a.amap[m][aj]) * 12;
-                    double rp[12], rq[12];
-#pragma unroll
-                    for (int e = 0; e < 12; ++e) { rp[e] = xp[m][e]; rq[e] = xq[e]; }
-                    const double* base = p.coords[m] + (size_t)conf[m] * p.n_atoms[m] * 3;
-                    for (int at = lane; at < p.n_atoms[m]; at += 32) {
-                        const double bx = base[3 * at], by = base[3 * at + 1], bz = base[3 * at + 2];
-                        const double x[3] = {(rp[0] * bx + rp[1] * by + rp[2] * bz) + rp[9], (rp[3] * bx + rp[4] * by + rp[5] * bz) + rp[10],
-                                             (rp[6] * bx + rp[7] * by + rp[8] * bz) + rp[11]};
-                        const double y[3] = {(rq[0] * bx + rq[1] * by + rq[2] * bz) + rq[9], (rq[3] * bx + rq[4] * by + rq[5] * bz) + rq[10],
-                                             (rq[6] * bx + rq[7] * by + rq[8] * bz) + rq[11]};
-                        // diff = p @ R - q
-                        const double dx = (x[0] * R.m[0] + x[1] * R.m[3] + x[2] * R.m[6]) - y[0];
-                        const double dy = (x[0] * R.m[1] + x[1] * R.m[4] + x[2] * R.m[7]) - y[1];
-                        const double dz = (x[0] * R.m[2] + x[1] * R.m[5] + x[2] * R.m[8]) - y[2];
-                        const double d2 = dx * dx + dy * dy + dz * dz;
-                        ss += d2;
-                        mx = fmax(mx, d2);
+    #pragma unroll
+                    for (int e = 0; e < 9; ++e) h[e] = wsum_d(h[e]);
+                    gsum = wsum_d(gsum);
+                    // screen: RMSD from the closed-form singular values; clearly dissimilar pairs (the common case
+                    // among kept poses) skip the Jacobi solve and the second pass over the atoms
+                    {
+                        const double msd = (gsum - 2.0 * singular_sum3(h)) / n_tot;
+                        const double lim = a.rmsd_thr + 1e-4;
+                        if (msd > lim * lim) continue;
                     }
+                    M3 R = kabsch_from_cov(h, nullptr);
+                    double ss = 0.0, mx = 0.0;
+    #pragma unroll
+                    for (int m = 0; m < 3; ++m) {
+                        const double* xq = a.xf_abs + (((size_t)g * 3 + m) * a.u_max + a.amap[m][aj]) * 12;
+                        double rp[12], rq[12];
+    #pragma unroll
+                        for (int e = 0; e < 12; ++e) { rp[e] = xp[m][e]; rq[e] = xq[e]; }
+                        const double* base = p.coords[m] + (size_t)conf[m] * p.n_atoms[m] * 3;
+                        for (int at = lane; at < p.n_atoms[m]; at += 32) {
+                            const double bx = base[3 * at], by = base[3 * at + 1], bz = base[3 * at + 2];
+                            const double x[3] = {(rp[0] * bx + rp[1] * by + rp[2] * bz) + rp[9], (rp[3] * bx + rp[4] * by + rp[5] * bz) + rp[10],
+                                                 (rp[6] * bx + rp[7] * by + rp[8] * bz) + rp[11]};
+                            const double y[3] = {(rq[0] * bx + rq[1] * by + rq[2] * bz) + rq[9], (rq[3] * bx + rq[4] * by + rq[5] * bz) + rq[10],
+                                                 (rq[6] * bx + rq[7] * by + rq[8] * bz) + rq[11]};
+                            // diff = p @ R - q
+                            const double dx = (x[0] * R.m[0] + x[1] * R.m[3] + x[2] * R.m[6]) - y[0];
+                            const double dy = (x[0] * R.m[1] + x[1] * R.m[4] + x[2] * R.m[7]) - y[1];
+                            const double dz = (x[0] * R.m[2] + x[1] * R.m[5] + x[2] * R.m[8]) - y[2];
+                            const double d2 = dx * dx + dy * dy + dz * dz;
+                            ss += d2;
+                            mx = fmax(mx, d2);
+                        }
+                    }
+                    ss = wsum_d(ss);
+                    mx = wmax_d(mx);
+                    const double rmsd = sqrt(ss / n_tot), maxdev = sqrt(mx);
+                    const bool rm_ok = rmsd < a.rmsd_thr, md_ok = maxdev < 2.0 * a.rmsd_thr;
+                    if (lane == 0) {
+                        const long long ref = g * n_ang + aj;
+                        if (fabs(rmsd - a.rmsd_thr) <= a.eps) push_tie3(a, pose, ref, rmsd, FC_TIE_RMSD, rm_ok);
+                        if (fabs(maxdev - 2.0 * a.rmsd_thr) <= a.eps) push_tie3(a, pose, ref, maxdev, FC_TIE_MAXDEV, md_ok);
+                    }
+                    similar = rm_ok && md_ok;
                 }
-                ss = wsum_d(ss);
-                mx = wmax_d(mx);
-                const double rmsd = sqrt(ss / n_tot), maxdev = sqrt(mx);
-                const bool rm_ok = rmsd < a.rmsd_thr, md_ok = maxdev < 2.0 * a.rmsd_thr;
-                if (lane == 0) {
-                    const long long ref = g * n_ang + aj;
-                    if (fabs(rmsd - a.rmsd_thr) <= a.eps) push_tie3(a, pose, ref, rmsd, FC_TIE_RMSD, rm_ok);
-                    if (fabs(maxdev - 2.0 * a.rmsd_thr) <= a.eps) push_tie3(a, pose, ref, maxdev, FC_TIE_MAXDEV, md_ok);
-                }
-                similar = rm_ok && md_ok;
             }
             if (!similar) {
                 if (lane == 0) {
@@ -766,7 +842,7 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
         DevBuf<double> d_coords[3], d_pvec[3], d_pmean[3], d_pnorm[3], d_angles, d_ua[3], d_xf, d_out, d_near_dist, d_gap;
         DevBuf<long long> d_react[3], d_kept;
         DevBuf<int> d_umap[3], d_amap[3], d_choice, d_cnt;
-        DevBuf<double> d_uang, d_xf_abs;
+        DevBuf<double> d_uang, d_xf_abs, d_mom[3];
         DevBuf<Cyc3Super> d_supers;
         DevBuf<Cyc3Group> d_groups;
         DevBuf<Cyc3Xf> d_gx;
@@ -790,6 +866,11 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
             CY(cudaMemcpyAsync(d_pvec[m].p, p->pivot_vec[m], rows * 24, cudaMemcpyHostToDevice, s));
             CY(cudaMemcpyAsync(d_pmean[m].p, p->pivot_mean[m], rows * 24, cudaMemcpyHostToDevice, s));
             CY(cudaMemcpyAsync(d_pnorm[m].p, pnorm[m].data(), rows * 8, cudaMemcpyHostToDevice, s));
+        }
+        for (int m = 0; m < 3; ++m) {
+            CY(d_mom[m].alloc((size_t)p->n_conf[m] * 10, s));
+            if (e == cudaSuccess)
+                cyc3_moments_kernel<<<(unsigned)((p->n_conf[m] + 3) / 4), 128, 0, s>>>(d_coords[m].p, p->n_conf[m], p->n_atoms[m], d_mom[m].p);
         }
         CY(d_angles.alloc((size_t)A * 3, s));
         CY(cudaMemcpyAsync(d_angles.p, p->angles, (size_t)A * 24, cudaMemcpyHostToDevice, s));
@@ -959,7 +1040,7 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
                                                                                   (int)uang_m[1].size(), (int)uang_m[2].size(), d_xf_abs.p);
             }
             a.xf_abs = d_xf_abs.p;
-            for (int m = 0; m < 3; ++m) a.amap[m] = d_amap[m].p;
+            for (int m = 0; m < 3; ++m) { a.amap[m] = d_amap[m].p; a.mom[m] = d_mom[m].p; }
             a.u_max = u_max;
             a.status = d_status.p; a.keep = d_keep.p;
             a.rmsd_thr = p->rmsd_thresh; a.eps = FC_NEAR_EPS;
