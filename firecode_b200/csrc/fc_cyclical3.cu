@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(256) cyc3_combine_kernel(Cyc3SimArgs a, long l
 }
 
 // one warp per group: keep-first over the clash survivors in angle order
-__global__ void __launch_bounds__(128) cyc3_group_similarity_kernel(Cyc3SimArgs a) {
+__global__ void __launch_bounds__(128, 3) cyc3_group_similarity_kernel(Cyc3SimArgs a) {
     const Cyc3Dev& p = a.p;
     const int lane = threadIdx.x & 31;
     const long long g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

@@ -94,3 +94,18 @@ def test_trimolecular_conf_tuple_slices_concatenate(gpu):
     assert base == rep.n_poses
     assert np.array_equal(np.concatenate(kept), rep.kept_indices)
     assert np.array_equal(np.concatenate(parts), poses)
+
+
+def test_trimolecular_many_survivors_per_group(gpu):
+    """A loose clash threshold leaves most of the 216 poses of a group alive, so groups accumulate more
+    than 32 kept poses: exercises the lane-parallel moment screen over several 32-pose batches and the
+    in-order exact evaluation of the pairs it cannot rule out."""
+    emb = make_embedder("cyclical", n_mols=3, n_conf=1, n_atoms=[60, 50, 55], seed=7, n_reactive=2, n_orb=1,
+                        thresh=0.2)
+    prob = problem.cyclical_problem(emb)
+    poses = embeds.cyclical_embed(emb)
+    rep = emb.b200_report
+    ref = _check_problem(prob, poses, emb.constrained_indices, rep)
+    per_group = np.bincount(ref["kept"] // len(prob.angles), minlength=len(ref["groups"]))
+    assert per_group.max() > 32, per_group
+    assert rep.n_clash_pass > rep.n_kept > 0
