@@ -295,6 +295,7 @@ __device__ __forceinline__ float singular_sum3f(const float* h) {
 
 constexpr float kScreenBand = 0.05f;   // A: FP32 covariance + FP32 closed form are good to a few 1e-3 A
 #define PS_ATOMS 64                    // atoms staged per step
+#define PS_LD 33                       // row stride (float4) of the staged tiles: 32 structures + 1 pad
 
 // 128 threads per 32 x 32 pair tile: thread (tc, tr) owns rows 4 tr .. 4 tr + 3 and columns 2 tc, 2 tc + 1
 // (8 pairs, 72 FP32 accumulators); per atom 4 broadcast LDS.128 (rows) + 2 LDS.128 (columns) feed 72 FFMA.
@@ -302,9 +303,9 @@ __global__ void __launch_bounds__(128) prune_screen_f32_kernel(PruneArgs a) {
     const PruneTile t = a.tiles[blockIdx.x];
     const int tc = threadIdx.x & 15, tr = threadIdx.x >> 4;
     const int chunk_end = t.chunk_begin + t.chunk_len;
-    extern __shared__ float4 s_stage[];  // [PS_ATOMS][32] rows, then [PS_ATOMS][32] columns
+    extern __shared__ float4 s_stage[];  // [PS_ATOMS][PS_LD] rows, then [PS_ATOMS][PS_LD] columns
     float4* sR = s_stage;
-    float4* sC = s_stage + PS_ATOMS * PR_TS;
+    float4* sC = s_stage + PS_ATOMS * PS_LD;
     float h[8][9];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
@@ -314,19 +315,24 @@ __global__ void __launch_bounds__(128) prune_screen_f32_kernel(PruneArgs a) {
     for (int a0 = 0; a0 < nh; a0 += PS_ATOMS) {
         const int na = min(PS_ATOMS, nh - a0);
         __syncthreads();
-        for (int e = threadIdx.x; e < PR_TS * na; e += 128) {
-            const int sidx = e / na, k = e - sidx * na;  // consecutive threads read consecutive atoms of a structure
+        // a warp stages one structure at a time: lanes read consecutive atoms (coalesced) and write with a row
+        // stride of PS_LD = 33 float4, so the 8 lanes of a quarter-warp hit 8 different 4-bank groups
+        for (int sidx = threadIdx.x >> 5; sidx < PR_TS; sidx += 4) {
             const int rpos = t.row0 + sidx, cpos = t.col0 + sidx;
-            sR[k * PR_TS + sidx] = rpos < chunk_end ? a.xcf[(size_t)a.active[rpos] * nh + a0 + k] : make_float4(0.f, 0.f, 0.f, 0.f);
-            sC[k * PR_TS + sidx] = cpos < chunk_end ? a.xcf[(size_t)a.active[cpos] * nh + a0 + k] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* rsrc = rpos < chunk_end ? a.xcf + (size_t)a.active[rpos] * nh + a0 : nullptr;
+            const float4* csrc = cpos < chunk_end ? a.xcf + (size_t)a.active[cpos] * nh + a0 : nullptr;
+            for (int k = threadIdx.x & 31; k < na; k += 32) {
+                sR[k * PS_LD + sidx] = rsrc ? rsrc[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+                sC[k * PS_LD + sidx] = csrc ? csrc[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
         __syncthreads();
 #pragma unroll 2
         for (int k = 0; k < na; ++k) {
-            const float4 q0 = sC[k * PR_TS + 2 * tc], q1 = sC[k * PR_TS + 2 * tc + 1];
+            const float4 q0 = sC[k * PS_LD + 2 * tc], q1 = sC[k * PS_LD + 2 * tc + 1];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float4 pr = sR[k * PR_TS + 4 * tr + i];
+                const float4 pr = sR[k * PS_LD + 4 * tr + i];
                 float* h0 = h[2 * i];
                 float* h1 = h[2 * i + 1];
                 h0[0] = fmaf(pr.x, q0.x, h0[0]); h0[1] = fmaf(pr.x, q0.y, h0[1]); h0[2] = fmaf(pr.x, q0.z, h0[2]);
@@ -609,7 +615,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                     unsigned long long found = 0;
                     if (two_stage) {
                         // FP32 screen of every pair of the tiles -> candidates; FP64 exact evaluation of the candidates
-                        const size_t smem = (size_t)2 * PS_ATOMS * PR_TS * sizeof(float4);
+                        const size_t smem = (size_t)2 * PS_ATOMS * PS_LD * sizeof(float4);
                         PR(cudaFuncSetAttribute(prune_screen_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                         prune_screen_f32_kernel<<<(unsigned)tiles.size(), 128, smem, s>>>(a);
                         PR(cudaGetLastError());
