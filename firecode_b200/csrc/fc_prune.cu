@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "fc_embed.cuh"
@@ -498,6 +499,10 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
         FC_REQUIRE(masses, "fc_prune: MOI pruning needs masses");
     }
     sm_count();
+    const bool trace = getenv("FC_CLASH_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_tiles = 0, t_kernels = 0, t_resolve = 0, t_upload = 0;
     cudaStream_t s;
     FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     int rc = FC_OK;
@@ -547,6 +552,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
             }
         }
         PR(d_active.alloc((size_t)n, s));
+        if (trace) { PR(cudaStreamSynchronize(s)); t_upload = now() - t_begin; }
         if (e != cudaSuccess) rc = cuda_fail(e, "fc_prune setup", __FILE__, __LINE__);
 
         std::vector<int> active;
@@ -559,6 +565,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
             for (uint8_t b : mask) n_active += b;
             if (!(k == 1 || (int64_t)min_per_chunk * k < n_active)) continue;
             ++passes;
+            double tp = now();
             // compacted active list + chunks over the FULL array (chunk size n // k, last takes the rest)
             active.clear();
             tiles.clear();
@@ -589,6 +596,8 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
             prev_size = size;
             prev_k = k;
             pairs.clear();
+            t_tiles += now() - tp;
+            tp = now();
             if (!tiles.empty()) {
                 e = d_tiles.alloc(tiles.size(), s);
                 PR(cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(PruneTile), cudaMemcpyHostToDevice, s));
@@ -653,6 +662,8 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                 }
                 if (rc) break;
             }
+            t_kernels += now() - tp;
+            tp = now();
             const std::vector<int2>* use = &pairs;
             if (world > 1) {
                 const void* recv = nullptr;
@@ -669,6 +680,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
             }
             similar_total += (int64_t)use->size();
             prune_resolve(mask, *use, keep_first != 0, snapshot != 0);
+            t_resolve += now() - tp;
         }
         if (!rc) {
             int n_t = 0;
@@ -691,6 +703,9 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
     cudaStreamSynchronize(s);
     cudaStreamDestroy(s);
     if (rc) return rc;
+    if (trace)
+        fprintf(stderr, "fc_prune: total %.1f ms: upload+centre %.1f, tile lists %.1f, kernels+readback %.1f, resolve %.1f\n",
+                now() - t_begin, t_upload, t_tiles, t_kernels, t_resolve);
     memcpy(mask_out, mask.data(), (size_t)n);
     if (n_ties_out) *n_ties_out = ties_total;
     if (stats_out) {
