@@ -82,3 +82,98 @@ def torsion_comp_check(coords, torsion, mask, thresh=1.5, max_clashes=0):
     closer than ``thresh`` (torsion_module.py:894-918)."""
     res = torsion_scan(coords, [torsion], [mask], [0.0], thresh=thresh, max_clashes=max_clashes, want_coords=False)
     return bool(res["passed"][0, 0, 0])
+
+
+# ------------------------------------------------------------------------------------------------
+# TFD ensemble pruning (torsion_module.py:957-1076)
+# ------------------------------------------------------------------------------------------------
+_TFD_SCHEDULE = (5e5, 2e5, 1e5, 5e4, 2e4, 1e4, 5000, 2000, 1000, 500, 200, 100, 50, 20, 10, 5, 2, 1)
+last_tfd_ties = None  # near-threshold decisions of the last prune_conformers_tfd call
+
+
+def _get_tf_mat(structures, quadruplets):
+    """Torsion fingerprint matrix (n, Q) in degrees (torsion_module.py:1046-1053), on the GPU."""
+    lib = _lib.load(require_device=True)
+    x = np.ascontiguousarray(np.asarray(structures, dtype=np.float64))
+    q = np.ascontiguousarray(np.asarray(quadruplets, dtype=np.int64).reshape(-1, 4))
+    tf = np.zeros((len(x), len(q)), dtype=np.float64)
+    _lib.check(lib.fc_tfd_fingerprints(_ptr(x), len(x), x.shape[1], _ptr(q), len(q), _ptr(tf)), "fc_tfd_fingerprints")
+    return tf
+
+
+def get_torsion_fingerprint(coords, quadruplets):
+    """Dihedral of every quadruplet of one structure (torsion_module.py:1070-1076)."""
+    return _get_tf_mat(np.asarray(coords, dtype=np.float64)[None], quadruplets)[0]
+
+
+def tfd_similarity(tfp1, tfp2, thresh=10):
+    """torsion_module.py:1056-1067 for one pair (two-row batch through the GPU first-match search)."""
+    tf = np.ascontiguousarray(np.stack([np.asarray(tfp1, dtype=np.float64), np.asarray(tfp2, dtype=np.float64)]))
+    return bool(_first_match(tf, [(0, 2)], thresh)[0][0] == 1)
+
+
+def _first_match(tf, chunks, thresh, tie_cap=1 << 16):
+    import ctypes as C
+
+    from .embeds import TIE_DTYPE
+
+    lib = _lib.load(require_device=True)
+    tf = np.ascontiguousarray(tf, dtype=np.float64)
+    n, nq = tf.shape
+    start = np.ascontiguousarray([c[0] for c in chunks], dtype=np.int64)
+    length = np.ascontiguousarray([c[1] for c in chunks], dtype=np.int64)
+    first = np.full(n, -1, dtype=np.int64)
+    ties = np.zeros(tie_cap, dtype=TIE_DTYPE)
+    n_ties = C.c_int64(0)
+    _lib.check(lib.fc_tfd_first_match(_ptr(tf), n, nq, _ptr(start), _ptr(length), len(chunks), float(thresh), _ptr(first),
+                                      _ptr(ties), tie_cap, C.byref(n_ties)), "fc_tfd_first_match")
+    return first, ties[: min(int(n_ties.value), tie_cap)]
+
+
+def prune_conformers_tfd(structures, quadruplets, thresh=10, verbose=False):
+    """Drop-in for firecode.torsion_module.prune_conformers_tfd (torsion_module.py:957-1043):
+    ``(structures[mask], mask)``.  Fingerprints and the per-chunk first-match searches run on the GPU; the
+    cluster resolution keeps the reference's own networkx calls (its outcome depends on set / graph
+    iteration order).  Quirks reproduced: the last subdivision of a pass ends at the number of active
+    structures, and masked-out structures keep taking part in later passes."""
+    global last_tfd_ties
+    from networkx import Graph, connected_components
+
+    structures = np.asarray(structures)
+    n = structures.shape[0]
+    tf = _get_tf_mat(structures, quadruplets)
+    final_mask = np.ones(n, dtype=bool)
+    all_ties = []
+    for k in _TFD_SCHEDULE:
+        num_active_str = int(np.count_nonzero(final_mask))
+        if not (k == 1 or 5 * k < num_active_str):
+            continue
+        if verbose:
+            print(f"Working on subgroups with k={k} ({num_active_str} candidates left) {' ' * 10}", end="\r")
+        d = int(n // k)
+        chunks = []
+        for step in range(int(k)):
+            if step == k - 1:
+                chunks.append((d * step, len(range(d * step, num_active_str))))
+            else:
+                chunks.append((d * step, len(range(d * step, int(d * (step + 1))))))
+        first, ties = _first_match(tf, chunks, thresh)
+        all_ties.append(ties)
+        for start, length in chunks:
+            if length < 2:
+                continue
+            matches = set()
+            found = first[start:start + length]
+            for i_rel in np.flatnonzero(found >= 0):  # ascending i, as the reference inserts them
+                matches.add((int(i_rel), int(found[i_rel]) - start))
+            if not matches:
+                continue
+            g = Graph(matches)
+            subgraphs = [g.subgraph(c) for c in connected_components(g)]
+            groups = [tuple(graph.nodes) for graph in subgraphs]
+            for group in groups:
+                for i in set(group) - {group[0]}:  # of each cluster, keep the first structure
+                    final_mask[i + start] = False
+    last_tfd_ties = np.concatenate(all_ties) if all_ties else None
+    return structures[final_mask], final_mask
+

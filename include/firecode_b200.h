@@ -255,6 +255,19 @@ int fc_prune_sharded(const double* structures, int64_t n, int32_t n_atoms, int32
                      int64_t tie_cap, int64_t* n_ties_out, int32_t rank, int32_t world,
                      fc_allgather_fn gather, void* gather_ctx);
 
+/* Torsion-fingerprint (TFD) ensemble pruning, the O(n^2) part of torsion_module.py:957-1043
+ * `prune_conformers_tfd` (embedder.py:1430-1437, torsion_module.py:875).
+ *  fc_tfd_fingerprints: `_get_tf_mat` (torsion_module.py:1046-1053): tf_out (n, n_quads) degrees.
+ *  fc_tfd_first_match : for every structure i of every chunk {start, len} of a pass, first_out[i] = the
+ *  first later structure j of the same chunk with sum_q wrap180(|tf_i - tf_j|) < thresh
+ *  (torsion_module.py:1056-1067), -1 if none -- what the reference's pair loops record before they break.
+ *  The host (Python, same networkx calls as the reference) turns the matches into clusters. */
+int fc_tfd_fingerprints(const double* structures, int64_t n, int32_t n_atoms, const int64_t* quadruplets,
+                        int32_t n_quads, double* tf_out);
+int fc_tfd_first_match(const double* tf, int64_t n, int32_t n_quads, const int64_t* chunk_start,
+                       const int64_t* chunk_len, int64_t n_chunks, double thresh, int64_t* first_out,
+                       fc_tie* ties_out, int64_t tie_cap, int64_t* n_ties_out);
+
 /* Batched torsion rotation with clash filtering: replaces the primitive pair
  * prism_pruner.utils.rotate_dihedral + torsion_module.py:894-918 `torsion_comp_check` (used at
  * torsion_module.py:523-552, 813-856) over every (conformer, torsion, angle) item.

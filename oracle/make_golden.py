@@ -110,5 +110,34 @@ def main():
         print(f"{name}: kept={len(structures)}")
 
 
+def tfd_cases():
+    """Seeded ensembles for the TFD-pruning fixture: (name, n, n_atoms, n_basins, seed)."""
+    return [("tfd_prune_a", 400, 20, 30, 1), ("tfd_prune_b", 1500, 16, 200, 2)]
+
+
+def make_tfd_case(n, n_atoms, n_basins, seed):
+    from firecode_b200 import synthetic
+
+    rng = np.random.default_rng(seed)
+    atoms, structures, _ = synthetic.pruning_ensemble(rng, n, n_atoms, n_basins, jitter=(0.0, 0.08))
+    quads = np.array([rng.choice(n_atoms, 4, replace=False) for _ in range(min(8, n_atoms - 3))], dtype=np.int64)
+    return structures, quads
+
+
+def main_tfd():
+    """prune_conformers_tfd of the UNMODIFIED reference (firecode/torsion_module.py:957-1043)."""
+    loader.install()
+    from firecode.torsion_module import prune_conformers_tfd
+
+    for name, n, n_atoms, n_basins, seed in tfd_cases():
+        structures, quads = make_tfd_case(n, n_atoms, n_basins, seed)
+        _, mask = prune_conformers_tfd(structures, quads)
+        np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), params=np.array([n, n_atoms, n_basins, seed]),
+                            quadruplets=quads, ref_mask=np.asarray(mask, dtype=bool),
+                            checksum=np.float64(structures.sum()))
+        print(f"{name}: kept {int(np.sum(mask))}/{n}")
+
+
 if __name__ == "__main__":
     main()
+    main_tfd()

@@ -628,3 +628,83 @@ def torsion_scan(coords, torsions, masks, angles, thresh=1.5, max_clashes=0):
                 out[ci, ti, ai] = new
                 passed[ci, ti, ai], dmin[ci, ti, ai] = torsion_comp_check(new, tor, np.asarray(mask, dtype=bool), thresh, max_clashes)
     return out, passed, dmin
+
+
+# ------------------------------------------------------------------------------------------------
+# TFD ensemble pruning -- firecode/torsion_module.py:957-1067 (called from embedder.py:1430-1437, the
+# `tfd` branch of similarity_refining, and torsion_module.py:875)
+# ------------------------------------------------------------------------------------------------
+TFD_SCHEDULE = (5e5, 2e5, 1e5, 5e4, 2e4, 1e4, 5000, 2000, 1000, 500, 200, 100, 50, 20, 10, 5, 2, 1)
+
+
+def tf_mat(structures, quadruplets):
+    """torsion_module.py:1046-1053."""
+    return np.array([torsion_fingerprint(s, quadruplets) for s in structures]).reshape(len(structures), len(quadruplets))
+
+
+def tfd_chunks(n, k, num_active):
+    """(start, length) of the k subdivisions of a pass (torsion_module.py:984-991): d = n // k structures
+    each, the LAST one ends at the number of still-active structures (not at n) -- reproduced as is."""
+    d = int(n // k)
+    out = []
+    for step in range(int(k)):
+        if step == k - 1:
+            length = len(range(d * step, num_active))
+        else:
+            length = len(range(d * step, int(d * (step + 1))))
+        out.append((d * step, length))
+    return out
+
+
+def tfd_resolve_chunk(matches):
+    """torsion_module.py:1022-1037: clusters of the match graph, the first node of each cluster (in
+    networkx's iteration order of the sub-graph) survives.  Returns the rejected relative indices."""
+    from networkx import Graph, connected_components
+
+    g = Graph(matches)
+    subgraphs = [g.subgraph(c) for c in connected_components(g)]
+    groups = [tuple(graph.nodes) for graph in subgraphs]
+    best_of_cluster = [group[0] for group in groups]
+    rejects = []
+    for members, best in zip(groups, best_of_cluster):
+        for i in set(members) - {best}:
+            rejects.append(i)
+    return rejects
+
+
+def prune_conformers_tfd(structures, quadruplets, thresh=10, ties=None, first_match=None):
+    """Reference driver of the TFD pruning on plain arrays.  Per chunk every structure i is matched with
+    the FIRST later structure of the chunk whose torsion-difference sum is below ``thresh`` (the cache of
+    known-dissimilar pairs only saves work); masked-out structures still take part (the loops never look
+    at the mask).  ``first_match(tf, chunks) -> (n,) int64`` (absolute index of the first match or -1)
+    replaces the pair loops when given (the CUDA path plugs in here in the parity tests)."""
+    import operator
+
+    ties = ties or Ties()
+    structures = np.asarray(structures, dtype=float)
+    n = len(structures)
+    tf = tf_mat(structures, quadruplets)
+    final_mask = np.ones(n, dtype=bool)
+    for k in TFD_SCHEDULE:
+        num_active = int(np.count_nonzero(final_mask))
+        if not (k == 1 or 5 * k < num_active):
+            continue
+        chunks = tfd_chunks(n, k, num_active)
+        first = None if first_match is None else first_match(tf, chunks)
+        for start, length in chunks:
+            matches = set()
+            for i_rel in range(length):
+                i_abs = i_rel + start
+                if first is not None:
+                    if first[i_abs] >= 0:
+                        matches.add((i_rel, int(first[i_abs]) - start))
+                    continue
+                for j_rel in range(i_rel + 1, length):
+                    j_abs = j_rel + start
+                    if ties.decide(("tfd", j_abs, i_abs), tfd_sum(tf[i_abs], tf[j_abs]), float(thresh), operator.lt):
+                        matches.add((i_rel, j_rel))
+                        break
+            for i in tfd_resolve_chunk(matches):
+                final_mask[i + start] = False
+    return structures[final_mask], final_mask
+
