@@ -475,6 +475,14 @@ def run_extras():
                                    "h2d_bytes": int(structures.nbytes),
                                    "conventions": {"keep": rep.keep, "pass_mode": rep.pass_mode}}
     del structures, kept, mask
+    # TFD ensemble pruning (torsion_module.py:957-1043): 20 000 conformers of a 40-atom molecule, 12 quadruplets
+    rng = np.random.default_rng(synthetic.SEED + 6)
+    atoms, tstruct, _ = synthetic.pruning_ensemble(rng, 20000, 40, 2000, jitter=(0.0, 0.08))
+    quads = np.array([rng.choice(40, 4, replace=False) for _ in range(12)], dtype=np.int64)
+    dt, (tkept, tmask) = timed(lambda: torsion.prune_conformers_tfd(tstruct, quads), reps=1)
+    out["TFD_pruning_20k"] = {"structures_per_s": len(tmask) / dt, "n": len(tmask), "kept": int(tmask.sum()),
+                              "seconds": dt, "note": "fingerprints + first-match searches on the GPU, cluster "
+                                                     "resolution (networkx, as the reference) on the host"}
     # C5: torsion scan, 1 000 conformers x 8 torsions x 36 steps of a 120-atom molecule
     rng = np.random.default_rng(synthetic.SEED + 5)
     atoms, coords, bonds, picks = synthetic.conformer_ensemble(rng, 1000, 120, n_torsions=8)
