@@ -103,6 +103,8 @@ SIGNATURES = {
                                    C.c_int64, c_i64p, C.c_int32, C.c_int32, ALLGATHER_FN, VP]),
     "fc_tfd_fingerprints": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_int32, VP]),
     "fc_tfd_first_match": (C.c_int, [VP, C.c_int64, C.c_int32, VP, VP, C.c_int64, C.c_double, VP, VP, C.c_int64, c_i64p]),
+    "fc_csearch_apply": (C.c_int, [VP, C.c_int32, C.c_int32, VP, C.c_int32, VP, VP, C.c_int64, C.c_double, C.c_int32,
+                                   C.c_int32, VP, VP, VP]),
     "fc_torsion_scan": (C.c_int, [VP, C.c_int32, C.c_int32, VP, C.c_int32, VP, VP, C.c_int32, C.c_double,
                                   C.c_int32, C.c_int32, C.c_int32, VP, VP, VP]),
     "fc_string_n_poses": (C.c_int64, [VP]),

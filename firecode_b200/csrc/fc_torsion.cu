@@ -9,6 +9,8 @@
 //   axis = sign * (x[i2] - x[i3]);  M = rot_mat_from_pointer(axis, angle);
 //   x[mask] = M (x[mask] - x[i3]) + x[i3];
 //   pass <=> #{(s, m): |x_s - x_m| < thresh, m moved, s static and not i2 / i3} <= max_clashes.
+#include <algorithm>
+
 #include "fc_embed.cuh"
 
 namespace fc {
@@ -88,6 +90,110 @@ __global__ void __launch_bounds__(128) torsion_scan_kernel(TorsionArgs p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Conformational-search inner loop: firecode/torsion_module.py:512-552 (random_csearch) = 813-856
+// (clustered_csearch).  One CTA per (starting structure, angle set); the torsions of a set are applied IN
+// ORDER to the running coordinates:
+//     temp = rotate_dihedral(cur, torsion, angle)                       (skipped when angle == 0)
+//     if not torsion_comp_check(temp):  back off 5 degrees at a time, at most angle // 5 times, until the check
+//                                       passes (then the bond counts as rotated)
+//     else: the bond counts as rotated
+//     cur = temp                                                        (also when the back-off never passed)
+// Output: final coordinates and the number of rotated bonds of every item (the drivers keep items with > 0).
+// ---------------------------------------------------------------------------------------------
+struct CsearchArgs {
+    const double* starts;        // (S, N, 3)
+    const int* torsions;         // (T, 4)
+    const unsigned char* masks;  // (T, N)
+    const int* angle_sets;       // (A, T) degrees (integers, Torsion.get_angles)
+    int n_starts, n_atoms, n_tors;
+    long long n_sets;
+    double thresh;
+    int handed, axis_sign;
+    double* out;                 // (S, A, N, 3)
+    int* rotated;                // (S, A)
+    unsigned char* near;         // (S, A) some clash distance met on the way was within FC_NEAR_EPS of thresh
+};
+
+// rotate the masked atoms of x (in shared memory) in place about the i2-i3 axis through i3
+__device__ __forceinline__ void csearch_rotate(double* x, const unsigned char* mask, int n, int i2, int i3, double angle,
+                                               int handed, int axis_sign, M3* s_rot, double* s_origin) {
+    if (threadIdx.x == 0) {
+        double axis[3] = {axis_sign * (x[3 * i2] - x[3 * i3]), axis_sign * (x[3 * i2 + 1] - x[3 * i3 + 1]),
+                          axis_sign * (x[3 * i2 + 2] - x[3 * i3 + 2])};
+        *s_rot = rot_from_pointer(axis, angle, handed);
+        s_origin[0] = x[3 * i3]; s_origin[1] = x[3 * i3 + 1]; s_origin[2] = x[3 * i3 + 2];
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+        if (!mask[a]) continue;
+        double d[3] = {x[3 * a] - s_origin[0], x[3 * a + 1] - s_origin[1], x[3 * a + 2] - s_origin[2]}, r[3];
+        m3_apply(*s_rot, d, r);
+        x[3 * a] = r[0] + s_origin[0]; x[3 * a + 1] = r[1] + s_origin[1]; x[3 * a + 2] = r[2] + s_origin[2];
+    }
+    __syncthreads();
+}
+
+// torsion_comp_check with max_clashes = 0: no (static, moved) pair closer than thresh; bond atoms excluded
+__device__ __forceinline__ bool csearch_check(const double* x, const unsigned char* mask, int n, int i2, int i3, double thresh,
+                                              int* near_flag) {
+    bool clash = false, near = false;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        int s = e / n, m = e - s * n;
+        if (!mask[m] || mask[s] || s == i2 || s == i3) continue;
+        double dx = x[3 * s] - x[3 * m], dy = x[3 * s + 1] - x[3 * m + 1], dz = x[3 * s + 2] - x[3 * m + 2];
+        double d = sqrt(dx * dx + dy * dy + dz * dz);
+        clash = clash || d < thresh;
+        near = near || fabs(d - thresh) <= FC_NEAR_EPS;
+    }
+    if (near) *near_flag = 1;
+    return !__syncthreads_or(clash ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(128) csearch_apply_kernel(CsearchArgs p) {
+    extern __shared__ double s_x[];  // running coordinates (N, 3)
+    __shared__ M3 s_rot;
+    __shared__ double s_origin[3];
+    __shared__ int s_near;
+    const long long item = blockIdx.x;
+    const long long set = item % p.n_sets;
+    const int start = (int)(item / p.n_sets);
+    const int n = p.n_atoms;
+    const double* src = p.starts + (size_t)start * n * 3;
+    for (int e = threadIdx.x; e < n * 3; e += blockDim.x) s_x[e] = src[e];
+    if (threadIdx.x == 0) s_near = 0;
+    __syncthreads();
+    int rotated = 0;
+    for (int t = 0; t < p.n_tors; ++t) {
+        const int angle = p.angle_sets[set * p.n_tors + t];
+        if (angle == 0) continue;  // uniform over the block
+        const int* tor = p.torsions + 4 * t;
+        const unsigned char* mask = p.masks + (size_t)t * n;
+        const int i2 = tor[1], i3 = tor[2];
+        csearch_rotate(s_x, mask, n, i2, i3, (double)angle, p.handed, p.axis_sign, &s_rot, s_origin);
+        if (csearch_check(s_x, mask, n, i2, i3, p.thresh, &s_near)) {
+            ++rotated;
+        } else {
+            // python: range(angle // 5) -- floor division, empty for negative angles
+            const int steps = angle >= 0 ? angle / 5 : 0;
+            for (int b = 0; b < steps; ++b) {
+                csearch_rotate(s_x, mask, n, i2, i3, -5.0, p.handed, p.axis_sign, &s_rot, s_origin);
+                if (csearch_check(s_x, mask, n, i2, i3, p.thresh, &s_near)) {
+                    ++rotated;
+                    break;
+                }
+            }
+        }
+    }
+    double* o = p.out + (size_t)item * n * 3;
+    for (int e = threadIdx.x; e < n * 3; e += blockDim.x) o[e] = s_x[e];
+    if (threadIdx.x == 0) {
+        p.rotated[item] = rotated;
+        p.near[item] = (unsigned char)(s_near ? 1 : 0);
+    }
+}
+
 }  // namespace fc
 
 using namespace fc;
@@ -147,3 +253,66 @@ extern "C" int fc_torsion_scan(const double* coords, int32_t n_conf, int32_t n_a
     cudaStreamDestroy(s);
     return rc;
 }
+
+extern "C" int fc_csearch_apply(const double* starts, int32_t n_starts, int32_t n_atoms, const int32_t* torsions,
+                                int32_t n_tors, const uint8_t* masks, const int32_t* angle_sets, int64_t n_sets,
+                                double thresh, int32_t rot_handedness, int32_t axis_sign, double* out_coords,
+                                int32_t* rotated_out, uint8_t* near_out) {
+    FC_REQUIRE(n_starts >= 0 && n_atoms > 0 && n_tors >= 0 && n_sets >= 0, "fc_csearch_apply: bad sizes");
+    const int64_t items = (int64_t)n_starts * n_sets;
+    if (items == 0) return FC_OK;
+    FC_REQUIRE(items < ((int64_t)1 << 31), "fc_csearch_apply: too many items (%lld)", (long long)items);
+    FC_REQUIRE(starts && out_coords && rotated_out && near_out && (n_tors == 0 || (torsions && masks && angle_sets)),
+               "fc_csearch_apply: null pointer");
+    for (int t = 0; t < n_tors; ++t) {
+        for (int k = 0; k < 4; ++k)
+            FC_REQUIRE(torsions[4 * t + k] >= 0 && torsions[4 * t + k] < n_atoms, "fc_csearch_apply: torsion index out of range");
+        FC_REQUIRE(!masks[(size_t)t * n_atoms + torsions[4 * t + 1]] && !masks[(size_t)t * n_atoms + torsions[4 * t + 2]],
+                   "fc_csearch_apply: the bond atoms of torsion %d must not be in its rotation mask", t);
+    }
+    sm_count();
+    cudaStream_t s;
+    FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int rc = FC_OK;
+    {
+        DevBuf<double> d_starts, d_out;
+        DevBuf<int> d_tors, d_sets, d_rot;
+        DevBuf<unsigned char> d_masks, d_near;
+        cudaError_t e = cudaSuccess;
+#define CS(call) do { if (e == cudaSuccess) e = (call); } while (0)
+        CS(d_starts.alloc((size_t)n_starts * n_atoms * 3, s));
+        CS(cudaMemcpyAsync(d_starts.p, starts, (size_t)n_starts * n_atoms * 24, cudaMemcpyHostToDevice, s));
+        CS(d_tors.alloc((size_t)std::max(n_tors, 1) * 4, s));
+        CS(d_masks.alloc((size_t)std::max(n_tors, 1) * n_atoms, s));
+        CS(d_sets.alloc((size_t)n_sets * std::max(n_tors, 1), s));
+        if (n_tors) {
+            CS(cudaMemcpyAsync(d_tors.p, torsions, (size_t)n_tors * 16, cudaMemcpyHostToDevice, s));
+            CS(cudaMemcpyAsync(d_masks.p, masks, (size_t)n_tors * n_atoms, cudaMemcpyHostToDevice, s));
+            CS(cudaMemcpyAsync(d_sets.p, angle_sets, (size_t)n_sets * n_tors * 4, cudaMemcpyHostToDevice, s));
+        }
+        CS(d_out.alloc((size_t)items * n_atoms * 3, s));
+        CS(d_rot.alloc((size_t)items, s));
+        CS(d_near.alloc((size_t)items, s));
+        if (e == cudaSuccess) {
+            CsearchArgs a{d_starts.p, d_tors.p, d_masks.p, d_sets.p, n_starts, n_atoms, n_tors, (long long)n_sets, thresh,
+                          rot_handedness >= 0 ? 1 : -1, axis_sign >= 0 ? 1 : -1, d_out.p, d_rot.p, d_near.p};
+            size_t smem = (size_t)n_atoms * 24;
+            if (smem > 48 * 1024)
+                CS(cudaFuncSetAttribute(csearch_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (e == cudaSuccess) {
+                csearch_apply_kernel<<<(unsigned)items, 128, smem, s>>>(a);
+                e = cudaGetLastError();
+            }
+        }
+        CS(cudaMemcpyAsync(out_coords, d_out.p, (size_t)items * n_atoms * 24, cudaMemcpyDeviceToHost, s));
+        CS(cudaMemcpyAsync(rotated_out, d_rot.p, (size_t)items * 4, cudaMemcpyDeviceToHost, s));
+        CS(cudaMemcpyAsync(near_out, d_near.p, (size_t)items, cudaMemcpyDeviceToHost, s));
+        CS(cudaStreamSynchronize(s));
+#undef CS
+        if (e != cudaSuccess) rc = cuda_fail(e, "fc_csearch_apply", __FILE__, __LINE__);
+    }
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    return rc;
+}
+

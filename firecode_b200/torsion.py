@@ -177,3 +177,112 @@ def prune_conformers_tfd(structures, quadruplets, thresh=10, verbose=False):
     last_tfd_ties = np.concatenate(all_ties) if all_ties else None
     return structures[final_mask], final_mask
 
+
+# ------------------------------------------------------------------------------------------------
+# conformational search drivers (torsion_module.py:436-586, 726-891)
+# ------------------------------------------------------------------------------------------------
+def csearch_apply(starts, torsions, masks, angle_sets, thresh=1.5):
+    """Inner loop of the csearch drivers (torsion_module.py:512-552 = 813-856), batched on the GPU: every
+    angle set is applied, torsion by torsion with the 5-degree back-off, to every starting structure.
+    Returns (coords (S, A, N, 3), rotated_bonds (S, A) int32, near (S, A) bool)."""
+    lib = _lib.load(require_device=True)
+    x = np.ascontiguousarray(np.asarray(starts, dtype=np.float64))
+    if x.ndim == 2:
+        x = x[None]
+    tors = np.ascontiguousarray(np.asarray(torsions, dtype=np.int32).reshape(-1, 4))
+    m = np.ascontiguousarray(np.asarray(masks, dtype=bool).reshape(len(tors), -1).astype(np.uint8))
+    sets = np.ascontiguousarray(np.asarray(angle_sets, dtype=np.int32).reshape(-1, max(len(tors), 1)))
+    s_, n = x.shape[:2]
+    a = len(sets) if len(tors) else 0
+    out = np.zeros((s_, a, n, 3), dtype=np.float64)
+    rotated = np.zeros((s_, a), dtype=np.int32)
+    near = np.zeros((s_, a), dtype=np.uint8)
+    rc = lib.fc_csearch_apply(_ptr(x), s_, n, _ptr(tors), len(tors), _ptr(m), _ptr(sets), a, float(thresh),
+                              int(conventions.ROT_HANDEDNESS), int(conventions.TORSION_AXIS_SIGN), _ptr(out), _ptr(rotated),
+                              _ptr(near))
+    _lib.check(rc, "fc_csearch_apply")
+    return out, rotated, near.astype(bool)
+
+
+def most_diverse_conformers(n, structures):
+    """torsion_module.py:574-586 ("TEMP: JUST RETURNS THE TOP n STRUCTURES": a sorted random choice)."""
+    if len(structures) <= n:
+        return list(np.array(structures))
+    indices = np.sort(np.random.choice(len(structures), size=n))
+    return list(np.array(structures)[indices])
+
+
+def _torsion_tables(torsions, graph):
+    tors = [tuple(int(i) for i in t.torsion) for t in torsions]
+    return tors, [get_rotation_mask(graph, t) for t in tors]
+
+
+def random_csearch(atoms, coords, torsions, graph, constrained_indices=None, n_out=100, max_tries=10000, rotations=None,
+                   title="test", logfunction=print, interactive_print=True, write_torsions=False, batch=4096):
+    """Drop-in for firecode.torsion_module.random_csearch (torsion_module.py:436-571): the shuffled angle
+    sets are applied in batches on the GPU and consumed in the reference's order, including its stopping
+    rule (the `a == max_tries` test only fires when a structure is appended)."""
+    from .utils import cartesian_product
+
+    if logfunction is not None:
+        logfunction(f"\n--> Random dihedral CSearch on {title}\n    mode 2 (random) - {len(torsions)} torsions")
+    angles = cartesian_product(*[t.get_angles() for t in torsions])
+    if rotations is not None:
+        angles = angles[np.count_nonzero(angles, axis=1) == rotations]
+    np.random.shuffle(angles)  # same call as the reference: identical RNG state -> identical order
+    tors, masks = _torsion_tables(torsions, graph)
+    coords = np.asarray(coords, dtype=np.float64)
+    new_structures = []
+    done = False
+    for lo in range(0, len(angles), batch):
+        out, rotated, _ = csearch_apply(coords, tors, masks, angles[lo:lo + batch])
+        for k in np.flatnonzero(rotated[0] != 0):
+            new_structures.append(out[0, k])
+            if len(new_structures) == n_out or lo + k == max_tries:
+                done = True
+                break
+        if done:
+            break
+    if logfunction is not None:
+        exhaustiveness = len(new_structures) / np.prod([t.n_fold for t in torsions])
+        logfunction(f"  Generated {len(new_structures)} conformers, (est. {round(100 * exhaustiveness, 2)} % of the total "
+                    "conformational space)")
+    return np.array(new_structures)
+
+
+def clustered_csearch(atoms, coords, torsions, graph, charge=0, mult=1, constrained_indices=None, n=100, n_out=100,
+                      title="test", logfunction=print, interactive_print=True, write_torsions=False, debug=False):
+    """Drop-in for firecode.torsion_module.clustered_csearch (torsion_module.py:726-891): all angle sets of
+    the (single) torsion group are applied to every starting point in one GPU call, the starting point itself
+    leads its block as in the reference, then TFD pruning (GPU) and the reference's "most diverse" cut."""
+    from .utils import cartesian_product
+
+    grouped_torsions = [torsions]
+    if logfunction is not None:
+        logfunction(f"\n--> Clustered CSearch on {title}\n    - {len(torsions)} torsions in 1 group - {[len(torsions)]}")
+    output_structures = []
+    starting_points = [np.asarray(coords, dtype=np.float64)]
+    new_structures = []
+    for tg, torsions_group in enumerate(grouped_torsions):
+        angles = cartesian_product(*[t.get_angles() for t in torsions_group])
+        tors, masks = _torsion_tables(torsions_group, graph)
+        out, rotated, _ = csearch_apply(np.array(starting_points), tors, masks, angles)
+        new_structures = []
+        for s_, sp in enumerate(starting_points):
+            new_structures.append(sp)
+            for k in np.flatnonzero(rotated[s_] != 0):
+                new_structures.append(out[s_, k])
+        torsion_array = np.array([t.torsion for t in torsions])
+        if tg + 1 != len(grouped_torsions) and n is not None and len(new_structures) > n:
+            new_structures = most_diverse_conformers(n, new_structures)
+        output_structures.extend(new_structures)
+        starting_points = new_structures
+    output_structures = list(prune_conformers_tfd(np.array(output_structures), torsion_array)[0])
+    if len(new_structures) > n_out:
+        output_structures = most_diverse_conformers(n_out, output_structures)
+    if logfunction is not None:
+        exhaustiveness = len(output_structures) / np.prod([t.n_fold for t in torsions])
+        logfunction(f"  Selected the most diverse {len(output_structures)} conformers, corresponding\n"
+                    f"  to about {round(100 * exhaustiveness, 2)} % of the total conformational space")
+    return np.array(output_structures)
+

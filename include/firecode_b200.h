@@ -293,6 +293,18 @@ int fc_rmsd_and_max_batch(const double* ref, const double* structures, int64_t n
 int fc_self_clash_batch(const double* coords, int64_t n, int32_t n_atoms, const uint8_t* bonded, double thresh,
                         int64_t* close_pairs_out, int64_t* nonbonded_out);
 
+/* Conformational-search inner loop, torsion_module.py:512-552 (random_csearch) = 813-856
+ * (clustered_csearch): for every (starting structure, angle set) the torsions of the set are applied in
+ * order -- rotate_dihedral, torsion_comp_check (thresh, max_clashes = 0), the 5-degree back-off loop
+ * (at most angle // 5 steps) -- to the running coordinates.  Item order: start-major, then angle set.
+ *  starts (n_starts, n_atoms, 3); torsions (n_tors, 4); masks (n_tors, n_atoms); angle_sets (n_sets, n_tors)
+ *  integer degrees; out_coords (items, n_atoms, 3); rotated_out (items) number of bonds that rotated;
+ *  near_out (items) 1 if a distance met on the way was within FC_NEAR_EPS of thresh. */
+int fc_csearch_apply(const double* starts, int32_t n_starts, int32_t n_atoms, const int32_t* torsions,
+                     int32_t n_tors, const uint8_t* masks, const int32_t* angle_sets, int64_t n_sets,
+                     double thresh, int32_t rot_handedness, int32_t axis_sign, double* out_coords,
+                     int32_t* rotated_out, uint8_t* near_out);
+
 /* FP32 FMA-pipe peak probe used by bench.py for the roofline denominator: runs a dependent-free
  * FFMA2 loop on every SM and returns achieved TFLOP/s (2 flop per FMA lane). */
 int fc_probe_fp32_peak(double* tflops_out, double* ms_out, void* stream);

@@ -138,6 +138,61 @@ def main_tfd():
         print(f"{name}: kept {int(np.sum(mask))}/{n}")
 
 
+class DuckTorsion:
+    """The attributes the csearch drivers read from firecode.torsion_module.Torsion (torsion_module.py:139-145)."""
+
+    def __init__(self, torsion, n_fold):
+        self.torsion, self.n_fold = tuple(int(i) for i in torsion), int(n_fold)
+
+    def get_angles(self):
+        return {2: (0, 180), 3: (0, 120, 240), 4: (0, 90, 180, 270), 6: (0, 60, 120, 180, 240, 300)}.get(self.n_fold)
+
+
+def make_csearch_case(n_atoms, n_tors, seed):
+    """(atoms, coords, graph, [(torsion, n_fold)]) of a seeded synthetic molecule."""
+    import networkx as nx
+
+    from firecode_b200 import synthetic
+
+    rng = np.random.default_rng(seed)
+    atoms, cc, bonds, picks = synthetic.conformer_ensemble(rng, 1, n_atoms, n_torsions=n_tors)
+    g = nx.Graph()
+    g.add_nodes_from(range(n_atoms))
+    g.add_edges_from(bonds)
+    tors = []
+    for p_, ch in picks:
+        nb_p = [k for k in g.neighbors(p_) if k != ch]
+        nb_c = [k for k in g.neighbors(ch) if k != p_]
+        if nb_p and nb_c:
+            tors.append(((nb_p[0], p_, ch, nb_c[0]), [3, 2, 4, 6][len(tors) % 4]))
+    return atoms, cc[0], g, tors
+
+
+CSEARCH_CASES = {"csearch_a": (30, 4, 5), "csearch_b": (45, 5, 8)}
+
+
+def main_csearch():
+    """random_csearch / clustered_csearch of the UNMODIFIED reference (torsion_module.py:436-571, 726-891)."""
+    loader.install()
+    from firecode.torsion_module import Torsion, clustered_csearch, random_csearch
+
+    for name, (n_atoms, n_tors, seed) in CSEARCH_CASES.items():
+        atoms, coords, g, tors = make_csearch_case(n_atoms, n_tors, seed)
+        ref_t = []
+        for t, nf in tors:
+            obj = Torsion(*t)
+            obj.n_fold = nf
+            ref_t.append(obj)
+        np.random.seed(seed)
+        rnd = random_csearch(atoms, coords, ref_t, g, n_out=25, logfunction=None, interactive_print=False)
+        np.random.seed(seed)
+        clu = clustered_csearch(atoms, coords, ref_t, g, n=1000, n_out=100000, logfunction=None, interactive_print=False)
+        np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), params=np.array([n_atoms, n_tors, seed]),
+                            random=rnd, clustered=clu, checksum=np.float64(coords.sum()))
+        print(f"{name}: random {rnd.shape}, clustered {clu.shape}")
+
+
 if __name__ == "__main__":
     main()
     main_tfd()
+    main_csearch()

@@ -708,3 +708,51 @@ def prune_conformers_tfd(structures, quadruplets, thresh=10, ties=None, first_ma
                 final_mask[i + start] = False
     return structures[final_mask], final_mask
 
+
+# ------------------------------------------------------------------------------------------------
+# csearch inner loop -- firecode/torsion_module.py:512-552 (random_csearch) = 813-856 (clustered_csearch)
+# ------------------------------------------------------------------------------------------------
+def csearch_apply(start, torsions, masks, angle_set, thresh=1.5):
+    """One angle set applied to one starting structure.  Returns (coords, rotated_bonds, closest) where
+    closest is the smallest |d - thresh| over every clash check made on the way."""
+    import os
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    from prism_pruner.utils import rotate_dihedral
+
+    new_coords = np.copy(np.asarray(start, dtype=float))
+    rotated_bonds = 0
+    closest = np.inf
+
+    def check(x, tor, mask):
+        nonlocal closest
+        _, i2, i3, _ = tor
+        antimask = ~mask
+        antimask[i2] = False
+        antimask[i3] = False
+        d = cdist(x[antimask], x[mask])
+        if d.size:
+            closest = min(closest, float(np.abs(d - thresh).min()))
+        return int(np.count_nonzero(d < thresh)) <= 0   # torsion_module.py:918
+
+    for t, tor in enumerate(torsions):
+        angle = int(angle_set[t])
+        if angle == 0:
+            continue
+        mask = np.asarray(masks[t], dtype=bool)
+        tor = tuple(int(i) for i in tor)
+        temp = rotate_dihedral(new_coords, tor, angle, mask=mask)
+        if not check(temp, tor, mask):
+            for _ in range(angle // 5):
+                temp = rotate_dihedral(temp, tor, -5, mask=mask)
+                if check(temp, tor, mask):
+                    rotated_bonds += 1
+                    break
+        else:
+            rotated_bonds += 1
+        new_coords = temp
+    return new_coords, rotated_bonds, closest
+
