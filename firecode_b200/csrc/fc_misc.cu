@@ -96,6 +96,51 @@ __global__ void __launch_bounds__(256) self_clash_kernel(const double* __restric
     }
 }
 
+// compenetration_check(structure, ids, thresh, max_clashes) (utils.py:544-575) for a batch of complete
+// structures (what RunEmbedding.compenetration_refining loops over, embedder.py:1954-1975): one CTA per
+// structure, FP64 distances as scipy cdist computes them.  Two fragments: #{d < thresh} <= max_clashes.
+// Three fragments: cumulative #{d <= thresh} over (m2,m1), (m3,m2), (m1,m3); the reference returns False as
+// soon as the running count exceeds max_clashes, which is the same as testing the total.
+__global__ void __launch_bounds__(256) structure_clash_kernel(const double* __restrict__ coords, int n_atoms, int n1, int n2,
+                                                              int n3, double thresh, long long* __restrict__ count_out,
+                                                              double* __restrict__ closest_out) {
+    const double* x = coords + (size_t)blockIdx.x * n_atoms * 3;
+    const int b1 = n1, b2 = n1 + n2;
+    long long cnt = 0;
+    double closest = 1e300;
+    // pair blocks as (rows, cols): two fragments -> (m2, m1); three -> (m2, m1), (m3, m2), (m1, m3)
+    const int n_blocks = n3 > 0 ? 3 : 1;
+    for (int blk = 0; blk < n_blocks; ++blk) {
+        int r0, r1, c0, c1;
+        if (blk == 0) { r0 = b1; r1 = b2; c0 = 0; c1 = b1; }
+        else if (blk == 1) { r0 = b2; r1 = n_atoms; c0 = b1; c1 = b2; }
+        else { r0 = 0; r1 = b1; c0 = b2; c1 = n_atoms; }
+        const int nr = r1 - r0, nc = c1 - c0;
+        for (long long e = threadIdx.x; e < (long long)nr * nc; e += blockDim.x) {
+            const int i = r0 + (int)(e / nc), j = c0 + (int)(e % nc);
+            const double dx = x[3 * i] - x[3 * j], dy = x[3 * i + 1] - x[3 * j + 1], dz = x[3 * i + 2] - x[3 * j + 2];
+            const double d = sqrt(dx * dx + dy * dy + dz * dz);
+            cnt += (n3 > 0 ? d <= thresh : d < thresh) ? 1 : 0;
+            closest = fmin(closest, fabs(d - thresh));
+        }
+    }
+    __shared__ long long s_c[8];
+    __shared__ double s_m[8];
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        closest = fmin(closest, __shfl_xor_sync(0xffffffffu, closest, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5] = cnt; s_m[threadIdx.x >> 5] = closest; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long c = 0;
+        double m = 1e300;
+        for (int w = 0; w < 8; ++w) { c += s_c[w]; m = fmin(m, s_m[w]); }
+        count_out[blockIdx.x] = c;
+        closest_out[blockIdx.x] = m;
+    }
+}
+
 }  // namespace fc
 
 using namespace fc;
@@ -167,3 +212,44 @@ extern "C" int fc_self_clash_batch(const double* coords, int64_t n, int32_t n_at
     if (e != cudaSuccess) return cuda_fail(e, "fc_self_clash_batch", __FILE__, __LINE__);
     return FC_OK;
 }
+
+extern "C" int fc_structure_clash_batch(const double* coords, int64_t n, int32_t n_atoms, const int32_t* ids, int32_t n_ids,
+                                        double thresh, int64_t* count_out, double* closest_out) {
+    FC_REQUIRE(n >= 0 && n_atoms > 0 && n < ((int64_t)1 << 31), "fc_structure_clash_batch: bad sizes");
+    FC_REQUIRE(ids && (n_ids == 2 || n_ids == 3), "fc_structure_clash_batch: ids must name two or three fragments");
+    int tot = 0;
+    for (int k = 0; k < n_ids; ++k) {
+        FC_REQUIRE(ids[k] > 0, "fc_structure_clash_batch: empty fragment");
+        tot += ids[k];
+    }
+    FC_REQUIRE(tot == n_atoms, "fc_structure_clash_batch: ids sum to %d, structures have %d atoms", tot, n_atoms);
+    if (n == 0) return FC_OK;
+    FC_REQUIRE(coords && count_out && closest_out, "fc_structure_clash_batch: null pointer");
+    sm_count();
+    cudaStream_t s;
+    FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaError_t e = cudaSuccess;
+    {
+        DevBuf<double> d_x, d_m;
+        DevBuf<long long> d_c;
+#define MS(call) do { if (e == cudaSuccess) e = (call); } while (0)
+        MS(d_x.alloc((size_t)n * n_atoms * 3, s));
+        MS(d_c.alloc((size_t)n, s));
+        MS(d_m.alloc((size_t)n, s));
+        MS(cudaMemcpyAsync(d_x.p, coords, (size_t)n * n_atoms * 24, cudaMemcpyHostToDevice, s));
+        if (e == cudaSuccess) {
+            structure_clash_kernel<<<(unsigned)n, 256, 0, s>>>(d_x.p, n_atoms, ids[0], ids[1], n_ids == 3 ? ids[2] : 0, thresh,
+                                                              d_c.p, d_m.p);
+            e = cudaGetLastError();
+        }
+        MS(cudaMemcpyAsync(count_out, d_c.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        MS(cudaMemcpyAsync(closest_out, d_m.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        MS(cudaStreamSynchronize(s));
+#undef MS
+    }
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    if (e != cudaSuccess) return cuda_fail(e, "fc_structure_clash_batch", __FILE__, __LINE__);
+    return FC_OK;
+}
+

@@ -90,8 +90,6 @@ def compenetration_check(coords, graph=None, ids=None, thresh=1.0, max_clashes=0
     ids of length 2: ``#{|m2_j - m1_i| < thresh} <= max_clashes`` (utils.py:544-551);
     ids of length 3: the three blocks (m2,m1), (m3,m2), (m1,m3) with ``<=`` (utils.py:553-575).
     The hot path never calls this per pose -- the screens batch it (firecode_b200.clash)."""
-    from .clash import compenetration_check_batch
-
     coords = np.ascontiguousarray(np.asarray(coords, dtype=np.float64))
     if ids is None:
         # not fragment-based (utils.py:523-542): quick count of pairs closer than 0.5 A, then -- given
@@ -111,18 +109,25 @@ def compenetration_check(coords, graph=None, ids=None, thresh=1.0, max_clashes=0
         if graph is None:
             return True
         return not (nonbonded[0] > max_clashes)
-    eye = np.array([[1.0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]])
-    if len(ids) == 2:
-        m1, m2 = coords[: ids[0]], coords[ids[0]:]
-        return bool(compenetration_check_batch(m1, m2, eye, thresh=thresh, max_clashes=max_clashes).mask[0])
-    if max_clashes != 0:
-        raise NotImplementedError("firecode_b200: trimolecular clash test with max_clashes > 0 is not built")
-    n1, n2 = ids[0], ids[0] + ids[1]
-    m1, m2, m3 = coords[:n1], coords[n1:n2], coords[n2:]
-    for a, b in ((m1, m2), (m2, m3), (m3, m1)):
-        if not compenetration_check_batch(a, b, eye, thresh=thresh, max_clashes=0, strict=False).mask[0]:
-            return False
-    return True
+    return bool(compenetration_check_structures(coords[None], ids, thresh=thresh, max_clashes=max_clashes)[0])
+
+
+def compenetration_check_structures(structures, ids, thresh=1.0, max_clashes=0, return_closest=False):
+    """``compenetration_check(structure, ids=ids, thresh, max_clashes)`` for every structure of a batch in one
+    GPU call: the loop of RunEmbedding.compenetration_refining (embedder.py:1954-1975).  Returns the bool mask
+    (and, on request, min |d - thresh| per structure)."""
+    from . import _lib
+
+    lib = _lib.load(require_device=True)
+    x = np.ascontiguousarray(np.asarray(structures, dtype=np.float64))
+    assert x.ndim == 3 and x.shape[2] == 3
+    idv = np.ascontiguousarray(np.asarray(ids, dtype=np.int32).ravel())
+    counts = np.zeros(len(x), dtype=np.int64)
+    closest = np.zeros(len(x), dtype=np.float64)
+    _lib.check(lib.fc_structure_clash_batch(x.ctypes.data, len(x), x.shape[1], idv.ctypes.data, len(idv), float(thresh),
+                                            counts.ctypes.data, closest.ctypes.data), "fc_structure_clash_batch")
+    mask = counts <= max_clashes
+    return (mask, closest) if return_closest else mask
 
 
 def rmsd_similarity(ref, structures, rmsd_thr=0.5):

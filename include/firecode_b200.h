@@ -305,6 +305,13 @@ int fc_csearch_apply(const double* starts, int32_t n_starts, int32_t n_atoms, co
                      double thresh, int32_t rot_handedness, int32_t axis_sign, double* out_coords,
                      int32_t* rotated_out, uint8_t* near_out);
 
+/* compenetration_check(structure, ids, thresh, max_clashes) (utils.py:544-575) for n complete structures --
+ * the loop of RunEmbedding.compenetration_refining (embedder.py:1954-1975).  ids: atoms per fragment (2 or 3).
+ * count_out[s] = clashing pairs (two fragments: d < thresh over (m2, m1); three: d <= thresh summed over
+ * (m2,m1), (m3,m2), (m1,m3)); the structure passes iff count <= max_clashes.  closest_out[s] = min |d - thresh|. */
+int fc_structure_clash_batch(const double* coords, int64_t n, int32_t n_atoms, const int32_t* ids, int32_t n_ids,
+                             double thresh, int64_t* count_out, double* closest_out);
+
 /* FP32 FMA-pipe peak probe used by bench.py for the roofline denominator: runs a dependent-free
  * FFMA2 loop on every SM and returns achieved TFLOP/s (2 flop per FMA lane). */
 int fc_probe_fp32_peak(double* tflops_out, double* ms_out, void* stream);

@@ -253,3 +253,20 @@ def test_cell_list_path_edge_geometries(gpu, monkeypatch):
     assert compenetration_check_batch(a40, b, far, thresh=1.5).mask.all()
     on_top = np.tile(np.array([[1.0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0]]), (64, 1))
     assert not compenetration_check_batch(a40, a40, on_top, thresh=1.5).mask.any()
+
+
+def test_structure_form_batch(gpu):
+    """utils.compenetration_check_structures == the reference loop of compenetration_refining
+    (embedder.py:1954-1975) over complete structures, two and three fragments, with max_clashes."""
+    from firecode_b200.utils import compenetration_check_structures
+
+    rng = np.random.default_rng(17)
+    structures = rng.normal(scale=2.6, size=(400, 33, 3))
+    for ids in ((15, 18), (10, 12, 11)):
+        for mc in (0, 1, 4):
+            mask, closest = compenetration_check_structures(structures, ids, thresh=1.3, max_clashes=mc, return_closest=True)
+            ref = np.array([port.compenetration_check(s, ids=ids, thresh=1.3, max_clashes=mc) for s in structures])
+            safe = closest > 1e-6
+            assert np.array_equal(mask[safe], ref[safe])
+            assert 0 < mask.sum() < len(mask) or mc == 4
+    assert compenetration_check_structures(structures[:0], (15, 18)).shape == (0,)
