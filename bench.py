@@ -363,9 +363,17 @@ def run_cuda(args):
         "note": "every atom pair evaluated (Gram form: 3 FMA + half an FMNMX3 per pair = 4 issue cycles per pair per "
                 "lane, so frac = 1.0 is this formulation's ceiling and the FMA pipe cannot exceed 75 %); run with "
                 "FC_CLASH_MODE=0 on the same poses, same status bytes"}
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_clash_cell_traffic.json" if cell_path else "r01_clash_allpairs_traffic.json")
+    if os.path.isfile(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic = (tj["dram_read_bytes"] + tj["dram_write_bytes"]) / tj["poses"] * n_poses
+        traffic_src = f"{os.path.relpath(tpath, ROOT)}: ncu --set full capture of {tj['poses']} poses, scaled per pose"
     roofline = {
         "bound": "fp32", "kernel": "fc::clash_cell_kernel" if cell_path else "fc::clash_f32_kernel",
-        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
+        "traffic_source": traffic_src, "algorithmic_bytes": n_poses * 97.0,
         "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x sm_max_mhz ({peak_kind} MEASURED_PEAKS.json clock); no FP32 figure in MEASURED_PEAKS.json",
         "algorithmic_flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs, "kernel_ms": kernel_ms,
         "fp32_probe_tflops": probe_tf.value,
