@@ -167,8 +167,10 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(walls) * 1e3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "C3 compenetration sweep: poses of two 150-atom fragments, thresh 1.5 A",
-                   "poses_per_step": n_sample, "n_atoms": [N_ATOMS, N_ATOMS]},
+        "config": {"workload": "C3 compenetration sweep: 10M candidate poses of two 150-atom fragments per GPU, thresh 1.5 A",
+                   "sample_poses_per_step": n_sample, "n_atoms": [N_ATOMS, N_ATOMS],
+                   "note": "each step screens a bounded sample of the same sweep (same fragments, same pose "
+                           "distribution) with the reference's per-pose arithmetic on all host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n_sample} poses per step of the C3 sweep, per-pose "
                                    "get_embed + scipy cdist compenetration_check (oracle/port.py), "
