@@ -10,6 +10,7 @@
 //   x[mask] = M (x[mask] - x[i3]) + x[i3];
 //   pass <=> #{(s, m): |x_s - x_m| < thresh, m moved, s static and not i2 / i3} <= max_clashes.
 #include <algorithm>
+#include <vector>
 
 #include "fc_embed.cuh"
 
@@ -26,6 +27,8 @@ struct TorsionArgs {
     double* out_coords;          // (C, T, A, N, 3) or null
     unsigned char* status;       // (C, T, A) FC_STATUS_*
     double* min_dist;            // (C, T, A) or null
+    const short* lists;          // (T, 2, N): moved atoms, then static atoms without i2 / i3 (compacted)
+    const int* list_len;         // (T, 2)
 };
 
 __global__ void __launch_bounds__(128) torsion_scan_kernel(TorsionArgs p) {
@@ -61,13 +64,16 @@ __global__ void __launch_bounds__(128) torsion_scan_kernel(TorsionArgs p) {
         double* o = p.out_coords + (size_t)item * p.n_atoms * 3;
         for (int e = threadIdx.x; e < p.n_atoms * 3; e += blockDim.x) o[e] = sx[e];
     }
-    // clash count between moved atoms and static atoms (bond atoms i2, i3 excluded)
+    // clash count between moved atoms and static atoms (bond atoms i2, i3 excluded): only those pairs are
+    // visited, through the per-torsion compacted index lists
     int clashes = 0;
     double dmin = 1e300;
     const int n = p.n_atoms;
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-        int s = e / n, m = e - s * n;
-        if (!mask[m] || mask[s] || s == i2 || s == i3) continue;
+    const short* moved = p.lists + (size_t)t * 2 * n;
+    const short* stat = moved + n;
+    const int n_m = p.list_len[2 * t], n_s = p.list_len[2 * t + 1];
+    for (int e = threadIdx.x; e < n_m * n_s; e += blockDim.x) {
+        const int s = stat[e / n_m], m = moved[e % n_m];
         double dx = sx[3 * s] - sx[3 * m], dy = sx[3 * s + 1] - sx[3 * m + 1], dz = sx[3 * s + 2] - sx[3 * m + 2];
         double d = sqrt(dx * dx + dy * dy + dz * dz);
         clashes += d < p.thresh ? 1 : 0;
@@ -206,6 +212,7 @@ extern "C" int fc_torsion_scan(const double* coords, int32_t n_conf, int32_t n_a
     const int64_t items = (int64_t)n_conf * n_tors * n_angles;
     if (items == 0) return FC_OK;
     FC_REQUIRE(items < ((int64_t)1 << 31), "fc_torsion_scan: too many items (%lld)", (long long)items);
+    FC_REQUIRE(n_atoms < 32768, "fc_torsion_scan: more than 32767 atoms");
     FC_REQUIRE(coords && torsions && masks && angles && status_out, "fc_torsion_scan: null pointer");
     for (int t = 0; t < n_tors * 4; ++t)
         FC_REQUIRE(torsions[t] >= 0 && torsions[t] < n_atoms, "fc_torsion_scan: torsion index out of range");
@@ -227,13 +234,33 @@ extern "C" int fc_torsion_scan(const double* coords, int32_t n_conf, int32_t n_a
         TS(cudaMemcpyAsync(d_masks.p, masks, (size_t)n_tors * n_atoms, cudaMemcpyHostToDevice, s));
         TS(d_angles.alloc(n_angles, s));
         TS(cudaMemcpyAsync(d_angles.p, angles, (size_t)n_angles * 8, cudaMemcpyHostToDevice, s));
+        std::vector<short> h_lists((size_t)std::max(n_tors, 1) * 2 * n_atoms, 0);
+        std::vector<int> h_len((size_t)std::max(n_tors, 1) * 2, 0);
+        for (int t = 0; t < n_tors; ++t) {
+            const int i2 = torsions[4 * t + 1], i3 = torsions[4 * t + 2];
+            short* moved = h_lists.data() + (size_t)t * 2 * n_atoms;
+            short* stat = moved + n_atoms;
+            int nm = 0, ns = 0;
+            for (int a = 0; a < n_atoms; ++a) {
+                if (masks[(size_t)t * n_atoms + a]) moved[nm++] = (short)a;
+                else if (a != i2 && a != i3) stat[ns++] = (short)a;
+            }
+            h_len[2 * t] = nm;
+            h_len[2 * t + 1] = ns;
+        }
+        DevBuf<short> d_lists;
+        DevBuf<int> d_len;
+        TS(d_lists.alloc(h_lists.size(), s));
+        TS(d_len.alloc(h_len.size(), s));
+        TS(cudaMemcpyAsync(d_lists.p, h_lists.data(), h_lists.size() * sizeof(short), cudaMemcpyHostToDevice, s));
+        TS(cudaMemcpyAsync(d_len.p, h_len.data(), h_len.size() * sizeof(int), cudaMemcpyHostToDevice, s));
         TS(d_status.alloc((size_t)items, s));
         if (out_coords) TS(d_out.alloc((size_t)items * n_atoms * 3, s));
         if (min_dist_out) TS(d_min.alloc((size_t)items, s));
         if (e == cudaSuccess) {
             TorsionArgs a{d_coords.p, d_tors.p, d_masks.p, d_angles.p, n_conf, n_atoms, n_tors, n_angles, thresh,
                           max_clashes, rot_handedness >= 0 ? 1 : -1, axis_sign >= 0 ? 1 : -1,
-                          out_coords ? d_out.p : nullptr, d_status.p, min_dist_out ? d_min.p : nullptr};
+                          out_coords ? d_out.p : nullptr, d_status.p, min_dist_out ? d_min.p : nullptr, d_lists.p, d_len.p};
             size_t smem = (size_t)n_atoms * 24;
             if (smem > 48 * 1024)
                 TS(cudaFuncSetAttribute(torsion_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
