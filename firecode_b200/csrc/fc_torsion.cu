@@ -117,6 +117,8 @@ struct CsearchArgs {
     long long n_sets;
     double thresh;
     int handed, axis_sign;
+    const short* lists;          // (T, 2, N): moved atoms, then static atoms without i2 / i3 (compacted)
+    const int* list_len;         // (T, 2)
     double* out;                 // (S, A, N, 3)
     int* rotated;                // (S, A)
     unsigned char* near;         // (S, A) some clash distance met on the way was within FC_NEAR_EPS of thresh
@@ -142,12 +144,11 @@ __device__ __forceinline__ void csearch_rotate(double* x, const unsigned char* m
 }
 
 // torsion_comp_check with max_clashes = 0: no (static, moved) pair closer than thresh; bond atoms excluded
-__device__ __forceinline__ bool csearch_check(const double* x, const unsigned char* mask, int n, int i2, int i3, double thresh,
-                                              int* near_flag) {
+__device__ __forceinline__ bool csearch_check(const double* x, const short* moved, int n_m, const short* stat, int n_s,
+                                              double thresh, int* near_flag) {
     bool clash = false, near = false;
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-        int s = e / n, m = e - s * n;
-        if (!mask[m] || mask[s] || s == i2 || s == i3) continue;
+    for (int e = threadIdx.x; e < n_m * n_s; e += blockDim.x) {
+        const int s = stat[e / n_m], m = moved[e % n_m];
         double dx = x[3 * s] - x[3 * m], dy = x[3 * s + 1] - x[3 * m + 1], dz = x[3 * s + 2] - x[3 * m + 2];
         double d = sqrt(dx * dx + dy * dy + dz * dz);
         clash = clash || d < thresh;
@@ -177,15 +178,18 @@ __global__ void __launch_bounds__(128) csearch_apply_kernel(CsearchArgs p) {
         const int* tor = p.torsions + 4 * t;
         const unsigned char* mask = p.masks + (size_t)t * n;
         const int i2 = tor[1], i3 = tor[2];
+        const short* moved = p.lists + (size_t)t * 2 * n;
+        const short* stat = moved + n;
+        const int n_m = p.list_len[2 * t], n_s = p.list_len[2 * t + 1];
         csearch_rotate(s_x, mask, n, i2, i3, (double)angle, p.handed, p.axis_sign, &s_rot, s_origin);
-        if (csearch_check(s_x, mask, n, i2, i3, p.thresh, &s_near)) {
+        if (csearch_check(s_x, moved, n_m, stat, n_s, p.thresh, &s_near)) {
             ++rotated;
         } else {
             // python: range(angle // 5) -- floor division, empty for negative angles
             const int steps = angle >= 0 ? angle / 5 : 0;
             for (int b = 0; b < steps; ++b) {
                 csearch_rotate(s_x, mask, n, i2, i3, -5.0, p.handed, p.axis_sign, &s_rot, s_origin);
-                if (csearch_check(s_x, mask, n, i2, i3, p.thresh, &s_near)) {
+                if (csearch_check(s_x, moved, n_m, stat, n_s, p.thresh, &s_near)) {
                     ++rotated;
                     break;
                 }
@@ -289,6 +293,7 @@ extern "C" int fc_csearch_apply(const double* starts, int32_t n_starts, int32_t 
     const int64_t items = (int64_t)n_starts * n_sets;
     if (items == 0) return FC_OK;
     FC_REQUIRE(items < ((int64_t)1 << 31), "fc_csearch_apply: too many items (%lld)", (long long)items);
+    FC_REQUIRE(n_atoms < 32768, "fc_csearch_apply: more than 32767 atoms");
     FC_REQUIRE(starts && out_coords && rotated_out && near_out && (n_tors == 0 || (torsions && masks && angle_sets)),
                "fc_csearch_apply: null pointer");
     for (int t = 0; t < n_tors; ++t) {
@@ -317,12 +322,32 @@ extern "C" int fc_csearch_apply(const double* starts, int32_t n_starts, int32_t 
             CS(cudaMemcpyAsync(d_masks.p, masks, (size_t)n_tors * n_atoms, cudaMemcpyHostToDevice, s));
             CS(cudaMemcpyAsync(d_sets.p, angle_sets, (size_t)n_sets * n_tors * 4, cudaMemcpyHostToDevice, s));
         }
+        std::vector<short> h_lists((size_t)std::max(n_tors, 1) * 2 * n_atoms, 0);
+        std::vector<int> h_len((size_t)std::max(n_tors, 1) * 2, 0);
+        for (int t = 0; t < n_tors; ++t) {
+            const int i2 = torsions[4 * t + 1], i3 = torsions[4 * t + 2];
+            short* moved = h_lists.data() + (size_t)t * 2 * n_atoms;
+            short* stat = moved + n_atoms;
+            int nm = 0, ns = 0;
+            for (int a = 0; a < n_atoms; ++a) {
+                if (masks[(size_t)t * n_atoms + a]) moved[nm++] = (short)a;
+                else if (a != i2 && a != i3) stat[ns++] = (short)a;
+            }
+            h_len[2 * t] = nm;
+            h_len[2 * t + 1] = ns;
+        }
+        DevBuf<short> d_lists;
+        DevBuf<int> d_len;
+        CS(d_lists.alloc(h_lists.size(), s));
+        CS(d_len.alloc(h_len.size(), s));
+        CS(cudaMemcpyAsync(d_lists.p, h_lists.data(), h_lists.size() * sizeof(short), cudaMemcpyHostToDevice, s));
+        CS(cudaMemcpyAsync(d_len.p, h_len.data(), h_len.size() * sizeof(int), cudaMemcpyHostToDevice, s));
         CS(d_out.alloc((size_t)items * n_atoms * 3, s));
         CS(d_rot.alloc((size_t)items, s));
         CS(d_near.alloc((size_t)items, s));
         if (e == cudaSuccess) {
             CsearchArgs a{d_starts.p, d_tors.p, d_masks.p, d_sets.p, n_starts, n_atoms, n_tors, (long long)n_sets, thresh,
-                          rot_handedness >= 0 ? 1 : -1, axis_sign >= 0 ? 1 : -1, d_out.p, d_rot.p, d_near.p};
+                          rot_handedness >= 0 ? 1 : -1, axis_sign >= 0 ? 1 : -1, d_lists.p, d_len.p, d_out.p, d_rot.p, d_near.p};
             size_t smem = (size_t)n_atoms * 24;
             if (smem > 48 * 1024)
                 CS(cudaFuncSetAttribute(csearch_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
