@@ -38,12 +38,14 @@ def test_struct_layouts_match_header_sizes(tmp_path):
     from firecode_b200 import _lib
 
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "firecode_b200.h"\nint main(void){printf("%zu %zu %zu\\n",'
-                   'sizeof(fc_tie), sizeof(fc_string_problem), sizeof(fc_cyclical_problem));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "firecode_b200.h"\nint main(void){printf("%zu %zu %zu %zu\\n",'
+                   'sizeof(fc_tie), sizeof(fc_string_problem), sizeof(fc_cyclical_problem), sizeof(fc_cyclical3_problem));'
+                   'return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    assert sizes == [ctypes.sizeof(_lib.Tie), ctypes.sizeof(_lib.StringProblemC), ctypes.sizeof(_lib.CyclicalProblemC)]
+    assert sizes == [ctypes.sizeof(_lib.Tie), ctypes.sizeof(_lib.StringProblemC), ctypes.sizeof(_lib.CyclicalProblemC),
+                     ctypes.sizeof(_lib.Cyclical3ProblemC)]
 
 
 def test_product_never_imports_the_oracle():
