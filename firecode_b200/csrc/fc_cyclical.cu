@@ -317,7 +317,13 @@ extern "C" int fc_cyclical_screen(const fc_cyclical_problem* p, fc_result** out)
             FC_REQUIRE(p->group_conf[2 * g + m] >= 0 && p->group_conf[2 * g + m] < p->n_conf[m], "group conformer out of range");
     sm_count();
     cudaStream_t s;
-    FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    {
+        cudaError_t se = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        if (se != cudaSuccess) {
+            fc_result_free(r);
+            return cuda_fail(se, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
+        }
+    }
     int rc = FC_OK;
     std::vector<uint8_t> h_status, h_keep;
     std::vector<int64_t> kept;

@@ -832,7 +832,13 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
 
     sm_count();
     cudaStream_t s;
-    FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    {
+        cudaError_t se = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        if (se != cudaSuccess) {
+            fc_result_free(r);
+            return cuda_fail(se, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
+        }
+    }
     int rc = FC_OK;
     const bool want_status = !(p->flags & FC_CYC3_NO_STATUS), want_coords = !(p->flags & FC_CYC3_NO_COORDS);
     if (want_status) r->status.resize((size_t)(G * A));
