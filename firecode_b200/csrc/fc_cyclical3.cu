@@ -908,7 +908,10 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
             rc = fc_clash_prepare_dev(d_coords[k].p, p->n_conf[k], p->n_atoms[k], p->thresh, 1, &prep[k], (void*)s);
 
         // ---- chunks of whole super-groups ------------------------------------------------------
-        const int64_t max_chunk_groups = std::max<int64_t>(64, ((int64_t)12 << 20) / A);  // ~12 M poses per chunk
+        // poses per chunk (FC_CYC3_CHUNK_POSES overrides): device buffers are ~20 B per pose + 96 B per pair-pose
+        int64_t chunk_poses = (int64_t)12 << 20;
+        if (const char* v = getenv("FC_CYC3_CHUNK_POSES")) chunk_poses = std::max<int64_t>(1 << 16, atoll(v));
+        const int64_t max_chunk_groups = std::max<int64_t>(64, chunk_poses / A);
         size_t sg_lo = 0;
         std::vector<uint8_t> h_status, h_keep, h_st;
         while (!rc && sg_lo < supers.size()) {
