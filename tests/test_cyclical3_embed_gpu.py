@@ -109,3 +109,28 @@ def test_trimolecular_many_survivors_per_group(gpu):
     per_group = np.bincount(ref["kept"] // len(prob.angles), minlength=len(ref["groups"]))
     assert per_group.max() > 32, per_group
     assert rep.n_clash_pass > rep.n_kept > 0
+
+
+@pytest.mark.parametrize("internal_as_array", [True, False])
+def test_trimolecular_pairing_filter(gpu, internal_as_array):
+    """User pairings restrict the orientations (embeds.py:473-476); a pairing that is an internal constraint
+    only counts when internal_constraints is NOT an ndarray (quirk N10, embeds.py:820-826)."""
+    emb = make_embedder("cyclical", n_mols=3, n_conf=[2, 2, 1], n_atoms=14, seed=5, n_reactive=2, n_orb=1)
+    base = problem.cyclical_problem(emb)
+    supers = port.cyclical_groups_trimol(base)
+    assert supers
+    couple = tuple(int(x) for x in supers[0]["ids"][0][0])      # a couple of orientation 0
+    bogus = (0, 1)                                           # never a couple between two molecules
+    emb.pairings_table = {"a": couple, "b": bogus}
+    emb.internal_constraints = np.array([bogus]) if internal_as_array else [bogus]
+    prob = problem.cyclical_problem(emb)
+    poses, constrained, rep = embeds.cyclical3_screen(prob)
+    ref = port.cyclical_embed_trimol(prob, ties=port.Ties(eps=1e-6, forced=rep.forced_decisions()))
+    assert len(ref["groups"]) == len(rep.group_choice)
+    if internal_as_array:
+        assert rep.n_poses == 0          # the bogus pairing can never be satisfied
+    else:
+        assert 0 < len(rep.group_choice) < 8 * len(supers)
+        assert np.array_equal(rep.kept_indices, ref["kept"])
+        assert np.array_equal(constrained, ref["constrained"])
+        assert all(couple in [tuple(c) for c in g["ids"]] for g in ref["groups"])
