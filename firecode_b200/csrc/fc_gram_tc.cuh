@@ -1,0 +1,360 @@
+// firecode_b200 -- tensor-core screen of the similarity pruning (tcgen05 / TMEM, sm_100a).
+//
+// The pair covariance of the Kabsch RMSD,  H(i, j)[a][b] = sum_k x_i[k][a] * x_j[k][b]  (centred heavy
+// atoms; what prism_pruner.rmsd.rmsd_and_max contracts per pair, call sites
+// /root/reference/firecode/embedder.py:1472, ensemble.py:230), over all pairs of a chunk IS a Gram
+// matrix: rows (structure, component), K = atoms.  gram_tc_kernel computes it on the 5th-generation
+// tensor cores in TF32 with FP32 accumulation in tensor memory and turns each 3x3 block into a
+// screening decision in the epilogue; pairs it cannot rule out go to the FP64 exact kernel, so the
+// kept set does not depend on TF32 rounding (the screen widens its band by a rigorous bound on it).
+//
+// Operand image (written per pass by gram_pack_kernel, read by 1-D bulk async copies): the active
+// structures of the pass sit at "padded positions" (every chunk starts at a multiple of 16); 8
+// consecutive positions form a group stored as [component a][k-core c][row r][4 floats] = the
+// no-swizzle K-major core-matrix layout of a UMMA shared-memory descriptor (core matrix = 8 rows x
+// 16 bytes).  The same bytes serve as operand A (M = 128 positions of one component: 16 groups,
+// stride 3 * kc * 128 B) and as operand B (N = 48 = 16 positions x 3 components: 6 row groups,
+// stride kc * 128 B), so a tile is one contiguous copy.
+//
+// CTA = 320 threads, one per SM, persistent over work items (128-row block x range of 16-column
+// tiles): warp 0 = copy producer (A once per item, B tiles through a 4-stage ring), warp 1 = MMA
+// issuer (3 components x kc / 2 k-steps of tcgen05.mma M128 N48 K8 per tile, two accumulator stages in
+// TMEM), warps 2-9 = epilogue (tcgen05.ld of 8 pairs' 3x3 blocks per thread, Frobenius bound, closed
+// form singular values for the few pairs that survive it).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fc {
+
+struct GramWork {
+    int row0;         // first padded position of the 128-row block (multiple of 8)
+    int col_tile0;    // first column tile; tile t covers positions [16 t, 16 t + 16)
+    int n_col_tiles;
+    int pend;         // end of the chunk (padded position): a pair needs prow < pcol < pend
+};
+
+struct GramArgs {
+    const float* img;         // operand image, (n_pos / 8) groups x 3 x kc x 8 x 4 floats
+    const float* gp;          // (n_pos) sum |x|^2 of the structure at the position, 0 for padding
+    const int* spos;          // (n_pos) structure index at the position, -1 for padding
+    const double* energies;   // (n structures) or null
+    double max_dE;
+    const GramWork* work;
+    int n_work;
+    int kc;                   // 16-byte k-cores per row (even, <= 24): atoms padded to 4 * kc
+    float thr_e;              // (max_rmsd + band)^2 * nh
+    float e0_scale;           // 1 - sqrt(3) * (bound on the relative TF32 product error)
+    int2* cand;               // pairs the screen could not rule out (structure indices, x < y)
+    unsigned long long* n_cand;
+    long long cand_cap;
+    float* dump;              // debug: H of every (prow, pcol) visited, [prow][dump_ld][9]; null in production
+    int dump_ld;
+    int* error;               // set when a barrier wait times out (the kernel then traps)
+};
+
+constexpr int kGramThreads = 320;
+constexpr int kGramBStages = 4;
+constexpr int kGramMaxKc = 24;
+// Relative bound on |H_tf32 - H|_F / (|p| |q|): operands are rounded to nearest TF32 (2^-11 each, so 2^-10 on a
+// product, Cauchy-Schwarz over the atoms); doubled to cover the accumulation inside the tensor core.  Measured on
+// random ensembles: 1.1e-4 (tools/gram_tc_test.cu).
+constexpr float kGramTf32Eps = 1.0f / 512.0f;
+
+__host__ __device__ inline size_t gram_smem_bytes(int kc) {
+    return (size_t)6144 * kc + (size_t)kGramBStages * 768 * kc + 256;
+}
+
+// ---- PTX plumbing -----------------------------------------------------------------------------------
+namespace gram {
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// bounded wait: a protocol error ends in a trap (reported through *error), never in a hung GPU
+__device__ __forceinline__ void bar_wait(unsigned bar, unsigned parity, int* error, int code) {
+    for (unsigned spin = 0; spin < (1u << 22); ++spin) {
+        unsigned ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    if (error) atomicExch(error, code);
+    __threadfence_system();
+    __trap();
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// no-swizzle K-major shared-memory matrix descriptor: lbo = byte distance of the two k-cores of one MMA,
+// sbo = byte distance of consecutive 8-row groups
+__device__ __forceinline__ uint64_t smem_desc(unsigned addr, unsigned lbo, unsigned sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, FP32 accumulate, M = 128, N from the instruction descriptor
+__device__ __forceinline__ void mma_tf32(unsigned d_tmem, uint64_t a_desc, uint64_t b_desc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, float* v) {
+    unsigned r0, r1, r2, r3, r4, r5, r6, r7;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                 : "r"(taddr));
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+    v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// closed-form sum of singular values of a 3x3 matrix (sign of the smallest from the determinant), FP32
+__device__ __forceinline__ float singular_sum(const float* h) {
+    float k0 = h[0] * h[0] + h[3] * h[3] + h[6] * h[6], k1 = h[0] * h[1] + h[3] * h[4] + h[6] * h[7];
+    float k2 = h[0] * h[2] + h[3] * h[5] + h[6] * h[8], k3 = h[1] * h[1] + h[4] * h[4] + h[7] * h[7];
+    float k4 = h[1] * h[2] + h[4] * h[5] + h[7] * h[8], k5 = h[2] * h[2] + h[5] * h[5] + h[8] * h[8];
+    float e1, e2, e3;
+    const float p1 = k1 * k1 + k2 * k2 + k4 * k4;
+    const float q = (k0 + k3 + k5) * (1.0f / 3.0f);
+    const float b0 = k0 - q, b3 = k3 - q, b5 = k5 - q;
+    const float p2 = b0 * b0 + b3 * b3 + b5 * b5 + 2.0f * p1;
+    if (!(p2 > 0.f)) {
+        e1 = e2 = e3 = q;
+    } else {
+        const float p = sqrtf(p2 * (1.0f / 6.0f)), ip = 1.0f / p;
+        const float c0 = b0 * ip, c3 = b3 * ip, c5 = b5 * ip, c1 = k1 * ip, c2 = k2 * ip, c4 = k4 * ip;
+        float r = 0.5f * (c0 * (c3 * c5 - c4 * c4) - c1 * (c1 * c5 - c4 * c2) + c2 * (c1 * c4 - c3 * c2));
+        r = fminf(1.0f, fmaxf(-1.0f, r));
+        const float phi = acosf(r) * (1.0f / 3.0f);
+        e1 = q + 2.0f * p * cosf(phi);
+        e3 = q + 2.0f * p * cosf(phi + 2.0943951f);
+        e2 = 3.0f * q - e1 - e3;
+    }
+    const float det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) + h[2] * (h[3] * h[7] - h[4] * h[6]);
+    const float s3 = sqrtf(fmaxf(e3, 0.f));
+    return sqrtf(fmaxf(e1, 0.f)) + sqrtf(fmaxf(e2, 0.f)) + (det < 0.f ? -s3 : s3);
+}
+}  // namespace gram
+
+// ---- operand image --------------------------------------------------------------------------------
+// one block per group of 8 positions; xcf = centred heavy-atom coordinates (n, nh) as float4
+__global__ void __launch_bounds__(256) gram_pack_kernel(const float4* __restrict__ xcf, const double* __restrict__ g,
+                                                        const int* __restrict__ spos, int nh, int kc, int n_groups,
+                                                        float* __restrict__ img, float* __restrict__ gp) {
+    const int grp = blockIdx.x;
+    if (grp >= n_groups) return;
+    __shared__ int s_idx[8];
+    if (threadIdx.x < 8) {
+        const int s = spos[grp * 8 + threadIdx.x];
+        s_idx[threadIdx.x] = s;
+        gp[grp * 8 + threadIdx.x] = s >= 0 ? (float)g[s] : 0.f;
+    }
+    __syncthreads();
+    const int per_group = 3 * kc * 32;
+    float* dst = img + (size_t)grp * per_group;
+    for (int e = threadIdx.x; e < per_group; e += blockDim.x) {
+        const int t = e & 3, r = (e >> 2) & 7, c = (e >> 5) % kc, comp = (e >> 5) / kc;
+        const int k = 4 * c + t, s = s_idx[r];
+        float v = 0.f;
+        if (s >= 0 && k < nh) {
+            const float4 x = xcf[(size_t)s * nh + k];
+            v = comp == 0 ? x.x : (comp == 1 ? x.y : x.z);
+        }
+        unsigned bits;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"(v));
+        dst[e] = __uint_as_float(bits);
+    }
+}
+
+// ---- the Gram screen --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
+    using namespace gram;
+    extern __shared__ __align__(128) uint8_t gram_smem[];
+    const int kc = a.kc;
+    const unsigned a_bytes = 6144u * kc, b_bytes = 768u * kc;
+    uint8_t* sA = gram_smem;
+    uint8_t* sB = gram_smem + a_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kGramBStages * b_bytes);
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 16);
+    const unsigned bar0 = smem_addr(bars);
+    // barrier ids
+    const unsigned A_FULL = bar0, A_EMPTY = bar0 + 8;
+    auto B_FULL = [&](unsigned s) { return bar0 + 16 + 8 * s; };
+    auto B_EMPTY = [&](unsigned s) { return bar0 + 48 + 8 * s; };
+    auto D_FULL = [&](unsigned s) { return bar0 + 80 + 8 * s; };
+    auto D_EMPTY = [&](unsigned s) { return bar0 + 96 + 8 * s; };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        bar_init(A_FULL, 1);
+        bar_init(A_EMPTY, 1);
+        for (unsigned s = 0; s < kGramBStages; ++s) { bar_init(B_FULL(s), 1); bar_init(B_EMPTY(s), 1); }
+        for (unsigned s = 0; s < 2; ++s) { bar_init(D_FULL(s), 1); bar_init(D_EMPTY(s), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // 512 columns of tensor memory: two accumulator stages x 3 components x 64 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+    const size_t group_floats = (size_t)3 * kc * 32;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- copy producer ----
+            unsigned bstage = 0, bphase = 0, aphase = 0;
+            for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+                const GramWork wk = a.work[w];
+                bar_wait(A_EMPTY, aphase ^ 1, a.error, 1);
+                bar_expect(A_FULL, a_bytes);
+                const float* src = a.img + (size_t)(wk.row0 >> 3) * group_floats;
+                for (unsigned g = 0; g < 16; ++g)
+                    bulk_load(smem_addr(sA) + g * (a_bytes / 16), src + g * group_floats, a_bytes / 16, A_FULL);
+                aphase ^= 1;
+                for (int t = 0; t < wk.n_col_tiles; ++t) {
+                    bar_wait(B_EMPTY(bstage), bphase ^ 1, a.error, 2);
+                    bar_expect(B_FULL(bstage), b_bytes);
+                    bulk_load(smem_addr(sB) + bstage * b_bytes, a.img + (size_t)(2 * (wk.col_tile0 + t)) * group_floats, b_bytes,
+                              B_FULL(bstage));
+                    if (++bstage == kGramBStages) { bstage = 0; bphase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer ----
+            // instruction descriptor: D = F32 (bit 4), A = B = TF32 (bits 7, 10), both K-major, N = 48 (>> 3 at bit 17),
+            // M = 128 (>> 4 at bit 24)
+            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (6u << 17) | (8u << 24);
+            unsigned bstage = 0, bphase = 0, aphase = 0, dstage = 0, dphase = 0;
+            const unsigned sA_addr = smem_addr(sA), sB_addr = smem_addr(sB);
+            for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+                const GramWork wk = a.work[w];
+                bar_wait(A_FULL, aphase, a.error, 3);
+                aphase ^= 1;
+                for (int t = 0; t < wk.n_col_tiles; ++t) {
+                    bar_wait(B_FULL(bstage), bphase, a.error, 4);
+                    bar_wait(D_EMPTY(dstage), dphase ^ 1, a.error, 5);
+                    tc_fence_after();
+                    for (unsigned comp = 0; comp < 3; ++comp) {
+                        const unsigned d_tmem = tmem_base + dstage * 256 + comp * 64;
+                        for (int k = 0; k < kc / 2; ++k) {
+                            const uint64_t da = smem_desc(sA_addr + comp * kc * 128 + k * 256, 128, 3 * kc * 128);
+                            const uint64_t db = smem_desc(sB_addr + bstage * b_bytes + k * 256, 128, kc * 128);
+                            mma_tf32(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(B_EMPTY(bstage));
+                    tc_commit(D_FULL(dstage));
+                    if (++bstage == kGramBStages) { bstage = 0; bphase ^= 1; }
+                    dstage ^= 1;
+                    if (dstage == 0) dphase ^= 1;
+                }
+                tc_commit(A_EMPTY);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- epilogue: thread = one row of the block (TMEM lane), 8 columns of the tile ----
+        const int quarter = warp & 3;          // TMEM lanes 32 * (warp % 4) ... are the ones this warp may read
+        const int half = (warp - 2) >> 2;      // which 8 of the 16 column positions
+        const int row_in_block = quarter * 32 + lane;
+        unsigned dstage = 0, dphase = 0;
+        for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
+            const GramWork wk = a.work[w];
+            const int prow = wk.row0 + row_in_block;
+            const int s_row = prow < wk.pend ? a.spos[prow] : -1;
+            const float g_row = prow < wk.pend ? a.gp[prow] : 0.f;
+            const double e_row = (a.energies && s_row >= 0) ? a.energies[s_row] : 0.0;
+            for (int t = 0; t < wk.n_col_tiles; ++t) {
+                __syncwarp();  // the tensor-memory loads below are warp-collective
+                bar_wait(D_FULL(dstage), dphase, a.error, 6);
+                tc_fence_after();
+                float h[3][3][8];  // [component of the row structure][component of the column structure][column]
+                const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + dstage * 256 + half * 24;
+#pragma unroll
+                for (int ca = 0; ca < 3; ++ca)
+#pragma unroll
+                    for (int cb = 0; cb < 3; ++cb) tmem_ld8(taddr + ca * 64 + cb * 8, h[ca][cb]);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bar_arrive(D_EMPTY(dstage));
+                dstage ^= 1;
+                if (dstage == 0) dphase ^= 1;
+
+                const int pcol0 = 16 * (wk.col_tile0 + t) + 8 * half;
+                if (a.dump) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int ca = 0; ca < 3; ++ca)
+#pragma unroll
+                            for (int cb = 0; cb < 3; ++cb)
+                                a.dump[((size_t)prow * a.dump_ld + pcol0 + r) * 9 + 3 * ca + cb] = h[ca][cb][r];
+                }
+                if (s_row < 0 || pcol0 + 7 <= prow || pcol0 >= wk.pend) continue;
+                const int4 sc0 = *reinterpret_cast<const int4*>(a.spos + pcol0);
+                const int4 sc1 = *reinterpret_cast<const int4*>(a.spos + pcol0 + 4);
+                const float4 gc0 = *reinterpret_cast<const float4*>(a.gp + pcol0);
+                const float4 gc1 = *reinterpret_cast<const float4*>(a.gp + pcol0 + 4);
+                const int s_col[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                const float g_col[8] = {gc0.x, gc0.y, gc0.z, gc0.w, gc1.x, gc1.y, gc1.z, gc1.w};
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int pcol = pcol0 + r;
+                    if (!(prow < pcol && pcol < wk.pend && s_col[r] >= 0)) continue;
+                    // lower bound on the true sum of squared deviations: E >= e0 - 2 * (sum of singular values), with the
+                    // TF32 rounding of H bounded by eps * |p| |q| <= eps * e0 / 2 in the Frobenius / nuclear norm
+                    const float u = (g_row + g_col[r]) * a.e0_scale - a.thr_e;
+                    float f2 = 0.f;
+#pragma unroll
+                    for (int ca = 0; ca < 3; ++ca)
+#pragma unroll
+                        for (int cb = 0; cb < 3; ++cb) f2 = fmaf(h[ca][cb][r], h[ca][cb][r], f2);
+                    // sum of singular values <= sqrt(3) |H|_F:  u - 2 sqrt(3 f2) >= 0  <=>  u >= 0 and u^2 >= 12 f2
+                    if (u >= 0.f && u * u >= 12.0f * f2) continue;
+                    float hh[9];
+#pragma unroll
+                    for (int ca = 0; ca < 3; ++ca)
+#pragma unroll
+                        for (int cb = 0; cb < 3; ++cb) hh[3 * ca + cb] = h[ca][cb][r];
+                    if (u - 2.0f * singular_sum(hh) > 0.f) continue;
+                    if (a.energies && !(fabs(e_row - a.energies[s_col[r]]) < a.max_dE)) continue;
+                    const unsigned long long slot = atomicAdd(a.n_cand, 1ull);
+                    if ((long long)slot < a.cand_cap) a.cand[slot] = make_int2(s_row, s_col[r]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace fc

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "fc_embed.cuh"
+#include "fc_gram_tc.cuh"
 
 namespace fc {
 
@@ -474,6 +475,19 @@ static void prune_resolve(std::vector<uint8_t>& mask, const std::vector<int2>& p
     }
 }
 
+// pairs (r, c) with r in [row0, min(row0 + 128, pend)), c in [max(col_lo, r + 1), col_hi): what one work item of the
+// tensor-core screen evaluates
+static int64_t gram_item_pairs(int64_t row0, int64_t col_lo, int64_t col_hi, int64_t pend) {
+    const int64_t ra = row0, rb = std::min(row0 + 128, pend);
+    if (col_hi <= col_lo) return 0;
+    int64_t total = 0;
+    const int64_t n1 = std::max<int64_t>(0, std::min(rb, col_lo) - ra);  // rows entirely left of the column range
+    total += n1 * (col_hi - col_lo);
+    const int64_t r1 = std::max(ra, col_lo), r2 = std::min(rb, col_hi - 1);  // rows inside it: col_hi - 1 - r columns each
+    if (r2 > r1) total += (r2 - r1) * (col_hi - 1) - (r1 + r2 - 1) * (r2 - r1) / 2;
+    return total;
+}
+
 // mode 0: RMSD, mode 1: MOI.  `sel` = indices of the atoms used for the RMSD (heavy atoms).
 // rank / world / gather: pair tiles of every pass are dealt round-robin to the ranks; the similar pairs each
 // rank finds are all-gathered through `gather` (NCCL or gloo behind the host language) and every rank resolves
@@ -516,6 +530,9 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
         DevBuf<int2> d_pairs, d_cand;
         DevBuf<float4> d_xcf;
         DevBuf<PruneTile> d_tiles;
+        DevBuf<float> d_img, d_gp;       // tensor-core screen: operand image and |x|^2 per padded position
+        DevBuf<int> d_spos, d_gram_err;
+        DevBuf<GramWork> d_work;
         DevBuf<unsigned long long> d_eval;
         DevBuf<TieRecord> d_ties;
         const int cap = (int)std::min<int64_t>(std::max<int64_t>(tie_cap, 1), 1 << 22);
@@ -559,6 +576,23 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
         std::vector<PruneTile> tiles;
         std::vector<int2> pairs, all_pairs;
         int64_t prev_size = 0, prev_k = 0;  // chunking of the last executed pass
+        // screen flavour: FC_PRUNE_FP64=1 -> FP64 pair kernel only; otherwise FP32 screen + FP64 exact stage, the screen
+        // on the tensor cores (gram_tc_kernel) unless FC_PRUNE_TC=0 or the molecule has more than 96 selected atoms
+        const char* env64 = getenv("FC_PRUNE_FP64");
+        const char* envtc = getenv("FC_PRUNE_TC");
+        const bool two_stage = mode == 0 && !(env64 && atoi(env64));
+        int kc = (n_sel + 3) / 4;
+        kc += kc & 1;
+        const bool use_tc = two_stage && kc <= kGramMaxKc && !(envtc && !atoi(envtc));
+        struct RowBlock { int row0, c_min, tile_end, pend; };
+        std::vector<int> spos;
+        std::vector<RowBlock> blocks;
+        std::vector<GramWork> work;
+        if (use_tc && rc == FC_OK) {
+            e = d_gram_err.alloc(1, s);
+            PR(cudaMemsetAsync(d_gram_err.p, 0, 4, s));
+            if (e != cudaSuccess) rc = cuda_fail(e, "fc_prune setup", __FILE__, __LINE__);
+        }
         for (int64_t k : kSchedule) {
             if (rc) break;
             int64_t n_active = 0;
@@ -566,47 +600,107 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
             if (!(k == 1 || (int64_t)min_per_chunk * k < n_active)) continue;
             ++passes;
             double tp = now();
-            // compacted active list + chunks over the FULL array (chunk size n // k, last takes the rest)
-            active.clear();
-            tiles.clear();
             const int64_t size = n / k;
-            int64_t tile_no = 0;
-            for (int64_t c = 0; c < k; ++c) {
-                int64_t first = c * size, last = (c == k - 1) ? n : size * (c + 1);
-                int begin = (int)active.size();
-                for (int64_t i = first; i < last; ++i)
-                    if (mask[(size_t)i]) active.push_back((int)i);
-                int len = (int)active.size() - begin;
-                if (len < 2) continue;  // nothing to compare
-                for (int r0 = 0; r0 < len; r0 += PR_TS)
-                    for (int c0 = r0; c0 < len; c0 += PR_TS) {
-                        const int rows = std::min(PR_TS, len - r0), cols = std::min(PR_TS, len - c0);
-                        const int64_t tile_pairs = r0 == c0 ? (int64_t)rows * (rows - 1) / 2 : (int64_t)rows * cols;
-                        // survivors that shared a chunk in an earlier pass are known to be dissimilar
+            if (use_tc) {
+                // padded positions (every chunk starts at a multiple of 16) and, per 128-row block, the column tiles that
+                // still need evaluating: tiles whose structures all shared a chunk with the block's first row in the
+                // previous pass are known dissimilar and form a prefix of the block's column range
+                spos.clear();
+                blocks.clear();
+                work.clear();
+                auto prev_chunk = [&](int idx) { return std::min<int64_t>((int64_t)idx / prev_size, prev_k - 1); };
+                int64_t col_tiles_total = 0;
+                for (int64_t c = 0; c < k; ++c) {
+                    const int64_t first = c * size, last = (c == k - 1) ? n : size * (c + 1);
+                    while (spos.size() % 16) spos.push_back(-1);
+                    const int pbegin = (int)spos.size();
+                    for (int64_t i = first; i < last; ++i)
+                        if (mask[(size_t)i]) spos.push_back((int)i);
+                    const int pend = (int)spos.size(), len = pend - pbegin;
+                    if (len < 2) continue;
+                    const int tile_end = (pend + 15) / 16;
+                    int64_t evaluated = 0;
+                    for (int row0 = pbegin; row0 < pend - 1; row0 += 128) {
+                        int c_min = row0 / 16;
                         if (prev_size > 0) {
-                            const int64_t lo_idx = active[(size_t)(begin + r0)], hi_idx = active[(size_t)(begin + c0 + cols - 1)];
-                            const int64_t ca = std::min(lo_idx / prev_size, prev_k - 1), cb = std::min(hi_idx / prev_size, prev_k - 1);
-                            if (ca == cb) { pairs_skipped += tile_pairs; continue; }
+                            const int64_t pc = prev_chunk(spos[(size_t)row0]);
+                            while (c_min < tile_end && prev_chunk(spos[(size_t)std::min(16 * (c_min + 1), pend) - 1]) == pc) ++c_min;
                         }
-                        if (tile_no++ % world != rank) continue;
-                        pairs_tiled += tile_pairs;
-                        tiles.push_back(PruneTile{begin + r0, begin + c0, begin, len});
+                        if (c_min >= tile_end) continue;
+                        blocks.push_back(RowBlock{row0, c_min, tile_end, pend});
+                        col_tiles_total += tile_end - c_min;
+                        evaluated += gram_item_pairs(row0, 16 * c_min, pend, pend);
                     }
+                    pairs_skipped += (int64_t)len * (len - 1) / 2 - evaluated;
+                }
+                // column ranges are cut so that every SM gets several work items of similar size
+                const int64_t seg = std::min<int64_t>(1024, std::max<int64_t>(16, col_tiles_total / ((int64_t)sm_count() * 8)));
+                int64_t item_no = 0;
+                for (const RowBlock& b : blocks)
+                    for (int c0 = b.c_min; c0 < b.tile_end; c0 += (int)seg) {
+                        const int nt = (int)std::min<int64_t>(seg, b.tile_end - c0);
+                        if (item_no++ % world != rank) continue;
+                        work.push_back(GramWork{b.row0, c0, nt, b.pend});
+                        pairs_tiled += gram_item_pairs(b.row0, 16 * c0, std::min(16 * (c0 + nt), b.pend), b.pend);
+                    }
+                while (spos.size() % 16) spos.push_back(-1);
+                spos.resize(spos.size() + 128, -1);  // a row block may read 128 positions from its first row
+            } else {
+                // compacted active list + chunks over the FULL array (chunk size n // k, last takes the rest)
+                active.clear();
+                tiles.clear();
+                int64_t tile_no = 0;
+                for (int64_t c = 0; c < k; ++c) {
+                    int64_t first = c * size, last = (c == k - 1) ? n : size * (c + 1);
+                    int begin = (int)active.size();
+                    for (int64_t i = first; i < last; ++i)
+                        if (mask[(size_t)i]) active.push_back((int)i);
+                    int len = (int)active.size() - begin;
+                    if (len < 2) continue;  // nothing to compare
+                    for (int r0 = 0; r0 < len; r0 += PR_TS)
+                        for (int c0 = r0; c0 < len; c0 += PR_TS) {
+                            const int rows = std::min(PR_TS, len - r0), cols = std::min(PR_TS, len - c0);
+                            const int64_t tile_pairs = r0 == c0 ? (int64_t)rows * (rows - 1) / 2 : (int64_t)rows * cols;
+                            // survivors that shared a chunk in an earlier pass are known to be dissimilar
+                            if (prev_size > 0) {
+                                const int64_t lo_idx = active[(size_t)(begin + r0)], hi_idx = active[(size_t)(begin + c0 + cols - 1)];
+                                const int64_t ca = std::min(lo_idx / prev_size, prev_k - 1), cb = std::min(hi_idx / prev_size, prev_k - 1);
+                                if (ca == cb) { pairs_skipped += tile_pairs; continue; }
+                            }
+                            if (tile_no++ % world != rank) continue;
+                            pairs_tiled += tile_pairs;
+                            tiles.push_back(PruneTile{begin + r0, begin + c0, begin, len});
+                        }
+                }
             }
             prev_size = size;
             prev_k = k;
             pairs.clear();
             t_tiles += now() - tp;
             tp = now();
-            if (!tiles.empty()) {
-                e = d_tiles.alloc(tiles.size(), s);
-                PR(cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(PruneTile), cudaMemcpyHostToDevice, s));
-                PR(cudaMemcpyAsync(d_active.p, active.data(), active.size() * 4, cudaMemcpyHostToDevice, s));
+            if (use_tc ? !work.empty() : !tiles.empty()) {
+                const size_t n_act = use_tc ? spos.size() : active.size();
+                e = cudaSuccess;
+                if (use_tc) {
+                    const size_t n_pos = spos.size(), img_floats = (n_pos / 8) * (size_t)3 * kc * 32;
+                    if (d_spos.n < n_pos) { PR(d_spos.alloc(n_pos + n_pos / 4, s)); PR(d_gp.alloc(n_pos + n_pos / 4, s)); }
+                    if (d_img.n < img_floats) PR(d_img.alloc(img_floats + img_floats / 4, s));
+                    if (d_work.n < work.size()) PR(d_work.alloc(work.size() + work.size() / 4, s));
+                    PR(cudaMemcpyAsync(d_spos.p, spos.data(), n_pos * 4, cudaMemcpyHostToDevice, s));
+                    PR(cudaMemcpyAsync(d_work.p, work.data(), work.size() * sizeof(GramWork), cudaMemcpyHostToDevice, s));
+                    if (e == cudaSuccess) {
+                        gram_pack_kernel<<<(unsigned)(n_pos / 8), 256, 0, s>>>(d_xcf.p, d_g.p, d_spos.p, n_sel, kc, (int)(n_pos / 8),
+                                                                              d_img.p, d_gp.p);
+                        e = cudaGetLastError();
+                    }
+                } else {
+                    e = d_tiles.alloc(tiles.size(), s);
+                    PR(cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(PruneTile), cudaMemcpyHostToDevice, s));
+                    PR(cudaMemcpyAsync(d_active.p, active.data(), active.size() * 4, cudaMemcpyHostToDevice, s));
+                }
                 if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pass setup", __FILE__, __LINE__); break; }
-                long long pair_cap = std::max<long long>(1 << 20, 8 * (long long)active.size());
-                long long cand_cap = std::max<long long>(1 << 21, 16 * (long long)active.size());
-                const char* env64 = getenv("FC_PRUNE_FP64");
-                const bool two_stage = mode == 0 && !(env64 && atoi(env64));
+                long long pair_cap = std::max<long long>(1 << 20, 8 * (long long)n_act);
+                long long cand_cap = std::max<long long>(1 << 21, 16 * (long long)n_act);
                 bool counted = false;  // ties / eigen-solve statistics are recorded by one exact run only
                 for (int attempt = 0; attempt < 4 && !rc; ++attempt) {
                     if (d_pairs.n < (size_t)pair_cap) PR(d_pairs.alloc((size_t)pair_cap, s));
@@ -623,10 +717,26 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                     a.ties = (ties_out && !counted) ? d_ties.p : nullptr; a.n_ties = d_nties.p; a.tie_cap = cap;
                     unsigned long long found = 0;
                     if (two_stage) {
-                        // FP32 screen of every pair of the tiles -> candidates; FP64 exact evaluation of the candidates
-                        const size_t smem = (size_t)2 * PS_ATOMS * PS_LD * sizeof(float4);
-                        PR(cudaFuncSetAttribute(prune_screen_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                        prune_screen_f32_kernel<<<(unsigned)tiles.size(), 128, smem, s>>>(a);
+                        // screen of every pair of the tiles -> candidates; FP64 exact evaluation of the candidates
+                        if (use_tc) {
+                            GramArgs ga{};
+                            ga.img = d_img.p; ga.gp = d_gp.p; ga.spos = d_spos.p;
+                            ga.energies = energies ? d_energy.p : nullptr; ga.max_dE = max_dE;
+                            ga.work = d_work.p; ga.n_work = (int)work.size(); ga.kc = kc;
+                            const float lim = (float)max_rmsd + kScreenBand;
+                            ga.thr_e = lim * lim * (float)n_sel;
+                            ga.e0_scale = 1.0f - 1.7320508f * kGramTf32Eps;
+                            ga.cand = d_cand.p; ga.n_cand = d_eval.p + 2; ga.cand_cap = cand_cap;
+                            ga.dump = nullptr; ga.dump_ld = 0; ga.error = d_gram_err.p;
+                            const size_t smem = gram_smem_bytes(kc);
+                            PR(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                            const unsigned grid = (unsigned)std::min<size_t>((size_t)sm_count(), work.size());
+                            gram_tc_kernel<<<grid, kGramThreads, smem, s>>>(ga);
+                        } else {
+                            const size_t smem = (size_t)2 * PS_ATOMS * PS_LD * sizeof(float4);
+                            PR(cudaFuncSetAttribute(prune_screen_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                            prune_screen_f32_kernel<<<(unsigned)tiles.size(), 128, smem, s>>>(a);
+                        }
                         PR(cudaGetLastError());
                         unsigned long long n_cand = 0;
                         PR(cudaMemcpyAsync(&n_cand, d_eval.p + 2, 8, cudaMemcpyDeviceToHost, s));

@@ -1,0 +1,133 @@
+// Standalone check of fc_gram_tc.cuh: tensor-core covariance blocks vs a CPU double-precision Gram, the
+// candidate list vs exact Kabsch RMSD (superset property), and kernel throughput.
+// build: nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -o tools/gram_tc_test tools/gram_tc_test.cu
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <random>
+#include <set>
+#include <vector>
+
+#include "../firecode_b200/csrc/fc_gram_tc.cuh"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
+
+static double sigma_sum(const double* h) {  // Jacobi on H^T H
+    double k[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { k[i][j] = 0; for (int m = 0; m < 3; ++m) k[i][j] += h[3 * m + i] * h[3 * m + j]; }
+    for (int sweep = 0; sweep < 60; ++sweep)
+        for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+            if (fabs(k[p][q]) < 1e-300) continue;
+            double th = 0.5 * atan2(2 * k[p][q], k[q][q] - k[p][p]), c = cos(th), s = sin(th);
+            double r[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+            r[p][p] = c; r[q][q] = c; r[p][q] = s; r[q][p] = -s;
+            double t[3][3], u[3][3];
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { t[i][j] = 0; for (int m = 0; m < 3; ++m) t[i][j] += r[m][i] * k[m][j]; }
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { u[i][j] = 0; for (int m = 0; m < 3; ++m) u[i][j] += t[i][m] * r[m][j]; }
+            memcpy(k, u, sizeof k);
+        }
+    double e[3] = {k[0][0], k[1][1], k[2][2]};
+    std::sort(e, e + 3);
+    double det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) + h[2] * (h[3] * h[7] - h[4] * h[6]);
+    double s3 = sqrt(std::max(e[0], 0.0));
+    return sqrt(std::max(e[2], 0.0)) + sqrt(std::max(e[1], 0.0)) + (det < 0 ? -s3 : s3);
+}
+
+int main(int argc, char** argv) {
+    const int n = argc > 1 ? atoi(argv[1]) : 300;
+    const int nh = argc > 2 ? atoi(argv[2]) : 58;
+    const int seg = argc > 3 ? atoi(argv[3]) : 5;
+    const bool check = n <= 2000;
+    int kc = (nh + 3) / 4; if (kc & 1) ++kc;
+    const double max_rmsd = 0.5, band = 0.05;
+    std::mt19937_64 rng(12345);
+    std::normal_distribution<double> nd(0.0, 1.0);
+    // structures: a few basins, jittered copies, centred
+    const int n_basins = std::max(1, n / 20);
+    std::vector<double> basin((size_t)n_basins * nh * 3);
+    for (auto& v : basin) v = 3.0 * nd(rng);
+    std::vector<double> x((size_t)n * nh * 3), g(n);
+    std::vector<float4> xf((size_t)n * nh);
+    for (int s = 0; s < n; ++s) {
+        const int b = (int)(rng() % n_basins);
+        const double sig = 0.05 + 0.3 * (double)(rng() % 1000) / 1000.0;
+        double mean[3] = {0, 0, 0};
+        for (int k = 0; k < nh; ++k) for (int c = 0; c < 3; ++c) { double v = basin[((size_t)b * nh + k) * 3 + c] + sig * nd(rng); x[((size_t)s * nh + k) * 3 + c] = v; mean[c] += v / nh; }
+        double gg = 0;
+        for (int k = 0; k < nh; ++k) { for (int c = 0; c < 3; ++c) { double& v = x[((size_t)s * nh + k) * 3 + c]; v -= mean[c]; gg += v * v; }
+            xf[(size_t)s * nh + k] = make_float4((float)x[((size_t)s * nh + k) * 3], (float)x[((size_t)s * nh + k) * 3 + 1], (float)x[((size_t)s * nh + k) * 3 + 2], 0.f); }
+        g[s] = gg;
+    }
+    const int pend = n, n_pos = ((n + 15) / 16) * 16 + 128;
+    std::vector<int> spos(n_pos, -1);
+    for (int i = 0; i < n; ++i) spos[i] = i;
+    std::vector<fc::GramWork> work;
+    const int n_tiles = (pend + 15) / 16;
+    for (int row0 = 0; row0 < pend - 1; row0 += 128)
+        for (int c0 = row0 / 16; c0 < n_tiles; c0 += seg) work.push_back(fc::GramWork{row0, c0, std::min(seg, n_tiles - c0), pend});
+    printf("n=%d nh=%d kc=%d n_pos=%d work items=%zu smem=%zu\n", n, nh, kc, n_pos, work.size(), fc::gram_smem_bytes(kc));
+
+    float4* d_xf; double* d_g; int* d_spos; float *d_img, *d_gp, *d_dump = nullptr; fc::GramWork* d_work; int2* d_cand; unsigned long long* d_nc; int* d_err;
+    const size_t img_floats = (size_t)(n_pos / 8) * 3 * kc * 32;
+    const long long cand_cap = 1 << 24;
+    CK(cudaMalloc(&d_xf, xf.size() * sizeof(float4))); CK(cudaMalloc(&d_g, n * 8)); CK(cudaMalloc(&d_spos, n_pos * 4));
+    CK(cudaMalloc(&d_img, img_floats * 4)); CK(cudaMalloc(&d_gp, n_pos * 4)); CK(cudaMalloc(&d_work, work.size() * sizeof(fc::GramWork)));
+    CK(cudaMalloc(&d_cand, cand_cap * sizeof(int2))); CK(cudaMalloc(&d_nc, 8)); CK(cudaMalloc(&d_err, 4));
+    CK(cudaMemcpy(d_xf, xf.data(), xf.size() * sizeof(float4), cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_g, g.data(), n * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_spos, spos.data(), n_pos * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_work, work.data(), work.size() * sizeof(fc::GramWork), cudaMemcpyHostToDevice));
+    CK(cudaMemset(d_nc, 0, 8)); CK(cudaMemset(d_err, 0, 4));
+    const int dump_ld = n_pos;
+    if (check) { CK(cudaMalloc(&d_dump, (size_t)n_pos * dump_ld * 9 * 4)); CK(cudaMemset(d_dump, 0, (size_t)n_pos * dump_ld * 9 * 4)); }
+    fc::gram_pack_kernel<<<n_pos / 8, 256>>>(d_xf, d_g, d_spos, nh, kc, n_pos / 8, d_img, d_gp);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    fc::GramArgs a{};
+    a.img = d_img; a.gp = d_gp; a.spos = d_spos; a.energies = nullptr; a.max_dE = 0; a.work = d_work; a.n_work = (int)work.size(); a.kc = kc;
+    const float lim = (float)(max_rmsd + band);
+    a.thr_e = lim * lim * nh; a.e0_scale = 1.0f - 1.7320508f * (1.0f / 512.0f);
+    a.cand = d_cand; a.n_cand = d_nc; a.cand_cap = cand_cap; a.dump = d_dump; a.dump_ld = dump_ld; a.error = d_err;
+    int dev_sms = 0; CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, 0));
+    const size_t smem = fc::gram_smem_bytes(kc);
+    CK(cudaFuncSetAttribute(fc::gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min<int>(dev_sms, (int)work.size());
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < (check ? 1 : 5); ++rep) {
+        CK(cudaMemset(d_nc, 0, 8));
+        cudaEventRecord(e0);
+        fc::gram_tc_kernel<<<grid, fc::kGramThreads, smem>>>(a);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { int err = -1; cudaMemcpy(&err, d_err, 4, cudaMemcpyDeviceToHost); printf("kernel failed: %s (barrier code %d)\n", cudaGetErrorString(e), err); return 2; }
+        float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms);
+    }
+    unsigned long long nc = 0; CK(cudaMemcpy(&nc, d_nc, 8, cudaMemcpyDeviceToHost));
+    const double pairs = 0.5 * n * (double)(n - 1);
+    printf("kernel %.3f ms, %.3e pairs -> %.3e pairs/s, candidates %llu\n", best, pairs, pairs / (best * 1e-3), nc);
+    if (!check) return 0;
+
+    std::vector<float> dump((size_t)n_pos * dump_ld * 9);
+    CK(cudaMemcpy(dump.data(), d_dump, dump.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<int2> cand(nc); if (nc) CK(cudaMemcpy(cand.data(), d_cand, nc * sizeof(int2), cudaMemcpyDeviceToHost));
+    std::set<std::pair<int, int>> cset; for (auto& c : cand) cset.insert({c.x, c.y});
+    double max_err = 0, max_rel_bound = 0; long long similar = 0, missing = 0, visited = 0;
+    for (int i = 0; i < n; ++i) for (int j = i + 1; j < n; ++j) {
+        double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < nh; ++k) for (int ca = 0; ca < 3; ++ca) for (int cb = 0; cb < 3; ++cb)
+            h[3 * ca + cb] += x[((size_t)i * nh + k) * 3 + ca] * x[((size_t)j * nh + k) * 3 + cb];
+        const float* d = &dump[((size_t)i * dump_ld + j) * 9];
+        double fro = 0;
+        for (int e = 0; e < 9; ++e) { fro += (d[e] - h[e]) * (d[e] - h[e]); max_err = std::max(max_err, fabs(d[e] - h[e])); }
+        ++visited;
+        max_rel_bound = std::max(max_rel_bound, sqrt(fro) / sqrt(g[i] * g[j]));
+        const double msd = (g[i] + g[j] - 2 * sigma_sum(h)) / nh;
+        if (msd < max_rmsd * max_rmsd) { ++similar; if (!cset.count({i, j})) { if (missing < 5) printf("MISSING similar pair (%d,%d) rmsd %.4f\n", i, j, sqrt(std::max(msd, 0.0))); ++missing; } }
+    }
+    printf("pairs checked %lld: max |H_tc - H_f64| = %.3e, max |dH|_F / (|p||q|) = %.3e (bound used %.3e), similar %lld, missing %lld, candidates %llu\n",
+           visited, max_err, max_rel_bound, 1.0 / 512, similar, missing, nc);
+    printf(missing == 0 && max_rel_bound < 1.0 / 1024 ? "OK\n" : "FAILED\n");
+    return missing == 0 ? 0 : 3;
+}
