@@ -61,6 +61,10 @@ struct TieRecord {
 
 fc_result* result_new();
 
+// fc_host.cu: pageable host rows -> device through two pinned staging buffers filled by several threads
+cudaError_t upload_rows_staged(double* dst, const double* src, int64_t n, int n_atoms, const int32_t* sel, int n_sel,
+                               cudaStream_t stream);
+
 // order-preserving compaction of the poses whose status has FC_STATUS_PASS set (CUB DeviceSelect)
 int compact_pass(const uint8_t* status, long long n, long long base, long long* out_idx, int* out_count,
                  cudaStream_t s);

@@ -52,9 +52,11 @@ struct GramArgs {
     float* dump;              // debug: H of every (prow, pcol) visited, [prow][dump_ld][9]; null in production
     int dump_ld;
     int* error;               // set when a barrier wait times out (the kernel then traps)
+    long long* prof;          // debug: cycle counters of CTA 0 (see tools/gram_tc_test.cu); null in production
+    int no_math;              // debug: the epilogue only drains tensor memory (measures the MMA / copy pipeline alone)
 };
 
-constexpr int kGramThreads = 320;
+constexpr int kGramThreads = 352;
 constexpr int kGramBStages = 4;
 constexpr int kGramMaxKc = 24;
 // Relative bound on |H_tf32 - H|_F / (|p| |q|): operands are rounded to nearest TF32 (2^-11 each, so 2^-10 on a
@@ -127,32 +129,6 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// closed-form sum of singular values of a 3x3 matrix (sign of the smallest from the determinant), FP32
-__device__ __forceinline__ float singular_sum(const float* h) {
-    float k0 = h[0] * h[0] + h[3] * h[3] + h[6] * h[6], k1 = h[0] * h[1] + h[3] * h[4] + h[6] * h[7];
-    float k2 = h[0] * h[2] + h[3] * h[5] + h[6] * h[8], k3 = h[1] * h[1] + h[4] * h[4] + h[7] * h[7];
-    float k4 = h[1] * h[2] + h[4] * h[5] + h[7] * h[8], k5 = h[2] * h[2] + h[5] * h[5] + h[8] * h[8];
-    float e1, e2, e3;
-    const float p1 = k1 * k1 + k2 * k2 + k4 * k4;
-    const float q = (k0 + k3 + k5) * (1.0f / 3.0f);
-    const float b0 = k0 - q, b3 = k3 - q, b5 = k5 - q;
-    const float p2 = b0 * b0 + b3 * b3 + b5 * b5 + 2.0f * p1;
-    if (!(p2 > 0.f)) {
-        e1 = e2 = e3 = q;
-    } else {
-        const float p = sqrtf(p2 * (1.0f / 6.0f)), ip = 1.0f / p;
-        const float c0 = b0 * ip, c3 = b3 * ip, c5 = b5 * ip, c1 = k1 * ip, c2 = k2 * ip, c4 = k4 * ip;
-        float r = 0.5f * (c0 * (c3 * c5 - c4 * c4) - c1 * (c1 * c5 - c4 * c2) + c2 * (c1 * c4 - c3 * c2));
-        r = fminf(1.0f, fmaxf(-1.0f, r));
-        const float phi = acosf(r) * (1.0f / 3.0f);
-        e1 = q + 2.0f * p * cosf(phi);
-        e3 = q + 2.0f * p * cosf(phi + 2.0943951f);
-        e2 = 3.0f * q - e1 - e3;
-    }
-    const float det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) + h[2] * (h[3] * h[7] - h[4] * h[6]);
-    const float s3 = sqrtf(fmaxf(e3, 0.f));
-    return sqrtf(fmaxf(e1, 0.f)) + sqrtf(fmaxf(e2, 0.f)) + (det < 0.f ? -s3 : s3);
-}
 }  // namespace gram
 
 // ---- operand image --------------------------------------------------------------------------------
@@ -206,7 +182,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
 
     if (threadIdx.x == 0) {
         bar_init(A_FULL, 1);
-        bar_init(A_EMPTY, 1);
+        bar_init(A_EMPTY, 2);
         for (unsigned s = 0; s < kGramBStages; ++s) { bar_init(B_FULL(s), 1); bar_init(B_EMPTY(s), 1); }
         for (unsigned s = 0; s < 2; ++s) { bar_init(D_FULL(s), 1); bar_init(D_EMPTY(s), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -235,48 +211,65 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                 aphase ^= 1;
                 for (int t = 0; t < wk.n_col_tiles; ++t) {
                     bar_wait(B_EMPTY(bstage), bphase ^ 1, a.error, 2);
+                    if (a.no_math & 4) {
+                        bar_arrive(B_FULL(bstage));
+                    } else {
                     bar_expect(B_FULL(bstage), b_bytes);
                     bulk_load(smem_addr(sB) + bstage * b_bytes, a.img + (size_t)(2 * (wk.col_tile0 + t)) * group_floats, b_bytes,
                               B_FULL(bstage));
+                    }
                     if (++bstage == kGramBStages) { bstage = 0; bphase ^= 1; }
                 }
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        if (lane == 0) {  // ---- MMA issuer ----
+    } else if (warp == 1 || warp == 10) {
+        if (lane == 0) {  // ---- MMA issuers ----
+            // Two issuing threads: a tcgen05.mma of this shape costs ~80 cycles in its issuing thread whatever N is
+            // (measured, tools/gram_tc_test.cu), so one thread alone caps the kernel.  Tile g (counted over the whole
+            // CTA) uses operand slot g % 4 and accumulator stage g % 2; issuer i takes the tiles with g % 2 == i.
             // instruction descriptor: D = F32 (bit 4), A = B = TF32 (bits 7, 10), both K-major, N = 48 (>> 3 at bit 17),
             // M = 128 (>> 4 at bit 24)
+            const unsigned issuer = warp == 1 ? 0u : 1u;
             const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (6u << 17) | (8u << 24);
-            unsigned bstage = 0, bphase = 0, aphase = 0, dstage = 0, dphase = 0;
+            unsigned g = 0, bphases = 0, aphase = 0, dphase = 0;  // one phase bit per operand slot
             const unsigned sA_addr = smem_addr(sA), sB_addr = smem_addr(sB);
             for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
                 const GramWork wk = a.work[w];
                 bar_wait(A_FULL, aphase, a.error, 3);
                 aphase ^= 1;
-                for (int t = 0; t < wk.n_col_tiles; ++t) {
-                    bar_wait(B_FULL(bstage), bphase, a.error, 4);
-                    bar_wait(D_EMPTY(dstage), dphase ^ 1, a.error, 5);
+                for (int t = 0; t < wk.n_col_tiles; ++t, ++g) {
+                    if ((g & 1u) != issuer) continue;
+                    const unsigned bs = g % kGramBStages;
+                    const long long c0 = clock64();
+                    bar_wait(B_FULL(bs), (bphases >> bs) & 1u, a.error, 4);
+                    const long long c1 = clock64();
+                    bar_wait(D_EMPTY(issuer), dphase ^ 1u, a.error, 5);
+                    const long long c2 = clock64();
                     tc_fence_after();
-                    for (unsigned comp = 0; comp < 3; ++comp) {
-                        const unsigned d_tmem = tmem_base + dstage * 256 + comp * 64;
-                        for (int k = 0; k < kc / 2; ++k) {
+                    // k-step outermost, the 3 independent accumulators (components) innermost
+                    const int ksteps = (a.no_math & 2) ? 1 : kc / 2;
+                    for (int k = 0; k < ksteps; ++k) {
+                        const uint64_t db = smem_desc(sB_addr + bs * b_bytes + k * 256, 128, kc * 128);
+                        for (unsigned comp = 0; comp < 3; ++comp) {
                             const uint64_t da = smem_desc(sA_addr + comp * kc * 128 + k * 256, 128, 3 * kc * 128);
-                            const uint64_t db = smem_desc(sB_addr + bstage * b_bytes + k * 256, 128, kc * 128);
-                            mma_tf32(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
+                            mma_tf32(tmem_base + issuer * 256 + comp * 64, da, db, idesc, k > 0 ? 1u : 0u);
                         }
                     }
-                    tc_commit(B_EMPTY(bstage));
-                    tc_commit(D_FULL(dstage));
-                    if (++bstage == kGramBStages) { bstage = 0; bphase ^= 1; }
-                    dstage ^= 1;
-                    if (dstage == 0) dphase ^= 1;
+                    tc_commit(B_EMPTY(bs));
+                    tc_commit(D_FULL(issuer));
+                    bphases ^= 1u << bs;
+                    dphase ^= 1u;
+                    if (a.prof && blockIdx.x == 0 && issuer == 0) {
+                        const long long c3 = clock64();
+                        a.prof[0] += c1 - c0; a.prof[1] += c2 - c1; a.prof[2] += c3 - c2; a.prof[3] += 1;
+                    }
                 }
                 tc_commit(A_EMPTY);
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp < 10) {
         // ---- epilogue: thread = one row of the block (TMEM lane), 8 columns of the tile ----
         const int quarter = warp & 3;          // TMEM lanes 32 * (warp % 4) ... are the ones this warp may read
         const int half = (warp - 2) >> 2;      // which 8 of the 16 column positions
@@ -290,7 +283,15 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
             const double e_row = (a.energies && s_row >= 0) ? a.energies[s_row] : 0.0;
             for (int t = 0; t < wk.n_col_tiles; ++t) {
                 __syncwarp();  // the tensor-memory loads below are warp-collective
+                // column metadata first: these loads fly while the accumulator is still being produced
+                const int pcol0 = 16 * (wk.col_tile0 + t) + 8 * half;
+                const int4 sc0 = *reinterpret_cast<const int4*>(a.spos + pcol0);
+                const int4 sc1 = *reinterpret_cast<const int4*>(a.spos + pcol0 + 4);
+                const float4 gc0 = *reinterpret_cast<const float4*>(a.gp + pcol0);
+                const float4 gc1 = *reinterpret_cast<const float4*>(a.gp + pcol0 + 4);
+                const long long e0 = clock64();
                 bar_wait(D_FULL(dstage), dphase, a.error, 6);
+                const long long e1 = clock64();
                 tc_fence_after();
                 float h[3][3][8];  // [component of the row structure][component of the column structure][column]
                 const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + dstage * 256 + half * 24;
@@ -302,10 +303,13 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(D_EMPTY(dstage));
+                if (a.prof && blockIdx.x == 0 && threadIdx.x == 64) {
+                    const long long e2 = clock64();
+                    a.prof[4] += e1 - e0; a.prof[5] += e2 - e1; a.prof[6] += 1;
+                }
                 dstage ^= 1;
                 if (dstage == 0) dphase ^= 1;
 
-                const int pcol0 = 16 * (wk.col_tile0 + t) + 8 * half;
                 if (a.dump) {
 #pragma unroll
                     for (int r = 0; r < 8; ++r)
@@ -315,33 +319,56 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                             for (int cb = 0; cb < 3; ++cb)
                                 a.dump[((size_t)prow * a.dump_ld + pcol0 + r) * 9 + 3 * ca + cb] = h[ca][cb][r];
                 }
-                if (s_row < 0 || pcol0 + 7 <= prow || pcol0 >= wk.pend) continue;
-                const int4 sc0 = *reinterpret_cast<const int4*>(a.spos + pcol0);
-                const int4 sc1 = *reinterpret_cast<const int4*>(a.spos + pcol0 + 4);
-                const float4 gc0 = *reinterpret_cast<const float4*>(a.gp + pcol0);
-                const float4 gc1 = *reinterpret_cast<const float4*>(a.gp + pcol0 + 4);
+                if ((a.no_math & 1) || s_row < 0 || pcol0 + 7 <= prow || pcol0 >= wk.pend) continue;
                 const int s_col[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
                 const float g_col[8] = {gc0.x, gc0.y, gc0.z, gc0.w, gc1.x, gc1.y, gc1.z, gc1.w};
+                // Lower bound on the true sum of squared deviations: E >= e0 - 2 S, S = sum of the singular values of H (largest
+                // root of the quartic below); the TF32 rounding of H moves S by at most sqrt(3) eps |p| |q| <= sqrt(3) eps e0 / 2,
+                // which e0_scale takes off e0.  A pair is ruled out as soon as an UPPER bound on S gives  u - 2 S > 0.
+                // Pass 1, branch-free over the 8 columns: S <= sqrt(3) |H|_F, i.e. u >= 0 and u^2 >= 12 |H|_F^2.
+                unsigned und = 0;
+                float uu[8], ff[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const int pcol = pcol0 + r;
-                    if (!(prow < pcol && pcol < wk.pend && s_col[r] >= 0)) continue;
-                    // lower bound on the true sum of squared deviations: E >= e0 - 2 * (sum of singular values), with the
-                    // TF32 rounding of H bounded by eps * |p| |q| <= eps * e0 / 2 in the Frobenius / nuclear norm
-                    const float u = (g_row + g_col[r]) * a.e0_scale - a.thr_e;
-                    float f2 = 0.f;
+                    const bool valid = prow < pcol && pcol < wk.pend && s_col[r] >= 0;
+                    uu[r] = (g_row + g_col[r]) * a.e0_scale - a.thr_e;
+                    const float fa = h[0][0][r] * h[0][0][r] + h[0][1][r] * h[0][1][r] + h[0][2][r] * h[0][2][r];
+                    const float fb = h[1][0][r] * h[1][0][r] + h[1][1][r] * h[1][1][r] + h[1][2][r] * h[1][2][r];
+                    const float fc2 = h[2][0][r] * h[2][0][r] + h[2][1][r] * h[2][1][r] + h[2][2][r] * h[2][2][r];
+                    ff[r] = fa + fb + fc2;
+                    if (valid && !(uu[r] >= 0.f && uu[r] * uu[r] >= 12.0f * ff[r])) und |= 1u << r;
+                }
+                if (und == 0) continue;
+                // Pass 2 for the columns pass 1 could not rule out
 #pragma unroll
-                    for (int ca = 0; ca < 3; ++ca)
-#pragma unroll
-                        for (int cb = 0; cb < 3; ++cb) f2 = fmaf(h[ca][cb][r], h[ca][cb][r], f2);
-                    // sum of singular values <= sqrt(3) |H|_F:  u - 2 sqrt(3 f2) >= 0  <=>  u >= 0 and u^2 >= 12 f2
-                    if (u >= 0.f && u * u >= 12.0f * f2) continue;
-                    float hh[9];
-#pragma unroll
-                    for (int ca = 0; ca < 3; ++ca)
-#pragma unroll
-                        for (int cb = 0; cb < 3; ++cb) hh[3 * ca + cb] = h[ca][cb][r];
-                    if (u - 2.0f * singular_sum(hh) > 0.f) continue;
+                for (int r = 0; r < 8; ++r) {
+                    if (!(und & (1u << r))) continue;
+                    const float u = uu[r], f2 = ff[r];
+                    // second symmetric function of the squared singular values = |cof H|_F^2, and det H
+                    const float h0 = h[0][0][r], h1 = h[0][1][r], h2 = h[0][2][r], h3 = h[1][0][r], h4 = h[1][1][r],
+                                h5 = h[1][2][r], h6 = h[2][0][r], h7 = h[2][1][r], h8 = h[2][2][r];
+                    const float c0 = h4 * h8 - h5 * h7, c1 = h5 * h6 - h3 * h8, c2 = h3 * h7 - h4 * h6;
+                    const float c3 = h2 * h7 - h1 * h8, c4 = h0 * h8 - h2 * h6, c5 = h1 * h6 - h0 * h7;
+                    const float c6 = h1 * h5 - h2 * h4, c7 = h2 * h3 - h0 * h5, c8 = h0 * h4 - h1 * h3;
+                    const float cc = c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3 + c4 * c4 + c5 * c5 + c6 * c6 + c7 * c7 + c8 * c8;
+                    const float det = h0 * c0 + h1 * c1 + h2 * c2;
+                    // S^2 = f2 + 2 e2 with e2 = sum of pairwise products of the singular values <= sqrt(3 cc); the approximate
+                    // square roots are scaled up by 2^-20 so that the result stays an upper bound
+                    float lam = __fsqrt_rn(f2 + 2.0f * __fsqrt_rn(3.0f * cc)) * 1.000001f;
+                    bool reject = u - 2.0f * lam > 0.f;
+                    // Newton from above on  P(x) = (x^2 - f2)^2 - 8 det x - 4 cc  (the QCP characteristic polynomial): every
+                    // iterate stays above the largest root S, so each one is a valid upper bound
+                    for (int it = 0; it < 6 && !reject; ++it) {
+                        const float tt = lam * lam - f2;
+                        const float pv = tt * tt - 8.0f * det * lam - 4.0f * cc, dp = 4.0f * lam * tt - 8.0f * det;
+                        if (!(dp > 0.f) || !(pv > 0.f)) break;
+                        const float step = __fdividef(pv, dp);
+                        lam -= step;
+                        reject = u - 2.0f * lam > 0.f;
+                        if (step <= 1e-5f * lam) break;
+                    }
+                    if (reject) continue;
                     if (a.energies && !(fabs(e_row - a.energies[s_col[r]]) < a.max_dE)) continue;
                     const unsigned long long slot = atomicAdd(a.n_cand, 1ull);
                     if ((long long)slot < a.cand_cap) a.cand[slot] = make_int2(s_row, s_col[r]);

@@ -41,7 +41,7 @@ __global__ void prune_center_kernel(const double* __restrict__ coords, int n_ato
     __shared__ double sm[3][32];
     double acc[3] = {0, 0, 0};
     for (int k = threadIdx.x; k < nh; k += blockDim.x) {
-        const double* a = src + 3 * sel[k];
+        const double* a = src + 3 * (sel ? sel[k] : k);
         acc[0] += a[0]; acc[1] += a[1]; acc[2] += a[2];
     }
     for (int c = 0; c < 3; ++c) {
@@ -60,7 +60,7 @@ __global__ void prune_center_kernel(const double* __restrict__ coords, int n_ato
     double gg = 0;
     double* dst = out + (size_t)s * nh * 3;
     for (int k = threadIdx.x; k < nh; k += blockDim.x) {
-        const double* a = src + 3 * sel[k];
+        const double* a = src + 3 * (sel ? sel[k] : k);
         double x = a[0] - mean[0], y = a[1] - mean[1], z = a[2] - mean[2];
         dst[3 * k] = x; dst[3 * k + 1] = y; dst[3 * k + 2] = z;
         outf[(size_t)s * nh + k] = make_float4((float)x, (float)y, (float)z, 0.f);
@@ -516,7 +516,10 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
     const bool trace = getenv("FC_CLASH_TRACE") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
-    double t_tiles = 0, t_kernels = 0, t_resolve = 0, t_upload = 0;
+    double t_tiles = 0, t_kernels = 0, t_resolve = 0, t_upload = 0, t_gram = 0;
+    unsigned long long cand_total = 0;
+    cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
+    if (trace) { cudaEventCreate(&ev_g0); cudaEventCreate(&ev_g1); }
     cudaStream_t s;
     FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     int rc = FC_OK;
@@ -538,8 +541,10 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
         const int cap = (int)std::min<int64_t>(std::max<int64_t>(tie_cap, 1), 1 << 22);
         cudaError_t e = cudaSuccess;
 #define PR(call) do { if (e == cudaSuccess) e = (call); } while (0)
-        PR(d_coords.alloc((size_t)n * n_atoms * 3, s));
-        PR(cudaMemcpyAsync(d_coords.p, structures, (size_t)n * n_atoms * 24, cudaMemcpyHostToDevice, s));
+        // only the atoms the criterion reads travel: the selected (heavy) atoms for the RMSD, all of them for the moments
+        const int n_up = mode == 0 ? n_sel : n_atoms;
+        PR(d_coords.alloc((size_t)n * n_up * 3, s));
+        PR(upload_rows_staged(d_coords.p, structures, n, n_atoms, mode == 0 ? sel : nullptr, n_up, s));
         PR(d_nties.alloc(4, s));
         PR(cudaMemsetAsync(d_nties.p, 0, 16, s));
         PR(d_eval.alloc(4, s));  // [0] eigen-solves, [1] similar pairs, [2] screen candidates of the current pass
@@ -556,7 +561,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
             PR(d_xcf.alloc((size_t)n * n_sel, s));
             PR(d_g.alloc((size_t)n, s));
             if (e == cudaSuccess) {
-                prune_center_kernel<<<(unsigned)n, 64, 0, s>>>(d_coords.p, n_atoms, d_sel.p, n_sel, n, d_xc.p, d_g.p, d_xcf.p);
+                prune_center_kernel<<<(unsigned)n, 64, 0, s>>>(d_coords.p, n_sel, nullptr, n_sel, n, d_xc.p, d_g.p, d_xcf.p);
                 e = cudaGetLastError();
             }
         } else {
@@ -731,7 +736,9 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                             const size_t smem = gram_smem_bytes(kc);
                             PR(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                             const unsigned grid = (unsigned)std::min<size_t>((size_t)sm_count(), work.size());
+                            if (trace) cudaEventRecord(ev_g0, s);
                             gram_tc_kernel<<<grid, kGramThreads, smem, s>>>(ga);
+                            if (trace) cudaEventRecord(ev_g1, s);
                         } else {
                             const size_t smem = (size_t)2 * PS_ATOMS * PS_LD * sizeof(float4);
                             PR(cudaFuncSetAttribute(prune_screen_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -741,6 +748,12 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                         unsigned long long n_cand = 0;
                         PR(cudaMemcpyAsync(&n_cand, d_eval.p + 2, 8, cudaMemcpyDeviceToHost, s));
                         PR(cudaStreamSynchronize(s));
+                        if (trace && use_tc && e == cudaSuccess) {
+                            float ms = 0;
+                            cudaEventElapsedTime(&ms, ev_g0, ev_g1);
+                            t_gram += ms;
+                            cand_total += n_cand;
+                        }
                         if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune screen", __FILE__, __LINE__); break; }
                         if ((long long)n_cand > cand_cap) {  // list too small: repeat with the exact size
                             cand_cap = (long long)n_cand;
@@ -814,8 +827,10 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
     cudaStreamDestroy(s);
     if (rc) return rc;
     if (trace)
-        fprintf(stderr, "fc_prune: total %.1f ms: upload+centre %.1f, tile lists %.1f, kernels+readback %.1f, resolve %.1f\n",
-                now() - t_begin, t_upload, t_tiles, t_kernels, t_resolve);
+        fprintf(stderr, "fc_prune: total %.1f ms: upload+centre %.1f, tile lists %.1f, kernels+readback %.1f (tensor-core screen %.1f, "
+                "%llu candidates), resolve %.1f\n",
+                now() - t_begin, t_upload, t_tiles, t_kernels, t_gram, cand_total, t_resolve);
+    if (ev_g0) { cudaEventDestroy(ev_g0); cudaEventDestroy(ev_g1); }
     memcpy(mask_out, mask.data(), (size_t)n);
     if (n_ties_out) *n_ties_out = ties_total;
     if (stats_out) {

@@ -89,7 +89,18 @@ def _run(structures, mode, sel, masses, max_rmsd, max_dev, moi_dev, energies, ma
                               ties=ties[: min(int(n_ties.value), tie_cap)], n_ties_total=int(n_ties.value),
                               keep=keep, pass_mode=pass_mode)
     mask = mask.astype(bool)
-    return x[mask], mask
+    return _take(lib, x, mask), mask
+
+
+def _take(lib, x, mask):
+    """``x[mask]`` for a C-contiguous array, copied by several host threads (fc_take_rows)."""
+    n_keep = int(np.count_nonzero(mask))
+    out = np.empty((n_keep,) + x.shape[1:], dtype=x.dtype)
+    if n_keep:
+        row_bytes = x.dtype.itemsize * int(np.prod(x.shape[1:]))
+        m8 = mask.view(np.uint8)
+        _lib.check(lib.fc_take_rows(_ptr(x), row_bytes, _ptr(m8), len(mask), _ptr(out), n_keep), "fc_take_rows")
+    return out
 
 
 def prune_by_rmsd(structures, atoms, max_rmsd=0.25, max_dev=None, energies=None, max_dE=0.0,

@@ -312,6 +312,11 @@ int fc_csearch_apply(const double* starts, int32_t n_starts, int32_t n_atoms, co
 int fc_structure_clash_batch(const double* coords, int64_t n, int32_t n_atoms, const int32_t* ids, int32_t n_ids,
                              double thresh, int64_t* count_out, double* closest_out);
 
+/* dst[j] = the j-th row of src with mask != 0 (row_bytes each), copied by several host threads: the
+ * `structures[mask]` every pruning entry point returns (consumer: apply_mask, embedder.py:1400-1408).
+ * n_dst must equal the number of selected rows. */
+int fc_take_rows(const void* src, int64_t row_bytes, const uint8_t* mask, int64_t n, void* dst, int64_t n_dst);
+
 /* FP32 FMA-pipe peak probe used by bench.py for the roofline denominator: runs a dependent-free
  * FFMA2 loop on every SM and returns achieved TFLOP/s (2 flop per FMA lane). */
 int fc_probe_fp32_peak(double* tflops_out, double* ms_out, void* stream);

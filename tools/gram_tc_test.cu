@@ -41,6 +41,7 @@ int main(int argc, char** argv) {
     const int nh = argc > 2 ? atoi(argv[2]) : 58;
     const int seg = argc > 3 ? atoi(argv[3]) : 5;
     const bool check = n <= 2000;
+    const int no_math = argc > 4 ? atoi(argv[4]) : 0;
     int kc = (nh + 3) / 4; if (kc & 1) ++kc;
     const double max_rmsd = 0.5, band = 0.05;
     std::mt19937_64 rng(12345);
@@ -88,7 +89,8 @@ int main(int argc, char** argv) {
     a.img = d_img; a.gp = d_gp; a.spos = d_spos; a.energies = nullptr; a.max_dE = 0; a.work = d_work; a.n_work = (int)work.size(); a.kc = kc;
     const float lim = (float)(max_rmsd + band);
     a.thr_e = lim * lim * nh; a.e0_scale = 1.0f - 1.7320508f * (1.0f / 512.0f);
-    a.cand = d_cand; a.n_cand = d_nc; a.cand_cap = cand_cap; a.dump = d_dump; a.dump_ld = dump_ld; a.error = d_err;
+    a.cand = d_cand; a.n_cand = d_nc; a.cand_cap = cand_cap; a.dump = d_dump; a.dump_ld = dump_ld; a.error = d_err; a.no_math = no_math;
+    long long* d_prof; CK(cudaMalloc(&d_prof, 64)); CK(cudaMemset(d_prof, 0, 64)); a.prof = d_prof;
     int dev_sms = 0; CK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, 0));
     const size_t smem = fc::gram_smem_bytes(kc);
     CK(cudaFuncSetAttribute(fc::gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -107,6 +109,9 @@ int main(int argc, char** argv) {
     unsigned long long nc = 0; CK(cudaMemcpy(&nc, d_nc, 8, cudaMemcpyDeviceToHost));
     const double pairs = 0.5 * n * (double)(n - 1);
     printf("kernel %.3f ms, %.3e pairs -> %.3e pairs/s, candidates %llu\n", best, pairs, pairs / (best * 1e-3), nc);
+    { long long pr[8]; CK(cudaMemcpy(pr, d_prof, 64, cudaMemcpyDeviceToHost));
+      if (pr[3] && pr[6]) printf("CTA0 per tile (cycles): mma thread wait B %.0f, wait D_EMPTY %.0f, issue+commit %.0f | epilogue warp: wait D_FULL %.0f, ld+arrive %.0f  (tiles %lld)\n",
+             (double)pr[0] / pr[3], (double)pr[1] / pr[3], (double)pr[2] / pr[3], (double)pr[4] / pr[6], (double)pr[5] / pr[6], pr[3]); }
     if (!check) return 0;
 
     std::vector<float> dump((size_t)n_pos * dump_ld * 9);
