@@ -16,11 +16,12 @@
 // stride 3 * kc * 128 B) and as operand B (N = 48 = 16 positions x 3 components: 6 row groups,
 // stride kc * 128 B), so a tile is one contiguous copy.
 //
-// CTA = 320 threads, one per SM, persistent over work items (128-row block x range of 16-column
-// tiles): warp 0 = copy producer (A once per item, B tiles through a 4-stage ring), warp 1 = MMA
-// issuer (3 components x kc / 2 k-steps of tcgen05.mma M128 N48 K8 per tile, two accumulator stages in
-// TMEM), warps 2-9 = epilogue (tcgen05.ld of 8 pairs' 3x3 blocks per thread, Frobenius bound, closed
-// form singular values for the few pairs that survive it).
+// CTA = 608 threads, one per SM, persistent over work items (128-row block x range of 16-column
+// tiles): warp 0 = copy producer (A once per item, B tiles through a 4-stage ring), warps 1 and 18 =
+// MMA issuers (alternate tiles; 3 components x kc / 2 k-steps of tcgen05.mma M128 N48 K8 per tile, two
+// accumulator stages in TMEM), warps 2-17 = epilogue (tcgen05.ld of 4 pairs' 3x3 blocks per thread,
+// Frobenius bound, cofactor bound, and a shared-memory queue that finishes the few remaining pairs with
+// a Newton iteration on the QCP quartic, 32 at a time).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -43,7 +44,7 @@ struct GramArgs {
     double max_dE;
     const GramWork* work;
     int n_work;
-    int kc;                   // 16-byte k-cores per row (even, <= 24): atoms padded to 4 * kc
+    int kc;                   // 16-byte k-cores per row (even, <= kGramMaxKc): atoms padded to 4 * kc
     float thr_e;              // (max_rmsd + band)^2 * nh
     float e0_scale;           // 1 - sqrt(3) * (bound on the relative TF32 product error)
     int2* cand;               // pairs the screen could not rule out (structure indices, x < y)
@@ -56,16 +57,18 @@ struct GramArgs {
     int no_math;              // debug: the epilogue only drains tensor memory (measures the MMA / copy pipeline alone)
 };
 
-constexpr int kGramThreads = 352;
+constexpr int kGramEpiWarps = 16;
+constexpr int kGramThreads = 32 * (3 + kGramEpiWarps);  // producer, two MMA issuers, epilogue warps
 constexpr int kGramBStages = 4;
-constexpr int kGramMaxKc = 24;
+constexpr int kGramMaxKc = 22;   // <= 88 selected atoms: operands + pair queues must fit the 227 KB of shared memory
+constexpr int kGramQueue = 32;   // entries of an epilogue warp's queue of pairs that need the Newton iteration
 // Relative bound on |H_tf32 - H|_F / (|p| |q|): operands are rounded to nearest TF32 (2^-11 each, so 2^-10 on a
 // product, Cauchy-Schwarz over the atoms); doubled to cover the accumulation inside the tensor core.  Measured on
 // random ensembles: 1.1e-4 (tools/gram_tc_test.cu).
 constexpr float kGramTf32Eps = 1.0f / 512.0f;
 
 __host__ __device__ inline size_t gram_smem_bytes(int kc) {
-    return (size_t)6144 * kc + (size_t)kGramBStages * 768 * kc + 256;
+    return (size_t)6144 * kc + (size_t)kGramBStages * 768 * kc + 256 + (size_t)kGramEpiWarps * 6 * kGramQueue * sizeof(float);
 }
 
 // ---- PTX plumbing -----------------------------------------------------------------------------------
@@ -127,6 +130,13 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, float* v) {
     v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
     v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
 }
+__device__ __forceinline__ void tmem_ld4(unsigned taddr, float* v) {
+    unsigned r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(taddr));
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 }  // namespace gram
@@ -162,6 +172,34 @@ __global__ void __launch_bounds__(256) gram_pack_kernel(const float4* __restrict
 }
 
 // ---- the Gram screen --------------------------------------------------------------------------------
+// Finishes the queued pairs of one warp, one lane per pair.  Entry = {u, f2, cc, det, row structure, column structure}.
+// Newton from above on  P(x) = (x^2 - f2)^2 - 8 det x - 4 cc  (the QCP characteristic polynomial, largest root = sum of the
+// singular values with the sign of det on the smallest): every iterate stays above the root, so each is a valid upper
+// bound; a pair whose bound never rules it out becomes a candidate for the FP64 kernel.
+__device__ __forceinline__ void gram_newton_flush(const GramArgs& a, const float* queue, int qn, int lane) {
+    __syncwarp();
+    if (lane < qn) {
+        const float* e = queue + 6 * lane;
+        const float u = e[0], f2 = e[1], cc = e[2], det = e[3];
+        float lam = sqrtf(f2 + 2.0f * sqrtf(3.0f * cc)) * 1.000001f;  // the pass-2 bound: the iteration starts above the root
+        bool reject = u - 2.0f * lam > 0.f;
+        for (int it = 0; it < 8 && !reject; ++it) {
+            const float tt = lam * lam - f2;
+            const float pv = tt * tt - 8.0f * det * lam - 4.0f * cc, dp = 4.0f * lam * tt - 8.0f * det;
+            if (!(dp > 0.f) || !(pv > 0.f)) break;
+            const float step = __fdividef(pv, dp);
+            lam -= step;
+            reject = u - 2.0f * lam > 0.f;
+            if (step <= 1e-5f * lam) break;
+        }
+        if (!reject) {
+            const unsigned long long slot = atomicAdd(a.n_cand, 1ull);
+            if ((long long)slot < a.cand_cap) a.cand[slot] = make_int2(__float_as_int(e[4]), __float_as_int(e[5]));
+        }
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
     using namespace gram;
     extern __shared__ __align__(128) uint8_t gram_smem[];
@@ -184,7 +222,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
         bar_init(A_FULL, 1);
         bar_init(A_EMPTY, 2);
         for (unsigned s = 0; s < kGramBStages; ++s) { bar_init(B_FULL(s), 1); bar_init(B_EMPTY(s), 1); }
-        for (unsigned s = 0; s < 2; ++s) { bar_init(D_FULL(s), 1); bar_init(D_EMPTY(s), 8); }
+        for (unsigned s = 0; s < 2; ++s) { bar_init(D_FULL(s), 1); bar_init(D_EMPTY(s), kGramEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // 512 columns of tensor memory: two accumulator stages x 3 components x 64 columns
@@ -223,7 +261,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
             }
         }
         __syncwarp();
-    } else if (warp == 1 || warp == 10) {
+    } else if (warp == 1 || warp == 2 + kGramEpiWarps) {
         if (lane == 0) {  // ---- MMA issuers ----
             // Two issuing threads: a tcgen05.mma of this shape costs ~80 cycles in its issuing thread whatever N is
             // (measured, tools/gram_tc_test.cu), so one thread alone caps the kernel.  Tile g (counted over the whole
@@ -241,11 +279,11 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                 for (int t = 0; t < wk.n_col_tiles; ++t, ++g) {
                     if ((g & 1u) != issuer) continue;
                     const unsigned bs = g % kGramBStages;
-                    const long long c0 = clock64();
+                    const long long c0 = a.prof ? clock64() : 0;
                     bar_wait(B_FULL(bs), (bphases >> bs) & 1u, a.error, 4);
-                    const long long c1 = clock64();
+                    const long long c1 = a.prof ? clock64() : 0;
                     bar_wait(D_EMPTY(issuer), dphase ^ 1u, a.error, 5);
-                    const long long c2 = clock64();
+                    const long long c2 = a.prof ? clock64() : 0;
                     tc_fence_after();
                     // k-step outermost, the 3 independent accumulators (components) innermost
                     const int ksteps = (a.no_math & 2) ? 1 : kc / 2;
@@ -269,12 +307,17 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
             }
         }
         __syncwarp();
-    } else if (warp < 10) {
-        // ---- epilogue: thread = one row of the block (TMEM lane), 8 columns of the tile ----
+    } else if (warp < 2 + kGramEpiWarps) {
+        // ---- epilogue: thread = one row of the block (TMEM lane), 4 of the 16 columns of the tile ----
+        // 16 warps: four per scheduler, so that the dependent FP32 chains of one warp are covered by the others
         const int quarter = warp & 3;          // TMEM lanes 32 * (warp % 4) ... are the ones this warp may read
-        const int half = (warp - 2) >> 2;      // which 8 of the 16 column positions
+        const int part = (warp - 2) >> 2;      // which 4 of the 16 column positions
         const int row_in_block = quarter * 32 + lane;
+        float* queue = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 2) * (6 * kGramQueue);  // this warp's pair queue
+        int qn = 0;                                                                              // warp-uniform fill level
         unsigned dstage = 0, dphase = 0;
+        // accumulator column of (column position 8 g + r, component cb) = 24 g + 8 cb + r
+        const unsigned tcol = (unsigned)(24 * (part >> 1) + 4 * (part & 1));
         for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
             const GramWork wk = a.work[w];
             const int prow = wk.row0 + row_in_block;
@@ -284,21 +327,19 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
             for (int t = 0; t < wk.n_col_tiles; ++t) {
                 __syncwarp();  // the tensor-memory loads below are warp-collective
                 // column metadata first: these loads fly while the accumulator is still being produced
-                const int pcol0 = 16 * (wk.col_tile0 + t) + 8 * half;
-                const int4 sc0 = *reinterpret_cast<const int4*>(a.spos + pcol0);
-                const int4 sc1 = *reinterpret_cast<const int4*>(a.spos + pcol0 + 4);
-                const float4 gc0 = *reinterpret_cast<const float4*>(a.gp + pcol0);
-                const float4 gc1 = *reinterpret_cast<const float4*>(a.gp + pcol0 + 4);
-                const long long e0 = clock64();
+                const int pcol0 = 16 * (wk.col_tile0 + t) + 4 * part;
+                const int4 sc = *reinterpret_cast<const int4*>(a.spos + pcol0);
+                const float4 gc = *reinterpret_cast<const float4*>(a.gp + pcol0);
+                const long long e0 = a.prof ? clock64() : 0;
                 bar_wait(D_FULL(dstage), dphase, a.error, 6);
-                const long long e1 = clock64();
+                const long long e1 = a.prof ? clock64() : 0;
                 tc_fence_after();
-                float h[3][3][8];  // [component of the row structure][component of the column structure][column]
-                const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + dstage * 256 + half * 24;
+                float h[3][3][4];  // [component of the row structure][component of the column structure][column]
+                const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + dstage * 256 + tcol;
 #pragma unroll
                 for (int ca = 0; ca < 3; ++ca)
 #pragma unroll
-                    for (int cb = 0; cb < 3; ++cb) tmem_ld8(taddr + ca * 64 + cb * 8, h[ca][cb]);
+                    for (int cb = 0; cb < 3; ++cb) tmem_ld4(taddr + ca * 64 + cb * 8, h[ca][cb]);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -312,67 +353,79 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
 
                 if (a.dump) {
 #pragma unroll
-                    for (int r = 0; r < 8; ++r)
+                    for (int r = 0; r < 4; ++r)
 #pragma unroll
                         for (int ca = 0; ca < 3; ++ca)
 #pragma unroll
                             for (int cb = 0; cb < 3; ++cb)
                                 a.dump[((size_t)prow * a.dump_ld + pcol0 + r) * 9 + 3 * ca + cb] = h[ca][cb][r];
                 }
-                if ((a.no_math & 1) || s_row < 0 || pcol0 + 7 <= prow || pcol0 >= wk.pend) continue;
-                const int s_col[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-                const float g_col[8] = {gc0.x, gc0.y, gc0.z, gc0.w, gc1.x, gc1.y, gc1.z, gc1.w};
+                const bool live = !((a.no_math & 1) || s_row < 0 || pcol0 + 3 <= prow || pcol0 >= wk.pend);
+                const int s_col[4] = {sc.x, sc.y, sc.z, sc.w};
+                const float g_col[4] = {gc.x, gc.y, gc.z, gc.w};
                 // Lower bound on the true sum of squared deviations: E >= e0 - 2 S, S = sum of the singular values of H (largest
-                // root of the quartic below); the TF32 rounding of H moves S by at most sqrt(3) eps |p| |q| <= sqrt(3) eps e0 / 2,
-                // which e0_scale takes off e0.  A pair is ruled out as soon as an UPPER bound on S gives  u - 2 S > 0.
-                // Pass 1, branch-free over the 8 columns: S <= sqrt(3) |H|_F, i.e. u >= 0 and u^2 >= 12 |H|_F^2.
+                // root of the quartic in gram_newton_flush); the TF32 rounding of H moves S by at most
+                // sqrt(3) eps |p| |q| <= sqrt(3) eps e0 / 2, which e0_scale takes off e0.  A pair is ruled out as soon as an UPPER
+                // bound on S gives  u - 2 S > 0.
+                // Pass 1, branch-free over the columns: S <= sqrt(3) |H|_F, i.e. u >= 0 and u^2 >= 12 |H|_F^2.
                 unsigned und = 0;
-                float uu[8], ff[8];
+                float uu[4], ff[4];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
+                for (int r = 0; r < 4; ++r) {
                     const int pcol = pcol0 + r;
-                    const bool valid = prow < pcol && pcol < wk.pend && s_col[r] >= 0;
+                    const bool valid = live && prow < pcol && pcol < wk.pend && s_col[r] >= 0;
                     uu[r] = (g_row + g_col[r]) * a.e0_scale - a.thr_e;
                     const float fa = h[0][0][r] * h[0][0][r] + h[0][1][r] * h[0][1][r] + h[0][2][r] * h[0][2][r];
                     const float fb = h[1][0][r] * h[1][0][r] + h[1][1][r] * h[1][1][r] + h[1][2][r] * h[1][2][r];
                     const float fc2 = h[2][0][r] * h[2][0][r] + h[2][1][r] * h[2][1][r] + h[2][2][r] * h[2][2][r];
                     ff[r] = fa + fb + fc2;
-                    if (valid && !(uu[r] >= 0.f && uu[r] * uu[r] >= 12.0f * ff[r])) und |= 1u << r;
+                    if (valid && (!(uu[r] >= 0.f && uu[r] * uu[r] >= 12.0f * ff[r]) || (a.no_math & 64))) und |= 1u << r;
                 }
-                if (und == 0) continue;
-                // Pass 2 for the columns pass 1 could not rule out
+                if (!__any_sync(0xffffffffu, und != 0)) continue;
+                // Pass 2 (about a third of the pairs of a conformer ensemble get here), again branch-free over the columns:
+                // S^2 = f2 + 2 e2 with e2 = sum of the pairwise products of the singular values <= sqrt(3 cc), cc = |cof H|_F^2.
+                // Without square roots:  u - 2 sqrt(f2 + 2 sqrt(3 cc)) > 0  <=>  u > 0,  v = u^2 - 4 f2 > 0,  v^2 > 192 cc.
+                float ccs[4], dets[4];
+                unsigned surv = 0;
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    if (!(und & (1u << r))) continue;
-                    const float u = uu[r], f2 = ff[r];
-                    // second symmetric function of the squared singular values = |cof H|_F^2, and det H
+                for (int r = 0; r < 4; ++r) {
                     const float h0 = h[0][0][r], h1 = h[0][1][r], h2 = h[0][2][r], h3 = h[1][0][r], h4 = h[1][1][r],
                                 h5 = h[1][2][r], h6 = h[2][0][r], h7 = h[2][1][r], h8 = h[2][2][r];
                     const float c0 = h4 * h8 - h5 * h7, c1 = h5 * h6 - h3 * h8, c2 = h3 * h7 - h4 * h6;
                     const float c3 = h2 * h7 - h1 * h8, c4 = h0 * h8 - h2 * h6, c5 = h1 * h6 - h0 * h7;
                     const float c6 = h1 * h5 - h2 * h4, c7 = h2 * h3 - h0 * h5, c8 = h0 * h4 - h1 * h3;
-                    const float cc = c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3 + c4 * c4 + c5 * c5 + c6 * c6 + c7 * c7 + c8 * c8;
-                    const float det = h0 * c0 + h1 * c1 + h2 * c2;
-                    // S^2 = f2 + 2 e2 with e2 = sum of pairwise products of the singular values <= sqrt(3 cc); the approximate
-                    // square roots are scaled up by 2^-20 so that the result stays an upper bound
-                    float lam = __fsqrt_rn(f2 + 2.0f * __fsqrt_rn(3.0f * cc)) * 1.000001f;
-                    bool reject = u - 2.0f * lam > 0.f;
-                    // Newton from above on  P(x) = (x^2 - f2)^2 - 8 det x - 4 cc  (the QCP characteristic polynomial): every
-                    // iterate stays above the largest root S, so each one is a valid upper bound
-                    for (int it = 0; it < 6 && !reject; ++it) {
-                        const float tt = lam * lam - f2;
-                        const float pv = tt * tt - 8.0f * det * lam - 4.0f * cc, dp = 4.0f * lam * tt - 8.0f * det;
-                        if (!(dp > 0.f) || !(pv > 0.f)) break;
-                        const float step = __fdividef(pv, dp);
-                        lam -= step;
-                        reject = u - 2.0f * lam > 0.f;
-                        if (step <= 1e-5f * lam) break;
-                    }
-                    if (reject) continue;
-                    if (a.energies && !(fabs(e_row - a.energies[s_col[r]]) < a.max_dE)) continue;
-                    const unsigned long long slot = atomicAdd(a.n_cand, 1ull);
-                    if ((long long)slot < a.cand_cap) a.cand[slot] = make_int2(s_row, s_col[r]);
+                    ccs[r] = (c0 * c0 + c1 * c1 + c2 * c2) + (c3 * c3 + c4 * c4 + c5 * c5) + (c6 * c6 + c7 * c7 + c8 * c8);
+                    dets[r] = h0 * c0 + h1 * c1 + h2 * c2;
+                    const float v = uu[r] * uu[r] - 4.0f * ff[r];
+                    const bool reject = uu[r] > 0.f && v > 0.f && v * v > 192.0f * ccs[r];
+                    if ((und & (1u << r)) && !reject) surv |= 1u << r;
                 }
+                if (!__any_sync(0xffffffffu, surv != 0)) continue;
+                // The few pairs that survive this too are queued (per warp, shared memory) and finished 32 at a time by
+                // gram_newton_flush, so the rare expensive path never runs with one active lane.
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    bool push = (surv >> r) & 1u;
+                    if (push && a.energies && !(fabs(e_row - a.energies[s_col[r]]) < a.max_dE)) push = false;
+                    const unsigned m = __ballot_sync(0xffffffffu, push);
+                    if (m == 0) continue;
+                    const int add = __popc(m);
+                    if (qn + add > kGramQueue) {
+                        gram_newton_flush(a, queue, qn, lane);
+                        qn = 0;
+                    }
+                    if (push) {
+                        float* e = queue + 6 * (qn + __popc(m & ((1u << lane) - 1u)));
+                        e[0] = uu[r]; e[1] = ff[r]; e[2] = ccs[r]; e[3] = dets[r];
+                        e[4] = __int_as_float(s_row); e[5] = __int_as_float(s_col[r]);
+                    }
+                    qn += add;
+                    __syncwarp();
+                }
+            }
+            if (qn) {
+                gram_newton_flush(a, queue, qn, lane);
+                qn = 0;
             }
         }
     }

@@ -639,7 +639,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                     pairs_skipped += (int64_t)len * (len - 1) / 2 - evaluated;
                 }
                 // column ranges are cut so that every SM gets several work items of similar size
-                const int64_t seg = std::min<int64_t>(1024, std::max<int64_t>(16, col_tiles_total / ((int64_t)sm_count() * 8)));
+                const int64_t seg = std::min<int64_t>(1024, std::max<int64_t>(16, col_tiles_total / ((int64_t)sm_count() * 32)));
                 int64_t item_no = 0;
                 for (const RowBlock& b : blocks)
                     for (int c0 = b.c_min; c0 < b.tile_end; c0 += (int)seg) {
@@ -753,6 +753,11 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                             cudaEventElapsedTime(&ms, ev_g0, ev_g1);
                             t_gram += ms;
                             cand_total += n_cand;
+                            long long tiles_in_pass = 0;
+                            for (const GramWork& wk : work) tiles_in_pass += wk.n_col_tiles;
+                            fprintf(stderr, "  pass k=%lld active=%lld items=%zu col-tiles=%lld (%.3e pair slots) screen %.3f ms, %llu candidates\n",
+                                    (long long)k, (long long)n_active, work.size(), tiles_in_pass, 2048.0 * (double)tiles_in_pass, ms,
+                                    n_cand);
                         }
                         if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune screen", __FILE__, __LINE__); break; }
                         if ((long long)n_cand > cand_cap) {  // list too small: repeat with the exact size
