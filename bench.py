@@ -483,7 +483,28 @@ def run_extras():
                                    "pairs_eigen_solved": rep.pairs_solved, "passes": rep.passes,
                                    "kept": int(mask.sum()), "n": len(mask), "seconds": dt,
                                    "h2d_bytes": int(structures.nbytes),
+                                   "library_ms": rep.wall_ms,
                                    "conventions": {"keep": rep.keep, "pass_mode": rep.pass_mode}}
+    if rep.screen_ms > 0:
+        # roofline of the tensor-core screen (fc::gram_tc_kernel), summed over the launches of the run: algorithmic work per
+        # pair = 51 N_h FLOP (covariance + norms + rotate-and-deviate); the tensor cores execute the covariance
+        # only, 18 FLOP per atom slot (K padded to a multiple of 8) per pair slot of every 128 x 16 tile
+        peaks, peak_kind = _peaks()
+        tf32_peak = 0.5 * float(peaks["bf16_tflops"])
+        sec = rep.screen_ms * 1e-3
+        kpad = 8 * ((rep.n_sel + 7) // 8)
+        alg_tf = 51.0 * rep.n_sel * rep.pairs_tiled / sec / 1e12
+        exe_tf = 18.0 * kpad * rep.screen_pair_slots / sec / 1e12
+        out["C4_rmsd_pruning_200k"]["roofline"] = {
+            "bound": "tensor", "kernel": "fc::gram_tc_kernel", "achieved": alg_tf, "peak": tf32_peak, "unit": "TFLOP/s",
+            "frac": alg_tf / tf32_peak, "traffic": None, "executed_tflops": exe_tf, "executed_frac": exe_tf / tf32_peak,
+            "kernel_ms_total": rep.screen_ms, "launches": rep.screen_launches, "pairs": rep.pairs_tiled,
+            "pair_slots": rep.screen_pair_slots, "candidates_to_fp64": rep.screen_candidates, "atoms_in_rmsd": rep.n_sel,
+            "peak_source": f"TF32 dense = half the {peak_kind} bf16 figure of MEASURED_PEAKS.json (no TF32 figure there)",
+            "note": "TF32 Gram matrix of the centred heavy-atom coordinates (tcgen05.mma M128 N48 K8, FP32 accumulators in TMEM); "
+                    "the kernel is bound by MMA issue (about 65 cycles per instruction whatever N is) and by its FP32 epilogue, "
+                    "not by tensor throughput; pairs the screen cannot rule out are re-evaluated in FP64",
+            "screen_pairs_per_s": rep.pairs_tiled / sec}
     del structures, kept, mask
     # TFD ensemble pruning (torsion_module.py:957-1043): 20 000 conformers of a 40-atom molecule, 12 quadruplets
     rng = np.random.default_rng(synthetic.SEED + 6)

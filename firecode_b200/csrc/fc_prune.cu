@@ -488,6 +488,14 @@ static int64_t gram_item_pairs(int64_t row0, int64_t col_lo, int64_t col_hi, int
     return total;
 }
 
+static thread_local double g_prune_timing[6] = {0, 0, 0, 0, 0, 0};
+
+extern "C" int fc_prune_timing(double* out6) {
+    FC_REQUIRE(out6, "fc_prune_timing: null pointer");
+    for (int i = 0; i < 6; ++i) out6[i] = g_prune_timing[i];
+    return FC_OK;
+}
+
 // mode 0: RMSD, mode 1: MOI.  `sel` = indices of the atoms used for the RMSD (heavy atoms).
 // rank / world / gather: pair tiles of every pass are dealt round-robin to the ranks; the similar pairs each
 // rank finds are all-gathered through `gather` (NCCL or gloo behind the host language) and every rank resolves
@@ -519,7 +527,10 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
     double t_tiles = 0, t_kernels = 0, t_resolve = 0, t_upload = 0, t_gram = 0;
     unsigned long long cand_total = 0;
     cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr;
-    if (trace) { cudaEventCreate(&ev_g0); cudaEventCreate(&ev_g1); }
+    cudaEventCreate(&ev_g0);
+    cudaEventCreate(&ev_g1);
+    double screen_slots = 0;
+    int64_t screen_launches = 0;
     cudaStream_t s;
     FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     int rc = FC_OK;
@@ -736,9 +747,9 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                             const size_t smem = gram_smem_bytes(kc);
                             PR(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                             const unsigned grid = (unsigned)std::min<size_t>((size_t)sm_count(), work.size());
-                            if (trace) cudaEventRecord(ev_g0, s);
+                            cudaEventRecord(ev_g0, s);
                             gram_tc_kernel<<<grid, kGramThreads, smem, s>>>(ga);
-                            if (trace) cudaEventRecord(ev_g1, s);
+                            cudaEventRecord(ev_g1, s);
                         } else {
                             const size_t smem = (size_t)2 * PS_ATOMS * PS_LD * sizeof(float4);
                             PR(cudaFuncSetAttribute(prune_screen_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -748,14 +759,16 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                         unsigned long long n_cand = 0;
                         PR(cudaMemcpyAsync(&n_cand, d_eval.p + 2, 8, cudaMemcpyDeviceToHost, s));
                         PR(cudaStreamSynchronize(s));
-                        if (trace && use_tc && e == cudaSuccess) {
+                        if (use_tc && e == cudaSuccess) {
                             float ms = 0;
                             cudaEventElapsedTime(&ms, ev_g0, ev_g1);
                             t_gram += ms;
                             cand_total += n_cand;
                             long long tiles_in_pass = 0;
                             for (const GramWork& wk : work) tiles_in_pass += wk.n_col_tiles;
-                            fprintf(stderr, "  pass k=%lld active=%lld items=%zu col-tiles=%lld (%.3e pair slots) screen %.3f ms, %llu candidates\n",
+                            screen_slots += 2048.0 * (double)tiles_in_pass;
+                            ++screen_launches;
+                            if (trace) fprintf(stderr, "  pass k=%lld active=%lld items=%zu col-tiles=%lld (%.3e pair slots) screen %.3f ms, %llu candidates\n",
                                     (long long)k, (long long)n_active, work.size(), tiles_in_pass, 2048.0 * (double)tiles_in_pass, ms,
                                     n_cand);
                         }
@@ -830,12 +843,23 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
     }
     cudaStreamSynchronize(s);
     cudaStreamDestroy(s);
-    if (rc) return rc;
+    if (rc) {
+        cudaEventDestroy(ev_g0);
+        cudaEventDestroy(ev_g1);
+        return rc;
+    }
     if (trace)
         fprintf(stderr, "fc_prune: total %.1f ms: upload+centre %.1f, tile lists %.1f, kernels+readback %.1f (tensor-core screen %.1f, "
                 "%llu candidates), resolve %.1f\n",
                 now() - t_begin, t_upload, t_tiles, t_kernels, t_gram, cand_total, t_resolve);
-    if (ev_g0) { cudaEventDestroy(ev_g0); cudaEventDestroy(ev_g1); }
+    cudaEventDestroy(ev_g0);
+    cudaEventDestroy(ev_g1);
+    g_prune_timing[0] = now() - t_begin;
+    g_prune_timing[1] = t_gram;
+    g_prune_timing[2] = (double)screen_launches;
+    g_prune_timing[3] = screen_slots;
+    g_prune_timing[4] = (double)cand_total;
+    g_prune_timing[5] = (double)n_sel;
     memcpy(mask_out, mask.data(), (size_t)n);
     if (n_ties_out) *n_ties_out = ties_total;
     if (stats_out) {

@@ -30,6 +30,12 @@ class PruneReport:
     n_ties_total: int = 0
     keep: str = "first"
     pass_mode: str = "greedy"
+    wall_ms: float = 0.0            # inside the library call
+    screen_ms: float = 0.0          # CUDA-event time of the tensor-core screen launches (0 when another screen ran)
+    screen_launches: int = 0
+    screen_pair_slots: float = 0.0  # 2048 per 128 x 16 tile the screen evaluated
+    screen_candidates: int = 0      # pairs handed to the FP64 exact kernel
+    n_sel: int = 0                  # atoms per structure that enter the RMSD
 
 
 last_report: PruneReport | None = None
@@ -84,7 +90,11 @@ def _run(structures, mode, sel, masses, max_rmsd, max_dev, moi_dev, energies, ma
         cb = _lib.ALLGATHER_FN(_gather)
         rc = lib.fc_prune_sharded(*args, int(rank), int(world), cb, None)
     _lib.check(rc, "fc_prune")
-    last_report = PruneReport(passes=int(stats[0]), pairs_tiled=int(stats[1]), pairs_solved=int(stats[2]),
+    tm = np.zeros(6, dtype=np.float64)
+    lib.fc_prune_timing(_ptr(tm))
+    last_report = PruneReport(wall_ms=float(tm[0]), screen_ms=float(tm[1]), screen_launches=int(tm[2]),
+                              screen_pair_slots=float(tm[3]), screen_candidates=int(tm[4]), n_sel=int(tm[5]),
+                              passes=int(stats[0]), pairs_tiled=int(stats[1]), pairs_solved=int(stats[2]),
                               pairs_skipped=int(stats[3]),
                               ties=ties[: min(int(n_ties.value), tie_cap)], n_ties_total=int(n_ties.value),
                               keep=keep, pass_mode=pass_mode)

@@ -312,6 +312,11 @@ int fc_csearch_apply(const double* starts, int32_t n_starts, int32_t n_atoms, co
 int fc_structure_clash_batch(const double* coords, int64_t n, int32_t n_atoms, const int32_t* ids, int32_t n_ids,
                              double thresh, int64_t* count_out, double* closest_out);
 
+/* Timing of the last fc_prune / fc_prune_sharded call on this thread (bench.py's roofline of the tensor-core
+ * screen): out6 = {wall ms of the call, CUDA-event ms summed over the screen kernel launches, launches,
+ * pair slots the screen evaluated (2048 per 128 x 16 tile), candidates it passed on, atoms per structure}. */
+int fc_prune_timing(double* out6);
+
 /* dst[j] = the j-th row of src with mask != 0 (row_bytes each), copied by several host threads: the
  * `structures[mask]` every pruning entry point returns (consumer: apply_mask, embedder.py:1400-1408).
  * n_dst must equal the number of selected rows. */

@@ -147,3 +147,45 @@ def test_prune_skips_pairs_known_from_earlier_passes(gpu):
     assert rep.passes >= 4 and rep.pairs_skipped > 0
     _, ref_mask = ref_pruner.prune_by_rmsd(structures, atoms, 0.3, ties=port.Ties(eps=1e-6, forced=_forced(rep)))
     assert np.array_equal(mask, ref_mask)
+
+
+@pytest.mark.parametrize("n_atoms,expect_tc", [(120, True), (36, True), (170, False)])
+def test_prune_screen_flavours_agree(gpu, monkeypatch, n_atoms, expect_tc):
+    """The tensor-core (TF32) screen, the FP32 screen and the FP64-only pair kernel must give the same mask: the
+    screens only decide which pairs reach the FP64 evaluation.  More than 88 selected atoms -> FP32 screen."""
+    rng = np.random.default_rng(synthetic.SEED + n_atoms)
+    atoms, structures, _ = synthetic.pruning_ensemble(rng, 3000, n_atoms, 60, jitter=(0.02, 0.45))
+    masks = {}
+    for name, env in (("tc", {}), ("fp32", {"FC_PRUNE_TC": "0"}), ("fp64", {"FC_PRUNE_FP64": "1"})):
+        for k in ("FC_PRUNE_TC", "FC_PRUNE_FP64"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _, masks[name] = pruner.prune_by_rmsd(structures, atoms, 0.5)
+        rep = pruner.last_report
+        if name == "tc":
+            assert (rep.screen_launches > 0) == expect_tc
+            assert rep.n_sel == int(np.sum(np.asarray(atoms) != "H"))
+            forced = _forced(rep)
+        else:
+            assert rep.screen_launches == 0
+    assert np.array_equal(masks["tc"], masks["fp32"])
+    assert np.array_equal(masks["tc"], masks["fp64"])
+    assert 1 < masks["tc"].sum() < len(structures)
+    _, ref_mask = ref_pruner.prune_by_rmsd(structures[:600], atoms, 0.5)
+    _, sub_mask = pruner.prune_by_rmsd(structures[:600], atoms, 0.5)
+    assert np.array_equal(sub_mask, ref_mask)
+
+
+def test_prune_all_similar_and_all_distinct(gpu):
+    """Every pair similar (the queue of pairs the screen cannot rule out overflows and is flushed repeatedly) and
+    every pair dissimilar (the screen rules out everything)."""
+    rng = np.random.default_rng(11)
+    atoms, structures, _ = synthetic.pruning_ensemble(rng, 1500, 60, 1, jitter=(0.0, 0.02))
+    _, mask = pruner.prune_by_rmsd(structures, atoms, 0.5)
+    assert mask.sum() == 1 and mask[0]
+    assert pruner.last_report.screen_candidates > 0
+    structures = 3.0 * rng.normal(size=(1500, 40, 3))      # unrelated point clouds
+    _, mask = pruner.prune_by_rmsd(structures, np.array(["C"] * 40), 0.5)
+    assert mask.all()
+    assert pruner.last_report.screen_launches > 0 and pruner.last_report.screen_candidates == 0
