@@ -16,10 +16,10 @@
 // stride 3 * kc * 128 B) and as operand B (N = 48 = 16 positions x 3 components: 6 row groups,
 // stride kc * 128 B), so a tile is one contiguous copy.
 //
-// CTA = 608 threads, one per SM, persistent over work items (128-row block x range of 16-column
-// tiles): warp 0 = copy producer (A once per item, B tiles through a 4-stage ring), warps 1 and 18 =
-// MMA issuers (alternate tiles; 3 components x kc / 2 k-steps of tcgen05.mma M128 N48 K8 per tile, two
-// accumulator stages in TMEM), warps 2-17 = epilogue (tcgen05.ld of 4 pairs' 3x3 blocks per thread,
+// CTA = 736 threads, one per SM, persistent over work items (128-row block x range of 16-column
+// tiles): warp 0 = copy producer (A once per item, B tiles through a 4-stage ring), warps 1-6 = MMA
+// issuers (one per accumulator stage and component: kc / 2 k-steps of tcgen05.mma M128 N48 K8 per tile, two
+// accumulator stages in TMEM), warps 7-22 = epilogue (tcgen05.ld of 4 pairs' 3x3 blocks per thread,
 // Frobenius bound, cofactor bound, and a shared-memory queue that finishes the few remaining pairs with
 // a Newton iteration on the QCP quartic, 32 at a time).
 #pragma once
@@ -58,7 +58,8 @@ struct GramArgs {
 };
 
 constexpr int kGramEpiWarps = 16;
-constexpr int kGramThreads = 32 * (3 + kGramEpiWarps);  // producer, two MMA issuers, epilogue warps
+constexpr int kGramIssuers = 6;     // MMA-issuing warps: (accumulator stage, component)
+constexpr int kGramThreads = 32 * (1 + kGramIssuers + kGramEpiWarps);  // producer, MMA issuers, epilogue warps
 constexpr int kGramBStages = 4;
 constexpr int kGramMaxKc = 22;   // <= 88 selected atoms: operands + pair queues must fit the 227 KB of shared memory
 constexpr int kGramQueue = 32;   // entries of an epilogue warp's queue of pairs that need the Newton iteration
@@ -220,9 +221,9 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
 
     if (threadIdx.x == 0) {
         bar_init(A_FULL, 1);
-        bar_init(A_EMPTY, 2);
-        for (unsigned s = 0; s < kGramBStages; ++s) { bar_init(B_FULL(s), 1); bar_init(B_EMPTY(s), 1); }
-        for (unsigned s = 0; s < 2; ++s) { bar_init(D_FULL(s), 1); bar_init(D_EMPTY(s), kGramEpiWarps); }
+        bar_init(A_EMPTY, kGramIssuers);
+        for (unsigned s = 0; s < kGramBStages; ++s) { bar_init(B_FULL(s), 1); bar_init(B_EMPTY(s), 3); }
+        for (unsigned s = 0; s < 2; ++s) { bar_init(D_FULL(s), 3); bar_init(D_EMPTY(s), kGramEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // 512 columns of tensor memory: two accumulator stages x 3 components x 64 columns
@@ -261,44 +262,45 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
             }
         }
         __syncwarp();
-    } else if (warp == 1 || warp == 2 + kGramEpiWarps) {
+    } else if (warp <= kGramIssuers) {
         if (lane == 0) {  // ---- MMA issuers ----
-            // Two issuing threads: a tcgen05.mma of this shape costs ~80 cycles in its issuing thread whatever N is
-            // (measured, tools/gram_tc_test.cu), so one thread alone caps the kernel.  Tile g (counted over the whole
-            // CTA) uses operand slot g % 4 and accumulator stage g % 2; issuer i takes the tiles with g % 2 == i.
+            // Six issuing threads: a tcgen05.mma costs its issuing thread 65-130 cycles whatever N is (the operands go
+            // through uniform registers; measured, tools/gram_tc_test.cu), while the tensor pipe needs ~24 cycles for this
+            // shape, so one issuer caps the kernel at a fifth of what the operand fetch allows.  Tile g (counted over the
+            // whole CTA) uses operand slot g % 4 and accumulator stage g % 2; issuer (stage, comp) issues the kc / 2
+            // k-steps of component comp for the tiles of its stage.
             // instruction descriptor: D = F32 (bit 4), A = B = TF32 (bits 7, 10), both K-major, N = 48 (>> 3 at bit 17),
             // M = 128 (>> 4 at bit 24)
-            const unsigned issuer = warp == 1 ? 0u : 1u;
+            const unsigned stage = (unsigned)(warp - 1) / 3u, comp = (unsigned)(warp - 1) % 3u;
             const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (6u << 17) | (8u << 24);
             unsigned g = 0, bphases = 0, aphase = 0, dphase = 0;  // one phase bit per operand slot
-            const unsigned sA_addr = smem_addr(sA), sB_addr = smem_addr(sB);
+            const unsigned sA_addr = smem_addr(sA) + comp * kc * 128, sB_addr = smem_addr(sB);
+            const unsigned d_tmem = tmem_base + stage * 256 + comp * 64;
             for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
                 const GramWork wk = a.work[w];
                 bar_wait(A_FULL, aphase, a.error, 3);
                 aphase ^= 1;
                 for (int t = 0; t < wk.n_col_tiles; ++t, ++g) {
-                    if ((g & 1u) != issuer) continue;
+                    if ((g & 1u) != stage) continue;
                     const unsigned bs = g % kGramBStages;
                     const long long c0 = a.prof ? clock64() : 0;
                     bar_wait(B_FULL(bs), (bphases >> bs) & 1u, a.error, 4);
                     const long long c1 = a.prof ? clock64() : 0;
-                    bar_wait(D_EMPTY(issuer), dphase ^ 1u, a.error, 5);
+                    bar_wait(D_EMPTY(stage), dphase ^ 1u, a.error, 5);
                     const long long c2 = a.prof ? clock64() : 0;
                     tc_fence_after();
-                    // k-step outermost, the 3 independent accumulators (components) innermost
                     const int ksteps = (a.no_math & 2) ? 1 : kc / 2;
+                    uint64_t da = smem_desc(sA_addr, 128, 3 * kc * 128), db = smem_desc(sB_addr + bs * b_bytes, 128, kc * 128);
                     for (int k = 0; k < ksteps; ++k) {
-                        const uint64_t db = smem_desc(sB_addr + bs * b_bytes + k * 256, 128, kc * 128);
-                        for (unsigned comp = 0; comp < 3; ++comp) {
-                            const uint64_t da = smem_desc(sA_addr + comp * kc * 128 + k * 256, 128, 3 * kc * 128);
-                            mma_tf32(tmem_base + issuer * 256 + comp * 64, da, db, idesc, k > 0 ? 1u : 0u);
-                        }
+                        mma_tf32(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
+                        da += 16;  // next k-step: 256 bytes further, in the 16-byte units of the start-address field
+                        db += 16;
                     }
                     tc_commit(B_EMPTY(bs));
-                    tc_commit(D_FULL(issuer));
+                    tc_commit(D_FULL(stage));
                     bphases ^= 1u << bs;
                     dphase ^= 1u;
-                    if (a.prof && blockIdx.x == 0 && issuer == 0) {
+                    if (a.prof && blockIdx.x == 0 && warp == 1) {
                         const long long c3 = clock64();
                         a.prof[0] += c1 - c0; a.prof[1] += c2 - c1; a.prof[2] += c3 - c2; a.prof[3] += 1;
                     }
@@ -307,13 +309,13 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
             }
         }
         __syncwarp();
-    } else if (warp < 2 + kGramEpiWarps) {
+    } else {
         // ---- epilogue: thread = one row of the block (TMEM lane), 4 of the 16 columns of the tile ----
         // 16 warps: four per scheduler, so that the dependent FP32 chains of one warp are covered by the others
         const int quarter = warp & 3;          // TMEM lanes 32 * (warp % 4) ... are the ones this warp may read
-        const int part = (warp - 2) >> 2;      // which 4 of the 16 column positions
+        const int part = (warp - 1 - kGramIssuers) >> 2;      // which 4 of the 16 column positions
         const int row_in_block = quarter * 32 + lane;
-        float* queue = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 2) * (6 * kGramQueue);  // this warp's pair queue
+        float* queue = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 1 - kGramIssuers) * (6 * kGramQueue);  // this warp's pair queue
         int qn = 0;                                                                              // warp-uniform fill level
         unsigned dstage = 0, dphase = 0;
         // accumulator column of (column position 8 g + r, component cb) = 24 g + 8 cb + r
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) bar_arrive(D_EMPTY(dstage));
-                if (a.prof && blockIdx.x == 0 && threadIdx.x == 64) {
+                if (a.prof && blockIdx.x == 0 && threadIdx.x == 32 * (1 + kGramIssuers)) {
                     const long long e2 = clock64();
                     a.prof[4] += e1 - e0; a.prof[5] += e2 - e1; a.prof[6] += 1;
                 }
