@@ -132,6 +132,7 @@ SIGNATURES = {
     "fc_rmsd_and_max_batch": (C.c_int, [VP, VP, C.c_int64, C.c_int32, C.c_int32, VP, VP]),
     "fc_self_clash_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_double, VP, VP]),
     "fc_structure_clash_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_int32, C.c_double, VP, VP]),
+    "fc_fitness_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, VP, C.c_int32, VP]),
     "fc_prune_timing": (C.c_int, [VP]),
     "fc_take_rows": (C.c_int, [VP, C.c_int64, VP, C.c_int64, VP, C.c_int64]),
     "fc_probe_fp32_peak": (C.c_int, [c_dp, c_dp, VP]),

@@ -253,3 +253,66 @@ extern "C" int fc_structure_clash_batch(const double* coords, int64_t n, int32_t
     return FC_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fitness_check over a batch (optimization_methods.py:163-180, looped by RunEmbedding.fitness_refining,
+// embedder.py:1997-2039): error[s] = sum over the structure's constraints with a target distance of
+// (|x_a - x_b| - target), accumulated in constraint order in FP64 without contraction, as the reference's loop does.
+// A constraint without target (None in the reference) is passed as NaN.
+// ---------------------------------------------------------------------------------------------
+namespace fc {
+__global__ void fitness_kernel(const double* __restrict__ coords, long long n, int n_atoms, const int* __restrict__ pairs,
+                               const double* __restrict__ targets, int n_constraints, double* __restrict__ error) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const double* x = coords + (size_t)s * n_atoms * 3;
+    double err = 0.0;
+    for (int c = 0; c < n_constraints; ++c) {
+        const double t = targets[(size_t)s * n_constraints + c];
+        if (t != t) continue;  // no target for this constraint
+        const int a = pairs[((size_t)s * n_constraints + c) * 2], b = pairs[((size_t)s * n_constraints + c) * 2 + 1];
+        const double dx = x[3 * a] - x[3 * b], dy = x[3 * a + 1] - x[3 * b + 1], dz = x[3 * a + 2] - x[3 * b + 2];
+        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        err = __dadd_rn(err, __dsub_rn(sqrt(d2), t));
+    }
+    error[s] = err;
+}
+}  // namespace fc
+
+extern "C" int fc_fitness_batch(const double* coords, int64_t n, int32_t n_atoms, const int32_t* pairs, const double* targets,
+                                int32_t n_constraints, double* error_out) {
+    FC_REQUIRE(n >= 0 && n_atoms > 0 && n_constraints >= 0 && n < ((int64_t)1 << 31), "fc_fitness_batch: bad sizes");
+    if (n == 0) return FC_OK;
+    FC_REQUIRE(coords && error_out && (n_constraints == 0 || (pairs && targets)), "fc_fitness_batch: null pointer");
+    for (int64_t i = 0; i < n * (int64_t)n_constraints * 2; ++i)
+        FC_REQUIRE(pairs[i] >= 0 && pairs[i] < n_atoms, "fc_fitness_batch: atom index %d out of range", (int)pairs[i]);
+    cudaStream_t s;
+    FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaError_t e = cudaSuccess;
+    {
+        DevBuf<double> d_x, d_t, d_e;
+        DevBuf<int> d_p;
+#define MS(call) do { if (e == cudaSuccess) e = (call); } while (0)
+        const size_t nc = (size_t)n * (size_t)std::max(n_constraints, 1);
+        MS(d_x.alloc((size_t)n * n_atoms * 3, s));
+        MS(d_t.alloc(nc, s));
+        MS(d_p.alloc(2 * nc, s));
+        MS(d_e.alloc((size_t)n, s));
+        MS(upload_rows_staged(d_x.p, coords, n, n_atoms, nullptr, n_atoms, s));
+        if (n_constraints > 0) {
+            MS(cudaMemcpyAsync(d_t.p, targets, (size_t)n * n_constraints * 8, cudaMemcpyHostToDevice, s));
+            MS(cudaMemcpyAsync(d_p.p, pairs, (size_t)n * n_constraints * 8, cudaMemcpyHostToDevice, s));
+        }
+        if (e == cudaSuccess) {
+            fitness_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_x.p, n, n_atoms, d_p.p, d_t.p, n_constraints, d_e.p);
+            e = cudaGetLastError();
+        }
+        MS(cudaMemcpyAsync(error_out, d_e.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+        MS(cudaStreamSynchronize(s));
+#undef MS
+    }
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    if (e != cudaSuccess) return cuda_fail(e, "fc_fitness_batch", __FILE__, __LINE__);
+    return FC_OK;
+}

@@ -312,6 +312,13 @@ int fc_csearch_apply(const double* starts, int32_t n_starts, int32_t n_atoms, co
 int fc_structure_clash_batch(const double* coords, int64_t n, int32_t n_atoms, const int32_t* ids, int32_t n_ids,
                              double thresh, int64_t* count_out, double* closest_out);
 
+/* fitness_check over a batch (optimization_methods.py:163-180, the loop of RunEmbedding.fitness_refining,
+ * embedder.py:1997-2039): error_out[s] = sum over the constraints of structure s of (|x_a - x_b| - target);
+ * pairs (n, n_constraints, 2), targets (n, n_constraints) with NaN where the reference has None.  The structure
+ * is kept iff error < threshold (decided by the caller, which also lists errors within 1e-6 of the threshold). */
+int fc_fitness_batch(const double* coords, int64_t n, int32_t n_atoms, const int32_t* pairs, const double* targets,
+                     int32_t n_constraints, double* error_out);
+
 /* Timing of the last fc_prune / fc_prune_sharded call on this thread (bench.py's roofline of the tensor-core
  * screen): out6 = {wall ms of the call, CUDA-event ms summed over the screen kernel launches, launches,
  * pair slots the screen evaluated (2048 per 128 x 16 tile), candidates it passed on, atoms per structure}. */

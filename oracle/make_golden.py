@@ -192,7 +192,91 @@ def main_csearch():
         print(f"{name}: random {rnd.shape}, clustered {clu.shape}")
 
 
+REFINING_CASES = {"refining_a": (300, 3, 11), "refining_b": (600, 2, 12)}   # name -> (structures, fragments, seed)
+
+
+def make_refining_case(n, n_frag, seed):
+    """A duck-typed embedder state after the embed: n structures of n_frag rigid fragments.  Structure s belongs to
+    basin s % n_basins (fragment offsets of the basin) with a small per-structure jitter, so that some structures
+    have clashing fragments, the constrained distances scatter around their targets, and basins give similar pairs."""
+    from firecode_b200 import synthetic
+
+    rng = np.random.default_rng(seed)
+    frags, ids = [], []
+    for _ in range(n_frag):
+        _, x, _, _ = synthetic.molecule_cloud(rng, int(rng.integers(8, 14)))
+        frags.append(x)
+        ids.append(len(x))
+    atoms = np.array(["C"] * int(sum(ids)))
+    offs = np.concatenate([[0], np.cumsum(ids)]).astype(int)
+    n_basins = max(2, n // 6)
+    basin_shift = rng.normal(size=(n_basins, n_frag, 3)) * 1.2
+    structures = np.zeros((n, int(offs[-1]), 3))
+    for s in range(n):
+        for f in range(n_frag):
+            structures[s, offs[f]:offs[f + 1]] = frags[f] + np.array([4.5 * f, 0.0, 0.0]) + basin_shift[s % n_basins, f] \
+                + rng.normal(size=3) * 0.05
+    pairs = np.array([[offs[f], offs[(f + 1) % n_frag] + 1] for f in range(n_frag)] + [[0, 2]])
+    pairs = np.sort(pairs, axis=1)
+    constrained = np.broadcast_to(pairs, (n,) + pairs.shape).copy()
+    table = {chr(ord("a") + i): tuple(int(v) for v in pr) for i, pr in enumerate(pairs[:-1])}   # last pair: no letter
+    dists = {lett: 4.0 + 0.5 * i for i, lett in enumerate(table)}
+    return atoms, structures, ids, constrained, table, dists
+
+
+def main_refining():
+    """compenetration_refining / fitness_refining / similarity_refining of the UNMODIFIED reference
+    (firecode/embedder.py:1954-2039, 1410-1514) called on a duck-typed embedder."""
+    loader.install()
+    from types import SimpleNamespace
+
+    from firecode.embedder import RunEmbedding
+
+    class Duck:
+        apply_mask = RunEmbedding.apply_mask
+        get_pairing_dists_from_constrained_indices = RunEmbedding.get_pairing_dists_from_constrained_indices
+        zero_candidates_check = RunEmbedding.zero_candidates_check
+
+        def log(self, *a, **k):
+            pass
+
+        def debuglog(self, *a, **k):
+            pass
+
+        def log_warnings(self):
+            pass
+
+    for name, (n, n_frag, seed) in REFINING_CASES.items():
+        atoms, structures, ids, constrained, table, dists = make_refining_case(n, n_frag, seed)
+        out = {}
+        for step in ("compenetration", "fitness", "similarity"):
+            d = Duck()
+            d.embed, d.ids, d.atoms = "multiembed", ids, atoms
+            d.options = SimpleNamespace(clash_thresh=1.5, max_clashes=2, rmsd=0.5)
+            d.structures, d.constrained_indices = structures.copy(), constrained.copy()
+            d.energies, d.exit_status = np.arange(n, dtype=float), np.zeros(n, dtype=bool)
+            d.pairings_table, d.objects = table, [None] * n_frag
+            d.get_pairing_dist_from_letter = lambda lett, dists=dists: dists[lett]
+            tag = np.arange(n)
+            d.tag = tag
+            if step == "compenetration":
+                d.constrained_indices = np.concatenate([constrained, np.broadcast_to(tag[:, None, None], (n, 1, 2))], axis=1)
+                RunEmbedding.compenetration_refining(d)
+                out[step] = d.constrained_indices[:, -1, 0].copy()
+            elif step == "fitness":
+                RunEmbedding.fitness_refining(d, threshold=3.0)
+                out[step] = d.energies.astype(np.int64)
+            else:
+                RunEmbedding.similarity_refining(d, tfd=False, moi=True, rmsd=True)
+                out[step] = d.energies.astype(np.int64)
+            print(f"{name}: {step} kept {len(out[step])}/{n}")
+        np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), params=np.array([n, n_frag, seed]),
+                            kept_compenetration=out["compenetration"], kept_fitness=out["fitness"],
+                            kept_similarity=out["similarity"], checksum=np.float64(structures.sum()))
+
+
 if __name__ == "__main__":
     main()
     main_tfd()
     main_csearch()
+    main_refining()

@@ -121,3 +121,24 @@ def test_vectorised_bimolecular_group_table_equals_loop_restatement():
                 for m in range(2):
                     assert np.array_equal(table["pivot"][i][m], prob.pivot_vec[m][r["conf"][m]][r["piv"][m]])
                     assert np.array_equal(table["mean"][i][m], prob.pivot_mean[m][r["conf"][m]][r["piv"][m]])
+
+
+def test_take_rows_matches_boolean_indexing():
+    """fc_take_rows (threaded gather behind the `structures[mask]` the pruning entry points return) is host-only."""
+    import ctypes as C
+
+    from firecode_b200 import _lib
+    from firecode_b200.pruner import _take
+
+    lib = _lib.load(require_device=False)
+    rng = np.random.default_rng(0)
+    for n, shape in ((0, (5, 3)), (1, (5, 3)), (1000, (7, 3)), (4099, (1, 3))):
+        x = rng.normal(size=(n,) + shape)
+        mask = rng.random(n) < 0.4
+        assert np.array_equal(_take(lib, x, mask), x[mask])
+    x = rng.normal(size=(10, 4, 3))
+    out = np.empty((3, 4, 3))
+    m = np.ones(10, dtype=np.uint8)
+    rc = lib.fc_take_rows(x.ctypes.data_as(C.c_void_p), 96, m.ctypes.data_as(C.c_void_p), 10,
+                          out.ctypes.data_as(C.c_void_p), 3)
+    assert rc != 0 and b"selects 10 rows" in lib.fc_last_error()
