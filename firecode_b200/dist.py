@@ -216,16 +216,26 @@ def cyclical_embed_sharded(embedder, group=None, screen=None, max_norm_delta=5.0
     return poses
 
 
-def prune_sharded(structures, atoms, kind="rmsd", group=None, **kw):
-    """prune_by_rmsd / prune_by_moment_of_inertia over all ranks of ``group``: pair tiles of every pass
+# Below this many pairs a pruning call is cheaper replicated on every rank than sharded: with the tensor-core
+# screen the GPU part of BASELINE config C4 (2e10 pairs, 5e9 evaluated) is 35 ms of an 85 ms call, the rest is
+# host work every rank repeats anyway, and each pass of the sharded driver adds two collectives
+# (measured on 8 B200: 0.164 s sharded against 0.085 s on one GPU).
+PRUNE_SHARD_MIN_PAIRS = 1e11
+
+
+def prune_sharded(structures, atoms, kind="rmsd", group=None, force_shard=False, **kw):
+    """prune_by_rmsd / prune_by_moment_of_inertia over all ranks of ``group``: work items of every pass
     are dealt round-robin to the ranks (structures replicated), the similar pairs each rank finds are
     all-gathered (8 bytes per pair) and every rank resolves the pass on the union -- the deterministic
-    ordered merge -- so all ranks return the same (structures[mask], mask) as a single-GPU call."""
+    ordered merge -- so all ranks return the same (structures[mask], mask) as a single-GPU call.
+    Ensembles with fewer than PRUNE_SHARD_MIN_PAIRS pairs are pruned redundantly on every rank instead
+    (same result, no collectives) unless ``force_shard``."""
     from . import pruner
 
     rank, world = world_info(group)
     fn = pruner.prune_by_rmsd if kind == "rmsd" else pruner.prune_by_moment_of_inertia
-    if world == 1:
+    n = len(structures)
+    if world == 1 or (not force_shard and 0.5 * n * (n - 1) < PRUNE_SHARD_MIN_PAIRS):
         return fn(structures, atoms, **kw)
     return fn(structures, atoms, shard=(rank, world, lambda buf: all_gather_varlen(buf, group)), **kw)
 

@@ -94,9 +94,9 @@ def _shard_worker(rank, world, port, q):
         atoms, structures, _ = syn.pruning_ensemble(rng, 3000, 20, 200, jitter=(0.02, 0.4))
         out = {}
         for keep, mode in (("first", "greedy"), ("last", "snapshot")):
-            _, mask = fdist.prune_sharded(structures, atoms, "rmsd", max_rmsd=0.4, keep=keep, pass_mode=mode)
+            _, mask = fdist.prune_sharded(structures, atoms, "rmsd", force_shard=True, max_rmsd=0.4, keep=keep, pass_mode=mode)
             out[(keep, mode)] = (mask, pr.last_report.pairs_tiled)
-        _, mmask = fdist.prune_sharded(structures, atoms, "moi")
+        _, mmask = fdist.prune_sharded(structures, atoms, "moi", force_shard=True)
         out["moi"] = (mmask, pr.last_report.pairs_tiled)
         q.put((rank, out))
     except Exception:  # pragma: no cover

@@ -48,7 +48,7 @@ def main():
     # pruning: tiles dealt to the ranks, similar-pair lists all-gathered
     atoms, structures, _ = synthetic.pruning_ensemble(np.random.default_rng(7), 6000, 40, 300, jitter=(0.02, 0.4))
     _, m1 = pruner.prune_by_rmsd(structures, atoms, 0.5)
-    _, mw = fdist.prune_sharded(structures, atoms, "rmsd", max_rmsd=0.5)
+    _, mw = fdist.prune_sharded(structures, atoms, "rmsd", force_shard=True, max_rmsd=0.5)
     assert np.array_equal(m1, mw)
     dist.barrier()
     if rank == 0:
