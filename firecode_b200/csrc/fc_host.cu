@@ -18,7 +18,7 @@ namespace fc {
 
 static int host_threads() {
     unsigned hc = std::thread::hardware_concurrency();
-    return (int)std::max(1u, std::min(8u, hc ? hc : 1u));
+    return (int)std::max(1u, std::min(16u, hc ? hc / 2u : 1u));  // half the hardware threads, at most 16
 }
 
 template <class F>

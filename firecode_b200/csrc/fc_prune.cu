@@ -622,6 +622,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                 // still need evaluating: tiles whose structures all shared a chunk with the block's first row in the
                 // previous pass are known dissimilar and form a prefix of the block's column range
                 spos.clear();
+                spos.reserve((size_t)n + 16 * (size_t)k + 256);
                 blocks.clear();
                 work.clear();
                 auto prev_chunk = [&](int idx) { return std::min<int64_t>((int64_t)idx / prev_size, prev_k - 1); };
@@ -639,8 +640,14 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                     for (int row0 = pbegin; row0 < pend - 1; row0 += 128) {
                         int c_min = row0 / 16;
                         if (prev_size > 0) {
+                            // first position of the chunk whose structure lies beyond the previous-pass chunk of the block's
+                            // first row: a tile is known dissimilar iff its last structure comes before that position
                             const int64_t pc = prev_chunk(spos[(size_t)row0]);
-                            while (c_min < tile_end && prev_chunk(spos[(size_t)std::min(16 * (c_min + 1), pend) - 1]) == pc) ++c_min;
+                            const int64_t idx_end = pc == prev_k - 1 ? n : (pc + 1) * prev_size;
+                            const int pos_e = (int)(std::lower_bound(spos.begin() + row0, spos.begin() + pend, idx_end,
+                                                                     [](int v, int64_t lim) { return (int64_t)v < lim; }) -
+                                                    spos.begin());
+                            c_min = pos_e >= pend ? tile_end : std::max(c_min, pos_e / 16);
                         }
                         if (c_min >= tile_end) continue;
                         blocks.push_back(RowBlock{row0, c_min, tile_end, pend});
