@@ -134,6 +134,7 @@ SIGNATURES = {
     "fc_structure_clash_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_int32, C.c_double, VP, VP]),
     "fc_fitness_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, VP, C.c_int32, VP]),
     "fc_prune_timing": (C.c_int, [VP]),
+    "fc_xyz_format": (C.c_int, [VP, C.c_int32, VP, C.c_int64, C.c_int32, VP, VP, C.c_int64, c_i64p]),
     "fc_take_rows": (C.c_int, [VP, C.c_int64, VP, C.c_int64, VP, C.c_int64]),
     "fc_probe_fp32_peak": (C.c_int, [c_dp, c_dp, VP]),
 }

@@ -8,7 +8,10 @@
 // (/root/reference/firecode/embedder.py:1400-1408 consumes it), done by several threads.
 #include <string.h>
 
+#include <stdio.h>
+
 #include <algorithm>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -38,6 +41,7 @@ struct PinnedPair {
     void* p[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     size_t bytes = 0;
+    int device = -1;  // the events belong to this device
 };
 static const size_t kStageBytes = (size_t)48 << 20;
 
@@ -46,13 +50,24 @@ static const size_t kStageBytes = (size_t)48 << 20;
 cudaError_t upload_rows_staged(double* dst, const double* src, int64_t n, int n_atoms, const int32_t* sel, int n_sel,
                                cudaStream_t stream) {
     static thread_local PinnedPair st;
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
     if (!st.p[0]) {
         for (int b = 0; b < 2; ++b) {
-            cudaError_t e = cudaHostAlloc(&st.p[b], kStageBytes, cudaHostAllocDefault);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&st.ev[b], cudaEventDisableTiming);
+            cudaError_t e = cudaHostAlloc(&st.p[b], kStageBytes, cudaHostAllocPortable);
             if (e != cudaSuccess) return e;
         }
         st.bytes = kStageBytes;
+    }
+    if (st.device != dev) {  // first use, or the thread moved to another device: events are per device
+        for (int b = 0; b < 2; ++b) {
+            if (st.ev[b]) cudaEventDestroy(st.ev[b]);
+            st.ev[b] = nullptr;
+            cudaError_t e = cudaEventCreateWithFlags(&st.ev[b], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        st.device = dev;
     }
     const size_t row_out = (size_t)n_sel * 24, row_in = (size_t)n_atoms * 24;
     const int64_t rows_per_chunk = std::max<int64_t>(1, (int64_t)(st.bytes / row_out));
@@ -100,5 +115,65 @@ extern "C" int fc_take_rows(const void* src, int64_t row_bytes, const uint8_t* m
             memcpy((char*)dst + (size_t)j * (size_t)row_bytes, (const char*)src + (size_t)kept[(size_t)j] * (size_t)row_bytes,
                    (size_t)row_bytes);
     });
+    return FC_OK;
+}
+
+// ---- xyz text of a batch of structures, byte-identical to the reference's write_xyz ---------------
+// (/root/reference/firecode/utils.py:105-116: "<n>\n<title>\n" then one line "%s     % .6f % .6f % .6f\n" per atom)
+extern "C" int fc_xyz_format(const char* symbols, int32_t sym_stride, const double* coords, int64_t n, int32_t n_atoms,
+                             const char* titles, char* out, int64_t out_cap, int64_t* out_len) {
+    FC_REQUIRE(n >= 0 && n_atoms >= 0 && sym_stride > 0 && out_len, "fc_xyz_format: bad arguments");
+    *out_len = 0;
+    if (n == 0) return FC_OK;
+    FC_REQUIRE((symbols && coords) || n_atoms == 0, "fc_xyz_format: null pointer");
+    // titles: n NUL-terminated strings back to back (null -> "temp", the reference's default)
+    std::vector<const char*> title((size_t)n, "temp");
+    if (titles) {
+        const char* t = titles;
+        for (int64_t s = 0; s < n; ++s) {
+            title[(size_t)s] = t;
+            t += strlen(t) + 1;
+        }
+    }
+    const int nt = (int)std::min<int64_t>(host_threads(), std::max<int64_t>(1, n * (int64_t)std::max(n_atoms, 1) / 4096));
+    std::vector<std::string> part((size_t)nt);
+    auto work = [&](int t) {
+        const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+        std::string& buf = part[(size_t)t];
+        buf.reserve((size_t)(hi - lo) * ((size_t)n_atoms * 48 + 32));
+        char line[256];
+        for (int64_t s = lo; s < hi; ++s) {
+            buf += std::to_string(n_atoms);
+            buf += '\n';
+            buf += title[(size_t)s];
+            buf += '\n';
+            const double* x = coords + (size_t)s * n_atoms * 3;
+            for (int k = 0; k < n_atoms; ++k) {
+                const char* sym = symbols + (size_t)k * sym_stride;
+                const int sl = (int)strnlen(sym, (size_t)sym_stride);
+                const int len = snprintf(line, sizeof line, "%.*s     % .6f % .6f % .6f\n", sl, sym, x[3 * k], x[3 * k + 1], x[3 * k + 2]);
+                buf.append(line, (size_t)std::min<int>(len, (int)sizeof line - 1));
+            }
+        }
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    int64_t total = 0;
+    for (const std::string& b : part) total += (int64_t)b.size();
+    *out_len = total;   // the size needed, also when the buffer is too small
+    if (!out || out_cap < total) {
+        set_error("fc_xyz_format: output needs %lld bytes, buffer holds %lld", (long long)total, (long long)out_cap);
+        return FC_ERR_INVALID;
+    }
+    char* dst = out;
+    for (const std::string& b : part) {
+        memcpy(dst, b.data(), b.size());
+        dst += b.size();
+    }
     return FC_OK;
 }

@@ -142,3 +142,52 @@ def rmsd_similarity(ref, structures, rmsd_thr=0.5):
         return False
     rmsd, maxdev = rmsd_and_max_batch(ref, structures, center=False)
     return bool(np.any((rmsd < rmsd_thr) & (maxdev < 2 * rmsd_thr)))
+
+
+def xyz_text(atoms, structures, titles=None):
+    """The xyz text of a batch of structures, byte-identical to looping the reference's ``write_xyz``
+    (utils.py:105-116) over them; formatted by several host threads in the library (fc_xyz_format)."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load(require_device=False)
+    x = np.ascontiguousarray(np.asarray(structures, dtype=np.float64))
+    assert x.ndim == 3 and x.shape[2] >= 3, f"{x.shape=}"
+    if x.shape[2] > 3:
+        x = np.ascontiguousarray(x[:, :, :3])
+    n, n_atoms = x.shape[:2]
+    sym = [str(a).encode() for a in atoms]
+    assert len(sym) == n_atoms, f"{len(sym)=} != {n_atoms=}"
+    stride = max([len(s) for s in sym] + [1])
+    symbuf = b"".join(s.ljust(stride, b"\0") for s in sym)
+    if titles is None:
+        tbuf = None
+    else:
+        titles = [titles] * n if isinstance(titles, str) else list(titles)
+        assert len(titles) == n
+        tbuf = b"".join(str(t).encode() + b"\0" for t in titles)
+    cap = n * (n_atoms * (stride + 56) + 64) + sum(len(str(t)) for t in (titles or []))
+    for _ in range(2):
+        out = C.create_string_buffer(max(cap, 1))
+        need = C.c_int64(0)
+        rc = lib.fc_xyz_format(symbuf, stride, x.ctypes.data, n, n_atoms, tbuf, out, cap, C.byref(need))
+        if rc == 0:
+            return out.raw[: need.value].decode()
+        if need.value <= cap:
+            _lib.check(rc, "fc_xyz_format")
+        cap = need.value
+    _lib.check(rc, "fc_xyz_format")
+
+
+def write_xyz(atoms, coords, output, title="temp"):
+    """utils.py:105-116: same signature, same bytes."""
+    atoms, coords = np.asarray(atoms), np.asarray(coords)
+    assert atoms.shape[0] == coords.shape[0], f"{atoms.shape[0]=} != {coords.shape[0]=}"
+    assert coords.shape[1] >= 3, f"{coords.shape[1]=}"
+    output.write(xyz_text(atoms, coords[None], [title]))
+
+
+def write_xyz_batch(atoms, structures, output, titles=None):
+    """All structures of an ensemble in one call (the reference loops write_xyz, e.g. embedder.py:1698-1716)."""
+    output.write(xyz_text(atoms, structures, titles))

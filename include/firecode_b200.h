@@ -329,6 +329,13 @@ int fc_prune_timing(double* out6);
  * n_dst must equal the number of selected rows. */
 int fc_take_rows(const void* src, int64_t row_bytes, const uint8_t* mask, int64_t n, void* dst, int64_t n_dst);
 
+/* xyz text of n structures, byte-identical to the reference's write_xyz (utils.py:105-116): per structure
+ * "<n_atoms>\n<title>\n" and one line "%s     % .6f % .6f % .6f\n" per atom.  symbols = n_atoms fixed-width
+ * (sym_stride bytes, NUL-padded) element symbols; titles = n NUL-terminated strings back to back (null: "temp").
+ * *out_len receives the size of the text; FC_ERR_INVALID when out_cap is smaller (call again with that size). */
+int fc_xyz_format(const char* symbols, int32_t sym_stride, const double* coords, int64_t n, int32_t n_atoms,
+                  const char* titles, char* out, int64_t out_cap, int64_t* out_len);
+
 /* FP32 FMA-pipe peak probe used by bench.py for the roofline denominator: runs a dependent-free
  * FFMA2 loop on every SM and returns achieved TFLOP/s (2 flop per FMA lane). */
 int fc_probe_fp32_peak(double* tflops_out, double* ms_out, void* stream);

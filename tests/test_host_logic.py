@@ -142,3 +142,54 @@ def test_take_rows_matches_boolean_indexing():
     rc = lib.fc_take_rows(x.ctypes.data_as(C.c_void_p), 96, m.ctypes.data_as(C.c_void_p), 10,
                           out.ctypes.data_as(C.c_void_p), 3)
     assert rc != 0 and b"selects 10 rows" in lib.fc_last_error()
+
+
+def _ref_write_xyz(atoms, coords, title):
+    """The reference's formatting, restated for boxes without /root/reference (utils.py:105-116)."""
+    s = str(len(coords)) + f"\n{title}\n"
+    for atom, c in zip(atoms, coords):
+        s += "%s     % .6f % .6f % .6f\n" % (atom, c[0], c[1], c[2])
+    return s
+
+
+def test_write_xyz_is_byte_identical():
+    import io
+
+    from firecode_b200 import utils
+
+    rng = np.random.default_rng(4)
+    atoms = np.array(["C", "H", "Cl", "Br", "N", "O", "H"])
+    structures = rng.normal(size=(700, 7, 3)) * np.array([1.0, 100.0, 1e-4])
+    structures[0, 0] = [0.0, -0.0, 1e-7]
+    structures[1, 1] = [123456.7890125, -0.0000005, 0.0000005]
+    structures[2, 2] = [1e15, -2.5e-7, 9.9999995]
+    titles = [f"structure {i} E = {i * 0.37:.3f}" for i in range(len(structures))]
+    want = "".join(_ref_write_xyz(atoms, s, t) for s, t in zip(structures, titles))
+    assert utils.xyz_text(atoms, structures, titles) == want
+    buf = io.StringIO()
+    utils.write_xyz(atoms, structures[5], buf, title="temp")
+    assert buf.getvalue() == _ref_write_xyz(atoms, structures[5], "temp")
+    buf = io.StringIO()
+    utils.write_xyz_batch(atoms, structures[:3], buf)
+    assert buf.getvalue() == "".join(_ref_write_xyz(atoms, s, "temp") for s in structures[:3])
+    assert utils.xyz_text(atoms, structures[:0]) == ""
+
+
+@pytest.mark.reference
+def test_write_xyz_equals_live_reference():
+    import io
+
+    from firecode_b200 import utils
+    from oracle import loader
+
+    loader.install()
+    from firecode.utils import write_xyz as ref_write_xyz
+
+    rng = np.random.default_rng(5)
+    atoms = np.array(["C", "H", "Si", "O"])
+    for i in range(20):
+        coords = rng.normal(size=(4, 3)) * 10.0 ** rng.integers(-3, 6)
+        a, b = io.StringIO(), io.StringIO()
+        ref_write_xyz(atoms, coords, a, title=f"t{i}")
+        utils.write_xyz(atoms, coords, b, title=f"t{i}")
+        assert a.getvalue() == b.getvalue()
