@@ -488,6 +488,92 @@ static int64_t gram_item_pairs(int64_t row0, int64_t col_lo, int64_t col_hi, int
     return total;
 }
 
+// One pass of the tensor-core screen, planned on the host: the active structures (mask != 0) of each of the k chunks
+// (n / k structures, the last takes the rest) get padded positions (every chunk starts at a multiple of 16) and, per
+// 128-row block, the column tiles that still need evaluating.  Two survivors of a common chunk of the previous pass
+// (chunk size prev_size, prev_k chunks; prev_size = 0 on the first pass) are known dissimilar, so the tiles whose
+// structures all shared the previous chunk of the block's first row -- a prefix of the block's column range -- are
+// left out.  Column ranges are cut into work items so that every SM gets several of similar size; item i goes to rank
+// i % world.  Adds to pairs_tiled (pairs this rank evaluates) and pairs_skipped (pairs no rank evaluates).
+static void plan_gram_pass(const std::vector<uint8_t>& mask, int64_t n, int64_t k, int64_t prev_size, int64_t prev_k, int world,
+                           int rank, int n_sms, std::vector<int>& spos, std::vector<GramWork>& work, int64_t& pairs_tiled,
+                           int64_t& pairs_skipped) {
+    struct RowBlock { int row0, c_min, tile_end, pend; };
+    std::vector<RowBlock> blocks;
+    spos.clear();
+    spos.reserve((size_t)n + 16 * (size_t)k + 256);
+    work.clear();
+    const int64_t size = n / k;
+    auto prev_chunk = [&](int idx) { return std::min<int64_t>((int64_t)idx / prev_size, prev_k - 1); };
+    int64_t col_tiles_total = 0;
+    for (int64_t c = 0; c < k; ++c) {
+        const int64_t first = c * size, last = (c == k - 1) ? n : size * (c + 1);
+        while (spos.size() % 16) spos.push_back(-1);
+        const int pbegin = (int)spos.size();
+        for (int64_t i = first; i < last; ++i)
+            if (mask[(size_t)i]) spos.push_back((int)i);
+        const int pend = (int)spos.size(), len = pend - pbegin;
+        if (len < 2) continue;
+        const int tile_end = (pend + 15) / 16;
+        int64_t evaluated = 0;
+        for (int row0 = pbegin; row0 < pend - 1; row0 += 128) {
+            int c_min = row0 / 16;
+            if (prev_size > 0) {
+                // first position of the chunk whose structure lies beyond the previous-pass chunk of the block's first
+                // row: a tile is known dissimilar iff its last structure comes before that position
+                const int64_t pc = prev_chunk(spos[(size_t)row0]);
+                const int64_t idx_end = pc == prev_k - 1 ? n : (pc + 1) * prev_size;
+                const int pos_e = (int)(std::lower_bound(spos.begin() + row0, spos.begin() + pend, idx_end,
+                                                         [](int v, int64_t lim) { return (int64_t)v < lim; }) -
+                                        spos.begin());
+                c_min = pos_e >= pend ? tile_end : std::max(c_min, pos_e / 16);
+            }
+            if (c_min >= tile_end) continue;
+            blocks.push_back(RowBlock{row0, c_min, tile_end, pend});
+            col_tiles_total += tile_end - c_min;
+            evaluated += gram_item_pairs(row0, 16 * c_min, pend, pend);
+        }
+        pairs_skipped += (int64_t)len * (len - 1) / 2 - evaluated;
+    }
+    const int64_t seg = std::min<int64_t>(1024, std::max<int64_t>(16, col_tiles_total / ((int64_t)n_sms * 32)));
+    int64_t item_no = 0;
+    for (const RowBlock& b : blocks)
+        for (int c0 = b.c_min; c0 < b.tile_end; c0 += (int)seg) {
+            const int nt = (int)std::min<int64_t>(seg, b.tile_end - c0);
+            if (item_no++ % world != rank) continue;
+            work.push_back(GramWork{b.row0, c0, nt, b.pend});
+            pairs_tiled += gram_item_pairs(b.row0, 16 * c0, std::min(16 * (c0 + nt), b.pend), b.pend);
+        }
+    while (spos.size() % 16) spos.push_back(-1);
+    spos.resize(spos.size() + 128, -1);  // a row block may read 128 positions from its first row
+}
+
+// Host-only view of plan_gram_pass for the tests (no CUDA call): positions and work items of one pass.
+extern "C" int fc_prune_plan(const uint8_t* mask, int64_t n, int64_t k, int64_t prev_k, int32_t world, int32_t rank, int32_t n_sms,
+                             int32_t* spos_out, int64_t spos_cap, int64_t* n_spos, int32_t* work_out, int64_t work_cap,
+                             int64_t* n_work, int64_t* counts_out) {
+    FC_REQUIRE(mask && n > 0 && k >= 1 && k <= n && prev_k >= 0 && prev_k <= n && world >= 1 && rank >= 0 && rank < world && n_sms >= 1,
+               "fc_prune_plan: bad arguments");
+    FC_REQUIRE(n_spos && n_work && counts_out, "fc_prune_plan: null pointer");
+    std::vector<uint8_t> m(mask, mask + n);
+    std::vector<int> spos;
+    std::vector<GramWork> work;
+    int64_t tiled = 0, skipped = 0;
+    plan_gram_pass(m, n, k, prev_k ? n / prev_k : 0, prev_k, world, rank, n_sms, spos, work, tiled, skipped);
+    *n_spos = (int64_t)spos.size();
+    *n_work = (int64_t)work.size();
+    counts_out[0] = tiled;
+    counts_out[1] = skipped;
+    FC_REQUIRE((int64_t)spos.size() <= spos_cap && (int64_t)work.size() <= work_cap && spos_out && work_out,
+               "fc_prune_plan: buffers too small (%lld positions, %lld items)", (long long)spos.size(), (long long)work.size());
+    memcpy(spos_out, spos.data(), spos.size() * sizeof(int));
+    for (size_t i = 0; i < work.size(); ++i) {
+        work_out[4 * i] = work[i].row0; work_out[4 * i + 1] = work[i].col_tile0;
+        work_out[4 * i + 2] = work[i].n_col_tiles; work_out[4 * i + 3] = work[i].pend;
+    }
+    return FC_OK;
+}
+
 static thread_local double g_prune_timing[6] = {0, 0, 0, 0, 0, 0};
 
 extern "C" int fc_prune_timing(double* out6) {
@@ -600,9 +686,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
         int kc = (n_sel + 3) / 4;
         kc += kc & 1;
         const bool use_tc = two_stage && kc <= kGramMaxKc && !(envtc && !atoi(envtc));
-        struct RowBlock { int row0, c_min, tile_end, pend; };
         std::vector<int> spos;
-        std::vector<RowBlock> blocks;
         std::vector<GramWork> work;
         if (use_tc && rc == FC_OK) {
             e = d_gram_err.alloc(1, s);
@@ -618,56 +702,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
             double tp = now();
             const int64_t size = n / k;
             if (use_tc) {
-                // padded positions (every chunk starts at a multiple of 16) and, per 128-row block, the column tiles that
-                // still need evaluating: tiles whose structures all shared a chunk with the block's first row in the
-                // previous pass are known dissimilar and form a prefix of the block's column range
-                spos.clear();
-                spos.reserve((size_t)n + 16 * (size_t)k + 256);
-                blocks.clear();
-                work.clear();
-                auto prev_chunk = [&](int idx) { return std::min<int64_t>((int64_t)idx / prev_size, prev_k - 1); };
-                int64_t col_tiles_total = 0;
-                for (int64_t c = 0; c < k; ++c) {
-                    const int64_t first = c * size, last = (c == k - 1) ? n : size * (c + 1);
-                    while (spos.size() % 16) spos.push_back(-1);
-                    const int pbegin = (int)spos.size();
-                    for (int64_t i = first; i < last; ++i)
-                        if (mask[(size_t)i]) spos.push_back((int)i);
-                    const int pend = (int)spos.size(), len = pend - pbegin;
-                    if (len < 2) continue;
-                    const int tile_end = (pend + 15) / 16;
-                    int64_t evaluated = 0;
-                    for (int row0 = pbegin; row0 < pend - 1; row0 += 128) {
-                        int c_min = row0 / 16;
-                        if (prev_size > 0) {
-                            // first position of the chunk whose structure lies beyond the previous-pass chunk of the block's
-                            // first row: a tile is known dissimilar iff its last structure comes before that position
-                            const int64_t pc = prev_chunk(spos[(size_t)row0]);
-                            const int64_t idx_end = pc == prev_k - 1 ? n : (pc + 1) * prev_size;
-                            const int pos_e = (int)(std::lower_bound(spos.begin() + row0, spos.begin() + pend, idx_end,
-                                                                     [](int v, int64_t lim) { return (int64_t)v < lim; }) -
-                                                    spos.begin());
-                            c_min = pos_e >= pend ? tile_end : std::max(c_min, pos_e / 16);
-                        }
-                        if (c_min >= tile_end) continue;
-                        blocks.push_back(RowBlock{row0, c_min, tile_end, pend});
-                        col_tiles_total += tile_end - c_min;
-                        evaluated += gram_item_pairs(row0, 16 * c_min, pend, pend);
-                    }
-                    pairs_skipped += (int64_t)len * (len - 1) / 2 - evaluated;
-                }
-                // column ranges are cut so that every SM gets several work items of similar size
-                const int64_t seg = std::min<int64_t>(1024, std::max<int64_t>(16, col_tiles_total / ((int64_t)sm_count() * 32)));
-                int64_t item_no = 0;
-                for (const RowBlock& b : blocks)
-                    for (int c0 = b.c_min; c0 < b.tile_end; c0 += (int)seg) {
-                        const int nt = (int)std::min<int64_t>(seg, b.tile_end - c0);
-                        if (item_no++ % world != rank) continue;
-                        work.push_back(GramWork{b.row0, c0, nt, b.pend});
-                        pairs_tiled += gram_item_pairs(b.row0, 16 * c0, std::min(16 * (c0 + nt), b.pend), b.pend);
-                    }
-                while (spos.size() % 16) spos.push_back(-1);
-                spos.resize(spos.size() + 128, -1);  // a row block may read 128 positions from its first row
+                plan_gram_pass(mask, n, k, prev_size, prev_k, world, rank, sm_count(), spos, work, pairs_tiled, pairs_skipped);
             } else {
                 // compacted active list + chunks over the FULL array (chunk size n // k, last takes the rest)
                 active.clear();

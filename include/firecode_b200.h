@@ -319,6 +319,15 @@ int fc_structure_clash_batch(const double* coords, int64_t n, int32_t n_atoms, c
 int fc_fitness_batch(const double* coords, int64_t n, int32_t n_atoms, const int32_t* pairs, const double* targets,
                      int32_t n_constraints, double* error_out);
 
+/* Host-only (no CUDA call): the padded position list and the work items (row0, col_tile0, n_col_tiles, pend) the
+ * tensor-core screen of fc_prune would use for one pass with k chunks over the structures with mask != 0, after a
+ * pass with prev_k chunks (0: first pass).  counts_out = {pairs in this rank's items, pairs known dissimilar}.
+ * Test hook for the planner (tests/test_host_logic.py); sizes come back in n_spos / n_work also when the buffers
+ * are too small. */
+int fc_prune_plan(const uint8_t* mask, int64_t n, int64_t k, int64_t prev_k, int32_t world, int32_t rank, int32_t n_sms,
+                  int32_t* spos_out, int64_t spos_cap, int64_t* n_spos, int32_t* work_out, int64_t work_cap,
+                  int64_t* n_work, int64_t* counts_out);
+
 /* Timing of the last fc_prune / fc_prune_sharded call on this thread (bench.py's roofline of the tensor-core
  * screen): out6 = {wall ms of the call, CUDA-event ms summed over the screen kernel launches, launches,
  * pair slots the screen evaluated (2048 per 128 x 16 tile), candidates it passed on, atoms per structure}. */

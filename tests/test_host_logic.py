@@ -193,3 +193,69 @@ def test_write_xyz_equals_live_reference():
         ref_write_xyz(atoms, coords, a, title=f"t{i}")
         utils.write_xyz(atoms, coords, b, title=f"t{i}")
         assert a.getvalue() == b.getvalue()
+
+
+def _plan(mask, k, prev_k, world=1, rank=0, n_sms=4):
+    import ctypes as C
+
+    from firecode_b200 import _lib
+
+    lib = _lib.load(require_device=False)
+    n = len(mask)
+    m8 = np.ascontiguousarray(mask, dtype=np.uint8)
+    spos = np.zeros(2 * n + 16 * k + 1024, dtype=np.int32)
+    work = np.zeros((n * 4 + 4096, 4), dtype=np.int32)
+    n_spos, n_work = C.c_int64(0), C.c_int64(0)
+    counts = np.zeros(2, dtype=np.int64)
+    rc = lib.fc_prune_plan(m8.ctypes.data, n, k, prev_k, world, rank, n_sms, spos.ctypes.data, len(spos), C.byref(n_spos),
+                           work.ctypes.data, len(work), C.byref(n_work), counts.ctypes.data)
+    assert rc == 0, lib.fc_last_error()
+    return spos[: n_spos.value], work[: n_work.value], counts
+
+
+@pytest.mark.parametrize("n,k,prev_k,world", [(700, 1, 0, 1), (700, 1, 2, 1), (3000, 5, 10, 3), (3000, 2, 5, 2),
+                                              (2500, 10, 20, 1), (1000, 1, 2, 8), (333, 3, 0, 2)])
+def test_prune_planner_covers_every_unknown_pair_once(n, k, prev_k, world):
+    """The work items of the tensor-core screen (row block x column-tile range, dealt to the ranks) must cover every
+    pair of active structures of a chunk exactly once, except pairs whose two members shared a chunk of the
+    previous pass (known dissimilar), which may be left out -- and nothing else may be left out."""
+    rng = np.random.default_rng(n + k)
+    mask = rng.random(n) < 0.6
+    size = n // k
+    chunk_of = np.minimum(np.arange(n) // size, k - 1)
+    prev_of = np.minimum(np.arange(n) // (n // prev_k), prev_k - 1) if prev_k else None
+    covered = {}
+    tiled_total = 0
+    for rank in range(world):
+        spos, work, counts = _plan(mask, k, prev_k, world, rank)
+        tiled_total += int(counts[0])
+        # position list: chunks start at multiples of 16, hold their active structures in order, -1 elsewhere
+        pos_active = np.flatnonzero(spos >= 0)
+        assert np.array_equal(spos[pos_active], np.flatnonzero(mask))
+        assert len(spos) % 16 == 0 and np.all(spos[-128:] == -1)
+        for c in range(k):
+            members = pos_active[chunk_of[spos[pos_active]] == c]
+            if len(members):
+                assert members[0] % 16 == 0 and np.array_equal(members, np.arange(members[0], members[0] + len(members)))
+        for row0, ct0, nt, pend in work:
+            assert row0 % 8 == 0 and nt >= 1 and spos[row0] >= 0
+            for r in range(row0, min(row0 + 128, pend)):
+                lo, hi = max(16 * ct0, r + 1), min(16 * (ct0 + nt), pend)
+                for c in range(lo, hi):
+                    key = (int(spos[r]), int(spos[c]))
+                    assert key[0] >= 0 and key[1] >= 0 and chunk_of[key[0]] == chunk_of[key[1]]
+                    assert key not in covered
+                    covered[key] = rank
+    assert tiled_total == len(covered)
+    act = np.flatnonzero(mask)
+    missing = 0
+    for c in range(k):
+        mem = act[chunk_of[act] == c]
+        for a_i in range(len(mem)):
+            for b_i in range(a_i + 1, len(mem)):
+                if (int(mem[a_i]), int(mem[b_i])) not in covered:
+                    missing += 1
+                    assert prev_of is not None and prev_of[mem[a_i]] == prev_of[mem[b_i]]
+    assert missing == int(counts[1])
+    if world > 1:
+        assert len(set(covered.values())) >= 2          # the items are dealt to the ranks
