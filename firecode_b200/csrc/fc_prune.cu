@@ -6,11 +6,13 @@
 // one restated in oracle/prism_pruner/pruner.py (PARITY UNPINNED), whose in-tree
 // structural analogue is firecode/torsion_module.py:957-1043.
 //
-// Driver (host, per pass k of the K schedule): the array is cut in k contiguous chunks; inside each
-// chunk the similarity of every pair of ACTIVE structures is evaluated on the GPU into a symmetric
-// bit matrix (prune_pairs_kernel: 32x32 pair tiles, coordinates staged in shared memory, 3x3
-// covariance accumulated in FP64 registers, Jacobi eigen-solve in FP64 registers), then one CTA per
-// chunk resolves the order-dependent keep rule (prune_sweep_kernel).
+// Driver (host, per pass k of the K schedule): the array is cut in k contiguous chunks; inside each chunk every
+// pair of ACTIVE structures is screened on the GPU -- by default on the tensor cores (fc_gram_tc.cuh: TF32 Gram
+// matrix of the centred coordinates, FP32 bounds on the sum of singular values in the epilogue), otherwise by
+// prune_screen_f32_kernel (FP32 CUDA cores, 32x32 pair tiles) -- and the pairs a screen cannot rule out are
+// decided in FP64 by prune_exact_kernel (one warp per pair: covariance, Jacobi, rotate-and-deviate as
+// rmsd_and_max does).  FC_PRUNE_FP64=1 and the MOI flavour use prune_pairs_kernel alone.  Similar pairs come
+// back as a compact list and the order-dependent keep rule is resolved on the host (prune_resolve).
 //   similar(i, j)  <=>  rmsd < max_rmsd  and  max deviation < max_dev      (heavy atoms, centred)
 //   MOI flavour    <=>  all three principal moments within max_deviation (relative to structure i)
 // Keep rules: "greedy" updates the mask in place (NMS sweep), "snapshot" reads the mask of the pass
