@@ -54,7 +54,8 @@ struct GramArgs {
     int dump_ld;
     int* error;               // set when a barrier wait times out (the kernel then traps)
     long long* prof;          // debug: cycle counters of CTA 0 (see tools/gram_tc_test.cu); null in production
-    int no_math;              // debug: the epilogue only drains tensor memory (measures the MMA / copy pipeline alone)
+    int no_math;              // debug bits (tools/gram_tc_test.cu; 0 in production): 1 = the epilogue only drains tensor
+                              // memory, 2 = one k-step per tile, 4 = no B copies, 64 = every valid pair takes pass 2
 };
 
 constexpr int kGramEpiWarps = 16;
