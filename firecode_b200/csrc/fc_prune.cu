@@ -537,7 +537,12 @@ static void plan_gram_pass(const std::vector<uint8_t>& mask, int64_t n, int64_t 
         }
         pairs_skipped += (int64_t)len * (len - 1) / 2 - evaluated;
     }
-    const int64_t seg = std::min<int64_t>(1024, std::max<int64_t>(16, col_tiles_total / ((int64_t)n_sms * 32)));
+    // items per SM: FC_PRUNE_ITEMS_PER_SM overrides (experiments); more items = better balance, more A reloads
+    static const int64_t items_per_sm = []() {
+        const char* v = getenv("FC_PRUNE_ITEMS_PER_SM");
+        return v && atoll(v) > 0 ? (int64_t)atoll(v) : (int64_t)32;
+    }();
+    const int64_t seg = std::min<int64_t>(1024, std::max<int64_t>(16, col_tiles_total / ((int64_t)n_sms * items_per_sm)));
     int64_t item_no = 0;
     for (const RowBlock& b : blocks)
         for (int c0 = b.c_min; c0 < b.tile_end; c0 += (int)seg) {
