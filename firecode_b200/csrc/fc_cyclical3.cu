@@ -754,7 +754,7 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
         }
     };
     const int64_t span = t_hi - t_lo;
-    int n_threads = (int)std::min<int64_t>(std::max(1u, std::min(8u, std::thread::hardware_concurrency())), std::max<int64_t>(1, span / 512));
+    int n_threads = (int)std::min<int64_t>(std::max(1u, std::min(16u, std::thread::hardware_concurrency())), std::max<int64_t>(1, span / 512));
     std::vector<EnumPart> parts((size_t)n_threads);
     {
         std::vector<std::thread> workers;
@@ -768,15 +768,38 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
     std::vector<Cyc3Super> supers;
     std::vector<Cyc3Group> groups;
     std::vector<HostGroup> hgroups;
-    for (EnumPart& L : parts) {
-        FC_REQUIRE(!L.bad, "fc_cyclical3_screen: facing atom out of range or too many groups");
-        const int s_off = (int)supers.size(), g_off = (int)groups.size();
-        for (Cyc3Super& x : L.supers) x.first_group += g_off;
-        for (Cyc3Group& x : L.groups) x.super += s_off;
-        supers.insert(supers.end(), L.supers.begin(), L.supers.end());
-        groups.insert(groups.end(), L.groups.begin(), L.groups.end());
-        hgroups.insert(hgroups.end(), L.hgroups.begin(), L.hgroups.end());
-        FC_REQUIRE(groups.size() < ((size_t)1 << 30), "too many groups for one call");
+    {
+        // concatenate the parts in range order (= the reference's loop order); every part is rebased and copied by
+        // its own thread
+        std::vector<size_t> s_off((size_t)n_threads + 1, 0), g_off((size_t)n_threads + 1, 0);
+        for (int w = 0; w < n_threads; ++w) {
+            FC_REQUIRE(!parts[(size_t)w].bad, "fc_cyclical3_screen: facing atom out of range or too many groups");
+            s_off[(size_t)w + 1] = s_off[(size_t)w] + parts[(size_t)w].supers.size();
+            g_off[(size_t)w + 1] = g_off[(size_t)w] + parts[(size_t)w].groups.size();
+        }
+        FC_REQUIRE(g_off.back() < ((size_t)1 << 30), "too many groups for one call");
+        supers.resize(s_off.back());
+        groups.resize(g_off.back());
+        hgroups.resize(g_off.back());
+        auto place = [&](int w) {
+            EnumPart& L = parts[(size_t)w];
+            const int so = (int)s_off[(size_t)w], go = (int)g_off[(size_t)w];
+            for (size_t i = 0; i < L.supers.size(); ++i) {
+                Cyc3Super x = L.supers[i];
+                x.first_group += go;
+                supers[(size_t)so + i] = x;
+            }
+            for (size_t i = 0; i < L.groups.size(); ++i) {
+                Cyc3Group x = L.groups[i];
+                x.super += so;
+                groups[(size_t)go + i] = x;
+            }
+            if (!L.hgroups.empty()) memcpy(&hgroups[(size_t)go], L.hgroups.data(), L.hgroups.size() * sizeof(HostGroup));
+        };
+        std::vector<std::thread> workers;
+        for (int w = 0; w + 1 < n_threads; ++w) workers.emplace_back(place, w);
+        place(n_threads - 1);
+        for (auto& th : workers) th.join();
     }
     const int64_t G = (int64_t)groups.size();
     t_enum = now() - t0;
