@@ -234,7 +234,10 @@ int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** out);
  *  mask_out (n) 1 = kept;  stats_out[4] = {passes, pairs whose covariance was accumulated, pairs
  *  eigen-solved, pairs skipped because both structures survived an earlier pass in the same chunk
  *  (such survivors are mutually dissimilar by construction)}.  Similar pairs are collected in a
- *  compact list; the order-dependent keep rule of a pass is resolved on the host in O(list). */
+ *  compact list; the order-dependent keep rule of a pass is resolved on the host in O(list).
+ *  Mode 0 screens the pairs on the tensor cores (TF32 Gram matrix of the centred coordinates, rigorous
+ *  rounding band) when n_sel <= 88 and on the FP32 CUDA cores otherwise; every pair a screen cannot rule
+ *  out is decided in FP64, so mask_out does not depend on the screen. */
 int fc_prune(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
              int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
              const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
