@@ -259,3 +259,32 @@ def test_prune_planner_covers_every_unknown_pair_once(n, k, prev_k, world):
     assert missing == int(counts[1])
     if world > 1:
         assert len(set(covered.values())) >= 2          # the items are dealt to the ranks
+
+
+def test_prune_sharded_replicates_small_ensembles(monkeypatch):
+    """dist.prune_sharded shards the pair work only above PRUNE_SHARD_MIN_PAIRS pairs (or when forced); below,
+    every rank prunes the whole ensemble with the single-GPU call (same result, no collectives)."""
+    from firecode_b200 import dist as fdist
+    from firecode_b200 import pruner
+
+    calls = []
+
+    def fake(structures, atoms, **kw):
+        calls.append(kw)
+        return structures, np.ones(len(structures), dtype=bool)
+
+    monkeypatch.setattr(pruner, "prune_by_rmsd", fake)
+    monkeypatch.setattr(pruner, "prune_by_moment_of_inertia", fake)
+    monkeypatch.setattr(fdist, "world_info", lambda group=None: (1, 4))
+    x = np.zeros((100, 3, 3))
+    fdist.prune_sharded(x, ["C"] * 3, "rmsd", max_rmsd=0.3)
+    assert "shard" not in calls[-1] and calls[-1]["max_rmsd"] == 0.3
+    fdist.prune_sharded(x, ["C"] * 3, "rmsd", force_shard=True, max_rmsd=0.3)
+    rank, world, gather = calls[-1]["shard"]
+    assert (rank, world) == (1, 4) and callable(gather)
+    monkeypatch.setattr(fdist, "PRUNE_SHARD_MIN_PAIRS", 1000.0)
+    fdist.prune_sharded(x, ["C"] * 3, "moi")
+    assert calls[-1]["shard"][:2] == (1, 4)
+    monkeypatch.setattr(fdist, "world_info", lambda group=None: (0, 1))
+    fdist.prune_sharded(x, ["C"] * 3, "rmsd", force_shard=True)
+    assert "shard" not in calls[-1]
