@@ -33,6 +33,9 @@ def fitness_check_batch(structures, constrained_indices, constrained_distances, 
     x = np.ascontiguousarray(np.asarray(structures, dtype=np.float64))
     assert x.ndim == 3 and x.shape[2] == 3
     p = len(x)
+    if p == 0:
+        empty = np.zeros(0, dtype=bool)
+        return (empty, np.zeros(0)) if return_errors else empty
     pairs = np.ascontiguousarray(np.asarray(constrained_indices, dtype=np.int32).reshape(p, -1, 2))
     m = pairs.shape[1]
     tg = np.array([[np.nan if t is None else float(t) for t in row] for row in constrained_distances],
