@@ -112,69 +112,122 @@ def make_fragments():
 
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline: the oracle port of utils.py:544-551 looped per pose, as the
-# reference does, on all host cores
+# reference does, on the host's physical cores (worker pool created OUTSIDE the timed window)
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    a, b, xf, thresh = args
+_CPU_CTX = {}
+
+
+def _cpu_init(a, b, thresh, use_reference):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    _CPU_CTX["a"], _CPU_CTX["b"], _CPU_CTX["thresh"] = a, b, thresh
+    fn = None
+    if use_reference:
+        try:
+            from oracle import loader
+
+            loader.install()
+            from firecode.utils import compenetration_check as fn  # the UNMODIFIED reference function
+        except Exception:
+            fn = None
+    if fn is None:
+        from oracle import port
+
+        fn = port.compenetration_check
+    _CPU_CTX["fn"] = fn
+
+
+def _cpu_worker(xf):
     from oracle import port
 
-    n_a = len(a)
+    a, b, thresh, fn = _CPU_CTX["a"], _CPU_CTX["b"], _CPU_CTX["thresh"], _CPU_CTX["fn"]
+    ids = (len(a), len(b))
     passed = 0
-    t0 = time.perf_counter()
     for p in range(len(xf)):
         pose = np.concatenate([a, port.place(b, xf[p])])  # get_embed, embeds.py:815-817
-        passed += bool(port.compenetration_check(pose, ids=(n_a, len(b)), thresh=thresh))
-    return passed, time.perf_counter() - t0
+        passed += bool(fn(pose, ids=ids, thresh=thresh))
+    return passed
 
 
-def cpu_screen_rate(n_sample, cores=None, seed=0):
-    """Poses/s of the reference-style per-pose CPU screen on `cores` processes."""
-    import multiprocessing as mp
+def physical_cores():
+    """Physical cores this process may use (hyperthread siblings counted once)."""
+    allowed = sorted(os.sched_getaffinity(0))
+    seen = set()
+    for cpu in allowed:
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{cpu}/topology/thread_siblings_list") as f:
+                seen.add(f.read().strip())
+        except OSError:
+            seen.add(str(cpu))
+    return max(1, len(seen)), len(allowed)
 
-    from firecode_b200 import synthetic
 
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    cores = cores or len(os.sched_getaffinity(0))
-    a, b = make_fragments()
-    rng = np.random.default_rng(synthetic.SEED + 1000 + seed)
-    xf = synthetic.sweep_poses(rng, a, b, n_sample)
-    parts = np.array_split(np.arange(n_sample), cores)
-    jobs = [(a, b, xf[idx], THRESH) for idx in parts if len(idx)]
-    ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(len(jobs)) as pool:
-        out = pool.map(_cpu_worker, jobs)
-    wall = time.perf_counter() - t0
-    return n_sample / wall, cores, sum(o[0] for o in out), wall
+class CpuScreen:
+    """Reference-style per-pose CPU screen on a pool of worker processes."""
+
+    def __init__(self, cores, use_reference=False):
+        import multiprocessing as mp
+
+        self.cores = cores
+        self.a, self.b = make_fragments()
+        self.kind = "port"
+        if use_reference and os.path.isdir("/root/reference/firecode"):
+            self.kind = "reference"
+        self.pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init,
+                                                initargs=(self.a, self.b, THRESH, self.kind == "reference"))
+        self.pool.map(_cpu_worker, [self.poses(8, seed=999)] * cores)  # workers imported and warm
+
+    def poses(self, n, seed=0):
+        from firecode_b200 import synthetic
+
+        rng = np.random.default_rng(synthetic.SEED + 1000 + seed)
+        return synthetic.sweep_poses(rng, self.a, self.b, n)
+
+    def rate(self, n_sample, seed=0):
+        xf = self.poses(n_sample, seed)
+        parts = [xf[idx] for idx in np.array_split(np.arange(n_sample), self.cores) if len(idx)]
+        t0 = time.perf_counter()
+        out = self.pool.map(_cpu_worker, parts)
+        wall = time.perf_counter() - t0
+        return n_sample / wall, sum(out), wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+WORKLOAD = "C3 compenetration sweep: 10M candidate poses of two 150-atom fragments per GPU, thresh 1.5 A"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0))
-    n_sample = 4000 * cores
+    cores, logical = physical_cores()
+    cpu = CpuScreen(cores)
+    n_sample = 6000 * cores
     for i in range(args.warmup):
-        cpu_screen_rate(max(cores * 200, 200), cores, seed=100 + i)
+        cpu.rate(max(cores * 200, 200), seed=100 + i)
     rates, walls = [], []
     for i in range(args.steps):
-        rate, _, _, wall = cpu_screen_rate(n_sample, cores, seed=i)
+        rate, _, wall = cpu.rate(n_sample, seed=i)
         rates.append(rate)
         walls.append(wall)
+    cpu.close()
     value = float(np.mean(rates))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(walls) * 1e3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "C3 compenetration sweep: 10M candidate poses of two 150-atom fragments per GPU, thresh 1.5 A",
+        "config": {"workload": WORKLOAD,
                    "sample_poses_per_step": n_sample, "n_atoms": [N_ATOMS, N_ATOMS],
-                   "note": "each step screens a bounded sample of the same sweep (same fragments, same pose "
-                           "distribution) with the reference's per-pose arithmetic on all host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                   "note": "SAMPLED: each step screens a bounded sample of the same sweep (same fragments, same pose "
+                           "distribution) with the reference's per-pose arithmetic on all physical host cores; the "
+                           "worker pool is created outside the timed window"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "logical_cpus": logical, "kind": cpu.kind,
                          "sample": f"{n_sample} poses per step of the C3 sweep, per-pose "
                                    "get_embed + scipy cdist compenetration_check (oracle/port.py), "
-                                   "multiprocessing over all host cores"},
+                                   "one worker process per physical core"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -184,6 +237,14 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
+def _profile_json(name):
+    path = os.path.join(ROOT, "profiles", name)
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f), os.path.relpath(path, ROOT)
+    return None, None
+
+
 def run_cuda(args):
     import ctypes as C
 
@@ -206,41 +267,88 @@ def run_cuda(args):
     a_dev = torch.from_numpy(a).to(dev)[None].contiguous()
     b_dev = torch.from_numpy(b).to(dev)[None].contiguous()
 
-    # pose set of this rank, generated on the device with the same recipe as synthetic.sweep_poses
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(synthetic.SEED + 17 * rank)
-    q = torch.randn(n_poses, 4, generator=gen, device=dev, dtype=torch.float64)
-    q = q / q.norm(dim=1, keepdim=True)
-    x, y, z, w = q.unbind(1)
-    rot = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
-                       2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
-                       2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], dim=1)
-    d = torch.randn(n_poses, 3, generator=gen, device=dev, dtype=torch.float64)
-    d = d / d.norm(dim=1, keepdim=True)
-    base = synthetic.radius_of_gyration(a) + synthetic.radius_of_gyration(b)
-    radius = base - 2.0 + 6.0 * torch.rand(n_poses, 1, generator=gen, device=dev, dtype=torch.float64)
-    xf = torch.cat([rot, d * radius], dim=1).float().double().contiguous()
-    del q, rot, d, radius, x, y, z, w
+    # pose set of this rank, generated on the device with the same recipe as synthetic.sweep_poses:
+    # a random quaternion and a translation on a shell, rounded to float32 (the compact pose, 28 B), and its
+    # documented FP64 expansion (R | t, 96 B) -- the two forms the screen accepts
+    def make_poses(n, seed):
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(seed)
+        q = torch.randn(n, 4, generator=gen, device=dev, dtype=torch.float64)
+        q = q / q.norm(dim=1, keepdim=True)
+        d = torch.randn(n, 3, generator=gen, device=dev, dtype=torch.float64)
+        d = d / d.norm(dim=1, keepdim=True)
+        base = synthetic.radius_of_gyration(a) + synthetic.radius_of_gyration(b)
+        radius = base - 2.0 + 6.0 * torch.rand(n, 1, generator=gen, device=dev, dtype=torch.float64)
+        p7 = torch.cat([q, d * radius], dim=1).float().contiguous()
+        x, y, z, w = p7[:, :4].double().unbind(1)
+        s = 2.0 / (((x * x + y * y) + z * z) + w * w)
+        rot = torch.stack([1 - s * (y * y + z * z), s * (x * y - z * w), s * (x * z + y * w),
+                           s * (x * y + z * w), 1 - s * (x * x + z * z), s * (y * z - x * w),
+                           s * (x * z - y * w), s * (y * z + x * w), 1 - s * (x * x + y * y)], dim=1)
+        return p7, torch.cat([rot, p7[:, 4:].double()], dim=1).contiguous()
 
-    status = torch.empty(n_poses, dtype=torch.uint8, device=dev)
-    bits = torch.empty((n_poses + 31) // 32, dtype=torch.int32, device=dev)
-    gathered = torch.empty(world * bits.numel(), dtype=torch.int32, device=dev) if world > 1 else None
+    pose7, xf = make_poses(n_poses, synthetic.SEED + 17 * rank)
+
+    n_words = (n_poses + 31) // 32
+    bits2 = [torch.empty(n_words, dtype=torch.int32, device=dev) for _ in range(2)]
+    gathered2 = [torch.empty(world * n_words, dtype=torch.int32, device=dev) for _ in range(2)] if world > 1 else None
     near = (torch.zeros(4, dtype=torch.int32, device=dev), torch.zeros(4096, dtype=torch.int64, device=dev),
             torch.zeros(4096, dtype=torch.float64, device=dev))
+    recheck_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    ev_bits = [torch.cuda.Event() for _ in range(2)]
+    ev_gath = [torch.cuda.Event() for _ in range(2)]
 
-    # 2x table prep, [bounding box + grid build,] screen kernel, FP64 recheck (+ pack)
-    launches_per_step = (6 if os.environ.get("FC_CLASH_MODE") != "0" else 4) + (1 if world > 1 else 0)
+    # kernels per step: A tables (Gram pairs, bounding box, cell grid), B tables (all-pairs layout, farthest-point
+    # order), three levels of the cell-list screen (one kernel in all-pairs mode), FP64 recheck (+ pack in all-pairs mode)
+    cell_mode = os.environ.get("FC_CLASH_MODE") != "0"
+    launches_per_step = 9 if cell_mode else 6
 
-    def step():
-        clash.screen_device(a_dev, b_dev, xf, THRESH, status_out=status, near=near)
+    def screen(poses, fmt, n, bits_out, status_out=None):
+        # one pass of the hot path: both fragments' tables, the screen, the FP64 recheck; survivors as a bitmask
+        prep = clash.DevicePrep(a_dev, THRESH, want_cells=True)
+        clash.screen_device_ex(prep, b_dev, poses[:n], fmt, bits_out=bits_out, status_out=status_out, near=near,
+                               recheck_count=recheck_cnt)
+        prep.free()
+
+    step_i = [0]
+
+    def step(poses=xf, fmt=clash.POSE_XF64, n=n_poses, words=n_words):
+        k = step_i[0] & 1
+        step_i[0] += 1
         if world > 1:
-            clash.pack_mask_device(status, bits)
-            dist.all_gather_into_tensor(gathered, bits)
+            torch.cuda.current_stream().wait_event(ev_gath[k])  # the all-gather that last read this buffer is done
+        screen(poses, fmt, n, bits2[k])
+        if world > 1:
+            # the bitmask exchange of step k rides a side stream and overlaps the screen of step k + 1
+            ev_bits[k].record()
+            with torch.cuda.stream(side):
+                side.wait_event(ev_bits[k])
+                dist.all_gather_into_tensor(gathered2[k][: world * words], bits2[k][:words])
+                ev_gath[k].record()
 
     def barrier():
         if world > 1:
+            side.synchronize()
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(n_steps, **kw):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(n_steps):
+            step(**kw)
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(side)  # the last exchange belongs to the timed region
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -251,23 +359,36 @@ def run_cuda(args):
         sampler.start()
         time.sleep(1.0)  # nvidia-smi needs a moment before its first sample
     lib.fc_clash_timing(1, None, None)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
+    recheck_cnt.zero_()
+    elapsed_ms = timed(args.steps)
     k_ms, k_n = C.c_double(0), C.c_int64(0)
     lib.fc_clash_timing(0, C.byref(k_ms), C.byref(k_n))
     clocks = sampler.stop() if rank == 0 else None
+    n_recheck = int(recheck_cnt.item()) // max(1, args.steps)
+    bits_cell = bits2[(step_i[0] - 1) & 1].clone()
+    n_pass = int(sum(bin(int(w) & 0xffffffff).count("1") for w in bits_cell[:64].tolist()))  # spot value, full count below
+    n_pass = int(torch.from_numpy(np.unpackbits(bits_cell.cpu().numpy().view(np.uint8))).sum().item())
+
+    # ---- same screen on the compact poses (28 B per pose read instead of 96 B) ----------------------
+    for _ in range(2):
+        step(poses=pose7, fmt=clash.POSE_Q7)
+    q7_ms = timed(max(1, min(args.steps, 10)), poses=pose7, fmt=clash.POSE_Q7) / max(1, min(args.steps, 10))
+    bits_q7 = bits2[(step_i[0] - 1) & 1].clone()
+    assert torch.equal(bits_q7, bits_cell), "compact-pose and f64-transform screens disagree"
+
+    # ---- strong scaling (BASELINE.json configs[2] as written: 10 M poses IN TOTAL over the N GPUs) -----
+    strong = None
     if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    n_pass = int((status & 1).sum().item())
-    n_recheck = int(((status & 2) != 0).sum().item())
+        n_strong = (args.poses // world + 31) // 32 * 32
+        w_strong = n_strong // 32
+        for _ in range(3):
+            step(n=n_strong, words=w_strong)
+        s_steps = max(1, min(args.steps, 20))
+        s_ms = timed(s_steps, n=n_strong, words=w_strong) / s_steps
+        strong = {"scaling": "strong", "total_poses": n_strong * world, "poses_per_gpu": n_strong, "ms_per_step": s_ms,
+                  "value": n_strong * world / (s_ms * 1e-3), "unit": UNIT, "steps": s_steps,
+                  "note": "same step (tables + screen + recheck + bitmask all-gather on a side stream), 10 M poses split "
+                          "over the ranks"}
 
     # ---- the all-pairs Gram-form kernel on the same poses (the formulation SURVEY.md 8d's FP32 roofline is
     #      written for); the default path above is the cell-list screen, which skips far atom pairs
@@ -278,39 +399,34 @@ def run_cuda(args):
     barrier()
     lib.fc_clash_timing(1, None, None)
     ap_steps = max(1, min(args.steps, 5))
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev2.record()
-    for _ in range(ap_steps):
-        step()
-    ev3.record()
-    barrier()
-    ap_ms_per_step = ev2.elapsed_time(ev3) / ap_steps
+    ap_ms_per_step = timed(ap_steps) / ap_steps
     ap_ms, ap_n = C.c_double(0), C.c_int64(0)
     lib.fc_clash_timing(0, C.byref(ap_ms), C.byref(ap_n))
-    ap_pass = int((status & 1).sum().item())
-    assert ap_pass == n_pass, "cell-list and all-pairs paths disagree"
+    bits_ap = bits2[(step_i[0] - 1) & 1].clone()
+    # mask EQUALITY of the two kernels on the full pose set (not only the pass count)
+    assert torch.equal(bits_ap, bits_cell), "cell-list and all-pairs paths disagree"
     if mode_default is None:
         os.environ.pop("FC_CLASH_MODE", None)
     else:
         os.environ["FC_CLASH_MODE"] = mode_default
     cell_path = mode_default != "0"
 
-    # ---- end to end through the public host API: pinned host xf in, status bytes out -----------
-    e2e = None
+    # ---- end to end through the public host API: pinned compact poses in, survivor bitmask out --------
     e2e_poses = min(n_poses, args.e2e_poses)
-    xf_host = torch.empty((e2e_poses, 12), dtype=torch.float64, pin_memory=True)
-    xf_host.copy_(xf[:e2e_poses])
-    xf_np = xf_host.numpy()
+    p7_host = clash.pinned_empty((e2e_poses, 7), np.float32)
+    p7_t = torch.from_numpy(p7_host)
+    p7_t.copy_(pose7[:e2e_poses])
+    bits_host = clash.pinned_empty(((e2e_poses + 31) // 32,), np.uint32)
     barrier()
     for _ in range(3):  # warm-up at the timed size: pinned staging buffer and pool reach their final size
-        clash.compenetration_check_batch(a, b, xf_np, thresh=THRESH)
+        clash.compenetration_check_batch_pose7(a, b, p7_host, thresh=THRESH, bits_out=bits_host)
     barrier()
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 10))
     per_step = []
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         t1 = time.perf_counter()
-        res = clash.compenetration_check_batch(a, b, xf_np, thresh=THRESH)
+        res = clash.compenetration_check_batch_pose7(a, b, p7_host, thresh=THRESH, bits_out=bits_host)
         per_step.append((time.perf_counter() - t1) * 1e3)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
@@ -318,22 +434,38 @@ def run_cuda(args):
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    assert int(res.mask.sum()) == int((status[:e2e_poses] & 1).sum().item()), "e2e and device paths disagree"
-    # raw pinned host -> device bandwidth of this box, for context: the e2e path moves 96 B per pose
-    dst = torch.empty_like(xf[:e2e_poses])
+    assert np.array_equal(res.bits, bits_cell.cpu().numpy().view(np.uint32)[: len(res.bits)]) or e2e_poses != n_poses, \
+        "e2e and device paths disagree"
+    # raw pinned host -> device bandwidth of this box, for context: the e2e path moves 28 B per pose
+    dst = torch.empty_like(pose7[:e2e_poses])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(3):
-        dst.copy_(xf_host, non_blocking=True)
+        dst.copy_(p7_t, non_blocking=True)
     torch.cuda.synchronize()
-    h2d_gbs = 3 * xf_host.numel() * 8 / (time.perf_counter() - t0) / 1e9
+    h2d_gbs = 3 * p7_t.numel() * 4 / (time.perf_counter() - t0) / 1e9
     del dst
     e2e = {"value": world * e2e_poses / e2e_s, "unit": UNIT, "h2d_gbs_pinned_measured": h2d_gbs,
-           "h2d_bound_poses_per_s": world * h2d_gbs * 1e9 / 96.0,
-           "h2d_bytes_per_step": int(e2e_poses * 96 + (len(a) + len(b)) * 24),
-           "d2h_bytes_per_step": int(e2e_poses), "poses_per_step": e2e_poses, "steps": e2e_steps,
+           "h2d_bound_poses_per_s": world * h2d_gbs * 1e9 / 28.0,
+           "h2d_bytes_per_step": int(e2e_poses * 28 + (len(a) + len(b)) * 24),
+           "d2h_bytes_per_step": int(res.bits.nbytes + 16), "poses_per_step": e2e_poses, "steps": e2e_steps,
            "ms_per_step_each": [round(x, 2) for x in per_step],
-           "api": "firecode_b200.clash.compenetration_check_batch -> C-ABI fc_clash_batch (pinned host buffers)"}
+           "api": "firecode_b200.clash.compenetration_check_batch_pose7 -> C-ABI fc_clash_batch_pose7 (pinned host "
+                  "buffers: 28 B per pose in, 1 bit per pose out)"}
+    # the f64-transform form of the same API (96 B per pose in, status bytes out), for comparison with round 1
+    xf_host = clash.pinned_empty((e2e_poses, 12), np.float64)
+    torch.from_numpy(xf_host).copy_(xf[:e2e_poses])
+    for _ in range(2):
+        clash.compenetration_check_batch(a, b, xf_host, thresh=THRESH)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        res64 = clash.compenetration_check_batch(a, b, xf_host, thresh=THRESH)
+    x64_s = (time.perf_counter() - t0) / 3
+    assert res64.n_pass == res.n_pass or e2e_poses != n_poses
+    e2e["xf64_api"] = {"value": world * e2e_poses / x64_s, "unit": UNIT, "h2d_bytes_per_step": int(e2e_poses * 96),
+                       "d2h_bytes_per_step": int(e2e_poses),
+                       "api": "firecode_b200.clash.compenetration_check_batch -> fc_clash_batch (f64 R|t, as round 1)"}
+    del xf_host, p7_host
 
     if rank != 0:
         if world > 1:
@@ -345,10 +477,9 @@ def run_cuda(args):
     peaks, peak_kind = _peaks()
     kernel_ms = k_ms.value / max(1, k_n.value)
     pairs = float(n_poses) * N_ATOMS * N_ATOMS
-    achieved_tf = FLOP_PER_PAIR * pairs / (kernel_ms * 1e-3) / 1e12
-    executed_tf = EXEC_FLOP_PER_PAIR * pairs / (kernel_ms * 1e-3) / 1e12
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    peak_tf = sms * 128 * 2 * peaks.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+    clock_hz = peaks.get("sm_max_mhz", 1965.0) * 1e6
+    peak_tf = sms * 128 * 2 * clock_hz / 1e12
     probe_tf, probe_ms = C.c_double(0), C.c_double(0)
     lib.fc_probe_fp32_peak(C.byref(probe_tf), C.byref(probe_ms), None)
     geom = (C.c_int32 * 4)()
@@ -362,40 +493,60 @@ def run_cuda(args):
         "poses_per_s": world * n_poses / (ap_ms_per_step * 1e-3),
         "executed_tflops": EXEC_FLOP_PER_PAIR * pairs / (ap_kernel_ms * 1e-3) / 1e12,
         "executed_frac": EXEC_FLOP_PER_PAIR * pairs / (ap_kernel_ms * 1e-3) / 1e12 / peak_tf,
+        "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x sm_max_mhz ({peak_kind} MEASURED_PEAKS.json clock); FFMA2 probe "
+                       f"measured {probe_tf.value:.1f} TFLOP/s in this run",
         "note": "every atom pair evaluated (Gram form: 3 FMA + half an FMNMX3 per pair = 4 issue cycles per pair per "
                 "lane, so frac = 1.0 is this formulation's ceiling and the FMA pipe cannot exceed 75 %); run with "
-                "FC_CLASH_MODE=0 on the same poses, same status bytes"}
-    traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_clash_cell_traffic.json" if cell_path else "r01_clash_allpairs_traffic.json")
-    if os.path.isfile(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic = (tj["dram_read_bytes"] + tj["dram_write_bytes"]) / tj["poses"] * n_poses
-        traffic_src = f"{os.path.relpath(tpath, ROOT)}: ncu --set full capture of {tj['poses']} poses, scaled per pose"
+                "FC_CLASH_MODE=0 on the same poses; survivor bitmask identical to the cell-list screen's (asserted)"}
+
+    # ---- roofline of the kernel that is timed.  The cell-list screen is bounded from below by its HBM traffic only
+    #      (96 B of transform read + 1 bit written per pose); what actually limits it is instruction issue, so the
+    #      issue-slot utilisation is reported beside it (warp instructions per pose from the committed ncu capture).
+    pose_bytes = 96.0 + 0.125
+    alg_bytes = n_poses * pose_bytes
+    hbm_achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    prof, prof_src = _profile_json("r02_clash_cell_profile.json")
+    traffic = None
+    issue = None
+    if prof:
+        traffic = (prof["dram_read_bytes"] + prof["dram_write_bytes"]) / prof["poses"] * n_poses
+        inst = prof["warp_inst_executed"] / prof["poses"] * n_poses
+        issue_peak = sms * 4 * clock_hz
+        issue = {"warp_inst_per_pose": prof["warp_inst_executed"] / prof["poses"], "achieved_inst_per_s": inst / (kernel_ms * 1e-3),
+                 "peak_inst_per_s": issue_peak, "frac": inst / (kernel_ms * 1e-3) / issue_peak,
+                 "source": f"{prof_src}: smsp__inst_executed.sum of the screen's level kernels over {prof['poses']} poses; peak = "
+                           f"{sms} SMs x 4 schedulers x sm_max_mhz"}
     roofline = {
-        "bound": "fp32", "kernel": "fc::clash_cell_kernel" if cell_path else "fc::clash_f32_kernel",
-        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
-        "traffic_source": traffic_src, "algorithmic_bytes": n_poses * 97.0,
-        "peak_source": f"{sms} SMs x 128 FP32 lanes x 2 x sm_max_mhz ({peak_kind} MEASURED_PEAKS.json clock); no FP32 figure in MEASURED_PEAKS.json",
-        "algorithmic_flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs, "kernel_ms": kernel_ms,
-        "fp32_probe_tflops": probe_tf.value,
-        "note": ("ALGORITHMIC work per SURVEY.md 8d = 8 FLOP x all N_A x N_B atom pairs of every pose; the cell-list "
-                 "kernel reaches the same decisions while evaluating only the pairs inside a candidate radius, so "
-                 "frac exceeds 1 (it measures work avoided, not pipe utilisation: ncu shows issue slots 74 % / ALU "
-                 "pipe 62 % busy, profiles/r01_clash_cell_ncu_summary.md); roofline_allpairs is the all-pairs "
-                 "kernel against the same peak") if cell_path else
-                "Gram-form kernel executes 3 FMA (6 flop) per pair for the 8 algorithmic flop of the difference form",
-        "hbm_gbs_peak": peaks.get("hbm_gbs"), "hbm_gbs_achieved": n_poses * 97.0 / (kernel_ms * 1e-3) / 1e9,
-        "hbm_frac": n_poses * 97.0 / (kernel_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6548.2)}
+        "bound": "hbm", "kernel": "fc::clash_cell_kernel (3 level launches)" if cell_path else "fc::clash_f32_kernel",
+        "achieved": hbm_achieved, "peak": peaks.get("hbm_gbs"), "unit": "GB/s", "frac": hbm_achieved / peaks.get("hbm_gbs", 6548.2),
+        "traffic": traffic, "traffic_source": prof_src, "algorithmic_bytes": alg_bytes,
+        "algorithmic_bytes_per_pose": pose_bytes, "peak_source": f"{peak_kind} MEASURED_PEAKS.json hbm_gbs (burst copy)",
+        "kernel_ms": kernel_ms, "issue": issue,
+        "work_avoided": {"allpairs_flop": FLOP_PER_PAIR * pairs, "allpairs_equivalent_tflops": FLOP_PER_PAIR * pairs / (kernel_ms * 1e-3) / 1e12,
+                         "speedup_over_allpairs_kernel": ap_kernel_ms / kernel_ms,
+                         "note": "SURVEY.md 8d counts 8 FLOP x all N_A x N_B atom pairs per pose; the cell-list screen reaches the "
+                                 "same decisions (bitmask equality asserted on the full set) while visiting only pairs inside a "
+                                 "candidate radius, so that figure measures work avoided and is NOT a roofline fraction"},
+        "note": "HBM is the only hard floor of this kernel (it reads each pose once); it is instruction-issue bound "
+                "(see `issue` and profiles/r02_clash_cell_ncu_summary.md), so frac is small by construction"}
 
     cpu = None
     if world == 1 and not args.no_cpu:
-        cores = len(os.sched_getaffinity(0))
-        n_sample = 4000 * cores
-        rate, cores, _, wall = cpu_screen_rate(n_sample, cores)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+        cores, logical = physical_cores()
+        cs = CpuScreen(cores)
+        n_sample = 6000 * cores
+        rate, _, wall = cs.rate(n_sample)
+        cs.close()
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "logical_cpus": logical, "kind": "port",
                "sample": f"{n_sample} poses of the same sweep ({wall:.1f} s wall): per-pose get_embed + "
-                         "scipy cdist compenetration_check (oracle/port.py) on all host cores"}
+                         "scipy cdist compenetration_check (oracle/port.py), one worker per physical core, pool "
+                         "created outside the timed window"}
+        if os.path.isdir("/root/reference/firecode"):
+            cs = CpuScreen(cores, use_reference=True)
+            rate_ref, _, wall_ref = cs.rate(n_sample)
+            cs.close()
+            cpu["reference_function"] = {"value": rate_ref, "kind": cs.kind, "seconds": wall_ref,
+                                         "note": "the unmodified firecode.utils.compenetration_check beside the port"}
 
     extras = None
     if world == 1 and not args.no_extras:
@@ -405,14 +556,19 @@ def run_cuda(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (+f64 recheck)", "data": "synthetic",
-        "config": {"workload": "C3 compenetration sweep: 10M candidate poses of two 150-atom fragments per GPU, thresh 1.5 A",
+        "config": {"workload": WORKLOAD,
                    "poses_per_gpu": n_poses, "n_atoms": [N_ATOMS, N_ATOMS], "l2": "inputs (960 MB of pose transforms per step) exceed L2",
                    "pass_fraction": n_pass / n_poses, "fp64_rechecks": n_recheck,
                    "path": "cell-list screen (default)" if cell_path else "all-pairs kernel (FC_CLASH_MODE=0)",
+                   "checks": "survivor bitmasks of the cell-list screen, the all-pairs kernel, the compact-pose screen and "
+                             "the host API are bit-identical on the full pose set (asserted in this run)",
                    "kernel_geometry": {"atoms_per_thread": geom[0], "threads_per_pose": geom[1],
                                        "poses_per_tile": geom[2], "threads_per_block": geom[3]}},
         "roofline": roofline,
         "roofline_allpairs": roofline_allpairs,
+        "device_resident_pose7": {"value": world * n_poses / (q7_ms * 1e-3), "unit": UNIT, "ms_per_step": q7_ms,
+                                  "note": "same step on the compact poses (28 B per pose read instead of 96 B)"},
+        "strong_scaling": strong,
         "cpu_baseline": cpu,
         "e2e": e2e,
         "clocks": clocks,

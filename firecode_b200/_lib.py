@@ -123,9 +123,16 @@ SIGNATURES = {
     "fc_clash_screen_prepared_dev": (C.c_int, [VP, VP, VP, C.c_int, C.c_int, VP, C.c_int64, VP, C.c_int64, C.c_int,
                                                C.c_int, VP, VP, VP, VP, VP, C.c_int64, C.c_int64, VP]),
     "fc_clash_prep_free": (None, [VP, VP]),
+    "fc_clash_cell_meta": (C.c_int, [VP, C.c_int, C.c_int, C.c_double, c_fp]),
     "fc_clash_batch": (C.c_int, [VP, C.c_int, C.c_int, VP, C.c_int, C.c_int, VP, C.c_int64, VP,
                                  C.c_int64, C.c_double, C.c_int, C.c_int, VP, VP, VP, VP, VP,
                                  C.c_int64]),
+    "fc_clash_screen_ex_dev": (C.c_int, [VP, VP, VP, C.c_int, C.c_int, VP, C.c_int, C.c_int64, VP, C.c_int64, C.c_int,
+                                         C.c_int, VP, VP, VP, VP, VP, VP, C.c_int64, C.c_int64, VP, VP]),
+    "fc_clash_batch_pose7": (C.c_int, [VP, C.c_int, C.c_int, VP, C.c_int, C.c_int, VP, C.c_int64, VP, C.c_int64,
+                                       C.c_double, C.c_int, C.c_int, VP, VP, VP, VP, VP, C.c_int64]),
+    "fc_host_alloc": (VP, [C.c_int64, c_i32p]),
+    "fc_host_free": (None, [VP]),
     "fc_clash_geometry": (C.c_int, [C.c_int, c_i32p]),
     "fc_clash_timing": (C.c_int, [C.c_int, c_dp, c_i64p]),
     "fc_pack_mask_dev": (C.c_int, [VP, C.c_int64, VP, VP]),

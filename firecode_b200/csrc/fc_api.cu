@@ -92,7 +92,7 @@ extern "C" int fc_pack_mask_dev(const uint8_t* status, int64_t n, uint32_t* bits
 }
 
 extern "C" const char* fc_last_error(void) { return g_err; }
-extern "C" int fc_version(void) { return 100; }
+extern "C" int fc_version(void) { return 200; }
 
 extern "C" int fc_device_count(void) {
     int n = 0;

@@ -20,6 +20,9 @@
 // `<` / `<=` compare, clash count).  Poses whose FP64 minimum distance lies within FC_NEAR_EPS of
 // the threshold are flagged and listed.
 #include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
 
 #include "fc_common.cuh"
 
@@ -386,28 +389,42 @@ __global__ void __launch_bounds__(ClashLaunch<TB>::kMaxThreads, 1) clash_f32_ker
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cell-list screen: the same decision without touching far atom pairs.
+// Cell-list screen (v2): the same decision without touching far atom pairs.
 // ---------------------------------------------------------------------------------------------
-// Fragment A (per conformer) is binned once per call into a G^3 grid over the bounding box of the whole
-// ensemble, padded by the clash radius.  A cell record (16 bytes, one LDG.128) holds the number of
-// candidate atoms and up to 15 of their indices: every atom whose distance to the cell CENTRE is at
-// most  rc = thresh + kCellPad + h*sqrt(3)/2  -- a superset of the atoms within thresh + kCellPad of ANY
-// point of the cell, hence of every atom that can decide the pose (the FP32 band is far below kCellPad;
-// poses whose band is not are sent to the FP64 recheck).  A query (pose, atom of B) transforms the atom,
-// finds its cell and evaluates only the listed atoms, in the difference form; cells with more than 15
-// candidates (count byte 255) fall back to scanning all atoms of A for that query.
-// One thread per pose, one warp per 32 consecutive poses; fragments and grid are read through L1/L2
-// (150 atoms = 2.4 KB, grid = G^3 * 16 B per conformer).  The FP32 band / FP64 recheck protocol of the
-// all-pairs kernel is unchanged, so both paths produce identical status bytes.
+// Fragment A (per conformer) is binned once per call into a G^3 grid of cubic cells CENTRED on the lattice
+// points o + n*h (n = 0 .. G-1 per axis).  A cell record (16 bytes, one LDG.128) holds the number of candidate
+// atoms and up to 15 of their indices: every atom whose distance to the cell centre is at most
+//      rc = thresh + kCellPad + h*sqrt(3)/2 + 1e-3
+// -- a superset of the atoms within thresh + kCellPad of ANY point of the cell, hence of every atom that can
+// decide the pose (the FP32 band and the cell-assignment rounding are far below kCellPad; poses whose band is
+// not are sent to the FP64 recheck).  Next to it a 1-bit-per-cell occupancy grid (32 KB per conformer at G = 64:
+// L1-resident).  The box is padded so that every BORDER cell is empty; a query point is clamped into the box for
+// free by the .SAT modifier of its last FFMA, so a point outside the box reads an (empty) border cell -- which
+// is the right answer, it is further than rc from every atom -- and neither phase needs a range check.
+//
+// One thread per pose; atoms of B in blocks of 32:
+//   phase 1 flags the atoms that land in an occupied cell: normalised box coordinates u = sat((R b + t - o) / ((G-1) h))
+//           (9 FFMA), one FFMA per axis scales u to the cell coordinate and adds 1.5 * 2^23 so that the cell number
+//           appears in the low mantissa bits -- scaled per axis so that x, y, z land in disjoint bit fields and the
+//           linear cell index is two LOP3s -- then one occupancy word and two funnel shifts;
+//   phase 2 visits only the flagged atoms: one LDG.128 cell record, difference-form distances to its candidates,
+//           early exit once the pose is decided (certain clash).
+// Early exit only pays if the lanes of a warp exit together, so the screen runs in LEVELS over the atoms of B
+// (atoms [0,32), [32,64), [64,n_b)), B being re-ordered once per call so that its first atoms are spread over its
+// surface (farthest-point order): a level finalises the poses it can decide and appends the others -- (pose, running
+// minimum) -- to a compact list that the next level processes with dense warps.
+// The FP32 band / FP64 recheck protocol of the all-pairs kernel is unchanged, so both paths produce identical
+// status bytes.  Poses arrive either as 12 doubles (R row-major, t) or in the compact form of fc_clash_screen_pose7_dev.
 constexpr float kCellPad = 0.05f;
+constexpr float kCellMagic = 12582912.0f;  // 1.5 * 2^23: the adder leaves round-to-nearest(x) in the low mantissa bits
 
 struct CellMeta {        // written by clash_bbox_kernel, read by the grid / query kernels
-    float ox, oy, oz;    // grid origin
-    float h, inv_h;      // cell edge
+    float ox, oy, oz;    // centre of cell (0, 0, 0)
+    float h;             // cell edge
+    float inv_span;      // 1 / ((g - 1) h): box coordinates u in [0, 1]
     float rc2;           // squared candidate radius around a cell centre
-    int g;               // cells per axis
-    int gmask;           // 2^ceil(log2 g) - 1
-    unsigned cell_bias;  // 0x4B400000 * (g*g + g + 1) mod 2^32 (biased -> linear cell index)
+    int g;               // cells per axis (power of two)
+    int shift;           // log2 g
 };
 
 __global__ void __launch_bounds__(256) clash_bbox_kernel(const double* __restrict__ a_coords, long long n_atoms_total,
@@ -429,25 +446,30 @@ __global__ void __launch_bounds__(256) clash_bbox_kernel(const double* __restric
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        float ext = 0.f, l[3];
-        const float pad = thresh + kCellPad + 0.01f;
+        float span = 0.f, mid[3];
         for (int c = 0; c < 3; ++c) {
             float a = 3e38f, b = -3e38f;
             for (int w = 0; w < 8; ++w) { a = fminf(a, s_lo[c][w]); b = fmaxf(b, s_hi[c][w]); }
-            l[c] = a - pad;
-            ext = fmaxf(ext, (b + pad) - l[c]);
+            mid[c] = 0.5f * (a + b);
+            span = fmaxf(span, b - a);
         }
+        // lattice of g points per axis over the atoms' extent plus, on both sides, more than the candidate radius:
+        // (g-1) h = span + 2 (thresh + kCellPad) + 0.05 + 1.8 h  =>  border lattice points are further than rc from
+        // every atom along their axis (margin 0.024 + 0.03 h), so border cells have no candidates
+        const float tp = thresh + kCellPad;
         CellMeta m;
-        m.ox = l[0]; m.oy = l[1]; m.oz = l[2];
-        m.h = ext / (float)g * 1.0001f;
-        m.inv_h = 1.0f / m.h;
-        float rc = thresh + kCellPad + m.h * 0.8661f + 1e-3f;
+        m.h = (span + 2.f * tp + 0.05f) / ((float)g - 2.8f);
+        const float ext = (float)(g - 1) * m.h;
+        m.ox = mid[0] - 0.5f * ext;
+        m.oy = mid[1] - 0.5f * ext;
+        m.oz = mid[2] - 0.5f * ext;
+        m.inv_span = 1.0f / ext;
+        float rc = tp + m.h * 0.8661f + 1e-3f;
         m.rc2 = rc * rc;
         m.g = g;
-        int pw = 1;
-        while (pw < g) pw <<= 1;
-        m.gmask = pw - 1;
-        m.cell_bias = 0x4B400000u * (unsigned)(g * g + g + 1);
+        int sh = 0;
+        while ((1 << sh) < g) ++sh;
+        m.shift = sh;
         *meta = m;
     }
 }
@@ -471,9 +493,9 @@ __global__ void __launch_bounds__(128) clash_grid_kernel(const double* __restric
     const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // g^3 is a multiple of 128
     if (cell >= n_cells) return;
     const int cx = (int)(cell % g), cy = (int)((cell / g) % g), cz = (int)(cell / ((long long)g * g));
-    const double px = (double)m.ox + ((double)cx + 0.5) * (double)m.h;
-    const double py = (double)m.oy + ((double)cy + 0.5) * (double)m.h;
-    const double pz = (double)m.oz + ((double)cz + 0.5) * (double)m.h;
+    const double px = (double)m.ox + (double)cx * (double)m.h;
+    const double py = (double)m.oy + (double)cy * (double)m.h;
+    const double pz = (double)m.oz + (double)cz * (double)m.h;
     unsigned bytes[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) bytes[k] = 0;
@@ -497,152 +519,345 @@ __global__ void __launch_bounds__(128) clash_grid_kernel(const double* __restric
     rec.w = bytes[12] | (bytes[13] << 8) | (bytes[14] << 16) | (bytes[15] << 24);
     grid[(size_t)conf * n_cells + cell] = rec;
     const unsigned any = __ballot_sync(0xffffffffu, count > 0);
-    if ((threadIdx.x & 31) == 0) occ[(size_t)conf * (n_cells / 32 + 1) + (cell >> 5)] = any;
-    if (cell == 0) occ[(size_t)conf * (n_cells / 32 + 1) + n_cells / 32] = 0u;  // spare word: the dummy cell
+    if ((threadIdx.x & 31) == 0) occ[(size_t)conf * (n_cells / 32) + (cell >> 5)] = any;
 }
+
+// Fragment B for the cell-list screen: [conf][n_b] float4 {x, y, z, 0} in farthest-point order for the first
+// `n_spread` positions (seed: the atom farthest from the centroid; then repeatedly the atom farthest from everything
+// chosen so far), original order behind them.  The screen's result does not depend on the order (a minimum over all
+// atoms); the order only decides how early a clashing pose is recognised.  One warp per conformer.
+__global__ void __launch_bounds__(32) clash_order_b_kernel(const double* __restrict__ coords, int n_b, int n_spread,
+                                                           float4* __restrict__ b_ord) {
+    extern __shared__ float s_ob[];  // x[n_b], y[n_b], z[n_b], d[n_b], then int taken-order [n_b]
+    float* sx = s_ob;
+    float* sy = sx + n_b;
+    float* sz = sy + n_b;
+    float* sd = sz + n_b;
+    int* sel = reinterpret_cast<int*>(sd + n_b);
+    const int conf = blockIdx.x, lane = threadIdx.x;
+    const double* src = coords + (size_t)conf * n_b * 3;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    for (int i = lane; i < n_b; i += 32) {
+        sx[i] = (float)src[3 * i];
+        sy[i] = (float)src[3 * i + 1];
+        sz[i] = (float)src[3 * i + 2];
+        cx += sx[i];
+        cy += sy[i];
+        cz += sz[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cx += __shfl_xor_sync(0xffffffffu, cx, o);
+        cy += __shfl_xor_sync(0xffffffffu, cy, o);
+        cz += __shfl_xor_sync(0xffffffffu, cz, o);
+    }
+    cx /= (float)n_b;
+    cy /= (float)n_b;
+    cz /= (float)n_b;
+    __syncwarp();
+    // distance to the chosen set; first round: distance to the centroid
+    float px = cx, py = cy, pz = cz;
+    for (int i = lane; i < n_b; i += 32) sd[i] = 3e38f;
+    const int rounds = n_spread < n_b ? n_spread : n_b;
+    for (int r = 0; r < rounds; ++r) {
+        float best = -1.f;
+        int best_i = 0x7fffffff;
+        for (int i = lane; i < n_b; i += 32) {
+            float d = sd[i];
+            if (d >= 0.f) {  // not taken yet
+                float dx = sx[i] - px, dy = sy[i] - py, dz = sz[i] - pz;
+                float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                d = r == 0 ? d2 : fminf(d, d2);
+                sd[i] = d;
+                if (d > best) { best = d; best_i = i; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+        }
+        if (lane == 0) {
+            sel[r] = best_i;
+            sd[best_i] = -1.f;  // taken
+        }
+        __syncwarp();
+        px = sx[best_i];
+        py = sy[best_i];
+        pz = sz[best_i];
+        if (r == 0)  // from now on: distance to the chosen atoms only
+            for (int i = lane; i < n_b; i += 32)
+                if (sd[i] >= 0.f) sd[i] = 3e38f;
+        __syncwarp();
+    }
+    if (lane == 0) {  // the rest in original order
+        int w = rounds;
+        for (int i = 0; i < n_b; ++i)
+            if (sd[i] >= 0.f) sel[w++] = i;
+    }
+    __syncwarp();
+    for (int i = lane; i < n_b; i += 32) {
+        const int k = sel[i];
+        b_ord[(size_t)conf * n_b + i] = make_float4(sx[k], sy[k], sz[k], 0.f);
+    }
+}
+
+// pose formats of the cell-list screen and the FP64 recheck
+enum { kPoseXf64 = 0, kPoseQ7 = 1 };
+
+// compact pose (fc_clash_screen_pose7_dev): q = (x, y, z, w) any non-zero quaternion, t; the rotation is
+//   R = I + (2 / |q|^2) * [[-(yy+zz), xy-zw, xz+yw], [xy+zw, -(xx+zz), yz-xw], [xz-yw, yz+xw, -(xx+yy)]]
+// FP64 expansion with every operation rounded on its own (no contraction), the order the header documents, so a host
+// restatement in plain numpy produces the same doubles.
+__device__ __forceinline__ void pose7_expand_f64(const float* __restrict__ p, double* r) {
+    const double x = (double)p[0], y = (double)p[1], z = (double)p[2], w = (double)p[3];
+    const double xx = __dmul_rn(x, x), yy = __dmul_rn(y, y), zz = __dmul_rn(z, z), ww = __dmul_rn(w, w);
+    const double n = __dadd_rn(__dadd_rn(__dadd_rn(xx, yy), zz), ww);
+    const double s = __ddiv_rn(2.0, n);
+    const double xy = __dmul_rn(x, y), xz = __dmul_rn(x, z), yz = __dmul_rn(y, z);
+    const double xw = __dmul_rn(x, w), yw = __dmul_rn(y, w), zw = __dmul_rn(z, w);
+    r[0] = __dsub_rn(1.0, __dmul_rn(s, __dadd_rn(yy, zz)));
+    r[1] = __dmul_rn(s, __dsub_rn(xy, zw));
+    r[2] = __dmul_rn(s, __dadd_rn(xz, yw));
+    r[3] = __dmul_rn(s, __dadd_rn(xy, zw));
+    r[4] = __dsub_rn(1.0, __dmul_rn(s, __dadd_rn(xx, zz)));
+    r[5] = __dmul_rn(s, __dsub_rn(yz, xw));
+    r[6] = __dmul_rn(s, __dsub_rn(xz, yw));
+    r[7] = __dmul_rn(s, __dadd_rn(yz, xw));
+    r[8] = __dsub_rn(1.0, __dmul_rn(s, __dadd_rn(xx, yy)));
+    r[9] = (double)p[4];
+    r[10] = (double)p[5];
+    r[11] = (double)p[6];
+}
+
+template <int FMT>
+__device__ __forceinline__ void pose_load_f32(const void* __restrict__ poses, long long pose, float* r) {
+    if (FMT == kPoseXf64) {
+        const double2* x = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(poses) + pose * 12);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const double2 v = __ldg(x + k);
+            r[2 * k] = (float)v.x;
+            r[2 * k + 1] = (float)v.y;
+        }
+    } else {
+        const float* p = reinterpret_cast<const float*>(poses) + pose * 7;
+        const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2), w = __ldg(p + 3);
+        const float xx = x * x, yy = y * y, zz = z * z;
+        const float s = 2.0f / (xx + yy + zz + w * w);
+        const float xy = x * y, xz = x * z, yz = y * z, xw = x * w, yw = y * w, zw = z * w;
+        r[0] = 1.f - s * (yy + zz);
+        r[1] = s * (xy - zw);
+        r[2] = s * (xz + yw);
+        r[3] = s * (xy + zw);
+        r[4] = 1.f - s * (xx + zz);
+        r[5] = s * (yz - xw);
+        r[6] = s * (xz - yw);
+        r[7] = s * (yz + xw);
+        r[8] = 1.f - s * (xx + yy);
+        r[9] = __ldg(p + 4);
+        r[10] = __ldg(p + 5);
+        r[11] = __ldg(p + 6);
+    }
+}
+
+struct CellItem {  // a pose a level could not decide, handed to the next level
+    unsigned pose;
+    float dmin2;
+};
 
 struct CellArgs {
     const float4* a_xyz;
     const float* a_rad;
-    const float4* b_tab;
+    const float4* b_ord;   // [conf][n_b] farthest-point order
     const float* b_rad;
     const uint4* grid;
     const unsigned* occ;
     const CellMeta* meta;
-    const double* xf;
+    const void* poses;     // (n_poses, 12) f64 or (n_poses, 7) f32
     const int4* tiles;
     long long n_tiles, n_poses;
-    int n_a, n_b, n_b_pad, tile_poses;
+    int n_a, n_b;
+    int j_lo, j_hi;        // atoms of B this level visits
+    int last;              // no level behind this one
     float thr2;
     int count_mode;
-    uint8_t* status;
+    const CellItem* in_list;   // null: level 0, item i is pose i
+    const unsigned* in_count;
+    CellItem* out_list;
+    unsigned* out_count;
+    uint8_t* status;       // may be null
+    unsigned* bits;        // may be null: survivor bitmask, bit (p & 31) of word p >> 5
     int* unc_count;
     UncEntry* unc_list;
 };
 
-__global__ void __launch_bounds__(128) clash_cell_kernel(CellArgs p) {
-    const long long pose = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pose >= p.n_poses) return;
-    int conf_a = 0, conf_b = 0;
-    if (p.tiles) {  // tiles are sorted by first pose: binary search
-        long long lo = 0, hi = p.n_tiles - 1;
-        while (lo < hi) {
-            long long mid = (lo + hi + 1) >> 1;
-            if ((long long)p.tiles[mid].z <= pose) lo = mid;
-            else hi = mid - 1;
-        }
-        int4 t = p.tiles[lo];
-        if (pose >= (long long)t.z + t.w) return;  // pose not covered by any tile
-        conf_a = t.x;
-        conf_b = t.y;
-    }
+template <int FMT>
+__global__ void __launch_bounds__(128, 6) clash_cell_kernel(CellArgs p) {
     const CellMeta m = *p.meta;
-    const int g = m.g;
-    const double* x = p.xf + pose * 12;
-    float r[12];
+    const int g = m.g, sh = m.shift;
+    const unsigned lane = threadIdx.x & 31u;
+    const long long n_items = p.in_list ? (long long)*p.in_count : p.n_poses;
+    // per-axis scale / magic constants: cell numbers in disjoint mantissa fields (x: bits [0,sh), y: [sh,2sh), z: [2sh,3sh));
+    // x rounds to the nearest lattice point; the y and z fields truncate, so half a cell is added to them
+    const float sx = (float)(g - 1), sy = (float)((g - 1) << sh), sz = (float)((g - 1) << (2 * sh));
+    const float mx = kCellMagic, my = kCellMagic + (float)(1 << (sh - 1)), mz = kCellMagic + (float)(1 << (2 * sh - 1));
+    const unsigned fx = (unsigned)(g - 1), fy = fx << sh, fz = fx << (2 * sh);
+    const size_t n_cells = (size_t)g * g * g;
+    for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_items;
+         base += (long long)gridDim.x * blockDim.x) {
+        const long long item = base + lane;
+        const bool valid = item < n_items;
+        long long pose = item;
+        float dmin2 = 3.0e38f;
+        if (valid && p.in_list) {
+            const CellItem it = p.in_list[item];
+            pose = it.pose;
+            dmin2 = it.dmin2;
+        }
+        int conf_a = 0, conf_b = 0;
+        bool covered = valid;
+        if (valid && p.tiles) {  // tiles are sorted by first pose: binary search
+            long long lo = 0, hi = p.n_tiles - 1;
+            while (lo < hi) {
+                long long mid = (lo + hi + 1) >> 1;
+                if ((long long)p.tiles[mid].z <= pose) lo = mid;
+                else hi = mid - 1;
+            }
+            const int4 t = p.tiles[lo];
+            covered = pose >= (long long)t.z && pose < (long long)t.z + t.w;  // else: pose not covered by any tile
+            conf_a = t.x;
+            conf_b = t.y;
+        }
+        bool push = false, pass = false;
+        if (covered) {
+            float r[12];
+            pose_load_f32<FMT>(p.poses, pose, r);
+            const float tnorm = sqrtf(fmaf(r[9], r[9], fmaf(r[10], r[10], r[11] * r[11])));
+            const float4* bt = p.b_ord + (size_t)conf_b * p.n_b;
+            const float4* at = p.a_xyz + (size_t)conf_a * p.n_a;
+            const uint4* gr = p.grid + (size_t)conf_a * n_cells;
+            // phase 1 leaves the magic constant's high bits in its cell number (two LOP3s instead of three): the
+            // constant is a multiple of 32 cells, i.e. a fixed number of words, taken off the table pointer here
+            const unsigned* oc = p.occ + (size_t)conf_a * (n_cells / 32) - (size_t)(0x4B400000u >> 5);
+            asm volatile("" : "+l"(oc));  // keep it a materialised pointer: word address = one IMAD.WIDE.U32
+            // same band as the all-pairs kernel (the difference form is at least as accurate as the Gram form)
+            const float ext = p.a_rad[conf_a] + p.b_rad[conf_b] + tnorm;
+            const float band = fmaf(1.5e-6f * ext, ext, 1e-6f);
+            // once the minimum is below this value the pose is decided (certain clash, or -- with max_clashes > 0 --
+            // certain to need the FP64 count): the remaining atoms are skipped
+            const float settle = p.count_mode ? p.thr2 + band : p.thr2 - band;
+            float q[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) r[k] = (float)__ldg(x + k);
-    const float tnorm = sqrtf(fmaf(r[9], r[9], fmaf(r[10], r[10], r[11] * r[11])));
-    const float4* bt = p.b_tab + (size_t)conf_b * p.n_b_pad;
-    const float4* at = p.a_xyz + (size_t)conf_a * p.n_a;
-    const uint4* gr = p.grid + (size_t)conf_a * g * g * g;
-    const unsigned* oc = p.occ + ((size_t)conf_a * ((size_t)g * g * g / 32 + 1));
-    // same band as the all-pairs kernel (the difference form is at least as accurate as the Gram form)
-    const float ext = p.a_rad[conf_a] + p.b_rad[conf_b] + tnorm;
-    const float band = fmaf(1.5e-6f * ext, ext, 1e-6f);
-    // once the minimum is below this value the pose is decided (certain clash, or -- with max_clashes > 0 --
-    // certain to need the FP64 count): the remaining atoms are skipped
-    const float settle = p.count_mode ? p.thr2 + band : p.thr2 - band;
-    float dmin2 = 3.0e38f;
-    // grid coordinates straight from the atom: (R b + t - o) / h, with the float->int conversion done by the
-    // FP32 adder (adding 1.5 * 2^23 leaves round-to-nearest(x - 0.5) in the low mantissa bits; which of two
-    // cells a point ON a cell face goes to is irrelevant, the candidate lists carry that slack, and both
-    // phases use the same arithmetic).  F2I would run on the quarter-rate conversion unit.
-    float q[12];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) q[k] = r[k] * m.inv_h;
-    q[9] = (r[9] - m.ox) * m.inv_h - 0.5f;
-    q[10] = (r[10] - m.oy) * m.inv_h - 0.5f;
-    q[11] = (r[11] - m.oz) * m.inv_h - 0.5f;
-    const unsigned kMagicBits = 0x4B400000u;
-    const unsigned range_mask = ~(unsigned)(m.gmask);  // bits that must equal kMagicBits for 0 <= n < 2^k
-    const unsigned dummy_cell = (unsigned)g * g * g;    // one spare, always-empty word behind the bit-grid
-    for (int j0 = 0; j0 < p.n_b && !(dmin2 < settle); j0 += 32) {
-        const int jn = min(32, p.n_b - j0);
-        // ---- phase 1: flag the atoms of B that land in a cell with candidates (no distances yet), so that
-        //      the lanes of a warp do not wait for each other's candidate loops on every atom.  Integer work
-        //      is kept minimal: the ALU pipe (16 lanes) is what bounds this loop.
-        unsigned bits = 0u;
+            for (int k = 0; k < 9; ++k) q[k] = r[k] * m.inv_span;
+            q[9] = (r[9] - m.ox) * m.inv_span;
+            q[10] = (r[10] - m.oy) * m.inv_span;
+            q[11] = (r[11] - m.oz) * m.inv_span;
+            for (int j0 = p.j_lo; j0 < p.j_hi && !(dmin2 < settle); j0 += 32) {
+                const int jn = min(32, p.j_hi - j0);
+                // ---- phase 1: flag the atoms of B that land in a cell with candidates (no distances yet), so that
+                //      the lanes of a warp do not wait for each other's candidate loops on every atom
+                unsigned bits = 0u;
 #pragma unroll 4
-        for (int k = 0; k < jn; ++k) {
-            const float4 b = __ldg(bt + j0 + k);
-            const unsigned ix = __float_as_uint(fmaf(q[0], b.x, fmaf(q[1], b.y, fmaf(q[2], b.z, q[9]))) + 12582912.0f);
-            const unsigned iy = __float_as_uint(fmaf(q[3], b.x, fmaf(q[4], b.y, fmaf(q[5], b.z, q[10]))) + 12582912.0f);
-            const unsigned iz = __float_as_uint(fmaf(q[6], b.x, fmaf(q[7], b.y, fmaf(q[8], b.z, q[11]))) + 12582912.0f);
-            // all three of the form kMagicBits + n with n < 2^k  <=>  their OR is (a point that is really inside
-            // always passes; a far-away point that slips through only costs a phase-2 visit, which re-checks)
-            const bool inside = ((ix | iy | iz) & range_mask) == kMagicBits;
-            const unsigned cell = inside ? (iz * (unsigned)(g * g) + iy * (unsigned)g + ix - m.cell_bias) : dummy_cell;
-            const unsigned word = __ldg(oc + (cell >> 5));
-            bits = __funnelshift_r(bits, __funnelshift_r(word, 0u, cell), 1);  // bit (cell & 31) of word -> top of bits
-        }
-        bits >>= (32 - jn);
-        // ---- phase 2: distances to the candidate atoms of the flagged atoms only
-        while (bits && !(dmin2 < settle)) {
-            const int k = __ffs(bits) - 1;
-            bits &= bits - 1u;
-            const float4 b = __ldg(bt + j0 + k);
-            const int cx = (int)(__float_as_uint(fmaf(q[0], b.x, fmaf(q[1], b.y, fmaf(q[2], b.z, q[9]))) + 12582912.0f) - kMagicBits);
-            const int cy = (int)(__float_as_uint(fmaf(q[3], b.x, fmaf(q[4], b.y, fmaf(q[5], b.z, q[10]))) + 12582912.0f) - kMagicBits);
-            const int cz = (int)(__float_as_uint(fmaf(q[6], b.x, fmaf(q[7], b.y, fmaf(q[8], b.z, q[11]))) + 12582912.0f) - kMagicBits);
-            if ((unsigned)cx >= (unsigned)g || (unsigned)cy >= (unsigned)g || (unsigned)cz >= (unsigned)g) continue;
-            const float bx = fmaf(r[0], b.x, fmaf(r[1], b.y, fmaf(r[2], b.z, r[9])));
-            const float by = fmaf(r[3], b.x, fmaf(r[4], b.y, fmaf(r[5], b.z, r[10])));
-            const float bz = fmaf(r[6], b.x, fmaf(r[7], b.y, fmaf(r[8], b.z, r[11])));
-            const uint4 rec = __ldg(gr + ((size_t)cz * g + cy) * g + cx);
-            const unsigned count = rec.x & 0xffu;
-            if (count == 255u) {  // crowded cell: all atoms of A
-                for (int i = 0; i < p.n_a; ++i) {
-                    const float4 a = __ldg(at + i);
-                    const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
-                    dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                for (int k = 0; k < jn; ++k) {
+                    const float4 b = __ldg(bt + j0 + k);
+                    const float ux = __saturatef(fmaf(q[0], b.x, fmaf(q[1], b.y, fmaf(q[2], b.z, q[9]))));
+                    const float uy = __saturatef(fmaf(q[3], b.x, fmaf(q[4], b.y, fmaf(q[5], b.z, q[10]))));
+                    const float uz = __saturatef(fmaf(q[6], b.x, fmaf(q[7], b.y, fmaf(q[8], b.z, q[11]))));
+                    // x keeps the bits of 1.5 * 2^23 above its field; y and z are merged in by bitwise select
+                    unsigned cell = __float_as_uint(fmaf(ux, sx, mx));
+                    cell = (cell & ~fy) | (__float_as_uint(fmaf(uy, sy, my)) & fy);
+                    cell = (cell & ~fz) | (__float_as_uint(fmaf(uz, sz, mz)) & fz);
+                    const unsigned word = __ldg(oc + (cell >> 5));
+                    bits = __funnelshift_r(bits, __funnelshift_r(word, 0u, cell), 1);  // bit (cell & 31) of word -> top of bits
                 }
-                continue;
+                bits >>= (32 - jn);
+                // ---- phase 2: distances to the candidate atoms of the flagged atoms only
+                while (bits && !(dmin2 < settle)) {
+                    const int k = __ffs(bits) - 1;
+                    bits &= bits - 1u;
+                    const float4 b = __ldg(bt + j0 + k);
+                    const float ux = __saturatef(fmaf(q[0], b.x, fmaf(q[1], b.y, fmaf(q[2], b.z, q[9]))));
+                    const float uy = __saturatef(fmaf(q[3], b.x, fmaf(q[4], b.y, fmaf(q[5], b.z, q[10]))));
+                    const float uz = __saturatef(fmaf(q[6], b.x, fmaf(q[7], b.y, fmaf(q[8], b.z, q[11]))));
+                    const unsigned cell = (__float_as_uint(fmaf(ux, sx, mx)) & fx) | (__float_as_uint(fmaf(uy, sy, my)) & fy) |
+                                          (__float_as_uint(fmaf(uz, sz, mz)) & fz);
+                    const float bx = fmaf(r[0], b.x, fmaf(r[1], b.y, fmaf(r[2], b.z, r[9])));
+                    const float by = fmaf(r[3], b.x, fmaf(r[4], b.y, fmaf(r[5], b.z, r[10])));
+                    const float bz = fmaf(r[6], b.x, fmaf(r[7], b.y, fmaf(r[8], b.z, r[11])));
+                    const uint4 rec = __ldg(gr + cell);
+                    const unsigned count = rec.x & 0xffu;
+                    if (count == 255u) {  // crowded cell: all atoms of A
+                        for (int i = 0; i < p.n_a; ++i) {
+                            const float4 a = __ldg(at + i);
+                            const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
+                            dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                        }
+                        continue;
+                    }
+                    unsigned long long q0 = (((unsigned long long)rec.y << 32) | rec.x) >> 8;  // indices 0..6
+                    unsigned long long q1 = ((unsigned long long)rec.w << 32) | rec.z;         // indices 7..14
+                    q0 |= q1 << 56;
+                    q1 >>= 8;
+                    for (unsigned c = 0; c < count; ++c) {
+                        const unsigned ai = (unsigned)(q0 & 0xffull);
+                        q0 = (q0 >> 8) | (q1 << 56);
+                        q1 >>= 8;
+                        const float4 a = __ldg(at + ai);
+                        const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
+                        dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                    }
+                }
             }
-            unsigned long long q0 = (((unsigned long long)rec.y << 32) | rec.x) >> 8;  // indices 0..6
-            unsigned long long q1 = ((unsigned long long)rec.w << 32) | rec.z;         // indices 7..14
-            q0 |= q1 << 56;
-            q1 >>= 8;
-            for (unsigned c = 0; c < count; ++c) {
-                const unsigned ai = (unsigned)(q0 & 0xffull);
-                q0 = (q0 >> 8) | (q1 << 56);
-                q1 >>= 8;
-                const float4 a = __ldg(at + ai);
-                const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
-                dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+            if (!p.last && !(dmin2 < settle)) {
+                push = true;  // undecided so far: the next level continues with the remaining atoms
+            } else {
+                uint8_t st;
+                bool uncertain;
+                if (p.count_mode) {
+                    uncertain = !(dmin2 > p.thr2 + band);
+                    st = FC_STATUS_PASS;
+                } else {
+                    uncertain = fabsf(dmin2 - p.thr2) <= band;
+                    st = dmin2 > p.thr2 ? FC_STATUS_PASS : 0;
+                }
+                // the candidate lists only cover thresh + kCellPad: a band that large cannot be trusted to them
+                if (band > kCellPad * sqrtf(p.thr2)) uncertain = true;
+                if (uncertain) {
+                    int slot = atomicAdd(p.unc_count, 1);
+                    UncEntry e;
+                    e.pose = pose;
+                    e.conf_a = conf_a;
+                    e.conf_b = conf_b;
+                    p.unc_list[slot] = e;
+                }
+                if (p.status) p.status[pose] = st;
+                pass = (st & FC_STATUS_PASS) && !uncertain;  // the FP64 recheck sets the bit of an undecided pose
+            }
+        }
+        // survivors of this level, compacted (one atomic per warp)
+        const unsigned pmask = __ballot_sync(0xffffffffu, push);
+        if (pmask) {
+            unsigned first = 0;
+            if (lane == 0) first = atomicAdd(p.out_count, (unsigned)__popc(pmask));
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (push) {
+                CellItem it;
+                it.pose = (unsigned)pose;
+                it.dmin2 = dmin2;
+                p.out_list[first + __popc(pmask & ((1u << lane) - 1u))] = it;
+            }
+        }
+        if (p.bits) {
+            if (!p.in_list) {  // level 0 owns the words: 32 consecutive poses per warp
+                const unsigned word = __ballot_sync(0xffffffffu, pass);
+                if (lane == 0) p.bits[base >> 5] = word;
+            } else if (pass) {
+                atomicOr(p.bits + (pose >> 5), 1u << (pose & 31));
             }
         }
     }
-    uint8_t st;
-    bool uncertain;
-    if (p.count_mode) {
-        uncertain = !(dmin2 > p.thr2 + band);
-        st = FC_STATUS_PASS;
-    } else {
-        uncertain = fabsf(dmin2 - p.thr2) <= band;
-        st = dmin2 > p.thr2 ? FC_STATUS_PASS : 0;
-    }
-    // the candidate lists only cover thresh + kCellPad: a band that large cannot be trusted to them
-    if (band > 2.0f * kCellPad * sqrtf(p.thr2) * 0.5f) uncertain = true;
-    if (uncertain) {
-        int slot = atomicAdd(p.unc_count, 1);
-        UncEntry e;
-        e.pose = pose;
-        e.conf_a = conf_a;
-        e.conf_b = conf_b;
-        p.unc_list[slot] = e;
-    }
-    p.status[pose] = st;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -651,35 +866,43 @@ __global__ void __launch_bounds__(128) clash_cell_kernel(CellArgs p) {
 struct RecheckArgs {
     const double* a_coords;
     const double* b_coords;
-    const double* xf;
+    const void* poses;  // (n_poses, 12) f64 or (n_poses, 7) f32
     int n_a, n_b;
     double thresh;
     int max_clashes;
     int strict;
     const int* unc_count;
     const UncEntry* unc_list;
-    uint8_t* status;
+    uint8_t* status;    // may be null
+    unsigned* bits;     // may be null: survivor bitmask (the FP32 pass left the bit of an undecided pose at 0)
     float* min_dist;
     int* near_count;
     long long* near_idx;
     double* near_dist;
     long long near_cap;
     long long pose_base;
+    int* recheck_total;  // may be null: running number of rechecked poses (host-buffer entry points)
 };
 
+template <int FMT>
 __global__ void __launch_bounds__(256) clash_recheck_f64_kernel(RecheckArgs p) {
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int n_unc = *p.unc_count;
+    if (p.recheck_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.recheck_total, n_unc);
     for (int u = blockIdx.x * warps_per_block + (threadIdx.x >> 5); u < n_unc;
          u += gridDim.x * warps_per_block) {
         UncEntry e = p.unc_list[u];
         const double* a = p.a_coords + (size_t)e.conf_a * p.n_a * 3;
         const double* b = p.b_coords + (size_t)e.conf_b * p.n_b * 3;
-        const double* x = p.xf + e.pose * 12;
         double r[12];
+        if (FMT == kPoseXf64) {
+            const double* x = reinterpret_cast<const double*>(p.poses) + e.pose * 12;
 #pragma unroll
-        for (int k = 0; k < 12; ++k) r[k] = x[k];
+            for (int k = 0; k < 12; ++k) r[k] = x[k];
+        } else {
+            pose7_expand_f64(reinterpret_cast<const float*>(p.poses) + e.pose * 7, r);
+        }
         int clashes = 0;
         double dmin = 1e300, closest = 1e300;
         for (int j = lane; j < p.n_b; j += 32) {
@@ -715,7 +938,8 @@ __global__ void __launch_bounds__(256) clash_recheck_f64_kernel(RecheckArgs p) {
                     }
                 }
             }
-            p.status[e.pose] = st;
+            if (p.status) p.status[e.pose] = st;
+            if (p.bits && (st & FC_STATUS_PASS)) atomicOr(p.bits + (e.pose >> 5), 1u << (e.pose & 31));
             if (p.min_dist) p.min_dist[e.pose] = (float)dmin;
         }
     }
@@ -841,7 +1065,7 @@ extern "C" int fc_clash_prepare_dev(const double* a_coords, int n_conf_a, int n_
     p->thresh = thresh;
     if (want_cells && n_a <= 254 && thresh > 0.0 && thresh < 1e3) {
         const size_t budget = (size_t)512 << 20;
-        for (int g_try : {64, 32}) {  // powers of two: the flag phase range-checks with one mask
+        for (int g_try : {64, 32}) {  // powers of two: the cell number of an axis is a mantissa bit field
             if ((size_t)n_conf_a * g_try * g_try * g_try * 16 <= budget) {
                 p->cell_g = g_try;
                 break;
@@ -856,7 +1080,7 @@ extern "C" int fc_clash_prepare_dev(const double* a_coords, int n_conf_a, int n_
     size_t off_meta = off_axyz + (cell_g ? (size_t)n_conf_a * n_a * 16 : 0);
     size_t off_grid = off_meta + (cell_g ? 64 : 0);
     size_t off_occ = off_grid + (cell_g ? (size_t)n_conf_a * n_cells * 16 : 0);
-    size_t total = off_occ + (cell_g ? (size_t)n_conf_a * (n_cells / 32 + 1) * 4 : 0);
+    size_t total = off_occ + (cell_g ? (size_t)n_conf_a * (n_cells / 32) * 4 : 0);
     cudaError_t e = cudaMallocAsync((void**)&p->buf, total, s);
     if (e != cudaSuccess) {
         delete p;
@@ -889,35 +1113,153 @@ extern "C" int fc_clash_prepare_dev(const double* a_coords, int n_conf_a, int n_
     return FC_OK;
 }
 
+// test hook (host pointers): geometry of the cell grid the screen builds for this ensemble and threshold
+extern "C" int fc_clash_cell_meta(const double* a_coords, int n_conf_a, int n_a, double thresh, float* out8) {
+    FC_REQUIRE(a_coords && out8 && n_conf_a > 0 && n_a > 0, "fc_clash_cell_meta: null pointer");
+    for (int k = 0; k < 8; ++k) out8[k] = 0.f;
+    double* d_a = nullptr;
+    const size_t bytes = (size_t)n_conf_a * n_a * 24;
+    FC_CUDA(cudaMalloc((void**)&d_a, bytes));
+    cudaError_t e = cudaMemcpy(d_a, a_coords, bytes, cudaMemcpyHostToDevice);
+    fc_clash_prep* prep = nullptr;
+    int rc = e == cudaSuccess ? fc_clash_prepare_dev(d_a, n_conf_a, n_a, thresh, 1, &prep, nullptr)
+                              : cuda_fail(e, "cudaMemcpy", __FILE__, __LINE__);
+    if (rc == FC_OK && prep->cell_g) {
+        CellMeta m;
+        e = cudaMemcpy(&m, prep->meta, sizeof(m), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy", __FILE__, __LINE__);
+        out8[0] = m.ox;
+        out8[1] = m.oy;
+        out8[2] = m.oz;
+        out8[3] = m.h;
+        out8[4] = (float)m.g;
+        out8[5] = sqrtf(m.rc2);
+        out8[6] = m.inv_span;
+        out8[7] = (float)m.shift;
+    }
+    if (prep) fc_clash_prep_free(prep, nullptr);
+    cudaDeviceSynchronize();
+    cudaFree(d_a);
+    return rc;
+}
+
 extern "C" void fc_clash_prep_free(fc_clash_prep* p, void* stream) {
     if (!p) return;
     if (p->buf) cudaFreeAsync(p->buf, (cudaStream_t)stream);
     delete p;
 }
 
-extern "C" int fc_clash_screen_prepared_dev(const fc_clash_prep* prep, const double* a_coords, const double* b_coords,
-                                            int n_conf_b, int n_b, const double* xf, int64_t n_poses,
-                                            const int32_t* tiles, int64_t n_tiles, int max_clashes, int strict,
-                                            uint8_t* status, float* min_dist, int32_t* near_count, int64_t* near_idx,
-                                            double* near_dist, int64_t near_cap, int64_t pose_index_base, void* stream) {
-    FC_REQUIRE(prep, "fc_clash_screen_prepared_dev: null preparation");
-    const int n_conf_a = prep->n_conf_a, n_a = prep->n_a;
-    const double thresh = prep->thresh;
-    FC_REQUIRE(n_b > 0 && n_conf_b > 0, "fc_clash_screen_dev: empty fragment");
-    FC_REQUIRE(n_poses >= 0 && max_clashes >= 0, "fc_clash_screen_dev: negative size");
-    if (n_poses == 0) return FC_OK;
-    FC_REQUIRE(a_coords && b_coords && xf && status, "fc_clash_screen_dev: null pointer");
-    cudaStream_t s = (cudaStream_t)stream;
-    const int sms = sm_count();  // also configures the stream-ordered memory pool on first use
+namespace fc {
+
+// B-side tables of a screen: all-pairs layout (padded float4), bounding radii and the farthest-point ordered copy
+// the cell-list levels read
+struct ClashBTabs {
+    unsigned char* buf = nullptr;
+    const float4* b_tab = nullptr;
+    const float* b_rad = nullptr;
+    const float4* b_ord = nullptr;
+    int n_b_pad = 0;
+};
+
+static int clash_prepare_b(const double* b_coords, int n_conf_b, int n_b, ClashBTabs* out, cudaStream_t s) {
     ClashGeom g = choose_geom(n_b);
     FC_REQUIRE(g.tb > 0, "fc_clash_screen_dev: fragment B too large (%d atoms)", n_b);
-    const int n_a_pad = prep->n_a_pad;
-    const int n_b_pad = g.chunks * g.tb;
-    if (!tiles) n_tiles = (n_poses + g.poses - 1) / g.poses;
-    FC_REQUIRE(n_tiles > 0, "fc_clash_screen_dev: empty tile list");
+    out->n_b_pad = g.chunks * g.tb;
+    const size_t off_rb = (size_t)n_conf_b * out->n_b_pad * 16;
+    const size_t off_ord = (off_rb + (size_t)n_conf_b * 4 + 15) / 16 * 16;
+    const size_t total = off_ord + (size_t)n_conf_b * n_b * 16;
+    FC_CUDA(cudaMallocAsync((void**)&out->buf, total, s));
+    clash_prep_kernel<<<n_conf_b, 128, 0, s>>>(b_coords, n_conf_b, n_b, out->n_b_pad, 0, (float4*)out->buf,
+                                               (float*)(out->buf + off_rb));
+    clash_order_b_kernel<<<n_conf_b, 32, (size_t)n_b * 20, s>>>(b_coords, n_b, 64, (float4*)(out->buf + off_ord));
+    out->b_tab = (const float4*)out->buf;
+    out->b_rad = (const float*)(out->buf + off_rb);
+    out->b_ord = (const float4*)(out->buf + off_ord);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cudaFreeAsync(out->buf, s);
+        out->buf = nullptr;
+        return cuda_fail(e, "clash_prepare_b kernels", __FILE__, __LINE__);
+    }
+    return FC_OK;
+}
 
-    size_t smem = (size_t)(n_a_pad + 2) * 16 + (size_t)n_b_pad * 16 + (size_t)2 * g.poses * 96 + 16 + (size_t)g.poses * 4;
-    FC_REQUIRE(smem <= 227 * 1024, "fc_clash_screen_dev: fragments need %zu B of shared memory", smem);
+static void clash_free_b(ClashBTabs* t, cudaStream_t s) {
+    if (t->buf) cudaFreeAsync(t->buf, s);
+    t->buf = nullptr;
+}
+
+__global__ void pose7_expand_kernel(const float* __restrict__ pose7, long long n, double* __restrict__ xf) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r[12];
+    pose7_expand_f64(pose7 + i * 7, r);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) xf[i * 12 + k] = r[k];
+}
+
+struct ScreenIO {
+    const void* poses = nullptr;
+    int fmt = kPoseXf64;
+    int64_t n_poses = 0;
+    const int32_t* tiles = nullptr;
+    int64_t n_tiles = 0;
+    int max_clashes = 0, strict = 1;
+    uint8_t* status = nullptr;
+    uint32_t* bits = nullptr;
+    float* min_dist = nullptr;
+    int32_t* near_count = nullptr;
+    int64_t* near_idx = nullptr;
+    double* near_dist = nullptr;
+    int64_t near_cap = 0;
+    int64_t pose_index_base = 0;
+    int32_t* recheck_total = nullptr;
+};
+
+template <int FMT>
+static int cell_grid_blocks(int sms) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, clash_cell_kernel<FMT>, 128, 0) != cudaSuccess || n <= 0) n = 4;
+        per_sm = n;
+    }
+    return sms * per_sm;
+}
+
+// level boundaries over the (re-ordered) atoms of B: FC_CLASH_LEVELS="32,64" overrides
+static int cell_levels(int n_b, int* bounds /* [<= 8] */) {
+    int n = 0;
+    bounds[n++] = 0;
+    const char* v = getenv("FC_CLASH_LEVELS");
+    if (v && *v) {
+        while (*v && n < 6) {
+            int b = atoi(v);
+            if (b > bounds[n - 1] && b < n_b) bounds[n++] = b;
+            while (*v && *v != ',') ++v;
+            if (*v == ',') ++v;
+        }
+    } else {
+        if (n_b > 48) bounds[n++] = 32;
+        if (n_b > 96) bounds[n++] = 64;
+    }
+    bounds[n] = n_b;
+    return n;  // number of levels
+}
+
+static int clash_screen_core(const fc_clash_prep* prep, const double* a_coords, const double* b_coords, int n_conf_b,
+                             int n_b, const ClashBTabs& bt, const ScreenIO& io, cudaStream_t s) {
+    const int n_a = prep->n_a;
+    const double thresh = prep->thresh;
+    const int64_t n_poses = io.n_poses;
+    if (n_poses == 0) return FC_OK;
+    const int sms = sm_count();  // also configures the stream-ordered memory pool on first use
+    ClashGeom g = choose_geom(n_b);
+    const int n_a_pad = prep->n_a_pad;
+    const int n_b_pad = bt.n_b_pad;
+    int64_t n_tiles = io.n_tiles;
+    if (!io.tiles) n_tiles = (n_poses + g.poses - 1) / g.poses;
+    FC_REQUIRE(n_tiles > 0, "fc_clash_screen_dev: empty tile list");
 
     // ---- path: all atom pairs (Gram-form FP32 kernel) or cell lists over fragment A -----------------
     int cell_g = 0;
@@ -925,127 +1267,227 @@ extern "C" int fc_clash_screen_prepared_dev(const fc_clash_prep* prep, const dou
         // FC_CLASH_MODE: 0 = all pairs, 1 = cell lists whenever possible, unset = automatic
         const char* v = getenv("FC_CLASH_MODE");
         const int mode = (v && *v) ? (atoi(v) ? 1 : 0) : 2;
-        const bool possible = !min_dist && prep->cell_g > 0;
+        const bool possible = !io.min_dist && prep->cell_g > 0 && n_poses < ((int64_t)1 << 31);
         const bool wanted = mode == 1 || (mode == 2 && n_poses >= 16384);
         if (possible && wanted) cell_g = prep->cell_g;
     }
 
-    // stream-ordered scratch: B tables, undecided-pose list
-    size_t b_bytes = (size_t)n_conf_b * n_b_pad * 16;
-    size_t off_b = 0, off_rb = off_b + b_bytes, off_cnt = (off_rb + (size_t)n_conf_b * 4 + 15) / 16 * 16;
-    size_t off_list = off_cnt + 16;
-    size_t total = off_list + (size_t)n_poses * sizeof(UncEntry);
+    // stream-ordered scratch: undecided-pose list, counters, (cell path) the two item lists of the levels,
+    // (all-pairs path) expanded transforms of compact poses and status bytes when only the bitmask is wanted
+    const size_t off_cnt = 0;
+    const size_t off_unc = 64;
+    size_t off_l0 = off_unc + (size_t)n_poses * sizeof(UncEntry);
+    size_t off_l1 = off_l0, off_xf = off_l0, off_st = off_l0, total = off_l0;
+    const bool need_xf = !cell_g && io.fmt == kPoseQ7;
+    const bool need_st = !cell_g && !io.status;
+    if (cell_g) {
+        off_l1 = off_l0 + (size_t)n_poses * sizeof(CellItem);
+        total = off_l1 + (size_t)n_poses * sizeof(CellItem);
+    } else {
+        off_st = off_xf + (need_xf ? (size_t)n_poses * 96 : 0);
+        total = off_st + (need_st ? ((size_t)n_poses + 15) / 16 * 16 : 0);
+    }
     unsigned char* scratch = nullptr;
     FC_CUDA(cudaMallocAsync((void**)&scratch, total, s));
-
-    clash_prep_kernel<<<n_conf_b, 128, 0, s>>>(b_coords, n_conf_b, n_b, n_b_pad, 0,
-                                               (float4*)(scratch + off_b), (float*)(scratch + off_rb));
-    FC_CUDA(cudaMemsetAsync(scratch + off_cnt, 0, 16, s));
-
-    ClashArgs a;
-    a.a_tab = prep->a_tab;
-    a.a_rad = prep->a_rad;
-    a.b_tab = (const float4*)(scratch + off_b);
-    a.b_rad = (const float*)(scratch + off_rb);
-    a.xf = xf;
-    a.tiles = (const int4*)tiles;
-    a.n_tiles = n_tiles;
-    a.n_poses = n_poses;
-    a.n_a_pad = n_a_pad;
-    a.n_b_pad = n_b_pad;
-    a.chunks = g.chunks;
-    a.poses = g.poses;
-    a.thr2 = (float)(thresh * thresh);
-    a.count_mode = max_clashes > 0;
-    {
-        const char* v = getenv("FC_CLASH_TMA");
-        a.use_tma = ((reinterpret_cast<uintptr_t>(xf) & 15) == 0) && !(v && atoi(v) == 0);
-    }
-    a.status = status;
-    a.min_dist = min_dist;
-    a.unc_count = (int*)(scratch + off_cnt);
-    a.unc_list = (UncEntry*)(scratch + off_list);
+    FC_CUDA(cudaMemsetAsync(scratch + off_cnt, 0, 64, s));
+    int* unc_count = (int*)(scratch + off_cnt);
+    UncEntry* unc_list = (UncEntry*)(scratch + off_unc);
+    uint8_t* status = io.status ? io.status : (need_st ? scratch + off_st : nullptr);
+    const void* poses_f64 = io.poses;  // what the FP64 recheck reads (format io.fmt unless expanded below)
+    int recheck_fmt = io.fmt;
+    cudaError_t e = cudaSuccess;
 
     if (cell_g) {
         CellArgs c;
         c.a_xyz = prep->a_xyz;
-        c.a_rad = a.a_rad;
-        c.b_tab = a.b_tab;
-        c.b_rad = a.b_rad;
+        c.a_rad = prep->a_rad;
+        c.b_ord = bt.b_ord;
+        c.b_rad = bt.b_rad;
         c.grid = prep->grid;
         c.occ = prep->occ;
         c.meta = prep->meta;
-        c.xf = xf;
-        c.tiles = (const int4*)tiles;
+        c.poses = io.poses;
+        c.tiles = (const int4*)io.tiles;
         c.n_tiles = n_tiles;
         c.n_poses = n_poses;
         c.n_a = n_a;
         c.n_b = n_b;
-        c.n_b_pad = n_b_pad;
-        c.tile_poses = g.poses;
-        c.thr2 = a.thr2;
-        c.count_mode = a.count_mode;
+        c.thr2 = (float)(thresh * thresh);
+        c.count_mode = io.max_clashes > 0;
         c.status = status;
-        c.unc_count = a.unc_count;
-        c.unc_list = a.unc_list;
+        c.bits = io.bits;
+        c.unc_count = unc_count;
+        c.unc_list = unc_list;
+        int bounds[8];
+        const int n_levels = cell_levels(n_b, bounds);
+        CellItem* lists[2] = {(CellItem*)(scratch + off_l0), (CellItem*)(scratch + off_l1)};
+        unsigned* counters = (unsigned*)(scratch + off_cnt) + 4;  // one per level, zeroed above
+        const int full_grid = io.fmt == kPoseQ7 ? cell_grid_blocks<kPoseQ7>(sms) : cell_grid_blocks<kPoseXf64>(sms);
         timing_begin(s);
-        clash_cell_kernel<<<(unsigned)((n_poses + 127) / 128), 128, 0, s>>>(c);
+        for (int lv = 0; lv < n_levels; ++lv) {
+            c.j_lo = bounds[lv];
+            c.j_hi = bounds[lv + 1];
+            c.last = lv == n_levels - 1;
+            c.in_list = lv ? lists[(lv - 1) & 1] : nullptr;
+            c.in_count = lv ? counters + (lv - 1) : nullptr;
+            c.out_list = lists[lv & 1];
+            c.out_count = counters + lv;
+            int grid = full_grid;
+            if (lv == 0) grid = (int)std::min<long long>(grid, (n_poses + 127) / 128);
+            if (io.fmt == kPoseQ7) clash_cell_kernel<kPoseQ7><<<grid, 128, 0, s>>>(c);
+            else clash_cell_kernel<kPoseXf64><<<grid, 128, 0, s>>>(c);
+        }
         timing_end(s);
-    }
-
-    // persistent grid: resident CTAs per SM follow from the register/thread budget
-    int ctas_per_sm = tb_max_threads(g.tb) / g.threads;
-    if (ctas_per_sm > 8) ctas_per_sm = 8;
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    long long grid_ll = (long long)sms * ctas_per_sm;
-    if (grid_ll > n_tiles) grid_ll = n_tiles;
-    int grid = (int)grid_ll;
-    cudaError_t e;
-    if (cell_g) {
         e = cudaGetLastError();
-    } else
-    switch (g.tb) {
-        case 2: e = launch_f32<2>(a, g.threads, smem, grid, s); break;
-        case 4: e = launch_f32<4>(a, g.threads, smem, grid, s); break;
-        case 6: e = launch_f32<6>(a, g.threads, smem, grid, s); break;
-        case 8: e = launch_f32<8>(a, g.threads, smem, grid, s); break;
-        case 10: e = launch_f32<10>(a, g.threads, smem, grid, s); break;
-        case 12: e = launch_f32<12>(a, g.threads, smem, grid, s); break;
-        case 15: e = launch_f32<15>(a, g.threads, smem, grid, s); break;
-        case 16: e = launch_f32<16>(a, g.threads, smem, grid, s); break;
-        case 20: e = launch_f32<20>(a, g.threads, smem, grid, s); break;
-        case 25: e = launch_f32<25>(a, g.threads, smem, grid, s); break;
-        default: e = launch_f32<30>(a, g.threads, smem, grid, s); break;
+    } else {
+        if (need_xf) {
+            pose7_expand_kernel<<<(unsigned)((n_poses + 255) / 256), 256, 0, s>>>((const float*)io.poses, n_poses,
+                                                                                 (double*)(scratch + off_xf));
+            poses_f64 = scratch + off_xf;
+            recheck_fmt = kPoseXf64;
+        }
+        size_t smem = (size_t)(n_a_pad + 2) * 16 + (size_t)n_b_pad * 16 + (size_t)2 * g.poses * 96 + 16 + (size_t)g.poses * 4;
+        if (smem > 227 * 1024) {
+            cudaFreeAsync(scratch, s);
+            FC_REQUIRE(false, "fc_clash_screen_dev: fragments need %zu B of shared memory", smem);
+        }
+        ClashArgs a;
+        a.a_tab = prep->a_tab;
+        a.a_rad = prep->a_rad;
+        a.b_tab = bt.b_tab;
+        a.b_rad = bt.b_rad;
+        a.xf = (const double*)poses_f64;
+        a.tiles = (const int4*)io.tiles;
+        a.n_tiles = n_tiles;
+        a.n_poses = n_poses;
+        a.n_a_pad = n_a_pad;
+        a.n_b_pad = n_b_pad;
+        a.chunks = g.chunks;
+        a.poses = g.poses;
+        a.thr2 = (float)(thresh * thresh);
+        a.count_mode = io.max_clashes > 0;
+        {
+            const char* v = getenv("FC_CLASH_TMA");
+            a.use_tma = ((reinterpret_cast<uintptr_t>(a.xf) & 15) == 0) && !(v && atoi(v) == 0);
+        }
+        a.status = status;
+        a.min_dist = io.min_dist;
+        a.unc_count = unc_count;
+        a.unc_list = unc_list;
+        // persistent grid: resident CTAs per SM follow from the register/thread budget
+        int ctas_per_sm = tb_max_threads(g.tb) / g.threads;
+        if (ctas_per_sm > 8) ctas_per_sm = 8;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        long long grid_ll = (long long)sms * ctas_per_sm;
+        if (grid_ll > n_tiles) grid_ll = n_tiles;
+        int grid = (int)grid_ll;
+        switch (g.tb) {
+            case 2: e = launch_f32<2>(a, g.threads, smem, grid, s); break;
+            case 4: e = launch_f32<4>(a, g.threads, smem, grid, s); break;
+            case 6: e = launch_f32<6>(a, g.threads, smem, grid, s); break;
+            case 8: e = launch_f32<8>(a, g.threads, smem, grid, s); break;
+            case 10: e = launch_f32<10>(a, g.threads, smem, grid, s); break;
+            case 12: e = launch_f32<12>(a, g.threads, smem, grid, s); break;
+            case 15: e = launch_f32<15>(a, g.threads, smem, grid, s); break;
+            case 16: e = launch_f32<16>(a, g.threads, smem, grid, s); break;
+            case 20: e = launch_f32<20>(a, g.threads, smem, grid, s); break;
+            case 25: e = launch_f32<25>(a, g.threads, smem, grid, s); break;
+            default: e = launch_f32<30>(a, g.threads, smem, grid, s); break;
+        }
     }
     if (e != cudaSuccess) {
         cudaFreeAsync(scratch, s);
-        return cuda_fail(e, "clash_f32_kernel launch", __FILE__, __LINE__);
+        return cuda_fail(e, "clash screen kernel launch", __FILE__, __LINE__);
     }
 
     RecheckArgs r;
     r.a_coords = a_coords;
     r.b_coords = b_coords;
-    r.xf = xf;
+    r.poses = poses_f64;
     r.n_a = n_a;
     r.n_b = n_b;
     r.thresh = thresh;
-    r.max_clashes = max_clashes;
-    r.strict = strict;
-    r.unc_count = a.unc_count;
-    r.unc_list = a.unc_list;
+    r.max_clashes = io.max_clashes;
+    r.strict = io.strict;
+    r.unc_count = unc_count;
+    r.unc_list = unc_list;
     r.status = status;
-    r.min_dist = min_dist;
-    r.near_count = near_count;
-    r.near_idx = (long long*)near_idx;
-    r.near_dist = near_dist;
-    r.near_cap = near_cap;
-    r.pose_base = pose_index_base;
-    clash_recheck_f64_kernel<<<sms * 2, 256, 0, s>>>(r);
+    r.bits = cell_g ? io.bits : nullptr;  // the all-pairs path packs the final status bytes below
+    r.min_dist = io.min_dist;
+    r.near_count = io.near_count;
+    r.near_idx = (long long*)io.near_idx;
+    r.near_dist = io.near_dist;
+    r.near_cap = io.near_cap;
+    r.pose_base = io.pose_index_base;
+    r.recheck_total = io.recheck_total;
+    if (recheck_fmt == kPoseQ7) clash_recheck_f64_kernel<kPoseQ7><<<sms * 2, 256, 0, s>>>(r);
+    else clash_recheck_f64_kernel<kPoseXf64><<<sms * 2, 256, 0, s>>>(r);
     e = cudaGetLastError();
+    int rc = FC_OK;
+    if (e == cudaSuccess && !cell_g && io.bits) rc = fc_pack_mask_dev(status, n_poses, io.bits, (void*)s);
     cudaError_t e2 = cudaFreeAsync(scratch, s);
     if (e != cudaSuccess) return cuda_fail(e, "clash_recheck_f64_kernel launch", __FILE__, __LINE__);
+    if (rc != FC_OK) return rc;
     if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFreeAsync", __FILE__, __LINE__);
     return FC_OK;
+}
+
+}  // namespace fc
+
+extern "C" int fc_clash_screen_ex_dev(const fc_clash_prep* prep, const double* a_coords, const double* b_coords,
+                                      int n_conf_b, int n_b, const void* poses, int pose_format, int64_t n_poses,
+                                      const int32_t* tiles, int64_t n_tiles, int max_clashes, int strict,
+                                      uint8_t* status, uint32_t* bits, float* min_dist, int32_t* near_count,
+                                      int64_t* near_idx, double* near_dist, int64_t near_cap, int64_t pose_index_base,
+                                      int32_t* recheck_count, void* stream) {
+    FC_REQUIRE(prep, "fc_clash_screen_ex_dev: null preparation");
+    FC_REQUIRE(n_b > 0 && n_conf_b > 0, "fc_clash_screen_dev: empty fragment");
+    FC_REQUIRE(n_poses >= 0 && max_clashes >= 0, "fc_clash_screen_dev: negative size");
+    FC_REQUIRE(pose_format == FC_POSE_XF64 || pose_format == FC_POSE_Q7, "fc_clash_screen_ex_dev: unknown pose format %d",
+               pose_format);
+    if (n_poses == 0) return FC_OK;
+    FC_REQUIRE(a_coords && b_coords && poses && (status || bits), "fc_clash_screen_dev: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    ClashBTabs bt;
+    int rc = clash_prepare_b(b_coords, n_conf_b, n_b, &bt, s);
+    if (rc) return rc;
+    ScreenIO io;
+    io.poses = poses;
+    io.fmt = pose_format == FC_POSE_Q7 ? kPoseQ7 : kPoseXf64;
+    io.n_poses = n_poses;
+    io.tiles = tiles;
+    io.n_tiles = n_tiles;
+    io.max_clashes = max_clashes;
+    io.strict = strict;
+    io.status = status;
+    io.bits = bits;
+    io.min_dist = min_dist;
+    io.near_count = near_count;
+    io.near_idx = near_idx;
+    io.near_dist = near_dist;
+    io.near_cap = near_cap;
+    io.pose_index_base = pose_index_base;
+    io.recheck_total = recheck_count;
+    rc = clash_screen_core(prep, a_coords, b_coords, n_conf_b, n_b, bt, io, s);
+    clash_free_b(&bt, s);
+    return rc;
+}
+
+extern "C" int fc_clash_screen_prepared_dev(const fc_clash_prep* prep, const double* a_coords, const double* b_coords,
+                                            int n_conf_b, int n_b, const double* xf, int64_t n_poses,
+                                            const int32_t* tiles, int64_t n_tiles, int max_clashes, int strict,
+                                            uint8_t* status, float* min_dist, int32_t* near_count, int64_t* near_idx,
+                                            double* near_dist, int64_t near_cap, int64_t pose_index_base, void* stream) {
+    FC_REQUIRE(n_poses <= 0 || status, "fc_clash_screen_dev: null pointer");
+    return fc_clash_screen_ex_dev(prep, a_coords, b_coords, n_conf_b, n_b, xf, FC_POSE_XF64, n_poses, tiles, n_tiles,
+                                  max_clashes, strict, status, nullptr, min_dist, near_count, near_idx, near_dist, near_cap,
+                                  pose_index_base, nullptr, stream);
+}
+
+static int clash_want_cells(int64_t n_poses, const float* min_dist) {
+    const char* v = getenv("FC_CLASH_MODE");
+    const int mode = (v && *v) ? (atoi(v) ? 1 : 0) : 2;
+    return !min_dist && (mode == 1 || (mode == 2 && n_poses >= 16384));
 }
 
 extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a,
@@ -1060,14 +1502,169 @@ extern "C" int fc_clash_screen_dev(const double* a_coords, int n_conf_a, int n_a
     if (n_poses == 0) return FC_OK;
     FC_REQUIRE(a_coords && b_coords && xf && status, "fc_clash_screen_dev: null pointer");
     fc_clash_prep* prep = nullptr;
-    const char* v = getenv("FC_CLASH_MODE");
-    const int mode = (v && *v) ? (atoi(v) ? 1 : 0) : 2;
-    const int want_cells = !min_dist && (mode == 1 || (mode == 2 && n_poses >= 16384));
-    int rc = fc_clash_prepare_dev(a_coords, n_conf_a, n_a, thresh, want_cells, &prep, stream);
+    int rc = fc_clash_prepare_dev(a_coords, n_conf_a, n_a, thresh, clash_want_cells(n_poses, min_dist), &prep, stream);
     if (rc) return rc;
     rc = fc_clash_screen_prepared_dev(prep, a_coords, b_coords, n_conf_b, n_b, xf, n_poses, tiles, n_tiles, max_clashes,
                                       strict, status, min_dist, near_count, near_idx, near_dist, near_cap,
                                       pose_index_base, stream);
     fc_clash_prep_free(prep, stream);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer screen of compact poses: chunked, double-buffered H2D(pose7) -> screen -> D2H(bitmask)
+// ------------------------------------------------------------------------------------------------
+extern "C" int fc_clash_batch_pose7(const double* a_coords, int n_conf_a, int n_a, const double* b_coords, int n_conf_b,
+                                    int n_b, const float* pose7, int64_t n_poses, const int32_t* tiles, int64_t n_tiles,
+                                    double thresh, int max_clashes, int strict, uint32_t* bits_out, uint8_t* status_out,
+                                    int64_t* counts, int64_t* near_idx, double* near_dist, int64_t near_cap) {
+    FC_REQUIRE(n_a > 0 && n_b > 0 && n_conf_a > 0 && n_conf_b > 0, "fc_clash_batch_pose7: empty fragment");
+    FC_REQUIRE(n_poses >= 0 && max_clashes >= 0, "fc_clash_batch_pose7: negative size");
+    if (counts) counts[0] = counts[1] = counts[2] = 0;
+    if (n_poses == 0) return FC_OK;
+    FC_REQUIRE(a_coords && b_coords && pose7 && bits_out, "fc_clash_batch_pose7: null pointer");
+    const int tile_poses = fc_clash_tile_poses(n_b);
+    FC_REQUIRE(tile_poses > 0, "fc_clash_batch_pose7: fragment B too large (%d atoms)", n_b);
+    if (tiles) {
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            const int32_t* q = tiles + 4 * t;
+            FC_REQUIRE(q[0] >= 0 && q[0] < n_conf_a && q[1] >= 0 && q[1] < n_conf_b && q[3] >= 0 && q[3] <= tile_poses &&
+                           q[2] >= 0 && (int64_t)q[2] + q[3] <= n_poses,
+                       "fc_clash_batch_pose7: tile %lld out of range", (long long)t);
+        }
+    }
+    const int64_t n_words = (n_poses + 31) / 32;
+    // grow-only pinned staging for what comes back (per host thread): bitmask words, then status bytes
+    static thread_local unsigned char* h_stage = nullptr;
+    static thread_local size_t h_stage_cap = 0;
+    const size_t stage_need = (size_t)n_words * 4 + (status_out ? (size_t)n_poses : 0);
+    if (h_stage_cap < stage_need) {
+        if (h_stage) cudaFreeHost(h_stage);
+        h_stage = nullptr;
+        h_stage_cap = 0;
+        size_t want = std::max<size_t>(stage_need, (size_t)1 << 20);
+        cudaError_t he = cudaHostAlloc((void**)&h_stage, want, cudaHostAllocDefault);
+        if (he != cudaSuccess) return cuda_fail(he, "cudaHostAlloc(result staging)", __FILE__, __LINE__);
+        h_stage_cap = want;
+    }
+    uint32_t* h_bits = (uint32_t*)h_stage;
+    uint8_t* h_status = status_out ? h_stage + (size_t)n_words * 4 : nullptr;
+
+    const int kBuf = 2;
+    cudaStream_t st[kBuf] = {nullptr, nullptr};
+    cudaEvent_t ev_setup = nullptr;
+    float* d_pose[kBuf] = {nullptr, nullptr};
+    uint32_t* d_bits = nullptr;
+    uint8_t* d_status = nullptr;
+    double *d_a = nullptr, *d_b = nullptr, *d_near_dist = nullptr;
+    int32_t *d_tiles = nullptr, *d_cnt = nullptr;
+    int64_t* d_near_idx = nullptr;
+    fc_clash_prep* prep = nullptr;
+    ClashBTabs bt;
+    int rc = FC_OK;
+    // with an explicit tile list the whole batch is one chunk (tiles index absolute poses); chunks are multiples of
+    // 32 poses so that every chunk owns whole bitmask words (FC_CLASH_CHUNK overrides the 1 M default)
+    int64_t chunk_env = 0;
+    if (const char* v = getenv("FC_CLASH_CHUNK")) chunk_env = atoll(v);
+    int64_t chunk = tiles ? n_poses : std::min<int64_t>(n_poses, chunk_env > 0 ? chunk_env : (int64_t)1 << 20);
+    chunk = (chunk + 31) / 32 * 32;
+
+#define FC_TRY(call)                                                 \
+    do {                                                             \
+        cudaError_t _e = (call);                                     \
+        if (_e != cudaSuccess) {                                     \
+            rc = cuda_fail(_e, #call, __FILE__, __LINE__);           \
+            goto done;                                               \
+        }                                                            \
+    } while (0)
+
+    sm_count();  // configures the memory pool on first use
+    for (int i = 0; i < kBuf; ++i) FC_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    FC_TRY(cudaEventCreateWithFlags(&ev_setup, cudaEventDisableTiming));
+    FC_TRY(cudaMallocAsync((void**)&d_a, (size_t)n_conf_a * n_a * 24, st[0]));
+    FC_TRY(cudaMallocAsync((void**)&d_b, (size_t)n_conf_b * n_b * 24, st[0]));
+    FC_TRY(cudaMallocAsync((void**)&d_bits, (size_t)n_words * 4, st[0]));
+    if (status_out) FC_TRY(cudaMallocAsync((void**)&d_status, (size_t)n_poses, st[0]));
+    FC_TRY(cudaMallocAsync((void**)&d_cnt, 16, st[0]));
+    if (near_cap > 0) {
+        FC_TRY(cudaMallocAsync((void**)&d_near_idx, (size_t)near_cap * 8, st[0]));
+        FC_TRY(cudaMallocAsync((void**)&d_near_dist, (size_t)near_cap * 8, st[0]));
+    }
+    for (int i = 0; i < kBuf; ++i) FC_TRY(cudaMallocAsync((void**)&d_pose[i], (size_t)chunk * 28, st[0]));
+    FC_TRY(cudaMemcpyAsync(d_a, a_coords, (size_t)n_conf_a * n_a * 24, cudaMemcpyHostToDevice, st[0]));
+    FC_TRY(cudaMemcpyAsync(d_b, b_coords, (size_t)n_conf_b * n_b * 24, cudaMemcpyHostToDevice, st[0]));
+    FC_TRY(cudaMemsetAsync(d_cnt, 0, 16, st[0]));
+    if (tiles) {
+        FC_TRY(cudaMallocAsync((void**)&d_tiles, (size_t)n_tiles * 16, st[0]));
+        FC_TRY(cudaMemcpyAsync(d_tiles, tiles, (size_t)n_tiles * 16, cudaMemcpyHostToDevice, st[0]));
+    }
+    // both fragments' tables once for the whole batch
+    rc = fc_clash_prepare_dev(d_a, n_conf_a, n_a, thresh, clash_want_cells(n_poses, nullptr), &prep, (void*)st[0]);
+    if (rc) goto done;
+    rc = clash_prepare_b(d_b, n_conf_b, n_b, &bt, st[0]);
+    if (rc) goto done;
+    FC_TRY(cudaEventRecord(ev_setup, st[0]));
+    for (int i = 1; i < kBuf; ++i) FC_TRY(cudaStreamWaitEvent(st[i], ev_setup, 0));
+    {
+        int b = 0;
+        for (int64_t first = 0; first < n_poses; first += chunk, b = (b + 1) % kBuf) {
+            const int64_t n = std::min<int64_t>(chunk, n_poses - first);
+            const int64_t w0 = first / 32, nw = (n + 31) / 32;
+            cudaStream_t s = st[b];
+            FC_TRY(cudaMemcpyAsync(d_pose[b], pose7 + first * 7, (size_t)n * 28, cudaMemcpyHostToDevice, s));
+            ScreenIO io;
+            io.poses = d_pose[b];
+            io.fmt = kPoseQ7;
+            io.n_poses = n;
+            io.tiles = d_tiles;
+            io.n_tiles = n_tiles;
+            io.max_clashes = max_clashes;
+            io.strict = strict;
+            io.status = d_status ? d_status + first : nullptr;
+            io.bits = d_bits + w0;
+            io.near_count = d_cnt;
+            io.near_idx = d_near_idx;
+            io.near_dist = d_near_dist;
+            io.near_cap = near_cap;
+            io.pose_index_base = first;
+            io.recheck_total = d_cnt + 1;
+            rc = clash_screen_core(prep, d_a, d_b, n_conf_b, n_b, bt, io, s);
+            if (rc != FC_OK) goto done;
+            FC_TRY(cudaMemcpyAsync(h_bits + w0, d_bits + w0, (size_t)nw * 4, cudaMemcpyDeviceToHost, s));
+            if (d_status) FC_TRY(cudaMemcpyAsync(h_status + first, d_status + first, (size_t)n, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    for (int i = 0; i < kBuf; ++i) FC_TRY(cudaStreamSynchronize(st[i]));
+    {
+        int64_t n_pass = 0;
+        for (int64_t w = 0; w < n_words; ++w) n_pass += __builtin_popcount(h_bits[w]);
+        memcpy(bits_out, h_bits, (size_t)n_words * 4);
+        if (status_out) memcpy(status_out, h_status, (size_t)n_poses);
+        int32_t cnt[4] = {0, 0, 0, 0};
+        FC_TRY(cudaMemcpy(cnt, d_cnt, 16, cudaMemcpyDeviceToHost));
+        const int64_t n_copy = std::min<int64_t>(cnt[0], near_cap);
+        if (n_copy > 0 && near_idx) FC_TRY(cudaMemcpy(near_idx, d_near_idx, (size_t)n_copy * 8, cudaMemcpyDeviceToHost));
+        if (n_copy > 0 && near_dist) FC_TRY(cudaMemcpy(near_dist, d_near_dist, (size_t)n_copy * 8, cudaMemcpyDeviceToHost));
+        if (counts) {
+            counts[0] = n_pass;
+            counts[1] = cnt[1];
+            counts[2] = cnt[0];
+        }
+    }
+done:
+    if (st[0]) {
+        for (int i = 0; i < kBuf; ++i)
+            if (st[i]) cudaStreamSynchronize(st[i]);
+        clash_free_b(&bt, st[0]);
+        fc_clash_prep_free(prep, (void*)st[0]);
+        void* bufs[] = {d_pose[0], d_pose[1], d_a, d_b, d_bits, d_status, d_tiles, d_cnt, d_near_idx, d_near_dist};
+        for (void* q : bufs)
+            if (q) cudaFreeAsync(q, st[0]);
+        cudaStreamSynchronize(st[0]);
+    }
+    for (int i = 0; i < kBuf; ++i)
+        if (st[i]) cudaStreamDestroy(st[i]);
+    if (ev_setup) cudaEventDestroy(ev_setup);
+    return rc;
+#undef FC_TRY
 }

@@ -177,3 +177,60 @@ extern "C" int fc_xyz_format(const char* symbols, int32_t sym_stride, const doub
     }
     return FC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// page-locked host memory on the GPU's NUMA node
+// ------------------------------------------------------------------------------------------------
+#include <sys/syscall.h>
+#include <unistd.h>
+
+namespace fc {
+
+// NUMA node of the current device from sysfs (-1: unknown / single node)
+static int device_numa_node() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), dev) != cudaSuccess) return -1;
+    for (char* c = bus; *c; ++c)
+        if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+}  // namespace fc
+
+extern "C" void* fc_host_alloc(int64_t bytes, int32_t* node_out) {
+    if (node_out) *node_out = -1;
+    if (bytes <= 0) return nullptr;
+    const int node = fc::device_numa_node();
+    bool bound = false;
+#ifdef SYS_set_mempolicy
+    if (node >= 0 && node < 64) {  // MPOL_PREFERRED = 1: pages of this thread's next allocations come from `node`
+        unsigned long mask = 1ul << node;
+        bound = syscall(SYS_set_mempolicy, 1, &mask, 65ul) == 0;
+    }
+#endif
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable);
+    if (e == cudaSuccess && p) memset(p, 0, (size_t)bytes);  // first touch while the policy is in force
+#ifdef SYS_set_mempolicy
+    if (bound) syscall(SYS_set_mempolicy, 0, nullptr, 0ul);  // MPOL_DEFAULT
+#endif
+    if (e != cudaSuccess) {
+        fc::cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__);
+        return nullptr;
+    }
+    if (node_out) *node_out = bound ? node : -1;
+    return p;
+}
+
+extern "C" void fc_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}

@@ -82,6 +82,47 @@ int fc_clash_screen_prepared_dev(const fc_clash_prep* prep, const double* a_coor
                                  uint8_t* status, float* min_dist, int32_t* near_count, int64_t* near_idx,
                                  double* near_dist, int64_t near_cap, int64_t pose_index_base, void* stream);
 void fc_clash_prep_free(fc_clash_prep* prep, void* stream);
+/* Test hook (host pointers): out8 = {x, y, z of the centre of cell (0,0,0), cell edge h, cells per axis, candidate
+ * radius, 1 / ((g-1) h), log2 g} of the cell grid the screen builds for this ensemble and threshold (zeros when
+ * it builds none); tests place atoms on cell faces with it. */
+int fc_clash_cell_meta(const double* a_coords, int n_conf_a, int n_a, double thresh, float* out8);
+
+/* General device entry of the screen: poses in either format, status bytes and / or the survivor bitmask.
+ *  pose_format FC_POSE_XF64: poses = (n_poses, 12) f64 as above.
+ *  pose_format FC_POSE_Q7  : poses = (n_poses, 7) f32 {qx, qy, qz, qw, tx, ty, tz}: any non-zero quaternion and
+ *            a translation, 28 bytes per pose instead of 96.  The pose it stands for is DEFINED as the FP64 expansion
+ *            (every operation rounded on its own, in this order; x, y, z, w, t converted to f64 first)
+ *                n = ((x*x + y*y) + z*z) + w*w;   s = 2 / n
+ *                R = [[1 - s*(y*y + z*z), s*(x*y - z*w),     s*(x*z + y*w)    ],
+ *                     [s*(x*y + z*w),     1 - s*(x*x + z*z), s*(y*z - x*w)    ],
+ *                     [s*(x*z - y*w),     s*(y*z + x*w),     1 - s*(x*x + y*y)]],   t = (tx, ty, tz)
+ *            which is what the FP64 recheck evaluates and what a CPU oracle must expand before it applies the
+ *            reference arithmetic (oracle/port.py:pose7_to_xf).
+ *  status    (n_poses) u8 or NULL;  bits (ceil(n_poses / 32)) u32 or NULL (at least one of the two): bit (i & 31) of
+ *            word i >> 5 = pose i passes -- written by the screen itself (warp ballot), the buffer the ranks exchange.
+ *  recheck_count (1) i32 device or NULL: incremented by the number of poses the FP64 recheck decided.
+ * Everything else as fc_clash_screen_prepared_dev. */
+#define FC_POSE_XF64 0
+#define FC_POSE_Q7 1
+int fc_clash_screen_ex_dev(const fc_clash_prep* prep, const double* a_coords, const double* b_coords, int n_conf_b,
+                           int n_b, const void* poses, int pose_format, int64_t n_poses, const int32_t* tiles,
+                           int64_t n_tiles, int max_clashes, int strict, uint8_t* status, uint32_t* bits,
+                           float* min_dist, int32_t* near_count, int64_t* near_idx, double* near_dist, int64_t near_cap,
+                           int64_t pose_index_base, int32_t* recheck_count, void* stream);
+
+/* Host-pointer entry for compact poses (FC_POSE_Q7): 28 bytes per pose go to the device and one BIT per pose comes
+ * back (bits_out, ceil(n_poses / 32) words; status_out optional), in chunks pipelined with the kernels.  Pass pinned
+ * memory (fc_host_alloc) for pose7 to reach the PCIe rate.  counts as fc_clash_batch. */
+int fc_clash_batch_pose7(const double* a_coords, int n_conf_a, int n_a, const double* b_coords, int n_conf_b, int n_b,
+                         const float* pose7, int64_t n_poses, const int32_t* tiles, int64_t n_tiles, double thresh,
+                         int max_clashes, int strict, uint32_t* bits_out, uint8_t* status_out, int64_t* counts,
+                         int64_t* near_idx, double* near_dist, int64_t near_cap);
+
+/* Page-locked host memory for the host-pointer entry points (cudaHostAlloc), placed on the NUMA node of the current
+ * device when the kernel allows it (set_mempolicy(MPOL_PREFERRED) around the allocation; the node comes from
+ * /sys/bus/pci/devices/<gpu>/numa_node).  node_out (may be NULL) receives that node or -1. */
+void* fc_host_alloc(int64_t bytes, int32_t* node_out);
+void fc_host_free(void* p);
 
 /* Host-pointer entry: same arguments in host memory; copies are pipelined in chunks with the
  * kernels.  counts[0] = passing poses, counts[1] = poses decided by the FP64 recheck,

@@ -42,6 +42,29 @@ def place(frag, xf):
     return (rot @ np.asarray(frag, dtype=float).T).T + np.asarray(xf[9:12], dtype=float)
 
 
+def pose7_to_xf(pose7):
+    """Compact poses (n, 7) float32 {qx, qy, qz, qw, tx, ty, tz} -> (n, 12) float64 transforms, the expansion
+    include/firecode_b200.h defines for FC_POSE_Q7 (every operation rounded on its own, in that order)."""
+    p = np.asarray(pose7, dtype=np.float32).reshape(-1, 7).astype(np.float64)
+    x, y, z, w = p[:, 0], p[:, 1], p[:, 2], p[:, 3]
+    xx, yy, zz, ww = x * x, y * y, z * z, w * w
+    n = ((xx + yy) + zz) + ww
+    s = 2.0 / n
+    xy, xz, yz, xw, yw, zw = x * y, x * z, y * z, x * w, y * w, z * w
+    xf = np.empty((len(p), 12))
+    xf[:, 0] = 1.0 - s * (yy + zz)
+    xf[:, 1] = s * (xy - zw)
+    xf[:, 2] = s * (xz + yw)
+    xf[:, 3] = s * (xy + zw)
+    xf[:, 4] = 1.0 - s * (xx + zz)
+    xf[:, 5] = s * (yz - xw)
+    xf[:, 6] = s * (xz - yw)
+    xf[:, 7] = s * (yz + xw)
+    xf[:, 8] = 1.0 - s * (xx + yy)
+    xf[:, 9:12] = p[:, 4:7]
+    return xf
+
+
 def clash_batch(frag_a, frag_b, xf, thresh=1.0, max_clashes=0, conf_a=None, conf_b=None,
                 strict=True, chunk=2048):
     """Reference decision for every pose of a batch, vectorised over poses.
