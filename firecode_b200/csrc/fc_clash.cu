@@ -474,20 +474,25 @@ __global__ void __launch_bounds__(256) clash_bbox_kernel(const double* __restric
     }
 }
 
-// a_xyz: [conf][n_a] float4 {x, y, z, 0};  grid: [conf][g^3] uint4 = {count, idx0..14} as bytes
-// occ:   [conf][g^3 / 32] one bit per cell: the cell has candidates (32 KB per conformer for g = 64: L1-resident)
+// a_u:  [conf][n_a] float4 {x, y, z, 0} in BOX coordinates u = (a - o) / ((g-1) h)  (the frame phase 2 measures in)
+// grid: [conf][g^3] uint4 = {count, idx0..14} as bytes
+// occ:  [conf][g^3 / 32] one bit per cell: the cell has candidates (32 KB per conformer for g = 64; the screen keeps
+//       the current conformer's copy in shared memory)
 __global__ void __launch_bounds__(128) clash_grid_kernel(const double* __restrict__ a_coords, int n_a,
-                                                         const CellMeta* __restrict__ meta, float4* __restrict__ a_xyz,
+                                                         const CellMeta* __restrict__ meta, float4* __restrict__ a_u,
                                                          uint4* __restrict__ grid, unsigned* __restrict__ occ) {
     extern __shared__ double s_a[];  // n_a * 3
     const int conf = blockIdx.y;
     const double* src = a_coords + (size_t)conf * n_a * 3;
     for (int i = threadIdx.x; i < n_a * 3; i += blockDim.x) s_a[i] = src[i];
-    if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < n_a; i += blockDim.x)
-            a_xyz[(size_t)conf * n_a + i] = make_float4((float)src[3 * i], (float)src[3 * i + 1], (float)src[3 * i + 2], 0.f);
-    __syncthreads();
     const CellMeta m = *meta;
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < n_a; i += blockDim.x) {
+            const double inv = 1.0 / ((double)(m.g - 1) * (double)m.h);
+            a_u[(size_t)conf * n_a + i] = make_float4((float)((src[3 * i] - (double)m.ox) * inv), (float)((src[3 * i + 1] - (double)m.oy) * inv),
+                                                      (float)((src[3 * i + 2] - (double)m.oz) * inv), 0.f);
+        }
+    __syncthreads();
     const int g = m.g;
     const long long n_cells = (long long)g * g * g;
     const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // g^3 is a multiple of 128
@@ -551,45 +556,39 @@ __global__ void __launch_bounds__(32) clash_order_b_kernel(const double* __restr
         cy += __shfl_xor_sync(0xffffffffu, cy, o);
         cz += __shfl_xor_sync(0xffffffffu, cz, o);
     }
-    cx /= (float)n_b;
-    cy /= (float)n_b;
-    cz /= (float)n_b;
-    __syncwarp();
     // distance to the chosen set; first round: distance to the centroid
-    float px = cx, py = cy, pz = cz;
+    float px = cx / (float)n_b, py = cy / (float)n_b, pz = cz / (float)n_b;
     for (int i = lane; i < n_b; i += 32) sd[i] = 3e38f;
+    __syncwarp();
+    // arg-max in ONE warp reduction: key = distance bits (a non-negative float orders like an unsigned) with the low 13
+    // bits replaced by 8191 - index (ties and the lost mantissa bits do not matter for a visiting order)
     const int rounds = n_spread < n_b ? n_spread : n_b;
     for (int r = 0; r < rounds; ++r) {
-        float best = -1.f;
-        int best_i = 0x7fffffff;
+        unsigned best = 0u;
         for (int i = lane; i < n_b; i += 32) {
             float d = sd[i];
             if (d >= 0.f) {  // not taken yet
-                float dx = sx[i] - px, dy = sy[i] - py, dz = sz[i] - pz;
-                float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                d = r == 0 ? d2 : fminf(d, d2);
+                const float dx = sx[i] - px, dy = sy[i] - py, dz = sz[i] - pz;
+                d = fminf(d, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
                 sd[i] = d;
-                if (d > best) { best = d; best_i = i; }
+                best = max(best, ((__float_as_uint(d) & ~8191u) | (unsigned)(8191 - i)) + 8192u);  // +8192: never 0
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-            if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
-        }
+        best = __reduce_max_sync(0xffffffffu, best);
+        const int best_i = 8191 - (int)(best & 8191u);
         if (lane == 0) {
             sel[r] = best_i;
             sd[best_i] = -1.f;  // taken
         }
-        __syncwarp();
         px = sx[best_i];
         py = sy[best_i];
         pz = sz[best_i];
-        if (r == 0)  // from now on: distance to the chosen atoms only
+        __syncwarp();
+        if (r == 0) {  // from now on: distance to the chosen atoms only
             for (int i = lane; i < n_b; i += 32)
                 if (sd[i] >= 0.f) sd[i] = 3e38f;
-        __syncwarp();
+            __syncwarp();
+        }
     }
     if (lane == 0) {  // the rest in original order
         int w = rounds;
@@ -632,18 +631,34 @@ __device__ __forceinline__ void pose7_expand_f64(const float* __restrict__ p, do
 }
 
 template <int FMT>
-__device__ __forceinline__ void pose_load_f32(const void* __restrict__ poses, long long pose, float* r) {
+struct RawPose {  // a pose as it sits in memory, converted to float
+    float v[FMT == kPoseXf64 ? 12 : 7];
+};
+
+template <int FMT>
+__device__ __forceinline__ void pose_load_raw(const void* __restrict__ poses, long long pose, RawPose<FMT>& raw) {
     if (FMT == kPoseXf64) {
         const double2* x = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(poses) + pose * 12);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             const double2 v = __ldg(x + k);
-            r[2 * k] = (float)v.x;
-            r[2 * k + 1] = (float)v.y;
+            raw.v[2 * k] = (float)v.x;
+            raw.v[2 * k + 1] = (float)v.y;
         }
     } else {
-        const float* p = reinterpret_cast<const float*>(poses) + pose * 7;
-        const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2), w = __ldg(p + 3);
+        const float* q = reinterpret_cast<const float*>(poses) + pose * 7;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) raw.v[k] = __ldg(q + k);
+    }
+}
+
+template <int FMT>
+__device__ __forceinline__ void pose_raw_to_f32(const RawPose<FMT>& raw, float* r) {
+    if (FMT == kPoseXf64) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) r[k] = raw.v[k];
+    } else {
+        const float x = raw.v[0], y = raw.v[1], z = raw.v[2], w = raw.v[3];
         const float xx = x * x, yy = y * y, zz = z * z;
         const float s = 2.0f / (xx + yy + zz + w * w);
         const float xy = x * y, xz = x * z, yz = y * z, xw = x * w, yw = y * w, zw = z * w;
@@ -656,19 +671,24 @@ __device__ __forceinline__ void pose_load_f32(const void* __restrict__ poses, lo
         r[6] = s * (xz - yw);
         r[7] = s * (yz + xw);
         r[8] = 1.f - s * (xx + yy);
-        r[9] = __ldg(p + 4);
-        r[10] = __ldg(p + 5);
-        r[11] = __ldg(p + 6);
+        r[9] = raw.v[4];
+        r[10] = raw.v[5];
+        r[11] = raw.v[6];
     }
 }
 
-struct CellItem {  // a pose a level could not decide, handed to the next level
+// a pose a level could not decide, handed to the next level with everything that level needs (64 bytes, four
+// LDG.128): the box-frame transform, the running minimum (box units) and the FP32 band (A^2)
+struct __align__(16) CellItem {
     unsigned pose;
     float dmin2;
+    unsigned spare;
+    float band;
+    float q[12];
 };
 
 struct CellArgs {
-    const float4* a_xyz;
+    const float4* a_u;
     const float* a_rad;
     const float4* b_ord;   // [conf][n_b] farthest-point order
     const float* b_rad;
@@ -693,120 +713,204 @@ struct CellArgs {
     UncEntry* unc_list;
 };
 
+struct CellConst {  // per-axis scale / magic constants and field masks of the cell number
+    float sx, sy, sz, mx, my, mz;
+    unsigned fx, fy, fz;
+};
+
+// box coordinates of atom b under the box-frame transform q, clamped into the box by the .SAT of the last FFMA
+#define FC_CELL_U(b)                                                                              \
+    const float ux = __saturatef(fmaf(q[0], (b).x, fmaf(q[1], (b).y, fmaf(q[2], (b).z, q[9]))));  \
+    const float uy = __saturatef(fmaf(q[3], (b).x, fmaf(q[4], (b).y, fmaf(q[5], (b).z, q[10])))); \
+    const float uz = __saturatef(fmaf(q[6], (b).x, fmaf(q[7], (b).y, fmaf(q[8], (b).z, q[11]))))
+
+// phase 1 for one block of <= 32 atoms: bit k of the result = atom j0 + k landed in a cell with candidates.
+// SMEM: the occupancy words of the pose's conformer are the CTA's shared-memory copy (byte offset = (cell >> 3) & mask);
+// otherwise they are read from global memory through a pointer that already discounts the magic constant's high bits.
+template <bool SMEM>
+__device__ __forceinline__ unsigned cell_flag_block(const float (&q)[12], const float4* __restrict__ bt, int jn,
+                                                    const CellConst& k, const unsigned* __restrict__ oc_global,
+                                                    const unsigned* s_occ_words, unsigned off_mask) {
+    unsigned flagged = 0u;
+#pragma unroll 4
+    for (int a = 0; a < jn; ++a) {
+        const float4 b = __ldg(bt + a);
+        FC_CELL_U(b);
+        // x keeps the bits of 1.5 * 2^23 above its field; y and z are merged in by bitwise select
+        unsigned cell = __float_as_uint(fmaf(ux, k.sx, k.mx));
+        cell = (cell & ~k.fy) | (__float_as_uint(fmaf(uy, k.sy, k.my)) & k.fy);
+        cell = (cell & ~k.fz) | (__float_as_uint(fmaf(uz, k.sz, k.mz)) & k.fz);
+        unsigned word;
+        if (SMEM) {
+            word = *reinterpret_cast<const unsigned*>(reinterpret_cast<const char*>(s_occ_words) + ((cell >> 3) & off_mask));
+        } else {
+            word = __ldg(oc_global + (cell >> 5));
+        }
+        flagged = __funnelshift_r(flagged, __funnelshift_r(word, 0u, cell), 1);  // bit (cell & 31) of word -> top of flagged
+    }
+    return flagged >> (32 - jn);
+}
+
+constexpr int kCellThreads = 256;
+
 template <int FMT>
-__global__ void __launch_bounds__(128, 6) clash_cell_kernel(CellArgs p) {
+__global__ void __launch_bounds__(kCellThreads, 3) clash_cell_kernel(CellArgs p) {
+    extern __shared__ unsigned s_occ[];  // occupancy bits of the cached conformer (g^3 / 32 words)
+    __shared__ int s_want;
     const CellMeta m = *p.meta;
     const int g = m.g, sh = m.shift;
     const unsigned lane = threadIdx.x & 31u;
-    const long long n_items = p.in_list ? (long long)*p.in_count : p.n_poses;
-    // per-axis scale / magic constants: cell numbers in disjoint mantissa fields (x: bits [0,sh), y: [sh,2sh), z: [2sh,3sh));
-    // x rounds to the nearest lattice point; the y and z fields truncate, so half a cell is added to them
-    const float sx = (float)(g - 1), sy = (float)((g - 1) << sh), sz = (float)((g - 1) << (2 * sh));
-    const float mx = kCellMagic, my = kCellMagic + (float)(1 << (sh - 1)), mz = kCellMagic + (float)(1 << (2 * sh - 1));
-    const unsigned fx = (unsigned)(g - 1), fy = fx << sh, fz = fx << (2 * sh);
+    const bool first = p.in_list == nullptr;
+    const long long n_items = first ? p.n_poses : (long long)*p.in_count;
+    // cell numbers in disjoint mantissa fields (x: bits [0,sh), y: [sh,2sh), z: [2sh,3sh)); x rounds to the nearest
+    // lattice point; the y and z fields truncate, so half a cell is added to them
+    CellConst kc;
+    kc.sx = (float)(g - 1);
+    kc.sy = (float)((g - 1) << sh);
+    kc.sz = (float)((g - 1) << (2 * sh));
+    kc.mx = kCellMagic;
+    kc.my = kCellMagic + (float)(1 << (sh - 1));
+    kc.mz = kCellMagic + (float)(1 << (2 * sh - 1));
+    kc.fx = (unsigned)(g - 1);
+    kc.fy = kc.fx << sh;
+    kc.fz = kc.fx << (2 * sh);
     const size_t n_cells = (size_t)g * g * g;
-    for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_items;
-         base += (long long)gridDim.x * blockDim.x) {
+    const unsigned n_words = (unsigned)(n_cells / 32);
+    const unsigned off_mask = (n_words - 1u) << 2;  // byte offset of a word inside the shared copy
+    const float u2 = m.inv_span * m.inv_span;  // A^2 -> box units
+    const float thr2u = p.thr2 * u2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long cta0 = (long long)blockIdx.x * blockDim.x;
+    int cached = -1;  // conformer of A whose occupancy bits sit in shared memory (CTA-uniform)
+    if (!p.tiles) {   // one conformer pair for every pose
+        for (unsigned w = threadIdx.x; w < n_words; w += blockDim.x) s_occ[w] = __ldg(p.occ + w);
+        cached = 0;
+        __syncthreads();
+    }
+    RawPose<FMT> nxt;
+#pragma unroll
+    for (int k = 0; k < (int)(sizeof(nxt.v) / 4); ++k) nxt.v[k] = 0.f;
+    if (first && cta0 + threadIdx.x < n_items) pose_load_raw<FMT>(p.poses, cta0 + threadIdx.x, nxt);
+    for (long long cta_base = cta0; cta_base < n_items; cta_base += stride) {
+        const long long base = cta_base + (threadIdx.x & ~31u);
         const long long item = base + lane;
         const bool valid = item < n_items;
         long long pose = item;
-        float dmin2 = 3.0e38f;
-        if (valid && p.in_list) {
-            const CellItem it = p.in_list[item];
-            pose = it.pose;
-            dmin2 = it.dmin2;
+        float dmin2 = 3.0e38f, band = 0.f;
+        float q[12];
+        RawPose<FMT> cur = nxt;
+        if (first) {  // the next item's pose travels while this one is screened
+            if (item + stride < n_items) pose_load_raw<FMT>(p.poses, item + stride, nxt);
+        } else if (valid) {
+            const float4* it = reinterpret_cast<const float4*>(p.in_list + item);
+            const float4 h0 = it[0], h1 = it[1], h2 = it[2], h3 = it[3];
+            pose = __float_as_uint(h0.x);
+            dmin2 = h0.y;
+            band = h0.w;
+            q[0] = h1.x; q[1] = h1.y; q[2] = h1.z; q[3] = h1.w;
+            q[4] = h2.x; q[5] = h2.y; q[6] = h2.z; q[7] = h2.w;
+            q[8] = h3.x; q[9] = h3.y; q[10] = h3.z; q[11] = h3.w;
         }
         int conf_a = 0, conf_b = 0;
         bool covered = valid;
-        if (valid && p.tiles) {  // tiles are sorted by first pose: binary search
-            long long lo = 0, hi = p.n_tiles - 1;
-            while (lo < hi) {
-                long long mid = (lo + hi + 1) >> 1;
-                if ((long long)p.tiles[mid].z <= pose) lo = mid;
-                else hi = mid - 1;
+        if (p.tiles) {
+            if (valid) {  // tiles are sorted by first pose: binary search
+                long long lo = 0, hi = p.n_tiles - 1;
+                while (lo < hi) {
+                    long long mid = (lo + hi + 1) >> 1;
+                    if ((long long)p.tiles[mid].z <= pose) lo = mid;
+                    else hi = mid - 1;
+                }
+                const int4 t = p.tiles[lo];
+                covered = pose >= (long long)t.z && pose < (long long)t.z + t.w;  // else: pose not covered by any tile
+                conf_a = t.x;
+                conf_b = t.y;
             }
-            const int4 t = p.tiles[lo];
-            covered = pose >= (long long)t.z && pose < (long long)t.z + t.w;  // else: pose not covered by any tile
-            conf_a = t.x;
-            conf_b = t.y;
+            // the CTA keeps the occupancy bits of ONE conformer of A in shared memory: the one its first item uses
+            // (poses are ordered by tile, so a batch rarely mixes conformers; the others read global memory)
+            if (threadIdx.x == 0) s_want = covered ? conf_a : cached;
+            __syncthreads();  // also: every warp is done with the previous batch's shared-memory reads
+            const int want = s_want;
+            if (want != cached) {
+                const unsigned* src = p.occ + (size_t)want * n_words;
+                for (unsigned w = threadIdx.x; w < n_words; w += blockDim.x) s_occ[w] = __ldg(src + w);
+                cached = want;
+                __syncthreads();
+            }
         }
         bool push = false, pass = false;
         if (covered) {
-            float r[12];
-            pose_load_f32<FMT>(p.poses, pose, r);
-            const float tnorm = sqrtf(fmaf(r[9], r[9], fmaf(r[10], r[10], r[11] * r[11])));
+            if (first) {
+                float r[12];
+                pose_raw_to_f32<FMT>(cur, r);
+                const float tnorm = sqrtf(fmaf(r[9], r[9], fmaf(r[10], r[10], r[11] * r[11])));
+                // same band as the all-pairs kernel (the difference form is at least as accurate as the Gram form)
+                const float ext = p.a_rad[conf_a] + p.b_rad[conf_b] + tnorm;
+                band = fmaf(1.5e-6f * ext, ext, 1e-6f);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) q[k] = r[k] * m.inv_span;
+                q[9] = (r[9] - m.ox) * m.inv_span;
+                q[10] = (r[10] - m.oy) * m.inv_span;
+                q[11] = (r[11] - m.oz) * m.inv_span;
+            }
             const float4* bt = p.b_ord + (size_t)conf_b * p.n_b;
-            const float4* at = p.a_xyz + (size_t)conf_a * p.n_a;
+            const float4* at = p.a_u + (size_t)conf_a * p.n_a;
             const uint4* gr = p.grid + (size_t)conf_a * n_cells;
             // phase 1 leaves the magic constant's high bits in its cell number (two LOP3s instead of three): the
             // constant is a multiple of 32 cells, i.e. a fixed number of words, taken off the table pointer here
-            const unsigned* oc = p.occ + (size_t)conf_a * (n_cells / 32) - (size_t)(0x4B400000u >> 5);
+            const unsigned* oc = p.occ + (size_t)conf_a * n_words - (size_t)(0x4B400000u >> 5);
             asm volatile("" : "+l"(oc));  // keep it a materialised pointer: word address = one IMAD.WIDE.U32
-            // same band as the all-pairs kernel (the difference form is at least as accurate as the Gram form)
-            const float ext = p.a_rad[conf_a] + p.b_rad[conf_b] + tnorm;
-            const float band = fmaf(1.5e-6f * ext, ext, 1e-6f);
+            const bool in_smem = conf_a == cached;
             // once the minimum is below this value the pose is decided (certain clash, or -- with max_clashes > 0 --
             // certain to need the FP64 count): the remaining atoms are skipped
-            const float settle = p.count_mode ? p.thr2 + band : p.thr2 - band;
-            float q[12];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) q[k] = r[k] * m.inv_span;
-            q[9] = (r[9] - m.ox) * m.inv_span;
-            q[10] = (r[10] - m.oy) * m.inv_span;
-            q[11] = (r[11] - m.oz) * m.inv_span;
+            const float bandu = band * u2;
+            const float settle = p.count_mode ? thr2u + bandu : thr2u - bandu;
             for (int j0 = p.j_lo; j0 < p.j_hi && !(dmin2 < settle); j0 += 32) {
                 const int jn = min(32, p.j_hi - j0);
                 // ---- phase 1: flag the atoms of B that land in a cell with candidates (no distances yet), so that
                 //      the lanes of a warp do not wait for each other's candidate loops on every atom
-                unsigned bits = 0u;
-#pragma unroll 4
-                for (int k = 0; k < jn; ++k) {
+                unsigned flagged = in_smem ? cell_flag_block<true>(q, bt + j0, jn, kc, oc, s_occ, off_mask)
+                                           : cell_flag_block<false>(q, bt + j0, jn, kc, oc, s_occ, off_mask);
+                // ---- phase 2: distances (box units) from the flagged atoms to the candidates of their cells
+                while (flagged && !(dmin2 < settle)) {
+                    const int k = __ffs(flagged) - 1;
+                    flagged &= flagged - 1u;
                     const float4 b = __ldg(bt + j0 + k);
-                    const float ux = __saturatef(fmaf(q[0], b.x, fmaf(q[1], b.y, fmaf(q[2], b.z, q[9]))));
-                    const float uy = __saturatef(fmaf(q[3], b.x, fmaf(q[4], b.y, fmaf(q[5], b.z, q[10]))));
-                    const float uz = __saturatef(fmaf(q[6], b.x, fmaf(q[7], b.y, fmaf(q[8], b.z, q[11]))));
-                    // x keeps the bits of 1.5 * 2^23 above its field; y and z are merged in by bitwise select
-                    unsigned cell = __float_as_uint(fmaf(ux, sx, mx));
-                    cell = (cell & ~fy) | (__float_as_uint(fmaf(uy, sy, my)) & fy);
-                    cell = (cell & ~fz) | (__float_as_uint(fmaf(uz, sz, mz)) & fz);
-                    const unsigned word = __ldg(oc + (cell >> 5));
-                    bits = __funnelshift_r(bits, __funnelshift_r(word, 0u, cell), 1);  // bit (cell & 31) of word -> top of bits
-                }
-                bits >>= (32 - jn);
-                // ---- phase 2: distances to the candidate atoms of the flagged atoms only
-                while (bits && !(dmin2 < settle)) {
-                    const int k = __ffs(bits) - 1;
-                    bits &= bits - 1u;
-                    const float4 b = __ldg(bt + j0 + k);
-                    const float ux = __saturatef(fmaf(q[0], b.x, fmaf(q[1], b.y, fmaf(q[2], b.z, q[9]))));
-                    const float uy = __saturatef(fmaf(q[3], b.x, fmaf(q[4], b.y, fmaf(q[5], b.z, q[10]))));
-                    const float uz = __saturatef(fmaf(q[6], b.x, fmaf(q[7], b.y, fmaf(q[8], b.z, q[11]))));
-                    const unsigned cell = (__float_as_uint(fmaf(ux, sx, mx)) & fx) | (__float_as_uint(fmaf(uy, sy, my)) & fy) |
-                                          (__float_as_uint(fmaf(uz, sz, mz)) & fz);
-                    const float bx = fmaf(r[0], b.x, fmaf(r[1], b.y, fmaf(r[2], b.z, r[9])));
-                    const float by = fmaf(r[3], b.x, fmaf(r[4], b.y, fmaf(r[5], b.z, r[10])));
-                    const float bz = fmaf(r[6], b.x, fmaf(r[7], b.y, fmaf(r[8], b.z, r[11])));
+                    FC_CELL_U(b);
+                    const unsigned cell = (__float_as_uint(fmaf(ux, kc.sx, kc.mx)) & kc.fx) |
+                                          (__float_as_uint(fmaf(uy, kc.sy, kc.my)) & kc.fy) |
+                                          (__float_as_uint(fmaf(uz, kc.sz, kc.mz)) & kc.fz);
                     const uint4 rec = __ldg(gr + cell);
                     const unsigned count = rec.x & 0xffu;
                     if (count == 255u) {  // crowded cell: all atoms of A
                         for (int i = 0; i < p.n_a; ++i) {
                             const float4 a = __ldg(at + i);
-                            const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
+                            const float dx = a.x - ux, dy = a.y - uy, dz = a.z - uz;
                             dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
                         }
                         continue;
                     }
+                    // candidates four at a time (independent loads); unused index bytes are 0 = atom 0, a real atom of A,
+                    // so measuring it as well cannot make the minimum wrong
                     unsigned long long q0 = (((unsigned long long)rec.y << 32) | rec.x) >> 8;  // indices 0..6
                     unsigned long long q1 = ((unsigned long long)rec.w << 32) | rec.z;         // indices 7..14
-                    q0 |= q1 << 56;
-                    q1 >>= 8;
-                    for (unsigned c = 0; c < count; ++c) {
-                        const unsigned ai = (unsigned)(q0 & 0xffull);
-                        q0 = (q0 >> 8) | (q1 << 56);
-                        q1 >>= 8;
-                        const float4 a = __ldg(at + ai);
-                        const float dx = a.x - bx, dy = a.y - by, dz = a.z - bz;
-                        dmin2 = fminf(dmin2, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+                    q0 |= q1 << 56;  // indices 0..7
+                    q1 >>= 8;        // indices 8..14
+                    for (unsigned c = 0; c < count; c += 4) {
+                        const unsigned i4 = (unsigned)q0;
+                        q0 = (q0 >> 32) | (q1 << 32);
+                        q1 >>= 32;
+                        const float4 a0 = __ldg(at + (i4 & 0xffu)), a1 = __ldg(at + ((i4 >> 8) & 0xffu));
+                        const float4 a2 = __ldg(at + ((i4 >> 16) & 0xffu)), a3 = __ldg(at + (i4 >> 24));
+                        float dx = a0.x - ux, dy = a0.y - uy, dz = a0.z - uz;
+                        const float d0 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        dx = a1.x - ux, dy = a1.y - uy, dz = a1.z - uz;
+                        const float d1 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        dx = a2.x - ux, dy = a2.y - uy, dz = a2.z - uz;
+                        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        dx = a3.x - ux, dy = a3.y - uy, dz = a3.z - uz;
+                        const float d3 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                        dmin2 = fminf(fminf(dmin2, fminf(d0, d1)), fminf(d2, d3));
                     }
                 }
             }
@@ -816,11 +920,11 @@ __global__ void __launch_bounds__(128, 6) clash_cell_kernel(CellArgs p) {
                 uint8_t st;
                 bool uncertain;
                 if (p.count_mode) {
-                    uncertain = !(dmin2 > p.thr2 + band);
+                    uncertain = !(dmin2 > thr2u + bandu);
                     st = FC_STATUS_PASS;
                 } else {
-                    uncertain = fabsf(dmin2 - p.thr2) <= band;
-                    st = dmin2 > p.thr2 ? FC_STATUS_PASS : 0;
+                    uncertain = fabsf(dmin2 - thr2u) <= bandu;
+                    st = dmin2 > thr2u ? FC_STATUS_PASS : 0;
                 }
                 // the candidate lists only cover thresh + kCellPad: a band that large cannot be trusted to them
                 if (band > kCellPad * sqrtf(p.thr2)) uncertain = true;
@@ -839,20 +943,21 @@ __global__ void __launch_bounds__(128, 6) clash_cell_kernel(CellArgs p) {
         // survivors of this level, compacted (one atomic per warp)
         const unsigned pmask = __ballot_sync(0xffffffffu, push);
         if (pmask) {
-            unsigned first = 0;
-            if (lane == 0) first = atomicAdd(p.out_count, (unsigned)__popc(pmask));
-            first = __shfl_sync(0xffffffffu, first, 0);
+            unsigned slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(p.out_count, (unsigned)__popc(pmask));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
             if (push) {
-                CellItem it;
-                it.pose = (unsigned)pose;
-                it.dmin2 = dmin2;
-                p.out_list[first + __popc(pmask & ((1u << lane) - 1u))] = it;
+                float4* it = reinterpret_cast<float4*>(p.out_list + slot0 + __popc(pmask & ((1u << lane) - 1u)));
+                it[0] = make_float4(__uint_as_float((unsigned)pose), dmin2, 0.f, band);
+                it[1] = make_float4(q[0], q[1], q[2], q[3]);
+                it[2] = make_float4(q[4], q[5], q[6], q[7]);
+                it[3] = make_float4(q[8], q[9], q[10], q[11]);
             }
         }
         if (p.bits) {
-            if (!p.in_list) {  // level 0 owns the words: 32 consecutive poses per warp
+            if (first) {  // level 0 owns the words: 32 consecutive poses per warp
                 const unsigned word = __ballot_sync(0xffffffffu, pass);
-                if (lane == 0) p.bits[base >> 5] = word;
+                if (lane == 0 && base < n_items) p.bits[base >> 5] = word;
             } else if (pass) {
                 atomicOr(p.bits + (pose >> 5), 1u << (pose & 31));
             }
@@ -884,14 +989,17 @@ struct RecheckArgs {
     int* recheck_total;  // may be null: running number of rechecked poses (host-buffer entry points)
 };
 
+// One CTA per undecided pose: the placed atoms of B go to shared memory once, warp w takes atoms w, w + 8, ... of B and
+// its lanes the atoms of A, so a pose costs (n_b / 8) x (n_a / 32) square roots per thread instead of n_a x n_b / 32.
 template <int FMT>
 __global__ void __launch_bounds__(256) clash_recheck_f64_kernel(RecheckArgs p) {
-    const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
+    extern __shared__ double s_placed[];  // n_b * 3
+    __shared__ int s_cl[8];
+    __shared__ double s_dm[8], s_cz[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_unc = *p.unc_count;
     if (p.recheck_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.recheck_total, n_unc);
-    for (int u = blockIdx.x * warps_per_block + (threadIdx.x >> 5); u < n_unc;
-         u += gridDim.x * warps_per_block) {
+    for (int u = blockIdx.x; u < n_unc; u += gridDim.x) {
         UncEntry e = p.unc_list[u];
         const double* a = p.a_coords + (size_t)e.conf_a * p.n_a * 3;
         const double* b = p.b_coords + (size_t)e.conf_b * p.n_b * 3;
@@ -903,16 +1011,21 @@ __global__ void __launch_bounds__(256) clash_recheck_f64_kernel(RecheckArgs p) {
         } else {
             pose7_expand_f64(reinterpret_cast<const float*>(p.poses) + e.pose * 7, r);
         }
-        int clashes = 0;
-        double dmin = 1e300, closest = 1e300;
-        for (int j = lane; j < p.n_b; j += 32) {
+        __syncthreads();  // previous pose's placed atoms are no longer read
+        for (int j = threadIdx.x; j < p.n_b; j += blockDim.x) {
             double bx = b[3 * j], by = b[3 * j + 1], bz = b[3 * j + 2];
             // (R @ b) + t, the get_embed expression embeds.py:815-817
-            double px = (r[0] * bx + r[1] * by + r[2] * bz) + r[9];
-            double py = (r[3] * bx + r[4] * by + r[5] * bz) + r[10];
-            double pz = (r[6] * bx + r[7] * by + r[8] * bz) + r[11];
-            for (int i = 0; i < p.n_a; ++i) {
-                double dx = px - a[3 * i], dy = py - a[3 * i + 1], dz = pz - a[3 * i + 2];
+            s_placed[3 * j] = (r[0] * bx + r[1] * by + r[2] * bz) + r[9];
+            s_placed[3 * j + 1] = (r[3] * bx + r[4] * by + r[5] * bz) + r[10];
+            s_placed[3 * j + 2] = (r[6] * bx + r[7] * by + r[8] * bz) + r[11];
+        }
+        __syncthreads();
+        int clashes = 0;
+        double dmin = 1e300, closest = 1e300;
+        for (int i = lane; i < p.n_a; i += 32) {
+            const double ax = a[3 * i], ay = a[3 * i + 1], az = a[3 * i + 2];
+            for (int j = warp; j < p.n_b; j += 8) {
+                double dx = s_placed[3 * j] - ax, dy = s_placed[3 * j + 1] - ay, dz = s_placed[3 * j + 2] - az;
                 double d = sqrt(dx * dx + dy * dy + dz * dz);
                 bool hit = p.strict ? (d < p.thresh) : (d <= p.thresh);
                 clashes += hit ? 1 : 0;
@@ -924,6 +1037,17 @@ __global__ void __launch_bounds__(256) clash_recheck_f64_kernel(RecheckArgs p) {
         dmin = warp_min(dmin);
         closest = warp_min(closest);
         if (lane == 0) {
+            s_cl[warp] = clashes;
+            s_dm[warp] = dmin;
+            s_cz[warp] = closest;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) {
+                clashes += s_cl[w];
+                dmin = fmin(dmin, s_dm[w]);
+                closest = fmin(closest, s_cz[w]);
+            }
             uint8_t st = FC_STATUS_RECHECKED;
             if (clashes <= p.max_clashes) st |= FC_STATUS_PASS;
             // with max_clashes == 0 only the minimum distance decides; otherwise any pair may
@@ -1045,7 +1169,7 @@ struct fc_clash_prep {
     unsigned char* buf = nullptr;  // stream-ordered allocation holding everything below
     const float4* a_tab = nullptr;  // Gram-form atom pairs (all-pairs kernel)
     const float* a_rad = nullptr;
-    const float4* a_xyz = nullptr;  // cell-list tables (cell_g > 0)
+    const float4* a_u = nullptr;    // cell-list tables (cell_g > 0): atoms in box coordinates
     const CellMeta* meta = nullptr;
     const uint4* grid = nullptr;
     const unsigned* occ = nullptr;
@@ -1092,13 +1216,13 @@ extern "C" int fc_clash_prepare_dev(const double* a_coords, int n_conf_a, int n_
     p->a_rad = (const float*)(p->buf + off_ra);
     if (cell_g) {
         CellMeta* meta = (CellMeta*)(p->buf + off_meta);
-        float4* a_xyz = (float4*)(p->buf + off_axyz);
+        float4* a_u = (float4*)(p->buf + off_axyz);
         uint4* grid_tab = (uint4*)(p->buf + off_grid);
         unsigned* occ = (unsigned*)(p->buf + off_occ);
         clash_bbox_kernel<<<1, 256, 0, s>>>(a_coords, (long long)n_conf_a * n_a, (float)thresh, cell_g, meta);
         dim3 gg((unsigned)((n_cells + 127) / 128), (unsigned)n_conf_a);
-        clash_grid_kernel<<<gg, 128, (size_t)n_a * 24, s>>>(a_coords, n_a, meta, a_xyz, grid_tab, occ);
-        p->a_xyz = a_xyz;
+        clash_grid_kernel<<<gg, 128, (size_t)n_a * 24, s>>>(a_coords, n_a, meta, a_u, grid_tab, occ);
+        p->a_u = a_u;
         p->meta = meta;
         p->grid = grid_tab;
         p->occ = occ;
@@ -1164,6 +1288,7 @@ struct ClashBTabs {
 static int clash_prepare_b(const double* b_coords, int n_conf_b, int n_b, ClashBTabs* out, cudaStream_t s) {
     ClashGeom g = choose_geom(n_b);
     FC_REQUIRE(g.tb > 0, "fc_clash_screen_dev: fragment B too large (%d atoms)", n_b);
+    FC_REQUIRE(n_b <= 8191, "fc_clash_screen_dev: fragment B too large (%d atoms)", n_b);
     out->n_b_pad = g.chunks * g.tb;
     const size_t off_rb = (size_t)n_conf_b * out->n_b_pad * 16;
     const size_t off_ord = (off_rb + (size_t)n_conf_b * 4 + 15) / 16 * 16;
@@ -1171,7 +1296,9 @@ static int clash_prepare_b(const double* b_coords, int n_conf_b, int n_b, ClashB
     FC_CUDA(cudaMallocAsync((void**)&out->buf, total, s));
     clash_prep_kernel<<<n_conf_b, 128, 0, s>>>(b_coords, n_conf_b, n_b, out->n_b_pad, 0, (float4*)out->buf,
                                                (float*)(out->buf + off_rb));
-    clash_order_b_kernel<<<n_conf_b, 32, (size_t)n_b * 20, s>>>(b_coords, n_b, 64, (float4*)(out->buf + off_ord));
+    if ((size_t)n_b * 20 > 48 * 1024)
+        cudaFuncSetAttribute(clash_order_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, n_b * 20);
+    clash_order_b_kernel<<<n_conf_b, 32, (size_t)n_b * 20, s>>>(b_coords, n_b, 32, (float4*)(out->buf + off_ord));
     out->b_tab = (const float4*)out->buf;
     out->b_rad = (const float*)(out->buf + off_rb);
     out->b_ord = (const float4*)(out->buf + off_ord);
@@ -1217,12 +1344,15 @@ struct ScreenIO {
 };
 
 template <int FMT>
-static int cell_grid_blocks(int sms) {
+static int cell_grid_blocks(int sms, size_t smem) {
     static int per_sm = 0;
-    if (per_sm == 0) {
+    static size_t for_smem = 0;
+    if (per_sm == 0 || for_smem != smem) {
+        cudaFuncSetAttribute(clash_cell_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, clash_cell_kernel<FMT>, 128, 0) != cudaSuccess || n <= 0) n = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, clash_cell_kernel<FMT>, kCellThreads, smem) != cudaSuccess || n <= 0) n = 2;
         per_sm = n;
+        for_smem = smem;
     }
     return sms * per_sm;
 }
@@ -1240,8 +1370,7 @@ static int cell_levels(int n_b, int* bounds /* [<= 8] */) {
             if (*v == ',') ++v;
         }
     } else {
-        if (n_b > 48) bounds[n++] = 32;
-        if (n_b > 96) bounds[n++] = 64;
+        if (n_b > 48) bounds[n++] = 32;  // measured on B200 (C3): two levels beat one (2.39 -> 1.81 ms) and three (1.93 ms)
     }
     bounds[n] = n_b;
     return n;  // number of levels
@@ -1299,7 +1428,7 @@ static int clash_screen_core(const fc_clash_prep* prep, const double* a_coords, 
 
     if (cell_g) {
         CellArgs c;
-        c.a_xyz = prep->a_xyz;
+        c.a_u = prep->a_u;
         c.a_rad = prep->a_rad;
         c.b_ord = bt.b_ord;
         c.b_rad = bt.b_rad;
@@ -1322,7 +1451,8 @@ static int clash_screen_core(const fc_clash_prep* prep, const double* a_coords, 
         const int n_levels = cell_levels(n_b, bounds);
         CellItem* lists[2] = {(CellItem*)(scratch + off_l0), (CellItem*)(scratch + off_l1)};
         unsigned* counters = (unsigned*)(scratch + off_cnt) + 4;  // one per level, zeroed above
-        const int full_grid = io.fmt == kPoseQ7 ? cell_grid_blocks<kPoseQ7>(sms) : cell_grid_blocks<kPoseXf64>(sms);
+        const size_t cell_smem = (size_t)cell_g * cell_g * cell_g / 8;  // the occupancy bits of one conformer
+        const int full_grid = io.fmt == kPoseQ7 ? cell_grid_blocks<kPoseQ7>(sms, cell_smem) : cell_grid_blocks<kPoseXf64>(sms, cell_smem);
         timing_begin(s);
         for (int lv = 0; lv < n_levels; ++lv) {
             c.j_lo = bounds[lv];
@@ -1333,9 +1463,9 @@ static int clash_screen_core(const fc_clash_prep* prep, const double* a_coords, 
             c.out_list = lists[lv & 1];
             c.out_count = counters + lv;
             int grid = full_grid;
-            if (lv == 0) grid = (int)std::min<long long>(grid, (n_poses + 127) / 128);
-            if (io.fmt == kPoseQ7) clash_cell_kernel<kPoseQ7><<<grid, 128, 0, s>>>(c);
-            else clash_cell_kernel<kPoseXf64><<<grid, 128, 0, s>>>(c);
+            if (lv == 0) grid = (int)std::min<long long>(grid, (n_poses + kCellThreads - 1) / kCellThreads);
+            if (io.fmt == kPoseQ7) clash_cell_kernel<kPoseQ7><<<grid, kCellThreads, cell_smem, s>>>(c);
+            else clash_cell_kernel<kPoseXf64><<<grid, kCellThreads, cell_smem, s>>>(c);
         }
         timing_end(s);
         e = cudaGetLastError();
@@ -1420,8 +1550,15 @@ static int clash_screen_core(const fc_clash_prep* prep, const double* a_coords, 
     r.near_cap = io.near_cap;
     r.pose_base = io.pose_index_base;
     r.recheck_total = io.recheck_total;
-    if (recheck_fmt == kPoseQ7) clash_recheck_f64_kernel<kPoseQ7><<<sms * 2, 256, 0, s>>>(r);
-    else clash_recheck_f64_kernel<kPoseXf64><<<sms * 2, 256, 0, s>>>(r);
+    {
+        const size_t rsmem = (size_t)n_b * 24;
+        if (rsmem > 48 * 1024) {
+            cudaFuncSetAttribute(clash_recheck_f64_kernel<kPoseQ7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+            cudaFuncSetAttribute(clash_recheck_f64_kernel<kPoseXf64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+        }
+        if (recheck_fmt == kPoseQ7) clash_recheck_f64_kernel<kPoseQ7><<<sms * 4, 256, rsmem, s>>>(r);
+        else clash_recheck_f64_kernel<kPoseXf64><<<sms * 4, 256, rsmem, s>>>(r);
+    }
     e = cudaGetLastError();
     int rc = FC_OK;
     if (e == cudaSuccess && !cell_g && io.bits) rc = fc_pack_mask_dev(status, n_poses, io.bits, (void*)s);
