@@ -218,12 +218,30 @@ __host__ __device__ inline M3 kabsch_from_cov(const double* h, double* sig /*3, 
         u2[i] = h[3 * i] * v2[0] + h[3 * i + 1] * v2[1] + h[3 * i + 2] * v2[2];
     }
     double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    if (!(n1 > 1e-150)) {  // H = 0 (e.g. a single selected atom after centring): every rotation is optimal
+        M3 id;
+        for (int i = 0; i < 9; ++i) id.m[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        if (sig) sig[0] = sig[1] = sig[2] = 0.0;
+        return id;
+    }
     for (int i = 0; i < 3; ++i) u1[i] /= n1;
     // Gram-Schmidt keeps u2 orthogonal to u1 when the second singular value is tiny
     double d = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
     for (int i = 0; i < 3; ++i) u2[i] -= d * u1[i];
     double n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
-    for (int i = 0; i < 3; ++i) u2[i] /= n2;
+    if (n2 > 1e-13 * n1) {
+        for (int i = 0; i < 3; ++i) u2[i] /= n2;
+    } else {
+        // rank <= 1 (collinear atoms): any unit vector orthogonal to u1 completes an optimal rotation (numpy's SVD
+        // returns one such completion too); take the coordinate axis least aligned with u1
+        int k = fabs(u1[0]) <= fabs(u1[1]) ? (fabs(u1[0]) <= fabs(u1[2]) ? 0 : 2) : (fabs(u1[1]) <= fabs(u1[2]) ? 1 : 2);
+        double e[3] = {0.0, 0.0, 0.0};
+        e[k] = 1.0;
+        const double de = u1[k];
+        for (int i = 0; i < 3; ++i) u2[i] = e[i] - de * u1[i];
+        n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+        for (int i = 0; i < 3; ++i) u2[i] /= n2;
+    }
     double u3[3] = {u1[1] * u2[2] - u1[2] * u2[1], u1[2] * u2[0] - u1[0] * u2[2], u1[0] * u2[1] - u1[1] * u2[0]};
     double v3[3] = {v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]};
     M3 r;

@@ -316,3 +316,17 @@ extern "C" int fc_fitness_batch(const double* coords, int64_t n, int32_t n_atoms
     if (e != cudaSuccess) return cuda_fail(e, "fc_fitness_batch", __FILE__, __LINE__);
     return FC_OK;
 }
+
+// Host-only test hook (no CUDA call): the Kabsch rotation the kernels use for a 3x3 cross-covariance h (row-major),
+// r_out = U D V^T, sig_out = singular values with the sign of the third set by det(h).  tests/test_host_logic.py
+// feeds it rank-deficient covariances (collinear atoms, a single atom).
+extern "C" int fc_kabsch_host(const double* h, double* r_out, double* sig_out) {
+    FC_REQUIRE(h && r_out, "fc_kabsch_host: null pointer");
+    double sig[3];
+    fc::M3 r = fc::kabsch_from_cov(h, sig);
+    for (int i = 0; i < 9; ++i) r_out[i] = r.m[i];
+    if (sig_out)
+        for (int i = 0; i < 3; ++i) sig_out[i] = sig[i];
+    return FC_OK;
+}
+

@@ -363,6 +363,12 @@ int fc_structure_clash_batch(const double* coords, int64_t n, int32_t n_atoms, c
 int fc_fitness_batch(const double* coords, int64_t n, int32_t n_atoms, const int32_t* pairs, const double* targets,
                      int32_t n_constraints, double* error_out);
 
+/* Host-only test hook (no CUDA call): the Kabsch rotation the kernels compute from a 3x3 cross-covariance h
+ * (row-major): r_out = U D V^T of the SVD h = U S V^T with D = diag(1, 1, det(U V^T)) (prism_pruner
+ * rmsd.get_alignment_matrix / algebra.py:42-49), sig_out (may be NULL) = singular values, the third signed by det(h).
+ * Defined for rank-deficient h as well (collinear or single atoms): any optimal rotation, never NaN. */
+int fc_kabsch_host(const double* h, double* r_out, double* sig_out);
+
 /* Host-only (no CUDA call): the padded position list and the work items (row0, col_tile0, n_col_tiles, pend) the
  * tensor-core screen of fc_prune would use for one pass with k chunks over the structures with mask != 0, after a
  * pass with prev_k chunks (0: first pass).  counts_out = {pairs in this rank's items, pairs known dissimilar}.

@@ -135,6 +135,104 @@ def prune_by_rmsd(structures, atoms, max_rmsd=0.25, max_dev=None, energies=None,
     return structures[mask], mask
 
 
+def _singular_sum_batch(h):
+    """sum of the singular values of (m, 3, 3) matrices, the smallest signed by det: closed-form eigenvalues of
+    H^T H (accurate to ~1e-8 relative; callers treat the result as a SCREEN and decide near-threshold pairs exactly)."""
+    k = np.einsum("mji,mjk->mik", h, h)
+    q = (k[:, 0, 0] + k[:, 1, 1] + k[:, 2, 2]) / 3.0
+    p1 = k[:, 0, 1] ** 2 + k[:, 0, 2] ** 2 + k[:, 1, 2] ** 2
+    b0, b3, b5 = k[:, 0, 0] - q, k[:, 1, 1] - q, k[:, 2, 2] - q
+    p2 = b0 * b0 + b3 * b3 + b5 * b5 + 2.0 * p1
+    p = np.sqrt(np.maximum(p2, 1e-300) / 6.0)
+    b = (k - q[:, None, None] * np.eye(3)) / p[:, None, None]
+    r = np.clip(0.5 * np.linalg.det(b), -1.0, 1.0)
+    phi = np.arccos(r) / 3.0
+    e1 = q + 2.0 * p * np.cos(phi)
+    e3 = q + 2.0 * p * np.cos(phi + 2.0943951023931954923)
+    e2 = 3.0 * q - e1 - e3
+    s3 = np.sqrt(np.maximum(e3, 0.0))
+    return np.sqrt(np.maximum(e1, 0.0)) + np.sqrt(np.maximum(e2, 0.0)) + np.where(np.linalg.det(h) < 0.0, -s3, s3)
+
+
+def prune_by_rmsd_vectorised(structures, atoms, max_rmsd=0.25, max_dev=None, ties=None, stats=None, row_block=256):
+    """prune_by_rmsd for the DEFAULT conventions (keep first, greedy passes), fast enough for the 20 k-structure subset
+    of BASELINE config C4: the same driver and the same per-pair decision (rmsd_and_max, center=True),
+    but the pairs of a chunk are first screened in bulk -- a pair whose closed-form RMSD exceeds max_rmsd by more than
+    1e-6 is dissimilar -- and two survivors of a common chunk of an earlier pass are not compared again (they were
+    compared there, which is what the loop version's cache records).  tests/test_host_logic.py checks that it returns
+    the loop version's mask."""
+    import operator
+
+    assert conventions.PRUNE_KEEP == "first" and conventions.PRUNE_PASS_MODE == "greedy"
+    structures = np.asarray(structures, dtype=float)
+    max_dev = conventions.PRUNE_MAXDEV_FACTOR * max_rmsd if max_dev is None else max_dev
+    sel = _heavy_mask(atoms) if conventions.PRUNE_RMSD_HEAVY_ONLY else np.ones(len(atoms), bool)
+    work = structures[:, sel, :]
+    n, n_h = work.shape[:2]
+    cen = work - work.mean(axis=1, keepdims=True)
+    e = (cen * cen).sum(axis=(1, 2))
+    flat = cen.reshape(n, n_h * 3)
+    limit = n_h * (max_rmsd + 1e-6) ** 2  # summed squared deviation below which a pair needs the exact evaluation
+
+    def exact(i, j):
+        rmsd, maxdev = rmsd_and_max(work[i], work[j], center=True)
+        if stats is not None:
+            stats.eval_calls += 1
+        if ties is None:
+            return rmsd < max_rmsd and maxdev < max_dev
+        return ties.decide(("rmsd", j, i), rmsd, max_rmsd, operator.lt) and \
+            ties.decide(("maxdev", j, i), maxdev, max_dev, operator.lt)
+
+    mask = np.ones(n, dtype=bool)
+    earlier = []  # chunk id of every structure in the passes run so far
+    for k in K_SCHEDULE:
+        active = int(np.count_nonzero(mask))
+        if not (k == 1 or conventions.PRUNE_MIN_PER_CHUNK * k < active):
+            continue
+        if stats is not None:
+            stats.passes.append((k, active))
+        cid = np.empty(n, dtype=np.int64)
+        for c, (first, last) in enumerate(chunk_bounds(n, k)):
+            cid[first:last] = c
+        for first, last in chunk_bounds(n, k):
+            idx = first + np.flatnonzero(mask[first:last])
+            if len(idx) < 2:
+                continue
+            cand = {}
+            for r0 in range(0, len(idx), row_block):
+                rows = idx[r0:r0 + row_block]
+                cols = idx[r0 + 1:]
+                if len(cols) == 0:
+                    continue
+                # H[i, j][a][b] = sum_k x_i[k][a] x_j[k][b] for the block, one GEMM
+                a = cen[rows].transpose(0, 2, 1).reshape(len(rows) * 3, n_h)
+                b = cen[cols].transpose(1, 0, 2).reshape(n_h, len(cols) * 3)
+                h = (a @ b).reshape(len(rows), 3, len(cols), 3).transpose(0, 2, 1, 3)
+                e0 = e[rows][:, None] + e[cols][None, :]
+                later = cols[None, :] > rows[:, None]
+                known = np.zeros_like(later)
+                for prev in earlier:
+                    known |= prev[rows][:, None] == prev[cols][None, :]
+                # Frobenius bound first (sum of singular values <= sqrt(3) |H|_F), closed form for what is left
+                fro = np.sqrt((h * h).sum(axis=(2, 3)))
+                maybe = later & ~known & (e0 - 2.0 * np.sqrt(3.0) * fro < limit)
+                ri, ci = np.nonzero(maybe)
+                if len(ri) == 0:
+                    continue
+                ssum = _singular_sum_batch(h[ri, ci])
+                close = e0[ri, ci] - 2.0 * ssum < limit
+                for i, j in zip(rows[ri[close]], cols[ci[close]]):
+                    cand.setdefault(int(i), []).append(int(j))
+            for i in sorted(cand):
+                if not mask[i]:
+                    continue
+                for j in sorted(cand[i]):
+                    if mask[j] and exact(i, j):
+                        mask[j] = False
+        earlier.append(cid)
+    return structures[mask], mask
+
+
 def principal_moments(structures, atoms):
     masses = np.array([MASSES_TABLE[str(a)] for a in atoms])
     return np.array([get_inertia_moments(s, masses) for s in np.asarray(structures, dtype=float)])

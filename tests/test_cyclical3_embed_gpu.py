@@ -134,3 +134,18 @@ def test_trimolecular_pairing_filter(gpu, internal_as_array):
         assert np.array_equal(rep.kept_indices, ref["kept"])
         assert np.array_equal(constrained, ref["constrained"])
         assert all(couple in [tuple(c) for c in g["ids"]] for g in ref["groups"])
+
+
+def test_trimolecular_c2_shaped_multi_conformer(gpu):
+    """a C2-shaped case -- three molecules of 60 atoms with three conformers EACH (27 conformer
+    triples, 216 groups, 46 656 poses of 180 atoms) -- against the oracle port: direction-search choices, clash mask,
+    kept indices in order, coordinates and constrained pairs."""
+    emb = make_embedder("cyclical", n_mols=3, n_conf=3, n_atoms=60, seed=11, n_reactive=2, n_orb=1, thresh=0.9)
+    prob = problem.cyclical_problem(emb)
+    poses = embeds.cyclical_embed(emb)
+    rep = emb.b200_report
+    ref = _check_problem(prob, poses, emb.constrained_indices, rep)
+    assert len(ref["groups"]) == 216 and rep.n_poses == 216 * 216
+    assert len(ref["kept"]) > 500 and int(ref["clash_pass"].sum()) > 2000
+    confs = {tuple(g["conf"]) for g in ref["groups"]} if "conf" in ref["groups"][0] else None
+    assert confs is None or len(confs) == 27

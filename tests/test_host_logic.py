@@ -288,3 +288,65 @@ def test_prune_sharded_replicates_small_ensembles(monkeypatch):
     monkeypatch.setattr(fdist, "world_info", lambda group=None: (0, 1))
     fdist.prune_sharded(x, ["C"] * 3, "rmsd", force_shard=True)
     assert "shard" not in calls[-1]
+
+
+def test_kabsch_rotation_is_defined_for_rank_deficient_covariances():
+    """three collinear atoms (rank-1 covariance) and a single atom (zero covariance) used to give an
+    all-NaN rotation, so exact duplicates of linear species were never pruned.  The rotation must be proper, finite
+    and optimal (trace(R^T H) = sum of the singular values) for every rank."""
+    import ctypes as C
+
+    from firecode_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(4)
+
+    def kabsch(h):
+        h = np.ascontiguousarray(h, dtype=np.float64)
+        r = np.zeros(9)
+        sig = np.zeros(3)
+        assert lib.fc_kabsch_host(h.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), sig.ctypes.data_as(C.c_void_p)) == 0
+        return r.reshape(3, 3), sig
+
+    cases = []
+    line = np.array([[-1.0, 0, 0], [0, 0, 0], [1.0, 0, 0]])  # three collinear axis-aligned atoms
+    cases.append(line.T @ line)
+    d = rng.normal(size=3)
+    pts = np.outer(np.array([-1.3, 0.2, 1.1]), d / np.linalg.norm(d))
+    q = pts @ synth_rot(rng).T
+    cases.append(pts.T @ q)                                    # rank 1, generic directions
+    cases.append(np.zeros((3, 3)))                             # single atom after centring
+    p2 = rng.normal(size=(5, 3)); p2[:, 2] = 0                 # planar: rank 2
+    cases.append(p2.T @ (p2 @ synth_rot(rng).T))
+    p3 = rng.normal(size=(7, 3))
+    cases.append(p3.T @ (p3 @ synth_rot(rng).T))               # full rank
+    cases.append(-(p3.T @ p3))                                 # reflection-like (det < 0)
+    for h in cases:
+        r, sig = kabsch(h)
+        assert np.all(np.isfinite(r)) and np.all(np.isfinite(sig))
+        assert np.abs(r @ r.T - np.eye(3)).max() < 1e-12 and abs(np.linalg.det(r) - 1.0) < 1e-12
+        s = np.linalg.svd(h, compute_uv=False)
+        best = s[0] + s[1] + (s[2] if np.linalg.det(h) >= 0 else -s[2])
+        assert abs(np.trace(r.T @ h) - best) <= 1e-10 * max(1.0, s[0])
+        assert np.allclose(np.abs(sig), s, atol=1e-7 * max(1.0, s[0]))  # sqrt of eigenvalues of H^T H: ~1e-8 sigma_1
+
+
+def synth_rot(rng):
+    from firecode_b200 import synthetic
+
+    return synthetic.random_rotations(rng, 1)[0]
+
+
+def test_vectorised_oracle_pruner_equals_the_loop_version():
+    """oracle.prism_pruner.pruner.prune_by_rmsd_vectorised (used for the 20 k C4 subset on the GPU box) returns the
+    mask of the plain loop restatement, near-threshold pairs included."""
+    from firecode_b200 import synthetic
+    from oracle.prism_pruner import pruner as ref_pruner
+
+    for seed, n, n_atoms, basins, jitter in ((1, 700, 30, 20, (0.02, 0.5)), (2, 900, 24, 6, (0.05, 0.3)),
+                                             (3, 450, 40, 450, (0.0, 0.0))):
+        atoms, structures, _ = synthetic.pruning_ensemble(np.random.default_rng(seed), n, n_atoms, basins, jitter=jitter)
+        _, slow = ref_pruner.prune_by_rmsd(structures, atoms, 0.5)
+        _, fast = ref_pruner.prune_by_rmsd_vectorised(structures, atoms, 0.5, row_block=64)
+        assert np.array_equal(slow, fast), seed
+        assert 0 < fast.sum() <= n

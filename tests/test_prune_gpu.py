@@ -189,3 +189,35 @@ def test_prune_all_similar_and_all_distinct(gpu):
     _, mask = pruner.prune_by_rmsd(structures, np.array(["C"] * 40), 0.5)
     assert mask.all()
     assert pruner.last_report.screen_launches > 0 and pruner.last_report.screen_candidates == 0
+
+
+def test_prune_c4_20k_subset_matches_oracle(gpu):
+    """kept-set equality with the oracle on the 20 k subset of BASELINE config C4 (120-atom molecule,
+    200 basins x 100 jittered copies), default conventions; the oracle is the vectorised form of the same driver
+    (tests/test_host_logic.py pins it to the loop restatement).  Nine chunked passes, ~8 000 kept."""
+    rng = np.random.default_rng(synthetic.SEED + 4)
+    atoms, structures, _ = synthetic.pruning_ensemble(rng, 20000, 120, 200)
+    out, mask = pruner.prune_by_rmsd(structures, atoms, 0.5)
+    rep = pruner.last_report
+    assert rep.passes >= 8 and rep.screen_launches > 0
+    ties = port.Ties(eps=1e-6, forced=_forced(rep))
+    _, ref_mask = ref_pruner.prune_by_rmsd_vectorised(structures, atoms, 0.5, ties=ties)
+    assert np.array_equal(mask, ref_mask)
+    assert np.array_equal(out, structures[ref_mask])
+    assert 4000 < mask.sum() < 16000
+
+
+def test_prune_rank_deficient_species(gpu):
+    """exact duplicates of a linear species (rank-1 covariance) and of a species with one heavy atom (zero
+    covariance after centring) are pruned, as numpy's SVD-based reference does."""
+    rng = np.random.default_rng(8)
+    co2 = np.array([[-1.16, 0, 0], [0, 0, 0], [1.16, 0, 0.0]])
+    structs = np.array([synthetic.random_rigid(rng, co2) for _ in range(6)])
+    _, mask = pruner.prune_by_rmsd(structs, np.array(["O", "C", "O"]), 0.25)
+    _, ref = ref_pruner.prune_by_rmsd(structs, np.array(["O", "C", "O"]), 0.25)
+    assert mask.tolist() == ref.tolist() == [True] + [False] * 5
+    water = np.array([[0, 0, 0.12], [0, 0.76, -0.47], [0, -0.76, -0.47]])
+    structs = np.array([synthetic.random_rigid(rng, water) for _ in range(5)])
+    _, mask = pruner.prune_by_rmsd(structs, np.array(["O", "H", "H"]), 0.25)
+    _, ref = ref_pruner.prune_by_rmsd(structs, np.array(["O", "H", "H"]), 0.25)
+    assert mask.tolist() == ref.tolist() == [True] + [False] * 4
