@@ -137,6 +137,8 @@ SIGNATURES = {
     "fc_clash_timing": (C.c_int, [C.c_int, c_dp, c_i64p]),
     "fc_pack_mask_dev": (C.c_int, [VP, C.c_int64, VP, VP]),
     "fc_rmsd_and_max_batch": (C.c_int, [VP, VP, C.c_int64, C.c_int32, C.c_int32, VP, VP]),
+    "fc_rmsd_rot_corr_pairs": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_int32, VP, C.c_int32, VP, VP, VP, VP, C.c_int64,
+                                         C.c_int32, C.c_int32, VP, VP, VP, VP]),
     "fc_self_clash_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_double, VP, VP]),
     "fc_structure_clash_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_int32, C.c_double, VP, VP]),
     "fc_fitness_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, VP, C.c_int32, VP]),

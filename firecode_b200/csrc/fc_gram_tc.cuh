@@ -52,7 +52,7 @@ struct GramArgs {
     long long cand_cap;
     float* dump;              // debug: H of every (prow, pcol) visited, [prow][dump_ld][9]; null in production
     int dump_ld;
-    int* error;               // set when a barrier wait times out (the kernel then traps)
+    int* error;               // set when a barrier wait times out (the kernel then runs out, the host reports it)
     long long* prof;          // debug: cycle counters of CTA 0 (see tools/gram_tc_test.cu); null in production
     int no_math;              // debug bits (tools/gram_tc_test.cu; 0 in production): 1 = the epilogue only drains tensor
                               // memory, 2 = one k-step per tile, 4 = no B copies, 64 = every valid pair takes pass 2
@@ -90,9 +90,15 @@ __device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigne
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
-// bounded wait: a protocol error ends in a trap (reported through *error), never in a hung GPU
+
+// Bounded mbarrier wait.  A protocol error must neither hang the GPU nor poison the CUDA context: after a short burst of
+// polls the wait looks at the clock (%globaltimer, two seconds: a TIME bound, so time-slicing, MPS or a debugger cannot
+// expire it spuriously) and at the abort flag; on expiry it records `code` in *error and gives up.  Every other wait of
+// the kernel then falls through as soon as it sees the flag, the kernel runs to its end with garbage that nobody reads,
+// and the host turns the flag into an error code (fc_prune: "gram_tc_kernel: mbarrier wait N timed out").
 __device__ __forceinline__ void bar_wait(unsigned bar, unsigned parity, int* error, int code) {
-    for (unsigned spin = 0; spin < (1u << 22); ++spin) {
+    unsigned long long t0 = 0;
+    for (unsigned spin = 0;; ++spin) {
         unsigned ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -100,10 +106,17 @@ __device__ __forceinline__ void bar_wait(unsigned bar, unsigned parity, int* err
             : "r"(bar), "r"(parity)
             : "memory");
         if (ok) return;
+        if ((spin & 0x3FFFu) == 0x3FFFu) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            const bool aborted = error && *reinterpret_cast<volatile int*>(error) != 0;
+            if (aborted || now - t0 > 2000000000ull) {
+                if (error && !aborted) atomicCAS(error, 0, code);
+                return;
+            }
+        }
     }
-    if (error) atomicExch(error, code);
-    __threadfence_system();
-    __trap();
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(256) prune_pairs_kernel(PruneArgs a) {
 // ---------------------------------------------------------------------------------------------
 // FP32 screen + FP64 exact evaluation of the pairs it cannot rule out
 // ---------------------------------------------------------------------------------------------
-// closed-form singular-value sum in FP32 (see singular_sum3): good to a few 1e-3 A on the RMSD, which is all
-// the screen needs -- its guard band is kScreenBand
+// closed-form UPPER BOUND on the singular-value sum in FP32 (see singular_sum3): the screen rejects a pair only when
+// even this bound leaves the RMSD above the threshold by kScreenBand
 __device__ __forceinline__ float singular_sum3f(const float* h) {
     float k0 = h[0] * h[0] + h[3] * h[3] + h[6] * h[6], k1 = h[0] * h[1] + h[3] * h[4] + h[6] * h[7];
     float k2 = h[0] * h[2] + h[3] * h[5] + h[6] * h[8], k3 = h[1] * h[1] + h[4] * h[4] + h[7] * h[7];
@@ -292,9 +292,12 @@ __device__ __forceinline__ float singular_sum3f(const float* h) {
         e3 = q + 2.0f * p * cosf(phi + 2.0943951f);
         e2 = 3.0f * q - e1 - e3;
     }
-    const float det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) + h[2] * (h[3] * h[7] - h[4] * h[6]);
-    const float s3 = sqrtf(fmaxf(e3, 0.f));
-    return sqrtf(fmaxf(e1, 0.f)) + sqrtf(fmaxf(e2, 0.f)) + (det < 0.f ? -s3 : s3);
+    // An UPPER bound is what a screen may reject on: the smallest singular value is ADDED whatever the sign of det H
+    // (for near-planar frames e3 is FP32 noise and the sign of an FP32 determinant is a coin toss; subtracting s3 there
+    // would lower the sum by ~1e-3 sigma_1 and could screen out a truly similar pair), and the FP32 error of the
+    // closed form (eigenvalues good to ~1e-6 sigma_1^2, i.e. ~1e-3 sigma_1 on the smallest root) is added explicitly.
+    const float s1 = sqrtf(fmaxf(e1, 0.f));
+    return s1 + sqrtf(fmaxf(e2, 0.f)) + sqrtf(fmaxf(e3, 0.f)) + 2e-3f * s1;
 }
 
 constexpr float kScreenBand = 0.05f;   // A: FP32 covariance + FP32 closed form are good to a few 1e-3 A
@@ -614,7 +617,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
         FC_REQUIRE(masses, "fc_prune: MOI pruning needs masses");
     }
     sm_count();
-    const bool trace = getenv("FC_CLASH_TRACE") != nullptr;
+    const bool trace = getenv("FC_PRUNE_TRACE") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
     double t_tiles = 0, t_kernels = 0, t_resolve = 0, t_upload = 0, t_gram = 0;
@@ -686,7 +689,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
         std::vector<int2> pairs, all_pairs;
         int64_t prev_size = 0, prev_k = 0;  // chunking of the last executed pass
         // screen flavour: FC_PRUNE_FP64=1 -> FP64 pair kernel only; otherwise FP32 screen + FP64 exact stage, the screen
-        // on the tensor cores (gram_tc_kernel) unless FC_PRUNE_TC=0 or the molecule has more than 96 selected atoms
+        // on the tensor cores (gram_tc_kernel) unless FC_PRUNE_TC=0 or the molecule has more than 88 selected atoms (kGramMaxKc)
         const char* env64 = getenv("FC_PRUNE_FP64");
         const char* envtc = getenv("FC_PRUNE_TC");
         const bool two_stage = mode == 0 && !(env64 && atoi(env64));
@@ -806,8 +809,15 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                         }
                         PR(cudaGetLastError());
                         unsigned long long n_cand = 0;
+                        int gram_err = 0;
                         PR(cudaMemcpyAsync(&n_cand, d_eval.p + 2, 8, cudaMemcpyDeviceToHost, s));
+                        if (use_tc) PR(cudaMemcpyAsync(&gram_err, d_gram_err.p, 4, cudaMemcpyDeviceToHost, s));
                         PR(cudaStreamSynchronize(s));
+                        if (e == cudaSuccess && gram_err) {  // a bounded mbarrier wait of the tensor-core screen expired
+                            set_error("gram_tc_kernel: mbarrier wait %d timed out (pass k=%lld)", gram_err, (long long)k);
+                            rc = FC_ERR_CUDA;
+                            break;
+                        }
                         if (use_tc && e == cudaSuccess) {
                             float ms = 0;
                             cudaEventElapsedTime(&ms, ev_g0, ev_g1);

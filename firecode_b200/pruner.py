@@ -141,23 +141,180 @@ def prune_by_moment_of_inertia(structures, atoms, max_deviation=None, energies=N
     return out, mask
 
 
+K_SCHEDULE = (500_000, 200_000, 100_000, 50_000, 20_000, 10_000, 5000, 2000, 1000, 500, 200, 100, 50, 20, 10, 5, 2, 1)
+
+
+@dataclass
+class RotCorrReport:
+    n_torsions: int = 0
+    n_folds: tuple = ()
+    passes: int = 0
+    pairs_evaluated: int = 0
+    ties: list = None            # [(kind, later, earlier, value, decision)] within 1e-6 of a threshold
+    choices: dict = None         # {((earlier, later), torsion): angle index} where the two best angles tie (gap <= 1e-9)
+    keep: str = "first"
+    pass_mode: str = "greedy"
+
+
+last_rot_corr_report: RotCorrReport | None = None
+
+
+def host_symmetry_torsions(coords, atoms, graph):
+    """The symmetric torsions of a structure, found by the HOST application's own torsion machinery (FIRECODE's
+    torsion_module.py:70-432 and prism_pruner.utils.get_double_bonds_indices, which a plugin runs inside of): graph
+    chemistry at set-up scale, O(atoms), not part of the per-pair hot path.  Selection as prune_by_rmsd_rot_corr's
+    ([UNVERIFIED-RECALL], see oracle/prism_pruner/pruner.py:symmetry_torsions).  Returns (quadruplets, angles, masks)."""
+    try:
+        from firecode.torsion_module import _get_hydrogen_bonds, _get_rotation_mask, _get_torsions, _is_nondummy
+        from prism_pruner.utils import get_double_bonds_indices
+    except Exception as exc:
+        raise _lib.FirecodeB200Error(
+            "prune_by_rmsd_rot_corr needs the symmetric torsions of the molecule: pass torsions=/angles=/masks= or run "
+            f"inside FIRECODE (firecode.torsion_module / prism_pruner.utils not importable: {exc})") from exc
+    atoms = np.asarray(atoms)
+    torsions = _get_torsions(graph, hydrogen_bonds=_get_hydrogen_bonds(atoms, coords, graph),
+                             double_bonds=get_double_bonds_indices(coords, atoms), keepdummy=True, mode="symmetry")
+    torsions = [t for t in torsions if not (_is_nondummy(t.i2, t.i3, graph) and _is_nondummy(t.i3, t.i2, graph))]
+    torsions = [t for t in torsions if "H" not in [str(atoms[i]) for i in t.torsion]]
+    angles = [tuple(float(x) for x in t.get_angles()) for t in torsions]
+    quads = [tuple(t.torsion) if _is_nondummy(t.i2, t.i3, graph) else tuple(reversed(t.torsion)) for t in torsions]
+    masks = [np.asarray(_get_rotation_mask(graph, q), dtype=bool) for q in quads]
+    return quads, angles, masks
+
+
+def rmsd_and_max_rot_corr_pairs(structures, atoms, pairs, torsions, angles, masks, want_choices=False):
+    """Symmetry-corrected (rmsd, maxdev) of structure pairs {earlier, later} on the GPU (C-ABI fc_rmsd_rot_corr_pairs)."""
+    lib = _lib.load(require_device=True)
+    x = np.ascontiguousarray(np.asarray(structures, dtype=np.float64))
+    n, n_atoms = x.shape[:2]
+    atoms = np.asarray(atoms)
+    sel = np.flatnonzero(np.array([str(a) != "H" for a in atoms])) if conventions.PRUNE_RMSD_HEAVY_ONLY else np.arange(n_atoms)
+    sel = np.ascontiguousarray(sel, dtype=np.int32)
+    pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1, 2))
+    tor = np.ascontiguousarray(np.asarray(torsions, dtype=np.int32).reshape(-1, 4))
+    n_tors = len(tor)
+    msk = np.ascontiguousarray(np.asarray(masks, dtype=np.uint8).reshape(n_tors, n_atoms)) if n_tors else None
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64) for a in angles])) if n_tors else None
+    off = np.ascontiguousarray(np.concatenate([[0], np.cumsum([len(a) for a in angles])]).astype(np.int32))
+    rmsd = np.empty(len(pairs))
+    dev = np.empty(len(pairs))
+    choice = np.zeros((len(pairs), max(n_tors, 1)), dtype=np.int32) if want_choices else None
+    gap = np.full((len(pairs), max(n_tors, 1)), np.inf) if want_choices else None
+    step = 1 << 22
+    for lo in range(0, len(pairs), step):
+        hi = min(len(pairs), lo + step)
+        rc = lib.fc_rmsd_rot_corr_pairs(_ptr(x), n, n_atoms, _ptr(sel), len(sel), _ptr(tor) if n_tors else None, n_tors,
+                                        _ptr(msk), _ptr(flat), _ptr(off), _ptr(pairs[lo:hi]), hi - lo,
+                                        int(conventions.ROT_HANDEDNESS), int(conventions.TORSION_AXIS_SIGN),
+                                        _ptr(rmsd[lo:hi]), _ptr(dev[lo:hi]),
+                                        None if choice is None else _ptr(choice[lo:hi]),
+                                        None if gap is None else _ptr(gap[lo:hi]))
+        _lib.check(rc, "fc_rmsd_rot_corr_pairs")
+    if want_choices:
+        return rmsd, dev, choice[:, :n_tors], gap[:, :n_tors]
+    return rmsd, dev
+
+
 def prune_by_rmsd_rot_corr(structures, atoms, graph, max_rmsd=0.25, max_dev=None, energies=None,
-                           max_dE=0.0, logfunction=None, debugfunction=None, keep=None, pass_mode=None):
-    """Symmetry-corrected RMSD pruning (embedder.py:1489).  The torsion-symmetry enumeration of
-    prism_pruner is a "next" row of the scope table: until it is built this
-    entry point applies the plain heavy-atom RMSD criterion, which is the first of the two tests
-    the corrected variant performs, and says so through ``logfunction``."""
+                           max_dE=0.0, logfunction=None, debugfunction=None, keep=None, pass_mode=None,
+                           torsions=None, angles=None, masks=None):
+    """Symmetry-corrected RMSD pruning (embedder.py:1485-1496, ensemble.py:253, operators.py:626): structures that
+    differ only by a rotation of a locally symmetric group (methyl, tert-butyl, CF3, phenyl ...) count as similar.
+    The pair distance is the symmetry-corrected RMSD of fc_rmsd_rot_corr_pairs, evaluated on the GPU for every
+    active pair of a chunk; the multi-pass chunked driver and its keep rule are those of prune_by_rmsd.  The
+    symmetric torsions come from the host application's torsion machinery unless passed in.  PARITY UNPINNED: the
+    algorithm is [UNVERIFIED-RECALL] of prism_pruner 0.0.7 (csrc/fc_rotcorr.cu states it)."""
+    global last_rot_corr_report
+    keep = conventions.PRUNE_KEEP if keep is None else keep
+    pass_mode = conventions.PRUNE_PASS_MODE if pass_mode is None else pass_mode
+    assert keep in ("first", "last") and pass_mode in ("greedy", "snapshot")
+    x = np.ascontiguousarray(np.asarray(structures, dtype=np.float64))
+    n = len(x)
+    max_dev = conventions.PRUNE_MAXDEV_FACTOR * max_rmsd if max_dev is None else max_dev
+    if torsions is None:
+        torsions, angles, masks = host_symmetry_torsions(x[0], atoms, graph) if n else ([], [], [])
+    rep = RotCorrReport(n_torsions=len(torsions), n_folds=tuple(len(a) for a in angles), ties=[], choices={},
+                        keep=keep, pass_mode=pass_mode)
+    last_rot_corr_report = rep
+    mask = np.ones(n, dtype=bool)
+    if len(torsions) == 0 or n < 2:
+        return x[mask], mask
     if logfunction is not None:
-        logfunction("firecode_b200: rotationally-corrected RMSD pruning not built yet - plain RMSD criterion applied")
-    return prune_by_rmsd(structures, atoms, max_rmsd=max_rmsd, max_dev=max_dev, energies=energies,
-                         max_dE=max_dE, debugfunction=debugfunction, keep=keep, pass_mode=pass_mode)
+        logfunction(f"Rotationally-corrected RMSD pruning: {len(torsions)} symmetric torsions ({list(rep.n_folds)}-fold)")
+    e = None if energies is None else np.asarray(energies, dtype=np.float64)
+    for k in K_SCHEDULE:
+        active = int(np.count_nonzero(mask))
+        if not (k == 1 or conventions.PRUNE_MIN_PER_CHUNK * k < active):
+            continue
+        rep.passes += 1
+        size = n // k
+        bounds = [(c * size, n if c == k - 1 else size * (c + 1)) for c in range(k)]
+        # every pair of structures active at the start of the pass, chunk by chunk, in one GPU call
+        blocks = []
+        for first, last in bounds:
+            idx = first + np.flatnonzero(mask[first:last])
+            if len(idx) > 1:
+                i, j = np.triu_indices(len(idx), 1)
+                blocks.append(np.stack([idx[i], idx[j]], axis=1))
+        if not blocks:
+            continue
+        pairs = np.concatenate(blocks)
+        if e is not None:
+            pairs = pairs[np.abs(e[pairs[:, 0]] - e[pairs[:, 1]]) < max_dE]
+        if len(pairs) == 0:
+            continue
+        rmsd, dev, choice, gap = rmsd_and_max_rot_corr_pairs(x, atoms, pairs, torsions, angles, masks, want_choices=True)
+        rep.pairs_evaluated += len(pairs)
+        similar = (rmsd < max_rmsd) & (dev < max_dev)
+        for kind, val, thr in (("rmsd", rmsd, max_rmsd), ("maxdev", dev, max_dev)):
+            for p in np.flatnonzero(np.abs(val - thr) <= 1e-6):
+                rep.ties.append((kind, int(pairs[p, 1]), int(pairs[p, 0]), float(val[p]), bool(val[p] < thr)))
+        for p, t in zip(*np.nonzero(gap <= 1e-9)):
+            rep.choices[((int(pairs[p, 0]), int(pairs[p, 1])), int(t))] = int(choice[p, t])
+        sim_pairs = pairs[similar]
+        # ordered resolution of the pass (the keep rule of prune_by_rmsd) over the similar pairs only
+        chunk_of = np.empty(n, dtype=np.int64)
+        for c, (first, last) in enumerate(bounds):
+            chunk_of[first:last] = c
+        partners = {}
+        for a, b in sim_pairs:
+            partners.setdefault(int(a), []).append(int(b))
+            partners.setdefault(int(b), []).append(int(a))
+        if pass_mode == "greedy":
+            order = range(n) if keep == "first" else range(n - 1, -1, -1)
+            for i in order:
+                if not mask[i]:
+                    continue
+                for j in partners.get(i, ()):
+                    if mask[j] and (j > i if keep == "first" else j < i):
+                        mask[j] = False
+        else:
+            snap = mask.copy()
+            for i in range(n):
+                if snap[i] and any(snap[j] and (j < i if keep == "first" else j > i) for j in partners.get(i, ())):
+                    mask[i] = False
+    if debugfunction is not None:
+        debugfunction(f"DEBUG: prune_by_rmsd_rot_corr (firecode_b200) - kept {int(mask.sum())}/{len(mask)}")
+    lib = _lib.load()
+    return _take(lib, x, mask), mask
 
 
-def prune(structures, atoms, max_rmsd=0.25, logfunction=None, debugfunction=None, **kw):
-    """MOI pruning followed by RMSD pruning (interfaces/goat.py:399)."""
+_PRUNE_KW = ("energies", "max_dE", "keep", "pass_mode", "shard")
+
+
+def prune(structures, atoms, max_rmsd=0.25, logfunction=None, debugfunction=None, max_dev=None, max_deviation=None,
+          **kw):
+    """MOI pruning followed by RMSD pruning (interfaces/goat.py:399).  energies / max_dE / keep / pass_mode / shard
+    reach both stages; anything else is a TypeError (a silently dropped energy window would un-gate the pruning)."""
+    unknown = [k for k in kw if k not in _PRUNE_KW]
+    if unknown:
+        raise TypeError(f"prune() got unexpected keyword arguments {unknown}")
     structures = np.asarray(structures, dtype=np.float64)
-    s1, m1 = prune_by_moment_of_inertia(structures, atoms, debugfunction=debugfunction)
-    s2, m2 = prune_by_rmsd(s1, atoms, max_rmsd=max_rmsd, debugfunction=debugfunction)
+    s1, m1 = prune_by_moment_of_inertia(structures, atoms, max_deviation=max_deviation, debugfunction=debugfunction, **kw)
+    kw2 = dict(kw)
+    if kw2.get("energies") is not None:
+        kw2["energies"] = np.asarray(kw2["energies"])[m1]
+    s2, m2 = prune_by_rmsd(s1, atoms, max_rmsd=max_rmsd, max_dev=max_dev, debugfunction=debugfunction, **kw2)
     mask = m1.copy()
     mask[np.flatnonzero(m1)] = m2
     return s2, mask

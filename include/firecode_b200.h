@@ -330,6 +330,20 @@ int fc_torsion_scan(const double* coords, int32_t n_conf, int32_t n_atoms, const
 int fc_rmsd_and_max_batch(const double* ref, const double* structures, int64_t n, int32_t n_atoms,
                           int32_t center, double* rmsd_out, double* maxdev_out);
 
+/* Symmetry-corrected RMSD of structure pairs, the per-pair arithmetic of prism_pruner.pruner.prune_by_rmsd_rot_corr
+ * (call sites embedder.py:1485-1496, ensemble.py:253, operators.py:626; algorithm [UNVERIFIED-RECALL], stated in
+ * csrc/fc_rotcorr.cu and oracle/prism_pruner/pruner.py): for pair p = {reference r, structure c}, a copy of c has every
+ * symmetric torsion, in order, set to the symmetry angle whose rotation of atom i4 alone best matches r on the four
+ * torsion atoms (first minimum), the torsion's rotating group (masks) following; then
+ * rmsd_and_max(r[sel], copy[sel], center=True).
+ *  structures (n, n_atoms, 3) host; torsions (n_tors, 4); masks (n_tors, n_atoms); angles flat, torsion t owns
+ *  angles[angle_offsets[t] .. angle_offsets[t+1]) degrees; pairs (n_pairs, 2); outputs (n_pairs);
+ *  choice_out / gap_out (n_pairs, n_tors) optional: winning angle index per torsion and the RMSD gap to the runner-up. */
+int fc_rmsd_rot_corr_pairs(const double* structures, int64_t n, int32_t n_atoms, const int32_t* sel, int32_t n_sel,
+                           const int32_t* torsions, int32_t n_tors, const uint8_t* masks, const double* angles,
+                           const int32_t* angle_offsets, const int32_t* pairs, int64_t n_pairs, int32_t rot_handedness,
+                           int32_t axis_sign, double* rmsd_out, double* maxdev_out, int32_t* choice_out, double* gap_out);
+
 /* Non-fragment branch of utils.py:523-542 `compenetration_check(coords, graph)` and algebra.py:52-54
  * `count_clashes` for n structures: close_pairs_out[s] = ordered atom pairs with 0 < d < 0.5 A,
  * nonbonded_out[s] = ordered pairs i != j with d < thresh and bonded[i * n_atoms + j] == 0

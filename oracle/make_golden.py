@@ -275,8 +275,95 @@ def main_refining():
                             kept_similarity=out["similarity"], checksum=np.float64(structures.sum()))
 
 
+def multiembed_arrangements(reactive1, reactive2):
+    """The arrangement enumeration of multiembed_bifunctional (multiembed.py:39-48), same expressions."""
+    loader.install()
+    from itertools import permutations
+
+    from firecode.utils import cartesian_product
+
+    pairs = cartesian_product(reactive1, reactive2)
+    return [((ix_1, ix_2), (iy_1, iy_2)) for ((ix_1, ix_2), (iy_1, iy_2)) in permutations(pairs, 2)
+            if ix_1 != iy_1 and ix_2 != iy_2]
+
+
+def main_multiembed():
+    """firecode/tests/embed_multiembed through the UNMODIFIED reference: every arrangement of multiembed_bifunctional
+    (multiembed.py:33-159) is run with the reference's own run_child_embedder, IN THIS PROCESS and in arrangement
+    order (the reference farms them out to a process pool and collects them in completion order).  Stored per
+    arrangement: the child's cyclical problem as plain arrays, the structures / constrained indices the child's
+    generate_candidates produced, the target distances fitness_refining read, and what run_child_embedder returned
+    after compenetration / fitness / similarity(rmsd=False) refining."""
+    loader.install()
+    import firecode.multiembed as mm
+    from firecode.embedder import RunEmbedding
+
+    from firecode_b200 import problem
+
+    captured = {}
+    orig = RunEmbedding.generate_candidates
+
+    def spy(self):
+        captured["problem"] = pack_cyclical_problem(problem.cyclical_problem(self))
+        captured["embed"] = self.embed
+        out = orig(self)
+        captured["structures"] = np.array(self.structures, dtype=float)
+        captured["constrained"] = np.asarray(self.constrained_indices).copy()
+        captured["atoms"] = np.asarray(self.atoms)
+        captured["table"] = {k: tuple(int(x) for x in v) for k, v in self.pairings_table.items()}
+        captured["dists"] = {k: self.get_pairing_dist_from_letter(k) for k in self.pairings_table}
+        captured["options"] = (float(self.options.clash_thresh), int(self.options.max_clashes), float(self.options.rmsd))
+        return out
+
+    RunEmbedding.generate_candidates = spy
+    try:
+        with loader.embedder_from_dir(loader.fixture_dir("embed_multiembed"), "embed_multiembed.txt") as emb:
+            assert emb.embed == "multiembed"
+            mol1, mol2 = emb.objects
+            arrangements = multiembed_arrangements(mol1.reactive_indices, mol2.reactive_indices)
+            out = {"n_arrangements": np.int64(len(arrangements)), "arrangements": np.array(arrangements, dtype=np.int64),
+                   "conventions": np.array(_conventions())}
+            total = 0
+            for i, arr in enumerate(arrangements):
+                captured.clear()
+                with loader._quiet():
+                    structures, constrained = mm.run_child_embedder(mol1.filename, mol2.filename,
+                                                                    constrained_indices=np.array(arr), i=i, options=emb.options)
+                structures = np.asarray(structures, dtype=float)
+                if "problem" not in captured:
+                    raise RuntimeError("child embed did not reach generate_candidates")
+                for k, v in captured["problem"].items():
+                    out[f"c{i}_{k}"] = v
+                zero = "structures" not in captured
+                n_tot = int(sum(captured["problem"]["ids"]))
+                out[f"c{i}_embed"] = np.array(captured["embed"])
+                out[f"c{i}_zero"] = np.bool_(zero)
+                out[f"c{i}_ref_structures"] = captured.get("structures", np.zeros((0, n_tot, 3)))
+                out[f"c{i}_ref_constrained"] = captured.get("constrained", np.zeros((0, 2, 2), dtype=np.int64))
+                out[f"c{i}_final_structures"] = structures.reshape(-1, n_tot, 3) if structures.size else np.zeros((0, n_tot, 3))
+                out[f"c{i}_final_constrained"] = np.asarray(constrained) if structures.size else np.zeros((0, 2, 2), dtype=np.int64)
+                if not zero:
+                    out[f"c{i}_table_keys"] = np.array(sorted(captured["table"]))
+                    out[f"c{i}_table_pairs"] = np.array([captured["table"][k] for k in sorted(captured["table"])], dtype=np.int64)
+                    out[f"c{i}_dists"] = np.array([np.nan if captured["dists"][k] is None else captured["dists"][k]
+                                                   for k in sorted(captured["table"])], dtype=float)
+                    out["atoms"] = captured["atoms"]
+                    out["options"] = np.array(captured["options"])
+                total += len(out[f"c{i}_final_structures"])
+                print(f"multiembed child {i + 1}/{len(arrangements)} {arr}: embed={captured['embed']} "
+                      f"generated {len(out[f'c{i}_ref_structures'])} -> {len(out[f'c{i}_final_structures'])} after refining")
+            np.savez_compressed(os.path.join(GOLDEN, "embed_multiembed.npz"), **out)
+            print(f"embed_multiembed: {len(arrangements)} arrangements, {total} structures in arrangement order")
+    finally:
+        RunEmbedding.generate_candidates = orig
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "multiembed":
+        main_multiembed()
+        sys.exit(0)
     main()
     main_tfd()
     main_csearch()
     main_refining()
+    main_multiembed()

@@ -19,6 +19,7 @@ from . import conventions
 from .algebra import get_inertia_moments
 from .periodic_table import MASSES_TABLE
 from .rmsd import rmsd_and_max
+from .utils import rotate_dihedral
 
 K_SCHEDULE = (500_000, 200_000, 100_000, 50_000, 20_000, 10_000, 5000, 2000, 1000, 500, 200, 100,
               50, 20, 10, 5, 2, 1)
@@ -255,14 +256,89 @@ def prune_by_moment_of_inertia(structures, atoms, max_deviation=None, energies=N
     return structures[mask], mask
 
 
+def symmetry_torsions(coords, atoms, graph):
+    """Torsions whose rotation is an element of local symmetry (methyl, tert-butyl, CF3, phenyl ...), their symmetry
+    angles and rotating groups, selected as [UNVERIFIED-RECALL] prism_pruner's prune_by_rmsd_rot_corr does with the
+    torsion machinery that FIRECODE keeps in-tree (torsion_module.py:70-147 Torsion / get_n_fold / get_angles, 176-268
+    _is_free / _is_nondummy, 271-352 _get_hydrogen_bonds, 354-382 _get_rotation_mask, 411-432 _get_torsions):
+    all rotable bonds including dummy ones (keepdummy=True, mode="symmetry"); keep those that ARE dummy in at least one
+    direction; drop quadruplets touching hydrogen (the RMSD is heavy-atom); orient each so that the dummy portion hangs
+    on the last index.  Needs the reference tree (CPU container only): GPU-box tests pass torsions explicitly."""
+    from firecode.torsion_module import _get_hydrogen_bonds, _get_rotation_mask, _get_torsions, _is_nondummy
+
+    from .utils import get_double_bonds_indices
+
+    atoms = np.asarray(atoms)
+    torsions = _get_torsions(graph, hydrogen_bonds=_get_hydrogen_bonds(atoms, coords, graph),
+                             double_bonds=get_double_bonds_indices(coords, atoms), keepdummy=True, mode="symmetry")
+    torsions = [t for t in torsions if not (_is_nondummy(t.i2, t.i3, graph) and _is_nondummy(t.i3, t.i2, graph))]
+    torsions = [t for t in torsions if "H" not in [str(atoms[i]) for i in t.torsion]]
+    angles = [tuple(float(x) for x in t.get_angles()) for t in torsions]
+    quads = [tuple(t.torsion) if _is_nondummy(t.i2, t.i3, graph) else tuple(reversed(t.torsion)) for t in torsions]
+    masks = [np.asarray(_get_rotation_mask(graph, q), dtype=bool) for q in quads]
+    return quads, angles, masks
+
+
+def rmsd_and_max_rot_corr(ref, coord, torsions, angles, masks, sel, forced_choice=None, choice_eps=0.0, key=None):
+    """[UNVERIFIED-RECALL] prism_pruner rmsd_and_max_rot_corr: a copy of ``coord`` has every symmetric torsion, in order,
+    set to the symmetry angle whose rotation of atom i4 ALONE (rotate_dihedral, indices_to_be_moved=[i4]) gives the
+    smallest centred Kabsch RMSD of the four torsion atoms against ``ref`` (first minimum of a ``<`` scan); the
+    torsion's rotating group then follows by that angle.  Returns rmsd_and_max(ref[sel], copy[sel], center=True).
+    ``forced_choice[(key, t)]`` overrides the scan where its two best angles are closer than ``choice_eps`` (the
+    parity tests hand in the GPU's listed choices, exactly as for the trimolecular direction search)."""
+    coord = np.array(coord, dtype=float)
+    for t, (torsion, rot_angles, mask) in enumerate(zip(torsions, angles, masks)):
+        quad = list(torsion)
+        vals = []
+        for angle in rot_angles:
+            trial = rotate_dihedral(coord, torsion, angle, indices_to_be_moved=[torsion[3]])
+            vals.append(rmsd_and_max(ref[quad], trial[quad], center=True)[0])
+        best = 0
+        for k in range(1, len(vals)):
+            if vals[k] < vals[best]:
+                best = k
+        if forced_choice is not None and len(vals) > 1:
+            order = np.argsort(vals, kind="stable")
+            if vals[order[1]] - vals[order[0]] <= choice_eps and (key, t) in forced_choice:
+                best = int(forced_choice[(key, t)])
+        if rot_angles[best] != 0:
+            coord = rotate_dihedral(coord, torsion, rot_angles[best], mask=mask)
+    return rmsd_and_max(ref[sel], coord[sel], center=True)
+
+
 def prune_by_rmsd_rot_corr(structures, atoms, graph, max_rmsd=0.25, max_dev=None, energies=None,
-                           max_dE=0.0, logfunction=None, debugfunction=None, stats=None,
+                           max_dE=0.0, logfunction=None, debugfunction=None, stats=None, ties=None,
+                           torsions=None, angles=None, masks=None, forced_choice=None, choice_eps=0.0,
                            **switches):
-    """Symmetry-corrected RMSD pruning. The torsion-symmetry enumeration lives in the absent
-    prism_pruner.torsion_module; this restatement falls back to plain heavy-atom RMSD pruning
-    (a "next" row)."""
-    return prune_by_rmsd(structures, atoms, max_rmsd=max_rmsd, max_dev=max_dev, energies=energies,
-                         max_dE=max_dE, debugfunction=debugfunction, stats=stats, **switches)
+    """Symmetry-corrected RMSD pruning (call sites embedder.py:1485-1496, ensemble.py:253, operators.py:626): the
+    multi-pass driver of prune_by_rmsd with rmsd_and_max_rot_corr(earlier, later) as the pair distance.  Without
+    symmetric torsions every structure is kept.  PARITY UNPINNED ([UNVERIFIED-RECALL] of prism_pruner 0.0.7)."""
+    import operator
+
+    structures = np.asarray(structures, dtype=float)
+    max_dev = conventions.PRUNE_MAXDEV_FACTOR * max_rmsd if max_dev is None else max_dev
+    sel = _heavy_mask(atoms) if conventions.PRUNE_RMSD_HEAVY_ONLY else np.ones(len(atoms), bool)
+    if torsions is None:
+        torsions, angles, masks = symmetry_torsions(structures[0], atoms, graph) if len(structures) else ([], [], [])
+    if len(torsions) == 0 or len(structures) == 0:
+        mask = np.ones(len(structures), dtype=bool)
+        return structures[mask], mask
+    if logfunction is not None:
+        logfunction(f"Rotationally-corrected RMSD pruning: {len(torsions)} symmetric torsions "
+                    f"({[len(a) for a in angles]}-fold)")
+
+    def evaluate_sim(i, j):
+        rmsd, maxdev = rmsd_and_max_rot_corr(structures[i], structures[j], torsions, angles, masks, sel,
+                                             forced_choice=forced_choice, choice_eps=choice_eps, key=(i, j))
+        if ties is None:
+            return rmsd < max_rmsd and maxdev < max_dev
+        return ties.decide(("rmsd", j, i), rmsd, max_rmsd, operator.lt) and \
+            ties.decide(("maxdev", j, i), maxdev, max_dev, operator.lt)
+
+    mask = prune_mask(len(structures), evaluate_sim, energies, max_dE, stats=stats, **switches)
+    if debugfunction is not None:
+        debugfunction(f"DEBUG: prune_by_rmsd_rot_corr - kept {int(mask.sum())}/{len(mask)}")
+    return structures[mask], mask
 
 
 def prune(structures, atoms, max_rmsd=0.25, logfunction=None, debugfunction=None, **kw):
