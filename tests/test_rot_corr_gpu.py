@@ -16,14 +16,17 @@ pytestmark = pytest.mark.gpu
 def rotor_molecule(rng, n_heavy, folds):
     """Heavy-atom tree + one symmetric rotor per entry of ``folds`` on distinct leaves.
     Returns atoms, coords, torsions [(g, p, x, f0)], angles, masks, plus per rotor the index list of its blades."""
-    atoms, xyz, bonds, parent = synthetic.molecule_cloud(rng, n_heavy, heavy_fraction=1.0)
+    for _ in range(200):  # a tree with enough leaves to carry the rotors
+        atoms, xyz, bonds, parent = synthetic.molecule_cloud(rng, n_heavy, heavy_fraction=1.0)
+        children = {i: [] for i in range(n_heavy)}
+        for p, c in bonds:
+            children[p].append(c)
+        leaves = [i for i in range(n_heavy) if not children[i] and parent[i] >= 0 and parent[parent[i]] >= 0]
+        if len(leaves) >= len(folds):
+            break
+    assert len(leaves) >= len(folds)
     atoms = list(atoms)
     coords = [r for r in xyz]
-    children = {i: [] for i in range(n_heavy)}
-    for p, c in bonds:
-        children[p].append(c)
-    leaves = [i for i in range(n_heavy) if not children[i] and parent[i] >= 0 and parent[parent[i]] >= 0]
-    assert len(leaves) >= len(folds)
     torsions, angles, blades = [], [], []
     for x, fold in zip(rng.permutation(leaves)[: len(folds)], folds):
         p, g = int(parent[x]), int(parent[parent[x]])
