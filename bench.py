@@ -602,30 +602,44 @@ def run_extras():
             r = fn()
         return (time.perf_counter() - t0) / reps, r
 
-    # C1: string embed, 2 x (10 conformers, 30 atoms), 2 centres, 36 angles = 14 400 tuples
+    # C1: string embed, 2 x (10 conformers, 30 atoms), 2 centres, 36 angles = 14 400 tuples -- through the
+    # reference-named entry point string_embed(embedder) (embeds.py:51-158): problem extraction + screen + coordinates
     emb = make_embedder("string", 10, 30, seed=synthetic.SEED, n_orb=2)
-    prob = problem.string_problem(emb)
-    dt, (poses, rep) = timed(lambda: embeds.string_screen(prob))
-    out["C1_string_embed"] = {"poses_per_s": rep.n_poses / dt, "poses": rep.n_poses, "kept": rep.n_kept,
-                              "clash_pass": rep.n_clash_pass, "seconds": dt}
+    dt, poses = timed(lambda: embeds.string_embed(emb), reps=5)
+    rep = emb.b200_report
+    out["C1_string_embed"] = {"api": "firecode_b200.embeds.string_embed(embedder)", "poses_per_s": rep.n_poses / dt,
+                              "poses": rep.n_poses, "kept": rep.n_kept, "clash_pass": rep.n_clash_pass, "seconds": dt,
+                              "returned_bytes": int(poses.nbytes)}
     # C2-like bimolecular cyclical embed: 2 x (50 conformers, 60 atoms), 4 pivots each, 36 angle pairs
     emb = make_embedder("cyclical", 50, 60, seed=synthetic.SEED + 1, n_reactive=2, n_orb=2)
-    cprob = problem.cyclical_problem(emb)
-    dt, (poses, cons, rep) = timed(lambda: embeds.cyclical_screen(cprob), reps=1)
-    out["C2_cyclical_embed_bimolecular"] = {"poses_per_s": rep.n_poses / dt, "poses": rep.n_poses, "kept": rep.n_kept,
-                                            "clash_pass": rep.n_clash_pass, "seconds": dt,
-                                            "note": "includes the host-side group table (numpy, vectorised)"}
+    dt, poses = timed(lambda: embeds.cyclical_embed(emb), reps=2)
+    rep = emb.b200_report
+    out["C2_cyclical_embed_bimolecular"] = {"api": "firecode_b200.embeds.cyclical_embed(embedder)", "poses_per_s": rep.n_poses / dt,
+                                            "poses": rep.n_poses, "kept": rep.n_kept, "clash_pass": rep.n_clash_pass,
+                                            "seconds": dt, "returned_bytes": int(poses.nbytes)}
     # C2 (BASELINE.json configs[1]): trimolecular cyclical embed, 3 x (50 conformers, 60 atoms), one pivot per
-    # molecule, 8 orientations, 216 angle triples = 125 000 conformer triples -> 1 M groups -> 216 M poses
+    # molecule, 8 orientations, 216 angle triples = 125 000 conformer triples -> 1 M groups -> 216 M poses.
+    # (a) the screen alone (kept indices, no coordinates), (b) the reference-named entry point, which also returns the
+    # coordinates of every kept pose (float64, (kept, 180, 3)) as the reference's cyclical_embed does
     emb = make_embedder("cyclical", 50, 60, seed=synthetic.SEED + 2, n_mols=3, n_reactive=2, n_orb=1)
     tprob = problem.cyclical_problem(emb)
     dt, (poses, cons, rep) = timed(lambda: embeds.cyclical3_screen(tprob, want_status=False, want_coords=False), reps=1)
     out["C2_cyclical_embed_trimolecular"] = {
+        "api": "firecode_b200.embeds.cyclical3_screen(problem, want_status=False, want_coords=False)",
         "poses_per_s": rep.n_poses / dt, "poses": rep.n_poses, "groups": int(len(rep.group_choice)),
         "kept": rep.n_kept, "clash_pass": rep.n_clash_pass, "seconds": dt,
         "min_direction_search_gap_deg": float(rep.group_gap.min()) if len(rep.group_gap) else None,
         "note": "full C2: group enumeration (C++), stateful 343-point direction search, 3 block screens over 36 "
                 "distinct angle pairs each, keep-first RMSD; kept-pose coordinates not materialised"}
+    t0 = time.perf_counter()
+    poses = embeds.cyclical_embed(emb)
+    dt = time.perf_counter() - t0
+    rep = emb.b200_report
+    out["C2_cyclical_embed_trimolecular_api"] = {
+        "api": "firecode_b200.embeds.cyclical_embed(embedder)", "poses_per_s": rep.n_poses / dt, "poses": rep.n_poses,
+        "kept": rep.n_kept, "seconds": dt, "returned_bytes": int(poses.nbytes),
+        "note": "the drop-in call: same screen plus the float64 coordinates of every kept pose, streamed to the caller's array"}
+    del poses
     # C4-like RMSD pruning: 20 000 conformers of a 120-atom molecule (400 basins)
     rng = np.random.default_rng(synthetic.SEED + 4)
     atoms, structures, _ = synthetic.pruning_ensemble(rng, 20000, 120, 400)

@@ -606,6 +606,25 @@ __global__ void cyc3_materialize_kernel(Cyc3Dev p, const long long* __restrict__
     }
 }
 
+// per kept pose: the rigid transform (R row-major, t) and the conformer of every molecule -- what is needed to place
+// its atoms later (fc_result_kept_coords streams the coordinates into the caller's buffer)
+__global__ void cyc3_kept_xf_kernel(Cyc3Dev p, const long long* __restrict__ kept, int n_kept, double* __restrict__ xf,
+                                    int32_t* __restrict__ conf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_kept * 3) return;
+    const int k = i / 3, m = i - 3 * k;
+    const long long pose = kept[k];
+    const long long g = pose / p.n_angles;
+    const int ai = (int)(pose - g * p.n_angles);
+    M3 rot;
+    double t[3];
+    cyc3_mol_xf(p, g, m, p.angles[3 * ai + m], rot, t);
+    double* o = xf + (size_t)i * 12;
+    for (int e = 0; e < 9; ++e) o[e] = rot.m[e];
+    o[9] = t[0]; o[10] = t[1]; o[11] = t[2];
+    conf[i] = p.supers[p.groups[g].super].conf[m];
+}
+
 // ---- host-side enumeration (reference loop order) ------------------------------------------------
 struct HostGroup {
     int ids[6];  // three sorted atom couples (embeds.py:774-784)
@@ -1128,16 +1147,19 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
                 const int n_kept = (int)ckept.size();
                 const size_t base = r->kept.size();
                 if (want_coords) {
-                    e = d_out.alloc((size_t)n_kept * n_tot * 3, s);
+                    // the coordinates are NOT produced here (5.8 GB at BASELINE config C2): the kept poses' transforms
+                    // stay on the device with the result, fc_result_kept_coords streams the atoms to the caller
+                    fc_result::LazySegment sgm;
+                    sgm.count = n_kept;
+                    e = cudaMalloc((void**)&sgm.d_xf, (size_t)n_kept * 36 * sizeof(double));
+                    if (e == cudaSuccess) e = cudaMalloc((void**)&sgm.d_conf, (size_t)n_kept * 3 * sizeof(int32_t));
                     if (e == cudaSuccess) {
-                        cyc3_materialize_kernel<<<n_kept, 128, 0, s>>>(d, d_kept.p, n_kept, d_out.p);
+                        cyc3_kept_xf_kernel<<<(unsigned)((n_kept * 3 + 127) / 128), 128, 0, s>>>(d, d_kept.p, n_kept, sgm.d_xf, sgm.d_conf);
                         e = cudaGetLastError();
                     }
-                    r->coords.resize((base + n_kept) * (size_t)n_tot * 3);
-                    CY(cudaMemcpyAsync(r->coords.data() + base * (size_t)n_tot * 3, d_out.p, (size_t)n_kept * n_tot * 24,
-                                       cudaMemcpyDeviceToHost, s));
+                    r->lazy.push_back(sgm);  // owned by the result from here on (freed with it, also on failure)
                     CY(cudaStreamSynchronize(s));
-                    if (e != cudaSuccess) { rc = cuda_fail(e, "materialize", __FILE__, __LINE__); break; }
+                    if (e != cudaSuccess) { rc = cuda_fail(e, "kept transforms", __FILE__, __LINE__); break; }
                 }
                 r->constrained.resize((base + n_kept) * 6);
                 for (int k = 0; k < n_kept; ++k) {
@@ -1148,6 +1170,18 @@ extern "C" int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** ou
             }
             if (trace) { t_mat += now() - tc; }
             sg_lo = sg_hi;
+        }
+        if (rc == FC_OK && !r->lazy.empty()) {  // device copies of the ensembles for the deferred placement
+            cudaGetDevice(&r->lazy_device);
+            r->lazy_n_mols = 3;
+            for (int m = 0; m < 3 && e == cudaSuccess; ++m) {
+                const size_t nb = (size_t)p->n_conf[m] * p->n_atoms[m] * 24;
+                r->lazy_n_atoms[m] = p->n_atoms[m];
+                e = cudaMalloc((void**)&r->lazy_coords[m], nb);
+                CY(cudaMemcpyAsync(r->lazy_coords[m], d_coords[m].p, nb, cudaMemcpyDeviceToDevice, s));
+            }
+            CY(cudaStreamSynchronize(s));
+            if (e != cudaSuccess) rc = cuda_fail(e, "ensemble copies", __FILE__, __LINE__);
         }
         for (int k = 0; k < 3; ++k) fc_clash_prep_free(prep[k], (void*)s);
 #undef CY

@@ -346,7 +346,85 @@ extern "C" int fc_result_status(const fc_result* r, uint8_t* out) { FC_COPY_OUT(
 extern "C" int fc_result_survivors(const fc_result* r, int64_t* out) { FC_COPY_OUT(r->survivors, out); }
 extern "C" int fc_result_fingerprints(const fc_result* r, double* out) { FC_COPY_OUT(r->fingerprints, out); }
 extern "C" int fc_result_kept_indices(const fc_result* r, int64_t* out) { FC_COPY_OUT(r->kept, out); }
-extern "C" int fc_result_kept_coords(const fc_result* r, double* out) { FC_COPY_OUT(r->coords, out); }
+namespace fc {
+// atoms of the molecules placed by per-pose transforms: out (n, sum of atoms, 3)
+__global__ void __launch_bounds__(128) place_kept_kernel(const double* __restrict__ xf, const int32_t* __restrict__ conf,
+                                                         const double* c0, const double* c1, const double* c2, int n0,
+                                                         int n1, int n2, int n_mols, long long n, double* __restrict__ out) {
+    const long long k = blockIdx.x;
+    if (k >= n) return;
+    __shared__ double s_xf[3][12];
+    if (threadIdx.x < n_mols * 12) s_xf[threadIdx.x / 12][threadIdx.x % 12] = xf[k * n_mols * 12 + threadIdx.x];
+    __syncthreads();
+    const int n_tot = n0 + n1 + n2;
+    double* o = out + (size_t)k * n_tot * 3;
+    for (int at = threadIdx.x; at < n_tot; at += blockDim.x) {
+        const int m = at < n0 ? 0 : (at < n0 + n1 ? 1 : 2);
+        const int local = at - (m == 0 ? 0 : (m == 1 ? n0 : n0 + n1));
+        const int na = m == 0 ? n0 : (m == 1 ? n1 : n2);
+        const double* base = m == 0 ? c0 : (m == 1 ? c1 : c2);
+        const double* b = base + ((size_t)conf[k * n_mols + m] * na + local) * 3;
+        const double* r = s_xf[m];
+        // (R @ b) + t, the get_embed expression embeds.py:815-817
+        o[3 * at] = (r[0] * b[0] + r[1] * b[1] + r[2] * b[2]) + r[9];
+        o[3 * at + 1] = (r[3] * b[0] + r[4] * b[1] + r[5] * b[2]) + r[10];
+        o[3 * at + 2] = (r[6] * b[0] + r[7] * b[1] + r[8] * b[2]) + r[11];
+    }
+}
+}  // namespace fc
+
+fc_result::~fc_result() {
+    if (lazy.empty() && !lazy_coords[0]) return;
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (lazy_device >= 0 && lazy_device != cur) cudaSetDevice(lazy_device);
+    for (LazySegment& sgm : lazy) {
+        if (sgm.d_xf) cudaFree(sgm.d_xf);
+        if (sgm.d_conf) cudaFree(sgm.d_conf);
+    }
+    for (int m = 0; m < 3; ++m)
+        if (lazy_coords[m]) cudaFree(lazy_coords[m]);
+    if (lazy_device >= 0 && lazy_device != cur && cur >= 0) cudaSetDevice(cur);
+}
+
+extern "C" int fc_result_kept_coords(const fc_result* r, double* out) {
+    FC_REQUIRE(r, "null result");
+    if (r->lazy.empty()) FC_COPY_OUT(r->coords, out);
+    FC_REQUIRE(out, "null output pointer");
+    int cur = -1;
+    FC_CUDA(cudaGetDevice(&cur));
+    if (r->lazy_device >= 0 && r->lazy_device != cur) FC_CUDA(cudaSetDevice(r->lazy_device));
+    const int n_tot = r->lazy_n_atoms[0] + r->lazy_n_atoms[1] + r->lazy_n_atoms[2];
+    const size_t pose_bytes = (size_t)n_tot * 24;
+    const int64_t slice = std::max<int64_t>(1, ((int64_t)256 << 20) / (int64_t)pose_bytes);  // 256 MB of coordinates per slice
+    cudaStream_t s = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    double* d_out[2] = {nullptr, nullptr};
+    for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaMalloc((void**)&d_out[b], (size_t)slice * pose_bytes);
+    size_t done = 0;
+    int b = 0;
+    for (const fc_result::LazySegment& sgm : r->lazy) {
+        for (int64_t lo = 0; lo < sgm.count && e == cudaSuccess; lo += slice, b ^= 1) {
+            const int64_t n = std::min<int64_t>(slice, sgm.count - lo);
+            fc::place_kept_kernel<<<(unsigned)n, 128, 0, s>>>(sgm.d_xf + lo * r->lazy_n_mols * 12, sgm.d_conf + lo * r->lazy_n_mols,
+                                                              r->lazy_coords[0], r->lazy_coords[1], r->lazy_coords[2],
+                                                              r->lazy_n_atoms[0], r->lazy_n_atoms[1], r->lazy_n_atoms[2],
+                                                              r->lazy_n_mols, n, d_out[b]);
+            e = cudaGetLastError();
+            // download_staged returns once the slice sits in the caller's buffer; the kernel of the next slice is
+            // short, so the copy engine and the host threads are what the loop keeps busy
+            if (e == cudaSuccess) e = fc::download_staged(reinterpret_cast<char*>(out) + done, d_out[b], (size_t)n * pose_bytes, s);
+            done += (size_t)n * pose_bytes;
+        }
+    }
+    if (s) cudaStreamSynchronize(s);
+    for (int k = 0; k < 2; ++k)
+        if (d_out[k]) cudaFree(d_out[k]);
+    if (s) cudaStreamDestroy(s);
+    if (r->lazy_device >= 0 && r->lazy_device != cur) cudaSetDevice(cur);
+    if (e != cudaSuccess) return fc::cuda_fail(e, "fc_result_kept_coords", __FILE__, __LINE__);
+    return FC_OK;
+}
 extern "C" int fc_result_constrained(const fc_result* r, int32_t* out) { FC_COPY_OUT(r->constrained, out); }
 extern "C" int fc_result_groups(const fc_result* r, int32_t* choice, double* gap) {
     FC_REQUIRE(r, "null result");

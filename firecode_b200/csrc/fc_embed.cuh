@@ -22,6 +22,21 @@ struct fc_result {
     int64_t n_groups = 0;
     std::vector<int32_t> group_choice;
     std::vector<double> group_gap;
+    // kept poses whose coordinates have NOT been materialised yet (trimolecular embed: 5.8 GB at BASELINE config C2):
+    // per kept pose the rigid transform of every molecule and its conformer stay on the device, in one segment per
+    // chunk of the screen; fc_result_kept_coords places the atoms slice by slice and streams them into the caller's
+    // buffer.  Freed with the result.
+    struct LazySegment {
+        double* d_xf = nullptr;   // (count, n_mols, 12) R row-major, t
+        int32_t* d_conf = nullptr;  // (count, n_mols)
+        int64_t count = 0;
+    };
+    std::vector<LazySegment> lazy;
+    double* lazy_coords[3] = {nullptr, nullptr, nullptr};  // device copies of the ensembles
+    int32_t lazy_n_atoms[3] = {0, 0, 0};
+    int32_t lazy_n_mols = 0;
+    int lazy_device = -1;
+    ~fc_result();
 };
 
 namespace fc {
@@ -60,6 +75,9 @@ struct TieRecord {
 };
 
 fc_result* result_new();
+// fc_host.cu: dst (host, pageable or pinned) <- src (device), through two pinned staging buffers drained by several
+// host threads while the copy engine fills the other one
+cudaError_t download_staged(void* dst, const void* src_dev, size_t bytes, cudaStream_t stream);
 
 // fc_host.cu: pageable host rows -> device through two pinned staging buffers filled by several threads
 cudaError_t upload_rows_staged(double* dst, const double* src, int64_t n, int n_atoms, const int32_t* sel, int n_sel,

@@ -178,6 +178,60 @@ extern "C" int fc_xyz_format(const char* symbols, int32_t sym_stride, const doub
     return FC_OK;
 }
 
+namespace fc {
+
+// dst (host) <- src_dev (device): pieces of kStageBytes travel into two pinned staging buffers; while the copy engine
+// fills one, several host threads copy the other into dst (for a fresh numpy array that is also where its pages are
+// first touched).  Synchronous: returns when dst holds everything.
+cudaError_t download_staged(void* dst, const void* src_dev, size_t bytes, cudaStream_t stream) {
+    static thread_local PinnedPair st;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (!st.p[0]) {
+        for (int b = 0; b < 2; ++b) {
+            e = cudaHostAlloc(&st.p[b], kStageBytes, cudaHostAllocPortable);
+            if (e != cudaSuccess) return e;
+        }
+        st.bytes = kStageBytes;
+    }
+    if (st.device != dev) {
+        for (int b = 0; b < 2; ++b) {
+            if (st.ev[b]) cudaEventDestroy(st.ev[b]);
+            e = cudaEventCreateWithFlags(&st.ev[b], cudaEventDisableTiming);
+            if (e != cudaSuccess) return e;
+        }
+        st.device = dev;
+    }
+    const char* src = static_cast<const char*>(src_dev);
+    char* out = static_cast<char*>(dst);
+    size_t pend_off[2] = {0, 0}, pend_n[2] = {0, 0};
+    int b = 0;
+    for (size_t off = 0; off < bytes || pend_n[0] || pend_n[1]; b ^= 1) {
+        if (pend_n[b]) {  // the piece that went into this staging buffer two steps ago
+            e = cudaEventSynchronize(st.ev[b]);
+            if (e != cudaSuccess) return e;
+            const char* from = static_cast<const char*>(st.p[b]);
+            char* to = out + pend_off[b];
+            parallel_ranges((int64_t)pend_n[b], (int64_t)1 << 20, [=](int64_t lo, int64_t hi) { memcpy(to + lo, from + lo, (size_t)(hi - lo)); });
+            pend_n[b] = 0;
+        }
+        if (off < bytes) {
+            const size_t n = std::min(kStageBytes, bytes - off);
+            e = cudaMemcpyAsync(st.p[b], src + off, n, cudaMemcpyDeviceToHost, stream);
+            if (e != cudaSuccess) return e;
+            e = cudaEventRecord(st.ev[b], stream);
+            if (e != cudaSuccess) return e;
+            pend_off[b] = off;
+            pend_n[b] = n;
+            off += n;
+        }
+    }
+    return cudaSuccess;
+}
+
+}  // namespace fc
+
 // ------------------------------------------------------------------------------------------------
 // page-locked host memory on the GPU's NUMA node
 // ------------------------------------------------------------------------------------------------

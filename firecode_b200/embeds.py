@@ -394,7 +394,9 @@ def cyclical_embed(embedder, max_norm_delta: float = 5.0):
     embedder.log(f"\n--> Performing {embedder.embed} embed ({pretty_num(embedder.candidates)} candidates)")
     prob = problem.cyclical_problem(embedder, max_norm_delta=max_norm_delta)
     if len(embedder.objects) == 3:
-        poses, constrained, report = cyclical3_screen(prob)
+        # the per-pose status bytes are not part of the reference's interface (216 MB at BASELINE config C2): they
+        # come back only when the caller asks for them (tests do, through embedder.b200_want_status)
+        poses, constrained, report = cyclical3_screen(prob, want_status=bool(getattr(embedder, "b200_want_status", False)))
     else:
         poses, constrained, report = cyclical_screen(prob)
     embedder.b200_report = report

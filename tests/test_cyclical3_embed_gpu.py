@@ -47,6 +47,7 @@ def test_trimolecular_embed_matches_oracle(gpu, kw):
     prob = problem.cyclical_problem(emb)
     n_tot = sum(c.shape[1] for c in prob.coords)
     try:
+        emb.b200_want_status = True
         poses = embeds.cyclical_embed(emb)
         constrained = emb.constrained_indices
     except ZeroCandidatesError:
@@ -103,6 +104,7 @@ def test_trimolecular_many_survivors_per_group(gpu):
     emb = make_embedder("cyclical", n_mols=3, n_conf=1, n_atoms=[60, 50, 55], seed=7, n_reactive=2, n_orb=1,
                         thresh=0.2)
     prob = problem.cyclical_problem(emb)
+    emb.b200_want_status = True
     poses = embeds.cyclical_embed(emb)
     rep = emb.b200_report
     ref = _check_problem(prob, poses, emb.constrained_indices, rep)
@@ -142,6 +144,7 @@ def test_trimolecular_c2_shaped_multi_conformer(gpu):
     kept indices in order, coordinates and constrained pairs."""
     emb = make_embedder("cyclical", n_mols=3, n_conf=3, n_atoms=60, seed=11, n_reactive=2, n_orb=1, thresh=0.9)
     prob = problem.cyclical_problem(emb)
+    emb.b200_want_status = True
     poses = embeds.cyclical_embed(emb)
     rep = emb.b200_report
     ref = _check_problem(prob, poses, emb.constrained_indices, rep)
