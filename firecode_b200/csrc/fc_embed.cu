@@ -221,34 +221,44 @@ __global__ void __launch_bounds__(256) tfd_vs_accepted_kernel(TfdArgs a, int b0,
     }
 }
 
-// all pairs INSIDE a block of 256 candidates, in parallel: bit t of simbits[i * 8 + (t >> 5)] is set iff rows
-// b0 + t and b0 + i (t > i) are similar.  Rows already rejected against earlier accepted rows are skipped.
+// all pairs INSIDE a block of kTfdBlock candidates, in parallel: bit t of simbits[i * kTfdWords + (t >> 5)] is set iff
+// rows b0 + t and b0 + i (t > i) are similar.  Rows already rejected against earlier accepted rows are skipped.
+constexpr int kTfdBlock = 1024;             // candidates per sweep step (the sweep is a chain of dependent launches:
+constexpr int kTfdWords = kTfdBlock / 32;   // C1 needs 11 steps with 1024 against 41 with 256)
+
 __global__ void __launch_bounds__(256) tfd_block_pairs_kernel(TfdArgs a, int b0, int b1, unsigned* __restrict__ simbits) {
     const int n = b1 - b0;
     const int total = n * (n - 1) / 2;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         // e -> (i, t) with i < t < n, row-major over the strict upper triangle
         int i = (int)((2.0f * n - 1.0f - sqrtf((2.0f * n - 1.0f) * (2.0f * n - 1.0f) - 8.0f * (float)e)) * 0.5f);
+        i = max(0, min(i, n - 2));
         while (i > 0 && (long long)i * (2 * n - i - 1) / 2 > e) --i;
         while ((long long)(i + 1) * (2 * n - i - 2) / 2 <= e) ++i;
         const int t = i + 1 + (e - i * (2 * n - i - 1) / 2);
         if (a.flag[b0 + i] || a.flag[b0 + t]) continue;
-        if (tfd_similar(a, b0 + t, b0 + i)) atomicOr(simbits + i * 8 + (t >> 5), 1u << (t & 31));
+        if (tfd_similar(a, b0 + t, b0 + i)) atomicOr(simbits + i * kTfdWords + (t >> 5), 1u << (t & 31));
     }
 }
 
-// ordered resolution inside the block from the pair bits: one warp, 256 steps of bit operations
-__global__ void __launch_bounds__(32) tfd_block_resolve_kernel(TfdArgs a, int b0, int b1, const unsigned* __restrict__ simbits) {
-    __shared__ unsigned s_bits[256 * 8];
-    const int lane = threadIdx.x;
+// ordered resolution inside the block from the pair bits: one warp, lane l owns the "still a candidate" bits of rows
+// 32 l .. 32 l + 31; n steps of bit operations on the bit matrix in shared memory
+__global__ void __launch_bounds__(256) tfd_block_resolve_kernel(TfdArgs a, int b0, int b1, const unsigned* __restrict__ simbits) {
+    extern __shared__ unsigned s_bits[];  // kTfdBlock * kTfdWords
     const int n = b1 - b0;
-    for (int w = lane; w < 256 * 8; w += 32) s_bits[w] = simbits[w];
-    unsigned alive = 0u;  // lanes 0..7: rows 32 * lane .. 32 * lane + 31 still candidates
-    if (lane < 8)
-        for (int k = 0; k < 32; ++k) {
-            const int r = 32 * lane + k;
-            if (r < n && a.flag[b0 + r] == 0) alive |= 1u << k;
-        }
+    {   // the whole CTA stages the bit matrix (128 KB); one warp then walks it
+        const uint4* src = reinterpret_cast<const uint4*>(simbits);
+        uint4* dst = reinterpret_cast<uint4*>(s_bits);
+        for (int w = threadIdx.x; w < n * kTfdWords / 4; w += blockDim.x) dst[w] = src[w];
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    unsigned alive = 0u;
+    for (int k = 0; k < 32; ++k) {
+        const int r = 32 * lane + k;
+        if (r < n && a.flag[b0 + r] == 0) alive |= 1u << k;
+    }
     __syncwarp();
     int n_acc = *a.n_acc;
     for (int i = 0; i < n; ++i) {
@@ -256,14 +266,13 @@ __global__ void __launch_bounds__(32) tfd_block_resolve_kernel(TfdArgs a, int b0
         if ((word >> (i & 31)) & 1u) {  // uniform: row b0 + i is accepted and rejects its similar later rows
             if (lane == 0) a.acc[n_acc] = b0 + i;
             ++n_acc;
-            if (lane < 8) alive &= ~s_bits[i * 8 + lane];
+            alive &= ~s_bits[i * kTfdWords + lane];
         }
     }
-    if (lane < 8)
-        for (int k = 0; k < 32; ++k) {
-            const int r = 32 * lane + k;
-            if (r < n) a.flag[b0 + r] = ((alive >> k) & 1u) ? 0 : 1;
-        }
+    for (int k = 0; k < 32; ++k) {
+        const int r = 32 * lane + k;
+        if (r < n) a.flag[b0 + r] = ((alive >> k) & 1u) ? 0 : 1;
+    }
     if (lane == 0) *a.n_acc = n_acc;
 }
 
@@ -273,16 +282,17 @@ int tfd_keepfirst_dev(const double* fp, const long long* label, int n, int q, do
     FC_CUDA(cudaMemsetAsync(flag, 0, (size_t)n * sizeof(int), s));
     FC_CUDA(cudaMemsetAsync(n_acc, 0, sizeof(int), s));
     unsigned* simbits = nullptr;
-    FC_CUDA(cudaMallocAsync((void**)&simbits, 256 * 8 * sizeof(unsigned), s));
+    const size_t bit_bytes = (size_t)kTfdBlock * kTfdWords * sizeof(unsigned);  // 128 KB
+    FC_CUDA(cudaMallocAsync((void**)&simbits, bit_bytes, s));
+    FC_CUDA(cudaFuncSetAttribute(tfd_block_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bit_bytes));
     TfdArgs a{fp, label, q, thr, eps, flag, acc, n_acc, ties, n_ties, tie_cap};
-    const int B = 256;
     const int grid = sm_count() * 8;
-    for (int b0 = 0; b0 < n; b0 += B) {
-        int b1 = std::min(n, b0 + B);
+    for (int b0 = 0; b0 < n; b0 += kTfdBlock) {
+        int b1 = std::min(n, b0 + kTfdBlock);
         if (b0 > 0) tfd_vs_accepted_kernel<<<grid, 256, 0, s>>>(a, b0, b1);
-        cudaMemsetAsync(simbits, 0, 256 * 8 * sizeof(unsigned), s);
-        if (b1 - b0 > 1) tfd_block_pairs_kernel<<<128, 256, 0, s>>>(a, b0, b1, simbits);
-        tfd_block_resolve_kernel<<<1, 32, 0, s>>>(a, b0, b1, simbits);
+        cudaMemsetAsync(simbits, 0, (size_t)(b1 - b0) * kTfdWords * sizeof(unsigned), s);
+        if (b1 - b0 > 1) tfd_block_pairs_kernel<<<sm_count() * 4, 256, 0, s>>>(a, b0, b1, simbits);
+        tfd_block_resolve_kernel<<<1, 256, bit_bytes, s>>>(a, b0, b1, simbits);
     }
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(simbits, s);
