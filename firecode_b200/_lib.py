@@ -94,6 +94,8 @@ SIGNATURES = {
     "fc_result_ties": (C.c_int64, [VP, VP, C.c_int64]),
     "fc_cyclical_screen": (C.c_int, [VP, C.POINTER(VP)]),
     "fc_cyclical3_screen": (C.c_int, [VP, C.POINTER(VP)]),
+    "fc_cyclical_groups": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP, VP, C.c_double, VP, C.c_int32, VP, C.c_int32, C.c_int64,
+                                     c_i64p, VP, VP, VP, VP, VP, VP]),
     "fc_result_groups": (C.c_int, [VP, VP, VP]),
     "fc_prune": (C.c_int, [VP, C.c_int64, C.c_int32, C.c_int32, VP, C.c_int32, VP, C.c_double, C.c_double,
                            C.c_double, VP, C.c_double, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP,

@@ -511,3 +511,78 @@ extern "C" int fc_cyclical_screen(const fc_cyclical_problem* p, fc_result** out)
     *out = r;
     return FC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Group table of the bimolecular cyclical embed, host only (no CUDA call): the reference's loops
+// embeds.py:596-641 -- conformer pairs (cartesian_product order: first index fastest), pivot pairs (first index
+// fastest), two orientations -- minus pivot pairs whose norms differ by more than max_norm_delta (embeds.py:624) and
+// arrangements that miss a user pairing (embeds.py:638-641; a pairing listed in `internal` counts as satisfied).
+// Pivot tables are CSR over conformers (rows off[c] .. off[c+1]).  Writes at most `cap` groups, returns the number
+// there are in *n_groups (call again with a larger cap if it exceeds it).
+// ------------------------------------------------------------------------------------------------
+extern "C" int fc_cyclical_groups(const int32_t* n_conf, const int64_t* off0, const double* vec0, const double* mean0,
+                                  const int64_t* ids0, const int64_t* off1, const double* vec1, const double* mean1,
+                                  const int64_t* ids1, double max_norm_delta, const int64_t* pairings, int32_t n_pairings,
+                                  const int64_t* internal, int32_t n_internal, int64_t cap, int64_t* n_groups,
+                                  int32_t* conf_out, double* pivot_out, double* mean_out, double* vecs_out, double* dirs_out,
+                                  int32_t* ids_out) {
+    FC_REQUIRE(n_conf && off0 && off1 && n_groups, "fc_cyclical_groups: null pointer");
+    FC_REQUIRE(cap == 0 || (conf_out && pivot_out && mean_out && vecs_out && dirs_out && ids_out), "fc_cyclical_groups: null output");
+    auto norm3 = [](const double* v) { return sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]); };  // np.linalg.norm(axis=1)
+    int64_t g = 0;
+    const int64_t n_cp = (int64_t)n_conf[0] * n_conf[1];
+    for (int64_t cp = 0; cp < n_cp; ++cp) {
+        const int64_t c0 = cp % n_conf[0], c1 = cp / n_conf[0];
+        const int64_t k0 = off0[c0 + 1] - off0[c0], k1 = off1[c1 + 1] - off1[c1];
+        for (int64_t p1 = 0; p1 < k1; ++p1)
+            for (int64_t p0 = 0; p0 < k0; ++p0) {
+                const int64_t r0 = off0[c0] + p0, r1 = off1[c1] + p1;
+                const double l0 = norm3(vec0 + 3 * r0), l1 = norm3(vec1 + 3 * r1);
+                if (fabs(l0 - l1) > max_norm_delta) continue;
+                for (int v = 0; v < 2; ++v) {
+                    // couples facing each other: swaps = [(0, 0), (0, 1)] (embeds.py:767)
+                    const int64_t a0 = ids0[2 * r0], a1 = ids0[2 * r0 + 1];
+                    const int64_t b0 = v ? ids1[2 * r1 + 1] : ids1[2 * r1], b1 = v ? ids1[2 * r1] : ids1[2 * r1 + 1];
+                    bool ok = true;
+                    for (int32_t q = 0; q < n_pairings && ok; ++q) {
+                        const int64_t pa = pairings[2 * q], pb = pairings[2 * q + 1];
+                        bool is_internal = false;
+                        for (int32_t t = 0; t < n_internal; ++t) is_internal = is_internal || (internal[2 * t] == pa && internal[2 * t + 1] == pb);
+                        if (is_internal) continue;
+                        ok = (a0 == pa && b0 == pb) || (a1 == pa && b1 == pb);
+                    }
+                    if (!ok) continue;
+                    if (g < cap) {
+                        conf_out[2 * g] = (int32_t)c0;
+                        conf_out[2 * g + 1] = (int32_t)c1;
+                        for (int k = 0; k < 3; ++k) {
+                            pivot_out[6 * g + k] = vec0[3 * r0 + k];
+                            pivot_out[6 * g + 3 + k] = vec1[3 * r1 + k];
+                            mean_out[6 * g + k] = mean0[3 * r0 + k];
+                            mean_out[6 * g + 3 + k] = mean1[3 * r1 + k];
+                        }
+                        // polygonize for two lengths (utils.py:262-271): centred collinear segments on x; the second
+                        // orientation multiplies segment 2 by -1 (its zeros become -0.0, as numpy's in-place product does)
+                        double* vv = vecs_out + 12 * g;
+                        for (int k = 0; k < 12; ++k) vv[k] = 0.0;
+                        vv[0] = -l0 / 2;
+                        vv[3] = l0 / 2;
+                        vv[6] = -l1 / 2;
+                        vv[9] = l1 / 2;
+                        if (v)
+                            for (int k = 6; k < 12; ++k) vv[k] *= -1.0;
+                        const double d[6] = {0.0, 1.0, 0.0, 0.0, -1.0, 0.0};
+                        for (int k = 0; k < 6; ++k) dirs_out[6 * g + k] = d[k];
+                        ids_out[4 * g] = (int32_t)a0;
+                        ids_out[4 * g + 1] = (int32_t)b0;
+                        ids_out[4 * g + 2] = (int32_t)a1;
+                        ids_out[4 * g + 3] = (int32_t)b1;
+                    }
+                    ++g;
+                }
+            }
+    }
+    *n_groups = g;
+    return FC_OK;
+}
+

@@ -201,86 +201,38 @@ def get_embed(mols, conf_ids):
 # ------------------------------------------------------------------------------------------------
 # cyclical embed (bimolecular path)
 # ------------------------------------------------------------------------------------------------
-_SWAPS2 = ((0, 0), (0, 1))
-
-
-def _cyclical_couples(pivot_ids, v):
-    """Atom couples facing each other for orientation v (embeds.py:753-772, two molecules)."""
-    o = [list(ids)[::-1] if _SWAPS2[v][i] else list(ids) for i, ids in enumerate(pivot_ids)]
-    return [(int(o[0][0]), int(o[1][0])), (int(o[0][1]), int(o[1][1]))]
-
-
-def _pairings_ok(prob, couples):
-    """User pairings must all appear in the active arrangement (embeds.py:638-641).  An ndarray
-    ``internal_constraints`` never matches (embeds.py:820-826)."""
-    if not prob.pairings:
-        return True
-    internal = [] if prob.internal_constraints_is_array else [tuple(x) for x in prob.internal_constraints]
-    return all((tuple(pair) in couples) or (tuple(pair) in internal) for pair in prob.pairings)
-
-
 def cyclical_groups(prob: problem.CyclicalProblem):
-    """Group table of the bimolecular cyclical embed in the reference's loop order
-    (embeds.py:596-641): conformer pairs (first index fastest) x pivot pairs (first index fastest) x
-    2 orientations, minus pivot pairs whose norms differ by more than max_norm_delta and arrangements
-    that miss a user pairing.  Vectorised over all groups (numpy); O(groups) memory."""
+    """Group table of the bimolecular cyclical embed in the reference's loop order (embeds.py:596-641): conformer
+    pairs (first index fastest) x pivot pairs (first index fastest) x 2 orientations, minus pivot pairs whose norms
+    differ by more than max_norm_delta and arrangements that miss a user pairing (an ndarray ``internal_constraints``
+    never matches: SURVEY.md quirk N10, embeds.py:820-826).  Enumerated by the library (C-ABI fc_cyclical_groups, host
+    code; the numpy version of round 1 took 24 of the 46 ms of a 2 x 50-conformer embed)."""
     assert prob.n_mols == 2
-    n_conf = [len(c) for c in prob.coords]
-    off, vec, mean, pid, norm = [], [], [], [], []
+    lib = _lib.load()
+    tabs = []
     for m in range(2):
         o, v = _csr(prob.pivot_vec[m], 3, np.float64)
         _, mp = _csr(prob.pivot_mean[m], 3, np.float64)
         _, ids = _csr(prob.pivot_ids[m], 2, np.int64)
-        off.append(o); vec.append(v); mean.append(mp); pid.append(ids)
-        # np.linalg.norm(axis=1): sqrt((x*x + y*y) + z*z)
-        norm.append(np.sqrt((v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2]))
-    # conformer pairs, first index fastest (cartesian_product of two ranges, quirk N1)
-    c0 = np.tile(np.arange(n_conf[0], dtype=np.int64), n_conf[1])
-    c1 = np.repeat(np.arange(n_conf[1], dtype=np.int64), n_conf[0])
-    k0 = (off[0][1:] - off[0][:-1])[c0]
-    k1 = (off[1][1:] - off[1][:-1])[c1]
-    per_pair = k0 * k1
-    total = int(per_pair.sum())
-    pair = np.repeat(np.arange(len(c0), dtype=np.int64), per_pair)
-    first = np.concatenate([[0], np.cumsum(per_pair)[:-1]])
-    q = np.arange(total, dtype=np.int64) - first[pair]
-    kk0 = np.maximum(k0[pair], 1)
-    p0, p1 = q % kk0, q // kk0                      # pivot pairs, first index fastest
-    r0, r1 = off[0][c0[pair]] + p0, off[1][c1[pair]] + p1
-    n0, n1 = norm[0][r0], norm[1][r1]
-    ok = ~(np.abs(n0 - n1) > prob.max_norm_delta)   # embeds.py:624
-    pair, r0, r1, n0, n1 = pair[ok], r0[ok], r1[ok], n0[ok], n1[ok]
-    g2 = len(pair)
-    # two orientations per surviving pivot pair, v fastest
-    rep = lambda x: np.repeat(x, 2, axis=0)  # noqa: E731
-    v = np.tile(np.array([0, 1]), g2)
-    pair, r0, r1, n0, n1 = rep(pair), rep(r0), rep(r1), rep(n0), rep(n1)
-    a0, a1 = pid[0][r0], pid[1][r1]                 # (G, 2) start / end cumnum
-    swap = v == 1                                   # swaps = [(0, 0), (0, 1)] (embeds.py:767)
-    b1 = np.where(swap[:, None], a1[:, ::-1], a1)
-    couples = np.stack([np.stack([a0[:, 0], b1[:, 0]], axis=1), np.stack([a0[:, 1], b1[:, 1]], axis=1)], axis=1)
-    if prob.pairings:
-        internal = [] if prob.internal_constraints_is_array else [tuple(x) for x in prob.internal_constraints]
-        keep = np.ones(len(v), dtype=bool)
-        for a, b in prob.pairings:
-            if (a, b) in internal:
-                continue
-            keep &= ((couples[:, 0, 0] == a) & (couples[:, 0, 1] == b)) | ((couples[:, 1, 0] == a) & (couples[:, 1, 1] == b))
-        pair, r0, r1, n0, n1, v, couples = pair[keep], r0[keep], r1[keep], n0[keep], n1[keep], v[keep], couples[keep]
-    g = len(v)
-    # polygonize for two lengths (utils.py:262-271): centred collinear segments, orientation 1 flips segment 2
-    vecs = np.zeros((g, 2, 2, 3))
-    vecs[:, 0, 0, 0], vecs[:, 0, 1, 0] = -n0 / 2, n0 / 2
-    vecs[:, 1, 0, 0], vecs[:, 1, 1, 0] = -n1 / 2, n1 / 2
-    vecs[v == 1, 1] *= -1
-    return {
-        "conf": np.ascontiguousarray(np.stack([c0[pair], c1[pair]], axis=1).astype(np.int32).reshape(g, 2)),
-        "pivot": np.ascontiguousarray(np.stack([vec[0][r0], vec[1][r1]], axis=1).reshape(g, 2, 3)),
-        "mean": np.ascontiguousarray(np.stack([mean[0][r0], mean[1][r1]], axis=1).reshape(g, 2, 3)),
-        "vecs": np.ascontiguousarray(vecs),
-        "dirs": np.ascontiguousarray(np.tile(np.array([[0.0, 1.0, 0.0], [0.0, -1.0, 0.0]]), (g, 1, 1))),
-        "ids": np.ascontiguousarray(couples.astype(np.int32).reshape(g, 2, 2)),
-    }
+        tabs.append((o, v, mp, ids))
+    n_conf = np.array([len(c) for c in prob.coords], dtype=np.int32)
+    pairings = np.ascontiguousarray(np.array(prob.pairings, dtype=np.int64).reshape(-1, 2))
+    internal = np.ascontiguousarray(np.array([] if prob.internal_constraints_is_array else prob.internal_constraints,
+                                             dtype=np.int64).reshape(-1, 2))
+    k0 = tabs[0][0][1:] - tabs[0][0][:-1]
+    k1 = tabs[1][0][1:] - tabs[1][0][:-1]
+    cap = 2 * int(k0.sum()) * int(k1.sum())      # every (pivot pair, orientation) of every conformer pair
+    out = {"conf": np.empty((cap, 2), dtype=np.int32), "pivot": np.empty((cap, 2, 3)), "mean": np.empty((cap, 2, 3)),
+           "vecs": np.empty((cap, 2, 2, 3)), "dirs": np.empty((cap, 2, 3)), "ids": np.empty((cap, 2, 2), dtype=np.int32)}
+    n_groups = C.c_int64(0)
+    rc = lib.fc_cyclical_groups(_ptr(n_conf), *(_ptr(t) for t in tabs[0]), *(_ptr(t) for t in tabs[1]),
+                                float(prob.max_norm_delta), _ptr(pairings), len(pairings), _ptr(internal), len(internal),
+                                cap, C.byref(n_groups), _ptr(out["conf"]), _ptr(out["pivot"]), _ptr(out["mean"]),
+                                _ptr(out["vecs"]), _ptr(out["dirs"]), _ptr(out["ids"]))
+    _lib.check(rc, "fc_cyclical_groups")
+    g = int(n_groups.value)
+    assert g <= cap
+    return {k: v[:g] for k, v in out.items()}
 
 
 def cyclical_screen(prob: problem.CyclicalProblem, rmsd_thresh=1.0, group_range=None, groups=None):

@@ -231,6 +231,20 @@ typedef struct fc_cyclical_problem {
 
 int fc_cyclical_screen(const fc_cyclical_problem* p, fc_result** out);
 
+/* Host only (no CUDA call): the group table fc_cyclical_screen consumes, enumerated in the reference's loop order
+ * (embeds.py:596-641): conformer pairs (first index fastest, utils.py:219-221), pivot pairs (first index fastest), two
+ * orientations; pivot pairs whose norms differ by more than max_norm_delta are dropped (embeds.py:624), and so are the
+ * arrangements that miss a user pairing (embeds.py:638-641; a pairing found in `internal` counts as satisfied).
+ *  n_conf[2]; per molecule m the pivot tables are CSR over its conformers: rows off_m[c] .. off_m[c+1] of
+ *  vec_m (rows, 3) Pivot.pivot, mean_m (rows, 3) Pivot.meanpoint, ids_m (rows, 2) start / end cumnum.
+ *  Writes at most cap groups into conf (G,2) pivot (G,2,3) mean (G,2,3) vecs (G,2,2,3) dirs (G,2,3) ids (G,2,2) and
+ *  returns their number in *n_groups (larger than cap: call again). */
+int fc_cyclical_groups(const int32_t* n_conf, const int64_t* off0, const double* vec0, const double* mean0,
+                       const int64_t* ids0, const int64_t* off1, const double* vec1, const double* mean1,
+                       const int64_t* ids1, double max_norm_delta, const int64_t* pairings, int32_t n_pairings,
+                       const int64_t* internal, int32_t n_internal, int64_t cap, int64_t* n_groups, int32_t* conf_out,
+                       double* pivot_out, double* mean_out, double* vecs_out, double* dirs_out, int32_t* ids_out);
+
 /* Cyclical embed, trimolecular body: replaces embeds.py:409-585 (`cyclical_embed` for three
  * molecules) including `_get_directions` (embeds.py:188-254) and the stateful 343-point grid search
  * `_adjust_directions` (embeds.py:256-407).  The library enumerates (conformer triple, pivot

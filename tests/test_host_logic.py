@@ -350,3 +350,41 @@ def test_vectorised_oracle_pruner_equals_the_loop_version():
         _, fast = ref_pruner.prune_by_rmsd_vectorised(structures, atoms, 0.5, row_block=64)
         assert np.array_equal(slow, fast), seed
         assert 0 < fast.sum() <= n
+
+
+def test_bimolecular_group_table_equals_the_oracle_enumeration():
+    """C-ABI fc_cyclical_groups (host code) against oracle.port.cyclical_groups_bimol: same groups in the same order,
+    with and without user pairings, with an internal constraint given as a list (matches) or as an ndarray (quirk N10:
+    never matches), and with the norm filter biting."""
+    from firecode_b200 import embeds, problem
+    from firecode_b200.synthetic_embedder import make_embedder
+    from oracle import port
+
+    emb = make_embedder("cyclical", [3, 2], [14, 11], seed=5, n_reactive=2, n_orb=2)
+    base = problem.cyclical_problem(emb)
+    ref0 = port.cyclical_groups_bimol(base)
+    assert len(ref0) > 8
+    couple = tuple(int(x) for x in ref0[1]["ids"][0])
+    other = tuple(int(x) for x in ref0[1]["ids"][1])
+    cases = [({}, np.array([]), 5.0), ({"a": couple}, np.array([]), 5.0), ({"a": couple, "b": (0, 1)}, [(0, 1)], 5.0),
+             ({"a": couple, "b": (0, 1)}, np.array([(0, 1)]), 5.0), ({"a": couple, "b": other}, np.array([]), 5.0),
+             ({}, np.array([]), 1e-3)]
+    for table, internal, delta in cases:
+        emb.pairings_table, emb.internal_constraints = table, internal
+        prob = problem.cyclical_problem(emb, max_norm_delta=delta)
+        got = embeds.cyclical_groups(prob)
+        ref = port.cyclical_groups_bimol(prob)
+        assert len(got["conf"]) == len(ref)
+        for g, r in enumerate(ref):
+            assert tuple(got["conf"][g]) == r["conf"]
+            assert [tuple(x) for x in got["ids"][g]] == [tuple(int(v) for v in c) for c in r["ids"]]
+            pv = [prob.pivot_vec[m][r["conf"][m]][r["piv"][m]] for m in range(2)]
+            pm = [prob.pivot_mean[m][r["conf"][m]][r["piv"][m]] for m in range(2)]
+            assert np.array_equal(got["pivot"][g], np.array(pv)) and np.array_equal(got["mean"][g], np.array(pm))
+            n0, n1 = r["norms"]
+            want = np.array([[[-n0 / 2, 0, 0], [n0 / 2, 0, 0]], [[-n1 / 2, 0, 0], [n1 / 2, 0, 0]]])
+            if r["v"] == 1:
+                want[1] *= -1
+            assert np.array_equal(got["vecs"][g], want)
+            assert np.array_equal(got["dirs"][g], [[0.0, 1.0, 0.0], [0.0, -1.0, 0.0]])
+    assert len(embeds.cyclical_groups(prob)["conf"]) < len(ref0)   # the last case: the norm filter dropped groups
