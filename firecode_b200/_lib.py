@@ -144,7 +144,7 @@ SIGNATURES = {
     "fc_self_clash_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_double, VP, VP]),
     "fc_structure_clash_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_int32, C.c_double, VP, VP]),
     "fc_fitness_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, VP, C.c_int32, VP]),
-    "fc_prune_plan": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, VP, C.c_int64,
+    "fc_prune_plan": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, VP, C.c_int64,
                                 VP, VP, C.c_int64, VP, VP]),
     "fc_prune_timing": (C.c_int, [VP]),
     "fc_kabsch_host": (C.c_int, [VP, VP, VP]),

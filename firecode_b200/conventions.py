@@ -8,6 +8,7 @@ TORSION_AXIS_SIGN = +1     # rotate_dihedral axis = sign * (coords[i2] - coords[
 PRUNE_KEEP = "first"       # which member of a similar pair survives
 PRUNE_PASS_MODE = "greedy"  # "greedy" (mask updated in place) or "snapshot" (mask read at pass start)
 PRUNE_MIN_PER_CHUNK = 20
+PRUNE_CHUNK_OVER = "full"   # a pass cuts the "full" array in k chunks of n // k structures, or the "active" structures in k chunks of n_active // k
 PRUNE_RMSD_HEAVY_ONLY = True
 PRUNE_MAXDEV_FACTOR = 2.0
 MOI_MAX_DEVIATION = 1e-2

@@ -500,19 +500,49 @@ static int64_t gram_item_pairs(int64_t row0, int64_t col_lo, int64_t col_hi, int
 // structures all shared the previous chunk of the block's first row -- a prefix of the block's column range -- are
 // left out.  Column ranges are cut into work items so that every SM gets several of similar size; item i goes to rank
 // i % world.  Adds to pairs_tiled (pairs this rank evaluates) and pairs_skipped (pairs no rank evaluates).
-static void plan_gram_pass(const std::vector<uint8_t>& mask, int64_t n, int64_t k, int64_t prev_size, int64_t prev_k, int world,
+// Chunk boundaries (k + 1 structure indices) of a pass.  "Full": k chunks of n / k consecutive STRUCTURES, the last takes
+// the rest -- what the oracle shim and FIRECODE's in-tree sibling driver do (torsion_module.py:973-1041).  "Active": k
+// chunks of n_active / k consecutive ACTIVE structures (SURVEY.md 8c's wording of the prism_pruner contract); as index
+// ranges: chunk c starts at the (c * size)-th active structure.  Which one prism_pruner 0.0.7 uses is unpinned:
+// conventions.PRUNE_CHUNK_OVER.
+static std::vector<int64_t> chunk_bounds(const std::vector<uint8_t>& mask, int64_t n, int64_t k, bool over_active) {
+    std::vector<int64_t> b((size_t)k + 1, n);
+    if (!over_active) {
+        const int64_t size = n / k;
+        for (int64_t c = 0; c < k; ++c) b[(size_t)c] = c * size;
+        return b;
+    }
+    int64_t n_active = 0;
+    for (uint8_t m : mask) n_active += m ? 1 : 0;
+    const int64_t size = std::max<int64_t>(1, n_active / k);
+    int64_t seen = 0, c = 0;
+    b[0] = 0;
+    for (int64_t i = 0; i < n && c + 1 < k; ++i) {
+        if (!mask[(size_t)i]) continue;
+        if (seen == (c + 1) * size) b[(size_t)++c] = i;
+        ++seen;
+    }
+    // chunks that found no active structure to start at stay empty ([n, n))
+    return b;
+}
+
+static inline int64_t chunk_of(const std::vector<int64_t>& bounds, int64_t idx) {
+    return (int64_t)(std::upper_bound(bounds.begin(), bounds.end() - 1, idx) - bounds.begin()) - 1;
+}
+
+static void plan_gram_pass(const std::vector<uint8_t>& mask, int64_t n, const std::vector<int64_t>& bounds,
+                           const std::vector<int64_t>& prev_bounds, int world,
                            int rank, int n_sms, std::vector<int>& spos, std::vector<GramWork>& work, int64_t& pairs_tiled,
                            int64_t& pairs_skipped) {
     struct RowBlock { int row0, c_min, tile_end, pend; };
     std::vector<RowBlock> blocks;
+    const int64_t k = (int64_t)bounds.size() - 1;
     spos.clear();
     spos.reserve((size_t)n + 16 * (size_t)k + 256);
     work.clear();
-    const int64_t size = n / k;
-    auto prev_chunk = [&](int idx) { return std::min<int64_t>((int64_t)idx / prev_size, prev_k - 1); };
     int64_t col_tiles_total = 0;
     for (int64_t c = 0; c < k; ++c) {
-        const int64_t first = c * size, last = (c == k - 1) ? n : size * (c + 1);
+        const int64_t first = bounds[(size_t)c], last = bounds[(size_t)c + 1];
         while (spos.size() % 16) spos.push_back(-1);
         const int pbegin = (int)spos.size();
         for (int64_t i = first; i < last; ++i)
@@ -523,11 +553,11 @@ static void plan_gram_pass(const std::vector<uint8_t>& mask, int64_t n, int64_t 
         int64_t evaluated = 0;
         for (int row0 = pbegin; row0 < pend - 1; row0 += 128) {
             int c_min = row0 / 16;
-            if (prev_size > 0) {
+            if (!prev_bounds.empty()) {
                 // first position of the chunk whose structure lies beyond the previous-pass chunk of the block's first
                 // row: a tile is known dissimilar iff its last structure comes before that position
-                const int64_t pc = prev_chunk(spos[(size_t)row0]);
-                const int64_t idx_end = pc == prev_k - 1 ? n : (pc + 1) * prev_size;
+                const int64_t pc = chunk_of(prev_bounds, spos[(size_t)row0]);
+                const int64_t idx_end = prev_bounds[(size_t)pc + 1];
                 const int pos_e = (int)(std::lower_bound(spos.begin() + row0, spos.begin() + pend, idx_end,
                                                          [](int v, int64_t lim) { return (int64_t)v < lim; }) -
                                         spos.begin());
@@ -560,8 +590,8 @@ static void plan_gram_pass(const std::vector<uint8_t>& mask, int64_t n, int64_t 
 
 // Host-only view of plan_gram_pass for the tests (no CUDA call): positions and work items of one pass.
 extern "C" int fc_prune_plan(const uint8_t* mask, int64_t n, int64_t k, int64_t prev_k, int32_t world, int32_t rank, int32_t n_sms,
-                             int32_t* spos_out, int64_t spos_cap, int64_t* n_spos, int32_t* work_out, int64_t work_cap,
-                             int64_t* n_work, int64_t* counts_out) {
+                             int32_t chunk_over_active, int32_t* spos_out, int64_t spos_cap, int64_t* n_spos, int32_t* work_out,
+                             int64_t work_cap, int64_t* n_work, int64_t* counts_out) {
     FC_REQUIRE(mask && n > 0 && k >= 1 && k <= n && prev_k >= 0 && prev_k <= n && world >= 1 && rank >= 0 && rank < world && n_sms >= 1,
                "fc_prune_plan: bad arguments");
     FC_REQUIRE(n_spos && n_work && counts_out, "fc_prune_plan: null pointer");
@@ -569,7 +599,10 @@ extern "C" int fc_prune_plan(const uint8_t* mask, int64_t n, int64_t k, int64_t 
     std::vector<int> spos;
     std::vector<GramWork> work;
     int64_t tiled = 0, skipped = 0;
-    plan_gram_pass(m, n, k, prev_k ? n / prev_k : 0, prev_k, world, rank, n_sms, spos, work, tiled, skipped);
+    // the previous pass is planned on the same mask here (the hook has no history): enough to test the coverage property
+    const std::vector<int64_t> bounds = chunk_bounds(m, n, k, chunk_over_active != 0);
+    const std::vector<int64_t> prev = prev_k ? chunk_bounds(m, n, prev_k, chunk_over_active != 0) : std::vector<int64_t>();
+    plan_gram_pass(m, n, bounds, prev, world, rank, n_sms, spos, work, tiled, skipped);
     *n_spos = (int64_t)spos.size();
     *n_work = (int64_t)work.size();
     counts_out[0] = tiled;
@@ -687,7 +720,9 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
         std::vector<int> active;
         std::vector<PruneTile> tiles;
         std::vector<int2> pairs, all_pairs;
-        int64_t prev_size = 0, prev_k = 0;  // chunking of the last executed pass
+        std::vector<int64_t> prev_bounds;  // chunking of the last executed pass (empty: none yet)
+        const bool over_active = (snapshot & 2) != 0;  // FC_PRUNE_CHUNK_ACTIVE
+        snapshot &= 1;
         // screen flavour: FC_PRUNE_FP64=1 -> FP64 pair kernel only; otherwise FP32 screen + FP64 exact stage, the screen
         // on the tensor cores (gram_tc_kernel) unless FC_PRUNE_TC=0 or the molecule has more than 88 selected atoms (kGramMaxKc)
         const char* env64 = getenv("FC_PRUNE_FP64");
@@ -710,16 +745,16 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
             if (!(k == 1 || (int64_t)min_per_chunk * k < n_active)) continue;
             ++passes;
             double tp = now();
-            const int64_t size = n / k;
+            const std::vector<int64_t> bounds = chunk_bounds(mask, n, k, over_active);
             if (use_tc) {
-                plan_gram_pass(mask, n, k, prev_size, prev_k, world, rank, sm_count(), spos, work, pairs_tiled, pairs_skipped);
+                plan_gram_pass(mask, n, bounds, prev_bounds, world, rank, sm_count(), spos, work, pairs_tiled, pairs_skipped);
             } else {
                 // compacted active list + chunks over the FULL array (chunk size n // k, last takes the rest)
                 active.clear();
                 tiles.clear();
                 int64_t tile_no = 0;
                 for (int64_t c = 0; c < k; ++c) {
-                    int64_t first = c * size, last = (c == k - 1) ? n : size * (c + 1);
+                    int64_t first = bounds[(size_t)c], last = bounds[(size_t)c + 1];
                     int begin = (int)active.size();
                     for (int64_t i = first; i < last; ++i)
                         if (mask[(size_t)i]) active.push_back((int)i);
@@ -730,10 +765,9 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                             const int rows = std::min(PR_TS, len - r0), cols = std::min(PR_TS, len - c0);
                             const int64_t tile_pairs = r0 == c0 ? (int64_t)rows * (rows - 1) / 2 : (int64_t)rows * cols;
                             // survivors that shared a chunk in an earlier pass are known to be dissimilar
-                            if (prev_size > 0) {
+                            if (!prev_bounds.empty()) {
                                 const int64_t lo_idx = active[(size_t)(begin + r0)], hi_idx = active[(size_t)(begin + c0 + cols - 1)];
-                                const int64_t ca = std::min(lo_idx / prev_size, prev_k - 1), cb = std::min(hi_idx / prev_size, prev_k - 1);
-                                if (ca == cb) { pairs_skipped += tile_pairs; continue; }
+                                if (chunk_of(prev_bounds, lo_idx) == chunk_of(prev_bounds, hi_idx)) { pairs_skipped += tile_pairs; continue; }
                             }
                             if (tile_no++ % world != rank) continue;
                             pairs_tiled += tile_pairs;
@@ -741,8 +775,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                         }
                 }
             }
-            prev_size = size;
-            prev_k = k;
+            prev_bounds = bounds;
             pairs.clear();
             t_tiles += now() - tp;
             tp = now();

@@ -41,15 +41,28 @@ class PruneReport:
 last_report: PruneReport | None = None
 
 
+def _chunk_bounds(mask, k, chunk_over):
+    """Index ranges [(first, last)] of the k chunks of a pass (conventions.PRUNE_CHUNK_OVER)."""
+    n = len(mask)
+    if chunk_over == "full":
+        size = n // k
+        return [(c * size, n if c == k - 1 else size * (c + 1)) for c in range(k)]
+    act = np.flatnonzero(mask)
+    size = max(1, len(act) // k)
+    starts = [0] + [int(act[c * size]) if c * size < len(act) else n for c in range(1, k)]
+    return [(starts[c], starts[c + 1] if c + 1 < k else n) for c in range(k)]
+
+
 def _run(structures, mode, sel, masses, max_rmsd, max_dev, moi_dev, energies, max_dE, keep, pass_mode,
-         tie_cap=1 << 16, shard=None):
+         tie_cap=1 << 16, shard=None, chunk_over=None):
     """``shard`` = (rank, world, allgather) runs the multi-GPU form: allgather(bytes ndarray) must
     return the rank-order concatenation of every rank's buffer (firecode_b200.dist supplies it)."""
     global last_report
     lib = _lib.load(require_device=True)
     keep = conventions.PRUNE_KEEP if keep is None else keep
     pass_mode = conventions.PRUNE_PASS_MODE if pass_mode is None else pass_mode
-    assert keep in ("first", "last") and pass_mode in ("greedy", "snapshot")
+    chunk_over = conventions.PRUNE_CHUNK_OVER if chunk_over is None else chunk_over
+    assert keep in ("first", "last") and pass_mode in ("greedy", "snapshot") and chunk_over in ("full", "active")
     x = np.ascontiguousarray(np.asarray(structures, dtype=np.float64))
     assert x.ndim == 3 and x.shape[2] == 3
     n, n_atoms = x.shape[:2]
@@ -64,7 +77,8 @@ def _run(structures, mode, sel, masses, max_rmsd, max_dev, moi_dev, energies, ma
         assert len(e_arr) == n
     args = (_ptr(x), n, n_atoms, mode, _ptr(sel_arr), 0 if sel_arr is None else len(sel_arr),
             _ptr(mass_arr), float(max_rmsd), float(max_dev), float(moi_dev), _ptr(e_arr),
-            float(max_dE), 1 if keep == "first" else 0, 1 if pass_mode == "snapshot" else 0,
+            float(max_dE), 1 if keep == "first" else 0,
+            (1 if pass_mode == "snapshot" else 0) | (2 if chunk_over == "active" else 0),
             int(conventions.PRUNE_MIN_PER_CHUNK), _ptr(mask), _ptr(stats), _ptr(ties), tie_cap, C.byref(n_ties))
     if shard is None:
         rc = lib.fc_prune(*args)
@@ -114,7 +128,7 @@ def _take(lib, x, mask):
 
 
 def prune_by_rmsd(structures, atoms, max_rmsd=0.25, max_dev=None, energies=None, max_dE=0.0,
-                  debugfunction=None, logfunction=None, keep=None, pass_mode=None, shard=None):
+                  debugfunction=None, logfunction=None, keep=None, pass_mode=None, shard=None, chunk_over=None):
     """Heavy-atom, centred Kabsch RMSD pruning: a structure is dropped when a kept one has
     rmsd < max_rmsd and max atomic deviation < max_dev (default 2 * max_rmsd)."""
     atoms = np.asarray(atoms)
@@ -123,19 +137,22 @@ def prune_by_rmsd(structures, atoms, max_rmsd=0.25, max_dev=None, energies=None,
         sel = np.flatnonzero(np.array([str(a) != "H" for a in atoms]))
     else:
         sel = np.arange(len(atoms))
-    out, mask = _run(structures, 0, sel, None, max_rmsd, max_dev, 0.0, energies, max_dE, keep, pass_mode, shard=shard)
+    out, mask = _run(structures, 0, sel, None, max_rmsd, max_dev, 0.0, energies, max_dE, keep, pass_mode, shard=shard,
+                     chunk_over=chunk_over)
     if debugfunction is not None:
         debugfunction(f"DEBUG: prune_by_rmsd (firecode_b200) - kept {int(mask.sum())}/{len(mask)}")
     return out, mask
 
 
 def prune_by_moment_of_inertia(structures, atoms, max_deviation=None, energies=None, max_dE=0.0,
-                               debugfunction=None, logfunction=None, keep=None, pass_mode=None, shard=None):
+                               debugfunction=None, logfunction=None, keep=None, pass_mode=None, shard=None,
+                               chunk_over=None):
     """Drop structures whose three principal moments of inertia are all within ``max_deviation``
     (relative, default 1 %) of a kept structure (CHANGELOG.md:256)."""
     max_deviation = conventions.MOI_MAX_DEVIATION if max_deviation is None else max_deviation
     masses = np.array([MASSES[str(a)] for a in np.asarray(atoms)])
-    out, mask = _run(structures, 1, None, masses, 0.0, 0.0, max_deviation, energies, max_dE, keep, pass_mode, shard=shard)
+    out, mask = _run(structures, 1, None, masses, 0.0, 0.0, max_deviation, energies, max_dE, keep, pass_mode, shard=shard,
+                     chunk_over=chunk_over)
     if debugfunction is not None:
         debugfunction(f"DEBUG: prune_by_moment_of_inertia (firecode_b200) - kept {int(mask.sum())}/{len(mask)}")
     return out, mask
@@ -217,7 +234,7 @@ def rmsd_and_max_rot_corr_pairs(structures, atoms, pairs, torsions, angles, mask
 
 def prune_by_rmsd_rot_corr(structures, atoms, graph, max_rmsd=0.25, max_dev=None, energies=None,
                            max_dE=0.0, logfunction=None, debugfunction=None, keep=None, pass_mode=None,
-                           torsions=None, angles=None, masks=None):
+                           torsions=None, angles=None, masks=None, chunk_over=None):
     """Symmetry-corrected RMSD pruning (embedder.py:1485-1496, ensemble.py:253, operators.py:626): structures that
     differ only by a rotation of a locally symmetric group (methyl, tert-butyl, CF3, phenyl ...) count as similar.
     The pair distance is the symmetry-corrected RMSD of fc_rmsd_rot_corr_pairs, evaluated on the GPU for every
@@ -227,7 +244,8 @@ def prune_by_rmsd_rot_corr(structures, atoms, graph, max_rmsd=0.25, max_dev=None
     global last_rot_corr_report
     keep = conventions.PRUNE_KEEP if keep is None else keep
     pass_mode = conventions.PRUNE_PASS_MODE if pass_mode is None else pass_mode
-    assert keep in ("first", "last") and pass_mode in ("greedy", "snapshot")
+    chunk_over = conventions.PRUNE_CHUNK_OVER if chunk_over is None else chunk_over
+    assert keep in ("first", "last") and pass_mode in ("greedy", "snapshot") and chunk_over in ("full", "active")
     x = np.ascontiguousarray(np.asarray(structures, dtype=np.float64))
     n = len(x)
     max_dev = conventions.PRUNE_MAXDEV_FACTOR * max_rmsd if max_dev is None else max_dev
@@ -247,8 +265,7 @@ def prune_by_rmsd_rot_corr(structures, atoms, graph, max_rmsd=0.25, max_dev=None
         if not (k == 1 or conventions.PRUNE_MIN_PER_CHUNK * k < active):
             continue
         rep.passes += 1
-        size = n // k
-        bounds = [(c * size, n if c == k - 1 else size * (c + 1)) for c in range(k)]
+        bounds = _chunk_bounds(mask, k, chunk_over)
         # every pair of structures active at the start of the pass, chunk by chunk, in one GPU call
         blocks = []
         for first, last in bounds:
@@ -299,7 +316,7 @@ def prune_by_rmsd_rot_corr(structures, atoms, graph, max_rmsd=0.25, max_dev=None
     return _take(lib, x, mask), mask
 
 
-_PRUNE_KW = ("energies", "max_dE", "keep", "pass_mode", "shard")
+_PRUNE_KW = ("energies", "max_dE", "keep", "pass_mode", "shard", "chunk_over")
 
 
 def prune(structures, atoms, max_rmsd=0.25, logfunction=None, debugfunction=None, max_dev=None, max_deviation=None,

@@ -285,7 +285,9 @@ int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** out);
  * a pass runs when k == 1 or min_per_chunk * k < active structures; chunks of n / k structures).
  *  structures (n, n_atoms, 3) f64 host;  sel (n_sel) atoms entering the RMSD (heavy atoms);
  *  masses (n_atoms) for mode 1;  energies (n) or NULL: pairs with |dE| >= max_dE are not compared;
- *  keep_first / snapshot: the two unpinned prism_pruner conventions;
+ *  keep_first / snapshot: the unpinned prism_pruner conventions; `snapshot` is a flag word: bit 0
+ *  (FC_PRUNE_SNAPSHOT) a pass reads the mask as it was when the pass started, bit 1 (FC_PRUNE_CHUNK_ACTIVE) the k
+ *  chunks of a pass hold n_active / k consecutive ACTIVE structures instead of n / k consecutive structures;
  *  mask_out (n) 1 = kept;  stats_out[4] = {passes, pairs whose covariance was accumulated, pairs
  *  eigen-solved, pairs skipped because both structures survived an earlier pass in the same chunk
  *  (such survivors are mutually dissimilar by construction)}.  Similar pairs are collected in a
@@ -293,6 +295,8 @@ int fc_cyclical3_screen(const fc_cyclical3_problem* p, fc_result** out);
  *  Mode 0 screens the pairs on the tensor cores (TF32 Gram matrix of the centred coordinates, rigorous
  *  rounding band) when n_sel <= 88 and on the FP32 CUDA cores otherwise; every pair a screen cannot rule
  *  out is decided in FP64, so mask_out does not depend on the screen. */
+#define FC_PRUNE_SNAPSHOT 1
+#define FC_PRUNE_CHUNK_ACTIVE 2
 int fc_prune(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
              int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
              const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
@@ -403,8 +407,8 @@ int fc_kabsch_host(const double* h, double* r_out, double* sig_out);
  * Test hook for the planner (tests/test_host_logic.py); sizes come back in n_spos / n_work also when the buffers
  * are too small. */
 int fc_prune_plan(const uint8_t* mask, int64_t n, int64_t k, int64_t prev_k, int32_t world, int32_t rank, int32_t n_sms,
-                  int32_t* spos_out, int64_t spos_cap, int64_t* n_spos, int32_t* work_out, int64_t work_cap,
-                  int64_t* n_work, int64_t* counts_out);
+                  int32_t chunk_over_active, int32_t* spos_out, int64_t spos_cap, int64_t* n_spos, int32_t* work_out,
+                  int64_t work_cap, int64_t* n_work, int64_t* counts_out);
 
 /* Timing of the last fc_prune / fc_prune_sharded call on this thread (bench.py's roofline of the tensor-core
  * screen): out6 = {wall ms of the call, CUDA-event ms summed over the screen kernel launches, launches,

@@ -19,6 +19,7 @@ PRUNE_PASS_MODE = "greedy"
 
 # prune(): minimum average number of active structures per chunk for a k-pass to run.
 PRUNE_MIN_PER_CHUNK = 20
+PRUNE_CHUNK_OVER = "full"   # a pass cuts the "full" array in k chunks of n // k structures, or the "active" structures in k chunks of n_active // k
 
 # prune_by_rmsd(): heavy atoms only, centred Kabsch, max deviation default = 2 * max_rmsd
 PRUNE_RMSD_HEAVY_ONLY = True

@@ -36,6 +36,16 @@ def chunk_bounds(n, k):
     return out
 
 
+def chunk_bounds_active(mask, k):
+    """[(first, last)] index ranges of k chunks holding n_active // k consecutive ACTIVE structures each (the last takes
+    the rest): the other reading of the driver ("split the active structures"), conventions.PRUNE_CHUNK_OVER."""
+    n = len(mask)
+    act = np.flatnonzero(mask)
+    size = max(1, len(act) // int(k))
+    starts = [0] + [int(act[c * size]) if c * size < len(act) else n for c in range(1, int(k))]
+    return [(starts[c], starts[c + 1] if c + 1 < int(k) else n) for c in range(int(k))]
+
+
 class PruneStats:
     def __init__(self):
         self.eval_calls = 0
@@ -44,12 +54,13 @@ class PruneStats:
 
 
 def prune_mask(n, evaluate_sim, energies=None, max_dE=0.0, keep=None, pass_mode=None,
-               min_per_chunk=None, stats=None):
+               min_per_chunk=None, stats=None, chunk_over=None):
     """Run the multi-pass chunked pruning driver over n structures and return the bool mask."""
     keep = conventions.PRUNE_KEEP if keep is None else keep
     pass_mode = conventions.PRUNE_PASS_MODE if pass_mode is None else pass_mode
     min_per_chunk = conventions.PRUNE_MIN_PER_CHUNK if min_per_chunk is None else min_per_chunk
-    assert keep in ("first", "last") and pass_mode in ("greedy", "snapshot")
+    chunk_over = conventions.PRUNE_CHUNK_OVER if chunk_over is None else chunk_over
+    assert keep in ("first", "last") and pass_mode in ("greedy", "snapshot") and chunk_over in ("full", "active")
     use_e = energies is not None
     if use_e:
         energies = np.asarray(energies, dtype=float)
@@ -80,7 +91,7 @@ def prune_mask(n, evaluate_sim, energies=None, max_dE=0.0, keep=None, pass_mode=
             stats.passes.append((k, active))
         in_mask = mask.copy() if pass_mode == "snapshot" else mask
         out_mask = mask.copy() if pass_mode == "snapshot" else mask
-        for first, last in chunk_bounds(n, k):
+        for first, last in (chunk_bounds(n, k) if chunk_over == "full" else chunk_bounds_active(mask, k)):
             order = range(first, last) if keep == "first" else range(last - 1, first - 1, -1)
             if pass_mode == "greedy":
                 # NMS sweep: a structure that is still active drops every later (keep-first) /

@@ -195,7 +195,7 @@ def test_write_xyz_equals_live_reference():
         assert a.getvalue() == b.getvalue()
 
 
-def _plan(mask, k, prev_k, world=1, rank=0, n_sms=4):
+def _plan(mask, k, prev_k, world=1, rank=0, n_sms=4, over_active=False):
     import ctypes as C
 
     from firecode_b200 import _lib
@@ -207,27 +207,36 @@ def _plan(mask, k, prev_k, world=1, rank=0, n_sms=4):
     work = np.zeros((n * 4 + 4096, 4), dtype=np.int32)
     n_spos, n_work = C.c_int64(0), C.c_int64(0)
     counts = np.zeros(2, dtype=np.int64)
-    rc = lib.fc_prune_plan(m8.ctypes.data, n, k, prev_k, world, rank, n_sms, spos.ctypes.data, len(spos), C.byref(n_spos),
-                           work.ctypes.data, len(work), C.byref(n_work), counts.ctypes.data)
+    rc = lib.fc_prune_plan(m8.ctypes.data, n, k, prev_k, world, rank, n_sms, 1 if over_active else 0, spos.ctypes.data, len(spos),
+                           C.byref(n_spos), work.ctypes.data, len(work), C.byref(n_work), counts.ctypes.data)
     assert rc == 0, lib.fc_last_error()
     return spos[: n_spos.value], work[: n_work.value], counts
 
 
+@pytest.mark.parametrize("over_active", [False, True])
 @pytest.mark.parametrize("n,k,prev_k,world", [(700, 1, 0, 1), (700, 1, 2, 1), (3000, 5, 10, 3), (3000, 2, 5, 2),
                                               (2500, 10, 20, 1), (1000, 1, 2, 8), (333, 3, 0, 2)])
-def test_prune_planner_covers_every_unknown_pair_once(n, k, prev_k, world):
+def test_prune_planner_covers_every_unknown_pair_once(n, k, prev_k, world, over_active):
     """The work items of the tensor-core screen (row block x column-tile range, dealt to the ranks) must cover every
     pair of active structures of a chunk exactly once, except pairs whose two members shared a chunk of the
     previous pass (known dissimilar), which may be left out -- and nothing else may be left out."""
     rng = np.random.default_rng(n + k)
     mask = rng.random(n) < 0.6
-    size = n // k
-    chunk_of = np.minimum(np.arange(n) // size, k - 1)
-    prev_of = np.minimum(np.arange(n) // (n // prev_k), prev_k - 1) if prev_k else None
+    def membership(kk):
+        """chunk of every structure: kk chunks of n // kk structures, or of n_active // kk ACTIVE structures"""
+        if not over_active:
+            return np.minimum(np.arange(n) // (n // kk), kk - 1)
+        act_idx = np.flatnonzero(mask)
+        sz = max(1, len(act_idx) // kk)
+        starts = np.array([0] + [act_idx[c * sz] if c * sz < len(act_idx) else n for c in range(1, kk)])
+        return np.searchsorted(starts, np.arange(n), side="right") - 1
+
+    chunk_of = membership(k)
+    prev_of = membership(prev_k) if prev_k else None
     covered = {}
     tiled_total = 0
     for rank in range(world):
-        spos, work, counts = _plan(mask, k, prev_k, world, rank)
+        spos, work, counts = _plan(mask, k, prev_k, world, rank, over_active=over_active)
         tiled_total += int(counts[0])
         # position list: chunks start at multiples of 16, hold their active structures in order, -1 elsewhere
         pos_active = np.flatnonzero(spos >= 0)

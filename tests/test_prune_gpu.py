@@ -36,6 +36,29 @@ def test_prune_by_rmsd_matches_oracle(gpu, keep, pass_mode, n, n_atoms, n_basins
     assert 1 < mask.sum() < n  # both similar and dissimilar pairs exist
 
 
+@pytest.mark.parametrize("keep,pass_mode", [("first", "greedy"), ("last", "snapshot")])
+def test_prune_chunks_over_active_structures(gpu, keep, pass_mode):
+    """The fifth unpinned convention: a pass may cut the ACTIVE structures in k chunks instead of the full
+    array (conventions.PRUNE_CHUNK_OVER = "active").  Both sides carry the switch; the kept sets agree for either setting
+    and differ between the settings on an ensemble with several passes."""
+    rng = np.random.default_rng(4242)
+    atoms, structures, _ = synthetic.pruning_ensemble(rng, 2600, 16, 90, jitter=(0.02, 0.35))
+    masks = {}
+    for chunk_over in ("full", "active"):
+        _, mask = pruner.prune_by_rmsd(structures, atoms, 0.4, keep=keep, pass_mode=pass_mode, chunk_over=chunk_over)
+        assert pruner.last_report.passes >= 4
+        ties = port.Ties(eps=1e-6, forced=_forced(pruner.last_report))
+        _, ref_mask = ref_pruner.prune_by_rmsd(structures, atoms, 0.4, ties=ties, keep=keep, pass_mode=pass_mode,
+                                               chunk_over=chunk_over)
+        assert np.array_equal(mask, ref_mask), chunk_over
+        masks[chunk_over] = mask
+        _, moi = pruner.prune_by_moment_of_inertia(structures, atoms, keep=keep, pass_mode=pass_mode, chunk_over=chunk_over)
+        _, ref_moi = ref_pruner.prune_by_moment_of_inertia(structures, atoms, keep=keep, pass_mode=pass_mode,
+                                                           chunk_over=chunk_over)
+        assert np.array_equal(moi, ref_moi), chunk_over
+    assert 1 < masks["full"].sum() < len(structures)
+
+
 def test_prune_with_energies_and_multipass(gpu):
     """Enough structures for several chunked passes (20 * k < active) and an energy window."""
     rng = np.random.default_rng(99)
