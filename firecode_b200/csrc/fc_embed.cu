@@ -14,7 +14,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
+
+#include <cooperative_groups.h>
 
 #include "fc_embed.cuh"
 
@@ -138,6 +141,13 @@ __global__ void tfd_fingerprint_kernel(StringDev p, const long long* __restrict_
     fp[i] = dihedral_deg(pt[0], pt[1], pt[2], pt[3]);
 }
 
+// out[i] = table[idx[i]]
+__global__ void gather_index_kernel(const long long* __restrict__ table, const int* __restrict__ idx, int n,
+                                    long long* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = table[idx[i]];
+}
+
 __global__ void string_materialize_kernel(StringDev p, const long long* __restrict__ kept, int n_kept,
                                           double* __restrict__ out) {
     int k = blockIdx.x;
@@ -221,59 +231,184 @@ __global__ void __launch_bounds__(256) tfd_vs_accepted_kernel(TfdArgs a, int b0,
     }
 }
 
-// all pairs INSIDE a block of kTfdBlock candidates, in parallel: bit t of simbits[i * kTfdWords + (t >> 5)] is set iff
-// rows b0 + t and b0 + i (t > i) are similar.  Rows already rejected against earlier accepted rows are skipped.
-constexpr int kTfdBlock = 1024;             // candidates per sweep step (the sweep is a chain of dependent launches:
-constexpr int kTfdWords = kTfdBlock / 32;   // C1 needs 11 steps with 1024 against 41 with 256)
+// ---- sweep inside a block of candidates ------------------------------------------------------------
+// The keep-first rule is the lexicographically first maximal independent set of the similarity graph: row t is accepted
+// iff no EARLIER accepted row is similar to it.  Instead of walking the rows one by one (a chain of n dependent steps),
+// all pairs of a block are evaluated at once into a bit matrix (tfd_block_matrix_kernel: bit i of word i / 32 of row t
+// says "t is similar to the earlier row i") and the rule is resolved by rounds over the whole block
+// (tfd_block_resolve_kernel, one cooperative launch): an undecided row is REJECTED as soon as a similar earlier row is
+// accepted and ACCEPTED once every similar earlier row is rejected; both verdicts are final, the lowest undecided row
+// can always be decided, and the number of rounds is the longest chain of dependent decisions (a handful in practice),
+// not the number of rows.  C1 (10 504 clash survivors): one block, 2 launches instead of 44.
+constexpr int kTfdBlock = 16384;            // candidates per sweep step (bit matrix of a full block: 32 MB)
+constexpr int kTfdWords = kTfdBlock / 32;
+constexpr int kTfdRowsPerCta = 256;
 
-__global__ void __launch_bounds__(256) tfd_block_pairs_kernel(TfdArgs a, int b0, int b1, unsigned* __restrict__ simbits) {
-    const int n = b1 - b0;
-    const int total = n * (n - 1) / 2;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        // e -> (i, t) with i < t < n, row-major over the strict upper triangle
-        int i = (int)((2.0f * n - 1.0f - sqrtf((2.0f * n - 1.0f) * (2.0f * n - 1.0f) - 8.0f * (float)e)) * 0.5f);
-        i = max(0, min(i, n - 2));
-        while (i > 0 && (long long)i * (2 * n - i - 1) / 2 > e) --i;
-        while ((long long)(i + 1) * (2 * n - i - 2) / 2 <= e) ++i;
-        const int t = i + 1 + (e - i * (2 * n - i - 1) / 2);
-        if (a.flag[b0 + i] || a.flag[b0 + t]) continue;
-        if (tfd_similar(a, b0 + t, b0 + i)) atomicOr(simbits + i * kTfdWords + (t >> 5), 1u << (t & 31));
+// similar <=> sum_k wrap(|x_k - y_k|) < thr, on explicit fingerprint rows (shared or global memory)
+__device__ __forceinline__ bool tfd_similar_rows(const TfdArgs& a, const double* __restrict__ x, const double* __restrict__ y,
+                                                 int row_new, int row_ref) {
+    double sum = 0.0;
+    const double stop = a.thr + a.eps;
+    for (int k = 0; k < a.q; ++k) {
+        double d = fabs(x[k] - y[k]);
+        d = fabs(d - (d > 180.0 ? 360.0 : 0.0));
+        sum += d;
+        if (sum > stop) return false;  // partial sums only grow: cannot come back under thr + eps
     }
-}
-
-// ordered resolution inside the block from the pair bits: one warp, lane l owns the "still a candidate" bits of rows
-// 32 l .. 32 l + 31; n steps of bit operations on the bit matrix in shared memory
-__global__ void __launch_bounds__(256) tfd_block_resolve_kernel(TfdArgs a, int b0, int b1, const unsigned* __restrict__ simbits) {
-    extern __shared__ unsigned s_bits[];  // kTfdBlock * kTfdWords
-    const int n = b1 - b0;
-    {   // the whole CTA stages the bit matrix (128 KB); one warp then walks it
-        const uint4* src = reinterpret_cast<const uint4*>(simbits);
-        uint4* dst = reinterpret_cast<uint4*>(s_bits);
-        for (int w = threadIdx.x; w < n * kTfdWords / 4; w += blockDim.x) dst[w] = src[w];
-    }
-    __syncthreads();
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
-    unsigned alive = 0u;
-    for (int k = 0; k < 32; ++k) {
-        const int r = 32 * lane + k;
-        if (r < n && a.flag[b0 + r] == 0) alive |= 1u << k;
-    }
-    __syncwarp();
-    int n_acc = *a.n_acc;
-    for (int i = 0; i < n; ++i) {
-        const unsigned word = __shfl_sync(0xffffffffu, alive, i >> 5);
-        if ((word >> (i & 31)) & 1u) {  // uniform: row b0 + i is accepted and rejects its similar later rows
-            if (lane == 0) a.acc[n_acc] = b0 + i;
-            ++n_acc;
-            alive &= ~s_bits[i * kTfdWords + lane];
+    const bool sim = sum < a.thr;
+    if (fabs(sum - a.thr) <= a.eps && a.ties) {
+        int slot = atomicAdd(a.n_ties, 1);
+        if (slot < a.tie_cap) {
+            TieRecord r;
+            r.a = a.label ? a.label[row_new] : row_new;
+            r.b = a.label ? a.label[row_ref] : row_ref;
+            r.value = sum;
+            r.kind = FC_TIE_TFD;
+            r.decision = sim ? 1 : 0;
+            a.ties[slot] = r;
         }
     }
-    for (int k = 0; k < 32; ++k) {
-        const int r = 32 * lane + k;
-        if (r < n) a.flag[b0 + r] = ((alive >> k) & 1u) ? 0 : 1;
+    return sim;
+}
+
+// CTA = 256 consecutive rows t of the block x one word (32 earlier rows i) of the bit matrix; thread = one row.
+// The lanes of a warp compare their own rows with the SAME earlier row at a time (shared-memory broadcast).
+// Rows already rejected against rows accepted in earlier blocks take no part (their words are 0).
+__global__ void __launch_bounds__(kTfdRowsPerCta) tfd_block_matrix_kernel(TfdArgs a, int b0, int nb, int W, int use_smem,
+                                                                          unsigned* __restrict__ simT) {
+    extern __shared__ double s_fp[];
+    const int w = blockIdx.x % W, rt = blockIdx.x / W;
+    const int t = rt * kTfdRowsPerCta + threadIdx.x;
+    const int t_hi = min(nb, (rt + 1) * kTfdRowsPerCta);  // rows of this CTA: [rt * 256, t_hi)
+    if (32 * w >= t_hi - 1) {  // no row of the CTA has an earlier row in this word
+        if (t < nb) simT[(size_t)t * W + w] = 0u;
+        return;
     }
-    if (lane == 0) *a.n_acc = n_acc;
+    const int qs = a.q | 1;  // odd stride: conflict-free 64-bit rows
+    double* s_rows = s_fp;
+    double* s_cols = s_fp + (size_t)kTfdRowsPerCta * qs;
+    __shared__ int s_cflag[32];
+    if (threadIdx.x < 32) {
+        const int i = 32 * w + threadIdx.x;
+        s_cflag[threadIdx.x] = i < nb ? a.flag[b0 + i] : 1;
+    }
+    if (use_smem) {
+        for (int e = threadIdx.x; e < 32 * a.q; e += blockDim.x) {
+            const int j = e / a.q, k = e - j * a.q, i = 32 * w + j;
+            s_cols[j * qs + k] = i < nb ? a.fp[(size_t)(b0 + i) * a.q + k] : 0.0;
+        }
+        const int rows = t_hi - rt * kTfdRowsPerCta;
+        for (int e = threadIdx.x; e < rows * a.q; e += blockDim.x) {
+            const int j = e / a.q, k = e - j * a.q;
+            s_rows[j * qs + k] = a.fp[(size_t)(b0 + rt * kTfdRowsPerCta + j) * a.q + k];
+        }
+    }
+    __syncthreads();
+    if (t >= nb) return;
+    unsigned word = 0u;
+    if (a.flag[b0 + t] == 0) {
+        const double* x = use_smem ? s_rows + (size_t)threadIdx.x * qs : a.fp + (size_t)(b0 + t) * a.q;
+        for (int j = 0; j < 32; ++j) {
+            const int i = 32 * w + j;
+            if (i >= t) break;
+            if (s_cflag[j]) continue;
+            const double* y = use_smem ? s_cols + (size_t)j * qs : a.fp + (size_t)(b0 + i) * a.q;
+            if (tfd_similar_rows(a, x, y, b0 + t, b0 + i)) word |= 1u << j;
+        }
+    }
+    simT[(size_t)t * W + w] = word;
+}
+
+// Rounds of the rule above over one block.  Cooperative launch, one CTA per SM.  Every CTA keeps its own copy of the
+// accepted / undecided bit masks in shared memory; a round = every undecided row gets a verdict from the masks (one warp
+// per row scans the row's words), grid-wide barrier, every CTA applies all verdicts to its copy.  The verdict array is
+// double-buffered by round parity, so one barrier per round is enough.  At the end CTA 0 appends the accepted rows, in
+// order, to the accepted list and writes the rejected flags.
+__global__ void __launch_bounds__(1024, 1) tfd_block_resolve_kernel(TfdArgs a, int b0, int nb, int W,
+                                                                    const unsigned* __restrict__ simT,
+                                                                    unsigned char* __restrict__ verdict /* [2][nb] */,
+                                                                    int* __restrict__ rounds_out) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ unsigned s_acc[kTfdWords], s_und[kTfdWords];
+    __shared__ int s_left;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g_warp = blockIdx.x * (blockDim.x >> 5) + warp, n_warps = gridDim.x * (blockDim.x >> 5);
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        unsigned u = 0u;
+        for (int k = 0; k < 32; ++k) {
+            const int r = 32 * w + k;
+            if (r < nb && a.flag[b0 + r] == 0) u |= 1u << k;
+        }
+        s_und[w] = u;
+        s_acc[w] = 0u;
+    }
+    __syncthreads();
+    for (int round = 0;; ++round) {
+        unsigned char* v = verdict + (size_t)(round & 1) * nb;
+        for (int t = g_warp; t < nb; t += n_warps) {
+            if (!((s_und[t >> 5] >> (t & 31)) & 1u)) continue;  // warp-uniform
+            unsigned hit_acc = 0u, hit_und = 0u;
+            const unsigned* row = simT + (size_t)t * W;
+            const int last = t > 0 ? (t - 1) >> 5 : -1;
+            for (int w = lane; w <= last; w += 32) {
+                const unsigned m = row[w];
+                hit_acc |= m & s_acc[w];
+                hit_und |= m & s_und[w];
+            }
+            const bool any_acc = __any_sync(0xffffffffu, hit_acc != 0u), any_und = __any_sync(0xffffffffu, hit_und != 0u);
+            if (lane == 0) v[t] = any_acc ? 2 : (any_und ? 0 : 1);  // 2 = rejected, 1 = accepted, 0 = still undecided
+        }
+        grid.sync();
+        if (threadIdx.x == 0) s_left = 0;
+        __syncthreads();
+        int left = 0;
+        for (int w = threadIdx.x; w < W; w += blockDim.x) {
+            unsigned u = s_und[w], acc = s_acc[w];
+            unsigned todo = u;
+            while (todo) {
+                const int k = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                const unsigned char d = v[32 * w + k];
+                if (d) {
+                    u &= ~(1u << k);
+                    if (d == 1) acc |= 1u << k;
+                }
+            }
+            s_und[w] = u;
+            s_acc[w] = acc;
+            left += __popc(u);
+        }
+        if (left) atomicAdd(&s_left, left);
+        __syncthreads();
+        if (s_left == 0) {  // every CTA holds the same masks: the exit is grid-uniform
+            if (blockIdx.x == 0 && threadIdx.x == 0 && rounds_out) *rounds_out += round + 1;
+            break;
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x != 0) return;
+    // accepted rows in order -> list; flags of the rejected rows
+    __shared__ int s_pref[kTfdWords + 1];
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int w = 0; w < W; ++w) { s_pref[w] = run; run += __popc(s_acc[w]); }
+        s_pref[W] = run;
+    }
+    __syncthreads();
+    const int n_acc0 = *a.n_acc;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        unsigned acc = s_acc[w];
+        int o = n_acc0 + s_pref[w];
+        for (int k = 0; k < 32; ++k) {
+            const int r = 32 * w + k;
+            if (r >= nb) break;
+            const bool kept = (acc >> k) & 1u;
+            if (kept) a.acc[o++] = b0 + r;
+            a.flag[b0 + r] = kept ? 0 : 1;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *a.n_acc = n_acc0 + s_pref[W];
 }
 
 int tfd_keepfirst_dev(const double* fp, const long long* label, int n, int q, double thr, double eps, int* flag,
@@ -281,21 +416,51 @@ int tfd_keepfirst_dev(const double* fp, const long long* label, int n, int q, do
     if (n == 0) return FC_OK;
     FC_CUDA(cudaMemsetAsync(flag, 0, (size_t)n * sizeof(int), s));
     FC_CUDA(cudaMemsetAsync(n_acc, 0, sizeof(int), s));
-    unsigned* simbits = nullptr;
-    const size_t bit_bytes = (size_t)kTfdBlock * kTfdWords * sizeof(unsigned);  // 128 KB
-    FC_CUDA(cudaMallocAsync((void**)&simbits, bit_bytes, s));
-    FC_CUDA(cudaFuncSetAttribute(tfd_block_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bit_bytes));
+    const int nb_max = std::min(n, kTfdBlock), w_max = (nb_max + 31) / 32;
+    unsigned* simT = nullptr;
+    unsigned char* verdict = nullptr;
+    const bool trace = getenv("FC_STRING_TRACE") != nullptr;
+    const size_t verdict_bytes = ((size_t)2 * nb_max + 15) / 16 * 16;
+    FC_CUDA(cudaMallocAsync((void**)&simT, (size_t)nb_max * w_max * sizeof(unsigned), s));
+    FC_CUDA(cudaMallocAsync((void**)&verdict, verdict_bytes + 16, s));
+    int* rounds = reinterpret_cast<int*>(verdict + verdict_bytes);
+    FC_CUDA(cudaMemsetAsync(rounds, 0, 16, s));
     TfdArgs a{fp, label, q, thr, eps, flag, acc, n_acc, ties, n_ties, tie_cap};
+    const size_t fp_smem = (size_t)(kTfdRowsPerCta + 32) * (size_t)(q | 1) * sizeof(double);
+    const int use_smem = fp_smem <= 200 * 1024 ? 1 : 0;
+    if (use_smem)
+        FC_CUDA(cudaFuncSetAttribute(tfd_block_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp_smem));
     const int grid = sm_count() * 8;
-    for (int b0 = 0; b0 < n; b0 += kTfdBlock) {
-        int b1 = std::min(n, b0 + kTfdBlock);
-        if (b0 > 0) tfd_vs_accepted_kernel<<<grid, 256, 0, s>>>(a, b0, b1);
-        cudaMemsetAsync(simbits, 0, (size_t)(b1 - b0) * kTfdWords * sizeof(unsigned), s);
-        if (b1 - b0 > 1) tfd_block_pairs_kernel<<<sm_count() * 4, 256, 0, s>>>(a, b0, b1, simbits);
-        tfd_block_resolve_kernel<<<1, 256, bit_bytes, s>>>(a, b0, b1, simbits);
+    cudaError_t e = cudaSuccess;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (trace) for (auto& x : ev) cudaEventCreate(&x);
+    for (int b0 = 0; b0 < n && e == cudaSuccess; b0 += kTfdBlock) {
+        int nb = std::min(n - b0, kTfdBlock), W = (nb + 31) / 32;
+        if (b0 > 0) tfd_vs_accepted_kernel<<<grid, 256, 0, s>>>(a, b0, b0 + nb);
+        if (trace) cudaEventRecord(ev[0], s);
+        const unsigned ctas = (unsigned)(((nb + kTfdRowsPerCta - 1) / kTfdRowsPerCta) * W);
+        tfd_block_matrix_kernel<<<ctas, kTfdRowsPerCta, use_smem ? fp_smem : 0, s>>>(a, b0, nb, W, use_smem, simT);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) break;
+        if (trace) cudaEventRecord(ev[1], s);
+        const unsigned* simT_c = simT;
+        void* args[] = {(void*)&a, (void*)&b0, (void*)&nb, (void*)&W, (void*)&simT_c, (void*)&verdict, (void*)&rounds};
+        e = cudaLaunchCooperativeKernel((const void*)tfd_block_resolve_kernel, dim3((unsigned)sm_count()), dim3(1024), args, 0, s);
+        if (trace && e == cudaSuccess) {
+            cudaEventRecord(ev[2], s);
+            cudaEventSynchronize(ev[2]);
+            float m1 = 0, m2 = 0;
+            int h_rounds = 0;
+            cudaEventElapsedTime(&m1, ev[0], ev[1]);
+            cudaEventElapsedTime(&m2, ev[1], ev[2]);
+            cudaMemcpy(&h_rounds, rounds, 4, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "  tfd sweep block %d (+%d rows, q = %d): pair matrix %.1f us, resolve %.1f us (%d rounds so far)\n", b0, nb, q,
+                    1e3 * m1, 1e3 * m2, h_rounds);
+        }
     }
-    cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(simbits, s);
+    if (trace) for (auto& x : ev) cudaEventDestroy(x);
+    cudaFreeAsync(simT, s);
+    cudaFreeAsync(verdict, s);
     FC_CUDA(e);
     return FC_OK;
 }
@@ -384,10 +549,11 @@ __global__ void __launch_bounds__(128) place_kept_kernel(const double* __restric
 }  // namespace fc
 
 fc_result::~fc_result() {
-    if (lazy.empty() && !lazy_coords[0]) return;
+    if (lazy.empty() && !lazy_coords[0] && !d_kept_coords) return;
     int cur = -1;
     cudaGetDevice(&cur);
     if (lazy_device >= 0 && lazy_device != cur) cudaSetDevice(lazy_device);
+    if (d_kept_coords) cudaFree(d_kept_coords);
     for (LazySegment& sgm : lazy) {
         if (sgm.d_xf) cudaFree(sgm.d_xf);
         if (sgm.d_conf) cudaFree(sgm.d_conf);
@@ -399,11 +565,17 @@ fc_result::~fc_result() {
 
 extern "C" int fc_result_kept_coords(const fc_result* r, double* out) {
     FC_REQUIRE(r, "null result");
-    if (r->lazy.empty()) FC_COPY_OUT(r->coords, out);
+    if (r->lazy.empty() && !r->d_kept_coords) FC_COPY_OUT(r->coords, out);
     FC_REQUIRE(out, "null output pointer");
     int cur = -1;
     FC_CUDA(cudaGetDevice(&cur));
     if (r->lazy_device >= 0 && r->lazy_device != cur) FC_CUDA(cudaSetDevice(r->lazy_device));
+    if (r->d_kept_coords) {  // string embed: already placed, one copy into the caller's array
+        cudaError_t ce = cudaMemcpy(out, r->d_kept_coords, r->d_kept_bytes, cudaMemcpyDeviceToHost);
+        if (r->lazy_device >= 0 && r->lazy_device != cur) cudaSetDevice(cur);
+        if (ce != cudaSuccess) return fc::cuda_fail(ce, "fc_result_kept_coords", __FILE__, __LINE__);
+        return FC_OK;
+    }
     const int n_tot = r->lazy_n_atoms[0] + r->lazy_n_atoms[1] + r->lazy_n_atoms[2];
     const size_t pose_bytes = (size_t)n_tot * 24;
     const int64_t slice = std::max<int64_t>(1, ((int64_t)256 << 20) / (int64_t)pose_bytes);  // 256 MB of coordinates per slice
@@ -755,9 +927,22 @@ extern "C" int fc_string_materialize(const fc_string_problem* p, const int64_t* 
 extern "C" int fc_string_screen(const fc_string_problem* p, fc_result** out) {
     FC_REQUIRE(out, "null output");
     *out = nullptr;
+    // FC_STRING_TRACE=1: wall-clock stage times on stderr (adds a stream synchronisation per stage)
+    const bool trace = getenv("FC_STRING_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_prev = t_begin;
+    auto mark = [&](const char* what, cudaStream_t st) {
+        if (!trace) return;
+        if (st) cudaStreamSynchronize(st);
+        const double t = now();
+        fprintf(stderr, "  fc_string_screen %-28s %8.1f us\n", what, t - t_prev);
+        t_prev = t;
+    };
     StringCtx c;
     int rc = string_ctx_init(c, p);
     if (rc) return rc;
+    mark("context + uploads", c.s);
     const int64_t total = string_total(p);
     fc_result* r = new fc_result();
     DevBuf<double> xf, fp, d_coords;
@@ -767,6 +952,7 @@ extern "C" int fc_string_screen(const fc_string_problem* p, fc_result** out) {
     const int tie_cap = 1 << 20;
     cudaStream_t s = c.s;
     rc = string_stage1(c, p, 0, total, r, &xf, &surv, &fp, d_ties, d_cnt, tie_cap);
+    mark("stage 1 (xf, clash, fp)", s);
     const int n_surv = (int)r->n_surv;
     if (!rc && n_surv > 0) {
         cudaError_t e = d_ties.alloc(tie_cap, s);
@@ -784,38 +970,35 @@ extern "C" int fc_string_screen(const fc_string_problem* p, fc_result** out) {
             if (e == cudaSuccess) e = cudaStreamSynchronize(s);
             if (e != cudaSuccess) rc = cuda_fail(e, "n_kept readback", __FILE__, __LINE__);
         }
+        mark("keep-first sweep", s);
         if (!rc && n_kept > 0) {
-            // accepted rows (ascending) -> absolute pose indices
-            std::vector<int> h_acc(n_kept);
-            e = cudaMemcpy(h_acc.data(), acc.p, (size_t)n_kept * 4, cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) rc = cuda_fail(e, "acc readback", __FILE__, __LINE__);
-            r->kept.resize(n_kept);
-            for (int i = 0; i < n_kept && !rc; ++i) r->kept[i] = r->survivors[(size_t)h_acc[i]];
+            // accepted rows (ascending) -> absolute pose indices, on the device; the coordinates of the kept poses are
+            // placed there too and stay with the result until the caller asks for them
             const size_t n_tot = (size_t)r->n_atoms;
-            if (!rc) {
-                e = d_kept.alloc(n_kept, s);
-                if (e == cudaSuccess) e = d_coords.alloc((size_t)n_kept * n_tot * 3, s);
-                if (e == cudaSuccess)
-                    e = cudaMemcpyAsync(d_kept.p, r->kept.data(), (size_t)n_kept * 8, cudaMemcpyHostToDevice, s);
-                if (e != cudaSuccess) rc = cuda_fail(e, "kept upload", __FILE__, __LINE__);
+            e = d_kept.alloc(n_kept, s);
+            if (e == cudaSuccess) {
+                r->d_kept_bytes = (size_t)n_kept * n_tot * 24;
+                e = cudaMallocAsync((void**)&r->d_kept_coords, r->d_kept_bytes, s);
+                cudaGetDevice(&r->lazy_device);
             }
-            if (!rc) {
-                string_materialize_kernel<<<n_kept, 128, 0, s>>>(c.dev, d_kept.p, n_kept, d_coords.p);
-                r->coords.resize((size_t)n_kept * n_tot * 3);
+            if (e == cudaSuccess) {
+                gather_index_kernel<<<(unsigned)((n_kept + 255) / 256), 256, 0, s>>>(surv.p, acc.p, n_kept, d_kept.p);
+                string_materialize_kernel<<<n_kept, 128, 0, s>>>(c.dev, d_kept.p, n_kept, r->d_kept_coords);
                 e = cudaGetLastError();
-                if (e == cudaSuccess)
-                    e = cudaMemcpyAsync(r->coords.data(), d_coords.p, r->coords.size() * 8, cudaMemcpyDeviceToHost, s);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-                if (e != cudaSuccess) rc = cuda_fail(e, "materialize", __FILE__, __LINE__);
             }
+            r->kept.resize(n_kept);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(r->kept.data(), d_kept.p, (size_t)n_kept * 8, cudaMemcpyDeviceToHost, s);
+            if (e != cudaSuccess) rc = cuda_fail(e, "materialize", __FILE__, __LINE__);
             r->n_kept = n_kept;
         }
         if (!rc) rc = fetch_ties(r, d_ties, d_cnt.p + 1, tie_cap, s);
+        mark("materialise + ties", s);
     }
     if (rc) {
         delete r;
         return rc;
     }
     *out = r;
+    if (trace) fprintf(stderr, "  fc_string_screen total %.1f us\n", now() - t_begin);
     return FC_OK;
 }

@@ -36,6 +36,10 @@ struct fc_result {
     int32_t lazy_n_atoms[3] = {0, 0, 0};
     int32_t lazy_n_mols = 0;
     int lazy_device = -1;
+    // string embed: coordinates of the kept poses stay on the device until fc_result_kept_coords copies them straight
+    // into the caller's array (no intermediate host copy)
+    double* d_kept_coords = nullptr;
+    size_t d_kept_bytes = 0;
     ~fc_result();
 };
 

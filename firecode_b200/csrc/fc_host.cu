@@ -6,11 +6,13 @@
 // (only the heavy atoms of it) in a third of the time.
 // fc_take_rows: the `structures[mask]` copy every pruning entry point returns
 // (/root/reference/firecode/embedder.py:1400-1408 consumes it), done by several threads.
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
-#include <stdio.h>
-
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -19,9 +21,27 @@
 
 namespace fc {
 
+// Worker threads for the host-side copies: one per physical core, at most 16 (FC_HOST_THREADS overrides).  The number of
+// hardware threads per core comes from sysfs; boxes that expose one thread per core (the B200 pool's VMs) use them all.
 static int host_threads() {
-    unsigned hc = std::thread::hardware_concurrency();
-    return (int)std::max(1u, std::min(16u, hc ? hc / 2u : 1u));  // half the hardware threads, at most 16
+    static const int n = []() {
+        if (const char* v = getenv("FC_HOST_THREADS"))
+            if (atoi(v) > 0) return std::min(64, atoi(v));
+        unsigned hc = std::thread::hardware_concurrency();
+        if (!hc) return 1;
+        unsigned per_core = 1;
+        if (FILE* f = fopen("/sys/devices/system/cpu/cpu0/topology/thread_siblings_list", "r")) {
+            char buf[64] = "";
+            if (fgets(buf, sizeof buf, f)) {
+                per_core = 1;
+                for (const char* c = buf; *c; ++c)
+                    if (*c == ',' || *c == '-') per_core = 2;
+            }
+            fclose(f);
+        }
+        return (int)std::max(1u, std::min(16u, hc / per_core));
+    }();
+    return n;
 }
 
 template <class F>
@@ -47,21 +67,31 @@ static const size_t kStageBytes = (size_t)48 << 20;
 
 // dst (device, n x n_sel x 3 doubles) <- src (host, n x n_atoms x 3 doubles) restricted to the atoms `sel`
 // (null = all atoms).  Asynchronous on `stream` except for the staging itself.
+//
+// A ring of kUpSlots pinned slots: worker threads (alive for the whole call) fill slot c % kUpSlots with the rows of
+// piece c, each its share of the rows, while the copy engine sends the pieces before it; the calling thread hands out
+// slots whose previous copy has finished and submits filled pieces in order.
+static const int kUpSlots = 4;
+static const size_t kUpSlotBytes = (size_t)16 << 20;
+struct UploadRing {
+    char* base = nullptr;
+    cudaEvent_t ev[kUpSlots] = {};
+    int device = -1;
+};
+
 cudaError_t upload_rows_staged(double* dst, const double* src, int64_t n, int n_atoms, const int32_t* sel, int n_sel,
                                cudaStream_t stream) {
-    static thread_local PinnedPair st;
+    static thread_local UploadRing st;
+    if (n <= 0) return cudaSuccess;
     int dev = 0;
     cudaError_t e0 = cudaGetDevice(&dev);
     if (e0 != cudaSuccess) return e0;
-    if (!st.p[0]) {
-        for (int b = 0; b < 2; ++b) {
-            cudaError_t e = cudaHostAlloc(&st.p[b], kStageBytes, cudaHostAllocPortable);
-            if (e != cudaSuccess) return e;
-        }
-        st.bytes = kStageBytes;
+    if (!st.base) {
+        cudaError_t e = cudaHostAlloc((void**)&st.base, kUpSlots * kUpSlotBytes, cudaHostAllocPortable);
+        if (e != cudaSuccess) return e;
     }
     if (st.device != dev) {  // first use, or the thread moved to another device: events are per device
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kUpSlots; ++b) {
             if (st.ev[b]) cudaEventDestroy(st.ev[b]);
             st.ev[b] = nullptr;
             cudaError_t e = cudaEventCreateWithFlags(&st.ev[b], cudaEventDisableTiming);
@@ -70,29 +100,89 @@ cudaError_t upload_rows_staged(double* dst, const double* src, int64_t n, int n_
         st.device = dev;
     }
     const size_t row_out = (size_t)n_sel * 24, row_in = (size_t)n_atoms * 24;
-    const int64_t rows_per_chunk = std::max<int64_t>(1, (int64_t)(st.bytes / row_out));
-    int buf = 0;
-    for (int64_t r0 = 0; r0 < n; r0 += rows_per_chunk, buf ^= 1) {
-        const int64_t rows = std::min(rows_per_chunk, n - r0);
-        cudaError_t e = cudaEventSynchronize(st.ev[buf]);  // the copy that last used this buffer has finished
-        if (e != cudaSuccess) return e;
-        char* stage = (char*)st.p[buf];
-        parallel_ranges(rows, 2048, [&](int64_t lo, int64_t hi) {
+    // the selection as runs of consecutive atoms {first atom, atoms}: heavy atoms usually sit together, so a row is a
+    // handful of memcpy calls instead of one per atom
+    std::vector<std::pair<int, int>> runs;
+    for (int k = 0; sel && k < n_sel; ++k) {
+        if (!runs.empty() && runs.back().first + runs.back().second == sel[k]) ++runs.back().second;
+        else runs.emplace_back(sel[k], 1);
+    }
+    const int64_t rows_per_piece = std::max<int64_t>(1, (int64_t)(kUpSlotBytes / row_out));
+    if ((size_t)rows_per_piece * row_out > kUpSlotBytes) return cudaErrorInvalidValue;  // one row larger than a slot
+    const int64_t n_pieces = (n + rows_per_piece - 1) / rows_per_piece;
+    const int nt = (int)std::min<int64_t>(host_threads(), std::max<int64_t>(1, std::min(n, rows_per_piece) / 512));
+
+    char* const ring = st.base;  // `st` is thread-local: the workers must not name it
+    std::mutex mu;
+    std::condition_variable cv;
+    int64_t released = 0;                              // pieces [0, released) may be filled
+    std::vector<int> filled((size_t)n_pieces, 0);      // workers done with piece c
+    auto fill = [&](int t) {
+        for (int64_t c = 0; c < n_pieces; ++c) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return released > c || released < 0; });
+                if (released < 0) return;  // the call failed
+            }
+            const int64_t r0 = c * rows_per_piece, rows = std::min(rows_per_piece, n - r0);
+            const int64_t lo = rows * t / nt, hi = rows * (t + 1) / nt;
+            char* stage = ring + (size_t)(c % kUpSlots) * kUpSlotBytes;
             for (int64_t r = lo; r < hi; ++r) {
                 const char* in = (const char*)src + (size_t)(r0 + r) * row_in;
                 char* out = stage + (size_t)r * row_out;
                 if (!sel) {
                     memcpy(out, in, row_out);
                 } else {
-                    for (int k = 0; k < n_sel; ++k) memcpy(out + (size_t)k * 24, in + (size_t)sel[k] * 24, 24);
+                    for (const auto& run : runs) {
+                        memcpy(out, in + (size_t)run.first * 24, (size_t)run.second * 24);
+                        out += (size_t)run.second * 24;
+                    }
                 }
             }
-        });
-        e = cudaMemcpyAsync((char*)dst + (size_t)r0 * row_out, stage, (size_t)rows * row_out, cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess) e = cudaEventRecord(st.ev[buf], stream);
-        if (e != cudaSuccess) return e;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ++filled[(size_t)c];
+            }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> workers;
+    workers.reserve((size_t)nt);
+    for (int t = 0; t < nt; ++t) workers.emplace_back(fill, t);
+    cudaError_t err = cudaSuccess;
+    int64_t next_release = 0;
+    // slot of piece r is free once the copy of piece r - kUpSlots has left the host (an event never recorded is complete)
+    auto release_upto = [&](int64_t limit) {
+        while (next_release < n_pieces && next_release < limit && err == cudaSuccess) {
+            err = cudaEventSynchronize(st.ev[next_release % kUpSlots]);
+            ++next_release;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                released = err == cudaSuccess ? next_release : -1;
+            }
+            cv.notify_all();
+        }
+    };
+    release_upto(kUpSlots - 1);
+    for (int64_t c = 0; c < n_pieces && err == cudaSuccess; ++c) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return filled[(size_t)c] == nt; });
+        }
+        const int64_t r0 = c * rows_per_piece, rows = std::min(rows_per_piece, n - r0);
+        err = cudaMemcpyAsync((char*)dst + (size_t)r0 * row_out, st.base + (size_t)(c % kUpSlots) * kUpSlotBytes,
+                              (size_t)rows * row_out, cudaMemcpyHostToDevice, stream);
+        if (err == cudaSuccess) err = cudaEventRecord(st.ev[c % kUpSlots], stream);
+        // piece c is in flight: waiting here for piece c - 2 never leaves the copy engine idle
+        if (err == cudaSuccess) release_upto(c + kUpSlots - 1);
     }
-    return cudaSuccess;
+    if (err != cudaSuccess) {
+        std::lock_guard<std::mutex> lk(mu);
+        released = -1;
+    }
+    cv.notify_all();
+    for (auto& w : workers) w.join();
+    return err;
 }
 
 }  // namespace fc

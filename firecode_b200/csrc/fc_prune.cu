@@ -379,10 +379,7 @@ __device__ __forceinline__ double prune_wsum(double v) {
 }
 
 // one warp per candidate pair: the FP64 evaluation that restates rmsd_and_max (centred heavy atoms)
-__global__ void __launch_bounds__(256) prune_exact_kernel(PruneArgs a, long long n_cand) {
-    const int lane = threadIdx.x & 31;
-    const long long c = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= n_cand) return;
+__device__ __forceinline__ void prune_exact_one(const PruneArgs& a, long long c, int lane) {
     const int2 pr = a.cand[c];
     const int nh = a.nh;
     const double* p = a.xc + (size_t)pr.x * nh * 3;
@@ -438,6 +435,17 @@ __global__ void __launch_bounds__(256) prune_exact_kernel(PruneArgs a, long long
     if (r_ok && m_ok) prune_push_pair(a, pr.x, pr.y);
 }
 
+// The number of candidates is read on the device (the screen's counter), so the host does not wait between the
+// screen and this launch.  A list that overflowed is left alone: the host repeats the pass with a larger one.
+__global__ void __launch_bounds__(256) prune_exact_kernel(PruneArgs a) {
+    const long long n_cand = (long long)*a.n_cand;
+    if (n_cand > a.cand_cap) return;
+    const int lane = threadIdx.x & 31;
+    const long long step = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long c = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < n_cand; c += step)
+        prune_exact_one(a, c, lane);
+}
+
 }  // namespace fc
 
 using namespace fc;
@@ -453,30 +461,49 @@ static const int64_t kSchedule[] = {500000, 200000, 100000, 50000, 20000, 10000,
 //              droppable side (later ones for keep-first, earlier ones for keep-last);
 //   snapshot : a structure is dropped if any structure on its keeper side that was active at the start of
 //              the pass is similar to it.
-static void prune_resolve(std::vector<uint8_t>& mask, const std::vector<int2>& pairs, bool keep_first, bool snapshot) {
+struct ResolveScratch {
+    std::vector<int> off, adj;  // CSR of the similar pairs by keeper-side structure, reused from pass to pass
+};
+
+static void prune_resolve(std::vector<uint8_t>& mask, const std::vector<int2>& pairs, bool keep_first, bool snapshot,
+                          ResolveScratch& sc) {
     if (pairs.empty()) return;
     if (snapshot) {
         for (const int2& p : pairs) mask[(size_t)(keep_first ? p.y : p.x)] = 0;
         return;
     }
     const size_t n = mask.size();
-    std::vector<int64_t> off(n + 1, 0);
-    for (const int2& p : pairs) off[(size_t)(keep_first ? p.x : p.y) + 1] += 1;
-    for (size_t i = 0; i < n; ++i) off[i + 1] += off[i];
-    std::vector<int> adj(pairs.size());
-    std::vector<int64_t> fill(off.begin(), off.end() - 1);
+    // structures that head at least one pair lie in [lo, hi]: the counting and the sweep stay inside that range
+    int lo = (int)n, hi = -1;
     for (const int2& p : pairs) {
-        if (keep_first) adj[(size_t)fill[(size_t)p.x]++] = p.y;
-        else adj[(size_t)fill[(size_t)p.y]++] = p.x;
+        const int h = keep_first ? p.x : p.y;
+        lo = std::min(lo, h);
+        hi = std::max(hi, h);
     }
+    const size_t span = (size_t)(hi - lo) + 2;
+    if (sc.off.size() < span) sc.off.resize(span);
+    if (sc.adj.size() < pairs.size()) sc.adj.resize(pairs.size());
+    int* off = sc.off.data();
+    int* adj = sc.adj.data();
+    memset(off, 0, span * sizeof(int));
+    for (const int2& p : pairs) off[(keep_first ? p.x : p.y) - lo + 1] += 1;
+    for (size_t i = 1; i < span; ++i) off[i] += off[i - 1];
+    // fill backwards so that off[i] ends up at the start of row i again
+    for (const int2& p : pairs) {
+        if (keep_first) adj[off[p.x - lo + 1]-- - 1] = p.y;
+        else adj[off[p.y - lo + 1]-- - 1] = p.x;
+    }
+    // after the fill off[i + 1] holds the START of row i; its end is the start of row i + 1, the last row ends at pairs.size()
+    auto row_begin = [&](size_t i) { return off[i + 1]; };
+    auto row_end = [&](size_t i) { return i + 2 < span ? off[i + 2] : (int)pairs.size(); };
     if (keep_first) {
-        for (size_t i = 0; i < n; ++i)
-            if (mask[i])
-                for (int64_t e = off[i]; e < off[i + 1]; ++e) mask[(size_t)adj[(size_t)e]] = 0;
+        for (size_t i = 0; i + 1 < span; ++i)
+            if (mask[(size_t)lo + i])
+                for (int e = row_begin(i); e < row_end(i); ++e) mask[(size_t)adj[e]] = 0;
     } else {
-        for (size_t i = n; i-- > 0;)
-            if (mask[i])
-                for (int64_t e = off[i]; e < off[i + 1]; ++e) mask[(size_t)adj[(size_t)e]] = 0;
+        for (size_t i = span - 1; i-- > 0;)
+            if (mask[(size_t)lo + i])
+                for (int e = row_begin(i); e < row_end(i); ++e) mask[(size_t)adj[e]] = 0;
     }
 }
 
@@ -545,8 +572,17 @@ static void plan_gram_pass(const std::vector<uint8_t>& mask, int64_t n, const st
         const int64_t first = bounds[(size_t)c], last = bounds[(size_t)c + 1];
         while (spos.size() % 16) spos.push_back(-1);
         const int pbegin = (int)spos.size();
-        for (int64_t i = first; i < last; ++i)
-            if (mask[(size_t)i]) spos.push_back((int)i);
+        {   // branch-free compaction of the chunk's active structures
+            spos.resize((size_t)pbegin + (size_t)(last - first));
+            int* out = spos.data() + pbegin;
+            const uint8_t* m = mask.data();
+            size_t w = 0;
+            for (int64_t i = first; i < last; ++i) {
+                out[w] = (int)i;
+                w += m[i] != 0;
+            }
+            spos.resize((size_t)pbegin + w);
+        }
         const int pend = (int)spos.size(), len = pend - pbegin;
         if (len < 2) continue;
         const int tile_end = (pend + 15) / 16;
@@ -660,10 +696,15 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
     cudaEventCreate(&ev_g1);
     double screen_slots = 0;
     int64_t screen_launches = 0;
+    // page-locked landing place of the per-pass counters (one per host thread, kept)
+    struct PassCounters { unsigned long long n_cand, found; int gram_err; };
+    static thread_local PassCounters* hb = nullptr;
+    if (!hb) FC_CUDA(cudaHostAlloc((void**)&hb, sizeof(PassCounters), cudaHostAllocPortable));
     cudaStream_t s;
     FC_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     int rc = FC_OK;
     std::vector<uint8_t> mask((size_t)n, 1);
+    ResolveScratch resolve_scratch;
     int64_t pairs_tiled = 0, passes = 0, pairs_skipped = 0, similar_total = 0;
     unsigned long long evals_total = 0;
     int64_t ties_total = 0;
@@ -841,47 +882,54 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                             prune_screen_f32_kernel<<<(unsigned)tiles.size(), 128, smem, s>>>(a);
                         }
                         PR(cudaGetLastError());
-                        unsigned long long n_cand = 0;
-                        int gram_err = 0;
-                        PR(cudaMemcpyAsync(&n_cand, d_eval.p + 2, 8, cudaMemcpyDeviceToHost, s));
-                        if (use_tc) PR(cudaMemcpyAsync(&gram_err, d_gram_err.p, 4, cudaMemcpyDeviceToHost, s));
+                        // the exact stage follows at once on the stream (it reads the candidate count on the device); one
+                        // wait per pass brings back both counters and the barrier code of the screen
+                        if (e == cudaSuccess) {
+                            prune_exact_kernel<<<(unsigned)(sm_count() * 8), 256, 0, s>>>(a);
+                            e = cudaGetLastError();
+                        }
+                        PR(cudaMemcpyAsync(&hb->n_cand, d_eval.p + 2, 8, cudaMemcpyDeviceToHost, s));
+                        PR(cudaMemcpyAsync(&hb->found, d_eval.p + 1, 8, cudaMemcpyDeviceToHost, s));
+                        if (use_tc) PR(cudaMemcpyAsync(&hb->gram_err, d_gram_err.p, 4, cudaMemcpyDeviceToHost, s));
+                        else hb->gram_err = 0;
                         PR(cudaStreamSynchronize(s));
-                        if (e == cudaSuccess && gram_err) {  // a bounded mbarrier wait of the tensor-core screen expired
-                            set_error("gram_tc_kernel: mbarrier wait %d timed out (pass k=%lld)", gram_err, (long long)k);
+                        const unsigned long long n_cand = hb->n_cand;
+                        found = hb->found;
+                        if (e == cudaSuccess && hb->gram_err) {  // a bounded mbarrier wait of the tensor-core screen expired
+                            set_error("gram_tc_kernel: mbarrier wait %d timed out (pass k=%lld)", hb->gram_err, (long long)k);
                             rc = FC_ERR_CUDA;
                             break;
                         }
-                        if (use_tc && e == cudaSuccess) {
+                        if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune screen", __FILE__, __LINE__); break; }
+                        if (use_tc) {
                             float ms = 0;
                             cudaEventElapsedTime(&ms, ev_g0, ev_g1);
                             t_gram += ms;
-                            cand_total += n_cand;
                             long long tiles_in_pass = 0;
                             for (const GramWork& wk : work) tiles_in_pass += wk.n_col_tiles;
-                            screen_slots += 2048.0 * (double)tiles_in_pass;
-                            ++screen_launches;
+                            if ((long long)n_cand <= cand_cap) {
+                                cand_total += n_cand;
+                                screen_slots += 2048.0 * (double)tiles_in_pass;
+                                ++screen_launches;
+                            }
                             if (trace) fprintf(stderr, "  pass k=%lld active=%lld items=%zu col-tiles=%lld (%.3e pair slots) screen %.3f ms, %llu candidates\n",
                                     (long long)k, (long long)n_active, work.size(), tiles_in_pass, 2048.0 * (double)tiles_in_pass, ms,
                                     n_cand);
                         }
-                        if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune screen", __FILE__, __LINE__); break; }
-                        if ((long long)n_cand > cand_cap) {  // list too small: repeat with the exact size
+                        if ((long long)n_cand > cand_cap) {  // list too small (the exact stage did nothing): repeat with the exact size
                             cand_cap = (long long)n_cand;
                             continue;
                         }
-                        if (n_cand) {
-                            prune_exact_kernel<<<(unsigned)((n_cand + 7) / 8), 256, 0, s>>>(a, (long long)n_cand);
-                            PR(cudaGetLastError());
-                            counted = true;
-                        }
+                        counted = true;
                     } else {
                         prune_pairs_kernel<<<(unsigned)tiles.size(), 256, 0, s>>>(a);
                         PR(cudaGetLastError());
                         counted = true;
+                        PR(cudaMemcpyAsync(&hb->found, d_eval.p + 1, 8, cudaMemcpyDeviceToHost, s));
+                        PR(cudaStreamSynchronize(s));
+                        found = hb->found;
+                        if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pass", __FILE__, __LINE__); break; }
                     }
-                    PR(cudaMemcpyAsync(&found, d_eval.p + 1, 8, cudaMemcpyDeviceToHost, s));
-                    PR(cudaStreamSynchronize(s));
-                    if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pass", __FILE__, __LINE__); break; }
                     if ((long long)found > pair_cap) {  // list too small: repeat the pass with the exact size
                         pair_cap = (long long)found;
                         continue;
@@ -912,7 +960,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                 use = &all_pairs;
             }
             similar_total += (int64_t)use->size();
-            prune_resolve(mask, *use, keep_first != 0, snapshot != 0);
+            prune_resolve(mask, *use, keep_first != 0, snapshot != 0, resolve_scratch);
             t_resolve += now() - tp;
         }
         if (!rc) {

@@ -83,7 +83,7 @@ class _Result:
          self.n_surv, self.n_quads, self.n_pairs, self.n_groups) = (int(x) for x in counts)
 
     def _get(self, fn, shape, dtype):
-        out = np.zeros(shape, dtype=dtype)
+        out = np.empty(shape, dtype=dtype)  # filled completely by the library
         if out.size:
             _lib.check(getattr(self.lib, fn)(self.handle, _ptr(out)), fn)
         return out
