@@ -243,18 +243,37 @@ __global__ void __launch_bounds__(256) tfd_vs_accepted_kernel(TfdArgs a, int b0,
 constexpr int kTfdBlock = 16384;            // candidates per sweep step (bit matrix of a full block: 32 MB)
 constexpr int kTfdWords = kTfdBlock / 32;
 constexpr int kTfdRowsPerCta = 256;
+constexpr int kTfdSegWords = 4;             // words of the bit matrix one CTA of the pair kernel walks
+constexpr int kTfdHead = 8;                 // terms of phase A of the pair kernel (kept in registers)
+constexpr int kTfdMaxOrderedQ = 1024;       // torsions per fingerprint up to which the pre-screen re-orders the terms
 
 // similar <=> sum_k wrap(|x_k - y_k|) < thr, on explicit fingerprint rows (shared or global memory)
 __device__ __forceinline__ bool tfd_similar_rows(const TfdArgs& a, const double* __restrict__ x, const double* __restrict__ y,
                                                  int row_new, int row_ref) {
     double sum = 0.0;
     const double stop = a.thr + a.eps;
-    for (int k = 0; k < a.q; ++k) {
+    // terms are ADDED in the reference's order; they are LOADED eight at a time so that the loads of a chunk are in
+    // flight together (one global round trip per chunk instead of one per term).  Leaving at a chunk boundary instead
+    // of at the first term over the limit changes nothing: partial sums only grow.
+    int k = 0;
+    for (; k + 8 <= a.q; k += 8) {
+        double xv[8], yv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { xv[u] = x[k + u]; yv[u] = y[k + u]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            double d = fabs(xv[u] - yv[u]);
+            d = fabs(d - (d > 180.0 ? 360.0 : 0.0));
+            sum += d;
+        }
+        if (sum > stop) return false;
+    }
+    for (; k < a.q; ++k) {
         double d = fabs(x[k] - y[k]);
         d = fabs(d - (d > 180.0 ? 360.0 : 0.0));
         sum += d;
-        if (sum > stop) return false;  // partial sums only grow: cannot come back under thr + eps
     }
+    if (sum > stop) return false;
     const bool sim = sum < a.thr;
     if (fabs(sum - a.thr) <= a.eps && a.ties) {
         int slot = atomicAdd(a.n_ties, 1);
@@ -271,52 +290,228 @@ __device__ __forceinline__ bool tfd_similar_rows(const TfdArgs& a, const double*
     return sim;
 }
 
-// CTA = 256 consecutive rows t of the block x one word (32 earlier rows i) of the bit matrix; thread = one row.
-// The lanes of a warp compare their own rows with the SAME earlier row at a time (shared-memory broadcast).
-// Rows already rejected against rows accepted in earlier blocks take no part (their words are 0).
-__global__ void __launch_bounds__(kTfdRowsPerCta) tfd_block_matrix_kernel(TfdArgs a, int b0, int nb, int W, int use_smem,
-                                                                          unsigned* __restrict__ simT) {
-    extern __shared__ double s_fp[];
-    const int w = blockIdx.x % W, rt = blockIdx.x / W;
-    const int t = rt * kTfdRowsPerCta + threadIdx.x;
-    const int t_hi = min(nb, (rt + 1) * kTfdRowsPerCta);  // rows of this CTA: [rt * 256, t_hi)
-    if (32 * w >= t_hi - 1) {  // no row of the CTA has an earlier row in this word
-        if (t < nb) simT[(size_t)t * W + w] = 0u;
-        return;
-    }
-    const int qs = a.q | 1;  // odd stride: conflict-free 64-bit rows
-    double* s_rows = s_fp;
-    double* s_cols = s_fp + (size_t)kTfdRowsPerCta * qs;
-    __shared__ int s_cflag[32];
-    if (threadIdx.x < 32) {
-        const int i = 32 * w + threadIdx.x;
-        s_cflag[threadIdx.x] = i < nb ? a.flag[b0 + i] : 1;
-    }
-    if (use_smem) {
-        for (int e = threadIdx.x; e < 32 * a.q; e += blockDim.x) {
-            const int j = e / a.q, k = e - j * a.q, i = 32 * w + j;
-            s_cols[j * qs + k] = i < nb ? a.fp[(size_t)(b0 + i) * a.q + k] : 0.0;
+// Order in which the FP32 pre-screen adds the torsion terms: most scattered torsion first (circular variance over a
+// sample of the rows), so that dissimilar pairs leave the loop after a few terms.  Speed only: the pre-screen has a
+// margin and every pair it cannot rule out is decided by the FP64 sum in the reference's term order.
+__global__ void __launch_bounds__(1024) tfd_order_kernel(const double* __restrict__ fp, int n, int q, int* __restrict__ perm) {
+    __shared__ float s_score[kTfdMaxOrderedQ];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_sample = min(n, 1024), stride = max(1, n / n_sample);
+    for (int k = warp; k < q; k += 32) {
+        float c = 0.f, sn = 0.f;
+        for (int r = lane; r < n_sample; r += 32) {
+            float sv, cv;
+            __sincosf((float)fp[(size_t)r * stride * q + k] * 0.017453292f, &sv, &cv);
+            c += cv;
+            sn += sv;
         }
-        const int rows = t_hi - rt * kTfdRowsPerCta;
-        for (int e = threadIdx.x; e < rows * a.q; e += blockDim.x) {
-            const int j = e / a.q, k = e - j * a.q;
-            s_rows[j * qs + k] = a.fp[(size_t)(b0 + rt * kTfdRowsPerCta + j) * a.q + k];
+        for (int o = 16; o > 0; o >>= 1) {
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+            sn += __shfl_xor_sync(0xffffffffu, sn, o);
         }
+        if (lane == 0) s_score[k] = c * c + sn * sn;  // small = scattered
     }
     __syncthreads();
-    if (t >= nb) return;
-    unsigned word = 0u;
-    if (a.flag[b0 + t] == 0) {
-        const double* x = use_smem ? s_rows + (size_t)threadIdx.x * qs : a.fp + (size_t)(b0 + t) * a.q;
-        for (int j = 0; j < 32; ++j) {
-            const int i = 32 * w + j;
-            if (i >= t) break;
-            if (s_cflag[j]) continue;
-            const double* y = use_smem ? s_cols + (size_t)j * qs : a.fp + (size_t)(b0 + i) * a.q;
-            if (tfd_similar_rows(a, x, y, b0 + t, b0 + i)) word |= 1u << j;
+    // rank of every term (ties by index): a stable sort by ascending score
+    for (int k = threadIdx.x; k < q; k += blockDim.x) {
+        int rank = 0;
+        const float mine = s_score[k];
+        for (int j = 0; j < q; ++j) rank += (s_score[j] < mine || (s_score[j] == mine && j < k)) ? 1 : 0;
+        perm[rank] = k;
+    }
+}
+
+// Group culling.  Rows come in the reference's enumeration order, so 32 consecutive rows mostly share their conformers
+// and with them most torsions: per group of 32 rows (one word of the bit matrix) and torsion, the interval of the values
+// (tfd_group_box_kernel); two groups whose intervals are apart by more than the threshold in the wrapped L1 norm
+// cannot hold a similar pair, and the pair kernel skips the whole 32 x 32 word (tfd_group_sep_kernel: one bit per
+// (row group, word)).  A lower bound only: groups that straddle +-180 degrees have wide intervals and are simply not culled.
+__global__ void __launch_bounds__(128) tfd_group_box_kernel(const double* __restrict__ fp, int b0, int nb, int q, int W,
+                                                            float* __restrict__ gmin, float* __restrict__ gmax) {
+    const int g = blockIdx.x;
+    const int r_end = min(32, nb - 32 * g);
+    for (int k = threadIdx.x; k < q; k += blockDim.x) {
+        float lo = 1e30f, hi = -1e30f;
+        for (int r = 0; r < r_end; ++r) {
+            const float v = (float)fp[(size_t)(b0 + 32 * g + r) * q + k];
+            lo = fminf(lo, v);
+            hi = fmaxf(hi, v);
+        }
+        gmin[(size_t)k * W + g] = lo;
+        gmax[(size_t)k * W + g] = hi;
+    }
+}
+
+// sep[rg * Wd + (w >> 5)] bit (w & 31) = 1: no row of group rg can be similar to a row of group w (w <= rg)
+__global__ void __launch_bounds__(128) tfd_group_sep_kernel(const float* __restrict__ gmin, const float* __restrict__ gmax, int W,
+                                                            int Wd, int q, float limit, unsigned* __restrict__ sep) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x, rg = blockIdx.y;
+    bool apart = true;
+    if (w < W && w <= rg) {
+        float sum = 0.f;
+        for (int k = 0; k < q && sum <= limit; ++k) {
+            const float a0 = gmin[(size_t)k * W + rg], a1 = gmax[(size_t)k * W + rg];
+            const float c0 = gmin[(size_t)k * W + w], c1 = gmax[(size_t)k * W + w];
+            const float gap = fmaxf(0.f, fmaxf(c0 - a1, a0 - c1));       // linear gap of the intervals
+            const float far = fmaxf(a1 - c0, c1 - a0);                   // largest linear difference of two members
+            sum += fmaxf(0.f, fminf(gap, 360.0f - far));                 // wrapped distance of any two members is at least this
+        }
+        apart = sum > limit;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, apart);
+    if ((threadIdx.x & 31) == 0 && w < 32 * Wd) sep[(size_t)rg * Wd + (w >> 5)] = m;
+}
+
+// CTA = 256 consecutive rows t of the block x a segment of kTfdSegWords words of the bit matrix (32 earlier rows each);
+// thread = one row.  The rows' fingerprints are staged once per CTA as FP32 in the order of `perm`, the 32 earlier rows
+// of a word per step; the lanes of a warp compare their own rows with the SAME earlier row at a time (broadcast).
+// FP32 pre-screen: the wrapped L1 distance of FP32-rounded fingerprints differs from the FP64 one by less than
+// `margin` (2e-4 per term, 0.02 floor: 50x the rounding analysis), so a pair whose FP32 sum exceeds thr + margin is
+// dissimilar and not near the threshold; everything else is decided (and, near the threshold, listed) in FP64.
+// Rows already rejected against rows accepted in earlier blocks take no part (their words are 0).
+__global__ void __launch_bounds__(kTfdRowsPerCta) tfd_block_matrix_kernel(TfdArgs a, int b0, int nb, int W, const int* __restrict__ perm,
+                                                                          const unsigned* __restrict__ sep, int Wd,
+                                                                          unsigned* __restrict__ simT) {
+    extern __shared__ float s_fp32[];
+    const int n_seg = (W + kTfdSegWords - 1) / kTfdSegWords;
+    const int seg = blockIdx.x % n_seg, rt = blockIdx.x / n_seg;
+    const int rows_per_cta = (int)blockDim.x;  // 256, fewer when the fingerprints are long
+    const int row0 = rt * rows_per_cta;
+    const int t = row0 + threadIdx.x;
+    const int t_hi = min(nb, row0 + rows_per_cta);  // rows of this CTA: [row0, t_hi)
+    const int w_lo = seg * kTfdSegWords, w_hi = min(W, w_lo + kTfdSegWords);
+    // words of the segment that hold an earlier row of some row of the CTA: 32 w < t_hi - 1
+    const int w_live = min(w_hi, (t_hi - 1 + 31) / 32);
+    if (w_live <= w_lo) {
+        if (t < nb)
+            for (int w = w_lo; w < w_hi; ++w) simT[(size_t)t * W + w] = 0u;
+        return;
+    }
+    // group culling bits of this CTA's row groups (one per warp) for the words of the segment
+    __shared__ unsigned s_sep[kTfdRowsPerCta / 32];
+    if (threadIdx.x < (int)blockDim.x / 32) {
+        const int rg = row0 / 32 + threadIdx.x;
+        s_sep[threadIdx.x] = rg < W ? (sep[(size_t)rg * Wd + (w_lo >> 5)] >> (w_lo & 31)) : 0xffffffffu;
+    }
+    __syncthreads();
+    {
+        unsigned all_apart = 0xffffffffu;
+        for (int k = 0; k < (int)blockDim.x / 32; ++k) all_apart &= s_sep[k];
+        bool any_live = false;
+        for (int w = w_lo; w < w_live; ++w) any_live |= !((all_apart >> (w - w_lo)) & 1u);
+        if (!any_live) {  // CTA-uniform: nothing in this segment can be similar
+            if (t < nb)
+                for (int w = w_lo; w < w_hi; ++w) simT[(size_t)t * W + w] = 0u;
+            return;
         }
     }
-    simT[(size_t)t * W + w] = word;
+    const int q = a.q, qs = q | 1;  // odd stride: conflict-free rows
+    float* s_rows = s_fp32;
+    float* s_cols = s_fp32 + (size_t)rows_per_cta * qs;
+    __shared__ int s_cflag[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < t_hi - row0; r += rows_per_cta / 32) {
+        const double* src = a.fp + (size_t)(b0 + row0 + r) * q;
+        for (int k = lane; k < q; k += 32) s_rows[r * qs + k] = (float)src[perm[k]];
+    }
+    const bool mine = t < nb && a.flag[b0 + t] == 0;
+    const float margin = 0.02f + 2e-4f * (float)q;
+    const float stop = (float)a.thr + margin;
+    // Two phases per word, because the cost of a warp is the cost of its slowest lane: (A) every lane adds the first
+    // kTfdHead terms of its row against each earlier row -- almost every pair is over the limit by then; (B) the few pairs
+    // that are not go to a per-warp queue and are finished 32 at a time, one pair per lane (the remaining FP32 terms,
+    // then the FP64 sum), so the long evaluations run on full warps.  Bits are set in a shared word per row.
+    __shared__ unsigned s_word[kTfdRowsPerCta];
+    __shared__ unsigned short s_queue[kTfdRowsPerCta / 32][64];
+    unsigned short* queue = s_queue[warp];
+    const int head = min(q, kTfdHead);
+    float xh[kTfdHead];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kTfdHead; ++k) xh[k] = k < head ? s_rows[(size_t)threadIdx.x * qs + k] : 0.f;
+    // finishes `cnt` queued pairs of this warp (entry = row within the warp << 5 | column within the word)
+    auto flush = [&](int cnt, int w) {
+        __syncwarp();
+        if (lane < cnt) {
+            const int ent = queue[lane], rl = ent >> 5, j = ent & 31;
+            const float* xx = s_rows + (size_t)(warp * 32 + rl) * qs;
+            const float* yy = s_cols + (size_t)j * qs;
+            float sum = 0.f;
+            for (int k = 0; k < q; ++k) {
+                const float d = fabsf(xx[k] - yy[k]);
+                sum += fminf(d, 360.0f - d);
+            }
+            if (sum <= stop) {
+                const int tt = row0 + warp * 32 + rl, i = 32 * w + j;
+                if (tfd_similar_rows(a, a.fp + (size_t)(b0 + tt) * q, a.fp + (size_t)(b0 + i) * q, b0 + tt, b0 + i))
+                    atomicOr(&s_word[warp * 32 + rl], 1u << j);
+            }
+        }
+        __syncwarp();
+    };
+    for (int w = w_lo; w < w_hi; ++w) {
+        bool word_live = w < w_live;  // CTA-uniform
+        if (word_live) {
+            unsigned all_apart = 1u;
+            for (int k = 0; k < (int)blockDim.x / 32; ++k) all_apart &= s_sep[k] >> (w - w_lo);
+            word_live = !(all_apart & 1u);
+        }
+        if (!word_live) {
+            if (t < nb) simT[(size_t)t * W + w] = 0u;
+            continue;
+        }
+        __syncthreads();  // the previous word's columns are no longer read
+        for (int r = warp; r < 32; r += rows_per_cta / 32) {
+            const int i = 32 * w + r;
+            if (lane == 0) s_cflag[r] = i < nb ? a.flag[b0 + i] : 1;
+            if (i < nb) {
+                const double* src = a.fp + (size_t)(b0 + i) * q;
+                for (int k = lane; k < q; k += 32) s_cols[r * qs + k] = (float)src[perm[k]];
+            }
+        }
+        s_word[threadIdx.x] = 0u;
+        __syncthreads();
+        int qn = 0;  // warp-uniform fill level of the queue
+        // earlier rows of this word for the LAST row of the warp (the lanes' own limits are checked per pair)
+        const int j_warp = ((s_sep[warp] >> (w - w_lo)) & 1u) ? 0 : min(32, row0 + warp * 32 + 31 - 32 * w);
+        for (int j = 0; j < j_warp; ++j) {
+            if (s_cflag[j]) continue;  // warp-uniform
+            const float* y = s_cols + (size_t)j * qs;
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < kTfdHead; ++k) {
+                const float d = fabsf(xh[k] - (k < head ? y[k] : 0.f));
+                sum += fminf(d, 360.0f - d);
+            }
+            const bool go_on = mine && 32 * w + j < t && sum <= stop;
+            const unsigned m = __ballot_sync(0xffffffffu, go_on);
+            if (m == 0u) continue;
+            const int add = __popc(m);
+            if (qn + add > 64) {
+                flush(min(qn, 32), w);  // qn <= 63 here: at most two rounds
+                if (qn > 32) {
+                    __syncwarp();
+                    if (lane < qn - 32) queue[lane] = queue[32 + lane];
+                    __syncwarp();
+                    flush(qn - 32, w);
+                }
+                qn = 0;
+            }
+            if (go_on) queue[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)((lane << 5) | j);
+            qn += add;
+        }
+        if (qn > 0) {
+            flush(min(qn, 32), w);
+            if (qn > 32) {
+                __syncwarp();
+                if (lane < qn - 32) queue[lane] = queue[32 + lane];
+                __syncwarp();
+                flush(qn - 32, w);
+            }
+        }
+        __syncwarp();
+        if (t < nb) simT[(size_t)t * W + w] = s_word[threadIdx.x];
+    }
 }
 
 // Rounds of the rule above over one block.  Cooperative launch, one CTA per SM.  Every CTA keeps its own copy of the
@@ -426,10 +621,23 @@ int tfd_keepfirst_dev(const double* fp, const long long* label, int n, int q, do
     int* rounds = reinterpret_cast<int*>(verdict + verdict_bytes);
     FC_CUDA(cudaMemsetAsync(rounds, 0, 16, s));
     TfdArgs a{fp, label, q, thr, eps, flag, acc, n_acc, ties, n_ties, tie_cap};
-    const size_t fp_smem = (size_t)(kTfdRowsPerCta + 32) * (size_t)(q | 1) * sizeof(double);
-    const int use_smem = fp_smem <= 200 * 1024 ? 1 : 0;
-    if (use_smem)
-        FC_CUDA(cudaFuncSetAttribute(tfd_block_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp_smem));
+    // FP32 copies of the rows of a CTA (256, fewer for long fingerprints) and of one word's earlier rows (32), staged in
+    // the pre-screen's term order
+    int rows_per_cta = kTfdRowsPerCta;
+    while (rows_per_cta > 32 && (size_t)(rows_per_cta + 32) * (size_t)(q | 1) * sizeof(float) > 200 * 1024) rows_per_cta /= 2;
+    const size_t fp_smem = (size_t)(rows_per_cta + 32) * (size_t)(q | 1) * sizeof(float);
+    FC_REQUIRE(fp_smem <= 200 * 1024 && q <= kTfdMaxOrderedQ, "fc_tfd: %d torsions per fingerprint are more than the sweep stages (800)", q);
+    FC_CUDA(cudaFuncSetAttribute(tfd_block_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp_smem));
+    int* perm = nullptr;
+    float* gbox = nullptr;    // [2][q][w_max] interval of every torsion over every group of 32 rows
+    unsigned* sep = nullptr;  // [w_max][wd_max] culling bits
+    const int wd_max = (w_max + 31) / 32;
+    FC_CUDA(cudaMallocAsync((void**)&perm, (size_t)std::max(q, 1) * sizeof(int), s));
+    FC_CUDA(cudaMallocAsync((void**)&gbox, (size_t)2 * std::max(q, 1) * w_max * sizeof(float), s));
+    FC_CUDA(cudaMallocAsync((void**)&sep, (size_t)w_max * wd_max * sizeof(unsigned), s));
+    // the same margins as the FP32 pre-screen of the pair kernel, once more for the FP32 interval arithmetic
+    const float sep_limit = (float)thr + 2.0f * (0.02f + 2e-4f * (float)q);
+    tfd_order_kernel<<<1, 1024, 0, s>>>(fp, n, q, perm);
     const int grid = sm_count() * 8;
     cudaError_t e = cudaSuccess;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -438,8 +646,13 @@ int tfd_keepfirst_dev(const double* fp, const long long* label, int n, int q, do
         int nb = std::min(n - b0, kTfdBlock), W = (nb + 31) / 32;
         if (b0 > 0) tfd_vs_accepted_kernel<<<grid, 256, 0, s>>>(a, b0, b0 + nb);
         if (trace) cudaEventRecord(ev[0], s);
-        const unsigned ctas = (unsigned)(((nb + kTfdRowsPerCta - 1) / kTfdRowsPerCta) * W);
-        tfd_block_matrix_kernel<<<ctas, kTfdRowsPerCta, use_smem ? fp_smem : 0, s>>>(a, b0, nb, W, use_smem, simT);
+        const unsigned ctas = (unsigned)(((nb + rows_per_cta - 1) / rows_per_cta) * ((W + kTfdSegWords - 1) / kTfdSegWords));
+        const int Wd = (W + 31) / 32;
+        float* gmin = gbox;
+        float* gmax = gbox + (size_t)std::max(q, 1) * w_max;
+        tfd_group_box_kernel<<<(unsigned)W, 128, 0, s>>>(fp, b0, nb, q, W, gmin, gmax);
+        tfd_group_sep_kernel<<<dim3((unsigned)(32 * Wd + 127) / 128, (unsigned)W), 128, 0, s>>>(gmin, gmax, W, Wd, q, sep_limit, sep);
+        tfd_block_matrix_kernel<<<ctas, rows_per_cta, fp_smem, s>>>(a, b0, nb, W, perm, sep, Wd, simT);
         e = cudaGetLastError();
         if (e != cudaSuccess) break;
         if (trace) cudaEventRecord(ev[1], s);
@@ -461,6 +674,9 @@ int tfd_keepfirst_dev(const double* fp, const long long* label, int n, int q, do
     if (trace) for (auto& x : ev) cudaEventDestroy(x);
     cudaFreeAsync(simT, s);
     cudaFreeAsync(verdict, s);
+    cudaFreeAsync(perm, s);
+    cudaFreeAsync(gbox, s);
+    cudaFreeAsync(sep, s);
     FC_CUDA(e);
     return FC_OK;
 }

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -146,6 +147,10 @@ cudaError_t upload_rows_staged(double* dst, const double* src, int64_t n, int n_
             cv.notify_all();
         }
     };
+    const bool trace = getenv("FC_PRUNE_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_wait_fill = 0, t_wait_slot = 0;
     std::vector<std::thread> workers;
     workers.reserve((size_t)nt);
     for (int t = 0; t < nt; ++t) workers.emplace_back(fill, t);
@@ -154,7 +159,9 @@ cudaError_t upload_rows_staged(double* dst, const double* src, int64_t n, int n_
     // slot of piece r is free once the copy of piece r - kUpSlots has left the host (an event never recorded is complete)
     auto release_upto = [&](int64_t limit) {
         while (next_release < n_pieces && next_release < limit && err == cudaSuccess) {
+            const double tw = now();
             err = cudaEventSynchronize(st.ev[next_release % kUpSlots]);
+            t_wait_slot += now() - tw;
             ++next_release;
             {
                 std::lock_guard<std::mutex> lk(mu);
@@ -166,8 +173,10 @@ cudaError_t upload_rows_staged(double* dst, const double* src, int64_t n, int n_
     release_upto(kUpSlots - 1);
     for (int64_t c = 0; c < n_pieces && err == cudaSuccess; ++c) {
         {
+            const double tw = now();
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return filled[(size_t)c] == nt; });
+            t_wait_fill += now() - tw;
         }
         const int64_t r0 = c * rows_per_piece, rows = std::min(rows_per_piece, n - r0);
         err = cudaMemcpyAsync((char*)dst + (size_t)r0 * row_out, st.base + (size_t)(c % kUpSlots) * kUpSlotBytes,
@@ -182,6 +191,10 @@ cudaError_t upload_rows_staged(double* dst, const double* src, int64_t n, int n_
     }
     cv.notify_all();
     for (auto& w : workers) w.join();
+    if (trace)
+        fprintf(stderr, "  upload_rows_staged: %lld rows, %.1f MB in %lld pieces, %d threads: %.2f ms on the host (waited %.2f ms for the "
+                "threads to fill, %.2f ms for the copy engine to free slots)\n", (long long)n, 1e-6 * (double)n * (double)row_out,
+                (long long)n_pieces, nt, now() - t_begin, t_wait_fill, t_wait_slot);
     return err;
 }
 

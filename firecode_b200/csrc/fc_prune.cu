@@ -24,6 +24,8 @@
 #include <chrono>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "fc_embed.cuh"
 #include "fc_gram_tc.cuh"
 
@@ -131,6 +133,9 @@ struct PruneArgs {
     int2* pairs;                 // similar pairs found in this pass (structure indices, x < y)
     unsigned long long* n_pairs; // ... their number (may exceed pair_cap: the pass is then repeated)
     long long pair_cap;
+    int swap_xy;                 // 1: a pair is stored {later, earlier} (keep-first), 0: {earlier, later} (keep-last) -- the
+                                 // structure that decides (the "head") is always .y, the droppable one .x, so that the
+                                 // list sorts by head as 64-bit keys
     unsigned long long* n_eval;  // pairs fully evaluated
     TieRecord* ties;
     int* n_ties;
@@ -143,7 +148,7 @@ struct PruneArgs {
 // similar pairs go to a compact list (sparse: survivors of earlier passes are mutually dissimilar)
 __device__ __forceinline__ void prune_push_pair(const PruneArgs& a, int s_lo, int s_hi) {
     unsigned long long slot = atomicAdd(a.n_pairs, 1ull);
-    if ((long long)slot < a.pair_cap) a.pairs[slot] = make_int2(s_lo, s_hi);
+    if ((long long)slot < a.pair_cap) a.pairs[slot] = a.swap_xy ? make_int2(s_hi, s_lo) : make_int2(s_lo, s_hi);
 }
 
 // 256 threads: thread (tx = column, ty) owns pairs (row ty + 8u, column tx), u = 0..3
@@ -462,23 +467,35 @@ static const int64_t kSchedule[] = {500000, 200000, 100000, 50000, 20000, 10000,
 //   snapshot : a structure is dropped if any structure on its keeper side that was active at the start of
 //              the pass is similar to it.
 struct ResolveScratch {
-    std::vector<int> off, adj;  // CSR of the similar pairs by keeper-side structure, reused from pass to pass
+    std::vector<int> off, adj;  // CSR of the similar pairs by head, reused from pass to pass
 };
 
+// A pair is {.x = droppable structure, .y = head}: the head, while alive, drops the other one (PruneArgs::swap_xy).
+// `sorted`: the list is ordered by head (ascending), as the single-rank driver gets it from the device sort -- one linear
+// scan, forwards for keep-first (heads are the earlier structures) and backwards for keep-last.  Otherwise (lists
+// gathered from several ranks) the pairs are bucketed by head first.
 static void prune_resolve(std::vector<uint8_t>& mask, const std::vector<int2>& pairs, bool keep_first, bool snapshot,
-                          ResolveScratch& sc) {
+                          bool sorted, ResolveScratch& sc) {
     if (pairs.empty()) return;
     if (snapshot) {
-        for (const int2& p : pairs) mask[(size_t)(keep_first ? p.y : p.x)] = 0;
+        for (const int2& p : pairs) mask[(size_t)p.x] = 0;
         return;
     }
-    const size_t n = mask.size();
-    // structures that head at least one pair lie in [lo, hi]: the counting and the sweep stay inside that range
-    int lo = (int)n, hi = -1;
+    if (sorted) {
+        if (keep_first) {
+            for (const int2& p : pairs)
+                if (mask[(size_t)p.y]) mask[(size_t)p.x] = 0;
+        } else {
+            for (size_t e = pairs.size(); e-- > 0;)
+                if (mask[(size_t)pairs[e].y]) mask[(size_t)pairs[e].x] = 0;
+        }
+        return;
+    }
+    // heads lie in [lo, hi]: the counting and the sweep stay inside that range
+    int lo = (int)mask.size(), hi = -1;
     for (const int2& p : pairs) {
-        const int h = keep_first ? p.x : p.y;
-        lo = std::min(lo, h);
-        hi = std::max(hi, h);
+        lo = std::min(lo, p.y);
+        hi = std::max(hi, p.y);
     }
     const size_t span = (size_t)(hi - lo) + 2;
     if (sc.off.size() < span) sc.off.resize(span);
@@ -486,14 +503,10 @@ static void prune_resolve(std::vector<uint8_t>& mask, const std::vector<int2>& p
     int* off = sc.off.data();
     int* adj = sc.adj.data();
     memset(off, 0, span * sizeof(int));
-    for (const int2& p : pairs) off[(keep_first ? p.x : p.y) - lo + 1] += 1;
+    for (const int2& p : pairs) off[p.y - lo + 1] += 1;
     for (size_t i = 1; i < span; ++i) off[i] += off[i - 1];
-    // fill backwards so that off[i] ends up at the start of row i again
-    for (const int2& p : pairs) {
-        if (keep_first) adj[off[p.x - lo + 1]-- - 1] = p.y;
-        else adj[off[p.y - lo + 1]-- - 1] = p.x;
-    }
-    // after the fill off[i + 1] holds the START of row i; its end is the start of row i + 1, the last row ends at pairs.size()
+    // fill backwards: afterwards off[i + 1] holds the START of row i; its end is the start of row i + 1
+    for (const int2& p : pairs) adj[off[p.y - lo + 1]-- - 1] = p.x;
     auto row_begin = [&](size_t i) { return off[i + 1]; };
     auto row_end = [&](size_t i) { return i + 2 < span ? off[i + 2] : (int)pairs.size(); };
     if (keep_first) {
@@ -711,7 +724,8 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
     {
         DevBuf<double> d_coords, d_xc, d_g, d_moi, d_mass, d_energy;
         DevBuf<int> d_sel, d_active, d_nties;
-        DevBuf<int2> d_pairs, d_cand;
+        DevBuf<int2> d_pairs, d_cand, d_pairs_sorted;
+        DevBuf<uint8_t> d_sort_tmp;
         DevBuf<float4> d_xcf;
         DevBuf<PruneTile> d_tiles;
         DevBuf<float> d_img, d_gp;       // tensor-core screen: operand image and |x|^2 per padded position
@@ -764,6 +778,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
         std::vector<int64_t> prev_bounds;  // chunking of the last executed pass (empty: none yet)
         const bool over_active = (snapshot & 2) != 0;  // FC_PRUNE_CHUNK_ACTIVE
         snapshot &= 1;
+        const bool sort_pairs = world == 1 && !snapshot;  // a single rank's list is sorted by head on the device
         // screen flavour: FC_PRUNE_FP64=1 -> FP64 pair kernel only; otherwise FP32 screen + FP64 exact stage, the screen
         // on the tensor cores (gram_tc_kernel) unless FC_PRUNE_TC=0 or the molecule has more than 88 selected atoms (kGramMaxKc)
         const char* env64 = getenv("FC_PRUNE_FP64");
@@ -855,6 +870,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                     a.max_rmsd = max_rmsd; a.max_dev = max_dev; a.max_dE = max_dE; a.moi_dev = moi_dev; a.eps = FC_NEAR_EPS;
                     a.pairs = d_pairs.p; a.n_pairs = d_eval.p + 1; a.pair_cap = pair_cap;
                     a.cand = d_cand.p; a.n_cand = d_eval.p + 2; a.cand_cap = cand_cap;
+                    a.swap_xy = keep_first ? 1 : 0;
                     a.n_eval = !counted ? d_eval.p : nullptr;
                     a.ties = (ties_out && !counted) ? d_ties.p : nullptr; a.n_ties = d_nties.p; a.tie_cap = cap;
                     unsigned long long found = 0;
@@ -936,7 +952,24 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                     }
                     pairs.resize((size_t)found);
                     if (found) {
-                        e = cudaMemcpy(pairs.data(), d_pairs.p, (size_t)found * sizeof(int2), cudaMemcpyDeviceToHost);
+                        const int2* src = d_pairs.p;
+                        if (sort_pairs && found > 1) {
+                            // order the list by head on the device (radix sort on the bits of the head only): the host
+                            // then resolves the pass in one linear scan instead of bucketing the pairs itself
+                            int head_bits = 1;
+                            while (((int64_t)1 << head_bits) < n) ++head_bits;
+                            if (d_pairs_sorted.n < (size_t)pair_cap) PR(d_pairs_sorted.alloc((size_t)pair_cap, s));
+                            size_t need = 0;
+                            PR(cub::DeviceRadixSort::SortKeys(nullptr, need, (const unsigned long long*)d_pairs.p,
+                                                              (unsigned long long*)d_pairs_sorted.p, (int)found, 32, 32 + head_bits, s));
+                            if (d_sort_tmp.n < need) PR(d_sort_tmp.alloc(need + need / 4 + 256, s));
+                            need = d_sort_tmp.n;
+                            PR(cub::DeviceRadixSort::SortKeys(d_sort_tmp.p, need, (const unsigned long long*)d_pairs.p,
+                                                              (unsigned long long*)d_pairs_sorted.p, (int)found, 32, 32 + head_bits, s));
+                            src = d_pairs_sorted.p;
+                        }
+                        PR(cudaMemcpyAsync(pairs.data(), src, (size_t)found * sizeof(int2), cudaMemcpyDeviceToHost, s));
+                        PR(cudaStreamSynchronize(s));
                         if (e != cudaSuccess) rc = cuda_fail(e, "fc_prune pair readback", __FILE__, __LINE__);
                     }
                     break;
@@ -960,7 +993,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                 use = &all_pairs;
             }
             similar_total += (int64_t)use->size();
-            prune_resolve(mask, *use, keep_first != 0, snapshot != 0, resolve_scratch);
+            prune_resolve(mask, *use, keep_first != 0, snapshot != 0, sort_pairs, resolve_scratch);
             t_resolve += now() - tp;
         }
         if (!rc) {

@@ -43,11 +43,14 @@ def keepfirst_gpu(fp, thr=10.0):
     return out.astype(bool)
 
 
-@pytest.mark.parametrize("n,q,centres", [(1, 3, 1), (2, 3, 1), (700, 4, 40), (20000, 5, 900), (40000, 3, 2500)])
+@pytest.mark.parametrize("n,q,centres", [(1, 3, 1), (2, 3, 1), (700, 4, 40), (20000, 5, 900), (40000, 3, 2500), (5000, 37, 200),
+                                         (3000, 300, 60)])
 def test_keepfirst_matches_sequential_sweep(gpu, n, q, centres):
     rng = np.random.default_rng(n + q)
     base = rng.uniform(-180.0, 180.0, size=(centres, q))
-    fp = base[rng.integers(0, centres, size=n)] + rng.normal(scale=2.5, size=(n, q))
+    # copies of a centre differ by about the threshold (10) in the wrapped L1 norm: both verdicts occur; q = 300 makes
+    # the pair kernel stage fewer rows per CTA, q = 37 is an odd fingerprint length
+    fp = base[rng.integers(0, centres, size=n)] + rng.normal(scale=8.0 / q, size=(n, q))
     fp = (fp + 180.0) % 360.0 - 180.0   # values on both sides of the +-180 wrap
     ref, margin = keepfirst_numpy(fp)
     assert margin > 1e-6            # no decision of this input sits on the threshold
