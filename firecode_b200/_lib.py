@@ -81,6 +81,9 @@ class Cyclical3ProblemC(C.Structure):
 # int (*fc_allgather_fn)(const void* send, int64_t send_bytes, const void** recv, int64_t* recv_bytes, void* ctx)
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, VP, C.c_int64, C.POINTER(VP), C.POINTER(C.c_int64), VP)
 
+# int (*fc_allgather_dev_fn)(const void* send_dev, void* recv_dev, int64_t bytes, void* stream, void* ctx)
+ALLGATHER_DEV_FN = C.CFUNCTYPE(C.c_int, VP, VP, C.c_int64, VP, VP)
+
 # name -> (restype, argtypes); must list every symbol include/firecode_b200.h declares
 SIGNATURES = {
     "fc_result_free": (None, [VP]),
@@ -103,6 +106,9 @@ SIGNATURES = {
     "fc_prune_sharded": (C.c_int, [VP, C.c_int64, C.c_int32, C.c_int32, VP, C.c_int32, VP, C.c_double, C.c_double,
                                    C.c_double, VP, C.c_double, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP,
                                    C.c_int64, c_i64p, C.c_int32, C.c_int32, ALLGATHER_FN, VP]),
+    "fc_prune_sharded_dev": (C.c_int, [VP, C.c_int64, C.c_int32, C.c_int32, VP, C.c_int32, VP, C.c_double, C.c_double,
+                                       C.c_double, VP, C.c_double, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP,
+                                       C.c_int64, c_i64p, C.c_int32, C.c_int32, ALLGATHER_DEV_FN, VP]),
     "fc_tfd_fingerprints": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_int32, VP]),
     "fc_tfd_first_match": (C.c_int, [VP, C.c_int64, C.c_int32, VP, VP, C.c_int64, C.c_double, VP, VP, C.c_int64, c_i64p]),
     "fc_csearch_apply": (C.c_int, [VP, C.c_int32, C.c_int32, VP, C.c_int32, VP, VP, C.c_int64, C.c_double, C.c_int32,

@@ -6,6 +6,7 @@
 // (only the heavy atoms of it) in a third of the time.
 // fc_take_rows: the `structures[mask]` copy every pruning entry point returns
 // (/root/reference/firecode/embedder.py:1400-1408 consumes it), done by several threads.
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -17,6 +18,10 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "fc_embed.cuh"
 
@@ -43,6 +48,36 @@ static int host_threads() {
         return (int)std::max(1u, std::min(16u, hc / per_core));
     }();
     return n;
+}
+
+// memcpy with non-temporal stores for the big one-way copies of this file (staging buffers the copy engine reads next,
+// result arrays the caller reads much later): the destination lines are not read into the cache first, which saves a
+// third of the memory traffic of a plain copy.  Falls back to memcpy for unaligned or short pieces.
+static inline void copy_stream(void* dst, const void* src, size_t bytes) {
+#if defined(__SSE2__)
+    if (bytes >= 256 && ((reinterpret_cast<uintptr_t>(dst) | bytes) & 15u) == 0) {
+        __m128i* d = static_cast<__m128i*>(dst);
+        const __m128i* s = static_cast<const __m128i*>(src);
+        const size_t n16 = bytes / 16;
+        size_t i = 0;
+        for (; i + 4 <= n16; i += 4) {
+            const __m128i a = _mm_loadu_si128(s + i), b = _mm_loadu_si128(s + i + 1);
+            const __m128i c = _mm_loadu_si128(s + i + 2), e = _mm_loadu_si128(s + i + 3);
+            _mm_stream_si128(d + i, a);
+            _mm_stream_si128(d + i + 1, b);
+            _mm_stream_si128(d + i + 2, c);
+            _mm_stream_si128(d + i + 3, e);
+        }
+        for (; i < n16; ++i) _mm_stream_si128(d + i, _mm_loadu_si128(s + i));
+        return;
+    }
+#endif
+    memcpy(dst, src, bytes);
+}
+static inline void copy_stream_fence() {
+#if defined(__SSE2__)
+    _mm_sfence();  // the streamed lines are globally visible before anyone is told the copy is done
+#endif
 }
 
 template <class F>
@@ -132,14 +167,15 @@ cudaError_t upload_rows_staged(double* dst, const double* src, int64_t n, int n_
                 const char* in = (const char*)src + (size_t)(r0 + r) * row_in;
                 char* out = stage + (size_t)r * row_out;
                 if (!sel) {
-                    memcpy(out, in, row_out);
+                    copy_stream(out, in, row_out);
                 } else {
                     for (const auto& run : runs) {
-                        memcpy(out, in + (size_t)run.first * 24, (size_t)run.second * 24);
+                        copy_stream(out, in + (size_t)run.first * 24, (size_t)run.second * 24);
                         out += (size_t)run.second * 24;
                     }
                 }
             }
+            copy_stream_fence();
             {
                 std::lock_guard<std::mutex> lk(mu);
                 ++filled[(size_t)c];
@@ -215,8 +251,9 @@ extern "C" int fc_take_rows(const void* src, int64_t row_bytes, const uint8_t* m
                (long long)kept.size(), (long long)n_dst);
     parallel_ranges(n_dst, 256, [&](int64_t lo, int64_t hi) {
         for (int64_t j = lo; j < hi; ++j)
-            memcpy((char*)dst + (size_t)j * (size_t)row_bytes, (const char*)src + (size_t)kept[(size_t)j] * (size_t)row_bytes,
-                   (size_t)row_bytes);
+            copy_stream((char*)dst + (size_t)j * (size_t)row_bytes, (const char*)src + (size_t)kept[(size_t)j] * (size_t)row_bytes,
+                        (size_t)row_bytes);
+        copy_stream_fence();
     });
     return FC_OK;
 }

@@ -678,15 +678,21 @@ extern "C" int fc_prune_timing(double* out6) {
 // rank / world / gather: pair tiles of every pass are dealt round-robin to the ranks; the similar pairs each
 // rank finds are all-gathered through `gather` (NCCL or gloo behind the host language) and every rank resolves
 // the pass on the union, so all ranks hold the same mask after every pass.
-extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
-                                int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
-                                const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
-                                int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
-                                int64_t tie_cap, int64_t* n_ties_out, int32_t rank, int32_t world,
-                                fc_allgather_fn gather, void* gather_ctx) {
+// gather      : host all-gather of byte buffers (structures replicated on every rank, lists staged through the host);
+// gather_dev  : device all-gather of equal-sized pieces (NCCL over NVLink behind the host language): every rank uploads
+//               only its 1 / world of the structures and the pieces are exchanged between the GPUs; per pass the ranks
+//               exchange their counters (16 bytes each) and their similar-pair lists device to device, the union is
+//               sorted by head on the device and every rank resolves the same list.
+static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
+                      int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
+                      const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
+                      int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
+                      int64_t tie_cap, int64_t* n_ties_out, int32_t rank, int32_t world,
+                      fc_allgather_fn gather, fc_allgather_dev_fn gather_dev, void* gather_ctx) {
     FC_REQUIRE(n >= 0 && n < ((int64_t)1 << 31) && n_atoms > 0, "fc_prune: bad sizes");
     FC_REQUIRE(world >= 1 && rank >= 0 && rank < world, "fc_prune: bad rank / world");
-    FC_REQUIRE(world == 1 || gather, "fc_prune: a multi-rank call needs an all-gather callback");
+    FC_REQUIRE(world == 1 || gather || gather_dev, "fc_prune: a multi-rank call needs an all-gather callback");
+    const bool dev_gather = world > 1 && gather_dev != nullptr;
     if (n_ties_out) *n_ties_out = 0;
     if (stats_out) stats_out[0] = stats_out[1] = stats_out[2] = stats_out[3] = 0;
     if (n == 0) return FC_OK;
@@ -724,8 +730,10 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
     {
         DevBuf<double> d_coords, d_xc, d_g, d_moi, d_mass, d_energy;
         DevBuf<int> d_sel, d_active, d_nties;
-        DevBuf<int2> d_pairs, d_cand, d_pairs_sorted;
+        DevBuf<int2> d_pairs, d_cand, d_pairs_sorted, d_pairs_all;
         DevBuf<uint8_t> d_sort_tmp;
+        DevBuf<unsigned long long> d_counts;       // device all-gather: {similar pairs, candidates} of every rank
+        std::vector<unsigned long long> h_counts;
         DevBuf<float4> d_xcf;
         DevBuf<PruneTile> d_tiles;
         DevBuf<float> d_img, d_gp;       // tensor-core screen: operand image and |x|^2 per padded position
@@ -738,8 +746,25 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
 #define PR(call) do { if (e == cudaSuccess) e = (call); } while (0)
         // only the atoms the criterion reads travel: the selected (heavy) atoms for the RMSD, all of them for the moments
         const int n_up = mode == 0 ? n_sel : n_atoms;
-        PR(d_coords.alloc((size_t)n * n_up * 3, s));
-        PR(upload_rows_staged(d_coords.p, structures, n, n_atoms, mode == 0 ? sel : nullptr, n_up, s));
+        if (!dev_gather) {
+            PR(d_coords.alloc((size_t)n * n_up * 3, s));
+            PR(upload_rows_staged(d_coords.p, structures, n, n_atoms, mode == 0 ? sel : nullptr, n_up, s));
+        } else {
+            // this rank's 1 / world of the rows travels over PCIe; the pieces are exchanged between the GPUs
+            const int64_t per = (n + world - 1) / world, lo = std::min<int64_t>(n, per * rank), hi = std::min<int64_t>(n, lo + per);
+            const size_t piece = (size_t)per * n_up * 3;
+            DevBuf<double> d_part;
+            PR(d_coords.alloc(piece * (size_t)world, s));
+            PR(d_part.alloc(piece, s));
+            PR(cudaMemsetAsync(d_part.p, 0, piece * 8, s));
+            if (hi > lo)
+                PR(upload_rows_staged(d_part.p, structures + (size_t)lo * n_atoms * 3, hi - lo, n_atoms, mode == 0 ? sel : nullptr, n_up, s));
+            if (e == cudaSuccess && gather_dev(d_part.p, d_coords.p, (int64_t)(piece * 8), (void*)s, gather_ctx) != 0) {
+                set_error("fc_prune: device all-gather of the structures failed");
+                rc = FC_ERR_INVALID;
+            }
+            PR(cudaStreamSynchronize(s));  // d_part is released below: the exchange must have read it
+        }
         PR(d_nties.alloc(4, s));
         PR(cudaMemsetAsync(d_nties.p, 0, 16, s));
         PR(d_eval.alloc(4, s));  // [0] eigen-solves, [1] similar pairs, [2] screen candidates of the current pass
@@ -778,7 +803,13 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
         std::vector<int64_t> prev_bounds;  // chunking of the last executed pass (empty: none yet)
         const bool over_active = (snapshot & 2) != 0;  // FC_PRUNE_CHUNK_ACTIVE
         snapshot &= 1;
-        const bool sort_pairs = world == 1 && !snapshot;  // a single rank's list is sorted by head on the device
+        // a single rank's list, and the union the device all-gather builds, are sorted by head on the device
+        const bool sort_pairs = (world == 1 || dev_gather) && !snapshot;
+        if (dev_gather && rc == FC_OK) {
+            e = d_counts.alloc((size_t)2 * world, s);
+            h_counts.assign((size_t)2 * world, 0);
+            if (e != cudaSuccess) rc = cuda_fail(e, "fc_prune setup", __FILE__, __LINE__);
+        }
         // screen flavour: FC_PRUNE_FP64=1 -> FP64 pair kernel only; otherwise FP32 screen + FP64 exact stage, the screen
         // on the tensor cores (gram_tc_kernel) unless FC_PRUNE_TC=0 or the molecule has more than 88 selected atoms (kGramMaxKc)
         const char* env64 = getenv("FC_PRUNE_FP64");
@@ -932,11 +963,11 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                                     (long long)k, (long long)n_active, work.size(), tiles_in_pass, 2048.0 * (double)tiles_in_pass, ms,
                                     n_cand);
                         }
-                        if ((long long)n_cand > cand_cap) {  // list too small (the exact stage did nothing): repeat with the exact size
+                        if (!dev_gather && (long long)n_cand > cand_cap) {  // list too small (the exact stage did nothing): repeat with the exact size
                             cand_cap = (long long)n_cand;
                             continue;
                         }
-                        counted = true;
+                        counted = (long long)n_cand <= cand_cap;  // (device all-gather: the ranks decide together below)
                     } else {
                         prune_pairs_kernel<<<(unsigned)tiles.size(), 256, 0, s>>>(a);
                         PR(cudaGetLastError());
@@ -945,6 +976,67 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
                         PR(cudaStreamSynchronize(s));
                         found = hb->found;
                         if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pass", __FILE__, __LINE__); break; }
+                    }
+                    if (dev_gather) {
+                        // every rank learns every rank's counters, so all of them take the same branch below
+                        if (gather_dev(d_eval.p + 1, d_counts.p, 16, (void*)s, gather_ctx) != 0) {
+                            set_error("fc_prune: device all-gather of the counters failed");
+                            rc = FC_ERR_INVALID;
+                            break;
+                        }
+                        PR(cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)16 * world, cudaMemcpyDeviceToHost, s));
+                        PR(cudaStreamSynchronize(s));
+                        if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune counters", __FILE__, __LINE__); break; }
+                        unsigned long long max_found = 0, max_cand = 0, total = 0;
+                        for (int r = 0; r < world; ++r) {
+                            max_found = std::max(max_found, h_counts[(size_t)2 * r]);
+                            max_cand = std::max(max_cand, h_counts[(size_t)2 * r + 1]);
+                            total += h_counts[(size_t)2 * r];
+                        }
+                        if (two_stage && (long long)max_cand > cand_cap) {  // some rank's candidate list overflowed: all repeat
+                            cand_cap = (long long)max_cand;  // (`counted` stays: a rank whose own list fitted has recorded its ties)
+                            continue;
+                        }
+                        if ((long long)max_found > pair_cap) {
+                            pair_cap = (long long)max_found;
+                            continue;
+                        }
+                        pairs.resize((size_t)total);
+                        if (total) {
+                            if (d_pairs_all.n < (size_t)world * max_found) PR(d_pairs_all.alloc((size_t)world * max_found, s));
+                            if (e == cudaSuccess && gather_dev(d_pairs.p, d_pairs_all.p, (int64_t)(max_found * sizeof(int2)), (void*)s, gather_ctx) != 0) {
+                                set_error("fc_prune: device all-gather of the similar pairs failed");
+                                rc = FC_ERR_INVALID;
+                                break;
+                            }
+                            // rank-order concatenation of the filled parts, then (greedy passes) ordered by head
+                            if (d_pairs_sorted.n < (size_t)total) PR(d_pairs_sorted.alloc((size_t)total + (size_t)total / 4, s));
+                            size_t at = 0;
+                            for (int r = 0; r < world; ++r) {
+                                const size_t cnt = (size_t)h_counts[(size_t)2 * r];
+                                if (cnt) PR(cudaMemcpyAsync(d_pairs_sorted.p + at, d_pairs_all.p + (size_t)r * max_found, cnt * sizeof(int2),
+                                                            cudaMemcpyDeviceToDevice, s));
+                                at += cnt;
+                            }
+                            const int2* src = d_pairs_sorted.p;
+                            if (sort_pairs && total > 1) {
+                                int head_bits = 1;
+                                while (((int64_t)1 << head_bits) < n) ++head_bits;
+                                if (d_pairs.n < (size_t)total) PR(d_pairs.alloc((size_t)total + (size_t)total / 4, s));
+                                size_t need = 0;
+                                PR(cub::DeviceRadixSort::SortKeys(nullptr, need, (const unsigned long long*)d_pairs_sorted.p,
+                                                                  (unsigned long long*)d_pairs.p, (int)total, 32, 32 + head_bits, s));
+                                if (d_sort_tmp.n < need) PR(d_sort_tmp.alloc(need + need / 4 + 256, s));
+                                need = d_sort_tmp.n;
+                                PR(cub::DeviceRadixSort::SortKeys(d_sort_tmp.p, need, (const unsigned long long*)d_pairs_sorted.p,
+                                                                  (unsigned long long*)d_pairs.p, (int)total, 32, 32 + head_bits, s));
+                                src = d_pairs.p;
+                            }
+                            PR(cudaMemcpyAsync(pairs.data(), src, (size_t)total * sizeof(int2), cudaMemcpyDeviceToHost, s));
+                            PR(cudaStreamSynchronize(s));
+                            if (e != cudaSuccess) rc = cuda_fail(e, "fc_prune pair exchange", __FILE__, __LINE__);
+                        }
+                        break;
                     }
                     if ((long long)found > pair_cap) {  // list too small: repeat the pass with the exact size
                         pair_cap = (long long)found;
@@ -979,7 +1071,7 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
             t_kernels += now() - tp;
             tp = now();
             const std::vector<int2>* use = &pairs;
-            if (world > 1) {
+            if (world > 1 && !dev_gather) {
                 const void* recv = nullptr;
                 int64_t recv_bytes = 0;
                 int grc = gather(pairs.data(), (int64_t)(pairs.size() * sizeof(int2)), &recv, &recv_bytes, gather_ctx);
@@ -1042,6 +1134,29 @@ extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_a
         stats_out[3] = pairs_skipped;             // pairs known dissimilar from an earlier pass, not re-evaluated
     }
     return FC_OK;
+}
+
+extern "C" int fc_prune_sharded(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
+                                int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
+                                const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
+                                int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
+                                int64_t tie_cap, int64_t* n_ties_out, int32_t rank, int32_t world,
+                                fc_allgather_fn gather, void* gather_ctx) {
+    return prune_impl(structures, n, n_atoms, mode, sel, n_sel, masses, max_rmsd, max_dev, moi_dev, energies, max_dE,
+                      keep_first, snapshot, min_per_chunk, mask_out, stats_out, ties_out, tie_cap, n_ties_out, rank, world,
+                      gather, nullptr, gather_ctx);
+}
+
+extern "C" int fc_prune_sharded_dev(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
+                                    int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
+                                    const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
+                                    int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
+                                    int64_t tie_cap, int64_t* n_ties_out, int32_t rank, int32_t world,
+                                    fc_allgather_dev_fn gather_dev, void* gather_ctx) {
+    FC_REQUIRE(world == 1 || gather_dev, "fc_prune_sharded_dev: a multi-rank call needs the device all-gather callback");
+    return prune_impl(structures, n, n_atoms, mode, sel, n_sel, masses, max_rmsd, max_dev, moi_dev, energies, max_dE,
+                      keep_first, snapshot, min_per_chunk, mask_out, stats_out, ties_out, tie_cap, n_ties_out, rank, world,
+                      nullptr, gather_dev, gather_ctx);
 }
 
 extern "C" int fc_prune(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,

@@ -216,6 +216,42 @@ def cyclical_embed_sharded(embedder, group=None, screen=None, max_norm_delta=5.0
     return poses
 
 
+class _RawDeviceBytes:
+    """A device address range as an object torch.as_tensor can wrap without copying."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def device_all_gather(group=None):
+    """The fc_allgather_dev_fn of the C-ABI on top of torch.distributed: gather(send_ptr, recv_ptr, nbytes, stream_ptr)
+    leaves the rank-order concatenation of every rank's ``nbytes`` device bytes at ``recv_ptr``, ordered on the
+    library's CUDA stream.  NCCL moves the bytes GPU to GPU (NVLink / NVSwitch on the box); with a gloo group (CPU
+    tests, several ranks sharing one GPU) the pieces are staged through the host."""
+    import torch
+
+    dist = _dist()
+    backend = dist.get_backend(group)
+    world = dist.get_world_size(group)
+
+    def gather(send_ptr, recv_ptr, nbytes, stream_ptr):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        send = torch.as_tensor(_RawDeviceBytes(send_ptr, nbytes), device=dev)
+        recv = torch.as_tensor(_RawDeviceBytes(recv_ptr, nbytes * world), device=dev)
+        ext = torch.cuda.ExternalStream(stream_ptr, device=dev)
+        with torch.cuda.stream(ext):
+            if backend == "nccl":
+                dist.all_gather_into_tensor(recv, send, group=group)
+            else:
+                ext.synchronize()
+                out = torch.empty(world * nbytes, dtype=torch.uint8)
+                dist.all_gather_into_tensor(out, send.cpu(), group=group)
+                recv.copy_(out)
+                ext.synchronize()
+
+    return gather
+
+
 # Below this many pairs a pruning call is cheaper replicated on every rank than sharded: with the tensor-core
 # screen the GPU part of BASELINE config C4 (2e10 pairs, 5e9 evaluated) is 35 ms of an 85 ms call, the rest is
 # host work every rank repeats anyway, and each pass of the sharded driver adds two collectives
@@ -223,7 +259,7 @@ def cyclical_embed_sharded(embedder, group=None, screen=None, max_norm_delta=5.0
 PRUNE_SHARD_MIN_PAIRS = 1e11
 
 
-def prune_sharded(structures, atoms, kind="rmsd", group=None, force_shard=False, **kw):
+def prune_sharded(structures, atoms, kind="rmsd", group=None, force_shard=False, host_staged=False, **kw):
     """prune_by_rmsd / prune_by_moment_of_inertia over all ranks of ``group``: work items of every pass
     are dealt round-robin to the ranks (structures replicated), the similar pairs each rank finds are
     all-gathered (8 bytes per pair) and every rank resolves the pass on the union -- the deterministic
@@ -237,7 +273,9 @@ def prune_sharded(structures, atoms, kind="rmsd", group=None, force_shard=False,
     n = len(structures)
     if world == 1 or (not force_shard and 0.5 * n * (n - 1) < PRUNE_SHARD_MIN_PAIRS):
         return fn(structures, atoms, **kw)
-    return fn(structures, atoms, shard=(rank, world, lambda buf: all_gather_varlen(buf, group)), **kw)
+    if host_staged:
+        return fn(structures, atoms, shard=(rank, world, lambda buf: all_gather_varlen(buf, group)), **kw)
+    return fn(structures, atoms, shard=(rank, world, None, device_all_gather(group)), **kw)
 
 
 def torsion_scan_sharded(coords, torsions, masks, angles, group=None, scan=None, **kw):

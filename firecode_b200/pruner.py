@@ -55,8 +55,9 @@ def _chunk_bounds(mask, k, chunk_over):
 
 def _run(structures, mode, sel, masses, max_rmsd, max_dev, moi_dev, energies, max_dE, keep, pass_mode,
          tie_cap=1 << 16, shard=None, chunk_over=None):
-    """``shard`` = (rank, world, allgather) runs the multi-GPU form: allgather(bytes ndarray) must
-    return the rank-order concatenation of every rank's buffer (firecode_b200.dist supplies it)."""
+    """``shard`` = (rank, world, allgather) runs the multi-GPU form with host-staged lists: allgather(bytes ndarray)
+    must return the rank-order concatenation of every rank's buffer; ``shard`` = (rank, world, None, allgather_dev) the
+    device-resident form (C-ABI fc_prune_sharded_dev).  firecode_b200.dist supplies both."""
     global last_report
     lib = _lib.load(require_device=True)
     keep = conventions.PRUNE_KEEP if keep is None else keep
@@ -82,8 +83,25 @@ def _run(structures, mode, sel, masses, max_rmsd, max_dev, moi_dev, energies, ma
             int(conventions.PRUNE_MIN_PER_CHUNK), _ptr(mask), _ptr(stats), _ptr(ties), tie_cap, C.byref(n_ties))
     if shard is None:
         rc = lib.fc_prune(*args)
+    elif len(shard) == 4 and shard[3] is not None:
+        # device all-gather: shard[3](send_ptr, recv_ptr, nbytes, stream_ptr) exchanges device buffers (NCCL); every rank
+        # uploads 1 / world of the structures, the lists never leave the GPUs until the union is sorted
+        rank, world, _, allgather_dev = shard
+
+        def _gather_dev(send, recv, nbytes, stream, ctx):
+            try:
+                allgather_dev(int(send or 0), int(recv or 0), int(nbytes), int(stream or 0))
+                return 0
+            except Exception:  # pragma: no cover - reported through the C-ABI error path
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        cb = _lib.ALLGATHER_DEV_FN(_gather_dev)
+        rc = lib.fc_prune_sharded_dev(*args, int(rank), int(world), cb, None)
     else:
-        rank, world, allgather = shard
+        rank, world, allgather = shard[:3]
         hold = {}
 
         def _gather(send, send_bytes, recv, recv_bytes, ctx):

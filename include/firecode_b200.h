@@ -317,6 +317,22 @@ int fc_prune_sharded(const double* structures, int64_t n, int32_t n_atoms, int32
                      int64_t tie_cap, int64_t* n_ties_out, int32_t rank, int32_t world,
                      fc_allgather_fn gather, void* gather_ctx);
 
+/* The same with the exchange steps on the GPUs (NCCL over NVLink behind the host language).  Every rank uploads only
+ * its 1 / world of the structures (rows [rank * ceil(n / world), ...)); the pieces, the per-pass counters and the
+ * similar-pair lists are exchanged device to device through
+ *   gather_dev(send, recv, bytes, stream, ctx): every rank contributes `bytes` bytes at the DEVICE address `send`;
+ *   on return the work is ordered on `stream` (a cudaStream_t) and leaves the rank-order concatenation (world * bytes)
+ *   at the DEVICE address `recv`.  Returns 0 on success.
+ * The union of a pass is sorted on the device and every rank resolves the same list: all ranks return the same mask,
+ * equal to the single-GPU one.  BASELINE config C4 "sharded over 8 GPUs". */
+typedef int (*fc_allgather_dev_fn)(const void* send_dev, void* recv_dev, int64_t bytes, void* stream, void* ctx);
+int fc_prune_sharded_dev(const double* structures, int64_t n, int32_t n_atoms, int32_t mode, const int32_t* sel,
+                         int32_t n_sel, const double* masses, double max_rmsd, double max_dev, double moi_dev,
+                         const double* energies, double max_dE, int32_t keep_first, int32_t snapshot,
+                         int32_t min_per_chunk, uint8_t* mask_out, int64_t* stats_out, fc_tie* ties_out,
+                         int64_t tie_cap, int64_t* n_ties_out, int32_t rank, int32_t world,
+                         fc_allgather_dev_fn gather_dev, void* gather_ctx);
+
 /* Torsion-fingerprint (TFD) ensemble pruning, the O(n^2) part of torsion_module.py:957-1043
  * `prune_conformers_tfd` (embedder.py:1430-1437, torsion_module.py:875).
  *  fc_tfd_fingerprints: `_get_tf_mat` (torsion_module.py:1046-1053): tf_out (n, n_quads) degrees.

@@ -116,11 +116,15 @@ def _shard_worker(rank, world, port, q):
         rng = np.random.default_rng(77)
         atoms, structures, _ = syn.pruning_ensemble(rng, 3000, 20, 200, jitter=(0.02, 0.4))
         out = {}
-        for keep, mode in (("first", "greedy"), ("last", "snapshot")):
-            _, mask = fdist.prune_sharded(structures, atoms, "rmsd", force_shard=True, max_rmsd=0.4, keep=keep, pass_mode=mode)
-            out[(keep, mode)] = (mask, pr.last_report.pairs_tiled)
-        _, mmask = fdist.prune_sharded(structures, atoms, "moi", force_shard=True)
-        out["moi"] = (mmask, pr.last_report.pairs_tiled)
+        # device-resident exchange (fc_prune_sharded_dev: 1 / world of the structures uploaded per rank, lists gathered and
+        # sorted on the GPU; gloo stages the device buffers through the host here) and the host-staged form
+        for staged in (False, True):
+            for keep, mode in (("first", "greedy"), ("last", "snapshot"), ("last", "greedy")):
+                _, mask = fdist.prune_sharded(structures, atoms, "rmsd", force_shard=True, host_staged=staged, max_rmsd=0.4,
+                                              keep=keep, pass_mode=mode)
+                out[(keep, mode, staged)] = (mask, pr.last_report.pairs_tiled)
+            _, mmask = fdist.prune_sharded(structures, atoms, "moi", force_shard=True, host_staged=staged)
+            out[("moi", staged)] = (mmask, pr.last_report.pairs_tiled)
         q.put((rank, out))
     except Exception:  # pragma: no cover
         import traceback
@@ -151,15 +155,17 @@ def test_prune_sharded_two_ranks_equals_single(gpu):
     assert all(not isinstance(v, str) for v in results.values()), results
     rng = np.random.default_rng(77)
     atoms, structures, _ = synthetic.pruning_ensemble(rng, 3000, 20, 200, jitter=(0.02, 0.4))
-    for keep, mode in (("first", "greedy"), ("last", "snapshot")):
+    for keep, mode in (("first", "greedy"), ("last", "snapshot"), ("last", "greedy")):
         _, single = pruner.prune_by_rmsd(structures, atoms, 0.4, keep=keep, pass_mode=mode)
         total = pruner.last_report.pairs_tiled
-        for r in (0, 1):
-            assert np.array_equal(results[r][(keep, mode)][0], single)
-        assert results[0][(keep, mode)][1] + results[1][(keep, mode)][1] == total
-        assert abs(results[0][(keep, mode)][1] - total / 2) < 0.2 * total
+        for staged in (False, True):
+            for r in (0, 1):
+                assert np.array_equal(results[r][(keep, mode, staged)][0], single), (keep, mode, staged, r)
+            assert results[0][(keep, mode, staged)][1] + results[1][(keep, mode, staged)][1] == total
+            assert abs(results[0][(keep, mode, staged)][1] - total / 2) < 0.2 * total
     _, single = pruner.prune_by_moment_of_inertia(structures, atoms)
-    assert np.array_equal(results[0]["moi"][0], single) and np.array_equal(results[1]["moi"][0], single)
+    for staged in (False, True):
+        assert np.array_equal(results[0][("moi", staged)][0], single) and np.array_equal(results[1][("moi", staged)][0], single)
 
 
 def test_prune_skips_pairs_known_from_earlier_passes(gpu):
