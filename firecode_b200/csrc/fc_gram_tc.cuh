@@ -24,6 +24,7 @@
 // a Newton iteration on the QCP quartic, 32 at a time).
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -44,7 +45,9 @@ struct GramArgs {
     double max_dE;
     const GramWork* work;
     int n_work;
-    int kc;                   // 16-byte k-cores per row (even, <= kGramMaxKc): atoms padded to 4 * kc
+    int kc;                   // 16-byte k-cores per row (even, <= kGramMaxKc): atoms padded to 8 * kc (FP16) / 4 * kc (TF32)
+    int tf32;                 // 0: operands are FP16 (default: same 11-bit significand as TF32, K = 16 per instruction,
+                              // half the operand bytes and half the tcgen05.mma count), 1: TF32 (FC_PRUNE_TF32=1)
     float thr_e;              // (max_rmsd + band)^2 * nh
     float e0_scale;           // 1 - sqrt(3) * (bound on the relative TF32 product error)
     int2* cand;               // pairs the screen could not rule out (structure indices, x < y)
@@ -62,7 +65,8 @@ constexpr int kGramEpiWarps = 16;
 constexpr int kGramIssuers = 6;     // MMA-issuing warps: (accumulator stage, component)
 constexpr int kGramThreads = 32 * (1 + kGramIssuers + kGramEpiWarps);  // producer, MMA issuers, epilogue warps
 constexpr int kGramBStages = 4;
-constexpr int kGramMaxKc = 22;   // <= 88 selected atoms: operands + pair queues must fit the 227 KB of shared memory
+constexpr int kGramMaxKc = 22;   // <= 176 selected atoms as FP16 (88 as TF32): operands + pair queues must fit the 227 KB of shared memory
+constexpr unsigned kGramWaitHintNs = 20000;  // suspend-time hint of the mbarrier waits (the phase completing ends the sleep)
 constexpr int kGramQueue = 32;   // entries of an epilogue warp's queue of pairs that need the Newton iteration
 // Relative bound on |H_tf32 - H|_F / (|p| |q|): operands are rounded to nearest TF32 (2^-11 each, so 2^-10 on a
 // product, Cauchy-Schwarz over the atoms); doubled to cover the accumulation inside the tensor core.  Measured on
@@ -96,17 +100,21 @@ __device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigne
 // expire it spuriously) and at the abort flag; on expiry it records `code` in *error and gives up.  Every other wait of
 // the kernel then falls through as soon as it sees the flag, the kernel runs to its end with garbage that nobody reads,
 // and the host turns the flag into an error code (fc_prune: "gram_tc_kernel: mbarrier wait N timed out").
+// The wait itself is mbarrier.try_wait WITH a suspend-time hint: the thread sleeps in hardware until the phase completes
+// (or the hint expires) instead of re-issuing polls.  ncu of the poll-loop version showed the seven single-thread
+// producer / issuer warps executing a third of all warp instructions of the kernel in their wait loops, competing with
+// the sixteen epilogue warps for issue slots ("not selected" was the top stall of the epilogue).
 __device__ __forceinline__ void bar_wait(unsigned bar, unsigned parity, int* error, int code) {
     unsigned long long t0 = 0;
     for (unsigned spin = 0;; ++spin) {
         unsigned ok;
         asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(kGramWaitHintNs)
             : "memory");
         if (ok) return;
-        if ((spin & 0x3FFFu) == 0x3FFFu) {
+        if ((spin & 0x3Fu) == 0x3Fu) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
@@ -137,6 +145,14 @@ __device__ __forceinline__ void mma_tf32(unsigned d_tmem, uint64_t a_desc, uint6
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with FP16 inputs (K = 16 per instruction)
+__device__ __forceinline__ void mma_f16(unsigned d_tmem, uint64_t a_desc, uint64_t b_desc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(unsigned taddr, float* v) {
     unsigned r0, r1, r2, r3, r4, r5, r6, r7;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -159,7 +175,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- operand image --------------------------------------------------------------------------------
 // one block per group of 8 positions; xcf = centred heavy-atom coordinates (n, nh) as float4
 __global__ void __launch_bounds__(256) gram_pack_kernel(const float4* __restrict__ xcf, const double* __restrict__ g,
-                                                        const int* __restrict__ spos, int nh, int kc, int n_groups,
+                                                        const int* __restrict__ spos, int nh, int kc, int n_groups, int tf32,
                                                         float* __restrict__ img, float* __restrict__ gp) {
     const int grp = blockIdx.x;
     if (grp >= n_groups) return;
@@ -170,19 +186,35 @@ __global__ void __launch_bounds__(256) gram_pack_kernel(const float4* __restrict
         gp[grp * 8 + threadIdx.x] = s >= 0 ? (float)g[s] : 0.f;
     }
     __syncthreads();
-    const int per_group = 3 * kc * 32;
+    const int per_group = 3 * kc * 32;  // 32-bit slots: one TF32 value or two FP16 values each
     float* dst = img + (size_t)grp * per_group;
     for (int e = threadIdx.x; e < per_group; e += blockDim.x) {
         const int t = e & 3, r = (e >> 2) & 7, c = (e >> 5) % kc, comp = (e >> 5) / kc;
-        const int k = 4 * c + t, s = s_idx[r];
-        float v = 0.f;
-        if (s >= 0 && k < nh) {
-            const float4 x = xcf[(size_t)s * nh + k];
-            v = comp == 0 ? x.x : (comp == 1 ? x.y : x.z);
+        const int s = s_idx[r];
+        if (tf32) {
+            const int k = 4 * c + t;
+            float v = 0.f;
+            if (s >= 0 && k < nh) {
+                const float4 x = xcf[(size_t)s * nh + k];
+                v = comp == 0 ? x.x : (comp == 1 ? x.y : x.z);
+            }
+            unsigned bits;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"(v));
+            dst[e] = __uint_as_float(bits);
+        } else {
+            const int k = 8 * c + 2 * t;  // atoms k, k + 1 of the 8 this k-core row holds
+            float v0 = 0.f, v1 = 0.f;
+            if (s >= 0 && k < nh) {
+                const float4 x = xcf[(size_t)s * nh + k];
+                v0 = comp == 0 ? x.x : (comp == 1 ? x.y : x.z);
+            }
+            if (s >= 0 && k + 1 < nh) {
+                const float4 x = xcf[(size_t)s * nh + k + 1];
+                v1 = comp == 0 ? x.x : (comp == 1 ? x.y : x.z);
+            }
+            const __half2 h = __floats2half2_rn(v0, v1);  // low half = atom k (lower address)
+            dst[e] = __uint_as_float(*reinterpret_cast<const unsigned*>(&h));
         }
-        unsigned bits;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(bits) : "f"(v));
-        dst[e] = __uint_as_float(bits);
     }
 }
 
@@ -286,7 +318,9 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
             // instruction descriptor: D = F32 (bit 4), A = B = TF32 (bits 7, 10), both K-major, N = 48 (>> 3 at bit 17),
             // M = 128 (>> 4 at bit 24)
             const unsigned stage = (unsigned)(warp - 1) / 3u, comp = (unsigned)(warp - 1) % 3u;
-            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (6u << 17) | (8u << 24);
+            // (FP16 operands: format code 0 in both fields, K = 16 per instruction -- the same 256 bytes per k-step)
+            const unsigned fmt = a.tf32 ? 2u : 0u;
+            const unsigned idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (6u << 17) | (8u << 24);
             unsigned g = 0, bphases = 0, aphase = 0, dphase = 0;  // one phase bit per operand slot
             const unsigned sA_addr = smem_addr(sA) + comp * kc * 128, sB_addr = smem_addr(sB);
             const unsigned d_tmem = tmem_base + stage * 256 + comp * 64;
@@ -306,7 +340,8 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                     const int ksteps = (a.no_math & 2) ? 1 : kc / 2;
                     uint64_t da = smem_desc(sA_addr, 128, 3 * kc * 128), db = smem_desc(sB_addr + bs * b_bytes, 128, kc * 128);
                     for (int k = 0; k < ksteps; ++k) {
-                        mma_tf32(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
+                        if (a.tf32) mma_tf32(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
+                        else mma_f16(d_tmem, da, db, idesc, k > 0 ? 1u : 0u);
                         da += 16;  // next k-step: 256 bytes further, in the 16-byte units of the start-address field
                         db += 16;
                     }

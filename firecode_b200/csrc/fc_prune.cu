@@ -811,11 +811,14 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
             if (e != cudaSuccess) rc = cuda_fail(e, "fc_prune setup", __FILE__, __LINE__);
         }
         // screen flavour: FC_PRUNE_FP64=1 -> FP64 pair kernel only; otherwise FP32 screen + FP64 exact stage, the screen
-        // on the tensor cores (gram_tc_kernel) unless FC_PRUNE_TC=0 or the molecule has more than 88 selected atoms (kGramMaxKc)
+        // on the tensor cores (gram_tc_kernel) unless FC_PRUNE_TC=0 or the molecule has more than 176 selected atoms (kGramMaxKc k-cores of 8 FP16 values)
         const char* env64 = getenv("FC_PRUNE_FP64");
         const char* envtc = getenv("FC_PRUNE_TC");
         const bool two_stage = mode == 0 && !(env64 && atoi(env64));
-        int kc = (n_sel + 3) / 4;
+        // operands of the tensor-core screen: FP16 (8 atoms per 16-byte k-core) unless FC_PRUNE_TF32=1 (4 atoms)
+        const char* envtf = getenv("FC_PRUNE_TF32");
+        const int gram_tf32 = envtf && atoi(envtf) ? 1 : 0;
+        int kc = gram_tf32 ? (n_sel + 3) / 4 : (n_sel + 7) / 8;
         kc += kc & 1;
         const bool use_tc = two_stage && kc <= kGramMaxKc && !(envtc && !atoi(envtc));
         std::vector<int> spos;
@@ -878,7 +881,7 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
                     PR(cudaMemcpyAsync(d_work.p, work.data(), work.size() * sizeof(GramWork), cudaMemcpyHostToDevice, s));
                     if (e == cudaSuccess) {
                         gram_pack_kernel<<<(unsigned)(n_pos / 8), 256, 0, s>>>(d_xcf.p, d_g.p, d_spos.p, n_sel, kc, (int)(n_pos / 8),
-                                                                              d_img.p, d_gp.p);
+                                                                              gram_tf32, d_img.p, d_gp.p);
                         e = cudaGetLastError();
                     }
                 } else {
@@ -911,7 +914,7 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
                             GramArgs ga{};
                             ga.img = d_img.p; ga.gp = d_gp.p; ga.spos = d_spos.p;
                             ga.energies = energies ? d_energy.p : nullptr; ga.max_dE = max_dE;
-                            ga.work = d_work.p; ga.n_work = (int)work.size(); ga.kc = kc;
+                            ga.work = d_work.p; ga.n_work = (int)work.size(); ga.kc = kc; ga.tf32 = gram_tf32;
                             const float lim = (float)max_rmsd + kScreenBand;
                             ga.thr_e = lim * lim * (float)n_sel;
                             ga.e0_scale = 1.0f - 1.7320508f * kGramTf32Eps;

@@ -178,15 +178,17 @@ def test_prune_skips_pairs_known_from_earlier_passes(gpu):
     assert np.array_equal(mask, ref_mask)
 
 
-@pytest.mark.parametrize("n_atoms,expect_tc", [(120, True), (36, True), (170, False)])
+@pytest.mark.parametrize("n_atoms,expect_tc", [(120, True), (36, True), (170, True), (300, False)])
 def test_prune_screen_flavours_agree(gpu, monkeypatch, n_atoms, expect_tc):
-    """The tensor-core (TF32) screen, the FP32 screen and the FP64-only pair kernel must give the same mask: the
-    screens only decide which pairs reach the FP64 evaluation.  More than 88 selected atoms -> FP32 screen."""
+    """The tensor-core screen (FP16 operands by default, TF32 with FC_PRUNE_TF32=1), the FP32 screen and the FP64-only pair
+    kernel must give the same mask: the screens only decide which pairs reach the FP64 evaluation.  More than 176 selected
+    atoms (88 as TF32) -> FP32 screen."""
     rng = np.random.default_rng(synthetic.SEED + n_atoms)
     atoms, structures, _ = synthetic.pruning_ensemble(rng, 3000, n_atoms, 60, jitter=(0.02, 0.45))
     masks = {}
-    for name, env in (("tc", {}), ("fp32", {"FC_PRUNE_TC": "0"}), ("fp64", {"FC_PRUNE_FP64": "1"})):
-        for k in ("FC_PRUNE_TC", "FC_PRUNE_FP64"):
+    n_sel = int(np.sum(np.asarray(atoms) != "H"))
+    for name, env in (("tc", {}), ("tf32", {"FC_PRUNE_TF32": "1"}), ("fp32", {"FC_PRUNE_TC": "0"}), ("fp64", {"FC_PRUNE_FP64": "1"})):
+        for k in ("FC_PRUNE_TC", "FC_PRUNE_FP64", "FC_PRUNE_TF32"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -194,10 +196,13 @@ def test_prune_screen_flavours_agree(gpu, monkeypatch, n_atoms, expect_tc):
         rep = pruner.last_report
         if name == "tc":
             assert (rep.screen_launches > 0) == expect_tc
-            assert rep.n_sel == int(np.sum(np.asarray(atoms) != "H"))
+            assert rep.n_sel == n_sel
             forced = _forced(rep)
+        elif name == "tf32":
+            assert (rep.screen_launches > 0) == (n_sel <= 88)
         else:
             assert rep.screen_launches == 0
+    assert np.array_equal(masks["tc"], masks["tf32"])
     assert np.array_equal(masks["tc"], masks["fp32"])
     assert np.array_equal(masks["tc"], masks["fp64"])
     assert 1 < masks["tc"].sum() < len(structures)

@@ -82,11 +82,11 @@ int main(int argc, char** argv) {
     CK(cudaMemset(d_nc, 0, 8)); CK(cudaMemset(d_err, 0, 4));
     const int dump_ld = n_pos;
     if (check) { CK(cudaMalloc(&d_dump, (size_t)n_pos * dump_ld * 9 * 4)); CK(cudaMemset(d_dump, 0, (size_t)n_pos * dump_ld * 9 * 4)); }
-    fc::gram_pack_kernel<<<n_pos / 8, 256>>>(d_xf, d_g, d_spos, nh, kc, n_pos / 8, d_img, d_gp);
+    fc::gram_pack_kernel<<<n_pos / 8, 256>>>(d_xf, d_g, d_spos, nh, kc, n_pos / 8, 1, d_img, d_gp);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     fc::GramArgs a{};
-    a.img = d_img; a.gp = d_gp; a.spos = d_spos; a.energies = nullptr; a.max_dE = 0; a.work = d_work; a.n_work = (int)work.size(); a.kc = kc;
+    a.img = d_img; a.gp = d_gp; a.spos = d_spos; a.energies = nullptr; a.max_dE = 0; a.work = d_work; a.n_work = (int)work.size(); a.kc = kc; a.tf32 = 1;
     const float lim = (float)(max_rmsd + band);
     a.thr_e = lim * lim * nh; a.e0_scale = 1.0f - 1.7320508f * (1.0f / 512.0f);
     a.cand = d_cand; a.n_cand = d_nc; a.cand_cap = cand_cap; a.dump = d_dump; a.dump_ld = dump_ld; a.error = d_err; a.no_math = no_math;
