@@ -467,6 +467,38 @@ def run_cuda(args):
                        "api": "firecode_b200.clash.compenetration_check_batch -> fc_clash_batch (f64 R|t, as round 1)"}
     del xf_host, p7_host
 
+    # second half of the metric on several GPUs: C4 (configs[3], "... sharded over 8 GPUs"): every rank uploads 1 / world of
+    # the structures, pair tiles dealt to the ranks, exchange steps on the devices over NCCL (fc_prune_sharded_dev)
+    c4_sharded = None
+    if world > 1 and not args.no_extras:
+        from firecode_b200 import dist as fdist
+        from firecode_b200 import pruner
+
+        rng4 = np.random.default_rng(synthetic.SEED + 4)
+        atoms4, structures4, _ = synthetic.pruning_ensemble(rng4, 200000, 120, 2000)
+        times = []
+        for rep_i in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            _, mask4 = fdist.prune_sharded(structures4, atoms4, "rmsd", force_shard=True, max_rmsd=0.5)
+            t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+        pairs = torch.tensor([float(pruner.last_report.pairs_tiled)], device=dev, dtype=torch.float64)
+        dist.all_reduce(pairs, op=dist.ReduceOp.SUM)
+        chk = torch.tensor([float(np.flatnonzero(mask4).sum())], device=dev, dtype=torch.float64)
+        chk_lo, chk_hi = chk.clone(), chk.clone()
+        dist.all_reduce(chk_lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(chk_hi, op=dist.ReduceOp.MAX)
+        sec = min(times[1:])
+        c4_sharded = {"metric": "RMSD pairs/s", "value": float(pairs.item()) / sec, "unit": "pairs/s", "seconds": sec,
+                      "seconds_each": [round(x, 4) for x in times], "n_gpus": world, "scaling": "strong",
+                      "workload": "C4: prune_by_rmsd of 200 k conformers x 120 atoms through dist.prune_sharded (device all-gather)",
+                      "pairs": int(pairs.item()), "kept": int(mask4.sum()), "mask_checksum": int(chk.item()),
+                      "all_ranks_same_mask": bool(chk_lo.item() == chk_hi.item()),
+                      "single_gpu_reference": "kept 80688, mask checksum in the N = 1 line (other_workloads.C4_rmsd_pruning_200k)"}
+        del structures4, mask4
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -577,6 +609,8 @@ def run_cuda(args):
     }
     # second half of BASELINE.json's metric ("... + RMSD pairs/s"): the C4 pruning run, surfaced at the top level
     c4 = (extras or {}).get("C4_rmsd_pruning_200k")
+    if c4_sharded:
+        line["rmsd_pairs"] = c4_sharded
     if c4:
         line["rmsd_pairs"] = {"metric": "RMSD pairs/s", "value": c4["rmsd_pairs_per_s"], "unit": "pairs/s",
                               "workload": "C4: prune_by_rmsd of 200 k conformers x 120 atoms through the host API",
@@ -584,37 +618,6 @@ def run_cuda(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def _tf32_probe():
-    """Measured dense TF32 throughput of this GPU (cuBLAS through torch.matmul, 8192^3, best of 10), the denominator of
-    the tensor-core pruning screen's roofline.  Returns (TFLOP/s, description) or (None, None)."""
-    try:
-        import torch
-
-        if not torch.cuda.is_available():
-            return None, None
-        old = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-        n = 8192
-        a = torch.randn(n, n, device="cuda", dtype=torch.float32)
-        b = torch.randn(n, n, device="cuda", dtype=torch.float32)
-        for _ in range(3):
-            torch.matmul(a, b)
-        best = 1e9
-        for _ in range(10):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            torch.matmul(a, b)
-            e1.record()
-            torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        torch.backends.cuda.matmul.allow_tf32 = old
-        del a, b
-        tf = 2.0 * n ** 3 / (best * 1e-3) / 1e12
-        return tf, f"measured in this run: torch.matmul fp32 with allow_tf32 (cuBLAS TF32), {n}^3, best of 10 = {tf:.0f} TFLOP/s"
-    except Exception:
-        return None, None
 
 
 def run_extras():
@@ -689,6 +692,7 @@ def run_extras():
                                    "pairs_skipped_known_dissimilar": rep.pairs_skipped,
                                    "pairs_eigen_solved": rep.pairs_solved, "passes": rep.passes,
                                    "kept": int(mask.sum()), "n": len(mask), "seconds": dt,
+                                   "mask_checksum": int(np.flatnonzero(mask).sum()),
                                    "h2d_bytes": int(structures.nbytes),
                                    "library_ms": rep.wall_ms,
                                    "conventions": {"keep": rep.keep, "pass_mode": rep.pass_mode}}
@@ -697,12 +701,11 @@ def run_extras():
         # pair = 51 N_h FLOP (covariance + norms + rotate-and-deviate); the tensor cores execute the covariance
         # only, 18 FLOP per atom slot (K padded to a multiple of 8) per pair slot of every 128 x 16 tile
         peaks, peak_kind = _peaks()
-        tf32_peak, tf32_src = _tf32_probe()
-        if tf32_peak is None:
-            tf32_peak = 0.5 * float(peaks["bf16_tflops"])
-            tf32_src = f"TF32 dense assumed = half the {peak_kind} bf16 figure of MEASURED_PEAKS.json (probe unavailable)"
+        # operands are FP16 (same tensor-core rate as bf16): the denominator is the MEASURED dense bf16 figure
+        tf32_peak = float(peaks["bf16_tflops"])
+        tf32_src = f"{peak_kind} MEASURED_PEAKS.json bf16_tflops (burst; FP16 operands run at the bf16 rate)"
         sec = rep.screen_ms * 1e-3
-        kpad = 8 * ((rep.n_sel + 7) // 8)
+        kpad = 16 * ((rep.n_sel + 15) // 16)
         alg_tf = 51.0 * rep.n_sel * rep.pairs_tiled / sec / 1e12
         exe_tf = 18.0 * kpad * rep.screen_pair_slots / sec / 1e12
         out["C4_rmsd_pruning_200k"]["roofline"] = {
@@ -710,12 +713,13 @@ def run_extras():
             "frac": exe_tf / tf32_peak, "traffic": None, "algorithmic_tflops": alg_tf,
             "kernel_ms_total": rep.screen_ms, "launches": rep.screen_launches, "pairs": rep.pairs_tiled,
             "pair_slots": rep.screen_pair_slots, "candidates_to_fp64": rep.screen_candidates, "atoms_in_rmsd": rep.n_sel,
-            "frac_note": "frac = EXECUTED tensor FLOP / measured TF32 peak (what the tensor pipe did); the algorithmic figure of "
+            "frac_note": "frac = EXECUTED tensor FLOP / measured dense 16-bit peak (what the tensor pipe did); the algorithmic figure of "
                          "SURVEY.md 8d (51 N_h FLOP per pair, never executed as such) is kept as algorithmic_tflops",
             "peak_source": tf32_src,
-            "note": "TF32 Gram matrix of the centred heavy-atom coordinates (tcgen05.mma M128 N48 K8, FP32 accumulators in TMEM); "
-                    "the kernel is bound by MMA issue (about 65 cycles per instruction whatever N is) and by its FP32 epilogue, "
-                    "not by tensor throughput; pairs the screen cannot rule out are re-evaluated in FP64",
+            "note": "FP16 Gram matrix of the centred heavy-atom coordinates (tcgen05.mma kind::f16 M128 N48 K16, FP32 accumulators in "
+                    "TMEM); the kernel is bound by its FP32 epilogue (3x3 singular-value bounds of 2048 pairs per tile: 410 "
+                    "warp instructions per epilogue warp and tile, profiles/r02_gram_tc_ncu_summary.md), not by tensor "
+                    "throughput; pairs the screen cannot rule out are re-evaluated in FP64",
             "screen_pairs_per_s": rep.pairs_tiled / sec}
     del structures, kept, mask
     # TFD ensemble pruning (torsion_module.py:957-1043): 20 000 conformers of a 40-atom molecule, 12 quadruplets

@@ -109,6 +109,8 @@ SIGNATURES = {
     "fc_prune_sharded_dev": (C.c_int, [VP, C.c_int64, C.c_int32, C.c_int32, VP, C.c_int32, VP, C.c_double, C.c_double,
                                        C.c_double, VP, C.c_double, C.c_int32, C.c_int32, C.c_int32, VP, VP, VP,
                                        C.c_int64, c_i64p, C.c_int32, C.c_int32, ALLGATHER_DEV_FN, VP]),
+    "fc_bond_graph_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_double, VP, VP]),
+    "fc_bond_delta_batch": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_double, VP, C.c_int32, VP, VP, VP]),
     "fc_tfd_fingerprints": (C.c_int, [VP, C.c_int64, C.c_int32, VP, C.c_int32, VP]),
     "fc_tfd_first_match": (C.c_int, [VP, C.c_int64, C.c_int32, VP, VP, C.c_int64, C.c_double, VP, VP, C.c_int64, c_i64p]),
     "fc_csearch_apply": (C.c_int, [VP, C.c_int32, C.c_int32, VP, C.c_int32, VP, VP, C.c_int64, C.c_double, C.c_int32,

@@ -333,6 +333,23 @@ int fc_prune_sharded_dev(const double* structures, int64_t n, int32_t n_atoms, i
                          int64_t tie_cap, int64_t* n_ties_out, int32_t rank, int32_t world,
                          fc_allgather_dev_fn gather_dev, void* gather_ctx);
 
+/* Batched bond-graph checks: the post-filters `scramble_check` and `molecule_check` (utils.py:341-400; callers
+ * embedder.py:2181-2195, 2430-2444, optimization_methods.py:139-147, operators.py:502, interfaces/goat.py:309).
+ * Atoms i != j of a structure are bonded iff |x_i - x_j| < factor * (radii[i] + radii[j]) -- prism_pruner's
+ * graphize / d_min_bond criterion (factor 1.2, covalent radii), FP64, strict <.
+ *  fc_bond_graph_batch: adj_out (n_struct, n_atoms, W = ceil(n_atoms / 32)) words, bit (j & 31) of word j >> 5 of row i
+ *    set iff i - j bonded (symmetric, no self loops).
+ *  fc_bond_delta_batch: delta_out[s] = number of bonds present in exactly one of {structure s, expected}, not counting
+ *    bonds that touch an atom with excluded[i] != 0 (excluded may be null).  `expected` has the layout of adj_out for
+ *    ONE structure (expected_per_structure = 0: scramble_check's union of the fragment graphs) or for every structure
+ *    (1: molecule_check against each structure's own un-optimised graph).
+ *  near_out[s] (may be null) = pairs of structure s whose distance lies within 1e-6 of their limit. */
+int fc_bond_graph_batch(const double* coords, int64_t n_struct, int32_t n_atoms, const double* radii, double factor,
+                        uint32_t* adj_out, int32_t* near_out);
+int fc_bond_delta_batch(const double* coords, int64_t n_struct, int32_t n_atoms, const double* radii, double factor,
+                        const uint32_t* expected, int32_t expected_per_structure, const uint8_t* excluded,
+                        int32_t* delta_out, int32_t* near_out);
+
 /* Torsion-fingerprint (TFD) ensemble pruning, the O(n^2) part of torsion_module.py:957-1043
  * `prune_conformers_tfd` (embedder.py:1430-1437, torsion_module.py:875).
  *  fc_tfd_fingerprints: `_get_tf_mat` (torsion_module.py:1046-1053): tf_out (n, n_quads) degrees.

@@ -358,12 +358,100 @@ def main_multiembed():
         RunEmbedding.generate_candidates = orig
 
 
+def make_scramble_case(seed, n_frag=2, n_struct=24):
+    """An assembly of n_frag small molecules (bond graphs from graphize of their rest geometry) and n_struct copies of
+    it: untouched, slightly jittered (no bond changes), with one atom pulled away (a bond breaks) and with two fragments
+    pushed together (bonds form); a few atoms are declared constrained (excluded)."""
+    from prism_pruner.graph_manipulations import graphize
+
+    from firecode_b200 import synthetic
+
+    rng = np.random.default_rng(seed)
+    frags, graphs, atoms = [], [], []
+    for f in range(n_frag):
+        sym, x, _, _ = synthetic.molecule_cloud(rng, int(rng.integers(7, 13)))
+        frags.append(x + np.array([7.0 * f, 0.0, 0.0]))
+        atoms += list(sym)
+        graphs.append(graphize(sym, x))
+    atoms = np.array(atoms)
+    base = np.concatenate(frags)
+    offs = np.concatenate([[0], np.cumsum([len(f) for f in frags])]).astype(int)
+    structures = np.repeat(base[None], n_struct, axis=0)
+    for s in range(n_struct):
+        kind = s % 4
+        if kind == 1:
+            structures[s] += rng.normal(size=base.shape) * 0.02
+        elif kind == 2:   # pull one atom of a random fragment away from the rest
+            f = int(rng.integers(n_frag))
+            a = int(rng.integers(offs[f], offs[f + 1]))
+            structures[s, a] += rng.normal(size=3) * rng.uniform(0.3, 1.5)
+        elif kind == 3:   # push fragment 1 towards fragment 0
+            structures[s, offs[1]:offs[2]] -= np.array([rng.uniform(2.0, 5.5), 0.0, 0.0])
+    excluded = sorted(int(v) for v in rng.choice(len(atoms), size=2, replace=False))
+    return atoms, structures, graphs, excluded
+
+
+def main_setup():
+    """Setup-side rows of the UNMODIFIED reference: the pivot tables Embedder._set_pivots builds on
+    the reference's own fixtures (embedder.py:902-987) and verdicts of utils.scramble_check / molecule_check
+    (utils.py:341-400) on seeded assemblies."""
+    loader.install()
+    from firecode.utils import molecule_check, scramble_check
+
+    out = {}
+    n_mol = 0
+    for name in ("embed_cyclical", "embed_chelotropic", "embed_trimolecular"):
+        with loader.embedder_from_dir(loader.fixture_dir(name), name + ".txt") as emb:
+            for m, mol in enumerate(emb.objects):
+                key = f"piv{n_mol}"
+                n_mol += 1
+                n_conf = len(mol.coords)
+                atoms_r = [list(mol.reactive_atoms_classes_dict[c].values()) for c in range(n_conf)]
+                for a in range(len(atoms_r[0])):
+                    out[f"{key}_centers{a}"] = np.array([np.asarray(atoms_r[c][a].center, dtype=float) for c in range(n_conf)])
+                out[f"{key}_n_ratoms"] = np.int64(len(atoms_r[0]))
+                out[f"{key}_suprafacial"] = np.bool_(bool(emb.options.suprafacial))
+                out[f"{key}_sigmastar"] = np.bool_(bool(mol.sp3_sigmastar))
+                out[f"{key}_name"] = np.array(f"{name}:{m}")
+                for c in range(n_conf):
+                    piv = mol.pivots[c]
+                    out[f"{key}_c{c}_start"] = np.array([p.start for p in piv]).reshape(-1, 3)
+                    out[f"{key}_c{c}_end"] = np.array([p.end for p in piv]).reshape(-1, 3)
+                    out[f"{key}_c{c}_pivot"] = np.array([p.pivot for p in piv]).reshape(-1, 3)
+                    out[f"{key}_c{c}_meanpoint"] = np.array([p.meanpoint for p in piv]).reshape(-1, 3)
+                    out[f"{key}_c{c}_index"] = np.array([p.index_ for p in piv], dtype=np.int64).reshape(-1, 2)
+                out[f"{key}_n_conf"] = np.int64(n_conf)
+    out["n_pivot_mols"] = np.int64(n_mol)
+    # scramble_check / molecule_check of the reference on seeded assemblies
+    n_cases = 3
+    for k in range(n_cases):
+        atoms, structures, graphs, excluded = make_scramble_case(100 + k, n_frag=2 + (k == 2))
+        out[f"scr{k}_atoms"] = np.array(atoms)
+        out[f"scr{k}_structures"] = structures
+        out[f"scr{k}_excluded"] = np.array(excluded, dtype=np.int64)
+        out[f"scr{k}_n_frag"] = np.int64(len(graphs))
+        for f, g in enumerate(graphs):
+            out[f"scr{k}_graph{f}_edges"] = np.array(sorted(tuple(sorted(e)) for e in g.edges), dtype=np.int64).reshape(-1, 2)
+            out[f"scr{k}_graph{f}_nodes"] = np.int64(len(g.nodes))
+        for mx in (0, 1, 3):
+            out[f"scr{k}_ok_max{mx}"] = np.array([scramble_check(atoms, s, excluded, graphs, max_newbonds=mx) for s in structures])
+            out[f"scr{k}_mol_ok_max{mx}"] = np.array([molecule_check(atoms, structures[0], s, max_newbonds=mx) for s in structures])
+    out["n_scramble_cases"] = np.int64(n_cases)
+    np.savez_compressed(os.path.join(GOLDEN, "setup_rows.npz"), conventions=np.array(_conventions()), **out)
+    print(f"setup_rows: {n_mol} pivot tables, {n_cases} scramble cases, verdicts "
+          f"{[int(out[f'scr{k}_ok_max0'].sum()) for k in range(n_cases)]} of {len(structures)} pass at max_newbonds = 0")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "multiembed":
         main_multiembed()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "setup":
+        main_setup()
         sys.exit(0)
     main()
     main_tfd()
     main_csearch()
     main_refining()
     main_multiembed()
+    main_setup()

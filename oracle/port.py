@@ -779,3 +779,60 @@ def csearch_apply(start, torsions, masks, angle_set, thresh=1.5):
         new_coords = temp
     return new_coords, rotated_bonds, closest
 
+
+
+# ------------------------------------------------------------------------------------------------
+# bond-graph post-filters (firecode/utils.py:341-400)
+# ------------------------------------------------------------------------------------------------
+def bond_set(atoms, coords):
+    """Sorted bonds of ``graphize(atoms, coords)`` (prism_pruner shim) without self loops."""
+    _shim()  # puts the prism_pruner shim on sys.path
+    from prism_pruner.graph_manipulations import graphize
+
+    return {tuple(sorted((int(a), int(b)))) for a, b in graphize(atoms, coords).edges if a != b}
+
+
+def assembly_bonds(mols_graphs):
+    """utils.py:371-377: the union of the fragments' bonds, shifted by the atoms before each fragment."""
+    bonds, pos = set(), 0
+    for graph in mols_graphs:
+        for a, b in graph.edges:
+            if a != b:
+                bonds.add(tuple(sorted((int(a) + pos, int(b) + pos))))
+        pos += len(graph.nodes)
+    return bonds
+
+
+def scramble_delta(atoms, structure, excluded_atoms, mols_graphs):
+    """The bonds scramble_check counts (utils.py:379-391): symmetric difference of expected and found bonds minus the
+    ones touching an excluded atom."""
+    bonds, new_bonds = assembly_bonds(mols_graphs), bond_set(atoms, structure)
+    delta = (bonds | new_bonds) - (bonds & new_bonds)
+    excluded = {int(a) for a in excluded_atoms}
+    return {b for b in delta if not (b[0] in excluded or b[1] in excluded)}
+
+
+def scramble_check(atoms, structure, excluded_atoms, mols_graphs, max_newbonds=0):
+    return len(scramble_delta(atoms, structure, excluded_atoms, mols_graphs)) <= max_newbonds
+
+
+def molecule_delta(atoms, old_coords, new_coords):
+    old_bonds, new_bonds = bond_set(atoms, old_coords), bond_set(atoms, new_coords)
+    return (old_bonds | new_bonds) - (old_bonds & new_bonds)
+
+
+def molecule_check(atoms, old_coords, new_coords, max_newbonds=0):
+    """utils.py:341-353."""
+    return len(molecule_delta(atoms, old_coords, new_coords)) <= max_newbonds
+
+
+def bond_near_threshold(atoms, coords, eps=1e-6):
+    """Number of atom pairs whose distance lies within eps of their bonding limit."""
+    _shim()
+    from prism_pruner.graph_manipulations import d_min_bond
+
+    atoms = np.asarray(atoms)
+    coords = np.asarray(coords, dtype=float)
+    d = np.sqrt(((coords[:, None] - coords[None]) ** 2).sum(-1))
+    n = len(atoms)
+    return sum(1 for i in range(n) for j in range(i + 1, n) if abs(d[i, j] - d_min_bond(atoms[i], atoms[j])) <= eps)
