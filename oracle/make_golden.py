@@ -442,7 +442,102 @@ def main_setup():
           f"{[int(out[f'scr{k}_ok_max0'].sum()) for k in range(n_cases)]} of {len(structures)} pass at max_newbonds = 0")
 
 
+class _DuckMol:
+    """What a reactive-atom class reads from a Hypermolecule (reactive_atoms_classes.py)."""
+
+    def __init__(self, atoms, edges, coords, reactive_indices, sp3_sigmastar, sigmatropic):
+        import networkx as nx
+
+        self.atoms = np.array(atoms)
+        self.graph = nx.Graph()
+        self.graph.add_nodes_from(range(len(atoms)))
+        self.graph.add_edges_from(edges)
+        self.coords = coords
+        self.reactive_indices = list(reactive_indices)
+        self.sp3_sigmastar = sp3_sigmastar
+        self.sigmatropic = list(sigmatropic)
+
+
+def orbital_cases():
+    """(name, class name, atoms, bonds, rest geometry, reactive atom, reactive indices, sp3_sigmastar, sigmatropic per
+    conformer) -- small molecules with idealised geometries; the conformers are jittered copies."""
+    t = 1.0 / np.sqrt(3.0)
+    methyl_x = [[0, 0, 0], [1.78, 0, 0], [-0.36, 1.03, 0], [-0.36, -0.51, 0.89], [-0.36, -0.51, -0.89]]
+    ethene = [[0, 0, 0], [1.34, 0, 0], [-0.56, 0.93, 0], [-0.56, -0.93, 0], [1.90, 0.93, 0], [1.90, -0.93, 0]]
+    ethene_bonds = [(0, 1), (0, 2), (0, 3), (1, 4), (1, 5)]
+    cases = [
+        ("single_plain", "Single", ["C", "Cl", "H", "H", "H"], [(0, 1), (0, 2), (0, 3), (0, 4)], methyl_x, 1, [1], False, None),
+        ("single_nodim", "Single", ["C", "Si", "H", "H", "H"], [(0, 1), (0, 2), (0, 3), (0, 4)], methyl_x, 1, [1], False, None),
+        ("single_sigmastar", "Single", ["C", "Cl", "H", "H", "H"], [(0, 1), (0, 2), (0, 3), (0, 4)], methyl_x, 1, [0, 1], True, None),
+        ("sp3_leaving_group", "Sp3", ["C", "Cl", "H", "H", "H"], [(0, 1), (0, 2), (0, 3), (0, 4)], methyl_x, 0, [0], False, None),
+        ("sp3_one_heavy", "Sp3", ["C", "C", "H", "H", "H"], [(0, 1), (0, 2), (0, 3), (0, 4)], methyl_x, 0, [0], False, None),
+        ("sp3_ambiguous", "Sp3", ["C", "C", "C", "H", "H"], [(0, 1), (0, 2), (0, 3), (0, 4)], methyl_x, 0, [0], False, None),
+        ("sp3_sigmastar", "Sp3", ["C", "Cl", "H", "H", "H"], [(0, 1), (0, 2), (0, 3), (0, 4)], methyl_x, 0, [0, 1], True, None),
+        ("sp2", "Sp2", ["C", "C", "H", "H", "H", "H"], ethene_bonds, ethene, 0, [0, 1], False, None),
+        ("ether", "Ether", ["O", "C", "C", "H"], [(0, 1), (0, 2), (1, 3)], [[0, 0, 0], [1.1, 0.8, 0], [-1.1, 0.8, 0], [1.9, 0.1, 0.3]],
+         0, [0], False, None),
+        ("ketone_sp2", "Ketone", ["O", "C", "C", "H"], [(0, 1), (1, 2), (1, 3)], [[0, 0, 0], [1.22, 0, 0], [1.95, 1.25, 0], [1.80, -0.93, 0.1]],
+         0, [0], False, [False, False, False, False]),
+        ("ketone_mixed", "Ketone", ["O", "C", "C", "H"], [(0, 1), (1, 2), (1, 3)], [[0, 0, 0], [1.22, 0, 0], [1.95, 1.25, 0], [1.80, -0.93, 0.1]],
+         0, [0], False, [True, False, True, True]),
+        ("ketone_ketene", "Ketone", ["O", "C", "C", "H", "H"], [(0, 1), (1, 2), (2, 3), (2, 4)],
+         [[0, 0, 0], [1.16, 0, 0], [2.47, 0, 0], [3.03, 0.93, 0], [3.03, -0.93, 0]], 0, [0], False, [False] * 4),
+        ("ketone_trilobe", "Ketone", ["O", "C", "H", "H", "C"], [(0, 1), (1, 2), (1, 3), (1, 4)],
+         [[0, 0, 0], [1.40, 0, 0], [1.76, 1.03, 0], [1.76, -0.51, 0.89], [1.90, -0.72, -1.25]], 0, [0], False, [False] * 4),
+        ("imine_lone_pair", "Imine", ["N", "C", "C", "H"], [(0, 1), (0, 2), (1, 3)], [[0, 0, 0], [1.27, 0.2, 0], [-0.8, 1.2, 0], [1.8, -0.7, 0]],
+         0, [0], False, [False] * 4),
+        ("imine_p", "Imine", ["N", "C", "C", "H"], [(0, 1), (0, 2), (1, 3)], [[0, 0, 0], [1.27, 0.2, 0], [-0.8, 1.2, 0], [1.8, -0.7, 0]],
+         0, [0], False, [True] * 4),
+    ]
+    del t
+    return cases
+
+
+def main_orbitals():
+    """Orbital centres by the UNMODIFIED reactive-atom classes (reactive_atoms_classes.py) on duck-typed molecules with
+    four jittered conformers each; the batched builder firecode_b200.orbitals is pinned to these."""
+    loader.install()
+    import firecode.reactive_atoms_classes as rac
+    from firecode.parameters import orb_dim_dict
+
+    rng = np.random.default_rng(20261018)
+    out = {}
+    names = []
+    for name, cls_name, atoms, bonds, rest, index, reactive, sigmastar, sigmatropic in orbital_cases():
+        rest = np.asarray(rest, dtype=float)
+        coords = np.array([rest + rng.normal(size=rest.shape) * 0.04 for _ in range(4)])
+        sigmatropic = [False] * 4 if sigmatropic is None else sigmatropic
+        mol = _DuckMol(atoms, bonds, coords, reactive, sigmastar, sigmatropic)
+        centers, kinds = [], []
+        for c in range(4):
+            atom = getattr(rac, cls_name)()
+            atom.init(mol, index, update=True, conf=c)
+            centers.append(np.asarray(atom.center, dtype=float))
+            kinds.append(repr(atom))
+        kind = kinds[0].split(" (")[0]
+        dim = orb_dim_dict.get(f"{atoms[index]} {kind}")
+        if dim is None and kind != "Single Bond":
+            dim = orb_dim_dict["Fallback"]
+        out[f"{name}_atoms"] = np.array(atoms)
+        out[f"{name}_bonds"] = np.array(bonds, dtype=np.int64)
+        out[f"{name}_coords"] = coords
+        out[f"{name}_index"] = np.int64(index)
+        out[f"{name}_reactive"] = np.array(reactive, dtype=np.int64)
+        out[f"{name}_sigmastar"] = np.bool_(sigmastar)
+        out[f"{name}_sigmatropic"] = np.array(sigmatropic)
+        out[f"{name}_kinds"] = np.array(kinds)
+        out[f"{name}_orb_dim"] = np.float64(np.nan if dim is None else dim)
+        out[f"{name}_centers"] = np.array(centers)
+        names.append(name)
+        print(f"orbitals {name}: {kinds[0]} -> centres {np.array(centers).shape}")
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLDEN, "orbitals.npz"), conventions=np.array(_conventions()), **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "orbitals":
+        main_orbitals()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "multiembed":
         main_multiembed()
         sys.exit(0)
@@ -455,3 +550,4 @@ if __name__ == "__main__":
     main_refining()
     main_multiembed()
     main_setup()
+    main_orbitals()
