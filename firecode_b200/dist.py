@@ -228,13 +228,12 @@ def device_all_gather(group=None):
     leaves the rank-order concatenation of every rank's ``nbytes`` device bytes at ``recv_ptr``, ordered on the
     library's CUDA stream.  NCCL moves the bytes GPU to GPU (NVLink / NVSwitch on the box); with a gloo group (CPU
     tests, several ranks sharing one GPU) the pieces are staged through the host."""
-    import torch
-
-    dist = _dist()
-    backend = dist.get_backend(group)
-    world = dist.get_world_size(group)
-
     def gather(send_ptr, recv_ptr, nbytes, stream_ptr):
+        import torch
+
+        dist = _dist()
+        backend = dist.get_backend(group)
+        world = dist.get_world_size(group)
         dev = torch.device("cuda", torch.cuda.current_device())
         send = torch.as_tensor(_RawDeviceBytes(send_ptr, nbytes), device=dev)
         recv = torch.as_tensor(_RawDeviceBytes(recv_ptr, nbytes * world), device=dev)

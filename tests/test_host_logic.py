@@ -289,7 +289,10 @@ def test_prune_sharded_replicates_small_ensembles(monkeypatch):
     fdist.prune_sharded(x, ["C"] * 3, "rmsd", max_rmsd=0.3)
     assert "shard" not in calls[-1] and calls[-1]["max_rmsd"] == 0.3
     fdist.prune_sharded(x, ["C"] * 3, "rmsd", force_shard=True, max_rmsd=0.3)
-    rank, world, gather = calls[-1]["shard"]
+    rank, world, gather, gather_dev = calls[-1]["shard"]   # default: the exchange steps run on the devices
+    assert (rank, world) == (1, 4) and gather is None and callable(gather_dev)
+    fdist.prune_sharded(x, ["C"] * 3, "rmsd", force_shard=True, host_staged=True, max_rmsd=0.3)
+    rank, world, gather = calls[-1]["shard"]               # host-staged lists (round 1)
     assert (rank, world) == (1, 4) and callable(gather)
     monkeypatch.setattr(fdist, "PRUNE_SHARD_MIN_PAIRS", 1000.0)
     fdist.prune_sharded(x, ["C"] * 3, "moi")
