@@ -5,8 +5,10 @@
 //   -> clash screen (fc_clash.cu) -> order-preserving compaction of the survivors
 //   -> torsion fingerprints of the survivors (tfd_fingerprint_kernel; torsion_module.py:1070-1076)
 //   -> keep-first sweep against ALL earlier accepted poses (embeds.py:59-84: the "LRU" cache never
-//      evicts), blocked so that every (candidate, accepted) pair is evaluated
-//      exactly once on the GPU and the order of acceptance is the reference's
+//      evicts) = the lexicographically first maximal independent set of the
+//      similarity graph: all pairs of a block of candidates into a bit matrix (FP32 pre-screen with
+//      a margin, FP64 decision), then rounds of final verdicts over the whole block in one
+//      cooperative launch -- the accepted set and its order are the reference's
 //   -> materialisation of the kept poses only (get_embed, embeds.py:808-817).
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>

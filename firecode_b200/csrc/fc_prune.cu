@@ -11,8 +11,10 @@
 // matrix of the centred coordinates, FP32 bounds on the sum of singular values in the epilogue), otherwise by
 // prune_screen_f32_kernel (FP32 CUDA cores, 32x32 pair tiles) -- and the pairs a screen cannot rule out are
 // decided in FP64 by prune_exact_kernel (one warp per pair: covariance, Jacobi, rotate-and-deviate as
-// rmsd_and_max does).  FC_PRUNE_FP64=1 and the MOI flavour use prune_pairs_kernel alone.  Similar pairs come
-// back as a compact list and the order-dependent keep rule is resolved on the host (prune_resolve).
+// rmsd_and_max does).  FC_PRUNE_FP64=1 and the MOI flavour use prune_pairs_kernel alone.  Similar pairs are
+// sorted by their deciding structure on the device and come back as one list, which the host resolves in a
+// linear scan (prune_resolve); a pass costs one host wait.  Several GPUs: work items dealt to the ranks, lists
+// all-gathered through the host (fc_prune_sharded) or GPU to GPU (fc_prune_sharded_dev).
 //   similar(i, j)  <=>  rmsd < max_rmsd  and  max deviation < max_dev      (heavy atoms, centred)
 //   MOI flavour    <=>  all three principal moments within max_deviation (relative to structure i)
 // Keep rules: "greedy" updates the mask in place (NMS sweep), "snapshot" reads the mask of the pass
