@@ -18,7 +18,7 @@
 //
 // CTA = 736 threads, one per SM, persistent over work items (128-row block x range of 16-column
 // tiles): warp 0 = copy producer (A once per item, B tiles through a 4-stage ring), warps 1-6 = MMA
-// issuers (one per accumulator stage and component: kc / 2 k-steps of tcgen05.mma M128 N48 K8 per tile, two
+// issuers (tile parity x component: kc / 2 k-steps of tcgen05.mma M128 N48 K16 (FP16) per tile, three
 // accumulator stages in TMEM), warps 7-22 = epilogue (tcgen05.ld of 4 pairs' 3x3 blocks per thread,
 // Frobenius bound, cofactor bound, and a shared-memory queue that finishes the few remaining pairs with
 // a Newton iteration on the QCP quartic, 32 at a time).
@@ -62,9 +62,11 @@ struct GramArgs {
 };
 
 constexpr int kGramEpiWarps = 16;
-constexpr int kGramIssuers = 6;     // MMA-issuing warps: (accumulator stage, component)
+constexpr int kGramIssuers = 6;     // MMA-issuing warps: (tile parity, component)
 constexpr int kGramThreads = 32 * (1 + kGramIssuers + kGramEpiWarps);  // producer, MMA issuers, epilogue warps
 constexpr int kGramBStages = 4;
+constexpr int kGramDStages = 3;     // accumulator stages in tensor memory: 3 x (3 components x 48 columns) = 432 of 512 columns
+constexpr unsigned kGramDStageCols = 160, kGramDCompCols = 48;
 constexpr int kGramMaxKc = 22;   // <= 176 selected atoms as FP16 (88 as TF32): operands + pair queues must fit the 227 KB of shared memory
 constexpr unsigned kGramWaitHintNs = 20000;  // suspend-time hint of the mbarrier waits (the phase completing ends the sleep)
 constexpr int kGramQueue = 32;   // entries of an epilogue warp's queue of pairs that need the Newton iteration
@@ -261,18 +263,18 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
     const unsigned A_FULL = bar0, A_EMPTY = bar0 + 8;
     auto B_FULL = [&](unsigned s) { return bar0 + 16 + 8 * s; };
     auto B_EMPTY = [&](unsigned s) { return bar0 + 48 + 8 * s; };
-    auto D_FULL = [&](unsigned s) { return bar0 + 80 + 8 * s; };
-    auto D_EMPTY = [&](unsigned s) { return bar0 + 96 + 8 * s; };
+    auto D_FULL = [&](unsigned s) { return bar0 + 80 + 8 * s; };    // 80, 88, 96
+    auto D_EMPTY = [&](unsigned s) { return bar0 + 104 + 8 * s; };  // 104, 112, 120 (16 barrier slots in all)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         bar_init(A_FULL, 1);
         bar_init(A_EMPTY, kGramIssuers);
         for (unsigned s = 0; s < kGramBStages; ++s) { bar_init(B_FULL(s), 1); bar_init(B_EMPTY(s), 3); }
-        for (unsigned s = 0; s < 2; ++s) { bar_init(D_FULL(s), 3); bar_init(D_EMPTY(s), kGramEpiWarps); }
+        for (unsigned s = 0; s < kGramDStages; ++s) { bar_init(D_FULL(s), 3); bar_init(D_EMPTY(s), kGramEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // 512 columns of tensor memory: two accumulator stages x 3 components x 64 columns
+    if (warp == 1) {  // 512 columns of tensor memory: three accumulator stages x 3 components x 48 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -312,18 +314,19 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
         if (lane == 0) {  // ---- MMA issuers ----
             // Six issuing threads: a tcgen05.mma costs its issuing thread 65-130 cycles whatever N is (the operands go
             // through uniform registers; measured, tools/gram_tc_test.cu), while the tensor pipe needs ~24 cycles for this
-            // shape, so one issuer caps the kernel at a fifth of what the operand fetch allows.  Tile g (counted over the
-            // whole CTA) uses operand slot g % 4 and accumulator stage g % 2; issuer (stage, comp) issues the kc / 2
-            // k-steps of component comp for the tiles of its stage.
+            // shape, so one issuer caps the kernel at a fifth of what the operand fetch allows.
             // instruction descriptor: D = F32 (bit 4), A = B = TF32 (bits 7, 10), both K-major, N = 48 (>> 3 at bit 17),
             // M = 128 (>> 4 at bit 24)
-            const unsigned stage = (unsigned)(warp - 1) / 3u, comp = (unsigned)(warp - 1) % 3u;
+            // Tile g (counted over the whole CTA) uses operand slot g % 4 and accumulator stage g % 3 (its k-th use has
+            // barrier parity k & 1, k = g / 3); issuer (p, comp) issues component comp of the tiles with g % 2 == p.  Three
+            // stages let the MMAs run two tiles ahead of the slowest epilogue warp (with two, the sixteen epilogue warps
+            // spent a quarter of their time waiting for a stage that the slowest of them had not released yet).
+            const unsigned stage = (unsigned)(warp - 1) / 3u, comp = (unsigned)(warp - 1) % 3u;  // stage = the parity p
             // (FP16 operands: format code 0 in both fields, K = 16 per instruction -- the same 256 bytes per k-step)
             const unsigned fmt = a.tf32 ? 2u : 0u;
             const unsigned idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (6u << 17) | (8u << 24);
-            unsigned g = 0, bphases = 0, aphase = 0, dphase = 0;  // one phase bit per operand slot
+            unsigned g = 0, bphases = 0, aphase = 0;  // one phase bit per operand slot
             const unsigned sA_addr = smem_addr(sA) + comp * kc * 128, sB_addr = smem_addr(sB);
-            const unsigned d_tmem = tmem_base + stage * 256 + comp * 64;
             for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
                 const GramWork wk = a.work[w];
                 bar_wait(A_FULL, aphase, a.error, 3);
@@ -334,7 +337,9 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                     const long long c0 = a.prof ? clock64() : 0;
                     bar_wait(B_FULL(bs), (bphases >> bs) & 1u, a.error, 4);
                     const long long c1 = a.prof ? clock64() : 0;
-                    bar_wait(D_EMPTY(stage), dphase ^ 1u, a.error, 5);
+                    const unsigned dst = g % kGramDStages, dpar = (g / kGramDStages) & 1u;
+                    const unsigned d_tmem = tmem_base + dst * kGramDStageCols + comp * kGramDCompCols;
+                    bar_wait(D_EMPTY(dst), dpar ^ 1u, a.error, 5);
                     const long long c2 = a.prof ? clock64() : 0;
                     tc_fence_after();
                     const int ksteps = (a.no_math & 2) ? 1 : kc / 2;
@@ -346,9 +351,8 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                         db += 16;
                     }
                     tc_commit(B_EMPTY(bs));
-                    tc_commit(D_FULL(stage));
+                    tc_commit(D_FULL(dst));
                     bphases ^= 1u << bs;
-                    dphase ^= 1u;
                     if (a.prof && blockIdx.x == 0 && warp == 1) {
                         const long long c3 = clock64();
                         a.prof[0] += c1 - c0; a.prof[1] += c2 - c1; a.prof[2] += c3 - c2; a.prof[3] += 1;
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
         const int row_in_block = quarter * 32 + lane;
         float* queue = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 1 - kGramIssuers) * (6 * kGramQueue);  // this warp's pair queue
         int qn = 0;                                                                              // warp-uniform fill level
-        unsigned dstage = 0, dphase = 0;
+        unsigned ge = 0;  // tiles seen so far: stage ge % 3, parity (ge / 3) & 1
         // accumulator column of (column position 8 g + r, component cb) = 24 g + 8 cb + r
         const unsigned tcol = (unsigned)(24 * (part >> 1) + 4 * (part & 1));
         for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
@@ -382,15 +386,17 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                 const int4 sc = *reinterpret_cast<const int4*>(a.spos + pcol0);
                 const float4 gc = *reinterpret_cast<const float4*>(a.gp + pcol0);
                 const long long e0 = a.prof ? clock64() : 0;
+                const unsigned dstage = ge % kGramDStages, dphase = (ge / kGramDStages) & 1u;
+                ++ge;
                 bar_wait(D_FULL(dstage), dphase, a.error, 6);
                 const long long e1 = a.prof ? clock64() : 0;
                 tc_fence_after();
                 float h[3][3][4];  // [component of the row structure][component of the column structure][column]
-                const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + dstage * 256 + tcol;
+                const unsigned taddr = tmem_base + ((unsigned)(quarter * 32) << 16) + dstage * kGramDStageCols + tcol;
 #pragma unroll
                 for (int ca = 0; ca < 3; ++ca)
 #pragma unroll
-                    for (int cb = 0; cb < 3; ++cb) tmem_ld4(taddr + ca * 64 + cb * 8, h[ca][cb]);
+                    for (int cb = 0; cb < 3; ++cb) tmem_ld4(taddr + ca * kGramDCompCols + cb * 8, h[ca][cb]);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -399,8 +405,6 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                     const long long e2 = clock64();
                     a.prof[4] += e1 - e0; a.prof[5] += e2 - e1; a.prof[6] += 1;
                 }
-                dstage ^= 1;
-                if (dstage == 0) dphase ^= 1;
 
                 if (a.dump) {
 #pragma unroll
