@@ -54,7 +54,7 @@ def _chunk_bounds(mask, k, chunk_over):
 
 
 def _run(structures, mode, sel, masses, max_rmsd, max_dev, moi_dev, energies, max_dE, keep, pass_mode,
-         tie_cap=1 << 16, shard=None, chunk_over=None):
+         tie_cap=1 << 16, shard=None, chunk_over=None, want_structures=True):
     """``shard`` = (rank, world, allgather) runs the multi-GPU form with host-staged lists: allgather(bytes ndarray)
     must return the rank-order concatenation of every rank's buffer; ``shard`` = (rank, world, None, allgather_dev) the
     device-resident form (C-ABI fc_prune_sharded_dev).  firecode_b200.dist supplies both."""
@@ -131,7 +131,9 @@ def _run(structures, mode, sel, masses, max_rmsd, max_dev, moi_dev, energies, ma
                               ties=ties[: min(int(n_ties.value), tie_cap)], n_ties_total=int(n_ties.value),
                               keep=keep, pass_mode=pass_mode)
     mask = mask.astype(bool)
-    return _take(lib, x, mask), mask
+    # want_structures=False: the mask alone (every rank of a sharded call would otherwise write its own copy of the kept
+    # structures -- 232 MB per rank at BASELINE config C4 -- through the one host memory they share)
+    return (_take(lib, x, mask) if want_structures else None), mask
 
 
 def _take(lib, x, mask):
@@ -146,7 +148,8 @@ def _take(lib, x, mask):
 
 
 def prune_by_rmsd(structures, atoms, max_rmsd=0.25, max_dev=None, energies=None, max_dE=0.0,
-                  debugfunction=None, logfunction=None, keep=None, pass_mode=None, shard=None, chunk_over=None):
+                  debugfunction=None, logfunction=None, keep=None, pass_mode=None, shard=None, chunk_over=None,
+                  want_structures=True):
     """Heavy-atom, centred Kabsch RMSD pruning: a structure is dropped when a kept one has
     rmsd < max_rmsd and max atomic deviation < max_dev (default 2 * max_rmsd)."""
     atoms = np.asarray(atoms)
@@ -156,7 +159,7 @@ def prune_by_rmsd(structures, atoms, max_rmsd=0.25, max_dev=None, energies=None,
     else:
         sel = np.arange(len(atoms))
     out, mask = _run(structures, 0, sel, None, max_rmsd, max_dev, 0.0, energies, max_dE, keep, pass_mode, shard=shard,
-                     chunk_over=chunk_over)
+                     chunk_over=chunk_over, want_structures=want_structures)
     if debugfunction is not None:
         debugfunction(f"DEBUG: prune_by_rmsd (firecode_b200) - kept {int(mask.sum())}/{len(mask)}")
     return out, mask
@@ -164,13 +167,13 @@ def prune_by_rmsd(structures, atoms, max_rmsd=0.25, max_dev=None, energies=None,
 
 def prune_by_moment_of_inertia(structures, atoms, max_deviation=None, energies=None, max_dE=0.0,
                                debugfunction=None, logfunction=None, keep=None, pass_mode=None, shard=None,
-                               chunk_over=None):
+                               chunk_over=None, want_structures=True):
     """Drop structures whose three principal moments of inertia are all within ``max_deviation``
     (relative, default 1 %) of a kept structure (CHANGELOG.md:256)."""
     max_deviation = conventions.MOI_MAX_DEVIATION if max_deviation is None else max_deviation
     masses = np.array([MASSES[str(a)] for a in np.asarray(atoms)])
     out, mask = _run(structures, 1, None, masses, 0.0, 0.0, max_deviation, energies, max_dE, keep, pass_mode, shard=shard,
-                     chunk_over=chunk_over)
+                     chunk_over=chunk_over, want_structures=want_structures)
     if debugfunction is not None:
         debugfunction(f"DEBUG: prune_by_moment_of_inertia (firecode_b200) - kept {int(mask.sum())}/{len(mask)}")
     return out, mask

@@ -240,6 +240,8 @@ def test_prune_c4_20k_subset_matches_oracle(gpu):
     assert np.array_equal(mask, ref_mask)
     assert np.array_equal(out, structures[ref_mask])
     assert 4000 < mask.sum() < 16000
+    none, mask_only = pruner.prune_by_rmsd(structures, atoms, 0.5, want_structures=False)   # the mask alone
+    assert none is None and np.array_equal(mask_only, mask)
 
 
 def test_prune_rank_deficient_species(gpu):
