@@ -48,8 +48,13 @@ def main():
     # pruning: tiles dealt to the ranks, similar-pair lists all-gathered
     atoms, structures, _ = synthetic.pruning_ensemble(np.random.default_rng(7), 6000, 40, 300, jitter=(0.02, 0.4))
     _, m1 = pruner.prune_by_rmsd(structures, atoms, 0.5)
-    _, mw = fdist.prune_sharded(structures, atoms, "rmsd", force_shard=True, max_rmsd=0.5)
-    assert np.array_equal(m1, mw)
+    _, mw = fdist.prune_sharded(structures, atoms, "rmsd", force_shard=True, max_rmsd=0.5)          # exchange on the devices
+    _, mh = fdist.prune_sharded(structures, atoms, "rmsd", force_shard=True, host_staged=True, max_rmsd=0.5)
+    none, mm = fdist.prune_sharded(structures, atoms, "rmsd", force_shard=True, max_rmsd=0.5, want_structures=False)
+    assert np.array_equal(m1, mw) and np.array_equal(m1, mh) and np.array_equal(m1, mm) and none is None
+    _, i1 = pruner.prune_by_moment_of_inertia(structures, atoms)
+    _, iw = fdist.prune_sharded(structures, atoms, "moi", force_shard=True)
+    assert np.array_equal(i1, iw)
     dist.barrier()
     if rank == 0:
         print(f"dist_check OK on {world} GPUs (clash, string, trimolecular, bimolecular, pruning)")
