@@ -711,6 +711,11 @@ def run_extras():
                                    "mask_checksum": int(np.flatnonzero(mask).sum()),
                                    "h2d_bytes": int(structures.nbytes),
                                    "library_ms": rep.wall_ms,
+                                   "screen_tiles_planned": rep.screen_tiles_planned,
+                                   "screen_tiles_multiplied": rep.screen_tiles_multiplied,
+                                   "screen_note": "a 128 x 16 tile whose structures' singular-value ranges are further apart than "
+                                                  "the threshold (E >= sum (sigma_k(P) - sigma_k(Q))^2) is ruled out without "
+                                                  "being multiplied; `pairs` counts every pair the screen decided",
                                    "conventions": {"keep": rep.keep, "pass_mode": rep.pass_mode}}
     if rep.screen_ms > 0:
         # roofline of the tensor-core screen (fc::gram_tc_kernel), summed over the launches of the run: algorithmic work per

@@ -55,6 +55,12 @@ struct GramArgs {
     long long cand_cap;
     float* dump;              // debug: H of every (prow, pcol) visited, [prow][dump_ld][9]; null in production
     int dump_ld;
+    const float4* tile_norm;  // per 16-position tile the ranges {lo1, hi1, lo2, hi2}, {lo3, hi3, -, -} of the three singular
+                              // values of its structures' centred coordinates ({+inf, -inf}: no structure), or null; with
+                              // it, a (row block, column tile) whose ranges are apart by more than cull_gap2 in squared
+                              // distance is skipped by all three roles: E >= sum_k (sigma_k(P) - sigma_k(Q))^2 (von Neumann)
+    float cull_gap2;          // the (banded) threshold on the summed squared deviation, with a safety factor
+    unsigned long long* tiles_done;  // += column tiles actually multiplied (statistics; may be null)
     int* error;               // set when a barrier wait times out (the kernel then runs out, the host reports it)
     long long* prof;          // debug: cycle counters of CTA 0 (see tools/gram_tc_test.cu); null in production
     int no_math;              // debug bits (tools/gram_tc_test.cu; 0 in production): 1 = the epilogue only drains tensor
@@ -220,6 +226,72 @@ __global__ void __launch_bounds__(256) gram_pack_kernel(const float4* __restrict
     }
 }
 
+// ---- tile culling -----------------------------------------------------------------------------------
+// For centred coordinate matrices P, Q (atoms x 3) the best superposition gives
+//   E = |P|^2 + |Q|^2 - 2 max_R tr(R P^T Q)  >=  sum_k (sigma_k(P) - sigma_k(Q))^2
+// (von Neumann's trace inequality; sigma_k = singular values, descending), so two structures whose shape numbers differ
+// by more than the threshold cannot be similar whatever their orientation.  The positions of a segment are sorted by
+// sigma_1; per 16-position tile the ranges of the three sigma_k; a (row block, column tile) pair whose ranges are too
+// far apart is skipped before anything is copied or multiplied.
+struct SigRange { float lo[3], hi[3]; };
+
+__global__ void gram_tile_norm_kernel(const float4* __restrict__ sig, const int* __restrict__ spos, int n_tiles,
+                                      float4* __restrict__ tile_norm) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const float inf = __int_as_float(0x7f800000);
+    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+    for (int k = 0; k < 16; ++k) {
+        const int sidx = spos[16 * t + k];
+        if (sidx >= 0) {
+            const float4 v = sig[sidx];
+            lo[0] = fminf(lo[0], v.x); hi[0] = fmaxf(hi[0], v.x);
+            lo[1] = fminf(lo[1], v.y); hi[1] = fmaxf(hi[1], v.y);
+            lo[2] = fminf(lo[2], v.z); hi[2] = fmaxf(hi[2], v.z);
+        }
+    }
+    tile_norm[2 * t] = make_float4(lo[0], hi[0], lo[1], hi[1]);
+    tile_norm[2 * t + 1] = make_float4(lo[2], hi[2], 0.f, 0.f);
+}
+
+// sort keys of the positions: (segment << 16) | the top 16 bits of sigma_1 (non-negative floats order like their bits; the
+// order inside a segment only has to be roughly by sigma_1: any order is valid, a rough one widens a tile's range by
+// less than 1 %); padding sorts behind the structures of its segment
+__global__ void gram_sort_key_kernel(const int* __restrict__ spos, const int* __restrict__ seg, const float4* __restrict__ sig,
+                                     int n_pos, unsigned long long* __restrict__ keys) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_pos) return;
+    const int sidx = spos[q];
+    const unsigned low = sidx >= 0 ? (__float_as_uint(sig[sidx].x) >> 16) : 0xffffu;
+    keys[q] = ((unsigned long long)(unsigned)seg[q] << 16) | low;
+}
+
+namespace gram {
+// ranges of the 128-row block starting at position row0 (8 tiles)
+__device__ __forceinline__ SigRange block_norm_range(const float4* __restrict__ tile_norm, int row0) {
+    const float inf = __int_as_float(0x7f800000);
+    SigRange r{{inf, inf, inf}, {-inf, -inf, -inf}};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 a = tile_norm[2 * ((row0 >> 4) + k)], b = tile_norm[2 * ((row0 >> 4) + k) + 1];
+        r.lo[0] = fminf(r.lo[0], a.x); r.hi[0] = fmaxf(r.hi[0], a.y);
+        r.lo[1] = fminf(r.lo[1], a.z); r.hi[1] = fmaxf(r.hi[1], a.w);
+        r.lo[2] = fminf(r.lo[2], b.x); r.hi[2] = fmaxf(r.hi[2], b.y);
+    }
+    return r;
+}
+// true: no pair of (row block with ranges `rows`, column tile `ct`) can be similar.  Evaluated identically by the copy
+// producer, the MMA issuers and the epilogue warps, which therefore agree on the sequence of tiles.  An empty range
+// ({+inf, -inf}) gives an infinite gap: culled; inf - inf does not occur.
+__device__ __forceinline__ bool tile_culled(const float4* __restrict__ tile_norm, const SigRange& rows, int ct, float cull_gap2) {
+    const float4 a = tile_norm[2 * ct], b = tile_norm[2 * ct + 1];
+    const float g0 = fmaxf(0.f, fmaxf(a.x - rows.hi[0], rows.lo[0] - a.y));
+    const float g1 = fmaxf(0.f, fmaxf(a.z - rows.hi[1], rows.lo[1] - a.w));
+    const float g2 = fmaxf(0.f, fmaxf(b.x - rows.hi[2], rows.lo[2] - b.y));
+    return fmaf(g0, g0, fmaf(g1, g1, g2 * g2)) > cull_gap2;
+}
+}  // namespace gram
+
 // ---- the Gram screen --------------------------------------------------------------------------------
 // Finishes the queued pairs of one warp, one lane per pair.  Entry = {u, f2, cc, det, row structure, column structure}.
 // Newton from above on  P(x) = (x^2 - f2)^2 - 8 det x - 4 cc  (the QCP characteristic polynomial, largest root = sum of the
@@ -243,7 +315,9 @@ __device__ __forceinline__ void gram_newton_flush(const GramArgs& a, const float
         }
         if (!reject) {
             const unsigned long long slot = atomicAdd(a.n_cand, 1ull);
-            if ((long long)slot < a.cand_cap) a.cand[slot] = make_int2(__float_as_int(e[4]), __float_as_int(e[5]));
+            // (structure indices ascending: positions are ordered by norm inside a segment, not by index)
+            const int s1 = __float_as_int(e[4]), s2 = __float_as_int(e[5]);
+            if ((long long)slot < a.cand_cap) a.cand[slot] = make_int2(min(s1, s2), max(s1, s2));
         }
     }
     __syncwarp();
@@ -288,6 +362,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
     if (warp == 0) {
         if (lane == 0) {  // ---- copy producer ----
             unsigned bstage = 0, bphase = 0, aphase = 0;
+            unsigned long long n_done = 0;
             for (int w = blockIdx.x; w < a.n_work; w += gridDim.x) {
                 const GramWork wk = a.work[w];
                 bar_wait(A_EMPTY, aphase ^ 1, a.error, 1);
@@ -296,7 +371,10 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                 for (unsigned g = 0; g < 16; ++g)
                     bulk_load(smem_addr(sA) + g * (a_bytes / 16), src + g * group_floats, a_bytes / 16, A_FULL);
                 aphase ^= 1;
+                const SigRange rows = a.tile_norm ? block_norm_range(a.tile_norm, wk.row0) : SigRange{};
                 for (int t = 0; t < wk.n_col_tiles; ++t) {
+                    if (a.tile_norm && tile_culled(a.tile_norm, rows, wk.col_tile0 + t, a.cull_gap2)) continue;
+                    ++n_done;
                     bar_wait(B_EMPTY(bstage), bphase ^ 1, a.error, 2);
                     if (a.no_math & 4) {
                         bar_arrive(B_FULL(bstage));
@@ -308,6 +386,7 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                     if (++bstage == kGramBStages) { bstage = 0; bphase ^= 1; }
                 }
             }
+            if (a.tiles_done && n_done) atomicAdd(a.tiles_done, n_done);
         }
         __syncwarp();
     } else if (warp <= kGramIssuers) {
@@ -331,13 +410,16 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
                 const GramWork wk = a.work[w];
                 bar_wait(A_FULL, aphase, a.error, 3);
                 aphase ^= 1;
-                for (int t = 0; t < wk.n_col_tiles; ++t, ++g) {
-                    if ((g & 1u) != stage) continue;
-                    const unsigned bs = g % kGramBStages;
+                const SigRange rows = a.tile_norm ? block_norm_range(a.tile_norm, wk.row0) : SigRange{};
+                for (int t = 0; t < wk.n_col_tiles; ++t) {
+                    if (a.tile_norm && tile_culled(a.tile_norm, rows, wk.col_tile0 + t, a.cull_gap2)) continue;
+                    const unsigned g_now = g++;
+                    if ((g_now & 1u) != stage) continue;
+                    const unsigned bs = g_now % kGramBStages;
                     const long long c0 = a.prof ? clock64() : 0;
                     bar_wait(B_FULL(bs), (bphases >> bs) & 1u, a.error, 4);
                     const long long c1 = a.prof ? clock64() : 0;
-                    const unsigned dst = g % kGramDStages, dpar = (g / kGramDStages) & 1u;
+                    const unsigned dst = g_now % kGramDStages, dpar = (g_now / kGramDStages) & 1u;
                     const unsigned d_tmem = tmem_base + dst * kGramDStageCols + comp * kGramDCompCols;
                     bar_wait(D_EMPTY(dst), dpar ^ 1u, a.error, 5);
                     const long long c2 = a.prof ? clock64() : 0;
@@ -379,7 +461,9 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_tc_kernel(GramArgs a) {
             const int s_row = prow < wk.pend ? a.spos[prow] : -1;
             const float g_row = prow < wk.pend ? a.gp[prow] : 0.f;
             const double e_row = (a.energies && s_row >= 0) ? a.energies[s_row] : 0.0;
+            const SigRange rows = a.tile_norm ? block_norm_range(a.tile_norm, wk.row0) : SigRange{};
             for (int t = 0; t < wk.n_col_tiles; ++t) {
+                if (a.tile_norm && tile_culled(a.tile_norm, rows, wk.col_tile0 + t, a.cull_gap2)) continue;  // warp-uniform
                 __syncwarp();  // the tensor-memory loads below are warp-collective
                 // column metadata first: these loads fly while the accumulator is still being produced
                 const int pcol0 = 16 * (wk.col_tile0 + t) + 4 * part;

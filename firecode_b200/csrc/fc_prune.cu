@@ -38,9 +38,11 @@ namespace fc {
 // ---------------------------------------------------------------------------------------------
 // heavy-atom coordinates centred on their mean: out (n, nh, 3); g[i] = sum |x|^2
 // outf: the same coordinates as float4 {x, y, z, 0} for the FP32 screen
+// sig (optional): the three singular values of the centred coordinate matrix, descending (square roots of the
+// eigenvalues of its 3x3 Gram matrix), the rotation-invariant shape numbers the screen culls tiles with
 __global__ void prune_center_kernel(const double* __restrict__ coords, int n_atoms, const int* __restrict__ sel,
                                     int nh, long long n, double* __restrict__ out, double* __restrict__ g,
-                                    float4* __restrict__ outf) {
+                                    float4* __restrict__ outf, float4* __restrict__ sig) {
     long long s = blockIdx.x;
     if (s >= n) return;
     const double* src = coords + (size_t)s * n_atoms * 3;
@@ -63,7 +65,7 @@ __global__ void prune_center_kernel(const double* __restrict__ coords, int n_ato
         mean[c] = v / nh;
     }
     __syncthreads();
-    double gg = 0;
+    double gg = 0, m2[6] = {0, 0, 0, 0, 0, 0};  // xx, xy, xz, yy, yz, zz
     double* dst = out + (size_t)s * nh * 3;
     for (int k = threadIdx.x; k < nh; k += blockDim.x) {
         const double* a = src + 3 * (sel ? sel[k] : k);
@@ -71,14 +73,36 @@ __global__ void prune_center_kernel(const double* __restrict__ coords, int n_ato
         dst[3 * k] = x; dst[3 * k + 1] = y; dst[3 * k + 2] = z;
         outf[(size_t)s * nh + k] = make_float4((float)x, (float)y, (float)z, 0.f);
         gg += x * x + y * y + z * z;
+        m2[0] += x * x; m2[1] += x * y; m2[2] += x * z; m2[3] += y * y; m2[4] += y * z; m2[5] += z * z;
     }
     for (int o = 16; o > 0; o >>= 1) gg += __shfl_xor_sync(0xffffffffu, gg, o);
     if ((threadIdx.x & 31) == 0) sm[0][threadIdx.x >> 5] = gg;
+    __shared__ double sm2[6][32];
+    if (sig) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+            double v = m2[c];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) sm2[c][threadIdx.x >> 5] = v;
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         double v = 0;
         for (int w = 0; w < (blockDim.x + 31) / 32; ++w) v += sm[0][w];
         g[s] = v;
+        if (sig) {
+            double t[6] = {0, 0, 0, 0, 0, 0};
+            for (int c = 0; c < 6; ++c)
+                for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t[c] += sm2[c][w];
+            const double a9[9] = {t[0], t[1], t[2], t[1], t[3], t[4], t[2], t[4], t[5]};
+            double w3[3], v9[9];
+            jacobi_eig3(a9, w3, v9);
+            if (w3[0] < w3[1]) { double q = w3[0]; w3[0] = w3[1]; w3[1] = q; }
+            if (w3[1] < w3[2]) { double q = w3[1]; w3[1] = w3[2]; w3[2] = q; }
+            if (w3[0] < w3[1]) { double q = w3[0]; w3[0] = w3[1]; w3[1] = q; }
+            sig[s] = make_float4((float)sqrt(fmax(w3[0], 0.0)), (float)sqrt(fmax(w3[1], 0.0)), (float)sqrt(fmax(w3[2], 0.0)), 0.f);
+        }
     }
 }
 
@@ -572,16 +596,27 @@ static inline int64_t chunk_of(const std::vector<int64_t>& bounds, int64_t idx) 
     return (int64_t)(std::upper_bound(bounds.begin(), bounds.end() - 1, idx) - bounds.begin()) - 1;
 }
 
+// `seg` (optional): per padded position, the number of the segment it belongs to -- a run of positions whose structures
+// shared a chunk of the previous pass (the whole chunk on the first pass); numbers increase along the positions and the
+// padding behind a chunk carries the number of the chunk's last segment.  The order of the positions INSIDE a segment
+// is free (pairs inside it are never evaluated, or -- first pass -- only by position order), which the driver uses to
+// sort them by norm on the device so that whole tiles can be culled.
 static void plan_gram_pass(const std::vector<uint8_t>& mask, int64_t n, const std::vector<int64_t>& bounds,
                            const std::vector<int64_t>& prev_bounds, int world,
                            int rank, int n_sms, std::vector<int>& spos, std::vector<GramWork>& work, int64_t& pairs_tiled,
-                           int64_t& pairs_skipped) {
+                           int64_t& pairs_skipped, std::vector<int>* seg = nullptr) {
     struct RowBlock { int row0, c_min, tile_end, pend; };
     std::vector<RowBlock> blocks;
     const int64_t k = (int64_t)bounds.size() - 1;
     spos.clear();
     spos.reserve((size_t)n + 16 * (size_t)k + 256);
     work.clear();
+    int seg_no = 0;
+    size_t seg_pc = 0;  // previous-pass chunk of the structure the segment numbering has reached
+    if (seg) {
+        seg->clear();
+        seg->reserve((size_t)n + 16 * (size_t)k + 256);
+    }
     int64_t col_tiles_total = 0;
     for (int64_t c = 0; c < k; ++c) {
         const int64_t first = bounds[(size_t)c], last = bounds[(size_t)c + 1];
@@ -599,6 +634,26 @@ static void plan_gram_pass(const std::vector<uint8_t>& mask, int64_t n, const st
             spos.resize((size_t)pbegin + w);
         }
         const int pend = (int)spos.size(), len = pend - pbegin;
+        if (seg) {
+            seg->resize((size_t)pbegin, seg_no);   // the padding in front of this chunk: last segment of the chunk before
+            seg->resize((size_t)pend);
+            int* sg = seg->data();
+            if (prev_bounds.empty()) {
+                if (len > 0) std::fill(sg + pbegin, sg + pend, ++seg_no);
+            } else {
+                // runs of positions whose structures shared a chunk of the previous pass (structures ascend over the whole
+                // pass, so the pointer into prev_bounds only advances)
+                for (int q = pbegin; q < pend;) {
+                    const int64_t idx = spos[(size_t)q];
+                    while (seg_pc + 2 < prev_bounds.size() && prev_bounds[seg_pc + 1] <= idx) ++seg_pc;
+                    const int64_t idx_end = prev_bounds[seg_pc + 1];
+                    const int q_end = (int)(std::lower_bound(spos.begin() + q, spos.begin() + pend, idx_end,
+                                                             [](int v, int64_t lim) { return (int64_t)v < lim; }) - spos.begin());
+                    std::fill(sg + q, sg + q_end, ++seg_no);
+                    q = q_end;
+                }
+            }
+        }
         if (len < 2) continue;
         const int tile_end = (pend + 15) / 16;
         int64_t evaluated = 0;
@@ -626,17 +681,18 @@ static void plan_gram_pass(const std::vector<uint8_t>& mask, int64_t n, const st
         const char* v = getenv("FC_PRUNE_ITEMS_PER_SM");
         return v && atoll(v) > 0 ? (int64_t)atoll(v) : (int64_t)32;
     }();
-    const int64_t seg = std::min<int64_t>(1024, std::max<int64_t>(16, col_tiles_total / ((int64_t)n_sms * items_per_sm)));
+    const int64_t item_tiles = std::min<int64_t>(1024, std::max<int64_t>(16, col_tiles_total / ((int64_t)n_sms * items_per_sm)));
     int64_t item_no = 0;
     for (const RowBlock& b : blocks)
-        for (int c0 = b.c_min; c0 < b.tile_end; c0 += (int)seg) {
-            const int nt = (int)std::min<int64_t>(seg, b.tile_end - c0);
+        for (int c0 = b.c_min; c0 < b.tile_end; c0 += (int)item_tiles) {
+            const int nt = (int)std::min<int64_t>(item_tiles, b.tile_end - c0);
             if (item_no++ % world != rank) continue;
             work.push_back(GramWork{b.row0, c0, nt, b.pend});
             pairs_tiled += gram_item_pairs(b.row0, 16 * c0, std::min(16 * (c0 + nt), b.pend), b.pend);
         }
     while (spos.size() % 16) spos.push_back(-1);
     spos.resize(spos.size() + 128, -1);  // a row block may read 128 positions from its first row
+    if (seg) seg->resize(spos.size(), seg_no + 1);  // trailing padding: a segment of its own, behind everything
 }
 
 // Host-only view of plan_gram_pass for the tests (no CUDA call): positions and work items of one pass.
@@ -669,6 +725,15 @@ extern "C" int fc_prune_plan(const uint8_t* mask, int64_t n, int64_t k, int64_t 
 }
 
 static thread_local double g_prune_timing[6] = {0, 0, 0, 0, 0, 0};
+
+static thread_local double g_prune_tiles[2] = {0, 0};
+
+extern "C" int fc_prune_tiles(double* out2) {
+    FC_REQUIRE(out2, "fc_prune_tiles: null pointer");
+    out2[0] = g_prune_tiles[0];
+    out2[1] = g_prune_tiles[1];
+    return FC_OK;
+}
 
 extern "C" int fc_prune_timing(double* out6) {
     FC_REQUIRE(out6, "fc_prune_timing: null pointer");
@@ -716,9 +781,10 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
     cudaEventCreate(&ev_g0);
     cudaEventCreate(&ev_g1);
     double screen_slots = 0;
+    long long tiles_planned = 0;
     int64_t screen_launches = 0;
     // page-locked landing place of the per-pass counters (one per host thread, kept)
-    struct PassCounters { unsigned long long n_cand, found; int gram_err; };
+    struct PassCounters { unsigned long long n_cand, found, tiles_done; int gram_err; };
     static thread_local PassCounters* hb = nullptr;
     if (!hb) FC_CUDA(cudaHostAlloc((void**)&hb, sizeof(PassCounters), cudaHostAllocPortable));
     cudaStream_t s;
@@ -739,7 +805,10 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
         DevBuf<float4> d_xcf;
         DevBuf<PruneTile> d_tiles;
         DevBuf<float> d_img, d_gp;       // tensor-core screen: operand image and |x|^2 per padded position
-        DevBuf<int> d_spos, d_gram_err;
+        DevBuf<int> d_spos, d_gram_err, d_spos_raw, d_seg;
+        DevBuf<unsigned long long> d_keys;
+        DevBuf<float4> d_tile_norm, d_sig;   // per tile: two float4 {lo1, hi1, lo2, hi2}, {lo3, hi3, -, -}; per structure: sigma
+        std::vector<int> seg;
         DevBuf<GramWork> d_work;
         DevBuf<unsigned long long> d_eval;
         DevBuf<TieRecord> d_ties;
@@ -782,8 +851,9 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
             PR(d_xc.alloc((size_t)n * n_sel * 3, s));
             PR(d_xcf.alloc((size_t)n * n_sel, s));
             PR(d_g.alloc((size_t)n, s));
+            PR(d_sig.alloc((size_t)n, s));
             if (e == cudaSuccess) {
-                prune_center_kernel<<<(unsigned)n, 64, 0, s>>>(d_coords.p, n_sel, nullptr, n_sel, n, d_xc.p, d_g.p, d_xcf.p);
+                prune_center_kernel<<<(unsigned)n, 64, 0, s>>>(d_coords.p, n_sel, nullptr, n_sel, n, d_xc.p, d_g.p, d_xcf.p, d_sig.p);
                 e = cudaGetLastError();
             }
         } else {
@@ -820,6 +890,9 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
         // operands of the tensor-core screen: FP16 (8 atoms per 16-byte k-core) unless FC_PRUNE_TF32=1 (4 atoms)
         const char* envtf = getenv("FC_PRUNE_TF32");
         const int gram_tf32 = envtf && atoi(envtf) ? 1 : 0;
+        // FC_PRUNE_CULL=0: positions stay in index order and every tile is multiplied (the round-2 start behaviour)
+        const char* envcull = getenv("FC_PRUNE_CULL");
+        const bool gram_cull = !(envcull && !atoi(envcull));
         int kc = gram_tf32 ? (n_sel + 3) / 4 : (n_sel + 7) / 8;
         kc += kc & 1;
         const bool use_tc = two_stage && kc <= kGramMaxKc && !(envtc && !atoi(envtc));
@@ -839,7 +912,8 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
             double tp = now();
             const std::vector<int64_t> bounds = chunk_bounds(mask, n, k, over_active);
             if (use_tc) {
-                plan_gram_pass(mask, n, bounds, prev_bounds, world, rank, sm_count(), spos, work, pairs_tiled, pairs_skipped);
+                plan_gram_pass(mask, n, bounds, prev_bounds, world, rank, sm_count(), spos, work, pairs_tiled, pairs_skipped,
+                               gram_cull ? &seg : nullptr);
             } else {
                 // compacted active list + chunks over the FULL array (chunk size n // k, last takes the rest)
                 active.clear();
@@ -879,11 +953,41 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
                     if (d_spos.n < n_pos) { PR(d_spos.alloc(n_pos + n_pos / 4, s)); PR(d_gp.alloc(n_pos + n_pos / 4, s)); }
                     if (d_img.n < img_floats) PR(d_img.alloc(img_floats + img_floats / 4, s));
                     if (d_work.n < work.size()) PR(d_work.alloc(work.size() + work.size() / 4, s));
-                    PR(cudaMemcpyAsync(d_spos.p, spos.data(), n_pos * 4, cudaMemcpyHostToDevice, s));
                     PR(cudaMemcpyAsync(d_work.p, work.data(), work.size() * sizeof(GramWork), cudaMemcpyHostToDevice, s));
+                    if (!gram_cull) {
+                        PR(cudaMemcpyAsync(d_spos.p, spos.data(), n_pos * 4, cudaMemcpyHostToDevice, s));
+                    } else {
+                        // positions ordered by norm inside every segment (device radix sort on {segment, norm}): row blocks and
+                        // column tiles then cover narrow ranges of the norm and the screen skips the tiles that are too far apart
+                        if (d_spos_raw.n < n_pos) {
+                            PR(d_spos_raw.alloc(n_pos + n_pos / 4, s));
+                            PR(d_seg.alloc(n_pos + n_pos / 4, s));
+                            PR(d_keys.alloc(2 * (n_pos + n_pos / 4), s));
+                            PR(d_tile_norm.alloc(2 * ((n_pos + n_pos / 4) / 16 + 16), s));
+                        }
+                        PR(cudaMemcpyAsync(d_spos_raw.p, spos.data(), n_pos * 4, cudaMemcpyHostToDevice, s));
+                        PR(cudaMemcpyAsync(d_seg.p, seg.data(), n_pos * 4, cudaMemcpyHostToDevice, s));
+                        unsigned long long* k_in = d_keys.p;
+                        unsigned long long* k_out = d_keys.p + d_keys.n / 2;
+                        if (e == cudaSuccess) {
+                            gram_sort_key_kernel<<<(unsigned)((n_pos + 255) / 256), 256, 0, s>>>(d_spos_raw.p, d_seg.p, d_sig.p, (int)n_pos, k_in);
+                            e = cudaGetLastError();
+                        }
+                        int seg_bits = 1;
+                        while (((long long)1 << seg_bits) <= (long long)seg.back()) ++seg_bits;
+                        size_t need = 0;
+                        PR(cub::DeviceRadixSort::SortPairs(nullptr, need, k_in, k_out, d_spos_raw.p, d_spos.p, (int)n_pos, 0, 16 + seg_bits, s));
+                        if (d_sort_tmp.n < need) PR(d_sort_tmp.alloc(need + need / 4 + 256, s));
+                        need = d_sort_tmp.n;
+                        PR(cub::DeviceRadixSort::SortPairs(d_sort_tmp.p, need, k_in, k_out, d_spos_raw.p, d_spos.p, (int)n_pos, 0, 16 + seg_bits, s));
+                    }
                     if (e == cudaSuccess) {
                         gram_pack_kernel<<<(unsigned)(n_pos / 8), 256, 0, s>>>(d_xcf.p, d_g.p, d_spos.p, n_sel, kc, (int)(n_pos / 8),
                                                                               gram_tf32, d_img.p, d_gp.p);
+                        e = cudaGetLastError();
+                    }
+                    if (gram_cull && e == cudaSuccess) {
+                        gram_tile_norm_kernel<<<(unsigned)((n_pos / 16 + 127) / 128), 128, 0, s>>>(d_sig.p, d_spos.p, (int)(n_pos / 16), d_tile_norm.p);
                         e = cudaGetLastError();
                     }
                 } else {
@@ -898,7 +1002,7 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
                 for (int attempt = 0; attempt < 4 && !rc; ++attempt) {
                     if (d_pairs.n < (size_t)pair_cap) PR(d_pairs.alloc((size_t)pair_cap, s));
                     if (two_stage && d_cand.n < (size_t)cand_cap) PR(d_cand.alloc((size_t)cand_cap, s));
-                    PR(cudaMemsetAsync(d_eval.p + 1, 0, 16, s));
+                    PR(cudaMemsetAsync(d_eval.p + 1, 0, 24, s));
                     if (e != cudaSuccess) { rc = cuda_fail(e, "fc_prune pair list", __FILE__, __LINE__); break; }
                     PruneArgs a{};
                     a.xc = d_xc.p; a.xcf = d_xcf.p; a.g = d_g.p; a.moi = d_moi.p; a.energies = energies ? d_energy.p : nullptr;
@@ -922,6 +1026,9 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
                             ga.e0_scale = 1.0f - 1.7320508f * kGramTf32Eps;
                             ga.cand = d_cand.p; ga.n_cand = d_eval.p + 2; ga.cand_cap = cand_cap;
                             ga.dump = nullptr; ga.dump_ld = 0; ga.error = d_gram_err.p;
+                            ga.tile_norm = gram_cull ? d_tile_norm.p : nullptr;
+                            ga.cull_gap2 = ga.thr_e * 1.002f;
+                            ga.tiles_done = d_eval.p + 3;
                             const size_t smem = gram_smem_bytes(kc);
                             PR(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                             const unsigned grid = (unsigned)std::min<size_t>((size_t)sm_count(), work.size());
@@ -942,6 +1049,7 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
                         }
                         PR(cudaMemcpyAsync(&hb->n_cand, d_eval.p + 2, 8, cudaMemcpyDeviceToHost, s));
                         PR(cudaMemcpyAsync(&hb->found, d_eval.p + 1, 8, cudaMemcpyDeviceToHost, s));
+                        PR(cudaMemcpyAsync(&hb->tiles_done, d_eval.p + 3, 8, cudaMemcpyDeviceToHost, s));
                         if (use_tc) PR(cudaMemcpyAsync(&hb->gram_err, d_gram_err.p, 4, cudaMemcpyDeviceToHost, s));
                         else hb->gram_err = 0;
                         PR(cudaStreamSynchronize(s));
@@ -961,12 +1069,13 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
                             for (const GramWork& wk : work) tiles_in_pass += wk.n_col_tiles;
                             if ((long long)n_cand <= cand_cap) {
                                 cand_total += n_cand;
-                                screen_slots += 2048.0 * (double)tiles_in_pass;
+                                screen_slots += 2048.0 * (double)hb->tiles_done;   // tiles actually multiplied
+                                tiles_planned += tiles_in_pass;
                                 ++screen_launches;
                             }
-                            if (trace) fprintf(stderr, "  pass k=%lld active=%lld items=%zu col-tiles=%lld (%.3e pair slots) screen %.3f ms, %llu candidates\n",
-                                    (long long)k, (long long)n_active, work.size(), tiles_in_pass, 2048.0 * (double)tiles_in_pass, ms,
-                                    n_cand);
+                            if (trace) fprintf(stderr, "  pass k=%lld active=%lld items=%zu col-tiles=%lld, %llu multiplied (%.3e pair slots) screen %.3f ms, %llu candidates\n",
+                                    (long long)k, (long long)n_active, work.size(), tiles_in_pass, hb->tiles_done,
+                                    2048.0 * (double)hb->tiles_done, ms, n_cand);
                         }
                         if (!dev_gather && (long long)n_cand > cand_cap) {  // list too small (the exact stage did nothing): repeat with the exact size
                             cand_cap = (long long)n_cand;
@@ -1120,8 +1229,8 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
     }
     if (trace)
         fprintf(stderr, "fc_prune: total %.1f ms: upload+centre %.1f, tile lists %.1f, kernels+readback %.1f (tensor-core screen %.1f, "
-                "%llu candidates), resolve %.1f\n",
-                now() - t_begin, t_upload, t_tiles, t_kernels, t_gram, cand_total, t_resolve);
+                "%.0f of %lld planned tiles multiplied, %llu candidates), resolve %.1f\n",
+                now() - t_begin, t_upload, t_tiles, t_kernels, t_gram, screen_slots / 2048.0, tiles_planned, cand_total, t_resolve);
     cudaEventDestroy(ev_g0);
     cudaEventDestroy(ev_g1);
     g_prune_timing[0] = now() - t_begin;
@@ -1130,6 +1239,8 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
     g_prune_timing[3] = screen_slots;
     g_prune_timing[4] = (double)cand_total;
     g_prune_timing[5] = (double)n_sel;
+    g_prune_tiles[0] = (double)tiles_planned;
+    g_prune_tiles[1] = screen_slots / 2048.0;
     memcpy(mask_out, mask.data(), (size_t)n);
     if (n_ties_out) *n_ties_out = ties_total;
     if (stats_out) {

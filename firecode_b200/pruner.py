@@ -36,6 +36,8 @@ class PruneReport:
     screen_pair_slots: float = 0.0  # 2048 per 128 x 16 tile the screen evaluated
     screen_candidates: int = 0      # pairs handed to the FP64 exact kernel
     n_sel: int = 0                  # atoms per structure that enter the RMSD
+    screen_tiles_planned: int = 0   # 128 x 16 tiles of the passes' work items ...
+    screen_tiles_multiplied: int = 0  # ... and those the screen did not skip by the shape bound (sigma ranges too far apart)
 
 
 last_report: PruneReport | None = None
@@ -124,7 +126,9 @@ def _run(structures, mode, sel, masses, max_rmsd, max_dev, moi_dev, energies, ma
     _lib.check(rc, "fc_prune")
     tm = np.zeros(6, dtype=np.float64)
     lib.fc_prune_timing(_ptr(tm))
-    last_report = PruneReport(wall_ms=float(tm[0]), screen_ms=float(tm[1]), screen_launches=int(tm[2]),
+    tl = np.zeros(2, dtype=np.float64)
+    lib.fc_prune_tiles(_ptr(tl))
+    last_report = PruneReport(screen_tiles_planned=int(tl[0]), screen_tiles_multiplied=int(tl[1]), wall_ms=float(tm[0]), screen_ms=float(tm[1]), screen_launches=int(tm[2]),
                               screen_pair_slots=float(tm[3]), screen_candidates=int(tm[4]), n_sel=int(tm[5]),
                               passes=int(stats[0]), pairs_tiled=int(stats[1]), pairs_solved=int(stats[2]),
                               pairs_skipped=int(stats[3]),

@@ -447,6 +447,11 @@ int fc_prune_plan(const uint8_t* mask, int64_t n, int64_t k, int64_t prev_k, int
  * screen): out6 = {wall ms of the call, CUDA-event ms summed over the screen kernel launches, launches,
  * pair slots the screen evaluated (2048 per 128 x 16 tile), candidates it passed on, atoms per structure}. */
 int fc_prune_timing(double* out6);
+/* Tile statistics of the tensor-core screen of the same call: out2 = {128 x 16 tiles planned, tiles multiplied}; the
+ * difference was skipped by the shape bound  E >= sum_k (sigma_k(P) - sigma_k(Q))^2  (singular values of the centred
+ * coordinates) after the positions of every known-dissimilar segment had been sorted by sigma_1 (FC_PRUNE_CULL=0
+ * disables both). */
+int fc_prune_tiles(double* out2);
 
 /* dst[j] = the j-th row of src with mask != 0 (row_bytes each), copied by several host threads: the
  * `structures[mask]` every pruning entry point returns (consumer: apply_mask, embedder.py:1400-1408).

@@ -188,8 +188,9 @@ def test_prune_screen_flavours_agree(gpu, monkeypatch, n_atoms, expect_tc):
     atoms, structures, _ = synthetic.pruning_ensemble(rng, 3000, n_atoms, 60, jitter=(0.02, 0.45))
     masks = {}
     n_sel = int(np.sum(np.asarray(atoms) != "H"))
-    for name, env in (("tc", {}), ("tf32", {"FC_PRUNE_TF32": "1"}), ("fp32", {"FC_PRUNE_TC": "0"}), ("fp64", {"FC_PRUNE_FP64": "1"})):
-        for k in ("FC_PRUNE_TC", "FC_PRUNE_FP64", "FC_PRUNE_TF32"):
+    for name, env in (("tc", {}), ("tf32", {"FC_PRUNE_TF32": "1"}), ("nocull", {"FC_PRUNE_CULL": "0"}), ("fp32", {"FC_PRUNE_TC": "0"}),
+                      ("fp64", {"FC_PRUNE_FP64": "1"})):
+        for k in ("FC_PRUNE_TC", "FC_PRUNE_FP64", "FC_PRUNE_TF32", "FC_PRUNE_CULL"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -199,11 +200,17 @@ def test_prune_screen_flavours_agree(gpu, monkeypatch, n_atoms, expect_tc):
             assert (rep.screen_launches > 0) == expect_tc
             assert rep.n_sel == n_sel
             forced = _forced(rep)
+            slots_with_culling = rep.screen_pair_slots
         elif name == "tf32":
             assert (rep.screen_launches > 0) == (n_sel <= 88)
+        elif name == "nocull":   # positions in index order, every planned tile multiplied
+            assert (rep.screen_launches > 0) == expect_tc
+            if expect_tc:
+                assert rep.screen_pair_slots >= slots_with_culling
         else:
             assert rep.screen_launches == 0
     assert np.array_equal(masks["tc"], masks["tf32"])
+    assert np.array_equal(masks["tc"], masks["nocull"])
     assert np.array_equal(masks["tc"], masks["fp32"])
     assert np.array_equal(masks["tc"], masks["fp64"])
     assert 1 < masks["tc"].sum() < len(structures)

@@ -107,3 +107,29 @@ def test_tf32_rounding_stays_inside_the_band_and_no_similar_pair_is_ruled_out():
     # and the band costs little: the pairs kept for the FP64 stage are within ~0.2 A of the threshold
     kept = ~ruled_out
     assert np.sqrt(np.maximum(true_msd[kept], 0)).max() < max_rmsd + 0.25
+
+
+def test_tile_culling_bound_von_neumann():
+    """Tile culling of the screen: for centred coordinate matrices P, Q the best superposition leaves
+    E = |P|^2 + |Q|^2 - 2 S >= sum_k (sigma_k(P) - sigma_k(Q))^2 (sigma = singular values, descending), whatever the
+    relative orientation -- also with the proper-rotation constraint (S carries the sign of det on the smallest singular
+    value, which only lowers it) and for planar / linear species."""
+    rng = np.random.default_rng(11)
+    for n_atoms in (3, 5, 20, 72):
+        p = rng.normal(size=(400, n_atoms, 3)) * rng.uniform(0.2, 3.0, size=(400, 1, 3))
+        q = rng.normal(size=(400, n_atoms, 3)) * rng.uniform(0.2, 3.0, size=(400, 1, 3))
+        q[:50] = p[:50] + rng.normal(size=(50, n_atoms, 3)) * 0.05              # near duplicates, rotated below
+        rot, _ = np.linalg.qr(rng.normal(size=(400, 3, 3)))
+        q = np.einsum("nij,nkj->nki", rot, q)                                     # random (im)proper orthogonal maps
+        p[100:120, :, 2] = 0.0                                                    # planar structures
+        p[120:130, :, 1:] = 0.0                                                   # linear structures
+        p -= p.mean(axis=1, keepdims=True)
+        q -= q.mean(axis=1, keepdims=True)
+        h = np.einsum("nka,nkb->nab", p, q)
+        e = (p * p).sum(axis=(1, 2)) + (q * q).sum(axis=(1, 2)) - 2.0 * _signed_sigma_sum(h)
+        sp = np.linalg.svd(p, compute_uv=False)
+        sq = np.linalg.svd(q, compute_uv=False)
+        bound = ((sp - sq) ** 2).sum(axis=1)
+        assert np.all(e >= bound - 1e-9 * (1.0 + bound)), (n_atoms, (bound - e).max())
+        # the one-number version (norms only) is weaker but also a bound
+        assert np.all(bound >= (np.linalg.norm(p, axis=(1, 2)) - np.linalg.norm(q, axis=(1, 2))) ** 2 - 1e-9)
