@@ -156,6 +156,7 @@ SIGNATURES = {
                                 VP, VP, C.c_int64, VP, VP]),
     "fc_prune_timing": (C.c_int, [VP]),
     "fc_prune_tiles": (C.c_int, [VP]),
+    "fc_prune_plan_segments": (C.c_int, [VP, C.c_int64, C.c_int64, C.c_int64, C.c_int32, VP, C.c_int64, c_i64p]),
     "fc_kabsch_host": (C.c_int, [VP, VP, VP]),
     "fc_xyz_format": (C.c_int, [VP, C.c_int32, VP, C.c_int64, C.c_int32, VP, VP, C.c_int64, c_i64p]),
     "fc_take_rows": (C.c_int, [VP, C.c_int64, VP, C.c_int64, VP, C.c_int64]),

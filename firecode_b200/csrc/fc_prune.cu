@@ -726,6 +726,23 @@ extern "C" int fc_prune_plan(const uint8_t* mask, int64_t n, int64_t k, int64_t 
 
 static thread_local double g_prune_timing[6] = {0, 0, 0, 0, 0, 0};
 
+// Host-only test hook: the segment number of every padded position of the same pass (see plan_gram_pass).
+extern "C" int fc_prune_plan_segments(const uint8_t* mask, int64_t n, int64_t k, int64_t prev_k, int32_t chunk_over_active,
+                                      int32_t* seg_out, int64_t seg_cap, int64_t* n_seg) {
+    FC_REQUIRE(mask && n > 0 && k >= 1 && k <= n && prev_k >= 0 && prev_k <= n && n_seg, "fc_prune_plan_segments: bad arguments");
+    std::vector<uint8_t> m(mask, mask + n);
+    std::vector<int> spos, seg;
+    std::vector<GramWork> work;
+    int64_t tiled = 0, skipped = 0;
+    const std::vector<int64_t> bounds = chunk_bounds(m, n, k, chunk_over_active != 0);
+    const std::vector<int64_t> prev = prev_k ? chunk_bounds(m, n, prev_k, chunk_over_active != 0) : std::vector<int64_t>();
+    plan_gram_pass(m, n, bounds, prev, 1, 0, 4, spos, work, tiled, skipped, &seg);
+    *n_seg = (int64_t)seg.size();
+    FC_REQUIRE((int64_t)seg.size() <= seg_cap && seg_out, "fc_prune_plan_segments: buffer too small (%lld positions)", (long long)seg.size());
+    memcpy(seg_out, seg.data(), seg.size() * sizeof(int));
+    return FC_OK;
+}
+
 static thread_local double g_prune_tiles[2] = {0, 0};
 
 extern "C" int fc_prune_tiles(double* out2) {

@@ -443,6 +443,14 @@ int fc_prune_plan(const uint8_t* mask, int64_t n, int64_t k, int64_t prev_k, int
                   int32_t chunk_over_active, int32_t* spos_out, int64_t spos_cap, int64_t* n_spos, int32_t* work_out,
                   int64_t work_cap, int64_t* n_work, int64_t* counts_out);
 
+/* Host-only test hook: segment number of every padded position of the pass fc_prune_plan describes.  A segment is a run
+ * of positions whose structures shared a chunk of the previous pass (the whole chunk when prev_k = 0); no pair inside a
+ * segment is evaluated (first pass: only by position order), so the driver may order its positions freely -- it sorts
+ * them by sigma_1 on the device for the tile culling.  Numbers do not decrease along the positions; padding carries the
+ * number of the segment before it. */
+int fc_prune_plan_segments(const uint8_t* mask, int64_t n, int64_t k, int64_t prev_k, int32_t chunk_over_active,
+                           int32_t* seg_out, int64_t seg_cap, int64_t* n_seg);
+
 /* Timing of the last fc_prune / fc_prune_sharded call on this thread (bench.py's roofline of the tensor-core
  * screen): out6 = {wall ms of the call, CUDA-event ms summed over the screen kernel launches, launches,
  * pair slots the screen evaluated (2048 per 128 x 16 tile), candidates it passed on, atoms per structure}. */

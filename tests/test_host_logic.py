@@ -270,6 +270,73 @@ def test_prune_planner_covers_every_unknown_pair_once(n, k, prev_k, world, over_
         assert len(set(covered.values())) >= 2          # the items are dealt to the ranks
 
 
+@pytest.mark.parametrize("over_active", [False, True])
+@pytest.mark.parametrize("n,k,prev_k", [(700, 1, 0), (700, 1, 2), (3000, 5, 10), (3000, 2, 5), (2500, 10, 20), (333, 3, 0)])
+def test_prune_segments_may_be_reordered(n, k, prev_k, over_active):
+    """The tile culling of the tensor-core screen sorts the positions of every SEGMENT by shape on the device.  That is
+    only legal if (1) a segment is a contiguous run of positions of one chunk whose structures shared a chunk of the
+    previous pass, (2) sorting by (segment, anything) leaves the padding where it is, and (3) the work items still cover
+    every unknown pair exactly once after an arbitrary permutation inside the segments."""
+    import ctypes as C
+
+    from firecode_b200 import _lib
+
+    rng = np.random.default_rng(7 * n + k)
+    mask = rng.random(n) < 0.6
+    spos, work, counts = _plan(mask, k, prev_k, over_active=over_active)
+    lib = _lib.load(require_device=False)
+    seg = np.zeros(len(spos) + 64, dtype=np.int32)
+    n_seg = C.c_int64(0)
+    m8 = np.ascontiguousarray(mask, dtype=np.uint8)
+    assert lib.fc_prune_plan_segments(m8.ctypes.data, n, k, prev_k, 1 if over_active else 0, seg.ctypes.data, len(seg),
+                                      C.byref(n_seg)) == 0, lib.fc_last_error()
+    assert n_seg.value == len(spos)
+    seg = seg[: len(spos)]
+    assert np.all(np.diff(seg) >= 0)                                   # (2) a stable sort by segment keeps the runs in place ...
+    real = spos >= 0
+    for sid in np.unique(seg):
+        run = np.flatnonzero(seg == sid)
+        assert np.array_equal(run, np.arange(run[0], run[-1] + 1))     # (1) contiguous
+        r = real[run]
+        assert not np.any(r[np.argmin(r):]) or r.all()                 # ... and padding sits behind the structures of its run
+
+    def membership(kk):
+        if not over_active:
+            return np.minimum(np.arange(n) // (n // kk), kk - 1)
+        act_idx = np.flatnonzero(mask)
+        sz = max(1, len(act_idx) // kk)
+        starts = np.array([0] + [act_idx[c * sz] if c * sz < len(act_idx) else n for c in range(1, kk)])
+        return np.searchsorted(starts, np.arange(n), side="right") - 1
+
+    chunk_of = membership(k)
+    prev_of = membership(prev_k) if prev_k else None
+    for sid in np.unique(seg[real]):
+        members = spos[(seg == sid) & real]
+        assert len(set(chunk_of[members])) == 1
+        if prev_of is not None:
+            assert len(set(prev_of[members])) == 1                     # (1) one chunk of the previous pass
+    # (3) shuffle the structures inside every segment and count the pairs the work items visit
+    shuffled = spos.copy()
+    for sid in np.unique(seg[real]):
+        at = np.flatnonzero((seg == sid) & real)
+        shuffled[at] = rng.permutation(spos[at])
+    covered = set()
+    for row0, ct0, nt, pend in work:
+        for r in range(row0, min(row0 + 128, pend)):
+            for c in range(max(16 * ct0, r + 1), min(16 * (ct0 + nt), pend)):
+                a_, b_ = int(shuffled[r]), int(shuffled[c])
+                key = (min(a_, b_), max(a_, b_))
+                assert a_ >= 0 and b_ >= 0 and chunk_of[a_] == chunk_of[b_] and key not in covered
+                covered.add(key)
+    act = np.flatnonzero(mask)
+    for c in range(k):
+        mem = act[chunk_of[act] == c]
+        for a_i in range(len(mem)):
+            for b_i in range(a_i + 1, len(mem)):
+                if (int(mem[a_i]), int(mem[b_i])) not in covered:
+                    assert prev_of is not None and prev_of[mem[a_i]] == prev_of[mem[b_i]]
+
+
 def test_prune_sharded_replicates_small_ensembles(monkeypatch):
     """dist.prune_sharded shards the pair work only above PRUNE_SHARD_MIN_PAIRS pairs (or when forced); below,
     every rank prunes the whole ensemble with the single-GPU call (same result, no collectives)."""
