@@ -38,11 +38,11 @@ namespace fc {
 // ---------------------------------------------------------------------------------------------
 // heavy-atom coordinates centred on their mean: out (n, nh, 3); g[i] = sum |x|^2
 // outf: the same coordinates as float4 {x, y, z, 0} for the FP32 screen
-// sig (optional): the three singular values of the centred coordinate matrix, descending (square roots of the
-// eigenvalues of its 3x3 Gram matrix), the rotation-invariant shape numbers the screen culls tiles with
+// mom (optional): the six second moments xx, xy, xz, yy, yz, zz of the centred coordinates (prune_sigma_kernel turns
+// them into the shape numbers the screen culls tiles with)
 __global__ void prune_center_kernel(const double* __restrict__ coords, int n_atoms, const int* __restrict__ sel,
                                     int nh, long long n, double* __restrict__ out, double* __restrict__ g,
-                                    float4* __restrict__ outf, float4* __restrict__ sig) {
+                                    float4* __restrict__ outf, double* __restrict__ mom) {
     long long s = blockIdx.x;
     if (s >= n) return;
     const double* src = coords + (size_t)s * n_atoms * 3;
@@ -78,7 +78,7 @@ __global__ void prune_center_kernel(const double* __restrict__ coords, int n_ato
     for (int o = 16; o > 0; o >>= 1) gg += __shfl_xor_sync(0xffffffffu, gg, o);
     if ((threadIdx.x & 31) == 0) sm[0][threadIdx.x >> 5] = gg;
     __shared__ double sm2[6][32];
-    if (sig) {
+    if (mom) {
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
             double v = m2[c];
@@ -91,19 +91,28 @@ __global__ void prune_center_kernel(const double* __restrict__ coords, int n_ato
         double v = 0;
         for (int w = 0; w < (blockDim.x + 31) / 32; ++w) v += sm[0][w];
         g[s] = v;
-        if (sig) {
-            double t[6] = {0, 0, 0, 0, 0, 0};
-            for (int c = 0; c < 6; ++c)
-                for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t[c] += sm2[c][w];
-            const double a9[9] = {t[0], t[1], t[2], t[1], t[3], t[4], t[2], t[4], t[5]};
-            double w3[3], v9[9];
-            jacobi_eig3(a9, w3, v9);
-            if (w3[0] < w3[1]) { double q = w3[0]; w3[0] = w3[1]; w3[1] = q; }
-            if (w3[1] < w3[2]) { double q = w3[1]; w3[1] = w3[2]; w3[2] = q; }
-            if (w3[0] < w3[1]) { double q = w3[0]; w3[0] = w3[1]; w3[1] = q; }
-            sig[s] = make_float4((float)sqrt(fmax(w3[0], 0.0)), (float)sqrt(fmax(w3[1], 0.0)), (float)sqrt(fmax(w3[2], 0.0)), 0.f);
-        }
+        if (mom)
+            for (int c = 0; c < 6; ++c) {
+                double t = 0;
+                for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += sm2[c][w];
+                mom[6 * s + c] = t;
+            }
     }
+}
+
+// sig[s] = the three singular values of the centred coordinate matrix of structure s, descending (square roots of the
+// eigenvalues of its 3x3 Gram matrix): the rotation-invariant shape numbers of the tile culling.  One thread per structure.
+__global__ void prune_sigma_kernel(const double* __restrict__ mom, long long n, float4* __restrict__ sig) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const double* t = mom + 6 * s;
+    const double a9[9] = {t[0], t[1], t[2], t[1], t[3], t[4], t[2], t[4], t[5]};
+    double w3[3], v9[9];
+    jacobi_eig3(a9, w3, v9);
+    if (w3[0] < w3[1]) { double q = w3[0]; w3[0] = w3[1]; w3[1] = q; }
+    if (w3[1] < w3[2]) { double q = w3[1]; w3[1] = w3[2]; w3[2] = q; }
+    if (w3[0] < w3[1]) { double q = w3[0]; w3[0] = w3[1]; w3[1] = q; }
+    sig[s] = make_float4((float)sqrt(fmax(w3[0], 0.0)), (float)sqrt(fmax(w3[1], 0.0)), (float)sqrt(fmax(w3[2], 0.0)), 0.f);
 }
 
 // principal moments of inertia (ascending) about the centre of mass: moi (n, 3)
@@ -870,8 +879,13 @@ static int prune_impl(const double* structures, int64_t n, int32_t n_atoms, int3
             PR(d_g.alloc((size_t)n, s));
             PR(d_sig.alloc((size_t)n, s));
             if (e == cudaSuccess) {
-                prune_center_kernel<<<(unsigned)n, 64, 0, s>>>(d_coords.p, n_sel, nullptr, n_sel, n, d_xc.p, d_g.p, d_xcf.p, d_sig.p);
-                e = cudaGetLastError();
+                DevBuf<double> d_mom;
+                e = d_mom.alloc((size_t)n * 6, s);
+                if (e == cudaSuccess) {
+                    prune_center_kernel<<<(unsigned)n, 64, 0, s>>>(d_coords.p, n_sel, nullptr, n_sel, n, d_xc.p, d_g.p, d_xcf.p, d_mom.p);
+                    prune_sigma_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_mom.p, n, d_sig.p);
+                    e = cudaGetLastError();
+                }
             }
         } else {
             PR(d_mass.alloc(n_atoms, s));
