@@ -251,18 +251,22 @@ def device_all_gather(group=None):
     return gather
 
 
-# Below this many pairs a pruning call is cheaper replicated on every rank than sharded: with the tensor-core
-# screen the GPU part of BASELINE config C4 (2e10 pairs, 5e9 evaluated) is 35 ms of an 85 ms call, the rest is
-# host work every rank repeats anyway, and each pass of the sharded driver adds two collectives
-# (measured on 8 B200: 0.164 s sharded against 0.085 s on one GPU).
-PRUNE_SHARD_MIN_PAIRS = 1e11
+# Below this many pairs a pruning call is replicated on every rank instead of sharded.  Measured on 8 B200 at BASELINE
+# config C4 (2e10 pairs, 5e9 decided by the screen): device-resident sharding returns the mask in 24 ms against 36 ms
+# on one GPU (round 1, host-staged: 0.164 s against 0.085 s), so the break-even lies near that size.
+PRUNE_SHARD_MIN_PAIRS = 1e10
 
 
 def prune_sharded(structures, atoms, kind="rmsd", group=None, force_shard=False, host_staged=False, **kw):
     """prune_by_rmsd / prune_by_moment_of_inertia over all ranks of ``group``: work items of every pass
-    are dealt round-robin to the ranks (structures replicated), the similar pairs each rank finds are
-    all-gathered (8 bytes per pair) and every rank resolves the pass on the union -- the deterministic
-    ordered merge -- so all ranks return the same (structures[mask], mask) as a single-GPU call.
+    are dealt round-robin to the ranks, the similar pairs each rank finds are all-gathered (8 bytes per
+    pair) and every rank resolves the pass on the union -- the deterministic ordered merge -- so all ranks
+    return the same (structures[mask], mask) as a single-GPU call.  By default the exchange steps run on the
+    GPUs (C-ABI fc_prune_sharded_dev through ``device_all_gather``: every rank uploads 1 / world of the
+    structures, pieces / counters / pair lists travel over NCCL); ``host_staged=True`` keeps the structures
+    replicated and stages the lists through the host.  ``want_structures=False`` (forwarded to the pruning
+    call) returns (None, mask): on a multi-GPU box every rank would otherwise write its own copy of the kept
+    structures through the one host memory the ranks share.
     Ensembles with fewer than PRUNE_SHARD_MIN_PAIRS pairs are pruned redundantly on every rank instead
     (same result, no collectives) unless ``force_shard``."""
     from . import pruner

@@ -61,7 +61,7 @@ def main():
             "kept": int(mask.sum()), "pairs_evaluated": n_pairs, "seconds": dt, "rmsd_pairs_per_s": float(n_pairs / dt),
             "passes": rep_.passes, "mask_checksum": int(np.flatnonzero(mask).sum()),
             "note": "work items dealt to the ranks, similar-pair lists all-gathered every pass" if force else
-                    "dist.prune_sharded default: fewer than PRUNE_SHARD_MIN_PAIRS pairs -> every rank prunes the whole "
+                    "dist.prune_sharded default (PRUNE_SHARD_MIN_PAIRS decides between sharding and pruning the whole "
                     "ensemble (no collectives)"}
     dist.barrier()
     if rank == 0:
