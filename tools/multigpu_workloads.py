@@ -62,7 +62,7 @@ def main():
             "passes": rep_.passes, "mask_checksum": int(np.flatnonzero(mask).sum()),
             "note": "work items dealt to the ranks, similar-pair lists all-gathered every pass" if force else
                     "dist.prune_sharded default (PRUNE_SHARD_MIN_PAIRS decides between sharding and pruning the whole "
-                    "ensemble (no collectives)"}
+                    "ensemble on every rank)"}
     dist.barrier()
     if rank == 0:
         print(json.dumps(out), flush=True)
