@@ -190,3 +190,43 @@ def orbital_centers(kind, coords, atoms, graph, index, orb_dim=None, reactive_in
                          "centre array would be ragged")
 
     raise NotImplementedError(f"orbital_centers: the '{kind}' centres stay with the host application (see module docstring)")
+
+
+def pairing_orb_dims(embedder, mol_index):
+    """{reactive atom index: orb_dim} imposed on molecule ``mol_index`` by the embedder's pairing distances
+    (``DIST(a=2.5)`` -> half the distance on both partners, embedder.py:856-883)."""
+    dims = {}
+    for letter, dist in getattr(embedder, "pairing_dists", {}).items():
+        r_index = embedder.pairings_dict[mol_index].get(letter)
+        if r_index is None or isinstance(r_index, tuple):
+            continue   # (tuples are internal constraints: no orbital spacing)
+        for r_i in ([r_index] if isinstance(r_index, (int, np.integer)) else r_index):
+            dims[int(r_i)] = dist / 2
+    return dims
+
+
+def compute_orbitals_batch(mol, write_back=False, orb_dims=None):
+    """What ``Hypermolecule.compute_orbitals`` leaves in ``reactive_atom.center`` (hypermolecule_class.py:166-183), for all
+    conformers at once: {reactive atom index: centres (n_conf, K, 3)}.  ``mol`` is the host application's molecule object
+    after ``_inspect_reactive_atoms`` (it supplies ``coords``, ``atoms``, ``graph``, ``reactive_indices``,
+    ``reactive_atoms_classes_dict`` for the class of every reactive atom, ``sp3_sigmastar`` and ``sigmatropic``).
+    ``orb_dims`` = {atom index: orb_dim} overrides the parameter table (``pairing_orb_dims`` builds it from an embedder).
+    ``write_back=True`` stores the rows into the per-conformer reactive-atom objects, as the reference's loop does."""
+    coords = np.asarray(mol.coords, dtype=np.float64)
+    orb_dims = orb_dims or {}
+    out = {}
+    for index, atom in mol.reactive_atoms_classes_dict[0].items():
+        kind = repr(atom)
+        symbol = str(mol.atoms[int(index)])
+        base = kind.split(" (")[0]
+        dim = orb_dims[int(index)] if int(index) in orb_dims else default_orb_dim(symbol, base)
+        centers, _ = orbital_centers(kind, coords, mol.atoms, mol.graph, int(index),
+                                     orb_dim=BOND_LENGTH if dim is None else dim,
+                                     reactive_indices=[int(r) for r in mol.reactive_indices],
+                                     sp3_sigmastar=bool(getattr(mol, "sp3_sigmastar", False)),
+                                     sigmatropic=getattr(mol, "sigmatropic", None))
+        out[int(index)] = centers
+        if write_back:
+            for c in range(len(coords)):
+                mol.reactive_atoms_classes_dict[c][index].center = centers[c].copy()
+    return out

@@ -62,3 +62,36 @@ def test_unsupported_kind_is_an_error_not_a_guess():
     g = _graph(3, [(0, 1), (0, 2)])
     with pytest.raises(NotImplementedError):
         orbitals.orbital_centers("sp", np.zeros((1, 3, 3)), ["C", "C", "C"], g, 0, orb_dim=1.0)
+
+
+@pytest.mark.reference
+def test_compute_orbitals_batch_equals_reference_on_its_fixtures():
+    """The whole-molecule form against the UNMODIFIED Hypermolecule.compute_orbitals on the reference's own fixtures
+    (every reactive atom of every molecule: sp3 / single-bond sigma-star pair, sp2, Ether, Ketone)."""
+    from oracle import loader
+
+    if not loader.reference_available():
+        pytest.skip("reference tree not present")
+    seen = set()
+    for name in ("embed_string", "embed_cyclical", "embed_chelotropic", "embed_trimolecular"):
+        with loader.embedder_from_dir(loader.fixture_dir(name), name + ".txt") as emb:
+            for m, mol in enumerate(emb.objects):
+                # orb_dim is the embedder's policy (parameter table, DIST pairings, per-embed adjustments such as
+                # embedder.py:1079-1080, hypermolecule_class.py:239-240): it is read off the reference's centres wherever
+                # the lobes sit at that distance from the atom; what is compared is the geometry of the lobes
+                dims = orbitals.pairing_orb_dims(emb, m)
+                for index, atom in mol.reactive_atoms_classes_dict[0].items():
+                    length = float(np.linalg.norm(np.asarray(atom.center[0]) - mol.coords[0][int(index)]))
+                    if repr(atom) == "Single Bond" and mol.sp3_sigmastar:
+                        # (these lobes are not unit vectors times orb_dim: scale against the unit-orb_dim construction)
+                        unit = orbitals.compute_orbitals_batch(mol, orb_dims={int(index): 1.0})[int(index)]
+                        length /= float(np.linalg.norm(unit[0, 0] - mol.coords[0][int(index)]))
+                    dims[int(index)] = length
+                got = orbitals.compute_orbitals_batch(mol, orb_dims=dims)
+                for index, atom in mol.reactive_atoms_classes_dict[0].items():
+                    ref = np.array([np.asarray(mol.reactive_atoms_classes_dict[c][index].center, dtype=float)
+                                    for c in range(len(mol.coords))])
+                    assert got[int(index)].shape == ref.shape, (name, index, repr(atom))
+                    assert np.abs(got[int(index)] - ref).max() < 1e-12, (name, index, repr(atom))
+                    seen.add(repr(atom).split(" (")[0])
+    assert {"sp3", "Single Bond", "sp2", "Ether", "Ketone"} <= seen
